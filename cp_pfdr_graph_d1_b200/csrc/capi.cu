@@ -1,0 +1,99 @@
+// capi.cu - the extern "C" surface declared in include/pfdr_b200.h.
+#include "solvers.cuh"
+#include <chrono>
+
+namespace pfdr {
+
+Context &ctx()
+{
+    static thread_local Context c;
+    return c;
+}
+
+static thread_local std::string g_err;
+
+// library-owned launch stream: graph capture is not allowed on the legacy default stream
+static cudaStream_t own_stream()
+{
+    static thread_local cudaStream_t s = nullptr;
+    if (!s) PFDR_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    return s;
+}
+
+static thread_local bool g_user_stream = false;
+static thread_local pfdr_b200_stats g_last_stats{};
+
+template <typename F>
+static int guarded(F &&f)
+{
+    try {
+        Context &c = ctx();
+        int ndev = 0;
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess || ndev == 0)
+            throw Error(PFDR_B200_ERR_CUDA, std::string("no usable CUDA device (libpfdr_b200 has no CPU fallback): ") +
+                                                cudaGetErrorString(e));
+        if (c.device >= 0) PFDR_CUDA(cudaSetDevice(c.device));
+        if (!g_user_stream) c.stream = own_stream();
+        c.stats = pfdr_b200_stats{};
+        c.in_loop = false;
+        const auto t0 = std::chrono::steady_clock::now();
+        f();
+        c.stats.total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        g_last_stats = c.stats;
+        return PFDR_B200_OK;
+    } catch (const Error &e) {
+        g_err = e.what();
+        cudaGetLastError();
+        return e.status;
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return PFDR_B200_ERR_CUDA;
+    }
+}
+
+}  // namespace pfdr
+
+using namespace pfdr;
+
+extern "C" {
+
+const char *pfdr_b200_last_error(void) { return g_err.c_str(); }
+int pfdr_b200_version(void) { return 100; }
+int pfdr_b200_set_device(int device) { ctx().device = device; return PFDR_B200_OK; }
+int pfdr_b200_set_stream(void *s)
+{
+    ctx().stream = (cudaStream_t) s;
+    g_user_stream = (s != nullptr);
+    return PFDR_B200_OK;
+}
+int pfdr_b200_get_last_stats(pfdr_b200_stats *out) { if (!out) return PFDR_B200_ERR_ARG; *out = g_last_stats; return PFDR_B200_OK; }
+
+#define QUAD_L1(SUF, real)                                                                              \
+int pfdr_b200_quadratic_d1_l1_##SUF(int V, int E, int N, real *X, const real *Y, const real *A,         \
+    const int *Eu, const int *Ev, const real *La_d1, const real *La_l1, int positivity, int Ltype,      \
+    const real *L, real rho, real condMin, real difRcd, real difTol, int itMax, int *it, real *Obj,     \
+    real *Dif, int verbose)                                                                             \
+{                                                                                                       \
+    return guarded([&] {                                                                                \
+        QuadProblem<real> q{V, E, N, X, Y, A, Eu, Ev, La_d1, La_l1, positivity, 0, 0, 0, Ltype, L, rho, \
+                            condMin, difRcd, difTol, itMax, it, Obj, Dif, verbose};                     \
+        solve_quadratic<real>(q);                                                                       \
+    });                                                                                                 \
+}                                                                                                       \
+int pfdr_b200_quadratic_d1_bounds_##SUF(int V, int E, int N, real *X, const real *Y, const real *A,     \
+    const int *Eu, const int *Ev, const real *La_d1, real lo, real hi, int Ltype, const real *L,        \
+    real rho, real condMin, real difRcd, real difTol, int itMax, int *it, real *Obj, real *Dif,         \
+    int verbose)                                                                                        \
+{                                                                                                       \
+    return guarded([&] {                                                                                \
+        QuadProblem<real> q{V, E, N, X, Y, A, Eu, Ev, La_d1, nullptr, 0, 1, lo, hi, Ltype, L, rho,      \
+                            condMin, difRcd, difTol, itMax, it, Obj, Dif, verbose};                     \
+        solve_quadratic<real>(q);                                                                       \
+    });                                                                                                 \
+}
+
+QUAD_L1(f32, float)
+QUAD_L1(f64, double)
+
+}  // extern "C"

@@ -1,0 +1,195 @@
+// common.cuh - shared plumbing of libpfdr_b200: error handling, device buffers, launch
+// accounting, the device-side control block of a PFDR solve and deterministic reductions.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include <cfloat>
+#include <cmath>
+#include "../../include/pfdr_b200.h"
+
+namespace pfdr {
+
+// ---------------------------------------------------------------------------------------------
+// errors: internal code throws, the C ABI catches and turns into status + message
+// ---------------------------------------------------------------------------------------------
+struct Error : std::runtime_error {
+    int status;
+    Error(int s, const std::string &m) : std::runtime_error(m), status(s) {}
+};
+
+#define PFDR_CUDA(call)                                                                        \
+    do {                                                                                       \
+        cudaError_t err__ = (call);                                                            \
+        if (err__ != cudaSuccess)                                                              \
+            throw ::pfdr::Error(PFDR_B200_ERR_CUDA, std::string(#call) + " failed: " +         \
+                                cudaGetErrorString(err__) + " (" __FILE__ ":" +                \
+                                std::to_string(__LINE__) + ")");                               \
+    } while (0)
+
+#define PFDR_REQUIRE(cond, msg)                                                                \
+    do { if (!(cond)) throw ::pfdr::Error(PFDR_B200_ERR_ARG, std::string(msg)); } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// per-thread run-time context: device, stream, statistics of the call in flight
+// ---------------------------------------------------------------------------------------------
+struct Context {
+    int device = -1;               // -1: keep the caller's current device
+    cudaStream_t stream = 0;
+    pfdr_b200_stats stats{};
+    bool in_loop = false;
+    void count_launch() { stats.launches++; if (in_loop) stats.loop_launches++; }
+};
+Context &ctx();
+
+#define PFDR_LAUNCH(kernel, grid, block, smem, ...)                                            \
+    do {                                                                                       \
+        kernel<<<(grid), (block), (smem), ::pfdr::ctx().stream>>>(__VA_ARGS__);                \
+        ::pfdr::ctx().count_launch();                                                          \
+        PFDR_CUDA(cudaGetLastError());                                                         \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// device memory
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    DevBuf() {}
+    explicit DevBuf(size_t count) { alloc(count); }
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    DevBuf &operator=(DevBuf &&o) noexcept { if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; } return *this; }
+    ~DevBuf() { release(); }
+    void alloc(size_t count) {
+        release();
+        n = count;
+        if (count) PFDR_CUDA(cudaMalloc((void **) &p, count * sizeof(T)));
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void zero() { if (p) PFDR_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), ctx().stream)); }
+    operator T *() const { return p; }
+};
+
+inline bool is_device_ptr(const void *q)
+{
+    if (!q) return false;
+    cudaPointerAttributes at;
+    cudaError_t e = cudaPointerGetAttributes(&at, q);
+    if (e != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+// A read-only input array that lives on the device for the duration of a call: either the
+// caller's own device pointer (used in place) or an uploaded copy of the caller's host array.
+template <typename T>
+struct DevIn {
+    const T *p = nullptr;
+    DevBuf<T> own;
+    void bind(const T *src, size_t count) {
+        if (!src || !count) { p = nullptr; return; }
+        if (is_device_ptr(src)) { p = src; return; }
+        own.alloc(count);
+        PFDR_CUDA(cudaMemcpyAsync(own.p, src, count * sizeof(T), cudaMemcpyHostToDevice, ctx().stream));
+        ctx().stats.h2d_bytes += (long long) (count * sizeof(T));
+        p = own.p;
+    }
+    operator const T *() const { return p; }
+};
+
+template <typename T>
+inline void copy_out(T *dst, const T *dev_src, size_t count)
+{
+    if (!dst || !count) return;
+    if (is_device_ptr(dst)) {
+        PFDR_CUDA(cudaMemcpyAsync(dst, dev_src, count * sizeof(T), cudaMemcpyDeviceToDevice, ctx().stream));
+    } else {
+        PFDR_CUDA(cudaMemcpyAsync(dst, dev_src, count * sizeof(T), cudaMemcpyDeviceToHost, ctx().stream));
+        ctx().stats.d2h_bytes += (long long) (count * sizeof(T));
+    }
+}
+
+inline int num_sms()
+{
+    static int sms = 0;
+    if (!sms) {
+        int dev; PFDR_CUDA(cudaGetDevice(&dev));
+        PFDR_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    return sms;
+}
+
+inline unsigned cdiv(size_t a, size_t b) { return (unsigned) ((a + b - 1) / b); }
+
+// ---------------------------------------------------------------------------------------------
+// control block of one solve, resident in device memory.  Every kernel of an iteration reads it,
+// so the host can enqueue whole batches of iterations without synchronising: once the stopping
+// (or reconditioning) test fires on the device, the remaining launches of the batch are no-ops.
+// ---------------------------------------------------------------------------------------------
+enum : int { ST_RUN = 0, ST_FINAL = 1, ST_RECOND = 2 };
+
+struct Ctl {
+    int it;            // completed iterations == index of the trip in flight; parity selects buffers
+    int state;         // ST_RUN | ST_FINAL (stop test fired: this trip only applies A / objective)
+                       //        | ST_RECOND (this trip applies A / objective, then the host reconditions)
+    int hold;          // set by the first iteration kernel that sees state != ST_RUN: freezes everything
+    int itMax;
+    int track;         // evolution is monitored (difTol > 0 || difRcd > 0 || Dif != NULL)
+    unsigned ticket;   // last-block-done counter
+    int pad0, pad1;
+    double dif;        // current evolution measure (as the reference's `dif`)
+    double tol;        // stop threshold in the units of dif  (quadratic: difTol^2, simplex: difTol)
+    double rcd;        // reconditioning threshold, same units
+    double eps;        // floor of the denominator (quadratic family)
+    double amp;        // preconditioner: mean-amplitude constant `c` of the reference
+    double scratch[4];
+};
+
+__device__ __forceinline__ int ld_flag(const int *p) { return *((const volatile int *) p); }
+
+// ---------------------------------------------------------------------------------------------
+// deterministic block reduction (fixed shuffle tree + fixed order over warps)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// all threads of the block must call; result valid in thread 0 (and broadcast to all)
+template <int NV>
+__device__ __forceinline__ void block_sum(double (&v)[NV], double *smem /* >= NV*32 doubles */)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; i++) v[i] = warp_sum(v[i]);
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; i++) smem[i * 32 + wid] = v[i];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+        double t = (lane < nw) ? smem[i * 32 + lane] : 0.0;
+        v[i] = warp_sum(t);
+    }
+}
+
+template <typename real> struct Pair;
+template <> struct Pair<float> { typedef float2 type; };
+template <> struct Pair<double> { typedef double2 type; };
+
+template <typename real> __host__ __device__ inline real real_eps();
+template <> __host__ __device__ inline float real_eps<float>() { return FLT_EPSILON; }
+template <> __host__ __device__ inline double real_eps<double>() { return DBL_EPSILON; }
+
+}  // namespace pfdr

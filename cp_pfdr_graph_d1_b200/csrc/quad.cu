@@ -1,0 +1,788 @@
+// quad.cu - PFDR for  1/2||y-Ax||^2 + sum_e La_d1|x_u-x_v| + { sum_v La_l1|x_v| (+ x>=0) | box },
+// the B200-native replacement of src/PFDR_graph_quadratic_d1_l1.cpp and
+// src/PFDR_graph_quadratic_d1_bounds.cpp of the reference (same iteration, different schedule).
+//
+// Schedule of one iteration ("trip") on the device:
+//   [N>0]  ax_partial -> ax_finish          R = Y - A X            (ref S1  :356-367)
+//          atr                              P = 2X - Ga.(-A^t R)   (ref S4+S6 :432-440,:463-464)
+//   [N<0]  ata_gemv                         P = 2X - Ga.(AtA X - AtY)          (ref :368-376,:441-445)
+//   [Obj]  objective                                              (ref S2  :388-422)
+//   iter   ONE fused kernel, one thread per vertex walking that vertex's half-edge row:
+//          d1 prox of every incident edge + relaxation (S7 :467-489), new edge copy written for
+//          the thread's own half only (the other half is recomputed by the neighbour's thread, the
+//          old copies come from the ping buffer), weighted average in the reference's summation
+//          order (S8 :492-497), vertex prox (S9 :500-512 / bounds :473-490), next forward point
+//          when A is diagonal (S1+S4+S6 of the next trip) and the evolution sums (S10 :515-529).
+// Per-edge constants of the reference (Wu, Wv, W_d1u, W_d1v, Th_d1: five E-arrays) are not stored:
+// with S[v] = sum of raw weights at v and T[v] = Ga[v].S[v] they are  Wu = w/S[u],
+// W_d1u = T[v]/(T[u]+T[v]), W_d1v = T[u]/(T[u]+T[v]), Th_d1 = (La_d1/w).(T[u]+T[v])   (ref :253-261)
+// so only the raw weight w is streamed per half-edge.
+#include "graph.cuh"
+#include "solvers.cuh"
+
+namespace pfdr {
+
+template <typename real> using pair_t = typename Pair<real>::type;
+
+template <typename real>
+struct QP {                       // kernel parameter block
+    Ctl *ctl;
+    int V, N, E;
+    const long long *slice_off; const int *nbr, *twin, *hkey;
+    real *w;                      // [slots] raw d1 weight of the half-edge's edge
+    real *thc;                    // [slots] La_d1/w after a reconditioning (NULL: thc0 for all)
+    real thc0;
+    real *Z0, *Z1;                // [slots] edge copies, ping/pong by iteration parity
+    pair_t<real> *XP0, *XP1;      // [V] (x, forward point 2x - Ga.grad), ping/pong
+    real *Xc;                     // [V] compact copy of the iterate (dense operators only)
+    real *T, *Sinv, *Ga, *Ga0, *G, *Thl1, *R, *AtY;
+    const real *Y, *A, *La_d1, *La_l1, *L;
+    const int *Eu, *Ev;
+    int Ltype, positivity, prox_kind, has_lo, has_hi;
+    real lo, hi, rho, condMin;
+    double *partial;
+    real *dObj, *dDif;
+    int nparts;                   // CTAs of ax_partial
+};
+
+template <typename real> __device__ __forceinline__ real rabs(real a) { return a < (real) 0 ? -a : a; }
+
+// gradient of the smooth part at vertex v (x = X[v]); dense cases read what the A-kernels left in G
+template <typename real>
+__device__ __forceinline__ real grad_at(const QP<real> &p, int v, real x)
+{
+    if (p.N == 0) return (p.A ? p.A[v] * x : x) - p.Y[v];
+    if (p.N < 0) return p.G[v] - p.Y[v];
+    return p.G[v];
+}
+
+// Sum NV doubles over the whole grid, deterministically: per-CTA partials, the last CTA to finish
+// adds them in a fixed order.  Returns true (in every thread) only in that last CTA, v valid in thread 0.
+template <int NV>
+__device__ bool grid_sum(Ctl *ctl, double *partial, double (&v)[NV], double *smem)
+{
+    __shared__ int s_last;
+    block_sum<NV>(v, smem);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; i++) partial[(size_t) blockIdx.x * NV + i] = v[i];
+        __threadfence();
+        const unsigned t = atomicAdd(&ctl->ticket, 1u);
+        s_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return false;
+    __threadfence();
+    double acc[NV];
+#pragma unroll
+    for (int i = 0; i < NV; i++) acc[i] = 0.0;
+    const volatile double *vp = partial;
+    for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
+#pragma unroll
+        for (int i = 0; i < NV; i++) acc[i] += vp[(size_t) b * NV + i];
+    }
+    block_sum<NV>(acc, smem);
+#pragma unroll
+    for (int i = 0; i < NV; i++) v[i] = acc[i];
+    if (threadIdx.x == 0) ctl->ticket = 0;
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// preconditioning (ref src/PFDR_graph_quadratic_d1_l1.cpp:57-268)
+// ---------------------------------------------------------------------------------------------
+// Ga0 = diag(A^tA) (:102-122) and the amplitude constant c (:125-154).  recond = 0: over the
+// coordinate-wise pseudo-inverse of Y; recond = 1: over the current iterate.
+template <typename real>
+__global__ void __launch_bounds__(256) amp_kernel(QP<real> p, int recond)
+{
+    __shared__ double smem[64];
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    double r[2] = {0.0, 0.0};
+    if (v < p.V) {
+        real a;
+        if (recond) {
+            const pair_t<real> *XP = (ld_flag(&p.ctl->it) & 1) ? p.XP1 : p.XP0;
+            a = XP[v].x;
+        } else {
+            real g0;
+            if (p.N > 0) { g0 = p.Ga0[v]; a = p.AtY[v] / g0; }           // colstats filled Ga0, AtY
+            else {
+                g0 = (p.N < 0) ? p.A[((size_t) p.V + 1) * (size_t) v] : (p.A ? p.A[v] : (real) 1);
+                p.Ga0[v] = g0;
+                a = (g0 > (real) 0) ? p.Y[v] / g0 : (real) 0;
+            }
+        }
+        if (a > (real) 0) { r[0] = (double) a; r[1] = 1.0; }          // ref :149-153
+        else if (a < (real) 0) { r[0] = -(double) a; r[1] = 1.0; }
+    }
+    if (grid_sum<2>(p.ctl, p.partial, r, smem) && threadIdx.x == 0)
+        p.ctl->amp = recond ? (double) ((real) r[0] / (real) r[1]) : (double) ((real) r[1] / (real) r[0]);
+}
+
+template <typename real>
+__device__ __forceinline__ real clamp_metric(const QP<real> &p, int v, real ga)
+{   // ref :222-239
+    const real bound = (real) 1.9 * ((real) 2 - p.rho);
+    if (p.Ltype == PFDR_B200_SCAL || p.L == nullptr) {
+        const real b = p.L ? bound / p.L[0] : bound;
+        if (ga > b) ga = b;
+    } else if (p.L[v] > (real) 0) {
+        const real b = bound / p.L[v];
+        if (ga > b) ga = b;
+    }
+    return ga;
+}
+
+// first preconditioning + initial state: w = c La_d1 (:160-166), S, Ga, T, Th_l1, z_e = x (:321-324)
+template <typename real>
+__global__ void __launch_bounds__(256) init_vertex_kernel(QP<real> p, const real *__restrict__ X0)
+{
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= p.V) return;
+    const real c = (real) p.ctl->amp;
+    const real x = X0[v];
+    const int lane = v & 31;
+    const long long base = p.slice_off[v >> 5];
+    const int width = (int) ((p.slice_off[(v >> 5) + 1] - base) >> 5);
+    real S = 0;
+    for (int j = 0; j < width; j++) {
+        const long long s = base + (long long) j * 32 + lane;
+        const int h = p.hkey[s];
+        if (h >= 0) {
+            const real wv = c * p.La_d1[h >> 1];
+            p.w[s] = wv; S += wv; p.Z0[s] = x;
+        }
+    }
+    real ga = p.Ga0[v] + S;
+    if (p.La_l1) ga += c * p.La_l1[v];
+    ga = clamp_metric(p, v, (real) 1 / ga);
+    p.Ga[v] = ga; p.Sinv[v] = (real) 1 / S; p.T[v] = ga * S;
+    if (p.La_l1) p.Thl1[v] = ga * p.La_l1[v];
+    pair_t<real> xp; xp.x = x;
+    xp.y = (p.N == 0) ? (real) 2 * x - ga * grad_at(p, v, x) : (real) 0;
+    p.XP0[v] = xp;
+    if (p.Xc) p.Xc[v] = x;
+}
+
+// reconditioning, everything that is local to a vertex row in one kernel (ref :89-99, :167-250):
+// subgradients from the old metric, new raw weights, new metric, new edge copies, new forward point.
+template <typename real>
+__global__ void __launch_bounds__(256) recond_vertex_kernel(QP<real> p)
+{
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= p.V) return;
+    const int cur = p.ctl->it & 1;
+    const pair_t<real> *XP = cur ? p.XP1 : p.XP0;
+    real *Z = cur ? p.Z1 : p.Z0;
+    real c = (real) p.ctl->amp;
+    const real x = XP[v].x, g = grad_at(p, v, x);
+    const real ga_old = p.Ga[v], sinv_old = p.Sinv[v];
+    const int lane = v & 31;
+    const long long base = p.slice_off[v >> 5];
+    const int width = (int) ((p.slice_off[(v >> 5) + 1] - base) >> 5);
+    real S = 0;
+    for (int j = 0; j < width; j++) {
+        const long long s = base + (long long) j * 32 + lane;
+        const int n = p.nbr[s];
+        if (n >= 0) {
+            const real Wold = p.w[s] * sinv_old;
+            Z[s] = (Wold / ga_old) * (x - ga_old * g - Z[s]);                 // ref :96-97
+            const real xn = XP[n].x;
+            real a = rabs(x), b = rabs(xn), d = rabs(x - xn);                   // ref :172-186
+            if (a < b) a = b;
+            if (a < c) a = c;
+            a *= p.condMin;
+            if (d < a) d = a;
+            const real wv = p.La_d1[p.hkey[s] >> 1] / d;
+            p.w[s] = wv; p.thc[s] = d; S += wv;
+        }
+    }
+    real ga = p.Ga0[v] + S;
+    if (p.La_l1) {                                                             // ref :209-218
+        c *= p.condMin;
+        real d = rabs(x);
+        if (d < c) d = c;
+        ga += p.La_l1[v] / d;
+    }
+    ga = clamp_metric(p, v, (real) 1 / ga);
+    const real sinv = (real) 1 / S;
+    p.Ga[v] = ga; p.Sinv[v] = sinv; p.T[v] = ga * S;
+    if (p.La_l1) p.Thl1[v] = ga * p.La_l1[v];
+    for (int j = 0; j < width; j++) {
+        const long long s = base + (long long) j * 32 + lane;
+        if (p.nbr[s] >= 0) Z[s] = x - ga * (g + Z[s] / (p.w[s] * sinv));        // ref :247-248
+    }
+    pair_t<real> xp; xp.x = x; xp.y = (real) 2 * x - ga * g;
+    (cur ? p.XP1 : p.XP0)[v] = xp;
+}
+
+template <typename real>
+__global__ void resume_kernel(QP<real> p, double rcd_factor)
+{
+    p.ctl->rcd *= rcd_factor; p.ctl->state = ST_RUN; p.ctl->hold = 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// the fused iteration kernel
+// ---------------------------------------------------------------------------------------------
+template <typename real, bool PER_SLOT_TH>
+__global__ void __launch_bounds__(256) quad_iter_kernel(QP<real> p)
+{
+    __shared__ double smem[64];
+    Ctl *ctl = p.ctl;
+    {
+        const int hold = ld_flag(&ctl->hold), state = ld_flag(&ctl->state);
+        if (hold != 0 || state != ST_RUN) {
+            if (hold == 0 && blockIdx.x == 0 && threadIdx.x == 0) ctl->hold = 1;
+            return;
+        }
+    }
+    const int it = ld_flag(&ctl->it);
+    const int cur = it & 1;
+    const real *__restrict__ Zin = cur ? p.Z1 : p.Z0;
+    real *__restrict__ Zout = cur ? p.Z0 : p.Z1;
+    const pair_t<real> *__restrict__ XPc = cur ? p.XP1 : p.XP0;
+    pair_t<real> *__restrict__ XPn = cur ? p.XP0 : p.XP1;
+    const real rho = p.rho;
+
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    double red[2] = {0.0, 0.0};
+    if (v < p.V) {
+        const int lane = v & 31;
+        const long long base = p.slice_off[v >> 5];
+        const int width = (int) ((p.slice_off[(v >> 5) + 1] - base) >> 5);
+        const pair_t<real> xp = XPc[v];
+        const real Tv = p.T[v], Sv = p.Sinv[v];
+        real acc = 0;
+#pragma unroll 2
+        for (int j = 0; j < width; j++) {
+            const long long s = base + (long long) j * 32 + lane;
+            const int n = p.nbr[s];
+            if (n >= 0) {
+                const int tw = p.twin[s];
+                const real wv = p.w[s], zo = Zin[s];
+                const pair_t<real> xn = XPc[n];
+                const real Tn = p.T[n], zt = Zin[tw];
+                const real tsum = Tv + Tn;
+                const real th = (PER_SLOT_TH ? p.thc[s] : p.thc0) * tsum;       // Th_d1
+                const real inv = (real) 1 / tsum;
+                const real wo = Tn * inv, wt = Tv * inv;                          // W_d1 own / twin side
+                const real po = xp.y - zo, pt = xn.y - zt;
+                const real a = wo * po + wt * pt;
+                real b = po - pt;
+                real zn;
+                if (b > th) { b -= th; zn = zo + rho * (a + wt * b - xp.x); }
+                else if (b < -th) { b += th; zn = zo + rho * (a + wt * b - xp.x); }
+                else zn = zo + rho * (a - xp.x);
+                Zout[s] = zn;
+                acc += (wv * Sv) * zn;
+            }
+        }
+        real x = acc;
+        if (p.prox_kind == 0) {                                                // ref l1.cpp :500-512
+            if (p.La_l1) {
+                const real th = p.Thl1[v];
+                if (x > th) x -= th;
+                else if (!p.positivity && x < -th) x += th;
+                else x = 0;
+            } else if (p.positivity) { if (x < (real) 0) x = 0; }
+        } else {                                                               // ref bounds.cpp :473-490
+            if (p.has_lo && x < p.lo) x = p.lo;
+            else if (p.has_hi && x > p.hi) x = p.hi;
+        }
+        pair_t<real> o; o.x = x;
+        o.y = (p.N == 0) ? (real) 2 * x - p.Ga[v] * grad_at(p, v, x) : (real) 0;
+        XPn[v] = o;
+        if (p.Xc) p.Xc[v] = x;
+        const real dx = xp.x - x;
+        red[0] = (double) (dx * dx); red[1] = (double) (x * x);
+    }
+    if (grid_sum<2>(ctl, p.partial, red, smem) && threadIdx.x == 0) {
+        double dif = ctl->dif;
+        if (ctl->track) {                                                      // ref :515-529
+            dif = (red[1] > ctl->eps) ? red[0] / red[1] : red[0] / ctl->eps;
+            ctl->dif = dif;
+            if (p.dDif) p.dDif[it] = (real) dif;
+        }
+        const int itn = it + 1;
+        ctl->it = itn;
+        if (itn == ctl->itMax || (real) dif < (real) ctl->tol) ctl->state = ST_FINAL;   // ref :429
+        else if ((real) dif < (real) ctl->rcd) ctl->state = ST_RECOND;                  // ref :448
+    }
+}
+
+template <typename real>
+__global__ void extract_x_kernel(QP<real> p, real *__restrict__ out)
+{
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= p.V) return;
+    const pair_t<real> *XP = (p.ctl->it & 1) ? p.XP1 : p.XP0;
+    out[v] = XP[v].x;
+}
+
+// ---------------------------------------------------------------------------------------------
+// objective (ref :388-422).  Runs once per trip when Obj is requested, before the stop test.
+// ---------------------------------------------------------------------------------------------
+template <typename real>
+__global__ void __launch_bounds__(256) objective_kernel(QP<real> p)
+{
+    __shared__ double smem[64];
+    Ctl *ctl = p.ctl;
+    if (ld_flag(&ctl->hold)) return;
+    const int it = ld_flag(&ctl->it);
+    const pair_t<real> *__restrict__ XP = (it & 1) ? p.XP1 : p.XP0;
+    double r[1] = {0.0};
+    const size_t stride = (size_t) gridDim.x * blockDim.x, t0 = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    for (size_t e = t0; e < (size_t) p.E; e += stride)
+        r[0] += (double) p.La_d1[e] * (double) rabs(XP[p.Eu[e]].x - XP[p.Ev[e]].x);
+    for (size_t v = t0; v < (size_t) p.V; v += stride) {
+        const real x = XP[v].x;
+        if (p.N == 0) r[0] += (double) x * ((double) 0.5 * (double) (p.A ? p.A[v] * x : x) - (double) p.Y[v]);
+        else if (p.N < 0) r[0] += (double) x * ((double) 0.5 * (double) p.G[v] - (double) p.Y[v]);
+        if (p.La_l1) r[0] += (double) p.La_l1[v] * (double) rabs(x);
+    }
+    if (p.N > 0)
+        for (size_t n = t0; n < (size_t) p.N; n += stride) r[0] += 0.5 * (double) p.R[n] * (double) p.R[n];
+    if (grid_sum<1>(ctl, p.partial, r, smem) && threadIdx.x == 0) p.dObj[it] = (real) r[0];
+}
+
+// ---------------------------------------------------------------------------------------------
+// dense operators
+// ---------------------------------------------------------------------------------------------
+template <typename real, int VEC> struct VecT;
+template <> struct VecT<float, 4> { typedef float4 type; };
+template <> struct VecT<float, 1> { typedef float type; };
+template <> struct VecT<double, 2> { typedef double2 type; };
+template <> struct VecT<double, 1> { typedef double type; };
+
+template <typename real, int VEC>
+__device__ __forceinline__ void vload(const real *q, real (&o)[VEC])
+{
+    typedef typename VecT<real, VEC>::type vt;
+    const vt t = __ldg(reinterpret_cast<const vt *>(q));
+    const real *tp = reinterpret_cast<const real *>(&t);
+#pragma unroll
+    for (int k = 0; k < VEC; k++) o[k] = tp[k];
+}
+
+// N<0:  G = (A^tA) X column by column (ref :368-376), then P = 2X - Ga.(G - AtY) (:441-445,:463-464).
+// CG columns per CTA pass so every X vector load feeds CG independent A streams.
+template <typename real, int VEC, int CG>
+__global__ void __launch_bounds__(256) ata_gemv_kernel(QP<real> p)
+{
+    __shared__ double smem[CG * 32];
+    if (ld_flag(&p.ctl->hold)) return;
+    pair_t<real> *XP = (ld_flag(&p.ctl->it) & 1) ? p.XP1 : p.XP0;
+    const size_t V = (size_t) p.V;
+    const real *__restrict__ X = p.Xc;
+    for (size_t c0 = (size_t) blockIdx.x * CG; c0 < V; c0 += (size_t) gridDim.x * CG) {
+        double acc[CG];
+        real part[CG];
+        const real *col[CG];
+#pragma unroll
+        for (int c = 0; c < CG; c++) { part[c] = 0; col[c] = p.A + V * (c0 + c < V ? c0 + c : V - 1); }
+        for (size_t u = (size_t) threadIdx.x * VEC; u < V; u += (size_t) blockDim.x * VEC) {
+            real xv[VEC];
+            vload<real, VEC>(X + u, xv);
+            real av[CG][VEC];
+#pragma unroll
+            for (int c = 0; c < CG; c++) vload<real, VEC>(col[c] + u, av[c]);
+#pragma unroll
+            for (int c = 0; c < CG; c++)
+#pragma unroll
+                for (int k = 0; k < VEC; k++) part[c] += av[c][k] * xv[k];
+        }
+#pragma unroll
+        for (int c = 0; c < CG; c++) acc[c] = (double) part[c];
+        block_sum<CG>(acc, smem);
+        if (threadIdx.x < CG && c0 + threadIdx.x < V) {
+            const size_t v = c0 + threadIdx.x;
+            real g = 0;
+#pragma unroll
+            for (int c = 0; c < CG; c++) if (c == (int) threadIdx.x) g = (real) acc[c];
+            p.G[v] = g;
+            const real x = X[v];
+            XP[v].y = (real) 2 * x - p.Ga[v] * (g - p.Y[v]);
+        }
+    }
+}
+
+// N>0, pass 1:  partial sums of A X over the CTA's block of columns (ref :356-367).
+// Lanes run along n (contiguous in the column-major A), TY columns are walked side by side.
+template <typename real, int VEC>
+__global__ void __launch_bounds__(256) ax_partial_kernel(QP<real> p, int TX, double *__restrict__ parts)
+{
+    extern __shared__ double dsm[];
+    if (ld_flag(&p.ctl->hold)) return;
+    const int N = p.N, TY = blockDim.x / TX;
+    const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+    const size_t V = (size_t) p.V;
+    const size_t v0 = V * blockIdx.x / gridDim.x, v1 = V * (blockIdx.x + 1) / gridDim.x;
+    const real *__restrict__ X = p.Xc;
+    const int nvec = (N + VEC - 1) / VEC;
+    for (int nb0 = 0; nb0 < nvec; nb0 += TX) {     // uniform trip count: every thread reaches the barriers
+        const int nb = nb0 + tx;
+        const bool on = nb < nvec;
+        double acc[VEC];
+        real part[VEC];
+#pragma unroll
+        for (int k = 0; k < VEC; k++) part[k] = 0;
+        if (on) {
+            const real *__restrict__ Ab = p.A + (size_t) nb * VEC;
+            size_t v = v0 + ty;
+            for (; v + 3 * (size_t) TY < v1; v += 4 * (size_t) TY) {
+                real a0[VEC], a1[VEC], a2[VEC], a3[VEC];
+                vload<real, VEC>(Ab + (size_t) N * v, a0);
+                vload<real, VEC>(Ab + (size_t) N * (v + TY), a1);
+                vload<real, VEC>(Ab + (size_t) N * (v + 2 * (size_t) TY), a2);
+                vload<real, VEC>(Ab + (size_t) N * (v + 3 * (size_t) TY), a3);
+                const real x0 = X[v], x1 = X[v + TY], x2 = X[v + 2 * (size_t) TY], x3 = X[v + 3 * (size_t) TY];
+#pragma unroll
+                for (int k = 0; k < VEC; k++) part[k] += a0[k] * x0 + a1[k] * x1 + a2[k] * x2 + a3[k] * x3;
+            }
+            for (; v < v1; v += TY) {
+                real a0[VEC];
+                vload<real, VEC>(Ab + (size_t) N * v, a0);
+                const real x0 = X[v];
+#pragma unroll
+                for (int k = 0; k < VEC; k++) part[k] += a0[k] * x0;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < VEC; k++) acc[k] = (double) part[k];
+        if (TY > 1) {       // fold the TY column lanes in a fixed order through shared memory
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < VEC; k++) dsm[((size_t) ty * TX + tx) * VEC + k] = acc[k];
+            __syncthreads();
+            if (ty == 0) {
+                for (int y = 1; y < TY; y++)
+#pragma unroll
+                    for (int k = 0; k < VEC; k++) acc[k] += dsm[((size_t) y * TX + tx) * VEC + k];
+            }
+        }
+        if (on && ty == 0) {
+#pragma unroll
+            for (int k = 0; k < VEC; k++)
+                if (nb * VEC + k < N) parts[(size_t) blockIdx.x * N + (size_t) nb * VEC + k] = acc[k];
+        }
+    }
+}
+
+template <typename real>
+__global__ void ax_finish_kernel(QP<real> p, const double *__restrict__ parts)
+{
+    if (ld_flag(&p.ctl->hold)) return;
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= p.N) return;
+    double a = 0;
+    for (int b = 0; b < p.nparts; b++) a += parts[(size_t) b * p.N + n];
+    p.R[n] = p.Y[n] - (real) a;
+}
+
+// N>0, pass 2 (mode 0):  G = -A^t R, P = 2X - Ga.G  (ref :432-440, :463-464); GL lanes per column.
+// mode 1 (setup): Ga0 = ||A_v||^2 and AtY = <A_v, Y>   (ref :102-110, :126-134).
+template <typename real, int VEC>
+__global__ void __launch_bounds__(256) atr_kernel(QP<real> p, int GL, int mode)
+{
+    if (mode == 0 && ld_flag(&p.ctl->hold)) return;
+    const int N = p.N;
+    const size_t gid = ((size_t) blockIdx.x * blockDim.x + threadIdx.x) / GL;
+    const int gl = threadIdx.x % GL;
+    const bool live = gid < (size_t) p.V;
+    const size_t v = live ? gid : (size_t) p.V - 1;
+    const real *__restrict__ col = p.A + (size_t) N * v;
+    const real *__restrict__ rhs = mode ? p.Y : p.R;
+    const int nvec = (N + VEC - 1) / VEC;
+    real s0 = 0, s1 = 0;
+    for (int nb = gl; nb < nvec; nb += GL) {
+        real a[VEC], r[VEC];
+        vload<real, VEC>(col + (size_t) nb * VEC, a);
+        vload<real, VEC>(rhs + (size_t) nb * VEC, r);
+#pragma unroll
+        for (int k = 0; k < VEC; k++) { s0 += a[k] * r[k]; if (mode) s1 += a[k] * a[k]; }
+    }
+    for (int o = GL >> 1; o > 0; o >>= 1) {
+        s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+        if (mode) s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    }
+    if (live && gl == 0) {
+        if (mode) { p.Ga0[v] = s1; p.AtY[v] = s0; }
+        else {
+            pair_t<real> *XP = (ld_flag(&p.ctl->it) & 1) ? p.XP1 : p.XP0;
+            const real g = -s0;
+            p.G[v] = g;
+            XP[v].y = (real) 2 * p.Xc[v] - p.Ga[v] * g;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+template <typename real>
+struct QuadSolver {
+    const QuadProblem<real> &q;
+    SellGraph g;
+    QP<real> p{};
+    DevBuf<Ctl> ctl;
+    DevIn<real> Y, A, La_d1, La_l1, L, X0;
+    DevIn<int> Eu, Ev;
+    DevBuf<real> w, thc, Z0, Z1, Xc, T, Sinv, Ga, Ga0, G, Thl1, R, AtY, dObj, dDif, Xout;
+    DevBuf<pair_t<real>> XP0, XP1;
+    DevBuf<double> partial, parts;
+    Ctl *hctl = nullptr;            // pinned mirror of the control block, one per batch in flight
+    cudaEvent_t ev[2]{}, ev_a{}, ev_b{}, ev_c{};
+    cudaGraphExec_t gexec = nullptr;
+    int graph_trips = 0;
+    int vec = 1, TX = 1, GL = 1, vgrid = 0;
+    size_t ax_smem = 0;
+
+    explicit QuadSolver(const QuadProblem<real> &q_) : q(q_) {}
+    ~QuadSolver()
+    {
+        if (gexec) cudaGraphExecDestroy(gexec);
+        if (hctl) cudaFreeHost(hctl);
+        for (auto e : {ev[0], ev[1], ev_a, ev_b, ev_c}) if (e) cudaEventDestroy(e);
+    }
+
+    void setup()
+    {
+        const int V = q.V, E = q.E, N = q.N;
+        PFDR_REQUIRE(V > 0 && E >= 0, "V must be positive and E non-negative");
+        PFDR_REQUIRE(q.itMax >= 0, "itMax must be non-negative");
+        PFDR_REQUIRE(N == 0 || q.A != nullptr, "A must not be NULL when N != 0");
+        cudaStream_t st = ctx().stream;
+        for (auto *e : {&ev[0], &ev[1], &ev_a, &ev_b, &ev_c}) PFDR_CUDA(cudaEventCreate(e));
+        PFDR_CUDA(cudaEventRecord(ev_a, st));
+        PFDR_CUDA(cudaMallocHost((void **) &hctl, 2 * sizeof(Ctl)));
+
+        const size_t ylen = (N > 0) ? (size_t) N : (size_t) V;
+        const size_t alen = (N > 0) ? (size_t) N * V : (N < 0 ? (size_t) V * V : (size_t) V);
+        Eu.bind(q.Eu, E); Ev.bind(q.Ev, E);
+        Y.bind(q.Y, ylen); A.bind(q.A, q.A ? alen : 0);
+        La_d1.bind(q.La_d1, E); La_l1.bind(q.prox_kind == 0 ? q.La_l1 : nullptr, V);
+        L.bind(q.L, q.L ? (q.Ltype == PFDR_B200_SCAL ? 1 : (size_t) V) : 0);
+        X0.bind(q.X, V);
+        build_sell(g, Eu, Ev, V, E, 32);
+
+        const size_t ns = (size_t) std::max<long long>(g.nslots, 1);
+        w.alloc(ns); Z0.alloc(ns); Z1.alloc(ns);
+        XP0.alloc(V); XP1.alloc(V); T.alloc(V); Sinv.alloc(V); Ga.alloc(V); Ga0.alloc(V);
+        if (La_l1.p) Thl1.alloc(V);
+        if (N != 0) { Xc.alloc(V); G.alloc(V); }
+        if (N > 0) { R.alloc(N); AtY.alloc(V); }
+        if (q.Obj) dObj.alloc((size_t) q.itMax + 1);
+        if (q.Dif) dDif.alloc((size_t) std::max(q.itMax, 1));
+        vgrid = (int) cdiv(V, 256);
+        ctl.alloc(1);
+
+        // padded slots of Z must never hold garbage that could turn into NaN traps: zero them
+        Z0.zero(); Z1.zero(); w.zero();
+
+        p.ctl = ctl.p; p.V = V; p.N = N; p.E = E;
+        p.slice_off = g.slice_off.p; p.nbr = g.nbr.p; p.twin = g.twin.p; p.hkey = g.hkey.p;
+        p.w = w.p; p.thc = nullptr; p.thc0 = 0; p.Z0 = Z0.p; p.Z1 = Z1.p; p.XP0 = XP0.p; p.XP1 = XP1.p;
+        p.Xc = Xc.p; p.T = T.p; p.Sinv = Sinv.p; p.Ga = Ga.p; p.Ga0 = Ga0.p; p.G = G.p; p.Thl1 = Thl1.p;
+        p.R = R.p; p.AtY = AtY.p; p.Y = Y.p; p.A = A.p; p.La_d1 = La_d1.p; p.La_l1 = La_l1.p; p.L = L.p;
+        p.Eu = Eu.p; p.Ev = Ev.p; p.Ltype = q.Ltype; p.positivity = q.positivity; p.prox_kind = q.prox_kind;
+        p.lo = q.lo; p.hi = q.hi;
+        p.has_lo = (q.prox_kind == 1 && -HUGE_VAL < (double) q.lo);
+        p.has_hi = (q.prox_kind == 1 && (double) q.hi < HUGE_VAL);
+        p.rho = q.rho; p.condMin = q.condMin; p.dObj = dObj.p; p.dDif = dDif.p;
+
+        // dense operator geometry
+        const int vmax = (sizeof(real) == 4) ? 4 : 2;
+        if (N > 0) {
+            const bool al = (N % vmax == 0) && (((uintptr_t) A.p) % 16 == 0) && (((uintptr_t) Y.p) % 16 == 0);
+            vec = al ? vmax : 1;
+            const int nvec = (N + vec - 1) / vec;
+            TX = 1; while (TX < nvec && TX < 256) TX <<= 1;
+            GL = 1; while (GL < nvec && GL < 32) GL <<= 1;
+            p.nparts = std::max(1, std::min(num_sms() * 4, (V + 63) / 64));
+            parts.alloc((size_t) p.nparts * N);
+            ax_smem = (256 / TX > 1) ? (size_t) 256 * vec * sizeof(double) : 0;
+        } else if (N < 0) {
+            vec = ((V % vmax == 0) && (((uintptr_t) A.p) % 16 == 0)) ? vmax : 1;
+        }
+        const int maxgrid = std::max(std::max(vgrid, p.nparts), num_sms() * 8);
+        partial.alloc((size_t) maxgrid * 4);
+        p.partial = partial.p;
+
+        // control block (ref :286-292, :339-343)
+        Ctl h{};
+        const real tol2 = q.difTol * q.difTol, rcd2 = q.difRcd * q.difRcd;
+        h.it = 0; h.state = (q.itMax == 0) ? ST_FINAL : ST_RUN; h.hold = 0; h.itMax = q.itMax;
+        h.track = (q.difTol > (real) 0 || q.difRcd > (real) 0 || q.Dif != nullptr);
+        h.tol = (double) tol2; h.rcd = (double) rcd2;
+        h.dif = (double) (tol2 > rcd2 ? tol2 : rcd2);
+        h.eps = (double) (((real) 0 < q.difTol && q.difTol < real_eps<real>()) ? q.difTol : real_eps<real>());
+        hctl[0] = h;
+        PFDR_CUDA(cudaMemcpyAsync(ctl.p, &hctl[0], sizeof(Ctl), cudaMemcpyHostToDevice, st));
+
+        // first preconditioning
+        if (N > 0) launch_atr(1);
+        PFDR_LAUNCH(amp_kernel<real>, vgrid, 256, 0, p, 0);
+        PFDR_LAUNCH(init_vertex_kernel<real>, vgrid, 256, 0, p, X0.p);
+        PFDR_CUDA(cudaStreamSynchronize(st));
+        double amp; PFDR_CUDA(cudaMemcpy(&amp, &ctl.p->amp, sizeof(double), cudaMemcpyDeviceToHost));
+        p.thc0 = (real) 1 / (real) amp;        // La_d1 / (c La_d1)
+        X0.own.release();
+        PFDR_CUDA(cudaEventRecord(ev_b, st));
+    }
+
+    void launch_atr(int mode)
+    {
+        const size_t threads = (size_t) q.V * GL;
+        if (vec > 1) PFDR_LAUNCH((atr_kernel<real, (sizeof(real) == 4 ? 4 : 2)>), cdiv(threads, 256), 256, 0, p, GL, mode);
+        else PFDR_LAUNCH((atr_kernel<real, 1>), cdiv(threads, 256), 256, 0, p, GL, mode);
+    }
+
+    void enqueue_trip()
+    {
+        constexpr int VM = (sizeof(real) == 4) ? 4 : 2;
+        if (q.N > 0) {
+            if (vec > 1) PFDR_LAUNCH((ax_partial_kernel<real, VM>), p.nparts, 256, ax_smem, p, TX, parts.p);
+            else PFDR_LAUNCH((ax_partial_kernel<real, 1>), p.nparts, 256, ax_smem, p, TX, parts.p);
+            PFDR_LAUNCH(ax_finish_kernel<real>, cdiv(q.N, 128), 128, 0, p, parts.p);
+            launch_atr(0);
+        } else if (q.N < 0) {
+            const int grid = std::min((q.V + 3) / 4, num_sms() * 4);
+            if (vec > 1) PFDR_LAUNCH((ata_gemv_kernel<real, VM, 4>), grid, 256, 0, p);
+            else PFDR_LAUNCH((ata_gemv_kernel<real, 1, 4>), grid, 256, 0, p);
+        }
+        if (q.Obj) {
+            const size_t work = std::max((size_t) q.E, std::max((size_t) q.V, (size_t) std::max(q.N, 0)));
+            PFDR_LAUNCH(objective_kernel<real>, std::min<unsigned>(cdiv(work, 256), num_sms() * 8), 256, 0, p);
+        }
+        if (p.thc) PFDR_LAUNCH((quad_iter_kernel<real, true>), vgrid, 256, 0, p);
+        else PFDR_LAUNCH((quad_iter_kernel<real, false>), vgrid, 256, 0, p);
+    }
+
+    int launches_per_trip() const { return (q.N > 0 ? 3 : (q.N < 0 ? 1 : 0)) + (q.Obj ? 1 : 0) + 1; }
+
+    // enqueue `trips` iterations; replays a captured CUDA graph when a whole batch is requested
+    void enqueue_batch(int trips, int batch)
+    {
+        cudaStream_t st = ctx().stream;
+        if (trips == batch && use_graph()) {
+            if (!gexec || graph_trips != batch) {
+                if (gexec) { cudaGraphExecDestroy(gexec); gexec = nullptr; }
+                cudaGraph_t graph;
+                const long long l0 = ctx().stats.launches, l1 = ctx().stats.loop_launches;
+                PFDR_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+                for (int i = 0; i < batch; i++) enqueue_trip();
+                PFDR_CUDA(cudaStreamEndCapture(st, &graph));
+                ctx().stats.launches = l0; ctx().stats.loop_launches = l1;
+                PFDR_CUDA(cudaGraphInstantiate(&gexec, graph, 0));
+                cudaGraphDestroy(graph);
+                graph_trips = batch;
+            }
+            PFDR_CUDA(cudaGraphLaunch(gexec, st));
+            ctx().stats.launches += (long long) batch * launches_per_trip();
+            ctx().stats.loop_launches += (long long) batch * launches_per_trip();
+        } else {
+            for (int i = 0; i < trips; i++) enqueue_trip();
+        }
+    }
+
+    static bool use_graph()
+    {
+        static int v = -1;
+        if (v < 0) { const char *e = getenv("PFDR_B200_GRAPH"); v = (e && e[0] == '0') ? 0 : 1; }
+        return v != 0;
+    }
+
+    void recondition()
+    {
+        if (!thc.p) { thc.alloc(std::max<size_t>(g.nslots, 1)); thc.zero(); p.thc = thc.p; }
+        if (gexec) { cudaGraphExecDestroy(gexec); gexec = nullptr; }   // kernel parameters changed
+        PFDR_LAUNCH(amp_kernel<real>, vgrid, 256, 0, p, 1);
+        PFDR_LAUNCH(recond_vertex_kernel<real>, vgrid, 256, 0, p);
+        PFDR_LAUNCH(resume_kernel<real>, 1, 1, 0, p, 0.01);                   // ref :458
+    }
+
+    void run()
+    {
+        cudaStream_t st = ctx().stream;
+        // batch: enough trips per host round trip to hide it, small enough to bound the no-op tail
+        const size_t work = (size_t) g.nslots + (size_t) q.V + (size_t) std::abs((double) q.N) * q.V;
+        int batch = work > (1u << 24) ? 4 : (work > (1u << 20) ? 16 : 64);
+        batch = std::max(1, std::min(batch, q.itMax + 1));
+        ctx().in_loop = true;
+        PFDR_CUDA(cudaEventRecord(ev_b, st));
+        // Pipelined: batch k is enqueued before the verdict of batch k-1 is read, so the GPU never
+        // idles on the host.  Launches enqueued after the device froze are no-ops.
+        long long enqueued = 0, budget = (long long) q.itMax + 1 + 2LL * batch;
+        int fresh_from = 0;             // batches older than this predate the last reconditioning
+        for (int k = 0;; k++) {
+            enqueue_batch(batch, batch);
+            enqueued += batch;
+            PFDR_CUDA(cudaMemcpyAsync(&hctl[k & 1], ctl.p, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
+            PFDR_CUDA(cudaEventRecord(ev[k & 1], st));
+            int verdict = 0;
+            if (k >= 1 && k - 1 >= fresh_from) verdict = inspect((k - 1) & 1);
+            if (verdict == 0 && enqueued >= budget) verdict = (k >= fresh_from) ? inspect(k & 1) : 0;
+            if (verdict == 1) break;
+            if (verdict == 2) {         // frozen for a reconditioning; batches <= k were no-ops past the freeze
+                PFDR_CUDA(cudaStreamSynchronize(st));
+                recondition();
+                fresh_from = k + 1;
+                budget = enqueued + (long long) q.itMax + 1 + 2LL * batch;
+            } else if (enqueued >= budget)
+                throw Error(PFDR_B200_ERR_CUDA, "PFDR loop did not terminate on the device");
+        }
+        PFDR_CUDA(cudaEventRecord(ev_c, st));
+        PFDR_CUDA(cudaStreamSynchronize(st));
+        ctx().in_loop = false;
+    }
+
+    // waits for batch slot b: 0 = still running, 1 = finished, 2 = frozen for a reconditioning
+    int inspect(int b)
+    {
+        PFDR_CUDA(cudaEventSynchronize(ev[b]));
+        const Ctl &h = hctl[b];
+        if (!h.hold) return 0;
+        return h.state == ST_FINAL ? 1 : (h.state == ST_RECOND ? 2 : 0);
+    }
+
+    void finish()
+    {
+        cudaStream_t st = ctx().stream;
+        Ctl h;
+        PFDR_CUDA(cudaMemcpyAsync(&hctl[0], ctl.p, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
+        PFDR_CUDA(cudaStreamSynchronize(st));
+        h = hctl[0];
+        Xout.alloc(q.V);
+        PFDR_LAUNCH(extract_x_kernel<real>, vgrid, 256, 0, p, Xout.p);
+        copy_out(q.X, Xout.p, q.V);
+        if (q.Obj) copy_out(q.Obj, dObj.p, (size_t) h.it + 1);
+        if (q.Dif && h.it > 0) copy_out(q.Dif, dDif.p, (size_t) h.it);
+        PFDR_CUDA(cudaStreamSynchronize(st));
+        if (q.it) *q.it = h.it;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ev_a, ev_b); ctx().stats.setup_ms = ms;
+        cudaEventElapsedTime(&ms, ev_b, ev_c); ctx().stats.loop_ms = ms;
+        ctx().stats.iterations = h.it;
+        if (q.verbose) {
+            printf("PFDR (B200): %d iterations (max. %d), iterate evolution %g, loop %.3f ms\n", h.it, q.itMax,
+                   h.dif, ctx().stats.loop_ms);
+            fflush(stdout);
+        }
+    }
+};
+
+template <typename real>
+void solve_quadratic(const QuadProblem<real> &q)
+{
+    QuadSolver<real> s(q);
+    s.setup();
+    s.run();
+    s.finish();
+}
+
+template void solve_quadratic<float>(const QuadProblem<float> &);
+template void solve_quadratic<double>(const QuadProblem<double> &);
+
+}  // namespace pfdr

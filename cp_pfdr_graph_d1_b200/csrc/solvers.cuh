@@ -1,0 +1,30 @@
+// solvers.cuh - host-side entry points behind the C ABI (capi.cu).
+#pragma once
+#include "common.cuh"
+
+namespace pfdr {
+
+// arguments of PFDR_graph_quadratic_d1_{l1,bounds}<real> (reference include/PFDR_graph_quadratic_d1_l1.hpp:36-42,
+// include/PFDR_graph_quadratic_d1_bounds.hpp:34-40); prox_kind 0 = l1 (+positivity), 1 = box [lo, hi]
+template <typename real>
+struct QuadProblem {
+    int V, E, N;
+    real *X; const real *Y, *A; const int *Eu, *Ev; const real *La_d1, *La_l1;
+    int positivity, prox_kind; real lo, hi;
+    int Ltype; const real *L; real rho, condMin, difRcd, difTol;
+    int itMax; int *it; real *Obj, *Dif; int verbose;
+};
+template <typename real> void solve_quadratic(const QuadProblem<real> &q);
+
+// arguments of PFDR_graph_loss_d1_simplex<real> (reference include/PFDR_graph_loss_d1_simplex.hpp:24-30)
+template <typename real>
+struct SimplexProblem {
+    int K, V, E; real al; const real *La_f; real *P; const real *Q; const int *Eu, *Ev; const real *La_d1;
+    real rho, condMin, difRcd, difTol; int itMax; int *it; real *Obj, *Dif; int verbose;
+};
+template <typename real> void solve_simplex(const SimplexProblem<real> &q);
+
+template <typename real> void proj_simplex_metric(real *X, const real *M, int D, int N, int nm, const real *A, int na);
+template <typename real> real operator_norm_matrix(int M, int N, const real *A, real nTol, int itMax, int nbInit, int verbose);
+
+}  // namespace pfdr

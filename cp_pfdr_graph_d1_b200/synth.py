@@ -1,0 +1,80 @@
+"""Seeded synthetic workloads of BASELINE.json / SURVEY.md section 8(d) (host generation, numpy)."""
+import numpy as np
+
+
+def grid_graph(n, nz=None):
+    """3D 6-connected grid, v = (z*n + y)*n + x; edges emitted vertex-major in the order +x, +y, +z."""
+    nz = n if nz is None else nz
+    idx = np.arange(n * n * nz, dtype=np.int64).reshape(nz, n, n)
+    cand_u = np.stack([idx, idx, idx], axis=-1)                                   # (z, y, x, dir)
+    cand_v = np.stack([idx + 1, idx + n, idx + n * n], axis=-1)
+    ok = np.zeros(cand_u.shape, bool)
+    ok[:, :, :-1, 0] = True
+    ok[:, :-1, :, 1] = True
+    ok[:-1, :, :, 2] = True
+    Eu = cand_u[ok].astype(np.int32)
+    Ev = cand_v[ok].astype(np.int32)
+    return n * n * nz, Eu, Ev
+
+
+def c2_denoise(n=100, dtype=np.float32, diag=True, seed=2, const_weights=False):
+    """C2: PFDR_graph_l22_d1_l1 denoising on the n^3 grid (4 constant z-slabs, levels 0,1,3,2, + U(-.5,.5))."""
+    V, Eu, Ev = grid_graph(n)
+    z = np.arange(V) // (n * n)
+    levels = np.array([0.0, 1.0, 3.0, 2.0])
+    Y = levels[np.minimum(4 * z // n, 3)] + np.random.default_rng(seed).uniform(-0.5, 0.5, V)
+    La_d1 = np.full(Eu.shape[0], 0.5) if const_weights else np.random.default_rng(seed + 1).uniform(0.25, 0.75, Eu.shape[0])
+    La_l2 = np.random.default_rng(seed + 2).uniform(0.5, 1.5, V) if diag else None
+    return dict(V=V, E=Eu.shape[0], Y=Y.astype(dtype), La_l2=None if La_l2 is None else La_l2.astype(dtype),
+                Eu=Eu, Ev=Ev, La_d1=La_d1.astype(dtype))
+
+
+def c4_simplex(n=64, K=16, dtype=np.float32, seed=6):
+    """C4: K-label smoothed-KL problem on the n^3 grid; truth label = 4*floor(4z/n) + floor(4y/n)."""
+    V, Eu, Ev = grid_graph(n)
+    v = np.arange(V)
+    z, y = v // (n * n), (v // n) % n
+    lab = (4 * np.minimum(4 * z // n, 3) + np.minimum(4 * y // n, 3)) % K
+    Q = np.random.default_rng(seed).uniform(0.0, 1.0, (V, K))
+    Q[v, lab] += 2.0
+    Q /= Q.sum(axis=1, keepdims=True)
+    return dict(V=V, E=Eu.shape[0], K=K, Q=Q.astype(dtype), Eu=Eu, Ev=Ev,
+                La_d1=np.full(Eu.shape[0], 0.2, dtype), al=0.05, labels=lab)
+
+
+def knn_graph(V=32768, k=10, seed=4):
+    """C3 graph: symmetrised, de-duplicated k-NN edges (u < v) of V uniform points in the unit cube."""
+    from scipy.spatial import cKDTree
+    pts = np.random.default_rng(seed).uniform(0.0, 1.0, (V, 3))
+    _, nn = cKDTree(pts).query(pts, k=k + 1)
+    u = np.repeat(np.arange(V), k)
+    w = nn[:, 1:].reshape(-1)
+    a, b = np.minimum(u, w), np.maximum(u, w)
+    key = np.unique(a.astype(np.int64) * V + b)
+    return pts, (key // V).astype(np.int32), (key % V).astype(np.int32)
+
+
+def c3_bounds_ata(V=32768, k=10, m=2048, dtype=np.float32, seed=4):
+    """C3: box-constrained problem with dense precomputed A^tA = G^tG/m + 0.1 I on a k-NN graph."""
+    pts, Eu, Ev = knn_graph(V, k, seed)
+    G = np.random.default_rng(seed + 1).standard_normal((m, V)).astype(np.float32)
+    AtA = (G.T @ G) / np.float32(m)
+    AtA[np.arange(V), np.arange(V)] += np.float32(0.1)
+    x0 = np.round(4 * pts[:, 0]) / 4
+    AtY = AtA.astype(np.float64) @ x0 + 0.01 * np.random.default_rng(seed + 2).standard_normal(V)
+    return dict(V=V, E=Eu.shape[0], AtA=np.asfortranarray(AtA.astype(dtype)), AtY=AtY.astype(dtype), Eu=Eu, Ev=Ev,
+                La_d1=np.full(Eu.shape[0], 0.02, dtype), x0=x0)
+
+
+def dense_problem(n=16, N=64, dtype=np.float32, seed=7):
+    """C5 in miniature: dense N-by-V lead field on the n^3 grid, two boxes of value 2, Y = A x0."""
+    V, Eu, Ev = grid_graph(n)
+    rng = np.random.default_rng(seed)
+    A = np.asfortranarray(rng.uniform(-1 / 16, 1 / 16, (N, V)).astype(dtype))
+    v = np.arange(V)
+    z, y, x = v // (n * n), (v // n) % n, v % n
+    x0 = np.zeros(V)
+    x0[(z < n // 3) & (y < n // 2) & (x < n // 2)] = 2.0
+    x0[(z >= 2 * n // 3) & (y >= n // 2)] = 2.0
+    Y = (A.astype(np.float64) @ x0).astype(dtype)
+    return dict(V=V, E=Eu.shape[0], N=N, A=A, Y=Y, Eu=Eu, Ev=Ev, La_d1=np.full(Eu.shape[0], 0.05, dtype), x0=x0)

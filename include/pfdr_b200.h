@@ -1,0 +1,110 @@
+/* pfdr_b200.h - C ABI of the B200-native PFDR hot path (libpfdr_b200.so).
+ *
+ * Drop-in boundary for ai3DVision/CP_PFDR_graph_d1: one extern "C" entry point per reference
+ * routine x {f32,f64}.  Argument lists, meanings and ownership are exactly those of the reference
+ * templates they replace (reference file:line cited at each prototype); `Lipschtype` travels as
+ * an int (SCAL = 0, DIAG = 1; include/PFDR_graph_quadratic_d1_l1.hpp:34) and every function
+ * returns an int status (0 = ok) because the reference's `void` cannot report a CUDA failure.
+ * csrc/shim_*.cpp re-creates the reference's C++ template symbols on top of this ABI so that
+ * the MEX / Boost-Python gateways and the cut-pursuit sources link unchanged.
+ *
+ * Pointers are plain host pointers, as in the reference.  As an extension every array argument
+ * may instead be a CUDA device pointer (detected with cudaPointerGetAttributes): it is then used
+ * in place / written in place without a host round trip.
+ *
+ * There is no CPU fallback: every entry point needs a CUDA device and fails with a non-zero
+ * status (message in pfdr_b200_last_error()) when none is usable.
+ */
+#ifndef PFDR_B200_H
+#define PFDR_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PFDR_B200_SCAL 0
+#define PFDR_B200_DIAG 1
+
+/* status codes */
+#define PFDR_B200_OK            0
+#define PFDR_B200_ERR_CUDA      1   /* CUDA runtime failure (no device, OOM, launch error)      */
+#define PFDR_B200_ERR_ARG       2   /* unsupported / inconsistent argument                       */
+#define PFDR_B200_ERR_NCCL      3   /* NCCL failure (sharded entry points only)                  */
+
+/* ---- quadratic + d1 + l1 (+ positivity) ----------------------------------------------------
+ * replaces PFDR_graph_quadratic_d1_l1<real>  (include/PFDR_graph_quadratic_d1_l1.hpp:36-42,
+ * src/PFDR_graph_quadratic_d1_l1.cpp:270-553).  N>0: A is N-by-V column major, Y length N;
+ * N<0: A is (A^tA) V-by-V, Y is A^tY; N==0: A is diag(A^tA) or NULL (identity).
+ * X[V] in/out (must be initialised); *it always written; Obj needs itMax+1 entries, Dif itMax. */
+int pfdr_b200_quadratic_d1_l1_f32(int V, int E, int N, float *X, const float *Y, const float *A,
+    const int *Eu, const int *Ev, const float *La_d1, const float *La_l1, int positivity,
+    int Ltype, const float *L, float rho, float condMin, float difRcd, float difTol, int itMax,
+    int *it, float *Obj, float *Dif, int verbose);
+int pfdr_b200_quadratic_d1_l1_f64(int V, int E, int N, double *X, const double *Y, const double *A,
+    const int *Eu, const int *Ev, const double *La_d1, const double *La_l1, int positivity,
+    int Ltype, const double *L, double rho, double condMin, double difRcd, double difTol, int itMax,
+    int *it, double *Obj, double *Dif, int verbose);
+
+/* ---- quadratic + d1 + box ------------------------------------------------------------------
+ * replaces PFDR_graph_quadratic_d1_bounds<real> (include/PFDR_graph_quadratic_d1_bounds.hpp:34-40,
+ * src/PFDR_graph_quadratic_d1_bounds.cpp:244-530).  min/max = -/+HUGE_VAL(F) for "no bound". */
+int pfdr_b200_quadratic_d1_bounds_f32(int V, int E, int N, float *X, const float *Y, const float *A,
+    const int *Eu, const int *Ev, const float *La_d1, float min, float max,
+    int Ltype, const float *L, float rho, float condMin, float difRcd, float difTol, int itMax,
+    int *it, float *Obj, float *Dif, int verbose);
+int pfdr_b200_quadratic_d1_bounds_f64(int V, int E, int N, double *X, const double *Y, const double *A,
+    const int *Eu, const int *Ev, const double *La_d1, double min, double max,
+    int Ltype, const double *L, double rho, double condMin, double difRcd, double difTol, int itMax,
+    int *it, double *Obj, double *Dif, int verbose);
+
+/* ---- loss + d1 + simplex -------------------------------------------------------------------
+ * replaces PFDR_graph_loss_d1_simplex<real> (include/PFDR_graph_loss_d1_simplex.hpp:24-30,
+ * src/PFDR_graph_loss_d1_simplex.cpp:372-715).  P, Q are K-by-V column major (P[v*K+k]);
+ * al = 0 linear, 0<al<1 smoothed Kullback-Leibler, al = 1 quadratic (al > 1 is undefined in the
+ * reference, SURVEY 5.1-10, and rejected here with PFDR_B200_ERR_ARG). */
+int pfdr_b200_loss_d1_simplex_f32(int K, int V, int E, float al, const float *La_f, float *P,
+    const float *Q, const int *Eu, const int *Ev, const float *La_d1, float rho, float condMin,
+    float difRcd, float difTol, int itMax, int *it, float *Obj, float *Dif, int verbose);
+int pfdr_b200_loss_d1_simplex_f64(int K, int V, int E, double al, const double *La_f, double *P,
+    const double *Q, const int *Eu, const int *Ev, const double *La_d1, double rho, double condMin,
+    double difRcd, double difTol, int itMax, int *it, double *Obj, double *Dif, int verbose);
+
+/* ---- proj_simplex_metric -------------------------------------------------------------------
+ * replaces proj_simplex_metric<real> (include/proj_simplex.hpp:33-35, src/proj_simplex_metric.cpp:18-83):
+ * in-place projection of the N columns (length D) of X onto {x>=0, sum x = A[min(n,na-1)]} in the
+ * metric diag(1/M[:,min(n,nm-1)]). */
+int pfdr_b200_proj_simplex_metric_f32(float *X, const float *M, int D, int N, int nm, const float *A, int na);
+int pfdr_b200_proj_simplex_metric_f64(double *X, const double *M, int D, int N, int nm, const double *A, int na);
+
+/* ---- operator_norm_matrix ------------------------------------------------------------------
+ * replaces operator_norm_matrix<real> (include/operator_norm_matrix.hpp:12-14,
+ * src/operator_norm_matrix.cpp:84-212): squared operator norm (largest eigenvalue of A^tA) by the
+ * power method, max over nbInit random starts; M or N == 0 means A already is A^tA / AA^t.
+ * The value is returned through *result. */
+int pfdr_b200_operator_norm_matrix_f32(int M, int N, const float *A, float nTol, int itMax, int nbInit,
+                                       int verbose, float *result);
+int pfdr_b200_operator_norm_matrix_f64(int M, int N, const double *A, double nTol, int itMax, int nbInit,
+                                       int verbose, double *result);
+
+/* ---- run-time controls and introspection (no counterpart in the reference) ----------------- */
+const char *pfdr_b200_last_error(void);      /* message of the last non-zero status (thread local) */
+int pfdr_b200_version(void);
+int pfdr_b200_set_device(int device);        /* CUDA device used by subsequent calls (default: current) */
+int pfdr_b200_set_stream(void *cuda_stream); /* cudaStream_t all kernels are launched on (default 0)    */
+
+typedef struct {
+    double setup_ms;       /* upload + half-edge layout + preconditioning (CUDA events)           */
+    double loop_ms;        /* the iteration loop only (CUDA events on the launch stream)          */
+    double total_ms;       /* whole call, host wall clock                                         */
+    long long launches;    /* kernels of this library launched by the call                        */
+    long long loop_launches;    /* ... of which inside the iteration loop                         */
+    int iterations;        /* == *it                                                              */
+    long long h2d_bytes, d2h_bytes;  /* host<->device bytes moved by the call                     */
+    long long slots;       /* padded half-edge slots of the SELL layout (>= 2E)                   */
+} pfdr_b200_stats;
+int pfdr_b200_get_last_stats(pfdr_b200_stats *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PFDR_B200_H */

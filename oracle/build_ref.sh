@@ -1,0 +1,34 @@
+#!/usr/bin/env bash
+# TEST INFRASTRUCTURE ONLY.
+# Compiles the UNMODIFIED reference sources where they lie under $REF (default
+# /root/reference) plus the extern "C" gateways of this directory into
+# oracle/_ref/libref.so.  Nothing from the reference is copied into the repo;
+# oracle/_ref/ is git-ignored (but travels to the GPU box with the snapshot).
+# Flags follow the reference's own build lines (python/CMakeLists.txt:33,
+# octave/compile_mex.m:41): -std=c++11 -O3 -fopenmp -DNDEBUG.
+set -euo pipefail
+HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
+REF="${REF:-/root/reference}"
+OUT="$HERE/_ref"
+if [ ! -d "$REF/src" ]; then
+    echo "build_ref.sh: $REF/src not present - keeping any prebuilt $OUT/libref.so" >&2
+    exit 0
+fi
+mkdir -p "$OUT/obj"
+CXXFLAGS="-std=c++11 -O3 -fopenmp -DNDEBUG -fPIC -w"
+pids=()
+objs=()
+for f in PFDR_graph_quadratic_d1_l1 PFDR_graph_quadratic_d1_bounds PFDR_graph_loss_d1_simplex \
+         proj_simplex_metric operator_norm_matrix CP_PFDR_graph_quadratic_d1_l1 \
+         CP_PFDR_graph_quadratic_d1_l1_duplex CP_PFDR_graph_quadratic_d1_bounds \
+         CP_PFDR_graph_loss_d1_simplex graph maxflow; do
+    g++ $CXXFLAGS -c "$REF/src/$f.cpp" -o "$OUT/obj/$f.o" & pids+=($!)
+    objs+=("$OUT/obj/$f.o")
+done
+for w in ref_wrap_l1 ref_wrap_bounds ref_wrap_misc; do
+    g++ $CXXFLAGS -I"$REF/include" -c "$HERE/$w.cpp" -o "$OUT/obj/$w.o" & pids+=($!)
+    objs+=("$OUT/obj/$w.o")
+done
+for p in "${pids[@]}"; do wait "$p"; done
+g++ -shared -fopenmp -Wl,-Bsymbolic-functions -o "$OUT/libref.so" "${objs[@]}"
+echo "built $OUT/libref.so"

@@ -1,0 +1,156 @@
+"""Pins the CPU restatement (oracle/liboracle.so) against the unmodified reference compiled from
+/root/reference (oracle/_ref/libref.so) on seeded inputs - the reference ships no golden vectors
+(SURVEY section 4), so outputs of the reference itself are the pin.  Also checks the numpy model of the
+GPU schedule (tests/sell_model.py) against the oracle.  CPU only."""
+import numpy as np
+import pytest
+
+from cp_pfdr_graph_d1_b200 import synth
+from cp_pfdr_graph_d1_b200.api import PFDR_graph_l22_d1_l1
+
+import sell_model
+
+TOL = {np.float32: 2e-4, np.float64: 1e-10}
+
+
+def rel(a, b):
+    return float(np.linalg.norm(a.astype(np.float64) - b) / max(np.linalg.norm(b), 1e-300))
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("variant", ["identity", "diag", "diag_l1_pos", "l1", "recond"])
+def test_quadratic_n0(oracle, reference, dtype, variant):
+    w = synth.c2_denoise(12, dtype, diag=(variant != "identity"))
+    kw = dict(difTol=1e-5, itMax=200, want_obj=True, want_dif=True)
+    if variant == "diag_l1_pos":
+        kw.update(La_l1=np.full(w["V"], 0.05, dtype), positivity=1)
+    if variant == "l1":
+        kw.update(La_l1=np.full(w["V"], 0.05, dtype), positivity=0, want_obj=False)
+    if variant == "recond":
+        kw.update(difRcd=1e-3, difTol=1e-6, itMax=400)
+    a = PFDR_graph_l22_d1_l1(w["Y"], w["La_l2"], w["Eu"], w["Ev"], w["La_d1"], backend=oracle, **kw)
+    b = PFDR_graph_l22_d1_l1(w["Y"], w["La_l2"], w["Eu"], w["Ev"], w["La_d1"], backend=reference, **kw)
+    assert abs(a.it - b.it) <= (0 if dtype is np.float64 else 2)
+    assert rel(a.X, b.X) < TOL[dtype]
+    n = min(a.it, b.it)
+    if kw.get("want_obj", True):
+        assert np.allclose(a.Obj[:n], b.Obj[:n], rtol=50 * TOL[dtype])
+    assert np.allclose(a.Dif[:n], b.Dif[:n], rtol=1e-2 if dtype is np.float32 else 1e-6, atol=1e-12)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("mode", ["direct", "ata"])
+@pytest.mark.parametrize("family", ["l1", "bounds"])
+def test_quadratic_dense(oracle, reference, dtype, mode, family):
+    w = synth.dense_problem(7, 24, dtype)
+    V = w["V"]
+    A64 = w["A"].astype(np.float64)
+    Lam = float(np.linalg.eigvalsh(A64.T @ A64).max())
+    if mode == "direct":
+        A, Y, N = w["A"], w["Y"], w["N"]
+    else:
+        A, Y, N = np.asfortranarray((A64.T @ A64).astype(dtype)), (A64.T @ w["Y"]).astype(dtype), -V
+    out = []
+    for be in (oracle, reference):
+        X = np.zeros(V, dtype)
+        kw = dict(Ltype=0, L=np.array([Lam], dtype), rho=1.5, condMin=1e-3, difRcd=0.0, difTol=1e-5, itMax=300,
+                  N=N, want_obj=True, want_dif=True)
+        if family == "l1":
+            r = be.PFDR_graph_quadratic_d1_l1(X, Y, A, w["Eu"], w["Ev"], w["La_d1"], np.full(V, 0.01, dtype), 1, **kw)
+        else:
+            r = be.PFDR_graph_quadratic_d1_bounds(X, Y, A, w["Eu"], w["Ev"], w["La_d1"], 0.0, 1.5, **kw)
+        out.append(r)
+    a, b = out
+    assert abs(a.it - b.it) <= (0 if dtype is np.float64 else 3)
+    assert rel(a.X, b.X) < 10 * TOL[dtype]
+    n = min(a.it, b.it)
+    assert np.allclose(a.Obj[:n], b.Obj[:n], rtol=1e-3 if dtype is np.float32 else 1e-8, atol=1e-6)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("al", [0.0, 0.05, 1.0])
+@pytest.mark.parametrize("variant", ["plain", "weighted", "recond", "labels"])
+def test_simplex(oracle, reference, dtype, al, variant):
+    w = synth.c4_simplex(8, 5, dtype)
+    kw = dict(rho=1.5, condMin=1e-2, difRcd=0.0, difTol=1e-4, itMax=150, want_obj=True, want_dif=True)
+    if variant == "weighted":
+        if al == 0.0:
+            pytest.skip("La_f is ignored by the linear loss")
+        kw["La_f"] = np.random.default_rng(9).uniform(0.5, 2.0, w["V"]).astype(dtype)
+    if variant == "recond":
+        kw.update(difRcd=1e-2, difTol=1e-5, itMax=300)
+    if variant == "labels":
+        kw.update(difTol=1.0, itMax=60)
+    out = []
+    for be in (oracle, reference):
+        P = w["Q"].copy()
+        out.append(be.PFDR_graph_loss_d1_simplex(P, w["Q"], al, w["Eu"], w["Ev"], w["La_d1"], **kw))
+    a, b = out
+    assert abs(a.it - b.it) <= (0 if dtype is np.float64 else 3)
+    assert rel(a.X, b.X) < 20 * TOL[dtype]
+    n = min(a.it, b.it)
+    assert np.allclose(a.Obj[:n], b.Obj[:n], rtol=1e-3 if dtype is np.float32 else 1e-8)
+    assert np.allclose(a.X.sum(axis=1), 1, atol=1e-4 if dtype is np.float32 else 1e-10)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_proj_simplex_metric(oracle, reference, dtype):
+    rng = np.random.default_rng(11)
+    X = rng.normal(0.3, 1.0, (257, 9)).astype(dtype)
+    M = rng.uniform(0.2, 1.0, (257, 9)).astype(dtype)
+    A = rng.uniform(0.5, 2.0, 3).astype(dtype)
+    a = oracle.proj_simplex_metric(X.copy(), M, A)
+    b = reference.proj_simplex_metric(X.copy(), M, A)
+    assert np.array_equal(a, b)                  # same operation order: bit-identical
+    tgt = np.concatenate([A, np.full(257 - 3, A[-1])])
+    assert np.allclose(a.sum(axis=1), tgt, rtol=1e-4 if dtype is np.float32 else 1e-12)
+    assert (a >= 0).all()
+    # single shared metric / single target (nm = na = 1)
+    a = oracle.proj_simplex_metric(X.copy(), M[:1])
+    b = reference.proj_simplex_metric(X.copy(), M[:1])
+    assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("shape", [(20, 50), (50, 20), (0, 30)])
+def test_operator_norm(oracle, reference, dtype, shape):
+    rng = np.random.default_rng(12)
+    M, N = shape
+    if M == 0:
+        B = rng.standard_normal((40, N))
+        A = np.asfortranarray((B.T @ B).astype(dtype))
+        lam = np.linalg.eigvalsh(A.astype(np.float64)).max()
+    else:
+        A = np.asfortranarray(rng.standard_normal((M, N)).astype(dtype))
+        lam = np.linalg.norm(A.astype(np.float64), 2) ** 2
+    a = oracle.operator_norm_matrix(A, M, N, 1e-4, 200, 8, seed=3)
+    b = reference.operator_norm_matrix(A, M, N, 1e-4, 200, 8)
+    # power method from random starts: both approach lambda_max from below
+    assert a <= lam * (1 + 1e-4) and b <= lam * (1 + 1e-4)
+    assert a > lam * 0.97 and b > lam * 0.97
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("variant", ["identity", "diag_l1_pos", "box"])
+def test_gpu_schedule_model(oracle, dtype, variant):
+    """the half-edge / recomputed-constants schedule of quad.cu reproduces the reference iteration"""
+    w = synth.c2_denoise(10, dtype, diag=(variant != "identity"))
+    V = w["V"]
+    A = w["La_l2"]
+    Y = w["Y"] if A is None else (A * w["Y"]).astype(dtype)
+    La_l1 = np.full(V, 0.05, dtype) if variant == "diag_l1_pos" else None
+    pos = int(variant == "diag_l1_pos")
+    kw = dict(rho=1.5, condMin=1e-3, difRcd=0.0, difTol=1e-5, itMax=150)
+    Ltype, L = (1, A) if A is not None else (0, None)
+    if variant == "box":
+        r = oracle.PFDR_graph_quadratic_d1_bounds(np.zeros(V, dtype), Y, A, w["Eu"], w["Ev"], w["La_d1"], 0.5, 2.5,
+                                                  Ltype, L, N=0, **kw)
+        box = (dtype(0.5), dtype(2.5))
+    else:
+        r = oracle.PFDR_graph_quadratic_d1_l1(np.zeros(V, dtype), Y, A, w["Eu"], w["Ev"], w["La_d1"], La_l1, pos,
+                                              Ltype, L, N=0, **kw)
+        box = None
+    x, it = sell_model.quad_n0(V, np.zeros(V, dtype), Y, A, w["Eu"], w["Ev"], w["La_d1"], La_l1, pos, box, Ltype, L,
+                               1.5, 1e-3, 1e-5, 150)
+    assert abs(it - r.it) <= (0 if dtype is np.float64 else 2)
+    assert rel(x, r.X) < (1e-4 if dtype is np.float32 else 1e-11)
