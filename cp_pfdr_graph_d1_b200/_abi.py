@@ -1,8 +1,8 @@
 """ctypes plumbing shared by every implementation of the PFDR C signatures.
 
-The product library (lib/libpfdr_b200.so, prefix ``pfdr_b200_``), the CPU restatement
-(oracle/liboracle.so, prefix ``oracle_``) and the compiled reference (oracle/_ref/libref.so,
-prefix ``ref_``) all expose the reference's argument lists
+The product library (lib/libpfdr_b200.so, prefix ``pfdr_b200_``) and the two CPU checkers that the
+test infrastructure under oracle/ builds (prefixes ``oracle_`` and ``ref_``; this package never loads
+them) all expose the reference's argument lists
 (/root/reference/include/PFDR_graph_quadratic_d1_l1.hpp:36-42, ..._bounds.hpp:34-40,
 PFDR_graph_loss_d1_simplex.hpp:24-30, proj_simplex.hpp:33-35, operator_norm_matrix.hpp:12-14),
 so one binder serves all three and the parity tests call them through identical code.

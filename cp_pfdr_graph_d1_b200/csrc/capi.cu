@@ -96,4 +96,32 @@ int pfdr_b200_quadratic_d1_bounds_##SUF(int V, int E, int N, real *X, const real
 QUAD_L1(f32, float)
 QUAD_L1(f64, double)
 
+#define SIMPLEX(SUF, real)                                                                              \
+int pfdr_b200_loss_d1_simplex_##SUF(int K, int V, int E, real al, const real *La_f, real *P,            \
+    const real *Q, const int *Eu, const int *Ev, const real *La_d1, real rho, real condMin,             \
+    real difRcd, real difTol, int itMax, int *it, real *Obj, real *Dif, int verbose)                    \
+{                                                                                                       \
+    return guarded([&] {                                                                                \
+        SimplexProblem<real> q{K, V, E, al, La_f, P, Q, Eu, Ev, La_d1, rho, condMin, difRcd, difTol,    \
+                               itMax, it, Obj, Dif, verbose};                                           \
+        solve_simplex<real>(q);                                                                         \
+    });                                                                                                 \
+}                                                                                                       \
+int pfdr_b200_proj_simplex_metric_##SUF(real *X, const real *M, int D, int N, int nm, const real *A,    \
+                                        int na)                                                         \
+{                                                                                                       \
+    return guarded([&] { proj_simplex_metric<real>(X, M, D, N, nm, A, na); });                          \
+}                                                                                                       \
+int pfdr_b200_operator_norm_matrix_##SUF(int M, int N, const real *A, real nTol, int itMax,             \
+                                         int nbInit, int verbose, real *result)                         \
+{                                                                                                       \
+    return guarded([&] {                                                                                \
+        PFDR_REQUIRE(result != nullptr, "operator_norm_matrix: result must not be NULL");               \
+        *result = operator_norm_matrix<real>(M, N, A, nTol, itMax, nbInit, verbose);                    \
+    });                                                                                                 \
+}
+
+SIMPLEX(f32, float)
+SIMPLEX(f64, double)
+
 }  // extern "C"

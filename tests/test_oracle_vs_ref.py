@@ -14,7 +14,7 @@ TOL = {np.float32: 2e-4, np.float64: 1e-10}
 
 
 def rel(a, b):
-    return float(np.linalg.norm(a.astype(np.float64) - b) / max(np.linalg.norm(b), 1e-300))
+    return float(np.linalg.norm(a.astype(np.float64) - b) / max(float(np.linalg.norm(b)), 1e-300))
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
