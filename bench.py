@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""bench.py - PFDR edge-updates/s on the BASELINE.json workloads (see DESIGN.md "Measurement").
+
+A *step* is one complete PFDR solve of `iters` iterations (difTol = 0, so exactly itMax iterations run)
+on the resident synthetic problem: solver.reset() (initial iterate + first preconditioning, device only)
+followed by solver.run().  `value` = E * iters * steps / time with every input already in HBM;
+`e2e` = the same metric through the one-shot C-ABI call with pinned HOST buffers (upload, half-edge layout,
+preconditioning, iterations, download of the iterate all inside the timed region).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2_f32|c2_f64|c4_f32|c4_f64] [--impl reference]
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def algorithmic_bytes(kind, V, E, r, K=1, diag=True, l1=False):
+    """minimal bytes that must cross HBM once per iteration."""
+    if kind == "quad":
+        return E * (8 + 5 * r) + V * 5 * r + (V * r if diag else 0) + (V * r if l1 else 0)
+    return E * (8 + r + 4 * r * K) + V * 5 * r * K
+
+
+WORKLOADS = {
+    # name: (kind, grid n, dtype, K, iterations per step)
+    "c2_f32": ("quad", 100, np.float32, 1, 500),
+    "c2_f64": ("quad", 100, np.float64, 1, 500),
+    "c4_f32": ("simplex", 252, np.float32, 16, 100),
+    "c4_f64": ("simplex", 252, np.float64, 16, 100),
+    "c4s_f32": ("simplex", 64, np.float32, 16, 100),      # parity-sized C4 (also what the CPU legs of C4 run)
+    "c4s_f64": ("simplex", 64, np.float64, 16, 100),
+}
+
+
+def describe(name):
+    kind, n, dt, K, iters = WORKLOADS[name]
+    if kind == "quad":
+        return (f"C2 PFDR_graph_l22_d1_l1 (diagonal A) denoising, 3D 6-connected grid {n}^3, "
+                f"{np.dtype(dt).name}, rho=1.5, difTol=0, itMax={iters}")
+    return (f"C4 PFDR_graph_loss_d1_simplex smoothed-KL (al=0.05), K={K}, 3D grid {n}^3, {np.dtype(dt).name}, "
+            f"rho=1.5, condMin=1e-2, difTol=0, itMax={iters}")
+
+
+# ------------------------------------------------------------------------------------------------
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def measured_traffic(name):
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get(name)
+    return None
+
+
+class ClockSampler:
+    """samples nvidia-smi clocks / throttle reasons while the timed region runs"""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.t.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+def host_inputs(name):
+    from cp_pfdr_graph_d1_b200 import synth
+    kind, n, dt, K, iters = WORKLOADS[name]
+    if kind == "quad":
+        w = synth.c2_denoise(n, dt, diag=True)
+        w["Ys"] = (w["La_l2"] * w["Y"]).astype(dt)          # the l22 gateway's pre-scaling (mex :54-60)
+        return w
+    return synth.c4_simplex(n, K, dt) if n <= 128 else None  # the full C4 is generated on the device
+
+
+def device_inputs_c4(n, K, dt, dev):
+    """full-size C4 generated on the device with torch (same recipe as synth.c4_simplex, torch RNG)"""
+    import torch
+    tdt = torch.float32 if dt is np.float32 else torch.float64
+    V = n ** 3
+    g = torch.Generator(device=dev).manual_seed(6)
+    v = torch.arange(V, device=dev)
+    z, y, x = v // (n * n), (v // n) % n, v % n
+    lab = (4 * torch.clamp(4 * z // n, max=3) + torch.clamp(4 * y // n, max=3)) % K
+    Q = torch.rand((V, K), generator=g, device=dev, dtype=tdt)
+    Q[v, lab] += 2.0
+    Q /= Q.sum(dim=1, keepdim=True)
+    eu, ev = [], []
+    for ok, d in ((x < n - 1, 1), (y < n - 1, n), (z < n - 1, n * n)):
+        eu.append(torch.where(ok, v, -1)); ev.append(torch.where(ok, v + d, -1))
+    Eu = torch.stack(eu, 1).reshape(-1); Ev = torch.stack(ev, 1).reshape(-1)
+    keep = Eu >= 0
+    Eu, Ev = Eu[keep].to(torch.int32).contiguous(), Ev[keep].to(torch.int32).contiguous()
+    La_d1 = torch.full((Eu.shape[0],), 0.2, device=dev, dtype=tdt)
+    return dict(V=V, E=int(Eu.shape[0]), K=K, Q=Q, Eu=Eu, Ev=Ev, La_d1=La_d1, al=0.05)
+
+
+def to_dev(a, dev):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+def make_solver(name, w, dev, itMax):
+    """solver handle over device-resident inputs"""
+    from cp_pfdr_graph_d1_b200 import api, DIAG
+    kind, n, dt, K, iters = WORKLOADS[name]
+    import torch
+    if kind == "quad":
+        d = {k: to_dev(w[k], dev) for k in ("Ys", "La_l2", "Eu", "Ev", "La_d1")}
+        d["X0"] = torch.zeros(w["V"], device=dev, dtype=d["Ys"].dtype)
+        torch.cuda.synchronize()
+        return api.QuadraticSolver(d["X0"], d["Ys"], d["La_l2"], d["Eu"], d["Ev"], d["La_d1"], None, 0, Ltype=DIAG,
+                                   L=d["La_l2"], rho=1.5, condMin=1e-3, difRcd=0.0, difTol=0.0, itMax=itMax, N=0), d
+    if isinstance(w["Q"], np.ndarray):
+        d = {k: to_dev(w[k], dev) for k in ("Q", "Eu", "Ev", "La_d1")}
+    else:
+        d = {k: w[k] for k in ("Q", "Eu", "Ev", "La_d1")}
+    torch.cuda.synchronize()
+    return api.SimplexSolver(d["Q"], d["Q"], 0.05, d["Eu"], d["Ev"], d["La_d1"], None, rho=1.5, condMin=1e-2,
+                             difRcd=0.0, difTol=0.0, itMax=itMax), d
+
+
+def one_shot_host(name, w, pinned, itMax, backend=None):
+    """the reference-facing call with HOST buffers (e2e leg and CPU legs); returns iterations done"""
+    from cp_pfdr_graph_d1_b200 import api, DIAG
+    b = backend or api._b()
+    kind = WORKLOADS[name][0]
+    if kind == "quad":
+        pinned["X"][:] = 0
+        r = b.PFDR_graph_quadratic_d1_l1(pinned["X"], pinned["Ys"], pinned["La_l2"], pinned["Eu"], pinned["Ev"],
+                                         pinned["La_d1"], None, 0, DIAG, pinned["La_l2"], 1.5, 1e-3, 0.0, 0.0,
+                                         itMax, 0)
+    else:
+        pinned["P"][:] = pinned["Q"]
+        r = b.PFDR_graph_loss_d1_simplex(pinned["P"], pinned["Q"], 0.05, pinned["Eu"], pinned["Ev"], pinned["La_d1"],
+                                         None, 1.5, 1e-2, 0.0, 0.0, itMax)
+    return r.it
+
+
+def pin(w, name, use_cuda=True):
+    import torch
+    kind = WORKLOADS[name][0]
+    keys = ("Ys", "La_l2", "Eu", "Ev", "La_d1") if kind == "quad" else ("Q", "Eu", "Ev", "La_d1")
+    out = {}
+    for k in keys:
+        t = torch.from_numpy(np.ascontiguousarray(w[k]))
+        out[k] = (t.pin_memory() if use_cuda else t).numpy()
+    xk, like = ("X", out["Ys"]) if kind == "quad" else ("P", out["Q"])
+    t = torch.zeros(like.shape, dtype=torch.from_numpy(like).dtype)
+    out[xk] = (t.pin_memory() if use_cuda else t).numpy()
+    return out
+
+
+def cpu_reference_rate(name, w, seconds_target=12.0):
+    """edge-updates/s of the reference's own CPU implementation (oracle/_ref, all host cores) on a bounded
+    sample of the workload: two-point timing (itMax = a, b) removes the setup.  Falls back to the serial port."""
+    from oracle import oracle as O
+    ref = O.reference()
+    kind_label, be, cores = ("reference", ref, ref.lib.ref_num_procs()) if ref is not None else ("port", O.oracle(), 1)
+    pinned = pin(w, name, use_cuda=False)
+    E = int(w["E"])
+
+    def run(itmax):
+        t0 = time.perf_counter()
+        one_shot_host(name, w, pinned, itmax, backend=be)
+        return time.perf_counter() - t0
+
+    a = 2
+    ta = run(a)
+    per_it = max(ta / (a + 1), 1e-4)
+    b = int(max(a + 4, min(400, seconds_target / 2 / per_it)))
+    tb = min(run(b), run(b))
+    ta = min(ta, run(a))
+    rate = E * (b - a) / max(tb - ta, 1e-9)
+    return {"value": rate, "unit": "edge_updates/s", "cores": int(cores), "kind": kind_label,
+            "sample": f"{describe(name).split(',')[0]}: iterations {a}..{b} of the same problem (two-point timing, "
+                      f"setup removed), {1e3 * (tb - ta) / (b - a):.2f} ms/iteration"}
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    name = args.workload
+    kind, n, dt, K, iters = WORKLOADS[name]
+    if n > 128:                                      # the CPU arm runs the parity-sized instance of C4
+        name = "c4s_f32" if dt is np.float32 else "c4s_f64"
+    w = host_inputs(name)
+    per_step = []
+    cb = None
+    for i in range(args.warmup + args.steps):
+        cb = cpu_reference_rate(name, w, seconds_target=6.0)
+        if i >= args.warmup:
+            per_step.append(cb["value"])
+    val = float(np.mean(per_step))
+    E = int(w["E"])
+    cb["value"] = val
+    line = {"impl": "reference", "metric": "pfdr_edge_updates_per_s", "value": val, "unit": "edge_updates/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * E * WORKLOADS[name][4] / val, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32" if dt is np.float32 else "f64", "data": "synthetic",
+            "config": {"workload": describe(name), "V": int(w["V"]), "E": E}, "cpu_baseline": cb,
+            "e2e": {"value": val, "unit": "edge_updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="c2_f32", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--iters", type=int, default=0, help="override iterations per step")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        from cp_pfdr_graph_d1_b200 import dist_bench
+        return dist_bench.main(args)
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    from cp_pfdr_graph_d1_b200 import api
+    stream = torch.cuda.Stream(dev)
+    api.set_stream(stream.cuda_stream)
+
+    name = args.workload
+    kind, n, dt, K, iters = WORKLOADS[name]
+    iters = args.iters or iters
+    r = np.dtype(dt).itemsize
+    w = host_inputs(name) or device_inputs_c4(n, K, dt, dev)
+    V, E = int(w["V"]), int(w["E"])
+    B_iter = algorithmic_bytes(kind, V, E, r, K)
+    solver, keep = make_solver(name, w, dev, iters)
+    setup = dict(solver.setup_stats)
+
+    def step():
+        solver.reset()
+        return solver.run()
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    loop_ms = launches = its = 0
+    with ClockSampler(local) as clk:
+        with torch.cuda.stream(stream):
+            ev0.record(stream)
+            for _ in range(args.steps):
+                st = step()
+                loop_ms += st["loop_ms"]; launches += st["launches"]; its += st["iterations"]
+            ev1.record(stream)
+        torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    assert its == iters * args.steps, (its, iters, args.steps)
+    value = E * its / (ms * 1e-3)
+    peak, peak_src = peaks()
+    achieved = B_iter * its / (loop_ms * 1e-3) / 1e9
+    line = {
+        "metric": "pfdr_edge_updates_per_s", "value": value, "unit": "edge_updates/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32" if dt is np.float32 else "f64", "data": "synthetic",
+        "config": {"workload": describe(name), "V": V, "E": E, "K": K, "iterations_per_step": iters,
+                   "slots": setup["slots"], "us_per_iteration": 1e3 * loop_ms / its,
+                   "edge_label_updates_per_s": value * K,
+                   "l2": f"no flush: one iteration streams {B_iter / 1e6:.0f} MB algorithmic "
+                         f"({'>' if B_iter > 126e6 else '<'} 126 MB L2); steps re-run the same resident problem"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": measured_traffic(name), "peak_source": peak_src,
+                     "kernel": "quad_iter_kernel" if kind == "quad" else "simplex_iter_kernel",
+                     "algorithmic_bytes_per_launch": B_iter,
+                     "avg_launch_us": 1e3 * loop_ms / its},
+        "setup_ms_device_resident": setup["setup_ms"],
+    }
+    solver.close()
+    del keep
+    torch.cuda.empty_cache()
+
+    if not args.no_e2e and isinstance(w.get("Q", w.get("Y")), np.ndarray):
+        pinned = pin(w, name)
+        one_shot_host(name, w, pinned, iters)                    # warm-up (allocator, graphs)
+        torch.cuda.synchronize()
+        t_e2e, h2d, d2h, n_e2e = 0.0, 0, 0, max(2, min(args.steps, 5))
+        for _ in range(n_e2e):
+            t0 = time.perf_counter()
+            done = one_shot_host(name, w, pinned, iters)
+            torch.cuda.synchronize()
+            t_e2e += time.perf_counter() - t0
+            s = api.last_stats()
+            h2d, d2h = s["h2d_bytes"], s["d2h_bytes"]
+            assert done == iters
+        line["e2e"] = {"value": E * iters * n_e2e / t_e2e, "unit": "edge_updates/s", "h2d_bytes_per_step": int(h2d),
+                       "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * t_e2e / n_e2e,
+                       "what": "one-shot C-ABI call, pinned host buffers in, host iterate out"}
+    else:
+        line["e2e"] = None
+    line["clocks"] = clk.summary()
+    if not args.no_cpu:
+        wn = name if n <= 128 else ("c4s_f32" if dt is np.float32 else "c4s_f64")
+        line["cpu_baseline"] = cpu_reference_rate(wn, host_inputs(wn) if wn != name else w)
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -78,3 +78,104 @@ def last_stats():
     s = _lib.Stats()
     _lib.load().pfdr_b200_get_last_stats(s)
     return s.asdict()
+
+
+# ---------------------------------------------------------------------------------------------------
+# resident solver handles (include/pfdr_b200.h "resident solver handles")
+# ---------------------------------------------------------------------------------------------------
+import ctypes as _C
+
+from ._abi import _CT, _as_int, _as_real, _ptr, _real_dtype
+
+
+class _Solver:
+    """Inputs, half-edge layout and work arrays stay in HBM; reset()/run() are device-only."""
+
+    def __init__(self):
+        self._h = _C.c_void_p()
+        self._lib = _lib.load()
+        self._keep = []
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise PfdrError(f"libpfdr_b200 status {rc}: {self._lib.pfdr_b200_last_error().decode()}")
+
+    def reset(self):
+        self._chk(self._lib.pfdr_b200_solver_reset(self._h))
+
+    def run(self):
+        self._chk(self._lib.pfdr_b200_solver_run(self._h))
+        return last_stats()
+
+    def fetch(self, want_obj=False, want_dif=False):
+        R = _CT[self._dt][0]
+        X = np.zeros(self._shape, self._dt)
+        it = _C.c_int(0)
+        Obj = np.zeros(self._itMax + 1, self._dt) if want_obj else None
+        Dif = np.zeros(max(self._itMax, 1), self._dt) if want_dif else None
+        self._lib.pfdr_b200_solver_fetch.argtypes = [_C.c_void_p, _C.c_void_p, _C.POINTER(_C.c_int), _C.c_void_p, _C.c_void_p]
+        self._chk(self._lib.pfdr_b200_solver_fetch(self._h, X.ctypes.data, _C.byref(it),
+                                                   None if Obj is None else Obj.ctypes.data,
+                                                   None if Dif is None else Dif.ctypes.data))
+        n = it.value
+        return Result(X, n, None if Obj is None else Obj[:n + 1], None if Dif is None else Dif[:n])
+
+    def close(self):
+        if self._h:
+            self._lib.pfdr_b200_solver_destroy.argtypes = [_C.c_void_p]
+            self._lib.pfdr_b200_solver_destroy(self._h)
+            self._h = _C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class QuadraticSolver(_Solver):
+    """Handle on PFDR_graph_quadratic_d1_l1 (prox='l1') / _bounds (prox='bounds'); arrays may be numpy or
+    torch CUDA tensors (kept referenced by the handle, used in place)."""
+
+    def __init__(self, X0, Y, A, Eu, Ev, La_d1, La_l1=None, positivity=0, min=-np.inf, max=np.inf, prox="l1",
+                 Ltype=SCAL, L=None, rho=1.5, condMin=1e-3, difRcd=0.0, difTol=1e-5, itMax=1000, N=0,
+                 want_obj=False, want_dif=False):
+        super().__init__()
+        dt = _real_dtype(X0)
+        R, suf = _CT[dt]
+        P, PI = _C.POINTER(R), _C.POINTER(_C.c_int)
+        self._dt, self._shape, self._itMax = dt, (int(X0.shape[0]),), itMax
+        Y, A, La_d1, La_l1, L, X0 = (_as_real(a, dt) for a in (Y, A, La_d1, La_l1, L, X0))
+        Eu, Ev = _as_int(Eu), _as_int(Ev)
+        self._keep = [X0, Y, A, Eu, Ev, La_d1, La_l1, L]
+        f = getattr(self._lib, f"pfdr_b200_solver_create_quadratic_{suf}")
+        f.argtypes = [_C.POINTER(_C.c_void_p), _C.c_int, _C.c_int, _C.c_int, _C.c_int, P, P, P, PI, PI, P, P, _C.c_int,
+                      R, R, _C.c_int, P, R, R, R, R, _C.c_int, _C.c_int, _C.c_int]
+        self._chk(f(_C.byref(self._h), 0 if prox == "l1" else 1, int(X0.shape[0]), int(Eu.shape[0]), int(N),
+                    _ptr(X0, R), _ptr(Y, R), _ptr(A, R), _ptr(Eu, _C.c_int), _ptr(Ev, _C.c_int), _ptr(La_d1, R),
+                    _ptr(La_l1, R), int(positivity), float(min), float(max), int(Ltype), _ptr(L, R), rho, condMin,
+                    difRcd, difTol, itMax, int(want_obj), int(want_dif)))
+        self.setup_stats = last_stats()
+
+
+class SimplexSolver(_Solver):
+    """Handle on PFDR_graph_loss_d1_simplex; P0, Q are (V, K)."""
+
+    def __init__(self, P0, Q, al, Eu, Ev, La_d1, La_f=None, rho=1.5, condMin=1e-2, difRcd=0.0, difTol=1e-4,
+                 itMax=500, want_obj=False, want_dif=False):
+        super().__init__()
+        dt = _real_dtype(P0)
+        R, suf = _CT[dt]
+        P, PI = _C.POINTER(R), _C.POINTER(_C.c_int)
+        V, K = int(P0.shape[0]), int(P0.shape[1])
+        self._dt, self._shape, self._itMax = dt, (V, K), itMax
+        P0, Q, La_d1, La_f = (_as_real(a, dt) for a in (P0, Q, La_d1, La_f))
+        Eu, Ev = _as_int(Eu), _as_int(Ev)
+        self._keep = [P0, Q, Eu, Ev, La_d1, La_f]
+        f = getattr(self._lib, f"pfdr_b200_solver_create_simplex_{suf}")
+        f.argtypes = [_C.POINTER(_C.c_void_p), _C.c_int, _C.c_int, _C.c_int, R, P, P, P, PI, PI, P, R, R, R, R,
+                      _C.c_int, _C.c_int, _C.c_int]
+        self._chk(f(_C.byref(self._h), K, V, int(Eu.shape[0]), al, _ptr(La_f, R), _ptr(P0, R), _ptr(Q, R),
+                    _ptr(Eu, _C.c_int), _ptr(Ev, _C.c_int), _ptr(La_d1, R), rho, condMin, difRcd, difTol, itMax,
+                    int(want_obj), int(want_dif)))
+        self.setup_stats = last_stats()

@@ -124,4 +124,55 @@ int pfdr_b200_operator_norm_matrix_##SUF(int M, int N, const real *A, real nTol,
 SIMPLEX(f32, float)
 SIMPLEX(f64, double)
 
+/* ---- resident solver handles ---- */
+#define HANDLE(SUF, real)                                                                               \
+int pfdr_b200_solver_create_quadratic_##SUF(pfdr_b200_solver **out, int prox_kind, int V, int E, int N, \
+    const real *X0, const real *Y, const real *A, const int *Eu, const int *Ev, const real *La_d1,      \
+    const real *La_l1, int positivity, real lo, real hi, int Ltype, const real *L, real rho,            \
+    real condMin, real difRcd, real difTol, int itMax, int want_obj, int want_dif)                      \
+{                                                                                                       \
+    return guarded([&] {                                                                                \
+        PFDR_REQUIRE(out != nullptr, "solver_create: out must not be NULL");                            \
+        real *flag = reinterpret_cast<real *>(sizeof(real));   /* non-NULL marker, never dereferenced */\
+        QuadProblem<real> q{V, E, N, const_cast<real *>(X0), Y, A, Eu, Ev, La_d1,                       \
+                            prox_kind == 0 ? La_l1 : nullptr, prox_kind == 0 ? positivity : 0,          \
+                            prox_kind, lo, hi, Ltype, L, rho, condMin, difRcd, difTol, itMax, nullptr,  \
+                            want_obj ? flag : nullptr, want_dif ? flag : nullptr, 0};                   \
+        *out = reinterpret_cast<pfdr_b200_solver *>(make_quadratic<real>(q));                           \
+    });                                                                                                 \
+}                                                                                                       \
+int pfdr_b200_solver_create_simplex_##SUF(pfdr_b200_solver **out, int K, int V, int E, real al,         \
+    const real *La_f, const real *P0, const real *Q, const int *Eu, const int *Ev, const real *La_d1,   \
+    real rho, real condMin, real difRcd, real difTol, int itMax, int want_obj, int want_dif)            \
+{                                                                                                       \
+    return guarded([&] {                                                                                \
+        PFDR_REQUIRE(out != nullptr, "solver_create: out must not be NULL");                            \
+        real *flag = reinterpret_cast<real *>(sizeof(real));                                            \
+        SimplexProblem<real> q{K, V, E, al, La_f, const_cast<real *>(P0), Q, Eu, Ev, La_d1, rho,        \
+                               condMin, difRcd, difTol, itMax, nullptr, want_obj ? flag : nullptr,      \
+                               want_dif ? flag : nullptr, 0};                                           \
+        *out = reinterpret_cast<pfdr_b200_solver *>(make_simplex<real>(q));                             \
+    });                                                                                                 \
+}
+
+HANDLE(f32, float)
+HANDLE(f64, double)
+
+int pfdr_b200_solver_reset(pfdr_b200_solver *s)
+{
+    return guarded([&] { PFDR_REQUIRE(s, "NULL solver"); reinterpret_cast<SolverBase *>(s)->reset(); });
+}
+int pfdr_b200_solver_run(pfdr_b200_solver *s)
+{
+    return guarded([&] { PFDR_REQUIRE(s, "NULL solver"); reinterpret_cast<SolverBase *>(s)->run(); });
+}
+int pfdr_b200_solver_fetch(pfdr_b200_solver *s, void *X, int *it, void *Obj, void *Dif)
+{
+    return guarded([&] { PFDR_REQUIRE(s, "NULL solver"); reinterpret_cast<SolverBase *>(s)->fetch(X, it, Obj, Dif); });
+}
+int pfdr_b200_solver_destroy(pfdr_b200_solver *s)
+{
+    return guarded([&] { delete reinterpret_cast<SolverBase *>(s); });
+}
+
 }  // extern "C"

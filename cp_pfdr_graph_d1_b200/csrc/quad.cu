@@ -522,8 +522,9 @@ __global__ void __launch_bounds__(256) atr_kernel(QP<real> p, int GL, int mode)
 // host side
 // ---------------------------------------------------------------------------------------------
 template <typename real>
-struct QuadSolver {
-    const QuadProblem<real> &q;
+struct QuadSolver : SolverBase {
+    const QuadProblem<real> q;
+    bool keep_x0 = false;
     SellGraph g;
     QP<real> p{};
     DevBuf<Ctl> ctl;
@@ -539,8 +540,8 @@ struct QuadSolver {
     int vec = 1, TX = 1, GL = 1, vgrid = 0;
     size_t ax_smem = 0;
 
-    explicit QuadSolver(const QuadProblem<real> &q_) : q(q_) {}
-    ~QuadSolver()
+    QuadSolver(const QuadProblem<real> &q_, bool keep) : q(q_), keep_x0(keep) {}
+    ~QuadSolver() override
     {
         if (gexec) cudaGraphExecDestroy(gexec);
         if (hctl) cudaFreeHost(hctl);
@@ -610,6 +611,18 @@ struct QuadSolver {
         partial.alloc((size_t) maxgrid * 4);
         p.partial = partial.p;
 
+        reset();
+        if (!keep_x0) X0.own.release();
+        PFDR_CUDA(cudaEventRecord(ev_b, st));
+    }
+
+    // initial iterate, edge copies, first preconditioning and control block: device work only
+    void reset() override
+    {
+        cudaStream_t st = ctx().stream;
+        PFDR_REQUIRE(X0.p != nullptr, "reset: the initial iterate was not kept on the device");
+        if (gexec && p.thc) { cudaGraphExecDestroy(gexec); gexec = nullptr; }
+        p.thc = nullptr;
         // control block (ref :286-292, :339-343)
         Ctl h{};
         const real tol2 = q.difTol * q.difTol, rcd2 = q.difRcd * q.difRcd;
@@ -620,16 +633,15 @@ struct QuadSolver {
         h.eps = (double) (((real) 0 < q.difTol && q.difTol < real_eps<real>()) ? q.difTol : real_eps<real>());
         hctl[0] = h;
         PFDR_CUDA(cudaMemcpyAsync(ctl.p, &hctl[0], sizeof(Ctl), cudaMemcpyHostToDevice, st));
-
         // first preconditioning
-        if (N > 0) launch_atr(1);
+        if (q.N > 0) launch_atr(1);
         PFDR_LAUNCH(amp_kernel<real>, vgrid, 256, 0, p, 0);
         PFDR_LAUNCH(init_vertex_kernel<real>, vgrid, 256, 0, p, X0.p);
+        PFDR_CUDA(cudaMemcpyAsync(&hctl[1], ctl.p, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
         PFDR_CUDA(cudaStreamSynchronize(st));
-        double amp; PFDR_CUDA(cudaMemcpy(&amp, &ctl.p->amp, sizeof(double), cudaMemcpyDeviceToHost));
-        p.thc0 = (real) 1 / (real) amp;        // La_d1 / (c La_d1)
-        X0.own.release();
-        PFDR_CUDA(cudaEventRecord(ev_b, st));
+        const real thc0 = (real) 1 / (real) hctl[1].amp;       // La_d1 / (c La_d1)
+        if (gexec && thc0 != p.thc0) { cudaGraphExecDestroy(gexec); gexec = nullptr; }
+        p.thc0 = thc0;
     }
 
     void launch_atr(int mode)
@@ -703,7 +715,7 @@ struct QuadSolver {
         PFDR_LAUNCH(resume_kernel<real>, 1, 1, 0, p, 0.01);                   // ref :458
     }
 
-    void run()
+    void run() override
     {
         cudaStream_t st = ctx().stream;
         // batch: enough trips per host round trip to hide it, small enough to bound the no-op tail
@@ -747,23 +759,28 @@ struct QuadSolver {
         return h.state == ST_FINAL ? 1 : (h.state == ST_RECOND ? 2 : 0);
     }
 
-    void finish()
+    void fetch(void *Xo, int *ito, void *Objo, void *Difo) override
     {
         cudaStream_t st = ctx().stream;
-        Ctl h;
         PFDR_CUDA(cudaMemcpyAsync(&hctl[0], ctl.p, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
         PFDR_CUDA(cudaStreamSynchronize(st));
-        h = hctl[0];
-        Xout.alloc(q.V);
-        PFDR_LAUNCH(extract_x_kernel<real>, vgrid, 256, 0, p, Xout.p);
-        copy_out(q.X, Xout.p, q.V);
-        if (q.Obj) copy_out(q.Obj, dObj.p, (size_t) h.it + 1);
-        if (q.Dif && h.it > 0) copy_out(q.Dif, dDif.p, (size_t) h.it);
+        const Ctl h = hctl[0];
+        if (Xo) {
+            if (is_device_ptr(Xo)) PFDR_LAUNCH(extract_x_kernel<real>, vgrid, 256, 0, p, (real *) Xo);
+            else {
+                Xout.alloc(q.V);
+                PFDR_LAUNCH(extract_x_kernel<real>, vgrid, 256, 0, p, Xout.p);
+                copy_out((real *) Xo, Xout.p, q.V);
+            }
+        }
+        if (Objo && dObj.p) copy_out((real *) Objo, dObj.p, (size_t) h.it + 1);
+        if (Difo && dDif.p && h.it > 0) copy_out((real *) Difo, dDif.p, (size_t) h.it);
         PFDR_CUDA(cudaStreamSynchronize(st));
-        if (q.it) *q.it = h.it;
+        if (ito) *ito = h.it;
         float ms = 0;
-        cudaEventElapsedTime(&ms, ev_a, ev_b); ctx().stats.setup_ms = ms;
-        cudaEventElapsedTime(&ms, ev_b, ev_c); ctx().stats.loop_ms = ms;
+        if (cudaEventElapsedTime(&ms, ev_a, ev_b) == cudaSuccess) ctx().stats.setup_ms = ms;
+        if (cudaEventElapsedTime(&ms, ev_b, ev_c) == cudaSuccess) ctx().stats.loop_ms = ms;
+        cudaGetLastError();
         ctx().stats.iterations = h.it;
         if (q.verbose) {
             printf("PFDR (B200): %d iterations (max. %d), iterate evolution %g, loop %.3f ms\n", h.it, q.itMax,
@@ -774,12 +791,22 @@ struct QuadSolver {
 };
 
 template <typename real>
+SolverBase *make_quadratic(const QuadProblem<real> &q)
+{
+    QuadSolver<real> *s = new QuadSolver<real>(q, true);
+    try { s->setup(); } catch (...) { delete s; throw; }
+    return s;
+}
+template SolverBase *make_quadratic<float>(const QuadProblem<float> &);
+template SolverBase *make_quadratic<double>(const QuadProblem<double> &);
+
+template <typename real>
 void solve_quadratic(const QuadProblem<real> &q)
 {
-    QuadSolver<real> s(q);
+    QuadSolver<real> s(q, false);
     s.setup();
     s.run();
-    s.finish();
+    s.fetch(q.X, q.it, q.Obj, q.Dif);
 }
 
 template void solve_quadratic<float>(const QuadProblem<float> &);

@@ -367,8 +367,9 @@ __global__ void simplex_extract_kernel(SP<real> p, real *__restrict__ out)
 // host side
 // ---------------------------------------------------------------------------------------------
 template <typename real>
-struct SimplexSolver {
-    const SimplexProblem<real> &q;
+struct SimplexSolver : SolverBase {
+    const SimplexProblem<real> q;
+    bool keep_p0 = false;
     SellGraph g;
     SP<real> p{};
     DevBuf<Ctl> ctl;
@@ -383,8 +384,8 @@ struct SimplexSolver {
     cudaGraphExec_t gexec = nullptr;
     int graph_trips = 0, grid = 0;
 
-    explicit SimplexSolver(const SimplexProblem<real> &q_) : q(q_) {}
-    ~SimplexSolver()
+    SimplexSolver(const SimplexProblem<real> &q_, bool keep) : q(q_), keep_p0(keep) {}
+    ~SimplexSolver() override
     {
         if (gexec) cudaGraphExecDestroy(gexec);
         if (hctl) cudaFreeHost(hctl);
@@ -433,6 +434,17 @@ struct SimplexSolver {
         p.Q = Q.p; p.La_f = La_f.p; p.La_d1 = La_d1.p; p.Eu = Eu.p; p.Ev = Ev.p;
         p.partial = partial.p; p.dObj = dObj.p; p.dDif = dDif.p;
 
+        reset();
+        if (!keep_p0) P0.own.release();
+        PFDR_CUDA(cudaEventRecord(ev_b, st));
+    }
+
+    void reset() override
+    {
+        cudaStream_t st = ctx().stream;
+        PFDR_REQUIRE(P0.p != nullptr, "reset: the initial iterate was not kept on the device");
+        if (gexec && p.wk) { cudaGraphExecDestroy(gexec); gexec = nullptr; }
+        p.wk = nullptr; p.thk = nullptr;
         Ctl h{};                                                                                  // ref :445-446
         h.it = 0; h.state = (q.itMax == 0) ? ST_FINAL : ST_RUN; h.itMax = q.itMax;
         h.track = (q.difTol > (real) 0 || q.difRcd > (real) 0 || q.Dif != nullptr);
@@ -442,8 +454,6 @@ struct SimplexSolver {
         PFDR_CUDA(cudaMemcpyAsync(ctl.p, &hctl[0], sizeof(Ctl), cudaMemcpyHostToDevice, st));
         PFDR_LAUNCH(simplex_precond_kernel<real>, grid, 256, 0, p, P0.p, 0);
         PFDR_CUDA(cudaStreamSynchronize(st));
-        P0.own.release();
-        PFDR_CUDA(cudaEventRecord(ev_b, st));
     }
 
     void enqueue_trip()
@@ -500,7 +510,7 @@ struct SimplexSolver {
         return h.state == ST_FINAL ? 1 : (h.state == ST_RECOND ? 2 : 0);
     }
 
-    void run()
+    void run() override
     {
         cudaStream_t st = ctx().stream;
         const size_t work = (size_t) g.nslots * q.K;
@@ -532,27 +542,29 @@ struct SimplexSolver {
         ctx().in_loop = false;
     }
 
-    void finish()
+    void fetch(void *Po, int *ito, void *Objo, void *Difo) override
     {
         cudaStream_t st = ctx().stream;
         PFDR_CUDA(cudaMemcpyAsync(&hctl[0], ctl.p, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
         PFDR_CUDA(cudaStreamSynchronize(st));
         const Ctl h = hctl[0];
         const size_t VK = (size_t) q.V * q.K;
-        if (is_device_ptr(q.P)) {
-            PFDR_LAUNCH(simplex_extract_kernel<real>, cdiv(VK, 256), 256, 0, p, q.P);
-        } else {
-            Pout.alloc(VK);
-            PFDR_LAUNCH(simplex_extract_kernel<real>, cdiv(VK, 256), 256, 0, p, Pout.p);
-            copy_out(q.P, Pout.p, VK);
+        if (Po) {
+            if (is_device_ptr(Po)) PFDR_LAUNCH(simplex_extract_kernel<real>, cdiv(VK, 256), 256, 0, p, (real *) Po);
+            else {
+                Pout.alloc(VK);
+                PFDR_LAUNCH(simplex_extract_kernel<real>, cdiv(VK, 256), 256, 0, p, Pout.p);
+                copy_out((real *) Po, Pout.p, VK);
+            }
         }
-        if (q.Obj) copy_out(q.Obj, dObj.p, (size_t) h.it + 1);
-        if (q.Dif && h.it > 0) copy_out(q.Dif, dDif.p, (size_t) h.it);
+        if (Objo && dObj.p) copy_out((real *) Objo, dObj.p, (size_t) h.it + 1);
+        if (Difo && dDif.p && h.it > 0) copy_out((real *) Difo, dDif.p, (size_t) h.it);
         PFDR_CUDA(cudaStreamSynchronize(st));
-        if (q.it) *q.it = h.it;
+        if (ito) *ito = h.it;
         float ms = 0;
-        cudaEventElapsedTime(&ms, ev_a, ev_b); ctx().stats.setup_ms = ms;
-        cudaEventElapsedTime(&ms, ev_b, ev_c); ctx().stats.loop_ms = ms;
+        if (cudaEventElapsedTime(&ms, ev_a, ev_b) == cudaSuccess) ctx().stats.setup_ms = ms;
+        if (cudaEventElapsedTime(&ms, ev_b, ev_c) == cudaSuccess) ctx().stats.loop_ms = ms;
+        cudaGetLastError();
         ctx().stats.iterations = h.it;
         if (q.verbose) {
             printf("PFDR simplex (B200): %d iterations (max. %d), evolution %g, loop %.3f ms\n", h.it, q.itMax, h.dif,
@@ -563,12 +575,22 @@ struct SimplexSolver {
 };
 
 template <typename real>
+SolverBase *make_simplex(const SimplexProblem<real> &q)
+{
+    SimplexSolver<real> *s = new SimplexSolver<real>(q, true);
+    try { s->setup(); } catch (...) { delete s; throw; }
+    return s;
+}
+template SolverBase *make_simplex<float>(const SimplexProblem<float> &);
+template SolverBase *make_simplex<double>(const SimplexProblem<double> &);
+
+template <typename real>
 void solve_simplex(const SimplexProblem<real> &q)
 {
-    SimplexSolver<real> s(q);
+    SimplexSolver<real> s(q, false);
     s.setup();
     s.run();
-    s.finish();
+    s.fetch(q.P, q.it, q.Obj, q.Dif);
 }
 template void solve_simplex<float>(const SimplexProblem<float> &);
 template void solve_simplex<double>(const SimplexProblem<double> &);

@@ -14,6 +14,16 @@ struct QuadProblem {
     int Ltype; const real *L; real rho, condMin, difRcd, difTol;
     int itMax; int *it; real *Obj, *Dif; int verbose;
 };
+
+// A solver resident on the device: layout + preconditioner built once, then reset()/run() any number
+// of times (the handle API of include/pfdr_b200.h; the one-shot entry points are create+run+fetch).
+struct SolverBase {
+    virtual ~SolverBase() {}
+    virtual void reset() = 0;                                   // back to the initial iterate (device only)
+    virtual void run() = 0;                                     // iterate until the stopping rule fires
+    virtual void fetch(void *X, int *it, void *Obj, void *Dif) = 0;
+};
+template <typename real> SolverBase *make_quadratic(const QuadProblem<real> &q);
 template <typename real> void solve_quadratic(const QuadProblem<real> &q);
 
 // arguments of PFDR_graph_loss_d1_simplex<real> (reference include/PFDR_graph_loss_d1_simplex.hpp:24-30)
@@ -22,6 +32,7 @@ struct SimplexProblem {
     int K, V, E; real al; const real *La_f; real *P; const real *Q; const int *Eu, *Ev; const real *La_d1;
     real rho, condMin, difRcd, difTol; int itMax; int *it; real *Obj, *Dif; int verbose;
 };
+template <typename real> SolverBase *make_simplex(const SimplexProblem<real> &q);
 template <typename real> void solve_simplex(const SimplexProblem<real> &q);
 
 template <typename real> void proj_simplex_metric(real *X, const real *M, int D, int N, int nm, const real *A, int na);

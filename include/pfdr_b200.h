@@ -86,6 +86,33 @@ int pfdr_b200_operator_norm_matrix_f32(int M, int N, const float *A, float nTol,
 int pfdr_b200_operator_norm_matrix_f64(int M, int N, const double *A, double nTol, int itMax, int nbInit,
                                        int verbose, double *result);
 
+/* ---- resident solver handles (no counterpart in the reference) --------------------------------
+ * The one-shot entry points above are create + run + fetch + destroy.  A handle keeps the inputs,
+ * the half-edge layout and all work arrays in HBM so that a caller (a benchmark, or a cut-pursuit
+ * loop re-solving on one graph) can reset()/run() repeatedly without touching the host.
+ * create: same arguments as the one-shot call; prox_kind 0 = l1 (+positivity), 1 = box [lo, hi];
+ * want_obj / want_dif select whether the per-iteration records are kept.  fetch: any pointer may be
+ * NULL; Obj needs it+1 entries, Dif it. */
+typedef struct pfdr_b200_solver pfdr_b200_solver;
+int pfdr_b200_solver_create_quadratic_f32(pfdr_b200_solver **out, int prox_kind, int V, int E, int N,
+    const float *X0, const float *Y, const float *A, const int *Eu, const int *Ev, const float *La_d1,
+    const float *La_l1, int positivity, float lo, float hi, int Ltype, const float *L, float rho,
+    float condMin, float difRcd, float difTol, int itMax, int want_obj, int want_dif);
+int pfdr_b200_solver_create_quadratic_f64(pfdr_b200_solver **out, int prox_kind, int V, int E, int N,
+    const double *X0, const double *Y, const double *A, const int *Eu, const int *Ev, const double *La_d1,
+    const double *La_l1, int positivity, double lo, double hi, int Ltype, const double *L, double rho,
+    double condMin, double difRcd, double difTol, int itMax, int want_obj, int want_dif);
+int pfdr_b200_solver_create_simplex_f32(pfdr_b200_solver **out, int K, int V, int E, float al,
+    const float *La_f, const float *P0, const float *Q, const int *Eu, const int *Ev, const float *La_d1,
+    float rho, float condMin, float difRcd, float difTol, int itMax, int want_obj, int want_dif);
+int pfdr_b200_solver_create_simplex_f64(pfdr_b200_solver **out, int K, int V, int E, double al,
+    const double *La_f, const double *P0, const double *Q, const int *Eu, const int *Ev, const double *La_d1,
+    double rho, double condMin, double difRcd, double difTol, int itMax, int want_obj, int want_dif);
+int pfdr_b200_solver_reset(pfdr_b200_solver *s);   /* back to the initial iterate + first preconditioning */
+int pfdr_b200_solver_run(pfdr_b200_solver *s);     /* iterate until the stopping rule fires (<= itMax)    */
+int pfdr_b200_solver_fetch(pfdr_b200_solver *s, void *X, int *it, void *Obj, void *Dif);
+int pfdr_b200_solver_destroy(pfdr_b200_solver *s);
+
 /* ---- run-time controls and introspection (no counterpart in the reference) ----------------- */
 const char *pfdr_b200_last_error(void);      /* message of the last non-zero status (thread local) */
 int pfdr_b200_version(void);

@@ -32,8 +32,9 @@ def test_quadratic_parity(gpu_api, oracle, name, dtype):
             np.abs(got.Obj[:n + 1] - ref.Obj[:n + 1]).max()
     if ref.Dif is not None and n:
         assert got.Dif.shape[0] == got.it
-        m = max(1, n // 2) if dtype is np.float32 else n
-        assert np.allclose(got.Dif[:m], ref.Dif[:m], rtol=5e-2 if dtype is np.float32 else 1e-4, atol=1e-14)
+        # compare the evolution record above the rounding floor of the type (it is a squared relative change)
+        sel = ref.Dif[:n] > (1e-9 if dtype is np.float32 else 1e-24)
+        assert np.allclose(got.Dif[:n][sel], ref.Dif[:n][sel], rtol=5e-2 if dtype is np.float32 else 1e-4)
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
@@ -77,3 +78,21 @@ def test_bad_edges_rejected(gpu_api):
     args[3][5] = 10 ** 7
     with pytest.raises(PfdrError):
         _b().PFDR_graph_quadratic_d1_l1(*args, **kw)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_resident_handle_matches_one_shot(gpu_api, dtype):
+    """create + (reset, run) x 2 + fetch == the one-shot entry point, bit for bit"""
+    fam, args, kw = problems.quad_case("grid_diag_l1_pos", dtype)
+    ref = problems.run_quad(gpu_api._b(), "grid_diag_l1_pos", dtype)
+    X0, Y, A, Eu, Ev, La_d1, La_l1, pos, Ltype, L = args
+    s = gpu_api.QuadraticSolver(X0, Y, A, Eu, Ev, La_d1, La_l1, pos, Ltype=Ltype, L=L, rho=kw["rho"],
+                                condMin=kw["condMin"], difRcd=kw["difRcd"], difTol=kw["difTol"], itMax=kw["itMax"],
+                                N=0, want_obj=True, want_dif=True)
+    for _ in range(2):
+        s.reset()
+        st = s.run()
+        r = s.fetch(want_obj=True, want_dif=True)
+        assert r.it == ref.it == st["iterations"]
+        assert np.array_equal(r.X, ref.X) and np.array_equal(r.Obj, ref.Obj) and np.array_equal(r.Dif, ref.Dif)
+    s.close()

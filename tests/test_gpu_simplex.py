@@ -82,3 +82,17 @@ def test_simplex_rejects_bad_args(gpu_api):
     args[2] = 1.5
     with pytest.raises(PfdrError):
         _b().PFDR_graph_loss_d1_simplex(*args, **kw)
+
+
+def test_resident_simplex_handle(gpu_api):
+    args, kw = problems.simplex_case("kla_k16", np.float32)
+    ref = problems.run_simplex(gpu_api._b(), "kla_k16", np.float32)
+    P0, Q, al, Eu, Ev, La_d1 = args
+    s = gpu_api.SimplexSolver(P0, Q, al, Eu, Ev, La_d1, rho=kw["rho"], condMin=kw["condMin"], difRcd=kw["difRcd"],
+                              difTol=kw["difTol"], itMax=kw["itMax"], want_obj=True, want_dif=True)
+    for _ in range(2):
+        s.reset()
+        s.run()
+        r = s.fetch(want_obj=True, want_dif=True)
+        assert r.it == ref.it and np.array_equal(r.X, ref.X) and np.array_equal(r.Obj, ref.Obj)
+    s.close()
