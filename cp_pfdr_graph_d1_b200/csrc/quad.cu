@@ -746,8 +746,13 @@ struct QuadSolver : SolverBase {
                 throw Error(PFDR_B200_ERR_CUDA, "PFDR loop did not terminate on the device");
         }
         PFDR_CUDA(cudaEventRecord(ev_c, st));
+        PFDR_CUDA(cudaMemcpyAsync(&hctl[0], ctl.p, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
         PFDR_CUDA(cudaStreamSynchronize(st));
         ctx().in_loop = false;
+        float ms = 0;
+        PFDR_CUDA(cudaEventElapsedTime(&ms, ev_b, ev_c));
+        ctx().stats.loop_ms = ms;
+        ctx().stats.iterations = hctl[0].it;
     }
 
     // waits for batch slot b: 0 = still running, 1 = finished, 2 = frozen for a reconditioning
