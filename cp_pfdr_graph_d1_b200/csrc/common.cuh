@@ -154,6 +154,18 @@ struct Ctl {
 
 __device__ __forceinline__ int ld_flag(const int *p) { return *((const volatile int *) p); }
 
+// One thread per CTA reads the control block and broadcasts it through shared memory: a million
+// threads polling the same L2 sector cost ~20 us per launch (measured, profiles/r01_notes.md).
+struct CtlView { int hold, state, it; };
+__device__ __forceinline__ CtlView load_ctl(const Ctl *ctl)
+{
+    __shared__ int s_ctl[3];
+    if (threadIdx.x == 0) { s_ctl[0] = ld_flag(&ctl->hold); s_ctl[1] = ld_flag(&ctl->state); s_ctl[2] = ld_flag(&ctl->it); }
+    __syncthreads();
+    CtlView v; v.hold = s_ctl[0]; v.state = s_ctl[1]; v.it = s_ctl[2];
+    return v;
+}
+
 // ---------------------------------------------------------------------------------------------
 // deterministic block reduction (fixed shuffle tree + fixed order over warps)
 // ---------------------------------------------------------------------------------------------
@@ -182,6 +194,18 @@ __device__ __forceinline__ void block_sum(double (&v)[NV], double *smem /* >= NV
         double t = (lane < nw) ? smem[i * 32 + lane] : 0.0;
         v[i] = warp_sum(t);
     }
+}
+
+// reciprocal for the recomputed edge constants: ~1 ulp (f32 MUFU.RCP; f64 MUFU.RCP64H + 2 Newton steps),
+// instead of the ~10 / ~25 instruction IEEE division sequences
+__device__ __forceinline__ float fast_rcp(float x) { return __fdividef(1.0f, x); }
+__device__ __forceinline__ double fast_rcp(double x)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = r * (2.0 - x * r);
+    r = r * (2.0 - x * r);
+    return r;
 }
 
 template <typename real> struct Pair;

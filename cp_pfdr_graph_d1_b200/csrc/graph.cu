@@ -96,6 +96,14 @@ void build_sell(SellGraph &g, const int *dEu, const int *dEv, int V, int E, int 
     PFDR_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, sl.p, g.slice_off.p, g.nslices + 1, st));
     ctx().stats.launches += 2;
 
+    // widest slice = max degree
+    DevBuf<int> dmax(1);
+    size_t tmp4 = 0;
+    PFDR_CUDA(cub::DeviceReduce::Max(nullptr, tmp4, g.deg.p, dmax.p, V, st));
+    DevBuf<unsigned char> tmpm(tmp4 + 16);
+    PFDR_CUDA(cub::DeviceReduce::Max(tmpm.p, tmp4, g.deg.p, dmax.p, V, st));
+    ctx().stats.launches += 1;
+    PFDR_CUDA(cudaMemcpyAsync(&g.max_width, dmax.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     long long nslots = 0; int hbad = 0;
     PFDR_CUDA(cudaMemcpyAsync(&nslots, g.slice_off.p + g.nslices, sizeof(long long), cudaMemcpyDeviceToHost, st));
     PFDR_CUDA(cudaMemcpyAsync(&hbad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, st));

@@ -21,6 +21,7 @@ struct SellGraph {
     int V = 0, E = 0, C = 32;
     int nslices = 0;
     long long nslots = 0;
+    int max_width = 0;             // widest slice (rows)
     DevBuf<long long> slice_off;   // [nslices+1] slot offset of each slice
     DevBuf<int> nbr;               // [nslots] vertex at the other end (-1: padding)
     DevBuf<int> twin;              // [nslots] slot of the opposite half-edge

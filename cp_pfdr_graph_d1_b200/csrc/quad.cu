@@ -33,8 +33,9 @@ struct QP {                       // kernel parameter block
     real *thc;                    // [slots] La_d1/w after a reconditioning (NULL: thc0 for all)
     real thc0;
     real *Z0, *Z1;                // [slots] edge copies, ping/pong by iteration parity
-    pair_t<real> *XP0, *XP1;      // [V] (x, forward point 2x - Ga.grad), ping/pong
-    real *Xc;                     // [V] compact copy of the iterate (dense operators only)
+    real *X0, *X1;                // [V] iterate, ping/pong by iteration parity
+    real *P0, *P1;                // [V] forward point 2x - Ga.grad(x), ping/pong (the only vertex value a
+                                  //     neighbour gathers, hence stored apart from x)
     real *T, *Sinv, *Ga, *Ga0, *G, *Thl1, *R, *AtY;
     const real *Y, *A, *La_d1, *La_l1, *L;
     const int *Eu, *Ev;
@@ -102,8 +103,7 @@ __global__ void __launch_bounds__(256) amp_kernel(QP<real> p, int recond)
     if (v < p.V) {
         real a;
         if (recond) {
-            const pair_t<real> *XP = (ld_flag(&p.ctl->it) & 1) ? p.XP1 : p.XP0;
-            a = XP[v].x;
+            a = ((p.ctl->it & 1) ? p.X1 : p.X0)[v];
         } else {
             real g0;
             if (p.N > 0) { g0 = p.Ga0[v]; a = p.AtY[v] / g0; }           // colstats filled Ga0, AtY
@@ -159,10 +159,8 @@ __global__ void __launch_bounds__(256) init_vertex_kernel(QP<real> p, const real
     ga = clamp_metric(p, v, (real) 1 / ga);
     p.Ga[v] = ga; p.Sinv[v] = (real) 1 / S; p.T[v] = ga * S;
     if (p.La_l1) p.Thl1[v] = ga * p.La_l1[v];
-    pair_t<real> xp; xp.x = x;
-    xp.y = (p.N == 0) ? (real) 2 * x - ga * grad_at(p, v, x) : (real) 0;
-    p.XP0[v] = xp;
-    if (p.Xc) p.Xc[v] = x;
+    p.X0[v] = x;
+    p.P0[v] = (p.N == 0) ? (real) 2 * x - ga * grad_at(p, v, x) : (real) 0;
 }
 
 // reconditioning, everything that is local to a vertex row in one kernel (ref :89-99, :167-250):
@@ -173,10 +171,10 @@ __global__ void __launch_bounds__(256) recond_vertex_kernel(QP<real> p)
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= p.V) return;
     const int cur = p.ctl->it & 1;
-    const pair_t<real> *XP = cur ? p.XP1 : p.XP0;
+    const real *X = cur ? p.X1 : p.X0;
     real *Z = cur ? p.Z1 : p.Z0;
     real c = (real) p.ctl->amp;
-    const real x = XP[v].x, g = grad_at(p, v, x);
+    const real x = X[v], g = grad_at(p, v, x);
     const real ga_old = p.Ga[v], sinv_old = p.Sinv[v];
     const int lane = v & 31;
     const long long base = p.slice_off[v >> 5];
@@ -188,7 +186,7 @@ __global__ void __launch_bounds__(256) recond_vertex_kernel(QP<real> p)
         if (n >= 0) {
             const real Wold = p.w[s] * sinv_old;
             Z[s] = (Wold / ga_old) * (x - ga_old * g - Z[s]);                 // ref :96-97
-            const real xn = XP[n].x;
+            const real xn = X[n];
             real a = rabs(x), b = rabs(xn), d = rabs(x - xn);                   // ref :172-186
             if (a < b) a = b;
             if (a < c) a = c;
@@ -213,8 +211,7 @@ __global__ void __launch_bounds__(256) recond_vertex_kernel(QP<real> p)
         const long long s = base + (long long) j * 32 + lane;
         if (p.nbr[s] >= 0) Z[s] = x - ga * (g + Z[s] / (p.w[s] * sinv));        // ref :247-248
     }
-    pair_t<real> xp; xp.x = x; xp.y = (real) 2 * x - ga * g;
-    (cur ? p.XP1 : p.XP0)[v] = xp;
+    (cur ? p.P1 : p.P0)[v] = (real) 2 * x - ga * g;
 }
 
 template <typename real>
@@ -226,24 +223,31 @@ __global__ void resume_kernel(QP<real> p, double rcd_factor)
 // ---------------------------------------------------------------------------------------------
 // the fused iteration kernel
 // ---------------------------------------------------------------------------------------------
-template <typename real, bool PER_SLOT_TH>
+// U half-edge rows of the vertex are in flight at once: first every index / weight / own-copy load of the
+// chunk is issued, then every gather (neighbour forward point, neighbour T, twin copy), then the arithmetic.
+// (v0 of this kernel kept 2 rows in flight and sat at 27 warps stalled on the scoreboard per issue.)
+template <typename real, bool PER_SLOT_TH, int U>
 __global__ void __launch_bounds__(256) quad_iter_kernel(QP<real> p)
 {
     __shared__ double smem[64];
     Ctl *ctl = p.ctl;
-    {
-        const int hold = ld_flag(&ctl->hold), state = ld_flag(&ctl->state);
-        if (hold != 0 || state != ST_RUN) {
-            if (hold == 0 && blockIdx.x == 0 && threadIdx.x == 0) ctl->hold = 1;
-            return;
-        }
+    const CtlView cv = load_ctl(ctl);
+    if (cv.hold != 0 || cv.state != ST_RUN) {
+        if (cv.hold == 0 && blockIdx.x == 0 && threadIdx.x == 0) ctl->hold = 1;
+        return;
     }
-    const int it = ld_flag(&ctl->it);
+    const int it = cv.it;
     const int cur = it & 1;
     const real *__restrict__ Zin = cur ? p.Z1 : p.Z0;
     real *__restrict__ Zout = cur ? p.Z0 : p.Z1;
-    const pair_t<real> *__restrict__ XPc = cur ? p.XP1 : p.XP0;
-    pair_t<real> *__restrict__ XPn = cur ? p.XP0 : p.XP1;
+    const real *__restrict__ Xc = cur ? p.X1 : p.X0;
+    const real *__restrict__ Pc = cur ? p.P1 : p.P0;
+    real *__restrict__ Xn = cur ? p.X0 : p.X1;
+    real *__restrict__ Pn = cur ? p.P0 : p.P1;
+    const real *__restrict__ Tg = p.T;
+    const int *__restrict__ nbr = p.nbr;
+    const int *__restrict__ twin = p.twin;
+    const real *__restrict__ wg = p.w;
     const real rho = p.rho;
 
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
@@ -252,31 +256,45 @@ __global__ void __launch_bounds__(256) quad_iter_kernel(QP<real> p)
         const int lane = v & 31;
         const long long base = p.slice_off[v >> 5];
         const int width = (int) ((p.slice_off[(v >> 5) + 1] - base) >> 5);
-        const pair_t<real> xp = XPc[v];
-        const real Tv = p.T[v], Sv = p.Sinv[v];
+        const int s0 = (int) base + lane;
+        const real xo = Xc[v], po_v = Pc[v];
+        const real Tv = Tg[v], Sv = p.Sinv[v];
         real acc = 0;
-#pragma unroll 2
-        for (int j = 0; j < width; j++) {
-            const long long s = base + (long long) j * 32 + lane;
-            const int n = p.nbr[s];
-            if (n >= 0) {
-                const int tw = p.twin[s];
-                const real wv = p.w[s], zo = Zin[s];
-                const pair_t<real> xn = XPc[n];
-                const real Tn = p.T[n], zt = Zin[tw];
-                const real tsum = Tv + Tn;
-                const real th = (PER_SLOT_TH ? p.thc[s] : p.thc0) * tsum;       // Th_d1
-                const real inv = (real) 1 / tsum;
-                const real wo = Tn * inv, wt = Tv * inv;                          // W_d1 own / twin side
-                const real po = xp.y - zo, pt = xn.y - zt;
-                const real a = wo * po + wt * pt;
-                real b = po - pt;
-                real zn;
-                if (b > th) { b -= th; zn = zo + rho * (a + wt * b - xp.x); }
-                else if (b < -th) { b += th; zn = zo + rho * (a + wt * b - xp.x); }
-                else zn = zo + rho * (a - xp.x);
-                Zout[s] = zn;
-                acc += (wv * Sv) * zn;
+        for (int j0 = 0; j0 < width; j0 += U) {
+            int n[U], tw[U];
+            real wv[U], zo[U], pn[U], Tn[U], zt[U], thc[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const bool in = j0 + u < width;
+                const int s = s0 + (j0 + u) * 32;
+                n[u] = in ? nbr[s] : -1;
+                tw[u] = in ? twin[s] : 0;
+                wv[u] = in ? wg[s] : (real) 0;
+                zo[u] = in ? Zin[s] : (real) 0;
+                thc[u] = PER_SLOT_TH ? (in ? p.thc[s] : (real) 0) : p.thc0;
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const bool ok = n[u] >= 0;
+                pn[u] = ok ? Pc[n[u]] : (real) 0;
+                Tn[u] = ok ? Tg[n[u]] : (real) 1;
+                zt[u] = ok ? Zin[tw[u]] : (real) 0;
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                if (n[u] >= 0) {
+                    const real tsum = Tv + Tn[u];
+                    const real th = thc[u] * tsum;                                // Th_d1
+                    const real inv = fast_rcp(tsum);
+                    const real wo = Tn[u] * inv, wt = Tv * inv;                   // W_d1 own / twin side
+                    const real po = po_v - zo[u], pt = pn[u] - zt[u];
+                    const real a = wo * po + wt * pt;
+                    real b = po - pt;
+                    b = (b > th) ? b - th : ((b < -th) ? b + th : (real) 0);      // soft threshold (ref :477-488)
+                    const real zn = zo[u] + rho * (a + wt * b - xo);
+                    Zout[s0 + (j0 + u) * 32] = zn;
+                    acc += (wv[u] * Sv) * zn;
+                }
             }
         }
         real x = acc;
@@ -291,11 +309,9 @@ __global__ void __launch_bounds__(256) quad_iter_kernel(QP<real> p)
             if (p.has_lo && x < p.lo) x = p.lo;
             else if (p.has_hi && x > p.hi) x = p.hi;
         }
-        pair_t<real> o; o.x = x;
-        o.y = (p.N == 0) ? (real) 2 * x - p.Ga[v] * grad_at(p, v, x) : (real) 0;
-        XPn[v] = o;
-        if (p.Xc) p.Xc[v] = x;
-        const real dx = xp.x - x;
+        Xn[v] = x;
+        if (p.N == 0) Pn[v] = (real) 2 * x - p.Ga[v] * grad_at(p, v, x);
+        const real dx = xo - x;
         red[0] = (double) (dx * dx); red[1] = (double) (x * x);
     }
     if (grid_sum<2>(ctl, p.partial, red, smem) && threadIdx.x == 0) {
@@ -312,13 +328,145 @@ __global__ void __launch_bounds__(256) quad_iter_kernel(QP<real> p)
     }
 }
 
+// Row-parallel variant: one thread per half-edge slot.  A CTA owns G slices (32 vertices each); warp (g, r)
+// walks rows r, r+W, ... of slice g, so every load is a single coalesced row and a vertex's W rows are in
+// flight in W different warps (thread-level instead of instruction-level parallelism, ~32 registers).
+// The per-vertex sum is taken from shared memory in row order by the slice's first warp, i.e. still in
+// the reference's edge order and with no atomics.
+template <typename real, bool PER_SLOT_TH, int W, int G>
+__global__ void __launch_bounds__(32 * W * G) quad_rows_kernel(QP<real> p, int nslices)
+{
+    __shared__ real contrib[G][W][32];
+    __shared__ int s_width[G];
+    __shared__ double s_red[2][G];
+    Ctl *ctl = p.ctl;
+    const CtlView cv = load_ctl(ctl);
+    if (cv.hold != 0 || cv.state != ST_RUN) {
+        if (cv.hold == 0 && blockIdx.x == 0 && threadIdx.x == 0) ctl->hold = 1;
+        return;
+    }
+    const int it = cv.it, cur = it & 1;
+    const real *__restrict__ Zin = cur ? p.Z1 : p.Z0;
+    real *__restrict__ Zout = cur ? p.Z0 : p.Z1;
+    const real *__restrict__ Xc = cur ? p.X1 : p.X0;
+    const real *__restrict__ Pc = cur ? p.P1 : p.P0;
+    const real *__restrict__ Tg = p.T;
+    const real rho = p.rho;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = warp / W, r = warp - g * W;
+    const int slice = blockIdx.x * G + g;
+    const bool live = slice < nslices;
+    const int v = slice * 32 + lane;
+    const bool vlive = live && v < p.V;
+    long long base = 0;
+    int width = 0;
+    if (live) { base = p.slice_off[slice]; width = (int) ((p.slice_off[slice + 1] - base) >> 5); }
+    if (r == 0 && lane == 0) s_width[g] = width;
+    real xo = 0, po_v = 0, Tv = 1, Sv = 0;
+    if (vlive) { xo = Xc[v]; po_v = Pc[v]; Tv = Tg[v]; Sv = p.Sinv[v]; }
+    __syncthreads();
+    int wmax = 0;
+#pragma unroll
+    for (int i = 0; i < G; i++) wmax = max(wmax, s_width[i]);
+    const int s0 = (int) base + lane;
+    real run = 0;
+    for (int j0 = 0; j0 < wmax; j0 += W) {
+        const int j = j0 + r;
+        real c = 0;
+        if (vlive && j < width) {
+            const int s = s0 + j * 32;
+            const int n = p.nbr[s];
+            if (n >= 0) {
+                const int tw = p.twin[s];
+                const real wv = p.w[s], zo = Zin[s];
+                const real thc = PER_SLOT_TH ? p.thc[s] : p.thc0;
+                const real pn = Pc[n], Tn = Tg[n], zt = Zin[tw];
+                const real tsum = Tv + Tn;
+                const real th = thc * tsum;
+                const real inv = fast_rcp(tsum);
+                const real wo = Tn * inv, wt = Tv * inv;
+                const real po = po_v - zo, pt = pn - zt;
+                const real a = wo * po + wt * pt;
+                real b = po - pt;
+                b = (b > th) ? b - th : ((b < -th) ? b + th : (real) 0);
+                const real zn = zo + rho * (a + wt * b - xo);
+                Zout[s] = zn;
+                c = (wv * Sv) * zn;
+            }
+        }
+        contrib[g][r][lane] = c;
+        __syncthreads();
+        if (r == 0) {
+#pragma unroll
+            for (int k = 0; k < W; k++) run += contrib[g][k][lane];
+        }
+        if (j0 + W < wmax) __syncthreads();
+    }
+    real d0 = 0, d1 = 0;
+    if (r == 0) {
+        if (vlive) {
+            real x = run;
+            if (p.prox_kind == 0) {                                            // ref l1.cpp :500-512
+                if (p.La_l1) {
+                    const real th = p.Thl1[v];
+                    if (x > th) x -= th;
+                    else if (!p.positivity && x < -th) x += th;
+                    else x = 0;
+                } else if (p.positivity) { if (x < (real) 0) x = 0; }
+            } else {                                                           // ref bounds.cpp :473-490
+                if (p.has_lo && x < p.lo) x = p.lo;
+                else if (p.has_hi && x > p.hi) x = p.hi;
+            }
+            (cur ? p.X0 : p.X1)[v] = x;
+            if (p.N == 0) (cur ? p.P0 : p.P1)[v] = (real) 2 * x - p.Ga[v] * grad_at(p, v, x);
+            const real dx = xo - x;
+            d0 = dx * dx; d1 = x * x;
+        }
+        // evolution sums (ref :515-529): 32 values in `real` inside the warp, double from there on
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { d0 += __shfl_xor_sync(0xffffffffu, d0, o); d1 += __shfl_xor_sync(0xffffffffu, d1, o); }
+        if (lane == 0) { s_red[0][g] = (double) d0; s_red[1][g] = (double) d1; }
+    }
+    __syncthreads();
+    __shared__ int s_last;
+    if (threadIdx.x == 0) {
+        double a = 0, b = 0;
+#pragma unroll
+        for (int i = 0; i < G; i++) { a += s_red[0][i]; b += s_red[1][i]; }
+        p.partial[2 * (size_t) blockIdx.x] = a; p.partial[2 * (size_t) blockIdx.x + 1] = b;
+        __threadfence();
+        s_last = (atomicAdd(&ctl->ticket, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    double acc[2] = {0.0, 0.0};
+    const volatile double *vp = p.partial;
+    for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) { acc[0] += vp[2 * (size_t) b]; acc[1] += vp[2 * (size_t) b + 1]; }
+    __shared__ double smem[64];
+    block_sum<2>(acc, smem);
+    if (threadIdx.x == 0) {
+        ctl->ticket = 0;
+        double dif = ctl->dif;
+        if (ctl->track) {
+            dif = (acc[1] > ctl->eps) ? acc[0] / acc[1] : acc[0] / ctl->eps;
+            ctl->dif = dif;
+            if (p.dDif) p.dDif[it] = (real) dif;
+        }
+        const int itn = it + 1;
+        ctl->it = itn;
+        if (itn == ctl->itMax || (real) dif < (real) ctl->tol) ctl->state = ST_FINAL;   // ref :429
+        else if ((real) dif < (real) ctl->rcd) ctl->state = ST_RECOND;                  // ref :448
+    }
+}
+
 template <typename real>
 __global__ void extract_x_kernel(QP<real> p, real *__restrict__ out)
 {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= p.V) return;
-    const pair_t<real> *XP = (p.ctl->it & 1) ? p.XP1 : p.XP0;
-    out[v] = XP[v].x;
+    out[v] = ((p.ctl->it & 1) ? p.X1 : p.X0)[v];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -329,15 +477,16 @@ __global__ void __launch_bounds__(256) objective_kernel(QP<real> p)
 {
     __shared__ double smem[64];
     Ctl *ctl = p.ctl;
-    if (ld_flag(&ctl->hold)) return;
-    const int it = ld_flag(&ctl->it);
-    const pair_t<real> *__restrict__ XP = (it & 1) ? p.XP1 : p.XP0;
+    const CtlView cv = load_ctl(ctl);
+    if (cv.hold) return;
+    const int it = cv.it;
+    const real *__restrict__ X = (it & 1) ? p.X1 : p.X0;
     double r[1] = {0.0};
     const size_t stride = (size_t) gridDim.x * blockDim.x, t0 = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
     for (size_t e = t0; e < (size_t) p.E; e += stride)
-        r[0] += (double) p.La_d1[e] * (double) rabs(XP[p.Eu[e]].x - XP[p.Ev[e]].x);
+        r[0] += (double) p.La_d1[e] * (double) rabs(X[p.Eu[e]] - X[p.Ev[e]]);
     for (size_t v = t0; v < (size_t) p.V; v += stride) {
-        const real x = XP[v].x;
+        const real x = X[v];
         if (p.N == 0) r[0] += (double) x * ((double) 0.5 * (double) (p.A ? p.A[v] * x : x) - (double) p.Y[v]);
         else if (p.N < 0) r[0] += (double) x * ((double) 0.5 * (double) p.G[v] - (double) p.Y[v]);
         if (p.La_l1) r[0] += (double) p.La_l1[v] * (double) rabs(x);
@@ -372,10 +521,11 @@ template <typename real, int VEC, int CG>
 __global__ void __launch_bounds__(256) ata_gemv_kernel(QP<real> p)
 {
     __shared__ double smem[CG * 32];
-    if (ld_flag(&p.ctl->hold)) return;
-    pair_t<real> *XP = (ld_flag(&p.ctl->it) & 1) ? p.XP1 : p.XP0;
+    const CtlView cv = load_ctl(p.ctl);
+    if (cv.hold) return;
+    real *P = (cv.it & 1) ? p.P1 : p.P0;
     const size_t V = (size_t) p.V;
-    const real *__restrict__ X = p.Xc;
+    const real *__restrict__ X = (cv.it & 1) ? p.X1 : p.X0;
     for (size_t c0 = (size_t) blockIdx.x * CG; c0 < V; c0 += (size_t) gridDim.x * CG) {
         double acc[CG];
         real part[CG];
@@ -403,7 +553,7 @@ __global__ void __launch_bounds__(256) ata_gemv_kernel(QP<real> p)
             for (int c = 0; c < CG; c++) if (c == (int) threadIdx.x) g = (real) acc[c];
             p.G[v] = g;
             const real x = X[v];
-            XP[v].y = (real) 2 * x - p.Ga[v] * (g - p.Y[v]);
+            P[v] = (real) 2 * x - p.Ga[v] * (g - p.Y[v]);
         }
     }
 }
@@ -414,12 +564,13 @@ template <typename real, int VEC>
 __global__ void __launch_bounds__(256) ax_partial_kernel(QP<real> p, int TX, double *__restrict__ parts)
 {
     extern __shared__ double dsm[];
-    if (ld_flag(&p.ctl->hold)) return;
+    const CtlView cv = load_ctl(p.ctl);
+    if (cv.hold) return;
     const int N = p.N, TY = blockDim.x / TX;
     const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
     const size_t V = (size_t) p.V;
     const size_t v0 = V * blockIdx.x / gridDim.x, v1 = V * (blockIdx.x + 1) / gridDim.x;
-    const real *__restrict__ X = p.Xc;
+    const real *__restrict__ X = (cv.it & 1) ? p.X1 : p.X0;
     const int nvec = (N + VEC - 1) / VEC;
     for (int nb0 = 0; nb0 < nvec; nb0 += TX) {     // uniform trip count: every thread reaches the barriers
         const int nb = nb0 + tx;
@@ -473,7 +624,7 @@ __global__ void __launch_bounds__(256) ax_partial_kernel(QP<real> p, int TX, dou
 template <typename real>
 __global__ void ax_finish_kernel(QP<real> p, const double *__restrict__ parts)
 {
-    if (ld_flag(&p.ctl->hold)) return;
+    if (load_ctl(p.ctl).hold) return;
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= p.N) return;
     double a = 0;
@@ -486,7 +637,8 @@ __global__ void ax_finish_kernel(QP<real> p, const double *__restrict__ parts)
 template <typename real, int VEC>
 __global__ void __launch_bounds__(256) atr_kernel(QP<real> p, int GL, int mode)
 {
-    if (mode == 0 && ld_flag(&p.ctl->hold)) return;
+    const CtlView cv = load_ctl(p.ctl);
+    if (mode == 0 && cv.hold) return;
     const int N = p.N;
     const size_t gid = ((size_t) blockIdx.x * blockDim.x + threadIdx.x) / GL;
     const int gl = threadIdx.x % GL;
@@ -510,10 +662,9 @@ __global__ void __launch_bounds__(256) atr_kernel(QP<real> p, int GL, int mode)
     if (live && gl == 0) {
         if (mode) { p.Ga0[v] = s1; p.AtY[v] = s0; }
         else {
-            pair_t<real> *XP = (ld_flag(&p.ctl->it) & 1) ? p.XP1 : p.XP0;
             const real g = -s0;
             p.G[v] = g;
-            XP[v].y = (real) 2 * p.Xc[v] - p.Ga[v] * g;
+            ((cv.it & 1) ? p.P1 : p.P0)[v] = (real) 2 * ((cv.it & 1) ? p.X1 : p.X0)[v] - p.Ga[v] * g;
         }
     }
 }
@@ -530,8 +681,7 @@ struct QuadSolver : SolverBase {
     DevBuf<Ctl> ctl;
     DevIn<real> Y, A, La_d1, La_l1, L, X0;
     DevIn<int> Eu, Ev;
-    DevBuf<real> w, thc, Z0, Z1, Xc, T, Sinv, Ga, Ga0, G, Thl1, R, AtY, dObj, dDif, Xout;
-    DevBuf<pair_t<real>> XP0, XP1;
+    DevBuf<real> w, thc, Z0, Z1, X0b, X1b, P0b, P1b, T, Sinv, Ga, Ga0, G, Thl1, R, AtY, dObj, dDif, Xout;
     DevBuf<double> partial, parts;
     Ctl *hctl = nullptr;            // pinned mirror of the control block, one per batch in flight
     cudaEvent_t ev[2]{}, ev_a{}, ev_b{}, ev_c{};
@@ -567,12 +717,13 @@ struct QuadSolver : SolverBase {
         L.bind(q.L, q.L ? (q.Ltype == PFDR_B200_SCAL ? 1 : (size_t) V) : 0);
         X0.bind(q.X, V);
         build_sell(g, Eu, Ev, V, E, 32);
+        rowsW = g.max_width;
 
         const size_t ns = (size_t) std::max<long long>(g.nslots, 1);
         w.alloc(ns); Z0.alloc(ns); Z1.alloc(ns);
-        XP0.alloc(V); XP1.alloc(V); T.alloc(V); Sinv.alloc(V); Ga.alloc(V); Ga0.alloc(V);
+        X0b.alloc(V); X1b.alloc(V); P0b.alloc(V); P1b.alloc(V); T.alloc(V); Sinv.alloc(V); Ga.alloc(V); Ga0.alloc(V);
         if (La_l1.p) Thl1.alloc(V);
-        if (N != 0) { Xc.alloc(V); G.alloc(V); }
+        if (N != 0) G.alloc(V);
         if (N > 0) { R.alloc(N); AtY.alloc(V); }
         if (q.Obj) dObj.alloc((size_t) q.itMax + 1);
         if (q.Dif) dDif.alloc((size_t) std::max(q.itMax, 1));
@@ -584,8 +735,8 @@ struct QuadSolver : SolverBase {
 
         p.ctl = ctl.p; p.V = V; p.N = N; p.E = E;
         p.slice_off = g.slice_off.p; p.nbr = g.nbr.p; p.twin = g.twin.p; p.hkey = g.hkey.p;
-        p.w = w.p; p.thc = nullptr; p.thc0 = 0; p.Z0 = Z0.p; p.Z1 = Z1.p; p.XP0 = XP0.p; p.XP1 = XP1.p;
-        p.Xc = Xc.p; p.T = T.p; p.Sinv = Sinv.p; p.Ga = Ga.p; p.Ga0 = Ga0.p; p.G = G.p; p.Thl1 = Thl1.p;
+        p.w = w.p; p.thc = nullptr; p.thc0 = 0; p.Z0 = Z0.p; p.Z1 = Z1.p;
+        p.X0 = X0b.p; p.X1 = X1b.p; p.P0 = P0b.p; p.P1 = P1b.p; p.T = T.p; p.Sinv = Sinv.p; p.Ga = Ga.p; p.Ga0 = Ga0.p; p.G = G.p; p.Thl1 = Thl1.p;
         p.R = R.p; p.AtY = AtY.p; p.Y = Y.p; p.A = A.p; p.La_d1 = La_d1.p; p.La_l1 = La_l1.p; p.L = L.p;
         p.Eu = Eu.p; p.Ev = Ev.p; p.Ltype = q.Ltype; p.positivity = q.positivity; p.prox_kind = q.prox_kind;
         p.lo = q.lo; p.hi = q.hi;
@@ -607,7 +758,7 @@ struct QuadSolver : SolverBase {
         } else if (N < 0) {
             vec = ((V % vmax == 0) && (((uintptr_t) A.p) % 16 == 0)) ? vmax : 1;
         }
-        const int maxgrid = std::max(std::max(vgrid, p.nparts), num_sms() * 8);
+        const int maxgrid = std::max(std::max(std::max(vgrid, g.nslices), p.nparts), num_sms() * 8);
         partial.alloc((size_t) maxgrid * 4);
         p.partial = partial.p;
 
@@ -668,8 +819,37 @@ struct QuadSolver : SolverBase {
             const size_t work = std::max((size_t) q.E, std::max((size_t) q.V, (size_t) std::max(q.N, 0)));
             PFDR_LAUNCH(objective_kernel<real>, std::min<unsigned>(cdiv(work, 256), num_sms() * 8), 256, 0, p);
         }
-        if (p.thc) PFDR_LAUNCH((quad_iter_kernel<real, true>), vgrid, 256, 0, p);
-        else PFDR_LAUNCH((quad_iter_kernel<real, false>), vgrid, 256, 0, p);
+        launch_iter();
+    }
+
+    // PFDR_B200_KERNEL=vertex selects the one-thread-per-vertex kernel (PFDR_B200_U rows in flight, default
+    // 8 / 4); the default is the row-parallel kernel with W warps per slice chosen from the widest slice.
+    int rowsW = 0;
+    void launch_iter()
+    {
+        static int U = -1, mode = -1;
+        if (U < 0) { const char *e = getenv("PFDR_B200_U"); U = e ? atoi(e) : 0; }
+        if (mode < 0) { const char *e = getenv("PFDR_B200_KERNEL"); mode = (e && !strcmp(e, "vertex")) ? 1 : 0; }
+        if (mode == 1) {
+            const int u = U > 0 ? U : (sizeof(real) == 4 ? 8 : 4);
+#define PFDR_ITER(UU)                                                                          \
+            do {                                                                               \
+                if (p.thc) PFDR_LAUNCH((quad_iter_kernel<real, true, UU>), vgrid, 256, 0, p);  \
+                else PFDR_LAUNCH((quad_iter_kernel<real, false, UU>), vgrid, 256, 0, p);       \
+            } while (0)
+            if (u <= 2) PFDR_ITER(2); else if (u <= 4) PFDR_ITER(4); else if (u <= 6) PFDR_ITER(6); else PFDR_ITER(8);
+#undef PFDR_ITER
+            return;
+        }
+        const int ns = g.nslices;
+#define PFDR_ROWS(WW, GG)                                                                                      \
+        do {                                                                                                   \
+            if (p.thc) PFDR_LAUNCH((quad_rows_kernel<real, true, WW, GG>), cdiv(ns, GG), 32 * WW * GG, 0, p, ns); \
+            else PFDR_LAUNCH((quad_rows_kernel<real, false, WW, GG>), cdiv(ns, GG), 32 * WW * GG, 0, p, ns);   \
+        } while (0)
+        if (rowsW <= 2) PFDR_ROWS(2, 4); else if (rowsW <= 4) PFDR_ROWS(4, 2); else if (rowsW <= 6) PFDR_ROWS(6, 2);
+        else PFDR_ROWS(8, 1);
+#undef PFDR_ROWS
     }
 
     int launches_per_trip() const { return (q.N > 0 ? 3 : (q.N < 0 ? 1 : 0)) + (q.Obj ? 1 : 0) + 1; }

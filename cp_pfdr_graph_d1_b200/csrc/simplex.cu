@@ -1,34 +1,43 @@
 // simplex.cu - PFDR for  loss(P;Q) + sum_e La_d1 sum_k |P_uk - P_vk|  with every P_v on the simplex,
 // the B200-native replacement of src/PFDR_graph_loss_d1_simplex.cpp (+ src/proj_simplex_metric.cpp).
 //
-// One fused kernel per iteration.  TPV = next power of two >= K lanes cooperate on one vertex (lane = label),
-// C = 32/TPV vertices share a warp and one SELL-C slice of the half-edge table (graph.cuh); the K labels of
-// a half-edge are contiguous, so every load of edge copies is one coalesced row.  Per trip and per
-// (half-edge, label): explicit step on both ends is already folded into the stored forward point FP
-// (ref :569-587), d1 prox + relaxation (:590-634) for the lane's own half, weighted average in edge order
-// (:637-648); then the K lanes of a vertex run proj_simplex_metric (:651, proj_simplex_metric.cpp:40-81)
-// redundantly through warp shuffles, write (P, FP) of the next trip and add up the evolution (:654-691).
-// Edge constants are recomputed from per-(vertex,label) S and T = Ga.S exactly as in quad.cu.
+// One fused kernel per iteration.  A lane owns LPT consecutive labels of one vertex (LPT = 4 when K % 4 == 0:
+// every access to a K-vector is then a 16/32-byte vector load; LPT = 1 otherwise), TPV = next power of two
+// >= K/LPT lanes cooperate on a vertex and C = 32/TPV vertices share a warp and one SELL-C slice of the
+// half-edge table (graph.cuh).  U half-edge rows are in flight per lane (loads of the whole chunk first,
+// then the gathers, then the arithmetic).  Per trip and per (half-edge, label):
+//   - the explicit step is already folded into the stored forward point FP = 2P - Ga.grad (ref :569-587),
+//     which is the only vertex value a neighbour gathers (P and FP are separate arrays for that reason);
+//   - d1 prox + relaxation (:590-634) for the lane's own half-edge copy, ping/pong buffers;
+//   - weighted average over the vertex's rows in edge order (:637-648);
+//   - projection on the simplex in the diagonal metric (:651): the lanes of a vertex run Michelot's
+//     active-set iteration in parallel (two group reductions per pass) - same projection as the reference's
+//     sequential recursion (proj_simplex_metric.cpp:40-81), which cost ~60 % of the v0 kernel's instructions;
+//   - next (P, FP) and the evolution sums (:654-691).
+// Edge constants are recomputed from T = Ga.S as in quad.cu:  W = w/S[u], W_d1u = T[v]/(T[u]+T[v]),
+// Th_d1 = (La_d1/w)(T[u]+T[v]); before any reconditioning w = La_d1[e] for all labels (:207-208), so
+// La_d1/w = 1, S is per vertex, and T doubles as the projection metric (the projection is invariant to a
+// positive rescaling of the metric, and the reference's normalisation Ga/max Ga (:362-369) is one).
 #include "graph.cuh"
 #include "solvers.cuh"
 
 namespace pfdr {
-
-template <typename real> using pair_t = typename Pair<real>::type;
 
 enum : int { LOSS_LIN = 0, LOSS_QUAD = 1, LOSS_KLA = 2 };
 
 template <typename real>
 struct SP {
     Ctl *ctl;
-    int K, V, E, TPV, C, logC, logTPV, loss, by_label;
+    int K, V, E, TPV, C, logC, logTPV, loss, by_label, LPT;
     real aK, a1, aK1, rho, condMin;
     const long long *slice_off; const int *nbr, *twin, *hkey;
-    real *w;                      // [slots]   raw weight (first preconditioning: La_d1[e] for every label)
-    real *wk, *thk;               // [slots*K] raw weight / its La_d1 ratio per label after a reconditioning
-    real *Z0, *Z1;                // [slots*K] edge copies
-    pair_t<real> *PF0, *PF1;      // [V*K] (P, forward point)
-    real *T, *Sinv, *Gn, *GaQ, *GaU;   // [V*K] Ga.S, 1/S, normalised metric, metric x first order info, raw metric
+    real *w;                      // [slots]   raw weight before any reconditioning (= La_d1[e] for every label)
+    real *wk, *thk;               // [slots*K] raw weight / La_d1 over it, per label, after a reconditioning
+    real *Z0, *Z1;                // [slots*K] edge copies, ping/pong
+    real *P0, *P1, *F0, *F1;      // [V*K] iterate and forward point, ping/pong
+    real *T, *GaQ;                // [V*K] Ga.S  and  metric x first-order information (:308-335)
+    real *Sinv;                   // [V]   1/S before any reconditioning
+    real *Sinvk, *Gn, *GaU;       // [V*K] 1/S per label, normalised metric (after a reconditioning), raw metric
     int *lab;                     // [V] previous arg-max label (difTol >= 1)
     const real *Q, *La_f, *La_d1;
     const int *Eu, *Ev;
@@ -37,6 +46,55 @@ struct SP {
 };
 
 template <typename real> __device__ __forceinline__ real sabs(real a) { return a < (real) 0 ? -a : a; }
+
+// ---- LPT-wide vectors of labels ----------------------------------------------------------------
+template <typename real, int L> struct VecN { real v[L]; };
+
+template <typename real, int L>
+__device__ __forceinline__ VecN<real, L> ldv(const real *q)
+{
+    VecN<real, L> r;
+    if constexpr (L == 1) r.v[0] = *q;
+    else if constexpr (sizeof(real) == 4) {
+        const float4 t = *reinterpret_cast<const float4 *>(q);
+        r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
+    } else {
+        const double2 a = *reinterpret_cast<const double2 *>(q), b = *reinterpret_cast<const double2 *>(q + 2);
+        r.v[0] = a.x; r.v[1] = a.y; r.v[2] = b.x; r.v[3] = b.y;
+    }
+    return r;
+}
+template <typename real, int L>
+__device__ __forceinline__ void stv(real *q, const VecN<real, L> &r)
+{
+    if constexpr (L == 1) *q = r.v[0];
+    else if constexpr (sizeof(real) == 4) *reinterpret_cast<float4 *>(q) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
+    else {
+        *reinterpret_cast<double2 *>(q) = make_double2(r.v[0], r.v[1]);
+        *reinterpret_cast<double2 *>(q + 2) = make_double2(r.v[2], r.v[3]);
+    }
+}
+template <typename real, int L>
+__device__ __forceinline__ VecN<real, L> splat(real x)
+{
+    VecN<real, L> r;
+#pragma unroll
+    for (int i = 0; i < L; i++) r.v[i] = x;
+    return r;
+}
+
+template <typename real>
+__device__ __forceinline__ real group_sum(real x, int TPV)
+{
+    for (int o = TPV >> 1; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    return x;
+}
+template <typename real>
+__device__ __forceinline__ real group_max(real x, int TPV)
+{
+    for (int o = TPV >> 1; o > 0; o >>= 1) x = max(x, __shfl_xor_sync(0xffffffffu, x, o));
+    return x;
+}
 
 template <int NV>
 __device__ bool grid_sum_s(Ctl *ctl, double *partial, double (&v)[NV], double *smem)
@@ -70,57 +128,19 @@ __device__ bool grid_sum_s(Ctl *ctl, double *partial, double (&v)[NV], double *s
 
 // forward point 2P - Ga.grad(P)  (ref :569-587)
 template <typename real>
-__device__ __forceinline__ real forward_point(const SP<real> &p, real P, real gaq, real q)
+__device__ __forceinline__ real forward_point(int loss, real aK1, real P, real gaq, real q)
 {
-    if (p.loss == LOSS_LIN) return (real) 2 * P + gaq;
-    if (p.loss == LOSS_QUAD) return (real) 2 * P - gaq * (P - q);
-    return (real) 2 * P + gaq / (p.aK1 + P);
+    if (loss == LOSS_LIN) return (real) 2 * P + gaq;
+    if (loss == LOSS_QUAD) return (real) 2 * P - gaq * (P - q);
+    return (real) 2 * P + gaq / (aK1 + P);
 }
-
-// proj_simplex_metric on the TPV lanes of one vertex (lane k holds x_k, m_k); every lane runs the
-// reference's sequential active-set recursion (proj_simplex_metric.cpp:43-81) on shuffled values, so the
-// result is the reference's up to the rounding of the inputs.  All 32 lanes must call.
+// P - Ga.grad(P), as the reference's subgradient expressions need it (:137-156, :337-358)
 template <typename real>
-__device__ __forceinline__ real simplex_project(real x, real m, real target, int k, int K, int TPV)
+__device__ __forceinline__ real explicit_point(int loss, real aK1, real P, real gaq, real q)
 {
-    const unsigned full = 0xffffffffu;
-    const real xs = x / m;
-    const real x0 = __shfl_sync(full, x, 0, TPV), m0 = __shfl_sync(full, m, 0, TPV);
-    real la = (x0 - target) / m0, s = m0;
-    unsigned act = 1u;
-    for (int d = 1; d < K; d++) {                                  // first pass  :49-58
-        const real xd = __shfl_sync(full, xs, d, TPV), md = __shfl_sync(full, m, d, TPV);
-        if (xd > la) { act |= 1u << d; s += md; la += md * (xd - la) / s; }
-    }
-    for (;;) {                                                     // pruning passes :60-73
-        bool changed = false;
-        for (int d = 0; d < K; d++) {
-            const real xd = __shfl_sync(full, xs, d, TPV), md = __shfl_sync(full, m, d, TPV);
-            if (((act >> d) & 1u) && xd < la) { act &= ~(1u << d); s -= md; la += md * (la - xd) / s; changed = true; }
-        }
-        if (!__any_sync(full, changed)) break;
-    }
-    return ((act >> k) & 1u) ? (xs - la) * m : (real) 0;           // :75-81
-}
-
-// first arg-max label of the K lanes of a vertex (ref :662-669); all 32 lanes must call
-template <typename real>
-__device__ __forceinline__ int argmax_label(real x, int K, int TPV)
-{
-    real a = __shfl_sync(0xffffffffu, x, 0, TPV);
-    int i = 0;
-    for (int d = 1; d < K; d++) {
-        const real xd = __shfl_sync(0xffffffffu, x, d, TPV);
-        if (xd > a) { a = xd; i = d; }
-    }
-    return i;
-}
-
-template <typename real>
-__device__ __forceinline__ real group_max(real x, int TPV)
-{
-    for (int o = TPV >> 1; o > 0; o >>= 1) x = max(x, __shfl_xor_sync(0xffffffffu, x, o));
-    return x;
+    if (loss == LOSS_LIN) return P + gaq;
+    if (loss == LOSS_QUAD) return P - gaq * (P - q);
+    return P + gaq / (aK1 + P);
 }
 
 // metric of one (vertex,label) from the loss Hessian and the weight sum S  (ref :160-190, :222-285)
@@ -136,14 +156,13 @@ __device__ __forceinline__ real metric(const SP<real> &p, int v, real P, real q,
         return ga;
     }
     const real a = p.aK1 + P, cq = p.aK + p.a1 * q;
-    real h = p.La_f ? p.La_f[v] * cq / (a * a) : cq / (a * a);
+    const real h = p.La_f ? p.La_f[v] * cq / (a * a) : cq / (a * a);
     real ga = (real) 1 / (h + S);
     const real b = p.La_f ? p.La_f[v] * (real) 1 / (p.aK1 * p.aK1) : (real) 1 / (p.aK1 * p.aK1);
     const real c = bound / (cq * b);
     if (ga > c) ga = c;
     return ga;
 }
-
 template <typename real>
 __device__ __forceinline__ real metric_times_info(const SP<real> &p, int v, real ga, real q)
 {   // GaQ, ref :308-335
@@ -152,81 +171,111 @@ __device__ __forceinline__ real metric_times_info(const SP<real> &p, int v, real
     return p.La_f ? p.La_f[v] * ga * (p.aK + p.a1 * q) : ga * (p.aK + p.a1 * q);
 }
 
-// gradient step folded as the reference's subgradient expressions need it:  P - Ga.grad(P)
-template <typename real>
-__device__ __forceinline__ real explicit_point(const SP<real> &p, real P, real gaq, real q)
+// first arg-max label over the lanes of a vertex (ref :662-669): ties go to the lowest label
+template <typename real, int LPT>
+__device__ __forceinline__ int group_argmax(const VecN<real, LPT> &x, int k0, int K, int TPV)
 {
-    if (p.loss == LOSS_LIN) return P + gaq;
-    if (p.loss == LOSS_QUAD) return P - gaq * (P - q);
-    return P + gaq / (p.aK1 + P);
+    real a = -HUGE_VAL; int i = 0x7fffffff;
+#pragma unroll
+    for (int t = 0; t < LPT; t++) if (k0 + t < K && x.v[t] > a) { a = x.v[t]; i = k0 + t; }
+    for (int o = TPV >> 1; o > 0; o >>= 1) {
+        const real b = __shfl_xor_sync(0xffffffffu, a, o);
+        const int j = __shfl_xor_sync(0xffffffffu, i, o);
+        if (b > a || (b == a && j < i)) { a = b; i = j; }
+    }
+    return i;
 }
 
 // ---------------------------------------------------------------------------------------------
-// first preconditioning (recond = 0, ref :160-370 with Zu == NULL) and reconditioning (recond = 1)
+// first preconditioning (recond = 0, ref :160-370 with Zu == NULL) and reconditioning (recond = 1):
+// everything is local to a vertex row, so one kernel does it all.
 // ---------------------------------------------------------------------------------------------
-template <typename real>
-__global__ void __launch_bounds__(256) simplex_precond_kernel(SP<real> p, const real *__restrict__ P0, int recond)
+template <typename real, int LPT>
+__global__ void __launch_bounds__(256) simplex_precond_kernel(SP<real> p, const real *__restrict__ Pinit, int recond)
 {
     const int lane = threadIdx.x & 31;
     const long long slice = ((long long) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (slice >= ((long long) p.V + p.C - 1) >> p.logC) return;     // whole warp leaves together
     const int K = p.K, TPV = p.TPV;
-    const int vl = lane >> p.logTPV, k = lane & (TPV - 1);
+    const int vl = lane >> p.logTPV, k0 = (lane & (TPV - 1)) * LPT;
     const int v = (int) (slice << p.logC) + vl;
-    const bool on = (v < p.V) && (k < K);
-    const size_t vk = (size_t) (on ? v : 0) * K + (on ? k : 0);
+    const bool on = (v < p.V) && (k0 < K);
+    const size_t vk = (size_t) (on ? v : 0) * K + (on ? k0 : 0);
     const int cur = recond ? (p.ctl->it & 1) : 0;
-    pair_t<real> *PF = cur ? p.PF1 : p.PF0;
+    real *Pb = cur ? p.P1 : p.P0, *Fb = cur ? p.F1 : p.F0;
     real *Z = cur ? p.Z1 : p.Z0;
-    const real P = recond ? PF[vk].x : P0[vk];
-    const real q = p.Q[vk];
+    const bool perk_old = recond && (p.ctl->scratch[0] != 0.0);   // weights already per label before this call
     const long long base = p.slice_off[slice];
     const int width = (int) ((p.slice_off[slice + 1] - base) >> p.logC);
-    const real ga_old = recond ? p.GaU[vk] : (real) 0, gaq_old = recond ? p.GaQ[vk] : (real) 0;
-    const real sinv_old = recond ? p.Sinv[vk] : (real) 0;
-    const bool perk_old = recond && (p.ctl->scratch[0] != 0.0);   // weights already per label before this call
-    real S = 0;
+    real P[LPT], q[LPT], S[LPT], ga_old[LPT], gaq_old[LPT], sinv_old[LPT];
+#pragma unroll
+    for (int i = 0; i < LPT; i++) {
+        const bool li = on && k0 + i < K;
+        P[i] = li ? (recond ? Pb[vk + i] : Pinit[vk + i]) : (real) 0;
+        q[i] = li ? p.Q[vk + i] : (real) 0;
+        S[i] = 0;
+        ga_old[i] = (recond && li) ? p.GaU[vk + i] : (real) 1;
+        gaq_old[i] = (recond && li) ? p.GaQ[vk + i] : (real) 0;
+        sinv_old[i] = (recond && li) ? (perk_old ? p.Sinvk[vk + i] : p.Sinv[v]) : (real) 0;
+    }
     for (int j = 0; j < width; j++) {
         const long long s = base + ((long long) j << p.logC) + vl;
         const int n = p.nbr[s];
         if (n >= 0 && on) {
-            const size_t sk = (size_t) s * K + k;
-            if (!recond) {
-                const real wv = p.La_d1[p.hkey[s] >> 1];                        // ref :207-208
-                if (k == 0) p.w[s] = wv;
-                S += wv; Z[sk] = P;                                             // ref :419-430
-            } else {
-                const real Wold = (perk_old ? p.wk[sk] : p.w[s]) * sinv_old;
-                Z[sk] = (Wold / ga_old) * (explicit_point(p, P, gaq_old, q) - Z[sk]);      // ref :137-156
-                real d = sabs(P - PF[(size_t) n * K + k].x);                              // ref :210-213
-                if (d < p.condMin) d = p.condMin;
-                const real wv = p.La_d1[p.hkey[s] >> 1] / d;
-                p.wk[sk] = wv; p.thk[sk] = d; S += wv;
-            }
-        }
-    }
-    const real ga = on ? metric(p, v, P, q, S) : (real) 1;
-    const real gmax = group_max(on ? ga : (real) 0, TPV);                     // ref :362-369
-    if (on) {
-        const real sinv = (real) 1 / S, gaq = metric_times_info(p, v, ga, q);
-        p.GaU[vk] = ga; p.T[vk] = ga * S; p.Sinv[vk] = sinv; p.GaQ[vk] = gaq; p.Gn[vk] = ga / gmax;
-        if (recond) {
-            for (int j = 0; j < width; j++) {
-                const long long s = base + ((long long) j << p.logC) + vl;
-                if (p.nbr[s] >= 0) {
-                    const size_t sk = (size_t) s * K + k;
-                    const real W = p.wk[sk] * sinv;
-                    if (p.loss == LOSS_QUAD) Z[sk] = P - gaq * (P - q + Z[sk] / W);       // ref :348-350
-                    else Z[sk] = explicit_point(p, P, gaq, q) - (ga / W) * Z[sk];          // ref :345-347,:351-353
+            const real la = p.La_d1[p.hkey[s] >> 1];
+            if (!recond && k0 == 0) p.w[s] = la;                               // ref :207-208
+#pragma unroll
+            for (int i = 0; i < LPT; i++) if (k0 + i < K) {
+                const size_t sk = (size_t) s * K + k0 + i;
+                if (!recond) { S[i] += la; Z[sk] = P[i]; }                       // ref :419-430
+                else {
+                    const real Wold = (perk_old ? p.wk[sk] : p.w[s]) * sinv_old[i];
+                    Z[sk] = (Wold / ga_old[i]) * (explicit_point(p.loss, p.aK1, P[i], gaq_old[i], q[i]) - Z[sk]);   // :137-156
+                    real d = sabs(P[i] - Pb[(size_t) n * K + k0 + i]);                                             // :210-213
+                    if (d < p.condMin) d = p.condMin;
+                    const real wv = la / d;
+                    p.wk[sk] = wv; p.thk[sk] = d; S[i] += wv;
                 }
             }
         }
-        pair_t<real> o; o.x = P; o.y = forward_point(p, P, gaq, q);
-        PF[vk] = o;
+    }
+    real ga[LPT], gloc = 0;
+#pragma unroll
+    for (int i = 0; i < LPT; i++) {
+        const bool li = on && k0 + i < K;
+        ga[i] = li ? metric(p, v, P[i], q[i], S[i]) : (real) 0;
+        gloc = max(gloc, ga[i]);
+    }
+    const real gmax = group_max(gloc, TPV);                                    // ref :362-369
+    if (on) {
+        if (!recond && k0 == 0) p.Sinv[v] = (real) 1 / S[0];
+#pragma unroll
+        for (int i = 0; i < LPT; i++) if (k0 + i < K) {
+            const real sinv = (real) 1 / S[i], gaq = metric_times_info(p, v, ga[i], q[i]);
+            if (p.GaU) p.GaU[vk + i] = ga[i];
+            p.T[vk + i] = ga[i] * S[i]; p.GaQ[vk + i] = gaq;
+            if (recond) {
+                p.Sinvk[vk + i] = sinv; p.Gn[vk + i] = ga[i] / gmax;
+                for (int j = 0; j < width; j++) {
+                    const long long s = base + ((long long) j << p.logC) + vl;
+                    if (p.nbr[s] >= 0) {
+                        const size_t sk = (size_t) s * K + k0 + i;
+                        const real W = p.wk[sk] * sinv;
+                        if (p.loss == LOSS_QUAD) Z[sk] = P[i] - gaq * (P[i] - q[i] + Z[sk] / W);                    // :348-350
+                        else Z[sk] = explicit_point(p.loss, p.aK1, P[i], gaq, q[i]) - (ga[i] / W) * Z[sk];        // :345-353
+                    }
+                }
+            }
+            Pb[vk + i] = P[i];
+            Fb[vk + i] = forward_point(p.loss, p.aK1, P[i], gaq, q[i]);
+        }
     }
     if (!recond && p.lab) {                                                   // ref :447-462
-        const int i = argmax_label(on ? P : (real) -HUGE_VAL, K, TPV);
-        if (on && k == 0) p.lab[v] = i;
+        VecN<real, LPT> pv;
+#pragma unroll
+        for (int i = 0; i < LPT; i++) pv.v[i] = P[i];
+        const int i = group_argmax<real, LPT>(pv, on ? k0 : K, K, TPV);
+        if (on && k0 == 0) p.lab[v] = i;
     }
 }
 
@@ -239,81 +288,148 @@ __global__ void simplex_resume_kernel(SP<real> p)
 // ---------------------------------------------------------------------------------------------
 // fused iteration
 // ---------------------------------------------------------------------------------------------
-template <typename real, bool PERK>
+template <typename real, int LPT, bool PERK, int LOSS, int U>
 __global__ void __launch_bounds__(256) simplex_iter_kernel(SP<real> p)
 {
+    typedef VecN<real, LPT> vec;
     __shared__ double smem[32];
     Ctl *ctl = p.ctl;
-    {
-        const int hold = ld_flag(&ctl->hold), state = ld_flag(&ctl->state);
-        if (hold != 0 || state != ST_RUN) {
-            if (hold == 0 && blockIdx.x == 0 && threadIdx.x == 0) ctl->hold = 1;
-            return;
-        }
+    const CtlView cv = load_ctl(ctl);
+    if (cv.hold != 0 || cv.state != ST_RUN) {
+        if (cv.hold == 0 && blockIdx.x == 0 && threadIdx.x == 0) ctl->hold = 1;
+        return;
     }
-    const int it = ld_flag(&ctl->it), cur = it & 1;
+    const int it = cv.it, cur = it & 1;
     const real *__restrict__ Zin = cur ? p.Z1 : p.Z0;
     real *__restrict__ Zout = cur ? p.Z0 : p.Z1;
-    const pair_t<real> *__restrict__ PFc = cur ? p.PF1 : p.PF0;
-    pair_t<real> *__restrict__ PFn = cur ? p.PF0 : p.PF1;
-    const int K = p.K, TPV = p.TPV, lane = threadIdx.x & 31;
+    const real *__restrict__ Pc = cur ? p.P1 : p.P0;
+    const real *__restrict__ Fc = cur ? p.F1 : p.F0;
+    real *__restrict__ Pn = cur ? p.P0 : p.P1;
+    real *__restrict__ Fn = cur ? p.F0 : p.F1;
+    const real *__restrict__ Tg = p.T;
+    const int *__restrict__ nbr = p.nbr;
+    const int *__restrict__ twin = p.twin;
+    const int K = p.K, TPV = p.TPV, C = p.C, lane = threadIdx.x & 31;
     const long long slice = ((long long) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const long long nslices = ((long long) p.V + p.C - 1) >> p.logC;
+    const long long nslices = ((long long) p.V + C - 1) >> p.logC;
     const real rho = p.rho;
     double red[1] = {0.0};
     if (slice < nslices) {                                                    // warp-uniform
-        const int vl = lane >> p.logTPV, k = lane & (TPV - 1);
+        const int vl = lane >> p.logTPV, k0 = (lane & (TPV - 1)) * LPT;
         const int v = (int) (slice << p.logC) + vl;
-        const bool on = (v < p.V) && (k < K);
-        const size_t vk = (size_t) (on ? v : 0) * K + (on ? k : 0);
-        const pair_t<real> pf = PFc[vk];
-        const real Tv = p.T[vk], Sv = p.Sinv[vk];
+        const bool on = (v < p.V) && (k0 < K);       // LPT == 4 requires K % 4 == 0: all LPT labels valid
+        const size_t vk = (size_t) (on ? v : 0) * K + (on ? k0 : 0);
+        const vec pold = ldv<real, LPT>(Pc + vk), fown = ldv<real, LPT>(Fc + vk), Tv = ldv<real, LPT>(Tg + vk);
+        vec Sv;
+        if (PERK) Sv = ldv<real, LPT>(p.Sinvk + vk); else Sv = splat<real, LPT>(p.Sinv[on ? v : 0]);
         const long long base = p.slice_off[slice];
         const int width = (int) ((p.slice_off[slice + 1] - base) >> p.logC);
-        real acc = 0;
-#pragma unroll 2
-        for (int j = 0; j < width; j++) {
-            const long long s = base + ((long long) j << p.logC) + vl;
-            const int n = p.nbr[s];
-            if (n >= 0 && on) {
-                const int tw = p.twin[s];
-                const size_t sk = (size_t) s * K + k, nk = (size_t) n * K + k;
-                const real zo = Zin[sk], zt = Zin[(size_t) tw * K + k];
-                const pair_t<real> pn = PFc[nk];
-                const real wv = PERK ? p.wk[sk] : p.w[s];
-                const real po = pf.y - zo, pt = pn.y - zt;
-                real zn;
-                if (p.loss == LOSS_LIN) {                                     // ref :599-614
-                    const real c = (real) 0.5 * (po + pt);
-                    real d = po - pt;
-                    if (d > (real) 2) zn = zo + rho * (c + (real) 0.5 * (d - (real) 2) - pf.x);
-                    else if (d < (real) -2) zn = zo + rho * (c + (real) 0.5 * (d + (real) 2) - pf.x);
-                    else zn = zo + rho * (c - pf.x);
-                } else {                                                      // ref :615-631
-                    const real Tn = p.T[nk];
-                    const real tsum = Tv + Tn, inv = (real) 1 / tsum;
-                    const real th = PERK ? p.thk[sk] * tsum : tsum;           // La_d1/w = 1 before a reconditioning
-                    const real wo = Tn * inv, wt = Tv * inv;
-                    const real c = wo * po + wt * pt;
-                    real d = po - pt;
-                    if (d > th) zn = zo + rho * (c + wt * (d - th) - pf.x);
-                    else if (d < -th) zn = zo + rho * (c + wt * (d + th) - pf.x);
-                    else zn = zo + rho * (c - pf.x);
-                }
-                Zout[sk] = zn;
-                acc += (wv * Sv) * zn;
-            }
+        const long long s0 = base + vl;
+        vec acc = splat<real, LPT>((real) 0);
+        // Software pipeline over the vertex's rows: the indices (and the lane's own copy) of row j+1 are
+        // requested while row j's gathers are in flight, so a row costs one memory round trip, not two.
+        int n_c = -1, tw_c = 0;
+        real w_c = 0;
+        vec zo_c = splat<real, LPT>((real) 0);
+        if (on && width > 0) {
+            n_c = nbr[s0]; tw_c = twin[s0];
+            if (!PERK) w_c = p.w[s0];
+            zo_c = ldv<real, LPT>(Zin + (size_t) s0 * K + k0);
         }
-        const real m = on ? p.Gn[vk] : (real) 1;
-        const real pnew = simplex_project<real>(on ? acc : (real) 0, m, (real) 1, k, K, TPV);
+        for (int j = 0; j < width; j++) {
+            const long long s = s0 + ((long long) j << p.logC);
+            const bool live = n_c >= 0;
+            vec zt, fn, tn, wvk, th;
+            if (live) {
+                zt = ldv<real, LPT>(Zin + (size_t) tw_c * K + k0);
+                fn = ldv<real, LPT>(Fc + (size_t) n_c * K + k0);
+                if (LOSS != LOSS_LIN) tn = ldv<real, LPT>(Tg + (size_t) n_c * K + k0);
+                if (PERK) { wvk = ldv<real, LPT>(p.wk + (size_t) s * K + k0); th = ldv<real, LPT>(p.thk + (size_t) s * K + k0); }
+            }
+            int n_n = -1, tw_n = 0;
+            real w_n = 0;
+            vec zo_n = zo_c;
+            if (on && j + 1 < width) {
+                const long long s2 = s + C;
+                n_n = nbr[s2]; tw_n = twin[s2];
+                if (!PERK) w_n = p.w[s2];
+                zo_n = ldv<real, LPT>(Zin + (size_t) s2 * K + k0);
+            }
+            if (live) {
+                vec zn;
+                const real ws = w_c * Sv.v[0];                                // row weight W = w/S (per vertex before recond.)
+#pragma unroll
+                for (int i = 0; i < LPT; i++) {
+                    const real po = fown.v[i] - zo_c.v[i], pt = fn.v[i] - zt.v[i];
+                    const real d0 = po - pt;
+                    if (LOSS == LOSS_LIN) {                                   // ref :599-614 (weights 1/2, threshold 2)
+                        const real ds = d0 - min(max(d0, (real) -2), (real) 2);
+                        zn.v[i] = zo_c.v[i] + rho * ((real) 0.5 * (po + pt) + (real) 0.5 * ds - pold.v[i]);
+                    } else {                                                  // ref :615-631
+                        const real tsum = Tv.v[i] + tn.v[i], inv = fast_rcp(tsum);
+                        const real t = PERK ? th.v[i] * tsum : tsum;          // La_d1/w = 1 before a reconditioning
+                        const real wo = tn.v[i] * inv, wt = Tv.v[i] * inv;    // W_d1 own / twin side
+                        const real ds = d0 - min(max(d0, -t), t);             // soft threshold, exact 0 inside
+                        // W_d1u.pu + W_d1v.pv = pt + wo.(po - pt) since the two weights sum to one
+                        zn.v[i] = zo_c.v[i] + rho * (fma(wo, d0, pt) + wt * ds - pold.v[i]);
+                    }
+                    acc.v[i] += (PERK ? wvk.v[i] * Sv.v[i] : ws) * zn.v[i];
+                }
+                stv<real, LPT>(Zout + (size_t) s * K + k0, zn);
+            }
+            n_c = n_n; tw_c = tw_n; w_c = w_n; zo_c = zo_n;
+        }
+        // ---- projection on the simplex in the metric m (Michelot, all lanes of the vertex in parallel) ----
+        vec m;
+        if (PERK) { if (on) m = ldv<real, LPT>(p.Gn + vk); else m = splat<real, LPT>((real) 1); }
+        else if (LOSS == LOSS_LIN) m = splat<real, LPT>((real) 1);     // Ga = 1/S is the same for all labels
+        else m = Tv;
+        vec xs;
+        unsigned act = 0;
+#pragma unroll
+        for (int i = 0; i < LPT; i++) {
+            if (!on) { m.v[i] = (real) 1; acc.v[i] = 0; }
+            xs.v[i] = acc.v[i] / m.v[i];
+            if (on && k0 + i < K) act |= 1u << i;
+        }
+        real la = 0;
+        for (;;) {
+            real sx = 0, sm = 0;
+#pragma unroll
+            for (int i = 0; i < LPT; i++) if ((act >> i) & 1u) { sx += acc.v[i]; sm += m.v[i]; }
+            sx = group_sum(sx, TPV); sm = group_sum(sm, TPV);
+            la = (sx - (real) 1) / sm;
+            unsigned keep = act;
+#pragma unroll
+            for (int i = 0; i < LPT; i++) if (((act >> i) & 1u) && xs.v[i] < la) keep &= ~(1u << i);
+            const bool changed = keep != act;
+            act = keep;
+            if (!__any_sync(0xffffffffu, changed)) break;
+        }
+        vec pnew;
+#pragma unroll
+        for (int i = 0; i < LPT; i++) pnew.v[i] = ((act >> i) & 1u) ? (xs.v[i] - la) * m.v[i] : (real) 0;
         if (on) {
-            pair_t<real> o; o.x = pnew; o.y = forward_point(p, pnew, p.GaQ[vk], p.loss == LOSS_QUAD ? p.Q[vk] : (real) 0);
-            PFn[vk] = o;
+            const vec gaq = ldv<real, LPT>(p.GaQ + vk);
+            vec qv = splat<real, LPT>((real) 0), f;
+            if (LOSS == LOSS_QUAD) qv = ldv<real, LPT>(p.Q + vk);
+#pragma unroll
+            for (int i = 0; i < LPT; i++) {
+                if (LOSS == LOSS_KLA) f.v[i] = (real) 2 * pnew.v[i] + gaq.v[i] * fast_rcp(p.aK1 + pnew.v[i]);
+                else f.v[i] = forward_point(LOSS, p.aK1, pnew.v[i], gaq.v[i], qv.v[i]);
+            }
+            stv<real, LPT>(Pn + vk, pnew);
+            stv<real, LPT>(Fn + vk, f);
         }
         if (p.by_label) {                                                     // ref :657-676
-            const int i = argmax_label(on ? pnew : (real) -HUGE_VAL, K, TPV);
-            if (on && k == 0 && ctl->track) { if (i != p.lab[v]) { red[0] = 1.0; p.lab[v] = i; } }
-        } else if (on) red[0] = (double) sabs(pf.x - pnew);                   // ref :681-687
+            const int i = group_argmax<real, LPT>(pnew, on ? k0 : K, K, TPV);
+            if (on && k0 == 0 && ctl->track) { if (i != p.lab[v]) { red[0] = 1.0; p.lab[v] = i; } }
+        } else if (on) {                                                      // ref :681-687
+            real d = 0;
+#pragma unroll
+            for (int i = 0; i < LPT; i++) d += sabs(pold.v[i] - pnew.v[i]);
+            red[0] = (double) d;
+        }
     }
     if (grid_sum_s<1>(ctl, p.partial, red, smem) && threadIdx.x == 0) {
         double dif = ctl->dif;
@@ -335,21 +451,22 @@ __global__ void __launch_bounds__(256) simplex_objective_kernel(SP<real> p)
 {
     __shared__ double smem[32];
     Ctl *ctl = p.ctl;
-    if (ld_flag(&ctl->hold)) return;
-    const int it = ld_flag(&ctl->it), K = p.K;
-    const pair_t<real> *__restrict__ PF = (it & 1) ? p.PF1 : p.PF0;
+    const CtlView cv = load_ctl(ctl);
+    if (cv.hold) return;
+    const int it = cv.it, K = p.K;
+    const real *__restrict__ P = (it & 1) ? p.P1 : p.P0;
     double r[1] = {0.0};
     const size_t stride = (size_t) gridDim.x * blockDim.x, t0 = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
     for (size_t i = t0; i < (size_t) p.V * K; i += stride) {
-        const real P = PF[i].x, q = p.Q[i];
+        const real Pv = P[i], q = p.Q[i];
         const double lf = p.La_f ? (double) p.La_f[i / K] : 1.0;
-        if (p.loss == LOSS_LIN) r[0] -= (double) P * (double) q;
-        else if (p.loss == LOSS_QUAD) { const double c = (double) P - (double) q; r[0] += 0.5 * lf * c * c; }
-        else { const real c = p.aK + p.a1 * q; r[0] += lf * (double) c * log((double) (c / (p.aK + p.a1 * P))); }
+        if (p.loss == LOSS_LIN) r[0] -= (double) Pv * (double) q;
+        else if (p.loss == LOSS_QUAD) { const double c = (double) Pv - (double) q; r[0] += 0.5 * lf * c * c; }
+        else { const real c = p.aK + p.a1 * q; r[0] += lf * (double) c * log((double) (c / (p.aK + p.a1 * Pv))); }
     }
     for (size_t i = t0; i < (size_t) p.E * K; i += stride) {
         const size_t e = i / K, k = i % K;
-        r[0] += (double) p.La_d1[e] * (double) sabs(PF[(size_t) p.Eu[e] * K + k].x - PF[(size_t) p.Ev[e] * K + k].x);
+        r[0] += (double) p.La_d1[e] * (double) sabs(P[(size_t) p.Eu[e] * K + k] - P[(size_t) p.Ev[e] * K + k]);
     }
     if (grid_sum_s<1>(ctl, p.partial, r, smem) && threadIdx.x == 0) p.dObj[it] = (real) r[0];
 }
@@ -359,8 +476,7 @@ __global__ void simplex_extract_kernel(SP<real> p, real *__restrict__ out)
 {
     const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t) p.V * p.K) return;
-    const pair_t<real> *PF = (p.ctl->it & 1) ? p.PF1 : p.PF0;
-    out[i] = PF[i].x;
+    out[i] = ((p.ctl->it & 1) ? p.P1 : p.P0)[i];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -375,14 +491,13 @@ struct SimplexSolver : SolverBase {
     DevBuf<Ctl> ctl;
     DevIn<real> Q, La_f, La_d1, P0;
     DevIn<int> Eu, Ev;
-    DevBuf<real> w, wk, thk, Z0, Z1, T, Sinv, Gn, GaQ, GaU, dObj, dDif, Pout;
-    DevBuf<pair_t<real>> PF0, PF1;
+    DevBuf<real> w, wk, thk, Z0, Z1, Pa, Pb, Fa, Fb, T, GaQ, Sinv, Sinvk, Gn, GaU, dObj, dDif, Pout, Qal;
     DevBuf<int> lab;
     DevBuf<double> partial;
     Ctl *hctl = nullptr;
     cudaEvent_t ev[2]{}, ev_a{}, ev_b{}, ev_c{};
     cudaGraphExec_t gexec = nullptr;
-    int graph_trips = 0, grid = 0;
+    int graph_trips = 0, grid = 0, LPT = 1;
 
     SimplexSolver(const SimplexProblem<real> &q_, bool keep) : q(q_), keep_p0(keep) {}
     ~SimplexSolver() override
@@ -396,23 +511,31 @@ struct SimplexSolver : SolverBase {
     {
         const int K = q.K, V = q.V, E = q.E;
         PFDR_REQUIRE(K >= 1 && V > 0 && E >= 0 && q.itMax >= 0, "K, V must be positive, E and itMax non-negative");
-        PFDR_REQUIRE(K <= 32, "K > 32 labels is not supported by this build (lanes of one warp hold the labels of a vertex)");
         PFDR_REQUIRE(q.al >= (real) 0 && q.al <= (real) 1, "al must lie in [0, 1] (the reference is undefined beyond, SURVEY 5.1-10)");
+        const char *fl = getenv("PFDR_B200_LPT");
+        LPT = (K % 4 == 0 && !(fl && fl[0] == '1')) ? 4 : 1;
+        PFDR_REQUIRE((K + LPT - 1) / LPT <= 32, "this build supports K <= 32 labels, or K <= 128 when K is a multiple of 4");
         cudaStream_t st = ctx().stream;
         for (auto *e : {&ev[0], &ev[1], &ev_a, &ev_b, &ev_c}) PFDR_CUDA(cudaEventCreate(e));
         PFDR_CUDA(cudaEventRecord(ev_a, st));
         PFDR_CUDA(cudaMallocHost((void **) &hctl, 2 * sizeof(Ctl)));
         int TPV = 1, logTPV = 0;
-        while (TPV < K) { TPV <<= 1; logTPV++; }
+        while (TPV * LPT < K) { TPV <<= 1; logTPV++; }
         const int C = 32 / TPV;
         int logC = 0; while ((1 << logC) < C) logC++;
         const size_t VK = (size_t) V * K;
         Eu.bind(q.Eu, E); Ev.bind(q.Ev, E); Q.bind(q.Q, VK); La_d1.bind(q.La_d1, E);
         La_f.bind(q.al > (real) 0 ? q.La_f : nullptr, V); P0.bind(q.P, VK);
+        if (LPT > 1 && ((uintptr_t) Q.p) % 32 != 0) {           // vector loads of Q (quadratic loss) need alignment
+            Qal.alloc(VK);
+            PFDR_CUDA(cudaMemcpyAsync(Qal.p, Q.p, VK * sizeof(real), cudaMemcpyDeviceToDevice, st));
+            Q.own = std::move(Qal); Q.p = Q.own.p;
+        }
         build_sell(g, Eu, Ev, V, E, C);
         const size_t ns = (size_t) std::max<long long>(g.nslots, 1);
         w.alloc(ns); Z0.alloc(ns * K); Z1.alloc(ns * K);
-        PF0.alloc(VK); PF1.alloc(VK); T.alloc(VK); Sinv.alloc(VK); Gn.alloc(VK); GaQ.alloc(VK); GaU.alloc(VK);
+        Pa.alloc(VK); Pb.alloc(VK); Fa.alloc(VK); Fb.alloc(VK); T.alloc(VK); GaQ.alloc(VK); Sinv.alloc(V);
+        if (q.difRcd > (real) 0) GaU.alloc(VK);
         Z0.zero(); Z1.zero(); w.zero();
         const bool by_label = q.difTol >= (real) 1;
         if (by_label) lab.alloc(V);
@@ -423,14 +546,15 @@ struct SimplexSolver : SolverBase {
         grid = (int) cdiv((size_t) nslices * 32, 256);
         partial.alloc((size_t) std::max(grid, num_sms() * 8) * 2);
 
-        p.ctl = ctl.p; p.K = K; p.V = V; p.E = E; p.TPV = TPV; p.C = C; p.logC = logC; p.logTPV = logTPV;
+        p.ctl = ctl.p; p.K = K; p.V = V; p.E = E; p.TPV = TPV; p.C = C; p.logC = logC; p.logTPV = logTPV; p.LPT = LPT;
         p.loss = (q.al == (real) 0) ? LOSS_LIN : (q.al == (real) 1 ? LOSS_QUAD : LOSS_KLA);
         p.by_label = by_label;
         p.aK = q.al / (real) K; p.a1 = (real) 1 - q.al; p.aK1 = p.aK / p.a1;                     // ref :386-391
         p.rho = q.rho; p.condMin = q.condMin;
         p.slice_off = g.slice_off.p; p.nbr = g.nbr.p; p.twin = g.twin.p; p.hkey = g.hkey.p;
-        p.w = w.p; p.wk = nullptr; p.thk = nullptr; p.Z0 = Z0.p; p.Z1 = Z1.p; p.PF0 = PF0.p; p.PF1 = PF1.p;
-        p.T = T.p; p.Sinv = Sinv.p; p.Gn = Gn.p; p.GaQ = GaQ.p; p.GaU = GaU.p; p.lab = lab.p;
+        p.w = w.p; p.wk = nullptr; p.thk = nullptr; p.Z0 = Z0.p; p.Z1 = Z1.p;
+        p.P0 = Pa.p; p.P1 = Pb.p; p.F0 = Fa.p; p.F1 = Fb.p; p.T = T.p; p.GaQ = GaQ.p; p.Sinv = Sinv.p;
+        p.Sinvk = nullptr; p.Gn = nullptr; p.GaU = GaU.p; p.lab = lab.p;
         p.Q = Q.p; p.La_f = La_f.p; p.La_d1 = La_d1.p; p.Eu = Eu.p; p.Ev = Ev.p;
         p.partial = partial.p; p.dObj = dObj.p; p.dDif = dDif.p;
 
@@ -439,12 +563,18 @@ struct SimplexSolver : SolverBase {
         PFDR_CUDA(cudaEventRecord(ev_b, st));
     }
 
+    void launch_precond(const real *Pinit, int recond)
+    {
+        if (LPT == 4) PFDR_LAUNCH((simplex_precond_kernel<real, 4>), grid, 256, 0, p, Pinit, recond);
+        else PFDR_LAUNCH((simplex_precond_kernel<real, 1>), grid, 256, 0, p, Pinit, recond);
+    }
+
     void reset() override
     {
         cudaStream_t st = ctx().stream;
         PFDR_REQUIRE(P0.p != nullptr, "reset: the initial iterate was not kept on the device");
         if (gexec && p.wk) { cudaGraphExecDestroy(gexec); gexec = nullptr; }
-        p.wk = nullptr; p.thk = nullptr;
+        p.wk = nullptr; p.thk = nullptr; p.Sinvk = nullptr; p.Gn = nullptr;
         Ctl h{};                                                                                  // ref :445-446
         h.it = 0; h.state = (q.itMax == 0) ? ST_FINAL : ST_RUN; h.itMax = q.itMax;
         h.track = (q.difTol > (real) 0 || q.difRcd > (real) 0 || q.Dif != nullptr);
@@ -452,8 +582,24 @@ struct SimplexSolver : SolverBase {
         h.dif = (double) (q.difTol > q.difRcd ? q.difTol : q.difRcd);
         hctl[0] = h;
         PFDR_CUDA(cudaMemcpyAsync(ctl.p, &hctl[0], sizeof(Ctl), cudaMemcpyHostToDevice, st));
-        PFDR_LAUNCH(simplex_precond_kernel<real>, grid, 256, 0, p, P0.p, 0);
+        launch_precond(P0.p, 0);
         PFDR_CUDA(cudaStreamSynchronize(st));
+    }
+
+    template <int L, bool PERK, int LOSS>
+    void launch_iter_u()
+    {
+        static int U = -1;
+        if (U < 0) { const char *e = getenv("PFDR_B200_U"); U = e ? atoi(e) : 0; }
+        (void) U;
+        PFDR_LAUNCH((simplex_iter_kernel<real, L, PERK, LOSS, 1>), grid, 256, 0, p);
+    }
+    template <int L, bool PERK>
+    void launch_iter_loss()
+    {
+        if (p.loss == LOSS_LIN) launch_iter_u<L, PERK, LOSS_LIN>();
+        else if (p.loss == LOSS_QUAD) launch_iter_u<L, PERK, LOSS_QUAD>();
+        else launch_iter_u<L, PERK, LOSS_KLA>();
     }
 
     void enqueue_trip()
@@ -462,8 +608,8 @@ struct SimplexSolver : SolverBase {
             const size_t work = (size_t) std::max(q.E, q.V) * q.K;
             PFDR_LAUNCH(simplex_objective_kernel<real>, std::min<unsigned>(cdiv(work, 256), num_sms() * 8), 256, 0, p);
         }
-        if (p.wk) PFDR_LAUNCH((simplex_iter_kernel<real, true>), grid, 256, 0, p);
-        else PFDR_LAUNCH((simplex_iter_kernel<real, false>), grid, 256, 0, p);
+        if (LPT == 4) { if (p.wk) launch_iter_loss<4, true>(); else launch_iter_loss<4, false>(); }
+        else { if (p.wk) launch_iter_loss<1, true>(); else launch_iter_loss<1, false>(); }
     }
     int launches_per_trip() const { return (q.Obj ? 1 : 0) + 1; }
 
@@ -493,12 +639,13 @@ struct SimplexSolver : SolverBase {
     void recondition()
     {
         if (!wk.p) {
-            const size_t n = (size_t) std::max<long long>(g.nslots, 1) * q.K;
+            const size_t n = (size_t) std::max<long long>(g.nslots, 1) * q.K, VK = (size_t) q.V * q.K;
             wk.alloc(n); thk.alloc(n); wk.zero(); thk.zero();
-            p.wk = wk.p; p.thk = thk.p;
+            Sinvk.alloc(VK); Gn.alloc(VK);
         }
+        p.wk = wk.p; p.thk = thk.p; p.Sinvk = Sinvk.p; p.Gn = Gn.p;
         if (gexec) { cudaGraphExecDestroy(gexec); gexec = nullptr; }
-        PFDR_LAUNCH(simplex_precond_kernel<real>, grid, 256, 0, p, (const real *) nullptr, 1);
+        launch_precond(nullptr, 1);
         PFDR_LAUNCH(simplex_resume_kernel<real>, 1, 1, 0, p);
     }
 
@@ -601,8 +748,33 @@ template void solve_simplex<float>(const SimplexProblem<float> &);
 template void solve_simplex<double>(const SimplexProblem<double> &);
 
 // ---------------------------------------------------------------------------------------------
-// stand-alone proj_simplex_metric (ref src/proj_simplex_metric.cpp:18-83)
+// stand-alone proj_simplex_metric (ref src/proj_simplex_metric.cpp:18-83).  Here the lanes of a column run the
+// reference's *sequential* recursion redundantly through shuffles, so the result tracks the reference to
+// the last bits (the fused iteration above uses the cheaper parallel active-set form).
 // ---------------------------------------------------------------------------------------------
+template <typename real>
+__device__ __forceinline__ real simplex_project_seq(real x, real m, real target, int k, int K, int TPV)
+{
+    const unsigned full = 0xffffffffu;
+    const real xs = x / m;
+    const real x0 = __shfl_sync(full, x, 0, TPV), m0 = __shfl_sync(full, m, 0, TPV);
+    real la = (x0 - target) / m0, s = m0;
+    unsigned act = 1u;
+    for (int d = 1; d < K; d++) {                                  // first pass  :49-58
+        const real xd = __shfl_sync(full, xs, d, TPV), md = __shfl_sync(full, m, d, TPV);
+        if (xd > la) { act |= 1u << d; s += md; la += md * (xd - la) / s; }
+    }
+    for (;;) {                                                     // pruning passes :60-73
+        bool changed = false;
+        for (int d = 0; d < K; d++) {
+            const real xd = __shfl_sync(full, xs, d, TPV), md = __shfl_sync(full, m, d, TPV);
+            if (((act >> d) & 1u) && xd < la) { act &= ~(1u << d); s -= md; la += md * (la - xd) / s; changed = true; }
+        }
+        if (!__any_sync(full, changed)) break;
+    }
+    return ((act >> k) & 1u) ? (xs - la) * m : (real) 0;           // :75-81
+}
+
 template <typename real>
 __global__ void __launch_bounds__(256) proj_small_kernel(real *__restrict__ X, const real *__restrict__ M, int D, int N,
                                                          int nm, const real *__restrict__ A, int na, int TPV, int logTPV)
@@ -618,7 +790,7 @@ __global__ void __launch_bounds__(256) proj_small_kernel(real *__restrict__ X, c
     const size_t mi = (size_t) (on ? (n < nm ? n : nm - 1) : 0) * D + (on ? d : 0);
     const real x = on ? X[xi] : (real) 0, m = on ? M[mi] : (real) 1;
     const real a = A[on ? (n < na ? n : na - 1) : 0];
-    const real r = simplex_project<real>(x, m, a, d, D, TPV);
+    const real r = simplex_project_seq<real>(x, m, a, d, D, TPV);
     if (on) X[xi] = r;
 }
 

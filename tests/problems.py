@@ -109,13 +109,15 @@ def run_quad(binder, name, dtype):
 
 
 SIMPLEX_CASES = ["kla", "kla_weighted", "kla_recond", "kla_labels", "kla_k16", "kla_k3", "kla_k1", "kla_k32",
+                 "kla_k12", "kla_k64", "kla_recond_k16", "kla_labels_k16", "kla_weighted_k16", "lin_k16", "lin_recond_k16",
+                 "quad_k16", "quad_recond_k16", "quad_weighted_k16", "kla_rand_k16",
                  "lin", "lin_recond", "quad", "quad_weighted", "quad_recond", "kla_rand", "kla_it0", "kla_notrack"]
 
 
 def simplex_case(name, dtype):
     K = 5
-    for tag, k in (("k16", 16), ("k3", 3), ("k1", 1), ("k32", 32)):
-        if tag in name:
+    for tag, k in (("k16", 16), ("k3", 3), ("k1", 1), ("k32", 32), ("k12", 12), ("k64", 64)):
+        if name.endswith("_" + tag) or ("_" + tag + "_") in name:
             K = k
     al = 0.0 if name.startswith("lin") else (1.0 if name.startswith("quad") else 0.05)
     kw = dict(rho=1.5, condMin=1e-2, difRcd=0.0, difTol=1e-4, itMax=150, want_obj=True, want_dif=True)
@@ -128,7 +130,7 @@ def simplex_case(name, dtype):
         Q = (Q / Q.sum(axis=1, keepdims=True)).astype(dtype)
         La_d1 = rng.uniform(0.05, 0.3, Eu.shape[0]).astype(dtype)
     else:
-        w = synth.c4_simplex(9 if K <= 5 else 7, K, dtype)
+        w = synth.c4_simplex(9 if K <= 5 else (7 if K <= 16 else 5), K, dtype)
         V, Eu, Ev, Q, La_d1 = w["V"], w["Eu"], w["Ev"], w["Q"], w["La_d1"]
     if "weighted" in name:
         kw["La_f"] = np.random.default_rng(9).uniform(0.5, 2.0, V).astype(dtype)
