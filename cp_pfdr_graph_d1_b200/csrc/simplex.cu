@@ -28,7 +28,7 @@ enum : int { LOSS_LIN = 0, LOSS_QUAD = 1, LOSS_KLA = 2 };
 template <typename real>
 struct SP {
     Ctl *ctl;
-    int K, V, E, TPV, C, logC, logTPV, loss, by_label, LPT;
+    int K, V, E, TPV, C, logC, logTPV, loss, by_label, LPT, stream_z;
     real aK, a1, aK1, rho, condMin;
     const long long *slice_off; const int *nbr, *twin, *hkey;
     real *w;                      // [slots]   raw weight before any reconditioning (= La_d1[e] for every label)
@@ -72,6 +72,17 @@ __device__ __forceinline__ void stv(real *q, const VecN<real, L> &r)
     else {
         *reinterpret_cast<double2 *>(q) = make_double2(r.v[0], r.v[1]);
         *reinterpret_cast<double2 *>(q + 2) = make_double2(r.v[2], r.v[3]);
+    }
+}
+// streaming (evict-first) store: the new edge copies are not touched again during this launch
+template <typename real, int L>
+__device__ __forceinline__ void stv_cs(real *q, const VecN<real, L> &r)
+{
+    if constexpr (L == 1) __stcs(q, r.v[0]);
+    else if constexpr (sizeof(real) == 4) __stcs(reinterpret_cast<float4 *>(q), make_float4(r.v[0], r.v[1], r.v[2], r.v[3]));
+    else {
+        __stcs(reinterpret_cast<double2 *>(q), make_double2(r.v[0], r.v[1]));
+        __stcs(reinterpret_cast<double2 *>(q + 2), make_double2(r.v[2], r.v[3]));
     }
 }
 template <typename real, int L>
@@ -288,8 +299,8 @@ __global__ void simplex_resume_kernel(SP<real> p)
 // ---------------------------------------------------------------------------------------------
 // fused iteration
 // ---------------------------------------------------------------------------------------------
-template <typename real, int LPT, bool PERK, int LOSS, int U>
-__global__ void __launch_bounds__(256) simplex_iter_kernel(SP<real> p)
+template <typename real, int LPT, bool PERK, int LOSS, int MINB>
+__global__ void __launch_bounds__(256, MINB) simplex_iter_kernel(SP<real> p)
 {
     typedef VecN<real, LPT> vec;
     __shared__ double smem[32];
@@ -375,7 +386,7 @@ __global__ void __launch_bounds__(256) simplex_iter_kernel(SP<real> p)
                     }
                     acc.v[i] += (PERK ? wvk.v[i] * Sv.v[i] : ws) * zn.v[i];
                 }
-                stv<real, LPT>(Zout + (size_t) s * K + k0, zn);
+                if (p.stream_z) stv_cs<real, LPT>(Zout + (size_t) s * K + k0, zn); else stv<real, LPT>(Zout + (size_t) s * K + k0, zn);
             }
             n_c = n_n; tw_c = tw_n; w_c = w_n; zo_c = zo_n;
         }
@@ -557,6 +568,7 @@ struct SimplexSolver : SolverBase {
         p.Sinvk = nullptr; p.Gn = nullptr; p.GaU = GaU.p; p.lab = lab.p;
         p.Q = Q.p; p.La_f = La_f.p; p.La_d1 = La_d1.p; p.Eu = Eu.p; p.Ev = Ev.p;
         p.partial = partial.p; p.dObj = dObj.p; p.dDif = dDif.p;
+        { const char *e = getenv("PFDR_B200_STREAMZ"); p.stream_z = (e && e[0] == '1') ? 1 : 0; }
 
         reset();
         if (!keep_p0) P0.own.release();
@@ -591,8 +603,15 @@ struct SimplexSolver : SolverBase {
     {
         static int U = -1;
         if (U < 0) { const char *e = getenv("PFDR_B200_U"); U = e ? atoi(e) : 0; }
+        // PFDR_B200_MINB (tuning): minimum resident CTAs per SM the compiler must fit registers for
+        static int MB = -1;
+        if (MB < 0) { const char *e = getenv("PFDR_B200_MINB"); MB = e ? atoi(e) : 0; }
         (void) U;
-        PFDR_LAUNCH((simplex_iter_kernel<real, L, PERK, LOSS, 1>), grid, 256, 0, p);
+        if (L == 4 && !PERK && LOSS == LOSS_KLA && MB == 5) PFDR_LAUNCH((simplex_iter_kernel<real, 4, false, LOSS_KLA, 5>), grid, 256, 0, p);
+        else if (L == 4 && !PERK && LOSS == LOSS_KLA && MB == 6) PFDR_LAUNCH((simplex_iter_kernel<real, 4, false, LOSS_KLA, 6>), grid, 256, 0, p);
+        else if (L == 4 && !PERK && LOSS == LOSS_KLA && MB == 8) PFDR_LAUNCH((simplex_iter_kernel<real, 4, false, LOSS_KLA, 8>), grid, 256, 0, p);
+        else if (L == 4 && !PERK && LOSS == LOSS_KLA && MB == 1) PFDR_LAUNCH((simplex_iter_kernel<real, 4, false, LOSS_KLA, 1>), grid, 256, 0, p);
+        else PFDR_LAUNCH((simplex_iter_kernel<real, L, PERK, LOSS, 4>), grid, 256, 0, p);
     }
     template <int L, bool PERK>
     void launch_iter_loss()
