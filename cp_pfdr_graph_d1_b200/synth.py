@@ -78,3 +78,53 @@ def dense_problem(n=16, N=64, dtype=np.float32, seed=7):
     x0[(z >= 2 * n // 3) & (y >= n // 2)] = 2.0
     Y = (A.astype(np.float64) @ x0).astype(dtype)
     return dict(V=V, E=Eu.shape[0], N=N, A=A, Y=Y, Eu=Eu, Ev=Ev, La_d1=np.full(Eu.shape[0], 0.05, dtype), x0=x0)
+
+
+def icosphere(level=5):
+    """triangulated unit sphere: vertices (V, 3) and undirected mesh edges (u < v); V = 10*4^level + 2"""
+    t = (1.0 + 5.0 ** 0.5) / 2.0
+    verts = [(-1, t, 0), (1, t, 0), (-1, -t, 0), (1, -t, 0), (0, -1, t), (0, 1, t), (0, -1, -t), (0, 1, -t),
+             (t, 0, -1), (t, 0, 1), (-t, 0, -1), (-t, 0, 1)]
+    faces = [(0, 11, 5), (0, 5, 1), (0, 1, 7), (0, 7, 10), (0, 10, 11), (1, 5, 9), (5, 11, 4), (11, 10, 2), (10, 7, 6),
+             (7, 1, 8), (3, 9, 4), (3, 4, 2), (3, 2, 6), (3, 6, 8), (3, 8, 9), (4, 9, 5), (2, 4, 11), (6, 2, 10),
+             (8, 6, 7), (9, 8, 1)]
+    verts = [np.array(v, float) / np.linalg.norm(v) for v in verts]
+    for _ in range(level):
+        cache, nf = {}, []
+
+        def mid(a, b):
+            key = (min(a, b), max(a, b))
+            if key not in cache:
+                m = verts[a] + verts[b]
+                verts.append(m / np.linalg.norm(m))
+                cache[key] = len(verts) - 1
+            return cache[key]
+        for a, b, c in faces:
+            ab, bc, ca = mid(a, b), mid(b, c), mid(c, a)
+            nf += [(a, ab, ca), (b, bc, ab), (c, ca, bc), (ab, bc, ca)]
+        faces = nf
+    F = np.array(faces)
+    e = np.concatenate([F[:, [0, 1]], F[:, [1, 2]], F[:, [2, 0]]])
+    e = np.unique(np.sort(e, axis=1), axis=0)
+    return np.array(verts), e[:, 0].astype(np.int32), e[:, 1].astype(np.int32)
+
+
+def eeg_like(level=5, N=91, dtype=np.float64, seed=1):
+    """C1 stand-in (data/EEG.mat is absent from the reference checkout): icosphere cortex,
+    N sensors on a concentric sphere with a smooth dipole-like lead field, sparse positive piecewise-constant
+    sources, noisy observations; parameters of octave/example_EEG_CP.m:20-27 apply."""
+    rng = np.random.default_rng(seed)
+    P, Eu, Ev = icosphere(level)
+    V = P.shape[0]
+    S = rng.standard_normal((N, 3))
+    S = 1.25 * S / np.linalg.norm(S, axis=1, keepdims=True)
+    D = S[:, None, :] - P[None, :, :]
+    A = np.einsum("nvk,vk->nv", D, P) / np.linalg.norm(D, axis=2) ** 3          # radial dipole potential
+    A /= np.linalg.norm(A, axis=0, keepdims=True).mean()
+    x0 = np.zeros(V)
+    for c, val in zip(rng.choice(V, 4, replace=False), (1.0, 1.5, 2.0, 1.0)):
+        x0[np.arccos(np.clip(P @ P[c], -1, 1)) < 0.25] = val
+    y = A @ x0
+    y = y + 0.02 * np.abs(y).max() * rng.standard_normal(N)
+    return dict(V=V, E=Eu.shape[0], N=N, A=np.asfortranarray(A.astype(dtype)), Y=y.astype(dtype), Eu=Eu, Ev=Ev,
+                La_d1=np.full(Eu.shape[0], 0.02, dtype), La_l1=np.full(V, 0.005, dtype), x0=x0, points=P)

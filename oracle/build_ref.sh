@@ -32,3 +32,21 @@ done
 for p in "${pids[@]}"; do wait "$p"; done
 g++ -shared -fopenmp -Wl,-Bsymbolic-functions -o "$OUT/libref.so" "${objs[@]}"
 echo "built $OUT/libref.so"
+
+# Drop-in check: the reference's UNMODIFIED cut-pursuit objects (CP_*.cpp, graph.cpp, maxflow.cpp) linked
+# against the B200 shim (cp_pfdr_graph_d1_b200/lib/libpfdr_b200_shim.so) instead of the reference's PFDR objects.
+#   libcp_b200.so          every hot-path routine from libpfdr_b200 (incl. operator_norm_matrix)
+#   libcp_b200_refnorm.so  the reference's own operator_norm_matrix kept (isolates the PFDR solvers)
+SHIMDIR="$HERE/../cp_pfdr_graph_d1_b200/lib"
+if [ -f "$SHIMDIR/libpfdr_b200_shim.so" ]; then
+    cp_objs=()
+    for f in CP_PFDR_graph_quadratic_d1_l1 CP_PFDR_graph_quadratic_d1_l1_duplex CP_PFDR_graph_quadratic_d1_bounds \
+             CP_PFDR_graph_loss_d1_simplex graph maxflow ref_wrap_l1 ref_wrap_bounds ref_wrap_misc; do
+        cp_objs+=("$OUT/obj/$f.o")
+    done
+    LINK=(-shared -fopenmp -Wl,-Bsymbolic-functions -L"$SHIMDIR" -lpfdr_b200_shim -lpfdr_b200
+          -Wl,-rpath,'$ORIGIN/../../cp_pfdr_graph_d1_b200/lib')
+    g++ -o "$OUT/libcp_b200.so" "${cp_objs[@]}" "${LINK[@]}"
+    g++ -o "$OUT/libcp_b200_refnorm.so" "${cp_objs[@]}" "$OUT/obj/operator_norm_matrix.o" "${LINK[@]}"
+    echo "built $OUT/libcp_b200.so $OUT/libcp_b200_refnorm.so"
+fi

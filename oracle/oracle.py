@@ -44,3 +44,98 @@ def reference():
         lib.ref_num_procs.restype = C.c_int
         _r = Binder(lib, "ref_", returns_status=False)
     return _r
+
+
+# ---------------------------------------------------------------------------------------------------
+# cut-pursuit gateways (the reference's UNMODIFIED CP_*.cpp): libref.so runs them on the reference's own
+# PFDR, libcp_b200*.so on the B200 PFDR through the drop-in shim (oracle/build_ref.sh).
+# ---------------------------------------------------------------------------------------------------
+import numpy as np  # noqa: E402
+
+CP_B200_SO = os.path.join(_HERE, "_ref", "libcp_b200.so")
+CP_B200_REFNORM_SO = os.path.join(_HERE, "_ref", "libcp_b200_refnorm.so")
+
+
+class CutPursuit:
+    def __init__(self, path):
+        self.lib = C.CDLL(path)
+
+    def _common(self, dt):
+        R = C.c_float if dt == np.float32 else C.c_double
+        return R, "f32" if dt == np.float32 else "f64", C.POINTER(R), C.POINTER(C.c_int)
+
+    def _finish(self, V, rV, Cv, rXp, dt, CP_it, Time, Obj, Dif):
+        n = rV.value
+        rX = np.ctypeslib.as_array(rXp, shape=(n,)).copy() if n else np.zeros(0, dt)
+        self.lib.ref_free.argtypes = [C.c_void_p]
+        self.lib.ref_free(C.cast(rXp, C.c_void_p))
+        k = CP_it.value
+        return dict(rV=n, Cv=Cv, rX=rX, CP_it=k, Time=Time[:k + 1], Obj=Obj[:k + 1], Dif=Dif[:k])
+
+    def quadratic_d1_l1(self, Y, A, Eu, Ev, La_d1, La_l1, positivity, N, CP_difTol=1e-4, CP_itMax=15, rho=1.5,
+                        condMin=1e-3, difRcd=0.0, difTol=1e-7, itMax=10000, verbose=0, duplex=0):
+        dt = Y.dtype.type
+        R, suf, PR, PI = self._common(dt)
+        V, E = (A.shape[1] if N > 0 else Y.shape[0]), Eu.shape[0]
+        f = getattr(self.lib, f"ref_CP_PFDR_graph_quadratic_d1_l1_{suf}")
+        f.restype = None
+        f.argtypes = [C.c_int, C.c_int, C.c_int, PI, PI, C.POINTER(PR), PR, PR, PI, PI, PR, PR, C.c_int, R, C.c_int,
+                      PI, R, R, R, R, C.c_int, C.POINTER(C.c_double), PR, PR, C.c_int, C.c_int]
+        rV, CP_it, rXp = C.c_int(0), C.c_int(0), PR()
+        Cv = np.zeros(V, np.int32)
+        Time, Obj, Dif = np.zeros(CP_itMax + 1), np.zeros(CP_itMax + 1, dt), np.zeros(max(CP_itMax, 1), dt)
+        p = lambda a, t=R: None if a is None else a.ctypes.data_as(C.POINTER(t))
+        f(V, E, N, C.byref(rV), p(Cv, C.c_int), C.byref(rXp), p(Y), p(A), p(Eu, C.c_int), p(Ev, C.c_int), p(La_d1),
+          p(La_l1), positivity, CP_difTol, CP_itMax, C.byref(CP_it), rho, condMin, difRcd, difTol, itMax,
+          Time.ctypes.data_as(C.POINTER(C.c_double)), p(Obj), p(Dif), verbose, duplex)
+        return self._finish(V, rV, Cv, rXp, dt, CP_it, Time, Obj, Dif)
+
+    def quadratic_d1_bounds(self, Y, A, Eu, Ev, La_d1, lo, hi, N, CP_difTol=1e-4, CP_itMax=10, rho=1.5, condMin=1e-3,
+                            difRcd=0.0, difTol=1e-7, itMax=10000, verbose=0):
+        dt = Y.dtype.type
+        R, suf, PR, PI = self._common(dt)
+        V, E = (A.shape[1] if N > 0 else Y.shape[0]), Eu.shape[0]
+        f = getattr(self.lib, f"ref_CP_PFDR_graph_quadratic_d1_bounds_{suf}")
+        f.restype = None
+        f.argtypes = [C.c_int, C.c_int, C.c_int, PI, PI, C.POINTER(PR), PR, PR, PI, PI, PR, R, R, R, C.c_int, PI, R, R,
+                      R, R, C.c_int, C.POINTER(C.c_double), PR, PR, C.c_int]
+        rV, CP_it, rXp = C.c_int(0), C.c_int(0), PR()
+        Cv = np.zeros(V, np.int32)
+        Time, Obj, Dif = np.zeros(CP_itMax + 1), np.zeros(CP_itMax + 1, dt), np.zeros(max(CP_itMax, 1), dt)
+        p = lambda a, t=R: None if a is None else a.ctypes.data_as(C.POINTER(t))
+        f(V, E, N, C.byref(rV), p(Cv, C.c_int), C.byref(rXp), p(Y), p(A), p(Eu, C.c_int), p(Ev, C.c_int), p(La_d1),
+          lo, hi, CP_difTol, CP_itMax, C.byref(CP_it), rho, condMin, difRcd, difTol, itMax,
+          Time.ctypes.data_as(C.POINTER(C.c_double)), p(Obj), p(Dif), verbose)
+        return self._finish(V, rV, Cv, rXp, dt, CP_it, Time, Obj, Dif)
+
+    def loss_d1_simplex(self, Q, al, Eu, Ev, La_d1, CP_difTol=1e-3, CP_itMax=10, rho=1.5, condMin=1e-2, difRcd=0.0,
+                        difTol=1e-4, itMax=1000, verbose=0):
+        dt = Q.dtype.type
+        R, suf, PR, PI = self._common(dt)
+        V, K, E = Q.shape[0], Q.shape[1], Eu.shape[0]
+        f = getattr(self.lib, f"ref_CP_PFDR_graph_loss_d1_simplex_{suf}")
+        f.restype = None
+        f.argtypes = [C.c_int, C.c_int, C.c_int, R, PI, PI, C.POINTER(PR), PR, PI, PI, PR, R, C.c_int, PI, R, R, R, R,
+                      C.c_int, C.POINTER(C.c_double), PR, PR, C.c_int]
+        rV, CP_it, rPp = C.c_int(0), C.c_int(0), PR()
+        Cv = np.zeros(V, np.int32)
+        Time, Obj, Dif = np.zeros(CP_itMax + 1), np.zeros(CP_itMax + 1, dt), np.zeros(max(CP_itMax, 1), dt)
+        p = lambda a, t=R: None if a is None else a.ctypes.data_as(C.POINTER(t))
+        f(K, V, E, al, C.byref(rV), p(Cv, C.c_int), C.byref(rPp), p(Q), p(Eu, C.c_int), p(Ev, C.c_int), p(La_d1),
+          CP_difTol, CP_itMax, C.byref(CP_it), rho, condMin, difRcd, difTol, itMax,
+          Time.ctypes.data_as(C.POINTER(C.c_double)), p(Obj), p(Dif), verbose)
+        n = rV.value
+        rP = np.ctypeslib.as_array(rPp, shape=(n, K)).copy()
+        self.lib.ref_free.argtypes = [C.c_void_p]
+        self.lib.ref_free(C.cast(rPp, C.c_void_p))
+        k = CP_it.value
+        return dict(rV=n, Cv=Cv, rX=rP, CP_it=k, Time=Time[:k + 1], Obj=Obj[:k + 1], Dif=Dif[:k])
+
+
+def cp_reference():
+    return CutPursuit(REF_SO) if os.path.exists(REF_SO) else None
+
+
+def cp_b200(refnorm=False):
+    path = CP_B200_REFNORM_SO if refnorm else CP_B200_SO
+    return CutPursuit(path) if os.path.exists(path) else None

@@ -1,0 +1,71 @@
+"""Drop-in check on the GPU: the reference's UNMODIFIED cut-pursuit (CP_*.cpp + BK maxflow, compiled where they
+lie by oracle/build_ref.sh) runs once on the reference's own PFDR (oracle/_ref/libref.so) and once on the B200
+PFDR through the C++ shim (oracle/_ref/libcp_b200*.so).  BASELINE.json: identical component counts and
+vertex->component assignments, reduced values within 1e-5 relative in float64."""
+import numpy as np
+import pytest
+
+from cp_pfdr_graph_d1_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cps(gpu_api):
+    from oracle import oracle as O
+    ref, b200n, b200 = O.cp_reference(), O.cp_b200(refnorm=True), O.cp_b200()
+    if ref is None or b200 is None or b200n is None:
+        pytest.skip("oracle/_ref cut-pursuit libraries not built (need /root/reference at build time)")
+    return ref, b200n, b200
+
+
+def rel(a, b):
+    return float(np.linalg.norm(a - b) / max(float(np.linalg.norm(b)), 1e-300))
+
+
+def check(r0, r1, tol=1e-5, strict=True):
+    if strict:
+        assert r1["rV"] == r0["rV"] and r1["CP_it"] == r0["CP_it"]
+        assert np.array_equal(r1["Cv"], r0["Cv"])
+        assert rel(r1["rX"], r0["rX"]) < tol
+        assert np.allclose(r1["Obj"], r0["Obj"], rtol=tol)
+    else:   # a different power-method start changes the metric, not the minimiser
+        x0, x1 = r0["rX"][r0["Cv"]], r1["rX"][r1["Cv"]]
+        assert rel(x1, x0) < 1e-2
+        assert abs(r1["Obj"][-1] - r0["Obj"][-1]) <= 1e-3 * abs(r0["Obj"][-1])
+
+
+@pytest.mark.parametrize("duplex", [0, 1])
+def test_cp_quadratic_l1_eeg_like(cps, duplex):
+    """config 1 stand-in (data/EEG.mat is absent): parameters of octave/example_EEG_CP.m:20-27"""
+    ref, b200n, b200 = cps
+    w = synth.eeg_like(4, 60, np.float64)
+    kw = dict(CP_difTol=1e-4, CP_itMax=6, rho=1.5, condMin=1e-3, difRcd=0.0, difTol=1e-7, itMax=3000, duplex=duplex)
+    args = (w["Y"], w["A"], w["Eu"], w["Ev"], w["La_d1"], w["La_l1"], 1, w["N"])
+    r0 = ref.quadratic_d1_l1(*args, **kw)
+    assert r0["rV"] > 10
+    check(r0, b200n.quadratic_d1_l1(*args, **kw))
+    check(r0, b200.quadratic_d1_l1(*args, **kw), strict=False)
+
+
+def test_cp_quadratic_bounds_ata(cps):
+    """config 3 in miniature: dense precomputed A^tA, box [0,1], k-NN graph"""
+    ref, b200n, b200 = cps
+    w = synth.c3_bounds_ata(600, 8, 256, np.float64)
+    kw = dict(CP_difTol=1e-4, CP_itMax=6, rho=1.5, condMin=1e-3, difRcd=0.0, difTol=1e-7, itMax=3000)
+    args = (w["AtY"], w["AtA"], w["Eu"], w["Ev"], w["La_d1"], 0.0, 1.0, -w["V"])
+    r0 = ref.quadratic_d1_bounds(*args, **kw)
+    check(r0, b200n.quadratic_d1_bounds(*args, **kw))
+    check(r0, b200.quadratic_d1_bounds(*args, **kw), strict=False)
+
+
+def test_cp_simplex(cps):
+    """CP variant of config 4 at parity size"""
+    ref, b200n, _ = cps
+    w = synth.c4_simplex(12, 6, np.float64)
+    kw = dict(CP_difTol=1e-3, CP_itMax=5, rho=1.5, condMin=1e-2, difRcd=0.0, difTol=1e-5, itMax=1000)
+    args = (w["Q"], 0.05, w["Eu"], w["Ev"], w["La_d1"])
+    r0 = ref.loss_d1_simplex(*args, **kw)
+    r1 = b200n.loss_d1_simplex(*args, **kw)
+    assert r1["rV"] == r0["rV"] and np.array_equal(r1["Cv"], r0["Cv"])
+    assert rel(r1["rX"], r0["rX"]) < 1e-5
