@@ -1,4 +1,6 @@
 """Seeded problem instances shared by the parity tests (CPU and GPU)."""
+import zlib
+
 import numpy as np
 
 from cp_pfdr_graph_d1_b200 import synth
@@ -31,7 +33,7 @@ def random_graph(V, E, seed, self_loops=3, dups=5, hub=True):
 def quad_case(name, dtype):
     """returns (family, args, kwargs) for Binder.PFDR_graph_quadratic_d1_{l1,bounds}; X starts at zero
     unless stated."""
-    rng = np.random.default_rng(abs(hash(name)) % (2 ** 31))
+    rng = np.random.default_rng(zlib.crc32(name.encode()))
     kw = dict(rho=1.5, condMin=1e-3, difRcd=0.0, difTol=1e-5, itMax=300, want_obj=True, want_dif=True)
     if name.startswith("grid"):
         n = 13

@@ -1,0 +1,86 @@
+"""Golden vectors: outputs of the reference itself (tests/golden/make_golden.py) for seeded inputs.
+CPU: the oracle restatement reproduces them.  GPU (-m gpu): the CUDA path reproduces them through the C ABI."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import problems
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+import make_golden as G  # noqa: E402
+
+GOLD = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_outputs.npz"))
+TOL_ORACLE = {np.float32: 2e-4, np.float64: 1e-9}
+TOL_GPU = {np.float32: 1e-3, np.float64: 1e-5}
+
+
+def rel(a, b):
+    return float(np.linalg.norm(a.astype(np.float64) - b) / max(float(np.linalg.norm(b)), 1e-300))
+
+
+def check(kind, name, dtype, binder, tol):
+    tag = np.dtype(dtype).name
+    if kind == "quad":
+        fam, args, kw = problems.quad_case(name, dtype)
+        r = problems.run_quad(binder, name, dtype)
+    else:
+        args, kw = problems.simplex_case(name, dtype)
+        r = problems.run_simplex(binder, name, dtype)
+    assert G.digest(args) == str(GOLD[f"{kind}/{name}/{tag}/sha"]), "seeded inputs drifted: regenerate the fixtures"
+    git = int(GOLD[f"{kind}/{name}/{tag}/it"])
+    assert abs(r.it - git) <= (0 if dtype is np.float64 else max(2, git // 10))
+    assert rel(r.X, GOLD[f"{kind}/{name}/{tag}/X"]) < tol
+    key = f"{kind}/{name}/{tag}/Obj"
+    if key in GOLD.files and r.Obj is not None:
+        n = min(r.it, git) + 1
+        g = GOLD[key]
+        assert np.allclose(r.Obj[:n], g[:n], rtol=10 * tol, atol=tol * max(float(np.abs(g).max()), 1.0) * 0.1)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("name", G.QUAD)
+def test_oracle_quadratic_golden(oracle, name, dtype):
+    check("quad", name, dtype, oracle, TOL_ORACLE[dtype])
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("name", G.SIMPLEX)
+def test_oracle_simplex_golden(oracle, name, dtype):
+    check("simplex", name, dtype, oracle, TOL_ORACLE[dtype])
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_oracle_proj_golden(oracle, dtype):
+    rng = np.random.default_rng(11)
+    X = rng.normal(0.3, 1.0, (300, 9)).astype(dtype)
+    M = rng.uniform(0.2, 1.0, (300, 9)).astype(dtype)
+    A = rng.uniform(0.5, 2.0, 3).astype(dtype)
+    assert np.array_equal(oracle.proj_simplex_metric(X.copy(), M, A), GOLD[f"proj/{np.dtype(dtype).name}/X"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("name", G.QUAD)
+def test_gpu_quadratic_golden(gpu_api, name, dtype):
+    check("quad", name, dtype, gpu_api._b(), TOL_GPU[dtype])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("name", G.SIMPLEX)
+def test_gpu_simplex_golden(gpu_api, name, dtype):
+    check("simplex", name, dtype, gpu_api._b(), TOL_GPU[dtype])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_gpu_proj_golden(gpu_api, dtype):
+    rng = np.random.default_rng(11)
+    X = rng.normal(0.3, 1.0, (300, 9)).astype(dtype)
+    M = rng.uniform(0.2, 1.0, (300, 9)).astype(dtype)
+    A = rng.uniform(0.5, 2.0, 3).astype(dtype)
+    got = gpu_api.proj_simplex_metric(X.copy(), M, A)
+    assert np.allclose(got, GOLD[f"proj/{np.dtype(dtype).name}/X"], rtol=1e-4 if dtype is np.float32 else 1e-11,
+                       atol=1e-6 if dtype is np.float32 else 1e-14)
