@@ -158,6 +158,53 @@ int pfdr_b200_solver_create_simplex_##SUF(pfdr_b200_solver **out, int K, int V, 
 HANDLE(f32, float)
 HANDLE(f64, double)
 
+/* ---- sharded handles: the shard description is only read during create ---- */
+#define HANDLE_SHARDED(SUF, real)                                                                       \
+int pfdr_b200_solver_create_quadratic_sharded_##SUF(pfdr_b200_solver **out, const pfdr_b200_shard *sh,  \
+    int prox_kind, int V, int E, int N, const real *X0, const real *Y, const real *A, const int *Eu,    \
+    const int *Ev, const real *La_d1, const real *La_l1, int positivity, real lo, real hi, int Ltype,   \
+    const real *L, real rho, real condMin, real difRcd, real difTol, int itMax, int want_obj,           \
+    int want_dif)                                                                                       \
+{                                                                                                       \
+    return guarded([&] {                                                                                \
+        PFDR_REQUIRE(out != nullptr && sh != nullptr, "solver_create_sharded: NULL argument");          \
+        real *flag = reinterpret_cast<real *>(sizeof(real));                                            \
+        QuadProblem<real> q{V, E, N, const_cast<real *>(X0), Y, A, Eu, Ev, La_d1,                       \
+                            prox_kind == 0 ? La_l1 : nullptr, prox_kind == 0 ? positivity : 0,          \
+                            prox_kind, lo, hi, Ltype, L, rho, condMin, difRcd, difTol, itMax, nullptr,  \
+                            want_obj ? flag : nullptr, want_dif ? flag : nullptr, 0, sh};               \
+        *out = reinterpret_cast<pfdr_b200_solver *>(make_quadratic<real>(q));                           \
+    });                                                                                                 \
+}                                                                                                       \
+int pfdr_b200_solver_create_simplex_sharded_##SUF(pfdr_b200_solver **out, const pfdr_b200_shard *sh,    \
+    int K, int V, int E, real al, const real *La_f, const real *P0, const real *Q, const int *Eu,       \
+    const int *Ev, const real *La_d1, real rho, real condMin, real difRcd, real difTol, int itMax,      \
+    int want_obj, int want_dif)                                                                         \
+{                                                                                                       \
+    return guarded([&] {                                                                                \
+        PFDR_REQUIRE(out != nullptr && sh != nullptr, "solver_create_sharded: NULL argument");          \
+        real *flag = reinterpret_cast<real *>(sizeof(real));                                            \
+        SimplexProblem<real> q{K, V, E, al, La_f, const_cast<real *>(P0), Q, Eu, Ev, La_d1, rho,        \
+                               condMin, difRcd, difTol, itMax, nullptr, want_obj ? flag : nullptr,      \
+                               want_dif ? flag : nullptr, 0, sh};                                       \
+        *out = reinterpret_cast<pfdr_b200_solver *>(make_simplex<real>(q));                             \
+    });                                                                                                 \
+}
+
+HANDLE_SHARDED(f32, float)
+HANDLE_SHARDED(f64, double)
+
+int pfdr_b200_comm_unique_id(void *out128)
+{
+    return guarded([&] { PFDR_REQUIRE(out128, "NULL id buffer"); comm_unique_id(out128); });
+}
+int pfdr_b200_comm_init(const void *id128, int world, int rank)
+{
+    return guarded([&] { PFDR_REQUIRE(id128 && world >= 1 && rank >= 0 && rank < world, "bad communicator arguments");
+                         comm_init(id128, world, rank); });
+}
+int pfdr_b200_comm_destroy(void) { return guarded([&] { comm_destroy(); }); }
+
 int pfdr_b200_solver_reset(pfdr_b200_solver *s)
 {
     return guarded([&] { PFDR_REQUIRE(s, "NULL solver"); reinterpret_cast<SolverBase *>(s)->reset(); });

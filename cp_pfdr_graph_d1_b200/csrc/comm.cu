@@ -1,0 +1,215 @@
+// comm.cu - see comm.cuh
+#include "comm.cuh"
+#include <dlfcn.h>
+#include <nccl.h>
+
+namespace pfdr {
+
+namespace {
+
+struct NcclApi {
+    void *h = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+NcclApi &api()
+{
+    static NcclApi a;
+    if (!a.h) {
+        a.h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!a.h) a.h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!a.h) throw Error(PFDR_B200_ERR_NCCL, std::string("cannot open libnccl.so.2: ") + dlerror());
+#define LOAD(name) a.name = reinterpret_cast<decltype(a.name)>(dlsym(a.h, "nccl" #name)); \
+        if (!a.name) throw Error(PFDR_B200_ERR_NCCL, "libnccl lacks nccl" #name)
+        LOAD(GetUniqueId); LOAD(CommInitRank); LOAD(CommDestroy); LOAD(GroupStart); LOAD(GroupEnd);
+        LOAD(Send); LOAD(Recv); LOAD(AllReduce); LOAD(GetErrorString);
+#undef LOAD
+    }
+    return a;
+}
+
+#define PFDR_NCCL(call)                                                                               \
+    do {                                                                                              \
+        ncclResult_t r__ = (call);                                                                    \
+        if (r__ != ncclSuccess)                                                                       \
+            throw Error(PFDR_B200_ERR_NCCL, std::string(#call) + " failed: " + api().GetErrorString(r__)); \
+    } while (0)
+
+template <typename real> struct NcclType;
+template <> struct NcclType<float> { static constexpr ncclDataType_t v = ncclFloat; };
+template <> struct NcclType<double> { static constexpr ncclDataType_t v = ncclDouble; };
+
+// out[i * width + k] = a[idx[i] * width + k], a = the ping or pong buffer selected by the iteration parity
+template <typename real>
+__global__ void gather_items_kernel(real *__restrict__ out, const real *a0, const real *a1, const Ctl *ctl,
+                                    const int *__restrict__ idx, size_t n, int width)
+{
+    const size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * width) return;
+    const real *a = (ctl && (ctl->it & 1)) ? a1 : a0;
+    const size_t i = t / width, k = t - i * width;
+    out[t] = a[(size_t) idx[i] * width + k];
+}
+template <typename real>
+__global__ void scatter_items_kernel(real *a0, real *a1, const Ctl *ctl, const real *__restrict__ in,
+                                     const int *__restrict__ idx, size_t n, int width)
+{
+    const size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * width) return;
+    real *a = (ctl && (ctl->it & 1)) ? a1 : a0;
+    const size_t i = t / width, k = t - i * width;
+    a[(size_t) idx[i] * width + k] = in[t];
+}
+__global__ void key_to_slot_kernel(const int *__restrict__ hkey, long long nslots, int *__restrict__ pos)
+{
+    const long long s = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < nslots && hkey[s] >= 0) pos[hkey[s]] = (int) s;
+}
+__global__ void map_keys_kernel(const int *__restrict__ keys, const int *__restrict__ pos, size_t n, int *__restrict__ out)
+{
+    const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = pos[keys[i]];
+}
+
+}  // namespace
+
+Comm &comm()
+{
+    static Comm c;
+    return c;
+}
+
+void comm_unique_id(void *out128)
+{
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is expected to be 128 bytes");
+    ncclUniqueId id;
+    PFDR_NCCL(api().GetUniqueId(&id));
+    memcpy(out128, &id, sizeof(id));
+}
+
+void comm_init(const void *id128, int world, int rank)
+{
+    comm_destroy();
+    ncclUniqueId id;
+    memcpy(&id, id128, sizeof(id));
+    ncclComm_t c;
+    PFDR_NCCL(api().CommInitRank(&c, world, id, rank));
+    comm().nccl = c; comm().world = world; comm().rank = rank;
+}
+
+void comm_destroy()
+{
+    if (comm().nccl) { api().CommDestroy((ncclComm_t) comm().nccl); comm().nccl = nullptr; comm().world = 1; comm().rank = 0; }
+}
+
+static ncclComm_t need_comm()
+{
+    if (!comm().nccl) throw Error(PFDR_B200_ERR_NCCL, "sharded solve without a communicator: call pfdr_b200_comm_init first");
+    return (ncclComm_t) comm().nccl;
+}
+
+void comm_allreduce_sum(double *buf, int count)
+{
+    PFDR_NCCL(api().AllReduce(buf, buf, count, ncclDouble, ncclSum, need_comm(), ctx().stream));
+    ctx().count_launch();
+}
+void comm_group_start() { PFDR_NCCL(api().GroupStart()); }
+void comm_group_end() { PFDR_NCCL(api().GroupEnd()); ctx().count_launch(); }
+template <typename real> void comm_send(const real *buf, size_t count, int peer)
+{
+    PFDR_NCCL(api().Send(buf, count, NcclType<real>::v, peer, need_comm(), ctx().stream));
+}
+template <typename real> void comm_recv(real *buf, size_t count, int peer)
+{
+    PFDR_NCCL(api().Recv(buf, count, NcclType<real>::v, peer, need_comm(), ctx().stream));
+}
+template void comm_send<float>(const float *, size_t, int);
+template void comm_send<double>(const double *, size_t, int);
+template void comm_recv<float>(float *, size_t, int);
+template void comm_recv<double>(double *, size_t, int);
+
+template <typename real>
+void Halo<real>::setup(const ShardInfo &s, const int *d_hkey, long long nslots, size_t nkeys, int width_)
+{
+    cudaStream_t st = ctx().stream;
+    nnb = s.nnb; width = width_;
+    rank.assign(s.nb_rank, s.nb_rank + nnb);
+    nsv.resize(nnb); nsh.resize(nnb); nrv.resize(nnb); nrh.resize(nnb);
+    sv_off.resize(nnb); sh_off.resize(nnb); rv_off.resize(nnb); rh_off.resize(nnb);
+    for (int i = 0; i < nnb; i++) {
+        nsv[i] = s.sv_off[i + 1] - s.sv_off[i]; nsh[i] = s.sh_off[i + 1] - s.sh_off[i];
+        nrv[i] = s.rv_off[i + 1] - s.rv_off[i]; nrh[i] = s.rh_off[i + 1] - s.rh_off[i];
+        sv_off[i] = s.sv_off[i]; sh_off[i] = s.sh_off[i]; rv_off[i] = s.rv_off[i]; rh_off[i] = s.rh_off[i];
+    }
+    const size_t tsv = nnb ? s.sv_off[nnb] : 0, tsh = nnb ? s.sh_off[nnb] : 0, trv = nnb ? s.rv_off[nnb] : 0,
+                 trh = nnb ? s.rh_off[nnb] : 0;
+    auto up = [&](DevBuf<int> &d, const int *h, size_t n) {
+        d.alloc(std::max<size_t>(n, 1));
+        if (n) PFDR_CUDA(cudaMemcpyAsync(d.p, h, n * sizeof(int), cudaMemcpyHostToDevice, st));
+    };
+    DevBuf<int> d_sh, d_rh, pos(std::max<size_t>(nkeys, 1));
+    up(d_sv, s.sv, tsv); up(d_rv, s.rv, trv); up(d_sh, s.sh, tsh); up(d_rh, s.rh, trh);
+    d_ss.alloc(std::max<size_t>(tsh, 1)); d_rs.alloc(std::max<size_t>(trh, 1));
+    if (nslots > 0) PFDR_LAUNCH(key_to_slot_kernel, cdiv((size_t) nslots, 256), 256, 0, d_hkey, nslots, pos.p);
+    if (tsh) PFDR_LAUNCH(map_keys_kernel, cdiv(tsh, 256), 256, 0, d_sh.p, pos.p, tsh, d_ss.p);
+    if (trh) PFDR_LAUNCH(map_keys_kernel, cdiv(trh, 256), 256, 0, d_rh.p, pos.p, trh, d_rs.p);
+    sendbuf.alloc(std::max<size_t>((2 * tsv + tsh) * width, 1));
+    recvbuf.alloc(std::max<size_t>((2 * trv + trh) * width, 1));
+    PFDR_CUDA(cudaStreamSynchronize(st));
+}
+
+template <typename real>
+void Halo<real>::exchange(PingPong<real> va0, PingPong<real> va1, PingPong<real> Zp, const Ctl *ctl)
+{
+    if (!nnb) return;
+    PingPong<real> va[2] = {va0, va1};
+    const int nva = va1.a[0] ? 2 : 1;
+    real *Z = Zp.a[0];
+    std::vector<size_t> soff(nnb), roff(nnb), scnt(nnb), rcnt(nnb);
+    size_t so = 0, ro = 0;
+    for (int i = 0; i < nnb; i++) {           // pack
+        soff[i] = so; roff[i] = ro;
+        for (int a = 0; a < nva; a++) {
+            if (nsv[i]) PFDR_LAUNCH(gather_items_kernel<real>, cdiv((size_t) nsv[i] * width, 256), 256, 0,
+                                    sendbuf.p + so, va[a].a[0], va[a].a[1], ctl, d_sv.p + sv_off[i], (size_t) nsv[i], width);
+            so += (size_t) nsv[i] * width;
+        }
+        if (Z) {
+            if (nsh[i]) PFDR_LAUNCH(gather_items_kernel<real>, cdiv((size_t) nsh[i] * width, 256), 256, 0,
+                                    sendbuf.p + so, Zp.a[0], Zp.a[1], ctl, d_ss.p + sh_off[i], (size_t) nsh[i], width);
+            so += (size_t) nsh[i] * width;
+        }
+        scnt[i] = so - soff[i];
+        rcnt[i] = ((size_t) nva * nrv[i] + (Z ? nrh[i] : 0)) * width;
+        ro += rcnt[i];
+    }
+    comm_group_start();
+    for (int i = 0; i < nnb; i++) {
+        if (scnt[i]) comm_send<real>(sendbuf.p + soff[i], scnt[i], rank[i]);
+        if (rcnt[i]) comm_recv<real>(recvbuf.p + roff[i], rcnt[i], rank[i]);
+    }
+    comm_group_end();
+    for (int i = 0; i < nnb; i++) {           // unpack
+        size_t o = roff[i];
+        for (int a = 0; a < nva; a++) {
+            if (nrv[i]) PFDR_LAUNCH(scatter_items_kernel<real>, cdiv((size_t) nrv[i] * width, 256), 256, 0,
+                                    va[a].a[0], va[a].a[1], ctl, recvbuf.p + o, d_rv.p + rv_off[i], (size_t) nrv[i], width);
+            o += (size_t) nrv[i] * width;
+        }
+        if (Z && nrh[i]) PFDR_LAUNCH(scatter_items_kernel<real>, cdiv((size_t) nrh[i] * width, 256), 256, 0,
+                                     Zp.a[0], Zp.a[1], ctl, recvbuf.p + o, d_rs.p + rh_off[i], (size_t) nrh[i], width);
+    }
+}
+
+template struct Halo<float>;
+template struct Halo<double>;
+
+}  // namespace pfdr

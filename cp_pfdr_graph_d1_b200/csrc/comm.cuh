@@ -1,0 +1,55 @@
+// comm.cuh - NCCL plumbing of the sharded (multi-GPU) solvers.  NCCL is opened at run time (dlopen of
+// libnccl.so.2: inside a torch process that is torch's own copy) so that single-GPU users of
+// libpfdr_b200.so - the MEX / Boost-Python gateways - carry no NCCL dependency.
+#pragma once
+#include "common.cuh"
+
+namespace pfdr {
+
+// description of this rank's shard = pfdr_b200_shard of include/pfdr_b200.h (mirrors ShardPlan / Neighbor of
+// cp_pfdr_graph_d1_b200/shard.py): all index arrays are HOST arrays; *_off have nnb+1 entries
+typedef pfdr_b200_shard ShardInfo;
+
+struct Comm {
+    void *nccl = nullptr;       // ncclComm_t
+    int world = 1, rank = 0;
+};
+Comm &comm();                    // process-wide communicator (one solve at a time per process)
+
+void comm_unique_id(void *out128);
+void comm_init(const void *id128, int world, int rank);
+void comm_destroy();
+
+// stream-ordered collectives on ctx().stream
+void comm_allreduce_sum(double *buf, int count);
+void comm_group_start();
+void comm_group_end();
+template <typename real> void comm_send(const real *buf, size_t count, int peer);
+template <typename real> void comm_recv(real *buf, size_t count, int peer);
+
+// a ping/pong pair of device arrays; kernels pick a[it & 1] from the control block (a[1] == a[0] for constants)
+template <typename real> struct PingPong {
+    real *a[2];
+    PingPong() { a[0] = a[1] = nullptr; }
+    PingPong(real *x) { a[0] = a[1] = x; }
+    PingPong(real *x, real *y) { a[0] = x; a[1] = y; }
+};
+
+// Halo engine shared by both solver families: per neighbour, a message is
+//   [ va[0][send vertices] ... va[nva-1][send vertices] | Z[send slots] ]   (each item `width` reals wide)
+template <typename real>
+struct Halo {
+    int nnb = 0, width = 1;
+    std::vector<int> rank, nsv, nsh, nrv, nrh;
+    std::vector<size_t> sv_off, sh_off, rv_off, rh_off;
+    DevBuf<int> d_sv, d_ss, d_rv, d_rs;           // send vertices / send slots / recv vertices / recv slots
+    DevBuf<real> sendbuf, recvbuf;
+
+    // hkey: [nslots] half-edge key of every slot (-1 padding); nkeys = 2 * local edges
+    void setup(const ShardInfo &s, const int *d_hkey, long long nslots, size_t nkeys, int width_);
+    // exchanges up to 2 vertex arrays (+ the half-edge copies Z when non-null), in place; with ctl the
+    // buffers of the CURRENT iteration parity are used (decided on the device, no host synchronisation)
+    void exchange(PingPong<real> va0, PingPong<real> va1, PingPong<real> Z, const Ctl *ctl);
+};
+
+}  // namespace pfdr

@@ -28,6 +28,8 @@ template <typename real>
 struct QP {                       // kernel parameter block
     Ctl *ctl;
     int V, N, E;
+    int Vown, sharded;            // vertices this rank owns (== V unless sharded: ghosts follow)
+    double *sums;                 // [2] reduction scratch of the sharded path (all-reduced between kernels)
     const long long *slice_off; const int *nbr, *twin, *hkey;
     real *w;                      // [slots] raw d1 weight of the half-edge's edge
     real *thc;                    // [slots] La_d1/w after a reconditioning (NULL: thc0 for all)
@@ -100,7 +102,7 @@ __global__ void __launch_bounds__(256) amp_kernel(QP<real> p, int recond)
     __shared__ double smem[64];
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     double r[2] = {0.0, 0.0};
-    if (v < p.V) {
+    if (v < p.Vown) {
         real a;
         if (recond) {
             a = ((p.ctl->it & 1) ? p.X1 : p.X0)[v];
@@ -116,8 +118,17 @@ __global__ void __launch_bounds__(256) amp_kernel(QP<real> p, int recond)
         if (a > (real) 0) { r[0] = (double) a; r[1] = 1.0; }          // ref :149-153
         else if (a < (real) 0) { r[0] = -(double) a; r[1] = 1.0; }
     }
-    if (grid_sum<2>(p.ctl, p.partial, r, smem) && threadIdx.x == 0)
-        p.ctl->amp = recond ? (double) ((real) r[0] / (real) r[1]) : (double) ((real) r[1] / (real) r[0]);
+    if (grid_sum<2>(p.ctl, p.partial, r, smem) && threadIdx.x == 0) {
+        if (p.sharded) { p.sums[0] = r[0]; p.sums[1] = r[1]; }       // finished by amp_finish_kernel after the all-reduce
+        else p.ctl->amp = recond ? (double) ((real) r[0] / (real) r[1]) : (double) ((real) r[1] / (real) r[0]);
+    }
+}
+
+template <typename real>
+__global__ void amp_finish_kernel(QP<real> p, int recond)
+{
+    const double a = p.sums[0], n = p.sums[1];
+    p.ctl->amp = recond ? (double) ((real) a / (real) n) : (double) ((real) n / (real) a);
 }
 
 template <typename real>
@@ -223,6 +234,31 @@ __global__ void resume_kernel(QP<real> p, double rcd_factor)
 // ---------------------------------------------------------------------------------------------
 // the fused iteration kernel
 // ---------------------------------------------------------------------------------------------
+// end of an iteration: evolution measure, iteration counter, stop / recondition decision (ref :429, :448, :515-529)
+template <typename real>
+__device__ void quad_finalize(const QP<real> &p, int it, double d, double c)
+{
+    Ctl *ctl = p.ctl;
+    double dif = ctl->dif;
+    if (ctl->track) {
+        dif = (c > ctl->eps) ? d / c : d / ctl->eps;
+        ctl->dif = dif;
+        if (p.dDif) p.dDif[it] = (real) dif;
+    }
+    const int itn = it + 1;
+    ctl->it = itn;
+    if (itn == ctl->itMax || (real) dif < (real) ctl->tol) ctl->state = ST_FINAL;
+    else if ((real) dif < (real) ctl->rcd) ctl->state = ST_RECOND;
+}
+
+// sharded path: the sums were all-reduced over the ranks between the iteration kernel and this one
+template <typename real>
+__global__ void quad_finalize_kernel(QP<real> p)
+{
+    if (p.ctl->hold != 0 || p.ctl->state != ST_RUN) return;
+    quad_finalize(p, p.ctl->it, p.sums[0], p.sums[1]);
+}
+
 // U half-edge rows of the vertex are in flight at once: first every index / weight / own-copy load of the
 // chunk is issued, then every gather (neighbour forward point, neighbour T, twin copy), then the arithmetic.
 // (v0 of this kernel kept 2 rows in flight and sat at 27 warps stalled on the scoreboard per issue.)
@@ -252,7 +288,7 @@ __global__ void __launch_bounds__(256) quad_iter_kernel(QP<real> p)
 
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     double red[2] = {0.0, 0.0};
-    if (v < p.V) {
+    if (v < p.Vown) {
         const int lane = v & 31;
         const long long base = p.slice_off[v >> 5];
         const int width = (int) ((p.slice_off[(v >> 5) + 1] - base) >> 5);
@@ -315,16 +351,8 @@ __global__ void __launch_bounds__(256) quad_iter_kernel(QP<real> p)
         red[0] = (double) (dx * dx); red[1] = (double) (x * x);
     }
     if (grid_sum<2>(ctl, p.partial, red, smem) && threadIdx.x == 0) {
-        double dif = ctl->dif;
-        if (ctl->track) {                                                      // ref :515-529
-            dif = (red[1] > ctl->eps) ? red[0] / red[1] : red[0] / ctl->eps;
-            ctl->dif = dif;
-            if (p.dDif) p.dDif[it] = (real) dif;
-        }
-        const int itn = it + 1;
-        ctl->it = itn;
-        if (itn == ctl->itMax || (real) dif < (real) ctl->tol) ctl->state = ST_FINAL;   // ref :429
-        else if ((real) dif < (real) ctl->rcd) ctl->state = ST_RECOND;                  // ref :448
+        if (p.sharded) { p.sums[0] = red[0]; p.sums[1] = red[1]; }
+        else quad_finalize(p, it, red[0], red[1]);
     }
 }
 
@@ -358,7 +386,7 @@ __global__ void __launch_bounds__(32 * W * G) quad_rows_kernel(QP<real> p, int n
     const int slice = blockIdx.x * G + g;
     const bool live = slice < nslices;
     const int v = slice * 32 + lane;
-    const bool vlive = live && v < p.V;
+    const bool vlive = live && v < p.Vown;
     long long base = 0;
     int width = 0;
     if (live) { base = p.slice_off[slice]; width = (int) ((p.slice_off[slice + 1] - base) >> 5); }
@@ -448,16 +476,8 @@ __global__ void __launch_bounds__(32 * W * G) quad_rows_kernel(QP<real> p, int n
     block_sum<2>(acc, smem);
     if (threadIdx.x == 0) {
         ctl->ticket = 0;
-        double dif = ctl->dif;
-        if (ctl->track) {
-            dif = (acc[1] > ctl->eps) ? acc[0] / acc[1] : acc[0] / ctl->eps;
-            ctl->dif = dif;
-            if (p.dDif) p.dDif[it] = (real) dif;
-        }
-        const int itn = it + 1;
-        ctl->it = itn;
-        if (itn == ctl->itMax || (real) dif < (real) ctl->tol) ctl->state = ST_FINAL;   // ref :429
-        else if ((real) dif < (real) ctl->rcd) ctl->state = ST_RECOND;                  // ref :448
+        if (p.sharded) { p.sums[0] = acc[0]; p.sums[1] = acc[1]; }
+        else quad_finalize(p, it, acc[0], acc[1]);
     }
 }
 
@@ -465,7 +485,7 @@ template <typename real>
 __global__ void extract_x_kernel(QP<real> p, real *__restrict__ out)
 {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= p.V) return;
+    if (v >= p.Vown) return;
     out[v] = ((p.ctl->it & 1) ? p.X1 : p.X0)[v];
 }
 
@@ -682,7 +702,10 @@ struct QuadSolver : SolverBase {
     DevIn<real> Y, A, La_d1, La_l1, L, X0;
     DevIn<int> Eu, Ev;
     DevBuf<real> w, thc, Z0, Z1, X0b, X1b, P0b, P1b, T, Sinv, Ga, Ga0, G, Thl1, R, AtY, dObj, dDif, Xout;
-    DevBuf<double> partial, parts;
+    DevBuf<double> partial, parts, sums;
+    Halo<real> halo;
+    bool sharded = false;
+    int ogrid = 0;                  // CTAs covering the owned vertices
     Ctl *hctl = nullptr;            // pinned mirror of the control block, one per batch in flight
     cudaEvent_t ev[2]{}, ev_a{}, ev_b{}, ev_c{};
     cudaGraphExec_t gexec = nullptr;
@@ -704,6 +727,12 @@ struct QuadSolver : SolverBase {
         PFDR_REQUIRE(V > 0 && E >= 0, "V must be positive and E non-negative");
         PFDR_REQUIRE(q.itMax >= 0, "itMax must be non-negative");
         PFDR_REQUIRE(N == 0 || q.A != nullptr, "A must not be NULL when N != 0");
+        sharded = q.shard != nullptr;
+        if (sharded) {
+            PFDR_REQUIRE(N == 0, "sharded solves support N == 0 (diagonal / identity A) in this build");
+            PFDR_REQUIRE(q.Obj == nullptr && q.difRcd == (real) 0, "sharded solves do not record Obj nor recondition in this build");
+            PFDR_REQUIRE(q.shard->Vown > 0 && q.shard->Vown <= V, "bad shard: Vown");
+        }
         cudaStream_t st = ctx().stream;
         for (auto *e : {&ev[0], &ev[1], &ev_a, &ev_b, &ev_c}) PFDR_CUDA(cudaEventCreate(e));
         PFDR_CUDA(cudaEventRecord(ev_a, st));
@@ -728,12 +757,14 @@ struct QuadSolver : SolverBase {
         if (q.Obj) dObj.alloc((size_t) q.itMax + 1);
         if (q.Dif) dDif.alloc((size_t) std::max(q.itMax, 1));
         vgrid = (int) cdiv(V, 256);
-        ctl.alloc(1);
+        ogrid = sharded ? (int) cdiv(q.shard->Vown, 256) : vgrid;
+        ctl.alloc(1); sums.alloc(2);
 
         // padded slots of Z must never hold garbage that could turn into NaN traps: zero them
         Z0.zero(); Z1.zero(); w.zero();
 
         p.ctl = ctl.p; p.V = V; p.N = N; p.E = E;
+        p.Vown = sharded ? q.shard->Vown : V; p.sharded = sharded ? 1 : 0; p.sums = sums.p;
         p.slice_off = g.slice_off.p; p.nbr = g.nbr.p; p.twin = g.twin.p; p.hkey = g.hkey.p;
         p.w = w.p; p.thc = nullptr; p.thc0 = 0; p.Z0 = Z0.p; p.Z1 = Z1.p;
         p.X0 = X0b.p; p.X1 = X1b.p; p.P0 = P0b.p; p.P1 = P1b.p; p.T = T.p; p.Sinv = Sinv.p; p.Ga = Ga.p; p.Ga0 = Ga0.p; p.G = G.p; p.Thl1 = Thl1.p;
@@ -762,6 +793,7 @@ struct QuadSolver : SolverBase {
         partial.alloc((size_t) maxgrid * 4);
         p.partial = partial.p;
 
+        if (sharded) halo.setup(*q.shard, g.hkey.p, g.nslots, 2 * (size_t) E, 1);
         reset();
         if (!keep_x0) X0.own.release();
         PFDR_CUDA(cudaEventRecord(ev_b, st));
@@ -786,8 +818,11 @@ struct QuadSolver : SolverBase {
         PFDR_CUDA(cudaMemcpyAsync(ctl.p, &hctl[0], sizeof(Ctl), cudaMemcpyHostToDevice, st));
         // first preconditioning
         if (q.N > 0) launch_atr(1);
-        PFDR_LAUNCH(amp_kernel<real>, vgrid, 256, 0, p, 0);
+        PFDR_LAUNCH(amp_kernel<real>, ogrid, 256, 0, p, 0);
+        if (sharded) { comm_allreduce_sum(sums.p, 2); PFDR_LAUNCH(amp_finish_kernel<real>, 1, 1, 0, p, 0); }
         PFDR_LAUNCH(init_vertex_kernel<real>, vgrid, 256, 0, p, X0.p);
+        // ghosts: the metric constants and forward point come from their owners
+        if (sharded) halo.exchange(PingPong<real>(T.p), PingPong<real>(P0b.p), PingPong<real>(), nullptr);
         PFDR_CUDA(cudaMemcpyAsync(&hctl[1], ctl.p, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
         PFDR_CUDA(cudaStreamSynchronize(st));
         const real thc0 = (real) 1 / (real) hctl[1].amp;       // La_d1 / (c La_d1)
@@ -820,22 +855,27 @@ struct QuadSolver : SolverBase {
             PFDR_LAUNCH(objective_kernel<real>, std::min<unsigned>(cdiv(work, 256), num_sms() * 8), 256, 0, p);
         }
         launch_iter();
+        if (sharded) {     // evolution sums over all ranks, then the new boundary values and cut-edge copies
+            comm_allreduce_sum(sums.p, 2);
+            PFDR_LAUNCH(quad_finalize_kernel<real>, 1, 1, 0, p);
+            halo.exchange(PingPong<real>(P0b.p, P1b.p), PingPong<real>(), PingPong<real>(Z0.p, Z1.p), ctl.p);
+        }
     }
 
-    // PFDR_B200_KERNEL=vertex selects the one-thread-per-vertex kernel (PFDR_B200_U rows in flight, default
-    // 8 / 4); the default is the row-parallel kernel with W warps per slice chosen from the widest slice.
+    // default: the one-thread-per-vertex kernel (PFDR_B200_U rows in flight, default 8 / 4);
+    // PFDR_B200_KERNEL=rows selects the row-parallel kernel (slower, kept for comparison: profiles/r01_notes.md).
     int rowsW = 0;
     void launch_iter()
     {
         static int U = -1, mode = -1;
         if (U < 0) { const char *e = getenv("PFDR_B200_U"); U = e ? atoi(e) : 0; }
-        if (mode < 0) { const char *e = getenv("PFDR_B200_KERNEL"); mode = (e && !strcmp(e, "vertex")) ? 1 : 0; }
+        if (mode < 0) { const char *e = getenv("PFDR_B200_KERNEL"); mode = (e && !strcmp(e, "rows")) ? 0 : 1; }
         if (mode == 1) {
             const int u = U > 0 ? U : (sizeof(real) == 4 ? 8 : 4);
 #define PFDR_ITER(UU)                                                                          \
             do {                                                                               \
-                if (p.thc) PFDR_LAUNCH((quad_iter_kernel<real, true, UU>), vgrid, 256, 0, p);  \
-                else PFDR_LAUNCH((quad_iter_kernel<real, false, UU>), vgrid, 256, 0, p);       \
+                if (p.thc) PFDR_LAUNCH((quad_iter_kernel<real, true, UU>), ogrid, 256, 0, p);  \
+                else PFDR_LAUNCH((quad_iter_kernel<real, false, UU>), ogrid, 256, 0, p);       \
             } while (0)
             if (u <= 2) PFDR_ITER(2); else if (u <= 4) PFDR_ITER(4); else if (u <= 6) PFDR_ITER(6); else PFDR_ITER(8);
 #undef PFDR_ITER
@@ -858,7 +898,7 @@ struct QuadSolver : SolverBase {
     void enqueue_batch(int trips, int batch)
     {
         cudaStream_t st = ctx().stream;
-        if (trips == batch && use_graph()) {
+        if (trips == batch && use_graph() && !sharded) {
             if (!gexec || graph_trips != batch) {
                 if (gexec) { cudaGraphExecDestroy(gexec); gexec = nullptr; }
                 cudaGraph_t graph;
@@ -951,11 +991,11 @@ struct QuadSolver : SolverBase {
         PFDR_CUDA(cudaStreamSynchronize(st));
         const Ctl h = hctl[0];
         if (Xo) {
-            if (is_device_ptr(Xo)) PFDR_LAUNCH(extract_x_kernel<real>, vgrid, 256, 0, p, (real *) Xo);
+            if (is_device_ptr(Xo)) PFDR_LAUNCH(extract_x_kernel<real>, ogrid, 256, 0, p, (real *) Xo);
             else {
-                Xout.alloc(q.V);
-                PFDR_LAUNCH(extract_x_kernel<real>, vgrid, 256, 0, p, Xout.p);
-                copy_out((real *) Xo, Xout.p, q.V);
+                Xout.alloc(p.Vown);
+                PFDR_LAUNCH(extract_x_kernel<real>, ogrid, 256, 0, p, Xout.p);
+                copy_out((real *) Xo, Xout.p, p.Vown);
             }
         }
         if (Objo && dObj.p) copy_out((real *) Objo, dObj.p, (size_t) h.it + 1);

@@ -29,6 +29,8 @@ template <typename real>
 struct SP {
     Ctl *ctl;
     int K, V, E, TPV, C, logC, logTPV, loss, by_label, LPT, stream_z;
+    int Vown, sharded, Vglobal;   // vertices this rank owns (== V unless sharded: ghosts follow), global count
+    double *sums;                 // [1] reduction scratch of the sharded path
     real aK, a1, aK1, rho, condMin;
     const long long *slice_off; const int *nbr, *twin, *hkey;
     real *w;                      // [slots]   raw weight before any reconditioning (= La_d1[e] for every label)
@@ -299,6 +301,29 @@ __global__ void simplex_resume_kernel(SP<real> p)
 // ---------------------------------------------------------------------------------------------
 // fused iteration
 // ---------------------------------------------------------------------------------------------
+// end of an iteration: evolution measure (ref :654-691), iteration counter, stop / recondition decision (:551, :554)
+template <typename real>
+__device__ void simplex_finalize(const SP<real> &p, int it, double s)
+{
+    Ctl *ctl = p.ctl;
+    double dif = ctl->dif;
+    if (ctl->track) {
+        dif = p.by_label ? s : s / (double) p.Vglobal;              // ref :688 divides by the (global) vertex count
+        ctl->dif = dif;
+        if (p.dDif) p.dDif[it] = (real) dif;
+    }
+    const int itn = it + 1;
+    ctl->it = itn;
+    if (itn == ctl->itMax || (real) dif < (real) ctl->tol) ctl->state = ST_FINAL;
+    else if ((real) dif < (real) ctl->rcd) ctl->state = ST_RECOND;
+}
+template <typename real>
+__global__ void simplex_finalize_kernel(SP<real> p)
+{
+    if (p.ctl->hold != 0 || p.ctl->state != ST_RUN) return;
+    simplex_finalize(p, p.ctl->it, p.sums[0]);
+}
+
 template <typename real, int LPT, bool PERK, int LOSS, int MINB>
 __global__ void __launch_bounds__(256, MINB) simplex_iter_kernel(SP<real> p)
 {
@@ -322,13 +347,13 @@ __global__ void __launch_bounds__(256, MINB) simplex_iter_kernel(SP<real> p)
     const int *__restrict__ twin = p.twin;
     const int K = p.K, TPV = p.TPV, C = p.C, lane = threadIdx.x & 31;
     const long long slice = ((long long) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const long long nslices = ((long long) p.V + C - 1) >> p.logC;
+    const long long nslices = ((long long) p.Vown + C - 1) >> p.logC;
     const real rho = p.rho;
     double red[1] = {0.0};
     if (slice < nslices) {                                                    // warp-uniform
         const int vl = lane >> p.logTPV, k0 = (lane & (TPV - 1)) * LPT;
         const int v = (int) (slice << p.logC) + vl;
-        const bool on = (v < p.V) && (k0 < K);       // LPT == 4 requires K % 4 == 0: all LPT labels valid
+        const bool on = (v < p.Vown) && (k0 < K);    // LPT == 4 requires K % 4 == 0: all LPT labels valid
         const size_t vk = (size_t) (on ? v : 0) * K + (on ? k0 : 0);
         const vec pold = ldv<real, LPT>(Pc + vk), fown = ldv<real, LPT>(Fc + vk), Tv = ldv<real, LPT>(Tg + vk);
         vec Sv;
@@ -443,16 +468,8 @@ __global__ void __launch_bounds__(256, MINB) simplex_iter_kernel(SP<real> p)
         }
     }
     if (grid_sum_s<1>(ctl, p.partial, red, smem) && threadIdx.x == 0) {
-        double dif = ctl->dif;
-        if (ctl->track) {
-            dif = p.by_label ? red[0] : red[0] / (double) p.V;
-            ctl->dif = dif;
-            if (p.dDif) p.dDif[it] = (real) dif;
-        }
-        const int itn = it + 1;
-        ctl->it = itn;
-        if (itn == ctl->itMax || (real) dif < (real) ctl->tol) ctl->state = ST_FINAL;   // ref :551
-        else if ((real) dif < (real) ctl->rcd) ctl->state = ST_RECOND;                  // ref :554
+        if (p.sharded) p.sums[0] = red[0];
+        else simplex_finalize(p, it, red[0]);
     }
 }
 
@@ -486,7 +503,7 @@ template <typename real>
 __global__ void simplex_extract_kernel(SP<real> p, real *__restrict__ out)
 {
     const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (size_t) p.V * p.K) return;
+    if (i >= (size_t) p.Vown * p.K) return;
     out[i] = ((p.ctl->it & 1) ? p.P1 : p.P0)[i];
 }
 
@@ -504,11 +521,13 @@ struct SimplexSolver : SolverBase {
     DevIn<int> Eu, Ev;
     DevBuf<real> w, wk, thk, Z0, Z1, Pa, Pb, Fa, Fb, T, GaQ, Sinv, Sinvk, Gn, GaU, dObj, dDif, Pout, Qal;
     DevBuf<int> lab;
-    DevBuf<double> partial;
+    DevBuf<double> partial, sums;
+    Halo<real> halo;
+    bool sharded = false;
     Ctl *hctl = nullptr;
     cudaEvent_t ev[2]{}, ev_a{}, ev_b{}, ev_c{};
     cudaGraphExec_t gexec = nullptr;
-    int graph_trips = 0, grid = 0, LPT = 1;
+    int graph_trips = 0, grid = 0, ogrid = 0, LPT = 1, Vglobal = 0;
 
     SimplexSolver(const SimplexProblem<real> &q_, bool keep) : q(q_), keep_p0(keep) {}
     ~SimplexSolver() override
@@ -523,6 +542,11 @@ struct SimplexSolver : SolverBase {
         const int K = q.K, V = q.V, E = q.E;
         PFDR_REQUIRE(K >= 1 && V > 0 && E >= 0 && q.itMax >= 0, "K, V must be positive, E and itMax non-negative");
         PFDR_REQUIRE(q.al >= (real) 0 && q.al <= (real) 1, "al must lie in [0, 1] (the reference is undefined beyond, SURVEY 5.1-10)");
+        sharded = q.shard != nullptr;
+        if (sharded) {
+            PFDR_REQUIRE(q.Obj == nullptr && q.difRcd == (real) 0, "sharded solves do not record Obj nor recondition in this build");
+            PFDR_REQUIRE(q.shard->Vown > 0 && q.shard->Vown <= V, "bad shard: Vown");
+        }
         const char *fl = getenv("PFDR_B200_LPT");
         LPT = (K % 4 == 0 && !(fl && fl[0] == '1')) ? 4 : 1;
         PFDR_REQUIRE((K + LPT - 1) / LPT <= 32, "this build supports K <= 32 labels, or K <= 128 when K is a multiple of 4");
@@ -552,11 +576,14 @@ struct SimplexSolver : SolverBase {
         if (by_label) lab.alloc(V);
         if (q.Obj) dObj.alloc((size_t) q.itMax + 1);
         if (q.Dif) dDif.alloc((size_t) std::max(q.itMax, 1));
-        ctl.alloc(1);
+        ctl.alloc(1); sums.alloc(1);
         const long long nslices = ((long long) V + C - 1) / C;
         grid = (int) cdiv((size_t) nslices * 32, 256);
+        const int Vown = sharded ? q.shard->Vown : V;
+        ogrid = (int) cdiv((size_t) (((long long) Vown + C - 1) / C) * 32, 256);
         partial.alloc((size_t) std::max(grid, num_sms() * 8) * 2);
 
+        p.Vown = Vown; p.sharded = sharded ? 1 : 0; p.sums = sums.p; p.Vglobal = sharded ? q.shard->Vglobal : V;
         p.ctl = ctl.p; p.K = K; p.V = V; p.E = E; p.TPV = TPV; p.C = C; p.logC = logC; p.logTPV = logTPV; p.LPT = LPT;
         p.loss = (q.al == (real) 0) ? LOSS_LIN : (q.al == (real) 1 ? LOSS_QUAD : LOSS_KLA);
         p.by_label = by_label;
@@ -570,6 +597,7 @@ struct SimplexSolver : SolverBase {
         p.partial = partial.p; p.dObj = dObj.p; p.dDif = dDif.p;
         { const char *e = getenv("PFDR_B200_STREAMZ"); p.stream_z = (e && e[0] == '1') ? 1 : 0; }
 
+        if (sharded) halo.setup(*q.shard, g.hkey.p, g.nslots, 2 * (size_t) E, K);
         reset();
         if (!keep_p0) P0.own.release();
         PFDR_CUDA(cudaEventRecord(ev_b, st));
@@ -595,6 +623,7 @@ struct SimplexSolver : SolverBase {
         hctl[0] = h;
         PFDR_CUDA(cudaMemcpyAsync(ctl.p, &hctl[0], sizeof(Ctl), cudaMemcpyHostToDevice, st));
         launch_precond(P0.p, 0);
+        if (sharded) halo.exchange(PingPong<real>(T.p), PingPong<real>(Fa.p), PingPong<real>(), nullptr);
         PFDR_CUDA(cudaStreamSynchronize(st));
     }
 
@@ -607,11 +636,11 @@ struct SimplexSolver : SolverBase {
         static int MB = -1;
         if (MB < 0) { const char *e = getenv("PFDR_B200_MINB"); MB = e ? atoi(e) : 0; }
         (void) U;
-        if (L == 4 && !PERK && LOSS == LOSS_KLA && MB == 5) PFDR_LAUNCH((simplex_iter_kernel<real, 4, false, LOSS_KLA, 5>), grid, 256, 0, p);
-        else if (L == 4 && !PERK && LOSS == LOSS_KLA && MB == 6) PFDR_LAUNCH((simplex_iter_kernel<real, 4, false, LOSS_KLA, 6>), grid, 256, 0, p);
-        else if (L == 4 && !PERK && LOSS == LOSS_KLA && MB == 8) PFDR_LAUNCH((simplex_iter_kernel<real, 4, false, LOSS_KLA, 8>), grid, 256, 0, p);
-        else if (L == 4 && !PERK && LOSS == LOSS_KLA && MB == 1) PFDR_LAUNCH((simplex_iter_kernel<real, 4, false, LOSS_KLA, 1>), grid, 256, 0, p);
-        else PFDR_LAUNCH((simplex_iter_kernel<real, L, PERK, LOSS, 4>), grid, 256, 0, p);
+        if (L == 4 && !PERK && LOSS == LOSS_KLA && MB == 5) PFDR_LAUNCH((simplex_iter_kernel<real, 4, false, LOSS_KLA, 5>), ogrid, 256, 0, p);
+        else if (L == 4 && !PERK && LOSS == LOSS_KLA && MB == 6) PFDR_LAUNCH((simplex_iter_kernel<real, 4, false, LOSS_KLA, 6>), ogrid, 256, 0, p);
+        else if (L == 4 && !PERK && LOSS == LOSS_KLA && MB == 8) PFDR_LAUNCH((simplex_iter_kernel<real, 4, false, LOSS_KLA, 8>), ogrid, 256, 0, p);
+        else if (L == 4 && !PERK && LOSS == LOSS_KLA && MB == 1) PFDR_LAUNCH((simplex_iter_kernel<real, 4, false, LOSS_KLA, 1>), ogrid, 256, 0, p);
+        else PFDR_LAUNCH((simplex_iter_kernel<real, L, PERK, LOSS, 4>), ogrid, 256, 0, p);
     }
     template <int L, bool PERK>
     void launch_iter_loss()
@@ -629,6 +658,11 @@ struct SimplexSolver : SolverBase {
         }
         if (LPT == 4) { if (p.wk) launch_iter_loss<4, true>(); else launch_iter_loss<4, false>(); }
         else { if (p.wk) launch_iter_loss<1, true>(); else launch_iter_loss<1, false>(); }
+        if (sharded) {     // evolution sum over all ranks, then the new boundary forward points and cut-edge copies
+            comm_allreduce_sum(sums.p, 1);
+            PFDR_LAUNCH(simplex_finalize_kernel<real>, 1, 1, 0, p);
+            halo.exchange(PingPong<real>(Fa.p, Fb.p), PingPong<real>(), PingPong<real>(Z0.p, Z1.p), ctl.p);
+        }
     }
     int launches_per_trip() const { return (q.Obj ? 1 : 0) + 1; }
 
@@ -637,7 +671,7 @@ struct SimplexSolver : SolverBase {
         cudaStream_t st = ctx().stream;
         static int use_graph = -1;
         if (use_graph < 0) { const char *e = getenv("PFDR_B200_GRAPH"); use_graph = (e && e[0] == '0') ? 0 : 1; }
-        if (!use_graph) { for (int i = 0; i < batch; i++) enqueue_trip(); return; }
+        if (!use_graph || sharded) { for (int i = 0; i < batch; i++) enqueue_trip(); return; }
         if (!gexec || graph_trips != batch) {
             if (gexec) { cudaGraphExecDestroy(gexec); gexec = nullptr; }
             cudaGraph_t graph;
@@ -719,7 +753,7 @@ struct SimplexSolver : SolverBase {
         PFDR_CUDA(cudaMemcpyAsync(&hctl[0], ctl.p, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
         PFDR_CUDA(cudaStreamSynchronize(st));
         const Ctl h = hctl[0];
-        const size_t VK = (size_t) q.V * q.K;
+        const size_t VK = (size_t) p.Vown * q.K;
         if (Po) {
             if (is_device_ptr(Po)) PFDR_LAUNCH(simplex_extract_kernel<real>, cdiv(VK, 256), 256, 0, p, (real *) Po);
             else {

@@ -1,6 +1,7 @@
 // solvers.cuh - host-side entry points behind the C ABI (capi.cu).
 #pragma once
 #include "common.cuh"
+#include "comm.cuh"
 
 namespace pfdr {
 
@@ -13,6 +14,7 @@ struct QuadProblem {
     int positivity, prox_kind; real lo, hi;
     int Ltype; const real *L; real rho, condMin, difRcd, difTol;
     int itMax; int *it; real *Obj, *Dif; int verbose;
+    const ShardInfo *shard = nullptr;   // non-NULL: this rank's part of a vertex-sharded problem (comm.cuh)
 };
 
 // A solver resident on the device: layout + preconditioner built once, then reset()/run() any number
@@ -31,6 +33,7 @@ template <typename real>
 struct SimplexProblem {
     int K, V, E; real al; const real *La_f; real *P; const real *Q; const int *Eu, *Ev; const real *La_d1;
     real rho, condMin, difRcd, difTol; int itMax; int *it; real *Obj, *Dif; int verbose;
+    const ShardInfo *shard = nullptr;
 };
 template <typename real> SolverBase *make_simplex(const SimplexProblem<real> &q);
 template <typename real> void solve_simplex(const SimplexProblem<real> &q);

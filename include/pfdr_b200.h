@@ -113,6 +113,42 @@ int pfdr_b200_solver_run(pfdr_b200_solver *s);     /* iterate until the stopping
 int pfdr_b200_solver_fetch(pfdr_b200_solver *s, void *X, int *it, void *Obj, void *Dif);
 int pfdr_b200_solver_destroy(pfdr_b200_solver *s);
 
+/* ---- vertex-sharded solves over NCCL (no counterpart in the reference) ---------------------
+ * One process per GPU.  Rank r owns a contiguous vertex range plus every edge touching it; vertices at the
+ * far end of a cut edge are ghosts numbered after the owned ones (cp_pfdr_graph_d1_b200/shard.py builds the
+ * plan).  Per iteration a rank exchanges, with each neighbour, the forward point of its boundary vertices and
+ * its half-edge copies on the cut edges (ncclSend/ncclRecv), and all ranks all-reduce the one or two scalars
+ * of the stopping rule.  Index arrays are HOST arrays in LOCAL numbering; *_off have nnb+1 entries.
+ * The problem arrays passed to the *_sharded constructors are the LOCAL ones (Vown + ghosts vertices, local
+ * edges); fetch() returns the Vown owned entries.  This build shards N == 0 problems without Obj/reconditioning. */
+typedef struct {
+    int Vown;                 /* vertices owned by this rank (local ids 0..Vown-1; ghosts follow)            */
+    int Vglobal;              /* vertices of the whole problem                                                */
+    int nnb;                  /* neighbouring ranks                                                           */
+    const int *nb_rank;       /* [nnb]                                                                        */
+    const int *sv_off, *sv;   /* vertices whose forward point neighbour i needs (owned ids)                   */
+    const int *sh_off, *sh;   /* our half-edges 2*e_local+side on the edges cut with neighbour i              */
+    const int *rv_off, *rv;   /* ghost ids filled by neighbour i's message                                    */
+    const int *rh_off, *rh;   /* their half-edges on the same cut edges, same order                           */
+} pfdr_b200_shard;
+int pfdr_b200_comm_unique_id(void *out128);                           /* rank 0: ncclGetUniqueId (128 bytes)  */
+int pfdr_b200_comm_init(const void *id128, int world, int rank);      /* every rank, after pfdr_b200_set_device */
+int pfdr_b200_comm_destroy(void);
+int pfdr_b200_solver_create_quadratic_sharded_f32(pfdr_b200_solver **out, const pfdr_b200_shard *shard,
+    int prox_kind, int V, int E, int N, const float *X0, const float *Y, const float *A, const int *Eu,
+    const int *Ev, const float *La_d1, const float *La_l1, int positivity, float lo, float hi, int Ltype,
+    const float *L, float rho, float condMin, float difRcd, float difTol, int itMax, int want_obj, int want_dif);
+int pfdr_b200_solver_create_quadratic_sharded_f64(pfdr_b200_solver **out, const pfdr_b200_shard *shard,
+    int prox_kind, int V, int E, int N, const double *X0, const double *Y, const double *A, const int *Eu,
+    const int *Ev, const double *La_d1, const double *La_l1, int positivity, double lo, double hi, int Ltype,
+    const double *L, double rho, double condMin, double difRcd, double difTol, int itMax, int want_obj, int want_dif);
+int pfdr_b200_solver_create_simplex_sharded_f32(pfdr_b200_solver **out, const pfdr_b200_shard *shard, int K, int V,
+    int E, float al, const float *La_f, const float *P0, const float *Q, const int *Eu, const int *Ev,
+    const float *La_d1, float rho, float condMin, float difRcd, float difTol, int itMax, int want_obj, int want_dif);
+int pfdr_b200_solver_create_simplex_sharded_f64(pfdr_b200_solver **out, const pfdr_b200_shard *shard, int K, int V,
+    int E, double al, const double *La_f, const double *P0, const double *Q, const int *Eu, const int *Ev,
+    const double *La_d1, double rho, double condMin, double difRcd, double difTol, int itMax, int want_obj, int want_dif);
+
 /* ---- run-time controls and introspection (no counterpart in the reference) ----------------- */
 const char *pfdr_b200_last_error(void);      /* message of the last non-zero status (thread local) */
 int pfdr_b200_version(void);
