@@ -142,6 +142,40 @@ def device_inputs_c4(n, K, dt, dev):
     return dict(V=V, E=int(Eu.shape[0]), K=K, Q=Q, Eu=Eu, Ev=Ev, La_d1=La_d1, al=0.05)
 
 
+def grid_slab_simplex(n, K, dt, world, rank):
+    """rank's z-slab of the full-size C4 grid, generated directly in local numbering (no global arrays):
+    same recipe as synth.c4_simplex with a per-vertex counter-based RNG so that every rank draws the same Q
+    for the vertices it shares with its neighbours."""
+    from cp_pfdr_graph_d1_b200 import shard
+    V = n ** 3
+    b = shard.slab_bounds(V, world)
+    v0, v1 = int(b[rank]), int(b[rank + 1])
+    lo, hi = max(v0 - n * n, 0), min(v1 + n * n, V)          # owned range plus one plane of possible ghosts each side
+    g = np.arange(lo, hi, dtype=np.int64)
+    z, y, x = g // (n * n), (g // n) % n, g % n
+    eu, ev = [], []
+    for ok, d in ((x < n - 1, 1), (y < n - 1, n), (z < n - 1, n * n)):
+        eu.append(np.where(ok, g, -1)); ev.append(np.where(ok, g + d, -1))
+    Eu, Ev = np.stack(eu, 1).reshape(-1), np.stack(ev, 1).reshape(-1)
+    keep = (Eu >= 0) & (Ev < hi) & (((Eu >= v0) & (Eu < v1)) | ((Ev >= v0) & (Ev < v1)))
+    Eu, Ev = Eu[keep], Ev[keep]
+    # global edge ids are only needed for ordering: vertex-major emission order == ascending (u, direction)
+    plan = shard.make_plan_local(V, Eu, Ev, world, rank, b)
+    gl = np.concatenate([np.arange(v0, v1), plan.ghosts])
+    zz, yy = gl // (n * n), (gl // n) % n
+    lab = (4 * np.minimum(4 * zz // n, 3) + np.minimum(4 * yy // n, 3)) % K
+    # counter-based uniform(0,1): splitmix64 of (vertex, label)
+    ctr = (gl[:, None].astype(np.uint64) * np.uint64(K) + np.arange(K, dtype=np.uint64)[None, :]) + np.uint64(0x9E3779B97F4A7C15)
+    zq = (ctr ^ (ctr >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    zq = (zq ^ (zq >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    zq = zq ^ (zq >> np.uint64(31))
+    Q = (zq >> np.uint64(11)).astype(np.float64) / 9007199254740992.0
+    Q[np.arange(gl.shape[0]), lab] += 2.0
+    Q /= Q.sum(axis=1, keepdims=True)
+    E_global = 3 * n * n * (n - 1)
+    return dict(plan=plan, V=V, E=E_global, Q=Q.astype(dt), La_d1=np.full(plan.Eu.shape[0], 0.2, dt))
+
+
 def to_dev(a, dev):
     import torch
     return torch.from_numpy(np.ascontiguousarray(a)).to(dev)

@@ -100,3 +100,9 @@ def make_plan(V, Eu, Ev, world, rank, bounds=None):
             recv_vertices=(plan.Vown + np.nonzero(gowner == s)[0]).astype(np.int32),
             recv_halfedges=(ours ^ 1).astype(np.int32)))
     return plan
+
+
+def make_plan_local(V, Eu, Ev, world, rank, bounds=None):
+    """as make_plan, but Eu/Ev hold only the edges touching this rank (global vertex ids, in global edge order):
+    for problems too large to enumerate every edge on every rank.  edge_ids are then positions in that list."""
+    return make_plan(V, Eu, Ev, world, rank, bounds)

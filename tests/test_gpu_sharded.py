@@ -74,7 +74,8 @@ def test_two_ranks_match_single_gpu(gpu_api, oracle, tmp_path, case):
         A = w["La_l2"]
         args = (np.zeros(w["V"]), A * w["Y"], A, w["Eu"], w["Ev"], w["La_d1"], np.full(w["V"], 0.05), 1, 1, A)
         kw = dict(rho=1.5, condMin=1e-3, difRcd=0.0, difTol=1e-5, itMax=300, N=0, want_dif=True)
-        one, ref = b.PFDR_graph_quadratic_d1_l1(*args, **kw), oracle.PFDR_graph_quadratic_d1_l1(*args, **kw)
+        one = b.PFDR_graph_quadratic_d1_l1(args[0].copy(), *args[1:], **kw)
+        ref = oracle.PFDR_graph_quadratic_d1_l1(args[0].copy(), *args[1:], **kw)
     elif case == "quad_rand":
         V = 3000
         Eu, Ev = problems.random_graph(V, 3 * V, 5)
@@ -83,7 +84,8 @@ def test_two_ranks_match_single_gpu(gpu_api, oracle, tmp_path, case):
         Y = A * (np.round(rng.uniform(0, 3, V)) + rng.normal(0, 0.2, V))
         args = (np.zeros(V), Y, A, Eu, Ev, rng.uniform(0.05, 0.5, Eu.shape[0]), 0.2, 2.5, 1, A)
         kw = dict(rho=1.5, condMin=1e-3, difRcd=0.0, difTol=1e-5, itMax=300, N=0, want_dif=True)
-        one, ref = b.PFDR_graph_quadratic_d1_bounds(*args, **kw), oracle.PFDR_graph_quadratic_d1_bounds(*args, **kw)
+        one = b.PFDR_graph_quadratic_d1_bounds(args[0].copy(), *args[1:], **kw)
+        ref = oracle.PFDR_graph_quadratic_d1_bounds(args[0].copy(), *args[1:], **kw)
     else:
         w = synth.c4_simplex(14, 16 if case == "simplex16" else 5, np.float64)
         args = (w["Q"].copy(), w["Q"], 0.05, w["Eu"], w["Ev"], w["La_d1"])
