@@ -47,26 +47,31 @@ template <typename real> struct NcclType;
 template <> struct NcclType<float> { static constexpr ncclDataType_t v = ncclFloat; };
 template <> struct NcclType<double> { static constexpr ncclDataType_t v = ncclDouble; };
 
-// out[i * width + k] = a[idx[i] * width + k], a = the ping or pong buffer selected by the iteration parity
-template <typename real>
-__global__ void gather_items_kernel(real *__restrict__ out, const real *a0, const real *a1, const Ctl *ctl,
-                                    const int *__restrict__ idx, size_t n, int width)
+__device__ __forceinline__ int halo_parity(const Ctl *ctl, int mode)
 {
-    const size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n * width) return;
-    const real *a = (ctl && (ctl->it & 1)) ? a1 : a0;
-    const size_t i = t / width, k = t - i * width;
-    out[t] = a[(size_t) idx[i] * width + k];
+    if (mode == PARITY_ZERO || !ctl) return 0;
+    const int it = ctl->it;
+    if (mode == PARITY_NEXT_IF_RAN && ctl->hold == 0 && ctl->state == ST_RUN) return (it + 1) & 1;
+    return it & 1;
 }
-template <typename real>
-__global__ void scatter_items_kernel(real *a0, real *a1, const Ctl *ctl, const real *__restrict__ in,
-                                     const int *__restrict__ idx, size_t n, int width)
+
+// pack:   out[seg.off + i*width + k] = A[idx[i]*width + k]      unpack: A[idx[i]*width + k] = in[seg.off + i*width + k]
+template <typename real, bool PACK>
+__global__ void halo_kernel(real *buf, PingPong<real> va0, PingPong<real> va1, PingPong<real> z, const Ctl *ctl,
+                            int parity_mode, const HaloSeg *__restrict__ segs, int nsegs, long long total, int width)
 {
-    const size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n * width) return;
-    real *a = (ctl && (ctl->it & 1)) ? a1 : a0;
-    const size_t i = t / width, k = t - i * width;
-    a[(size_t) idx[i] * width + k] = in[t];
+    const long long t = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total * width) return;
+    const long long item = t / width;
+    const int k = (int) (t - item * width);
+    int sidx = 0;
+    while (sidx + 1 < nsegs && item >= segs[sidx + 1].start) sidx++;
+    const HaloSeg sg = segs[sidx];
+    const int par = halo_parity(ctl, parity_mode);
+    real *arr = sg.arr == 0 ? va0.a[par] : (sg.arr == 1 ? va1.a[par] : z.a[par]);
+    const long long i = item - sg.start;
+    const size_t a = (size_t) sg.idx[i] * width + k, b = (size_t) sg.off + (size_t) i * width + k;
+    if (PACK) buf[b] = arr[a]; else arr[a] = buf[b];
 }
 __global__ void key_to_slot_kernel(const int *__restrict__ hkey, long long nslots, int *__restrict__ pos)
 {
@@ -163,50 +168,52 @@ void Halo<real>::setup(const ShardInfo &s, const int *d_hkey, long long nslots, 
     if (trh) PFDR_LAUNCH(map_keys_kernel, cdiv(trh, 256), 256, 0, d_rh.p, pos.p, trh, d_rs.p);
     sendbuf.alloc(std::max<size_t>((2 * tsv + tsh) * width, 1));
     recvbuf.alloc(std::max<size_t>((2 * trv + trh) * width, 1));
+    // segment tables
+    for (int layout = 0; layout < 2; layout++) {
+        std::vector<HaloSeg> ps, us;
+        soff[layout].assign(nnb, 0); roff[layout].assign(nnb, 0); scnt[layout].assign(nnb, 0); rcnt[layout].assign(nnb, 0);
+        long long pstart = 0, ustart = 0;
+        size_t so = 0, ro = 0;
+        for (int i = 0; i < nnb; i++) {
+            soff[layout][i] = so; roff[layout][i] = ro;
+            const int narr = layout == 0 ? 2 : 1;
+            for (int a = 0; a < narr; a++) {
+                if (nsv[i]) { ps.push_back({d_sv.p + sv_off[i], pstart, nsv[i], (long long) so, a}); pstart += nsv[i]; so += (size_t) nsv[i] * width; }
+                if (nrv[i]) { us.push_back({d_rv.p + rv_off[i], ustart, nrv[i], (long long) ro, a}); ustart += nrv[i]; ro += (size_t) nrv[i] * width; }
+            }
+            if (layout == 1) {
+                if (nsh[i]) { ps.push_back({d_ss.p + sh_off[i], pstart, nsh[i], (long long) so, 2}); pstart += nsh[i]; so += (size_t) nsh[i] * width; }
+                if (nrh[i]) { us.push_back({d_rs.p + rh_off[i], ustart, nrh[i], (long long) ro, 2}); ustart += nrh[i]; ro += (size_t) nrh[i] * width; }
+            }
+            scnt[layout][i] = so - soff[layout][i]; rcnt[layout][i] = ro - roff[layout][i];
+        }
+        nseg[layout] = (int) ps.size();
+        pack_items[layout] = pstart; unpack_items[layout] = ustart;
+        d_pack[layout].alloc(std::max<size_t>(ps.size(), 1)); d_unpack[layout].alloc(std::max<size_t>(us.size(), 1));
+        if (!ps.empty()) PFDR_CUDA(cudaMemcpyAsync(d_pack[layout].p, ps.data(), ps.size() * sizeof(HaloSeg), cudaMemcpyHostToDevice, st));
+        if (!us.empty()) PFDR_CUDA(cudaMemcpyAsync(d_unpack[layout].p, us.data(), us.size() * sizeof(HaloSeg), cudaMemcpyHostToDevice, st));
+        PFDR_CUDA(cudaStreamSynchronize(st));      // ps / us die at the end of this scope
+        nuseg[layout] = (int) us.size();
+    }
     PFDR_CUDA(cudaStreamSynchronize(st));
 }
 
 template <typename real>
-void Halo<real>::exchange(PingPong<real> va0, PingPong<real> va1, PingPong<real> Zp, const Ctl *ctl)
+void Halo<real>::exchange(int layout, PingPong<real> va0, PingPong<real> va1, PingPong<real> Z, const Ctl *ctl, int parity)
 {
     if (!nnb) return;
-    PingPong<real> va[2] = {va0, va1};
-    const int nva = va1.a[0] ? 2 : 1;
-    real *Z = Zp.a[0];
-    std::vector<size_t> soff(nnb), roff(nnb), scnt(nnb), rcnt(nnb);
-    size_t so = 0, ro = 0;
-    for (int i = 0; i < nnb; i++) {           // pack
-        soff[i] = so; roff[i] = ro;
-        for (int a = 0; a < nva; a++) {
-            if (nsv[i]) PFDR_LAUNCH(gather_items_kernel<real>, cdiv((size_t) nsv[i] * width, 256), 256, 0,
-                                    sendbuf.p + so, va[a].a[0], va[a].a[1], ctl, d_sv.p + sv_off[i], (size_t) nsv[i], width);
-            so += (size_t) nsv[i] * width;
-        }
-        if (Z) {
-            if (nsh[i]) PFDR_LAUNCH(gather_items_kernel<real>, cdiv((size_t) nsh[i] * width, 256), 256, 0,
-                                    sendbuf.p + so, Zp.a[0], Zp.a[1], ctl, d_ss.p + sh_off[i], (size_t) nsh[i], width);
-            so += (size_t) nsh[i] * width;
-        }
-        scnt[i] = so - soff[i];
-        rcnt[i] = ((size_t) nva * nrv[i] + (Z ? nrh[i] : 0)) * width;
-        ro += rcnt[i];
-    }
+    if (pack_items[layout])
+        PFDR_LAUNCH((halo_kernel<real, true>), cdiv((size_t) pack_items[layout] * width, 256), 256, 0, sendbuf.p, va0, va1, Z,
+                    ctl, parity, d_pack[layout].p, nseg[layout], pack_items[layout], width);
     comm_group_start();
     for (int i = 0; i < nnb; i++) {
-        if (scnt[i]) comm_send<real>(sendbuf.p + soff[i], scnt[i], rank[i]);
-        if (rcnt[i]) comm_recv<real>(recvbuf.p + roff[i], rcnt[i], rank[i]);
+        if (scnt[layout][i]) comm_send<real>(sendbuf.p + soff[layout][i], scnt[layout][i], rank[i]);
+        if (rcnt[layout][i]) comm_recv<real>(recvbuf.p + roff[layout][i], rcnt[layout][i], rank[i]);
     }
     comm_group_end();
-    for (int i = 0; i < nnb; i++) {           // unpack
-        size_t o = roff[i];
-        for (int a = 0; a < nva; a++) {
-            if (nrv[i]) PFDR_LAUNCH(scatter_items_kernel<real>, cdiv((size_t) nrv[i] * width, 256), 256, 0,
-                                    va[a].a[0], va[a].a[1], ctl, recvbuf.p + o, d_rv.p + rv_off[i], (size_t) nrv[i], width);
-            o += (size_t) nrv[i] * width;
-        }
-        if (Z && nrh[i]) PFDR_LAUNCH(scatter_items_kernel<real>, cdiv((size_t) nrh[i] * width, 256), 256, 0,
-                                     Zp.a[0], Zp.a[1], ctl, recvbuf.p + o, d_rs.p + rh_off[i], (size_t) nrh[i], width);
-    }
+    if (unpack_items[layout])
+        PFDR_LAUNCH((halo_kernel<real, false>), cdiv((size_t) unpack_items[layout] * width, 256), 256, 0, recvbuf.p, va0, va1, Z,
+                    ctl, parity, d_unpack[layout].p, nuseg[layout], unpack_items[layout], width);
 }
 
 template struct Halo<float>;

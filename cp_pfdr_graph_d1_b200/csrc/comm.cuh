@@ -36,7 +36,12 @@ template <typename real> struct PingPong {
 };
 
 // Halo engine shared by both solver families: per neighbour, a message is
-//   [ va[0][send vertices] ... va[nva-1][send vertices] | Z[send slots] ]   (each item `width` reals wide)
+//   [ va0[send vertices] | va1[send vertices] (optional) | Z[send slots] (optional) ]   (each item `width` reals wide)
+// One pack kernel, one grouped ncclSend/ncclRecv, one unpack kernel per exchange.
+struct HaloSeg { const int *idx; long long start, n, off; int arr; };   // arr: 0 = va0, 1 = va1, 2 = Z
+
+enum : int { PARITY_ZERO = 0, PARITY_CUR = 1, PARITY_NEXT_IF_RAN = 2 };
+
 template <typename real>
 struct Halo {
     int nnb = 0, width = 1;
@@ -44,12 +49,17 @@ struct Halo {
     std::vector<size_t> sv_off, sh_off, rv_off, rh_off;
     DevBuf<int> d_sv, d_ss, d_rv, d_rs;           // send vertices / send slots / recv vertices / recv slots
     DevBuf<real> sendbuf, recvbuf;
+    // segment tables for the two message layouts: [0] = two vertex arrays (setup), [1] = one vertex array + Z (iteration)
+    DevBuf<HaloSeg> d_pack[2], d_unpack[2];
+    int nseg[2] = {0, 0}, nuseg[2] = {0, 0};
+    long long pack_items[2] = {0, 0}, unpack_items[2] = {0, 0};
+    std::vector<size_t> soff[2], roff[2], scnt[2], rcnt[2];
 
     // hkey: [nslots] half-edge key of every slot (-1 padding); nkeys = 2 * local edges
     void setup(const ShardInfo &s, const int *d_hkey, long long nslots, size_t nkeys, int width_);
-    // exchanges up to 2 vertex arrays (+ the half-edge copies Z when non-null), in place; with ctl the
-    // buffers of the CURRENT iteration parity are used (decided on the device, no host synchronisation)
-    void exchange(PingPong<real> va0, PingPong<real> va1, PingPong<real> Z, const Ctl *ctl);
+    // layout 0: va0, va1 (no Z); layout 1: va0 + Z.  parity selects which of the ping/pong buffers is used,
+    // decided on the device from the control block (no host synchronisation)
+    void exchange(int layout, PingPong<real> va0, PingPong<real> va1, PingPong<real> Z, const Ctl *ctl, int parity);
 };
 
 }  // namespace pfdr

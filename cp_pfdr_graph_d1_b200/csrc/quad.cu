@@ -822,7 +822,7 @@ struct QuadSolver : SolverBase {
         if (sharded) { comm_allreduce_sum(sums.p, 2); PFDR_LAUNCH(amp_finish_kernel<real>, 1, 1, 0, p, 0); }
         PFDR_LAUNCH(init_vertex_kernel<real>, vgrid, 256, 0, p, X0.p);
         // ghosts: the metric constants and forward point come from their owners
-        if (sharded) halo.exchange(PingPong<real>(T.p), PingPong<real>(P0b.p), PingPong<real>(), nullptr);
+        if (sharded) halo.exchange(0, PingPong<real>(T.p), PingPong<real>(P0b.p), PingPong<real>(), nullptr, PARITY_ZERO);
         PFDR_CUDA(cudaMemcpyAsync(&hctl[1], ctl.p, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
         PFDR_CUDA(cudaStreamSynchronize(st));
         const real thc0 = (real) 1 / (real) hctl[1].amp;       // La_d1 / (c La_d1)
@@ -855,10 +855,11 @@ struct QuadSolver : SolverBase {
             PFDR_LAUNCH(objective_kernel<real>, std::min<unsigned>(cdiv(work, 256), num_sms() * 8), 256, 0, p);
         }
         launch_iter();
-        if (sharded) {     // evolution sums over all ranks, then the new boundary values and cut-edge copies
+        if (sharded) {     // new boundary forward points and cut-edge copies to the neighbours (taken from the buffers the
+                           // iteration kernel just wrote), evolution sums over all ranks, then the iteration is closed
+            halo.exchange(1, PingPong<real>(P0b.p, P1b.p), PingPong<real>(), PingPong<real>(Z0.p, Z1.p), ctl.p, PARITY_NEXT_IF_RAN);
             comm_allreduce_sum(sums.p, 2);
             PFDR_LAUNCH(quad_finalize_kernel<real>, 1, 1, 0, p);
-            halo.exchange(PingPong<real>(P0b.p, P1b.p), PingPong<real>(), PingPong<real>(Z0.p, Z1.p), ctl.p);
         }
     }
 
@@ -892,13 +893,13 @@ struct QuadSolver : SolverBase {
 #undef PFDR_ROWS
     }
 
-    int launches_per_trip() const { return (q.N > 0 ? 3 : (q.N < 0 ? 1 : 0)) + (q.Obj ? 1 : 0) + 1; }
+    int launches_per_trip() const { return (q.N > 0 ? 3 : (q.N < 0 ? 1 : 0)) + (q.Obj ? 1 : 0) + 1 + (sharded ? 5 : 0); }
 
     // enqueue `trips` iterations; replays a captured CUDA graph when a whole batch is requested
     void enqueue_batch(int trips, int batch)
     {
         cudaStream_t st = ctx().stream;
-        if (trips == batch && use_graph() && !sharded) {
+        if (trips == batch && use_graph()) {
             if (!gexec || graph_trips != batch) {
                 if (gexec) { cudaGraphExecDestroy(gexec); gexec = nullptr; }
                 cudaGraph_t graph;

@@ -623,7 +623,7 @@ struct SimplexSolver : SolverBase {
         hctl[0] = h;
         PFDR_CUDA(cudaMemcpyAsync(ctl.p, &hctl[0], sizeof(Ctl), cudaMemcpyHostToDevice, st));
         launch_precond(P0.p, 0);
-        if (sharded) halo.exchange(PingPong<real>(T.p), PingPong<real>(Fa.p), PingPong<real>(), nullptr);
+        if (sharded) halo.exchange(0, PingPong<real>(T.p), PingPong<real>(Fa.p), PingPong<real>(), nullptr, PARITY_ZERO);
         PFDR_CUDA(cudaStreamSynchronize(st));
     }
 
@@ -659,19 +659,19 @@ struct SimplexSolver : SolverBase {
         if (LPT == 4) { if (p.wk) launch_iter_loss<4, true>(); else launch_iter_loss<4, false>(); }
         else { if (p.wk) launch_iter_loss<1, true>(); else launch_iter_loss<1, false>(); }
         if (sharded) {     // evolution sum over all ranks, then the new boundary forward points and cut-edge copies
+            halo.exchange(1, PingPong<real>(Fa.p, Fb.p), PingPong<real>(), PingPong<real>(Z0.p, Z1.p), ctl.p, PARITY_NEXT_IF_RAN);
             comm_allreduce_sum(sums.p, 1);
             PFDR_LAUNCH(simplex_finalize_kernel<real>, 1, 1, 0, p);
-            halo.exchange(PingPong<real>(Fa.p, Fb.p), PingPong<real>(), PingPong<real>(Z0.p, Z1.p), ctl.p);
         }
     }
-    int launches_per_trip() const { return (q.Obj ? 1 : 0) + 1; }
+    int launches_per_trip() const { return (q.Obj ? 1 : 0) + 1 + (sharded ? 5 : 0); }
 
     void enqueue_batch(int batch)
     {
         cudaStream_t st = ctx().stream;
         static int use_graph = -1;
         if (use_graph < 0) { const char *e = getenv("PFDR_B200_GRAPH"); use_graph = (e && e[0] == '0') ? 0 : 1; }
-        if (!use_graph || sharded) { for (int i = 0; i < batch; i++) enqueue_trip(); return; }
+        if (!use_graph) { for (int i = 0; i < batch; i++) enqueue_trip(); return; }
         if (!gexec || graph_trips != batch) {
             if (gexec) { cudaGraphExecDestroy(gexec); gexec = nullptr; }
             cudaGraph_t graph;
