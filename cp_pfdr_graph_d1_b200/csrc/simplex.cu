@@ -301,6 +301,97 @@ __global__ void simplex_resume_kernel(SP<real> p)
 // ---------------------------------------------------------------------------------------------
 // fused iteration
 // ---------------------------------------------------------------------------------------------
+// d1 prox + relaxation of one half-edge row for the lane's LPT labels (ref :590-634); accumulates W.z into acc
+template <typename real, int LPT, bool PERK, int LOSS>
+__device__ __forceinline__ VecN<real, LPT> prox_row(real rho, const VecN<real, LPT> &fown, const VecN<real, LPT> &pold,
+    const VecN<real, LPT> &Tv, const VecN<real, LPT> &Sv, const VecN<real, LPT> &zo, const VecN<real, LPT> &zt,
+    const VecN<real, LPT> &fn, const VecN<real, LPT> &tn, const VecN<real, LPT> &wvk, const VecN<real, LPT> &th, real w,
+    VecN<real, LPT> &acc)
+{
+    VecN<real, LPT> zn;
+    const real ws = w * Sv.v[0];                                              // row weight W = w/S (per vertex before recond.)
+#pragma unroll
+    for (int i = 0; i < LPT; i++) {
+        const real po = fown.v[i] - zo.v[i], pt = fn.v[i] - zt.v[i];
+        const real d0 = po - pt;
+        if (LOSS == LOSS_LIN) {                                               // ref :599-614 (weights 1/2, threshold 2)
+            const real ds = d0 - min(max(d0, (real) -2), (real) 2);
+            zn.v[i] = zo.v[i] + rho * ((real) 0.5 * (po + pt) + (real) 0.5 * ds - pold.v[i]);
+        } else {                                                              // ref :615-631
+            const real tsum = Tv.v[i] + tn.v[i], inv = fast_rcp(tsum);
+            const real t = PERK ? th.v[i] * tsum : tsum;                      // La_d1/w = 1 before a reconditioning
+            const real wo = tn.v[i] * inv, wt = Tv.v[i] * inv;                // W_d1 own / twin side
+            const real ds = d0 - min(max(d0, -t), t);                         // soft threshold, exact 0 inside
+            // W_d1u.pu + W_d1v.pv = pt + wo.(po - pt) since the two weights sum to one
+            zn.v[i] = zo.v[i] + rho * (fma(wo, d0, pt) + wt * ds - pold.v[i]);
+        }
+        acc.v[i] += (PERK ? wvk.v[i] * Sv.v[i] : ws) * zn.v[i];
+    }
+    return zn;
+}
+
+// projection on the simplex in the metric m (Michelot's active-set iteration, all lanes of the vertex in parallel,
+// ref :651 / proj_simplex_metric.cpp:40-81), next (P, FP) (:569-587) and this lane's share of the evolution (:654-691)
+template <typename real, int LPT, bool PERK, int LOSS>
+__device__ __forceinline__ double simplex_epilogue(const SP<real> &p, Ctl *ctl, bool on, int v, int k0, size_t vk,
+    VecN<real, LPT> acc, const VecN<real, LPT> &Tv, const VecN<real, LPT> &pold, real *__restrict__ Pn, real *__restrict__ Fn)
+{
+    typedef VecN<real, LPT> vec;
+    const int K = p.K, TPV = p.TPV;
+    vec m;
+    if (PERK) { if (on) m = ldv<real, LPT>(p.Gn + vk); else m = splat<real, LPT>((real) 1); }
+    else if (LOSS == LOSS_LIN) m = splat<real, LPT>((real) 1);     // Ga = 1/S is the same for all labels
+    else m = Tv;
+    vec xs;
+    unsigned act = 0;
+#pragma unroll
+    for (int i = 0; i < LPT; i++) {
+        if (!on) { m.v[i] = (real) 1; acc.v[i] = 0; }
+        xs.v[i] = acc.v[i] / m.v[i];
+        if (on && k0 + i < K) act |= 1u << i;
+    }
+    real la = 0;
+    for (;;) {
+        real sx = 0, sm = 0;
+#pragma unroll
+        for (int i = 0; i < LPT; i++) if ((act >> i) & 1u) { sx += acc.v[i]; sm += m.v[i]; }
+        sx = group_sum(sx, TPV); sm = group_sum(sm, TPV);
+        la = (sx - (real) 1) / sm;
+        unsigned keep = act;
+#pragma unroll
+        for (int i = 0; i < LPT; i++) if (((act >> i) & 1u) && xs.v[i] < la) keep &= ~(1u << i);
+        const bool changed = keep != act;
+        act = keep;
+        if (!__any_sync(0xffffffffu, changed)) break;
+    }
+    vec pnew;
+#pragma unroll
+    for (int i = 0; i < LPT; i++) pnew.v[i] = ((act >> i) & 1u) ? (xs.v[i] - la) * m.v[i] : (real) 0;
+    if (on) {
+        const vec gaq = ldv<real, LPT>(p.GaQ + vk);
+        vec qv = splat<real, LPT>((real) 0), f;
+        if (LOSS == LOSS_QUAD) qv = ldv<real, LPT>(p.Q + vk);
+#pragma unroll
+        for (int i = 0; i < LPT; i++) {
+            if (LOSS == LOSS_KLA) f.v[i] = (real) 2 * pnew.v[i] + gaq.v[i] * fast_rcp(p.aK1 + pnew.v[i]);
+            else f.v[i] = forward_point(LOSS, p.aK1, pnew.v[i], gaq.v[i], qv.v[i]);
+        }
+        stv<real, LPT>(Pn + vk, pnew);
+        stv<real, LPT>(Fn + vk, f);
+    }
+    double red = 0.0;
+    if (p.by_label) {                                                         // ref :657-676
+        const int i = group_argmax<real, LPT>(pnew, on ? k0 : K, K, TPV);
+        if (on && k0 == 0 && ctl->track) { if (i != p.lab[v]) { red = 1.0; p.lab[v] = i; } }
+    } else if (on) {                                                          // ref :681-687
+        real d = 0;
+#pragma unroll
+        for (int i = 0; i < LPT; i++) d += sabs(pold.v[i] - pnew.v[i]);
+        red = (double) d;
+    }
+    return red;
+}
+
 // end of an iteration: evolution measure (ref :654-691), iteration counter, stop / recondition decision (:551, :554)
 template <typename real>
 __device__ void simplex_finalize(const SP<real> &p, int it, double s)
@@ -392,86 +483,19 @@ __global__ void __launch_bounds__(256, MINB) simplex_iter_kernel(SP<real> p)
                 zo_n = ldv<real, LPT>(Zin + (size_t) s2 * K + k0);
             }
             if (live) {
-                vec zn;
-                const real ws = w_c * Sv.v[0];                                // row weight W = w/S (per vertex before recond.)
-#pragma unroll
-                for (int i = 0; i < LPT; i++) {
-                    const real po = fown.v[i] - zo_c.v[i], pt = fn.v[i] - zt.v[i];
-                    const real d0 = po - pt;
-                    if (LOSS == LOSS_LIN) {                                   // ref :599-614 (weights 1/2, threshold 2)
-                        const real ds = d0 - min(max(d0, (real) -2), (real) 2);
-                        zn.v[i] = zo_c.v[i] + rho * ((real) 0.5 * (po + pt) + (real) 0.5 * ds - pold.v[i]);
-                    } else {                                                  // ref :615-631
-                        const real tsum = Tv.v[i] + tn.v[i], inv = fast_rcp(tsum);
-                        const real t = PERK ? th.v[i] * tsum : tsum;          // La_d1/w = 1 before a reconditioning
-                        const real wo = tn.v[i] * inv, wt = Tv.v[i] * inv;    // W_d1 own / twin side
-                        const real ds = d0 - min(max(d0, -t), t);             // soft threshold, exact 0 inside
-                        // W_d1u.pu + W_d1v.pv = pt + wo.(po - pt) since the two weights sum to one
-                        zn.v[i] = zo_c.v[i] + rho * (fma(wo, d0, pt) + wt * ds - pold.v[i]);
-                    }
-                    acc.v[i] += (PERK ? wvk.v[i] * Sv.v[i] : ws) * zn.v[i];
-                }
+                const vec zn = prox_row<real, LPT, PERK, LOSS>(rho, fown, pold, Tv, Sv, zo_c, zt, fn, tn, wvk, th, w_c, acc);
                 if (p.stream_z) stv_cs<real, LPT>(Zout + (size_t) s * K + k0, zn); else stv<real, LPT>(Zout + (size_t) s * K + k0, zn);
             }
             n_c = n_n; tw_c = tw_n; w_c = w_n; zo_c = zo_n;
         }
-        // ---- projection on the simplex in the metric m (Michelot, all lanes of the vertex in parallel) ----
-        vec m;
-        if (PERK) { if (on) m = ldv<real, LPT>(p.Gn + vk); else m = splat<real, LPT>((real) 1); }
-        else if (LOSS == LOSS_LIN) m = splat<real, LPT>((real) 1);     // Ga = 1/S is the same for all labels
-        else m = Tv;
-        vec xs;
-        unsigned act = 0;
-#pragma unroll
-        for (int i = 0; i < LPT; i++) {
-            if (!on) { m.v[i] = (real) 1; acc.v[i] = 0; }
-            xs.v[i] = acc.v[i] / m.v[i];
-            if (on && k0 + i < K) act |= 1u << i;
-        }
-        real la = 0;
-        for (;;) {
-            real sx = 0, sm = 0;
-#pragma unroll
-            for (int i = 0; i < LPT; i++) if ((act >> i) & 1u) { sx += acc.v[i]; sm += m.v[i]; }
-            sx = group_sum(sx, TPV); sm = group_sum(sm, TPV);
-            la = (sx - (real) 1) / sm;
-            unsigned keep = act;
-#pragma unroll
-            for (int i = 0; i < LPT; i++) if (((act >> i) & 1u) && xs.v[i] < la) keep &= ~(1u << i);
-            const bool changed = keep != act;
-            act = keep;
-            if (!__any_sync(0xffffffffu, changed)) break;
-        }
-        vec pnew;
-#pragma unroll
-        for (int i = 0; i < LPT; i++) pnew.v[i] = ((act >> i) & 1u) ? (xs.v[i] - la) * m.v[i] : (real) 0;
-        if (on) {
-            const vec gaq = ldv<real, LPT>(p.GaQ + vk);
-            vec qv = splat<real, LPT>((real) 0), f;
-            if (LOSS == LOSS_QUAD) qv = ldv<real, LPT>(p.Q + vk);
-#pragma unroll
-            for (int i = 0; i < LPT; i++) {
-                if (LOSS == LOSS_KLA) f.v[i] = (real) 2 * pnew.v[i] + gaq.v[i] * fast_rcp(p.aK1 + pnew.v[i]);
-                else f.v[i] = forward_point(LOSS, p.aK1, pnew.v[i], gaq.v[i], qv.v[i]);
-            }
-            stv<real, LPT>(Pn + vk, pnew);
-            stv<real, LPT>(Fn + vk, f);
-        }
-        if (p.by_label) {                                                     // ref :657-676
-            const int i = group_argmax<real, LPT>(pnew, on ? k0 : K, K, TPV);
-            if (on && k0 == 0 && ctl->track) { if (i != p.lab[v]) { red[0] = 1.0; p.lab[v] = i; } }
-        } else if (on) {                                                      // ref :681-687
-            real d = 0;
-#pragma unroll
-            for (int i = 0; i < LPT; i++) d += sabs(pold.v[i] - pnew.v[i]);
-            red[0] = (double) d;
-        }
+        red[0] = simplex_epilogue<real, LPT, PERK, LOSS>(p, ctl, on, v, k0, vk, acc, Tv, pold, Pn, Fn);
     }
     if (grid_sum_s<1>(ctl, p.partial, red, smem) && threadIdx.x == 0) {
         if (p.sharded) p.sums[0] = red[0];
         else simplex_finalize(p, it, red[0]);
     }
 }
+
 
 // objective (ref :477-544)
 template <typename real>
@@ -640,7 +664,7 @@ struct SimplexSolver : SolverBase {
         else if (L == 4 && !PERK && LOSS == LOSS_KLA && MB == 6) PFDR_LAUNCH((simplex_iter_kernel<real, 4, false, LOSS_KLA, 6>), ogrid, 256, 0, p);
         else if (L == 4 && !PERK && LOSS == LOSS_KLA && MB == 8) PFDR_LAUNCH((simplex_iter_kernel<real, 4, false, LOSS_KLA, 8>), ogrid, 256, 0, p);
         else if (L == 4 && !PERK && LOSS == LOSS_KLA && MB == 1) PFDR_LAUNCH((simplex_iter_kernel<real, 4, false, LOSS_KLA, 1>), ogrid, 256, 0, p);
-        else PFDR_LAUNCH((simplex_iter_kernel<real, L, PERK, LOSS, 4>), ogrid, 256, 0, p);
+        else PFDR_LAUNCH((simplex_iter_kernel<real, L, PERK, LOSS, (sizeof(real) == 4 ? 4 : 2)>), ogrid, 256, 0, p);
     }
     template <int L, bool PERK>
     void launch_iter_loss()
