@@ -356,6 +356,85 @@ __global__ void __launch_bounds__(256) quad_iter_kernel(QP<real> p)
     }
 }
 
+// Pipelined variant: one row at a time, the next row's indices / weight / own copy are requested while the
+// current row's gathers are in flight (as simplex_iter_kernel).  Few registers -> up to 64 warps per SM.
+template <typename real, bool PER_SLOT_TH, int MINB>
+__global__ void __launch_bounds__(256, MINB) quad_iter_pipe_kernel(QP<real> p)
+{
+    __shared__ double smem[64];
+    Ctl *ctl = p.ctl;
+    const CtlView cv = load_ctl(ctl);
+    if (cv.hold != 0 || cv.state != ST_RUN) {
+        if (cv.hold == 0 && blockIdx.x == 0 && threadIdx.x == 0) ctl->hold = 1;
+        return;
+    }
+    const int it = cv.it, cur = it & 1;
+    const real *__restrict__ Zin = cur ? p.Z1 : p.Z0;
+    real *__restrict__ Zout = cur ? p.Z0 : p.Z1;
+    const real *__restrict__ Pc = cur ? p.P1 : p.P0;
+    const real *__restrict__ Tg = p.T;
+    const int *__restrict__ nbr = p.nbr;
+    const int *__restrict__ twin = p.twin;
+    const real *__restrict__ wg = p.w;
+    const real rho = p.rho;
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    double red[2] = {0.0, 0.0};
+    if (v < p.Vown) {
+        const long long base = p.slice_off[v >> 5];
+        const int width = (int) ((p.slice_off[(v >> 5) + 1] - base) >> 5);
+        int s = (int) base + (v & 31);
+        const real xo = (cur ? p.X1 : p.X0)[v], po_v = Pc[v];
+        const real Tv = Tg[v], Sv = p.Sinv[v];
+        real acc = 0;
+        int n_c = -1, tw_c = 0;
+        real w_c = 0, zo_c = 0, th_c = p.thc0;
+        if (width > 0) { n_c = nbr[s]; tw_c = twin[s]; w_c = wg[s]; zo_c = Zin[s]; if (PER_SLOT_TH) th_c = p.thc[s]; }
+        for (int j = 0; j < width; j++, s += 32) {
+            const bool live = n_c >= 0;
+            real pn = 0, Tn = 1, zt = 0;
+            if (live) { pn = Pc[n_c]; Tn = Tg[n_c]; zt = Zin[tw_c]; }
+            int n_n = -1, tw_n = 0;
+            real w_n = 0, zo_n = 0, th_n = p.thc0;
+            if (j + 1 < width) {
+                n_n = nbr[s + 32]; tw_n = twin[s + 32]; w_n = wg[s + 32]; zo_n = Zin[s + 32];
+                if (PER_SLOT_TH) th_n = p.thc[s + 32];
+            }
+            if (live) {
+                const real tsum = Tv + Tn, inv = fast_rcp(tsum);
+                const real th = th_c * tsum;                                  // Th_d1
+                const real wo = Tn * inv, wt = Tv * inv;                      // W_d1 own / twin side
+                const real po = po_v - zo_c, pt = pn - zt, d0 = po - pt;
+                const real b = d0 - min(max(d0, -th), th);                    // soft threshold (ref :477-488), exact 0 inside
+                // W_d1u.pu + W_d1v.pv = pt + wo.(po - pt): the two weights sum to one
+                const real zn = zo_c + rho * (fma(wo, d0, pt) + wt * b - xo);
+                Zout[s] = zn;
+                acc += (w_c * Sv) * zn;
+            }
+            n_c = n_n; tw_c = tw_n; w_c = w_n; zo_c = zo_n; th_c = th_n;
+        }
+        real x = acc;
+        if (p.prox_kind == 0) {                                                // ref l1.cpp :500-512
+            if (p.La_l1) {
+                const real th = p.Thl1[v];
+                if (x > th) x -= th;
+                else if (!p.positivity && x < -th) x += th;
+                else x = 0;
+            } else if (p.positivity) { if (x < (real) 0) x = 0; }
+        } else {                                                               // ref bounds.cpp :473-490
+            if (p.has_lo && x < p.lo) x = p.lo;
+            else if (p.has_hi && x > p.hi) x = p.hi;
+        }
+        (cur ? p.X0 : p.X1)[v] = x;
+        if (p.N == 0) (cur ? p.P0 : p.P1)[v] = (real) 2 * x - p.Ga[v] * grad_at(p, v, x);
+        const real dx = xo - x;
+        red[0] = (double) (dx * dx); red[1] = (double) (x * x);
+    }
+    if (grid_sum<2>(ctl, p.partial, red, smem) && threadIdx.x == 0) {
+        if (p.sharded) { p.sums[0] = red[0]; p.sums[1] = red[1]; }
+        else quad_finalize(p, it, red[0], red[1]);
+    }
+}
+
 // Row-parallel variant: one thread per half-edge slot.  A CTA owns G slices (32 vertices each); warp (g, r)
 // walks rows r, r+W, ... of slice g, so every load is a single coalesced row and a vertex's W rows are in
 // flight in W different warps (thread-level instead of instruction-level parallelism, ~32 registers).
@@ -863,14 +942,28 @@ struct QuadSolver : SolverBase {
         }
     }
 
-    // default: the one-thread-per-vertex kernel (PFDR_B200_U rows in flight, default 8 / 4);
-    // PFDR_B200_KERNEL=rows selects the row-parallel kernel (slower, kept for comparison: profiles/r01_notes.md).
+    // default: one thread per vertex, rows software-pipelined (quad_iter_pipe_kernel).  For comparison
+    // (profiles/r01_notes.md): PFDR_B200_PIPE=0 -> chunked kernel (PFDR_B200_U rows in flight, default 8 / 4),
+    // PFDR_B200_KERNEL=rows -> row-parallel kernel.
     int rowsW = 0;
     void launch_iter()
     {
         static int U = -1, mode = -1;
         if (U < 0) { const char *e = getenv("PFDR_B200_U"); U = e ? atoi(e) : 0; }
         if (mode < 0) { const char *e = getenv("PFDR_B200_KERNEL"); mode = (e && !strcmp(e, "rows")) ? 0 : 1; }
+        // default: pipelined kernel at 8 (f32) / 6 (f64) CTAs per SM; PFDR_B200_PIPE=0 selects the chunked kernel
+        static int pipe = -1;
+        if (pipe < 0) { const char *e = getenv("PFDR_B200_PIPE"); pipe = e ? atoi(e) : (sizeof(real) == 4 ? 8 : 6); }
+        if (mode == 1 && pipe > 0) {
+#define PFDR_PIPE(MB)                                                                              \
+            do {                                                                                   \
+                if (p.thc) PFDR_LAUNCH((quad_iter_pipe_kernel<real, true, MB>), ogrid, 256, 0, p); \
+                else PFDR_LAUNCH((quad_iter_pipe_kernel<real, false, MB>), ogrid, 256, 0, p);      \
+            } while (0)
+            if (pipe >= 8) PFDR_PIPE(8); else if (pipe >= 6) PFDR_PIPE(6); else PFDR_PIPE(4);
+#undef PFDR_PIPE
+            return;
+        }
         if (mode == 1) {
             const int u = U > 0 ? U : (sizeof(real) == 4 ? 8 : 4);
 #define PFDR_ITER(UU)                                                                          \
