@@ -23,10 +23,14 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 
-def algorithmic_bytes(kind, V, E, r, K=1, diag=True, l1=False):
+def algorithmic_bytes(kind, V, E, r, K=1, diag=True, l1=False, N=0):
     """minimal bytes that must cross HBM once per iteration."""
     if kind == "quad":
         return E * (8 + 5 * r) + V * 5 * r + (V * r if diag else 0) + (V * r if l1 else 0)
+    if kind == "ata":
+        return E * (8 + 5 * r) + V * 5 * r + V * V * r + 2 * r * V
+    if kind == "dense":
+        return E * (8 + 5 * r) + V * 5 * r + 2 * N * V * r + 2 * r * V
     return E * (8 + r + 4 * r * K) + V * 5 * r * K
 
 
@@ -38,6 +42,10 @@ WORKLOADS = {
     "c4_f64": ("simplex", 252, np.float64, 16, 100),
     "c4s_f32": ("simplex", 64, np.float32, 16, 100),      # parity-sized C4 (also what the CPU legs of C4 run)
     "c4s_f64": ("simplex", 64, np.float64, 16, 100),
+    # dense operators (device-generated): C3 direct PFDR with precomputed A^tA (V = 32768, k-NN graph),
+    # and a single-GPU slice of C5 (dense N = 256 lead field on a 160^3 grid: A is 4.2 GB)
+    "c3_f32": ("ata", 32768, np.float32, 1, 50),
+    "c5s_f32": ("dense", 160, np.float32, 1, 50),
 }
 
 
@@ -46,6 +54,12 @@ def describe(name):
     if kind == "quad":
         return (f"C2 PFDR_graph_l22_d1_l1 (diagonal A) denoising, 3D 6-connected grid {n}^3, "
                 f"{np.dtype(dt).name}, rho=1.5, difTol=0, itMax={iters}")
+    if kind == "ata":
+        return (f"C3 PFDR_graph_quadratic_d1_bounds, dense precomputed AtA V={n}, box [0,1], 10-NN graph, "
+                f"{np.dtype(dt).name}, SCAL L, rho=1.5, difTol=0, itMax={iters}")
+    if kind == "dense":
+        return (f"C5 slice PFDR_graph_quadratic_d1_l1, dense A N=256 on a 3D grid {n}^3, {np.dtype(dt).name}, SCAL L, "
+                f"rho=1, difTol=0, itMax={iters}")
     return (f"C4 PFDR_graph_loss_d1_simplex smoothed-KL (al=0.05), K={K}, 3D grid {n}^3, {np.dtype(dt).name}, "
             f"rho=1.5, condMin=1e-2, difTol=0, itMax={iters}")
 
@@ -113,6 +127,8 @@ class ClockSampler:
 def host_inputs(name):
     from cp_pfdr_graph_d1_b200 import synth
     kind, n, dt, K, iters = WORKLOADS[name]
+    if kind in ("ata", "dense"):
+        return None
     if kind == "quad":
         w = synth.c2_denoise(n, dt, diag=True)
         w["Ys"] = (w["La_l2"] * w["Y"]).astype(dt)          # the l22 gateway's pre-scaling (mex :54-60)
@@ -176,6 +192,51 @@ def grid_slab_simplex(n, K, dt, world, rank):
     return dict(plan=plan, V=V, E=E_global, Q=Q.astype(dt), La_d1=np.full(plan.Eu.shape[0], 0.2, dt))
 
 
+def torch_lambda_max(matvec, V, dev, tdt, iters=30):
+    """largest eigenvalue of A^tA by power iteration in torch (bench input preparation only)"""
+    import torch
+    x = torch.randn(V, device=dev, dtype=tdt, generator=torch.Generator(device=dev).manual_seed(11))
+    lam = 1.0
+    for _ in range(iters):
+        x = x / x.norm()
+        x = matvec(x)
+        lam = float(x.norm())
+    return lam * 1.01
+
+
+def device_inputs_dense(name, dev):
+    """C3 / C5-slice inputs generated on the device (the matrices are several GB)"""
+    import torch
+    from cp_pfdr_graph_d1_b200 import synth
+    kind, n, dt, K, iters = WORKLOADS[name]
+    tdt = torch.float32 if dt is np.float32 else torch.float64
+    g = torch.Generator(device=dev).manual_seed(5)
+    if kind == "ata":
+        V, m = n, 2048
+        pts, Eu, Ev = synth.knn_graph(V, 10, 4)
+        G = torch.randn((m, V), generator=g, device=dev, dtype=tdt)
+        AtA = (G.t() @ G) / m
+        AtA.diagonal().add_(0.1)
+        del G
+        x0 = torch.from_numpy(np.round(4 * pts[:, 0]) / 4).to(dev, tdt)
+        AtY = AtA @ x0 + 0.01 * torch.randn(V, generator=g, device=dev, dtype=tdt)
+        lam = torch_lambda_max(lambda x: AtA @ x, V, dev, tdt)
+        return dict(V=V, E=int(Eu.shape[0]), N=-V, A=AtA.contiguous(), Y=AtY, Eu=to_dev(Eu, dev), Ev=to_dev(Ev, dev),
+                    La_d1=torch.full((Eu.shape[0],), 0.02, device=dev, dtype=tdt), L=torch.tensor([lam], device=dev, dtype=tdt))
+    V, Eu, Ev = synth.grid_graph(n)
+    N = 256
+    At = (torch.rand((V, N), generator=g, device=dev, dtype=tdt) - 0.5) / 8       # (V, N) row-major == N-by-V column-major
+    v = torch.arange(V, device=dev)
+    z, y, x = v // (n * n), (v // n) % n, v % n
+    x0 = torch.zeros(V, device=dev, dtype=tdt)
+    x0[(z < n // 3) & (y < n // 2) & (x < n // 2)] = 2.0
+    x0[(z >= 2 * n // 3) & (y >= n // 2)] = 2.0
+    Y = At.t() @ x0
+    lam = torch_lambda_max(lambda t: At @ (At.t() @ t), V, dev, tdt, iters=15)
+    return dict(V=V, E=int(Eu.shape[0]), N=N, A=At, Y=Y, Eu=to_dev(Eu, dev), Ev=to_dev(Ev, dev),
+                La_d1=torch.full((Eu.shape[0],), 0.05, device=dev, dtype=tdt), L=torch.tensor([lam], device=dev, dtype=tdt))
+
+
 def to_dev(a, dev):
     import torch
     return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
@@ -186,6 +247,16 @@ def make_solver(name, w, dev, itMax):
     from cp_pfdr_graph_d1_b200 import api, DIAG
     kind, n, dt, K, iters = WORKLOADS[name]
     import torch
+    if kind in ("ata", "dense"):
+        d = dict(w)
+        d["X0"] = torch.zeros(w["V"], device=dev, dtype=w["Y"].dtype)
+        torch.cuda.synchronize()
+        if kind == "ata":
+            return api.QuadraticSolver(d["X0"], d["Y"], d["A"], d["Eu"], d["Ev"], d["La_d1"], min=0.0, max=1.0,
+                                       prox="bounds", Ltype=0, L=d["L"], rho=1.5, condMin=1e-3, difRcd=0.0, difTol=0.0,
+                                       itMax=itMax, N=w["N"]), d
+        return api.QuadraticSolver(d["X0"], d["Y"], d["A"], d["Eu"], d["Ev"], d["La_d1"], None, 0, Ltype=0, L=d["L"],
+                                   rho=1.0, condMin=1e-3, difRcd=0.0, difTol=0.0, itMax=itMax, N=w["N"]), d
     if kind == "quad":
         d = {k: to_dev(w[k], dev) for k in ("Ys", "La_l2", "Eu", "Ev", "La_d1")}
         d["X0"] = torch.zeros(w["V"], device=dev, dtype=d["Ys"].dtype)
@@ -319,9 +390,13 @@ def main():
     kind, n, dt, K, iters = WORKLOADS[name]
     iters = args.iters or iters
     r = np.dtype(dt).itemsize
-    w = host_inputs(name) or device_inputs_c4(n, K, dt, dev)
+    if kind in ("ata", "dense"):
+        w = device_inputs_dense(name, dev)
+        args.no_cpu = args.no_e2e = True                 # several-GB matrices: device-resident legs only
+    else:
+        w = host_inputs(name) or device_inputs_c4(n, K, dt, dev)
     V, E = int(w["V"]), int(w["E"])
-    B_iter = algorithmic_bytes(kind, V, E, r, K)
+    B_iter = algorithmic_bytes(kind, V, E, r, K, N=abs(int(w.get("N", 0))) if kind == "dense" else 0)
     solver, keep = make_solver(name, w, dev, iters)
     setup = dict(solver.setup_stats)
 
@@ -359,7 +434,8 @@ def main():
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": measured_traffic(name), "peak_source": peak_src,
-                     "kernel": "quad_iter_kernel" if kind == "quad" else "simplex_iter_kernel",
+                     "kernel": {"quad": "quad_iter_pipe_kernel", "simplex": "simplex_iter_kernel", "ata": "ata_gemv_kernel",
+                                "dense": "ax_partial_kernel + atr_kernel"}[kind],
                      "algorithmic_bytes_per_launch": B_iter,
                      "avg_launch_us": 1e3 * loop_ms / its},
         "setup_ms_device_resident": setup["setup_ms"],

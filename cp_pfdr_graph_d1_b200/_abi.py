@@ -42,6 +42,16 @@ def _real_dtype(a):
 
 
 def _as_real(a, dt):
+    """1-D arrays: contiguous; 2-D matrices: COLUMN-major (the reference's layout for A, A^tA; a (V, K) label
+    array is passed C-ordered on purpose and handled by the simplex binder itself)"""
+    if a is None or not isinstance(a, np.ndarray):
+        return a
+    if a.ndim == 2:
+        return np.asfortranarray(a, dtype=dt)
+    return np.ascontiguousarray(a, dtype=dt)
+
+
+def _as_rows(a, dt):
     if a is None or not isinstance(a, np.ndarray):
         return a
     return np.ascontiguousarray(a, dtype=dt)
@@ -123,7 +133,7 @@ class Binder:
         PR, PI = C.POINTER(R), C.POINTER(C.c_int)
         V, K = int(P.shape[0]), int(P.shape[1])
         E = int(Eu.shape[0])
-        Q, La_d1, La_f = (_as_real(a, dt) for a in (Q, La_d1, La_f))
+        Q, La_d1, La_f = (_as_rows(a, dt) for a in (Q, La_d1, La_f))
         Eu, Ev = _as_int(Eu), _as_int(Ev)
         it = C.c_int(0)
         Obj = np.zeros(itMax + 1, dt) if want_obj else None
@@ -144,8 +154,8 @@ class Binder:
         R, suf = _CT[dt]
         PR = C.POINTER(R)
         N, D = int(X.shape[0]), int(X.shape[1])
-        M = _as_real(M, dt)
-        A = np.ones(1, dt) if A is None else _as_real(np.atleast_1d(A), dt)
+        M = _as_rows(M, dt)
+        A = np.ones(1, dt) if A is None else _as_rows(np.atleast_1d(A), dt)
         f = self._fn("proj_simplex_metric", suf, [PR, PR, C.c_int, C.c_int, C.c_int, PR, C.c_int])
         self._check(f(_ptr(X, R), _ptr(M, R), D, N, int(M.shape[0]), _ptr(A, R), int(A.shape[0])))
         return X

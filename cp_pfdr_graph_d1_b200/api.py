@@ -85,7 +85,7 @@ def last_stats():
 # ---------------------------------------------------------------------------------------------------
 import ctypes as _C
 
-from ._abi import _CT, _as_int, _as_real, _ptr, _real_dtype
+from ._abi import _CT, _as_int, _as_real, _as_rows, _ptr, _real_dtype
 
 
 class _Solver:
@@ -169,7 +169,7 @@ class SimplexSolver(_Solver):
         P, PI = _C.POINTER(R), _C.POINTER(_C.c_int)
         V, K = int(P0.shape[0]), int(P0.shape[1])
         self._dt, self._shape, self._itMax = dt, (V, K), itMax
-        P0, Q, La_d1, La_f = (_as_real(a, dt) for a in (P0, Q, La_d1, La_f))
+        P0, Q, La_d1, La_f = (_as_rows(a, dt) for a in (P0, Q, La_d1, La_f))
         Eu, Ev = _as_int(Eu), _as_int(Ev)
         self._keep = [P0, Q, Eu, Ev, La_d1, La_f]
         f = getattr(self._lib, f"pfdr_b200_solver_create_simplex_{suf}")

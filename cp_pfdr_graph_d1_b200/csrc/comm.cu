@@ -168,52 +168,58 @@ void Halo<real>::setup(const ShardInfo &s, const int *d_hkey, long long nslots, 
     if (trh) PFDR_LAUNCH(map_keys_kernel, cdiv(trh, 256), 256, 0, d_rh.p, pos.p, trh, d_rs.p);
     sendbuf.alloc(std::max<size_t>((2 * tsv + tsh) * width, 1));
     recvbuf.alloc(std::max<size_t>((2 * trv + trh) * width, 1));
-    // segment tables
-    for (int layout = 0; layout < 2; layout++) {
-        std::vector<HaloSeg> ps, us;
-        soff[layout].assign(nnb, 0); roff[layout].assign(nnb, 0); scnt[layout].assign(nnb, 0); rcnt[layout].assign(nnb, 0);
-        long long pstart = 0, ustart = 0;
-        size_t so = 0, ro = 0;
-        for (int i = 0; i < nnb; i++) {
-            soff[layout][i] = so; roff[layout][i] = ro;
-            const int narr = layout == 0 ? 2 : 1;
-            for (int a = 0; a < narr; a++) {
-                if (nsv[i]) { ps.push_back({d_sv.p + sv_off[i], pstart, nsv[i], (long long) so, a}); pstart += nsv[i]; so += (size_t) nsv[i] * width; }
-                if (nrv[i]) { us.push_back({d_rv.p + rv_off[i], ustart, nrv[i], (long long) ro, a}); ustart += nrv[i]; ro += (size_t) nrv[i] * width; }
-            }
-            if (layout == 1) {
-                if (nsh[i]) { ps.push_back({d_ss.p + sh_off[i], pstart, nsh[i], (long long) so, 2}); pstart += nsh[i]; so += (size_t) nsh[i] * width; }
-                if (nrh[i]) { us.push_back({d_rs.p + rh_off[i], ustart, nrh[i], (long long) ro, 2}); ustart += nrh[i]; ro += (size_t) nrh[i] * width; }
-            }
-            scnt[layout][i] = so - soff[layout][i]; rcnt[layout][i] = ro - roff[layout][i];
-        }
-        nseg[layout] = (int) ps.size();
-        pack_items[layout] = pstart; unpack_items[layout] = ustart;
-        d_pack[layout].alloc(std::max<size_t>(ps.size(), 1)); d_unpack[layout].alloc(std::max<size_t>(us.size(), 1));
-        if (!ps.empty()) PFDR_CUDA(cudaMemcpyAsync(d_pack[layout].p, ps.data(), ps.size() * sizeof(HaloSeg), cudaMemcpyHostToDevice, st));
-        if (!us.empty()) PFDR_CUDA(cudaMemcpyAsync(d_unpack[layout].p, us.data(), us.size() * sizeof(HaloSeg), cudaMemcpyHostToDevice, st));
-        PFDR_CUDA(cudaStreamSynchronize(st));      // ps / us die at the end of this scope
-        nuseg[layout] = (int) us.size();
-    }
     PFDR_CUDA(cudaStreamSynchronize(st));
 }
 
 template <typename real>
-void Halo<real>::exchange(int layout, PingPong<real> va0, PingPong<real> va1, PingPong<real> Z, const Ctl *ctl, int parity)
+void Halo<real>::build(int mask)
+{
+    Layout &L = layouts[mask];
+    cudaStream_t st = ctx().stream;
+    std::vector<HaloSeg> ps, us;
+    L.soff.assign(nnb, 0); L.roff.assign(nnb, 0); L.scnt.assign(nnb, 0); L.rcnt.assign(nnb, 0);
+    long long pstart = 0, ustart = 0;
+    size_t so = 0, ro = 0;
+    for (int i = 0; i < nnb; i++) {
+        L.soff[i] = so; L.roff[i] = ro;
+        for (int a = 0; a < 2; a++) {
+            if (!(mask & (a == 0 ? HALO_VA0 : HALO_VA1))) continue;
+            if (nsv[i]) { ps.push_back({d_sv.p + sv_off[i], pstart, nsv[i], (long long) so, a}); pstart += nsv[i]; so += (size_t) nsv[i] * width; }
+            if (nrv[i]) { us.push_back({d_rv.p + rv_off[i], ustart, nrv[i], (long long) ro, a}); ustart += nrv[i]; ro += (size_t) nrv[i] * width; }
+        }
+        if (mask & HALO_Z) {
+            if (nsh[i]) { ps.push_back({d_ss.p + sh_off[i], pstart, nsh[i], (long long) so, 2}); pstart += nsh[i]; so += (size_t) nsh[i] * width; }
+            if (nrh[i]) { us.push_back({d_rs.p + rh_off[i], ustart, nrh[i], (long long) ro, 2}); ustart += nrh[i]; ro += (size_t) nrh[i] * width; }
+        }
+        L.scnt[i] = so - L.soff[i]; L.rcnt[i] = ro - L.roff[i];
+    }
+    L.npseg = (int) ps.size(); L.nuseg = (int) us.size();
+    L.pack_items = pstart; L.unpack_items = ustart;
+    L.d_pack.alloc(std::max<size_t>(ps.size(), 1)); L.d_unpack.alloc(std::max<size_t>(us.size(), 1));
+    if (!ps.empty()) PFDR_CUDA(cudaMemcpyAsync(L.d_pack.p, ps.data(), ps.size() * sizeof(HaloSeg), cudaMemcpyHostToDevice, st));
+    if (!us.empty()) PFDR_CUDA(cudaMemcpyAsync(L.d_unpack.p, us.data(), us.size() * sizeof(HaloSeg), cudaMemcpyHostToDevice, st));
+    PFDR_CUDA(cudaStreamSynchronize(st));      // ps / us die at the end of this scope
+    L.built = true;
+}
+
+template <typename real>
+void Halo<real>::exchange(int mask, PingPong<real> va0, PingPong<real> va1, PingPong<real> Z, const Ctl *ctl, int parity)
 {
     if (!nnb) return;
-    if (pack_items[layout])
-        PFDR_LAUNCH((halo_kernel<real, true>), cdiv((size_t) pack_items[layout] * width, 256), 256, 0, sendbuf.p, va0, va1, Z,
-                    ctl, parity, d_pack[layout].p, nseg[layout], pack_items[layout], width);
+    Layout &L = layouts[mask];
+    if (!L.built) throw Error(PFDR_B200_ERR_ARG, "halo layout used before build()");
+    if (L.pack_items)
+        PFDR_LAUNCH((halo_kernel<real, true>), cdiv((size_t) L.pack_items * width, 256), 256, 0, sendbuf.p, va0, va1, Z,
+                    ctl, parity, L.d_pack.p, L.npseg, L.pack_items, width);
     comm_group_start();
     for (int i = 0; i < nnb; i++) {
-        if (scnt[layout][i]) comm_send<real>(sendbuf.p + soff[layout][i], scnt[layout][i], rank[i]);
-        if (rcnt[layout][i]) comm_recv<real>(recvbuf.p + roff[layout][i], rcnt[layout][i], rank[i]);
+        if (L.scnt[i]) comm_send<real>(sendbuf.p + L.soff[i], L.scnt[i], rank[i]);
+        if (L.rcnt[i]) comm_recv<real>(recvbuf.p + L.roff[i], L.rcnt[i], rank[i]);
     }
     comm_group_end();
-    if (unpack_items[layout])
-        PFDR_LAUNCH((halo_kernel<real, false>), cdiv((size_t) unpack_items[layout] * width, 256), 256, 0, recvbuf.p, va0, va1, Z,
-                    ctl, parity, d_unpack[layout].p, nuseg[layout], unpack_items[layout], width);
+    if (L.unpack_items)
+        PFDR_LAUNCH((halo_kernel<real, false>), cdiv((size_t) L.unpack_items * width, 256), 256, 0, recvbuf.p, va0, va1, Z,
+                    ctl, parity, L.d_unpack.p, L.nuseg, L.unpack_items, width);
 }
 
 template struct Halo<float>;

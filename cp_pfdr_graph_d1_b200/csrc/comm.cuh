@@ -42,6 +42,8 @@ struct HaloSeg { const int *idx; long long start, n, off; int arr; };   // arr: 
 
 enum : int { PARITY_ZERO = 0, PARITY_CUR = 1, PARITY_NEXT_IF_RAN = 2 };
 
+enum : int { HALO_VA0 = 1, HALO_VA1 = 2, HALO_Z = 4 };     // what a message carries
+
 template <typename real>
 struct Halo {
     int nnb = 0, width = 1;
@@ -49,17 +51,20 @@ struct Halo {
     std::vector<size_t> sv_off, sh_off, rv_off, rh_off;
     DevBuf<int> d_sv, d_ss, d_rv, d_rs;           // send vertices / send slots / recv vertices / recv slots
     DevBuf<real> sendbuf, recvbuf;
-    // segment tables for the two message layouts: [0] = two vertex arrays (setup), [1] = one vertex array + Z (iteration)
-    DevBuf<HaloSeg> d_pack[2], d_unpack[2];
-    int nseg[2] = {0, 0}, nuseg[2] = {0, 0};
-    long long pack_items[2] = {0, 0}, unpack_items[2] = {0, 0};
-    std::vector<size_t> soff[2], roff[2], scnt[2], rcnt[2];
+    struct Layout {                                // segment tables of one message composition (built on first use)
+        bool built = false;
+        DevBuf<HaloSeg> d_pack, d_unpack;
+        int npseg = 0, nuseg = 0;
+        long long pack_items = 0, unpack_items = 0;
+        std::vector<size_t> soff, roff, scnt, rcnt;
+    } layouts[8];
 
     // hkey: [nslots] half-edge key of every slot (-1 padding); nkeys = 2 * local edges
     void setup(const ShardInfo &s, const int *d_hkey, long long nslots, size_t nkeys, int width_);
-    // layout 0: va0, va1 (no Z); layout 1: va0 + Z.  parity selects which of the ping/pong buffers is used,
-    // decided on the device from the control block (no host synchronisation)
-    void exchange(int layout, PingPong<real> va0, PingPong<real> va1, PingPong<real> Z, const Ctl *ctl, int parity);
+    void build(int mask);
+    // mask = HALO_VA0 | HALO_VA1 | HALO_Z: which of the arrays travel.  parity selects which of the ping/pong
+    // buffers is used, decided on the device from the control block (no host synchronisation)
+    void exchange(int mask, PingPong<real> va0, PingPong<real> va1, PingPong<real> Z, const Ctl *ctl, int parity);
 };
 
 }  // namespace pfdr

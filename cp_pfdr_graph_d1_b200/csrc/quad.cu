@@ -30,6 +30,7 @@ struct QP {                       // kernel parameter block
     int V, N, E;
     int Vown, sharded;            // vertices this rank owns (== V unless sharded: ghosts follow)
     double *sums;                 // [2] reduction scratch of the sharded path (all-reduced between kernels)
+    double *rsum;                 // [N] sum of A x over this rank's columns (sharded dense A)
     const long long *slice_off; const int *nbr, *twin, *hkey;
     real *w;                      // [slots] raw d1 weight of the half-edge's edge
     real *thc;                    // [slots] La_d1/w after a reconditioning (NULL: thc0 for all)
@@ -667,7 +668,7 @@ __global__ void __launch_bounds__(256) ax_partial_kernel(QP<real> p, int TX, dou
     if (cv.hold) return;
     const int N = p.N, TY = blockDim.x / TX;
     const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
-    const size_t V = (size_t) p.V;
+    const size_t V = (size_t) p.Vown;
     const size_t v0 = V * blockIdx.x / gridDim.x, v1 = V * (blockIdx.x + 1) / gridDim.x;
     const real *__restrict__ X = (cv.it & 1) ? p.X1 : p.X0;
     const int nvec = (N + VEC - 1) / VEC;
@@ -728,7 +729,15 @@ __global__ void ax_finish_kernel(QP<real> p, const double *__restrict__ parts)
     if (n >= p.N) return;
     double a = 0;
     for (int b = 0; b < p.nparts; b++) a += parts[(size_t) b * p.N + n];
-    p.R[n] = p.Y[n] - (real) a;
+    if (p.sharded) p.rsum[n] = a;                 // all-reduced over the ranks, then ax_apply_kernel
+    else p.R[n] = p.Y[n] - (real) a;
+}
+
+template <typename real>
+__global__ void ax_apply_kernel(QP<real> p)
+{
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n < p.N) p.R[n] = p.Y[n] - (real) p.rsum[n];
 }
 
 // N>0, pass 2 (mode 0):  G = -A^t R, P = 2X - Ga.G  (ref :432-440, :463-464); GL lanes per column.
@@ -741,8 +750,8 @@ __global__ void __launch_bounds__(256) atr_kernel(QP<real> p, int GL, int mode)
     const int N = p.N;
     const size_t gid = ((size_t) blockIdx.x * blockDim.x + threadIdx.x) / GL;
     const int gl = threadIdx.x % GL;
-    const bool live = gid < (size_t) p.V;
-    const size_t v = live ? gid : (size_t) p.V - 1;
+    const bool live = gid < (size_t) p.Vown;
+    const size_t v = live ? gid : (size_t) p.Vown - 1;
     const real *__restrict__ col = p.A + (size_t) N * v;
     const real *__restrict__ rhs = mode ? p.Y : p.R;
     const int nvec = (N + VEC - 1) / VEC;
@@ -781,7 +790,7 @@ struct QuadSolver : SolverBase {
     DevIn<real> Y, A, La_d1, La_l1, L, X0;
     DevIn<int> Eu, Ev;
     DevBuf<real> w, thc, Z0, Z1, X0b, X1b, P0b, P1b, T, Sinv, Ga, Ga0, G, Thl1, R, AtY, dObj, dDif, Xout;
-    DevBuf<double> partial, parts, sums;
+    DevBuf<double> partial, parts, sums, rsum;
     Halo<real> halo;
     bool sharded = false;
     int ogrid = 0;                  // CTAs covering the owned vertices
@@ -808,7 +817,7 @@ struct QuadSolver : SolverBase {
         PFDR_REQUIRE(N == 0 || q.A != nullptr, "A must not be NULL when N != 0");
         sharded = q.shard != nullptr;
         if (sharded) {
-            PFDR_REQUIRE(N == 0, "sharded solves support N == 0 (diagonal / identity A) in this build");
+            PFDR_REQUIRE(N >= 0, "sharded solves support N >= 0 (A diagonal, identity or dense N-by-Vown) in this build");
             PFDR_REQUIRE(q.Obj == nullptr && q.difRcd == (real) 0, "sharded solves do not record Obj nor recondition in this build");
             PFDR_REQUIRE(q.shard->Vown > 0 && q.shard->Vown <= V, "bad shard: Vown");
         }
@@ -818,7 +827,9 @@ struct QuadSolver : SolverBase {
         PFDR_CUDA(cudaMallocHost((void **) &hctl, 2 * sizeof(Ctl)));
 
         const size_t ylen = (N > 0) ? (size_t) N : (size_t) V;
-        const size_t alen = (N > 0) ? (size_t) N * V : (N < 0 ? (size_t) V * V : (size_t) V);
+        // sharded dense A holds the OWNED columns only (ghost columns are never applied on this rank)
+        const size_t acols = (sharded && N > 0) ? (size_t) q.shard->Vown : (size_t) V;
+        const size_t alen = (N > 0) ? (size_t) N * acols : (N < 0 ? (size_t) V * V : (size_t) V);
         Eu.bind(q.Eu, E); Ev.bind(q.Ev, E);
         Y.bind(q.Y, ylen); A.bind(q.A, q.A ? alen : 0);
         La_d1.bind(q.La_d1, E); La_l1.bind(q.prox_kind == 0 ? q.La_l1 : nullptr, V);
@@ -832,7 +843,7 @@ struct QuadSolver : SolverBase {
         X0b.alloc(V); X1b.alloc(V); P0b.alloc(V); P1b.alloc(V); T.alloc(V); Sinv.alloc(V); Ga.alloc(V); Ga0.alloc(V);
         if (La_l1.p) Thl1.alloc(V);
         if (N != 0) G.alloc(V);
-        if (N > 0) { R.alloc(N); AtY.alloc(V); }
+        if (N > 0) { R.alloc(N); AtY.alloc(V); rsum.alloc(N); p.rsum = rsum.p; }
         if (q.Obj) dObj.alloc((size_t) q.itMax + 1);
         if (q.Dif) dDif.alloc((size_t) std::max(q.itMax, 1));
         vgrid = (int) cdiv(V, 256);
@@ -862,7 +873,7 @@ struct QuadSolver : SolverBase {
             const int nvec = (N + vec - 1) / vec;
             TX = 1; while (TX < nvec && TX < 256) TX <<= 1;
             GL = 1; while (GL < nvec && GL < 32) GL <<= 1;
-            p.nparts = std::max(1, std::min(num_sms() * 4, (V + 63) / 64));
+            p.nparts = std::max(1, std::min(num_sms() * 4, ((sharded ? q.shard->Vown : V) + 63) / 64));
             parts.alloc((size_t) p.nparts * N);
             ax_smem = (256 / TX > 1) ? (size_t) 256 * vec * sizeof(double) : 0;
         } else if (N < 0) {
@@ -872,7 +883,10 @@ struct QuadSolver : SolverBase {
         partial.alloc((size_t) maxgrid * 4);
         p.partial = partial.p;
 
-        if (sharded) halo.setup(*q.shard, g.hkey.p, g.nslots, 2 * (size_t) E, 1);
+        if (sharded) {
+            halo.setup(*q.shard, g.hkey.p, g.nslots, 2 * (size_t) E, 1);
+            halo.build(HALO_VA0 | HALO_VA1); halo.build(HALO_VA0 | HALO_Z); halo.build(HALO_VA0); halo.build(HALO_Z);
+        }
         reset();
         if (!keep_x0) X0.own.release();
         PFDR_CUDA(cudaEventRecord(ev_b, st));
@@ -901,7 +915,7 @@ struct QuadSolver : SolverBase {
         if (sharded) { comm_allreduce_sum(sums.p, 2); PFDR_LAUNCH(amp_finish_kernel<real>, 1, 1, 0, p, 0); }
         PFDR_LAUNCH(init_vertex_kernel<real>, vgrid, 256, 0, p, X0.p);
         // ghosts: the metric constants and forward point come from their owners
-        if (sharded) halo.exchange(0, PingPong<real>(T.p), PingPong<real>(P0b.p), PingPong<real>(), nullptr, PARITY_ZERO);
+        if (sharded) halo.exchange(HALO_VA0 | HALO_VA1, PingPong<real>(T.p), PingPong<real>(P0b.p), PingPong<real>(), nullptr, PARITY_ZERO);
         PFDR_CUDA(cudaMemcpyAsync(&hctl[1], ctl.p, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
         PFDR_CUDA(cudaStreamSynchronize(st));
         const real thc0 = (real) 1 / (real) hctl[1].amp;       // La_d1 / (c La_d1)
@@ -911,7 +925,7 @@ struct QuadSolver : SolverBase {
 
     void launch_atr(int mode)
     {
-        const size_t threads = (size_t) q.V * GL;
+        const size_t threads = (size_t) p.Vown * GL;
         if (vec > 1) PFDR_LAUNCH((atr_kernel<real, (sizeof(real) == 4 ? 4 : 2)>), cdiv(threads, 256), 256, 0, p, GL, mode);
         else PFDR_LAUNCH((atr_kernel<real, 1>), cdiv(threads, 256), 256, 0, p, GL, mode);
     }
@@ -923,7 +937,13 @@ struct QuadSolver : SolverBase {
             if (vec > 1) PFDR_LAUNCH((ax_partial_kernel<real, VM>), p.nparts, 256, ax_smem, p, TX, parts.p);
             else PFDR_LAUNCH((ax_partial_kernel<real, 1>), p.nparts, 256, ax_smem, p, TX, parts.p);
             PFDR_LAUNCH(ax_finish_kernel<real>, cdiv(q.N, 128), 128, 0, p, parts.p);
+            if (sharded) {
+                comm_allreduce_sum(rsum.p, q.N);
+                PFDR_LAUNCH(ax_apply_kernel<real>, cdiv(q.N, 128), 128, 0, p);
+            }
             launch_atr(0);
+            // the forward point of this iterate exists only now: ghosts get it before the edge prox
+            if (sharded) halo.exchange(HALO_VA0, PingPong<real>(P0b.p, P1b.p), PingPong<real>(), PingPong<real>(), ctl.p, PARITY_CUR);
         } else if (q.N < 0) {
             const int grid = std::min((q.V + 3) / 4, num_sms() * 4);
             if (vec > 1) PFDR_LAUNCH((ata_gemv_kernel<real, VM, 4>), grid, 256, 0, p);
@@ -936,7 +956,8 @@ struct QuadSolver : SolverBase {
         launch_iter();
         if (sharded) {     // new boundary forward points and cut-edge copies to the neighbours (taken from the buffers the
                            // iteration kernel just wrote), evolution sums over all ranks, then the iteration is closed
-            halo.exchange(1, PingPong<real>(P0b.p, P1b.p), PingPong<real>(), PingPong<real>(Z0.p, Z1.p), ctl.p, PARITY_NEXT_IF_RAN);
+            halo.exchange(q.N == 0 ? (HALO_VA0 | HALO_Z) : HALO_Z, PingPong<real>(P0b.p, P1b.p), PingPong<real>(),
+                          PingPong<real>(Z0.p, Z1.p), ctl.p, PARITY_NEXT_IF_RAN);
             comm_allreduce_sum(sums.p, 2);
             PFDR_LAUNCH(quad_finalize_kernel<real>, 1, 1, 0, p);
         }
@@ -986,7 +1007,7 @@ struct QuadSolver : SolverBase {
 #undef PFDR_ROWS
     }
 
-    int launches_per_trip() const { return (q.N > 0 ? 3 : (q.N < 0 ? 1 : 0)) + (q.Obj ? 1 : 0) + 1 + (sharded ? 5 : 0); }
+    int launches_per_trip() const { return (q.N > 0 ? 3 : (q.N < 0 ? 1 : 0)) + (q.Obj ? 1 : 0) + 1 + (sharded ? (q.N > 0 ? 10 : 5) : 0); }
 
     // enqueue `trips` iterations; replays a captured CUDA graph when a whole batch is requested
     void enqueue_batch(int trips, int batch)

@@ -621,7 +621,7 @@ struct SimplexSolver : SolverBase {
         p.partial = partial.p; p.dObj = dObj.p; p.dDif = dDif.p;
         { const char *e = getenv("PFDR_B200_STREAMZ"); p.stream_z = (e && e[0] == '1') ? 1 : 0; }
 
-        if (sharded) halo.setup(*q.shard, g.hkey.p, g.nslots, 2 * (size_t) E, K);
+        if (sharded) { halo.setup(*q.shard, g.hkey.p, g.nslots, 2 * (size_t) E, K); halo.build(HALO_VA0 | HALO_VA1); halo.build(HALO_VA0 | HALO_Z); }
         reset();
         if (!keep_p0) P0.own.release();
         PFDR_CUDA(cudaEventRecord(ev_b, st));
@@ -647,7 +647,7 @@ struct SimplexSolver : SolverBase {
         hctl[0] = h;
         PFDR_CUDA(cudaMemcpyAsync(ctl.p, &hctl[0], sizeof(Ctl), cudaMemcpyHostToDevice, st));
         launch_precond(P0.p, 0);
-        if (sharded) halo.exchange(0, PingPong<real>(T.p), PingPong<real>(Fa.p), PingPong<real>(), nullptr, PARITY_ZERO);
+        if (sharded) halo.exchange(HALO_VA0 | HALO_VA1, PingPong<real>(T.p), PingPong<real>(Fa.p), PingPong<real>(), nullptr, PARITY_ZERO);
         PFDR_CUDA(cudaStreamSynchronize(st));
     }
 
@@ -683,7 +683,7 @@ struct SimplexSolver : SolverBase {
         if (LPT == 4) { if (p.wk) launch_iter_loss<4, true>(); else launch_iter_loss<4, false>(); }
         else { if (p.wk) launch_iter_loss<1, true>(); else launch_iter_loss<1, false>(); }
         if (sharded) {     // evolution sum over all ranks, then the new boundary forward points and cut-edge copies
-            halo.exchange(1, PingPong<real>(Fa.p, Fb.p), PingPong<real>(), PingPong<real>(Z0.p, Z1.p), ctl.p, PARITY_NEXT_IF_RAN);
+            halo.exchange(HALO_VA0 | HALO_Z, PingPong<real>(Fa.p, Fb.p), PingPong<real>(), PingPong<real>(Z0.p, Z1.p), ctl.p, PARITY_NEXT_IF_RAN);
             comm_allreduce_sum(sums.p, 1);
             PFDR_LAUNCH(simplex_finalize_kernel<real>, 1, 1, 0, p);
         }

@@ -63,31 +63,45 @@ def _shard_struct(plan, keep):
 
 
 class ShardedQuadraticSolver(_Solver):
-    """PFDR_graph_quadratic_d1_{l1,bounds} with N == 0 on this rank's shard.  Arrays are the GLOBAL host arrays;
-    the plan slices them (pass `local=True` when they are already local)."""
+    """PFDR_graph_quadratic_d1_{l1,bounds} on this rank's shard: A is None / 1-D (N = 0) or a dense 2-D
+    N-by-V matrix (N > 0, this rank keeps its owned columns; Y then has length N and is not sliced).  Arrays are the
+    GLOBAL host arrays and the plan slices them; pass `local=True` when they are already local (dense A: owned
+    columns only; arrays may then also be torch CUDA tensors)."""
 
     def __init__(self, plan, X0, Y, A, La_d1, La_l1=None, positivity=0, min=-np.inf, max=np.inf, prox="l1", Ltype=0,
-                 L=None, rho=1.5, condMin=1e-3, difTol=1e-5, itMax=1000, want_dif=False, local=False):
+                 L=None, rho=1.5, condMin=1e-3, difTol=1e-5, itMax=1000, want_dif=False, local=False, N=None):
         super().__init__()
-        dt = np.dtype(X0.dtype)
+        from ._abi import _real_dtype, _ptr
+        dt = _real_dtype(X0)
         R, suf = _CT[dt]
         P, PI = C.POINTER(R), C.POINTER(C.c_int)
-        va = (lambda a: a) if local else plan.vertex_array
-        ea = (lambda a: a) if local else plan.edge_array
-        X0l, Yl, Al, La_l1l = (None if a is None else np.ascontiguousarray(va(a), dtype=dt) for a in (X0, Y, A, La_l1))
-        Ll = None if L is None else (np.ascontiguousarray(L, dtype=dt) if Ltype == 0 else np.ascontiguousarray(va(L), dtype=dt))
-        La_d1l = np.ascontiguousarray(ea(La_d1), dtype=dt)
+        dense = A is not None and len(A.shape) == 2
+        if N is None:
+            N = int(A.shape[0]) if dense else 0
+        if local:
+            X0l, Yl, Al, La_l1l, Ll, La_d1l = X0, Y, A, La_l1, L, La_d1
+        else:
+            va, ea = plan.vertex_array, plan.edge_array
+            X0l, La_l1l = (None if a is None else np.ascontiguousarray(va(a), dtype=dt) for a in (X0, La_l1))
+            if dense:
+                Yl = np.ascontiguousarray(Y, dtype=dt)
+                Al = np.asfortranarray(np.asarray(A)[:, plan.v0:plan.v1], dtype=dt)
+            else:
+                Yl = np.ascontiguousarray(va(Y), dtype=dt)
+                Al = None if A is None else np.ascontiguousarray(va(A), dtype=dt)
+            Ll = None if L is None else (np.ascontiguousarray(L, dtype=dt) if Ltype == 0 else np.ascontiguousarray(va(L), dtype=dt))
+            La_d1l = np.ascontiguousarray(ea(La_d1), dtype=dt)
         Eu, Ev = np.ascontiguousarray(plan.Eu, np.int32), np.ascontiguousarray(plan.Ev, np.int32)
         self._keep = [X0l, Yl, Al, La_l1l, Ll, La_d1l, Eu, Ev]
         self._dt, self._shape, self._itMax, self.plan = dt, (plan.Vown,), itMax, plan
         sh = _shard_struct(plan, self._keep)
-        ptr = lambda a, t=R: None if a is None else a.ctypes.data_as(C.POINTER(t))
         f = getattr(self._lib, f"pfdr_b200_solver_create_quadratic_sharded_{suf}")
         f.argtypes = [C.POINTER(C.c_void_p), C.POINTER(_Shard), C.c_int, C.c_int, C.c_int, C.c_int, P, P, P, PI, PI, P, P,
                       C.c_int, R, R, C.c_int, P, R, R, R, R, C.c_int, C.c_int, C.c_int]
-        self._chk(f(C.byref(self._h), C.byref(sh), 0 if prox == "l1" else 1, plan.Vloc, int(Eu.shape[0]), 0, ptr(X0l),
-                    ptr(Yl), ptr(Al), ptr(Eu, C.c_int), ptr(Ev, C.c_int), ptr(La_d1l), ptr(La_l1l), int(positivity),
-                    float(min), float(max), int(Ltype), ptr(Ll), rho, condMin, 0.0, difTol, itMax, 0, int(want_dif)))
+        self._chk(f(C.byref(self._h), C.byref(sh), 0 if prox == "l1" else 1, plan.Vloc, int(Eu.shape[0]), int(N),
+                    _ptr(X0l, R), _ptr(Yl, R), _ptr(Al, R), _ptr(Eu, C.c_int), _ptr(Ev, C.c_int), _ptr(La_d1l, R),
+                    _ptr(La_l1l, R), int(positivity), float(min), float(max), int(Ltype), _ptr(Ll, R), rho, condMin, 0.0,
+                    difTol, itMax, 0, int(want_dif)))
         self.setup_stats = last_stats()
 
 
