@@ -46,6 +46,9 @@ WORKLOADS = {
     # and a single-GPU slice of C5 (dense N = 256 lead field on a 160^3 grid: A is 4.2 GB)
     "c3_f32": ("ata", 32768, np.float32, 1, 50),
     "c5s_f32": ("dense", 160, np.float32, 1, 50),
+    # C5 at full size (sharded runs only: the 256 x 128M matrix is 131 GB) and a mid-size version for 2-GPU boxes
+    "c5_f32": ("dense", 504, np.float32, 1, 20),
+    "c5m_f32": ("dense", 252, np.float32, 1, 20),
 }
 
 
@@ -58,7 +61,8 @@ def describe(name):
         return (f"C3 PFDR_graph_quadratic_d1_bounds, dense precomputed AtA V={n}, box [0,1], 10-NN graph, "
                 f"{np.dtype(dt).name}, SCAL L, rho=1.5, difTol=0, itMax={iters}")
     if kind == "dense":
-        return (f"C5 slice PFDR_graph_quadratic_d1_l1, dense A N=256 on a 3D grid {n}^3, {np.dtype(dt).name}, SCAL L, "
+        which = "C5" if n == 504 else "C5 (reduced grid)"
+        return (f"{which} PFDR_graph_quadratic_d1_l1, dense A N=256 on a 3D grid {n}^3, {np.dtype(dt).name}, SCAL L, "
                 f"rho=1, difTol=0, itMax={iters}")
     return (f"C4 PFDR_graph_loss_d1_simplex smoothed-KL (al=0.05), K={K}, 3D grid {n}^3, {np.dtype(dt).name}, "
             f"rho=1.5, condMin=1e-2, difTol=0, itMax={iters}")
@@ -235,6 +239,48 @@ def device_inputs_dense(name, dev):
     lam = torch_lambda_max(lambda t: At @ (At.t() @ t), V, dev, tdt, iters=15)
     return dict(V=V, E=int(Eu.shape[0]), N=N, A=At, Y=Y, Eu=to_dev(Eu, dev), Ev=to_dev(Ev, dev),
                 La_d1=torch.full((Eu.shape[0],), 0.05, device=dev, dtype=tdt), L=torch.tensor([lam], device=dev, dtype=tdt))
+
+
+def grid_slab_plan(n, world, rank):
+    """shard plan of the n^3 grid for this rank, built from the edges touching its z-slab only"""
+    from cp_pfdr_graph_d1_b200 import shard
+    V = n ** 3
+    b = shard.slab_bounds(V, world)
+    v0, v1 = int(b[rank]), int(b[rank + 1])
+    lo, hi = max(v0 - n * n, 0), min(v1 + n * n, V)
+    g = np.arange(lo, hi, dtype=np.int64)
+    z, y, x = g // (n * n), (g // n) % n, g % n
+    eu, ev = [], []
+    for ok, d in ((x < n - 1, 1), (y < n - 1, n), (z < n - 1, n * n)):
+        eu.append(np.where(ok, g, -1)); ev.append(np.where(ok, g + d, -1))
+    Eu, Ev = np.stack(eu, 1).reshape(-1), np.stack(ev, 1).reshape(-1)
+    keep = (Eu >= 0) & (Ev < hi) & (((Eu >= v0) & (Eu < v1)) | ((Ev >= v0) & (Ev < v1)))
+    return shard.make_plan_local(V, Eu[keep], Ev[keep], world, rank, b)
+
+
+def device_slab_dense(n, N, dt, world, rank, dev):
+    """this rank's part of C5: owned columns of the hashed lead field (generated on the device), Y = A x0 summed
+    over the ranks, SCAL L from the Marchenko-Pastur edge of a matrix with iid U(-1/16, 1/16) entries"""
+    import torch
+    import torch.distributed as dist
+    tdt = torch.float32 if dt is np.float32 else torch.float64
+    plan = grid_slab_plan(n, world, rank)
+    V, Vown = n ** 3, plan.Vown
+    g = torch.Generator(device=dev).manual_seed(1000 + rank)
+    At = (torch.rand((Vown, N), generator=g, device=dev, dtype=tdt) - 0.5) / 8     # (Vown, N) row-major == N x Vown col-major
+    v = torch.arange(plan.v0, plan.v1, device=dev)
+    z, y, x = v // (n * n), (v // n) % n, v % n
+    x0 = torch.zeros(Vown, device=dev, dtype=tdt)
+    x0[(z < n // 3) & (y < n // 2) & (x < n // 2)] = 2.0
+    x0[(z >= 2 * n // 3) & (y >= n // 2)] = 2.0
+    Y = (At.t() @ x0).contiguous()
+    if world > 1:
+        dist.all_reduce(Y)
+    lam = 1.05 * (V ** 0.5 + N ** 0.5) ** 2 / 768.0
+    E = 3 * n * n * (n - 1)
+    return dict(plan=plan, V=V, E=E, N=N, A=At, Y=Y, X0=torch.zeros(plan.Vloc, device=dev, dtype=tdt),
+                La_d1=torch.full((plan.Eu.shape[0],), 0.05, device=dev, dtype=tdt),
+                L=torch.tensor([lam], device=dev, dtype=tdt))
 
 
 def to_dev(a, dev):

@@ -27,7 +27,16 @@ def main(args):
     kind, n, dt, K, iters = B.WORKLOADS[name]
     iters = args.iters or iters
     r = np.dtype(dt).itemsize
-    if n > 128 and kind == "simplex":
+    Ndense = 0
+    if kind == "dense":
+        w = B.device_slab_dense(n, 256, dt, world, rank, torch.device("cuda", local))
+        plan, V, E, Ndense = w["plan"], w["V"], w["E"], w["N"]
+        torch.cuda.synchronize()
+        solver = pd.ShardedQuadraticSolver(plan, w["X0"], w["Y"], w["A"], w["La_d1"], None, 0, Ltype=0, L=w["L"], rho=1.0,
+                                           condMin=1e-3, difTol=0.0, itMax=iters, local=True, N=Ndense)
+    elif kind == "ata":
+        raise SystemExit("AtA problems do not shard (DESIGN.md section 6): run this workload with --gpus 1")
+    elif n > 128 and kind == "simplex":
         w = B.grid_slab_simplex(n, K, dt, world, rank)            # slab generated directly (no global arrays)
         plan, V, E = w["plan"], w["V"], w["E"]
         solver = pd.ShardedSimplexSolver(plan, w["Q"], w["Q"], 0.05, w["La_d1"], rho=1.5, condMin=1e-2, difTol=0.0,
@@ -42,7 +51,7 @@ def main(args):
         else:
             solver = pd.ShardedSimplexSolver(plan, w["Q"], w["Q"], 0.05, w["La_d1"], rho=1.5, condMin=1e-2, difTol=0.0,
                                              itMax=iters)
-    B_iter = B.algorithmic_bytes(kind, V, E, r, K)
+    B_iter = B.algorithmic_bytes(kind, V, E, r, K, N=Ndense)
 
     def step():
         solver.reset()
@@ -85,7 +94,8 @@ def main(args):
             "gpu_launches": int(t[2]),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak * world, "unit": "GB/s",
                          "frac": achieved / (peak * world), "traffic": None, "peak_source": peak_src + f" x {world} GPUs",
-                         "kernel": "quad_iter_kernel" if kind == "quad" else "simplex_iter_kernel",
+                         "kernel": {"quad": "quad_iter_pipe_kernel", "simplex": "simplex_iter_kernel",
+                                    "dense": "ax_partial_kernel + atr_kernel"}[kind],
                          "algorithmic_bytes_per_launch": B_iter / world, "avg_launch_us": 1e3 * loop_ms_max / its},
             "e2e": None, "clocks": clk.summary(),
         }
