@@ -57,23 +57,59 @@ Context &ctx();
 // ---------------------------------------------------------------------------------------------
 // device memory
 // ---------------------------------------------------------------------------------------------
+// Device memory comes from the stream-ordered allocator (cudaMallocAsync on the launch stream) with the pool's
+// release threshold lifted, so the ~25 arrays of a solve cost microseconds after the first call instead of a
+// cudaMalloc/cudaFree pair each (tens of milliseconds per solve: most of the one-shot entry points' overhead,
+// and they are called once per cut-pursuit iteration by the reference's outer loop).  PFDR_B200_POOL=0 reverts.
+inline bool use_pool()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("PFDR_B200_POOL");
+        v = (e && e[0] == '0') ? 0 : 1;
+        if (v) {
+            int dev = 0, ok = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&ok, cudaDevAttrMemoryPoolsSupported, dev);
+            cudaMemPool_t pool;
+            if (ok && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+                unsigned long long thr = ~0ull;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+            } else v = 0;
+            cudaGetLastError();
+        }
+    }
+    return v != 0;
+}
+
 template <typename T>
 struct DevBuf {
     T *p = nullptr;
     size_t n = 0;
+    bool pooled = false;
     DevBuf() {}
     explicit DevBuf(size_t count) { alloc(count); }
     DevBuf(const DevBuf &) = delete;
     DevBuf &operator=(const DevBuf &) = delete;
-    DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
-    DevBuf &operator=(DevBuf &&o) noexcept { if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; } return *this; }
+    DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n), pooled(o.pooled) { o.p = nullptr; o.n = 0; }
+    DevBuf &operator=(DevBuf &&o) noexcept
+    {
+        if (this != &o) { release(); p = o.p; n = o.n; pooled = o.pooled; o.p = nullptr; o.n = 0; }
+        return *this;
+    }
     ~DevBuf() { release(); }
     void alloc(size_t count) {
         release();
         n = count;
-        if (count) PFDR_CUDA(cudaMalloc((void **) &p, count * sizeof(T)));
+        if (!count) return;
+        pooled = use_pool();
+        if (pooled) PFDR_CUDA(cudaMallocAsync((void **) &p, count * sizeof(T), ctx().stream));
+        else PFDR_CUDA(cudaMalloc((void **) &p, count * sizeof(T)));
     }
-    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void release() {
+        if (p) { if (pooled) cudaFreeAsync(p, ctx().stream); else cudaFree(p); }
+        p = nullptr; n = 0;
+    }
     void zero() { if (p) PFDR_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), ctx().stream)); }
     operator T *() const { return p; }
 };

@@ -59,7 +59,49 @@ __global__ void link_kernel(const int *__restrict__ Eu, const int *__restrict__ 
     twin[slot] = pos[i ^ 1];
 }
 
+__global__ void max_offset_kernel(const int *__restrict__ Eu, const int *__restrict__ Ev, int E, int *__restrict__ out)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    int d = 0;
+    if (e < E) d = abs(Eu[e] - Ev[e]);
+    for (int o = 16; o > 0; o >>= 1) d = max(d, __shfl_xor_sync(0xffffffffu, d, o));
+    if ((threadIdx.x & 31) == 0 && d > 0) atomicMax(out, d);
+}
+__global__ void count_offset_kernel(const int *__restrict__ Eu, const int *__restrict__ Ev, int E, const int *__restrict__ band,
+                                    int *__restrict__ count)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool hit = e < E && abs(Eu[e] - Ev[e]) == *band;
+    const unsigned m = __ballot_sync(0xffffffffu, hit);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(count, __popc(m));
+}
+__global__ void slice_key_kernel(int nslices, int C, int band, int T, unsigned long long *__restrict__ key, int *__restrict__ val)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nslices) return;
+    const long long v = (long long) s * C;
+    const long long z = v / band, r = v % band;
+    const long long ntile_z = ((long long) nslices * C + band - 1) / band + 1;
+    key[s] = (unsigned long long) (((r / T) * ntile_z + z) * T + (r % T));
+    val[s] = s;
+}
+
 }  // namespace
+
+void build_slice_order(const SellGraph &g, int nslices, int T, DevBuf<int> &order)
+{
+    cudaStream_t st = ctx().stream;
+    DevBuf<unsigned long long> key(nslices), skey(nslices);
+    DevBuf<int> val(nslices);
+    order.alloc(nslices);
+    PFDR_LAUNCH(slice_key_kernel, cdiv(nslices, 256), 256, 0, nslices, g.C, g.band, T, key.p, val.p);
+    size_t tb = 0;
+    PFDR_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, key.p, skey.p, val.p, order.p, nslices, 0, 64, st));
+    DevBuf<unsigned char> tmp(tb + 16);
+    PFDR_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, key.p, skey.p, val.p, order.p, nslices, 0, 64, st));
+    ctx().stats.launches += 1;
+    PFDR_CUDA(cudaStreamSynchronize(st));
+}
 
 void build_sell(SellGraph &g, const int *dEu, const int *dEv, int V, int E, int C)
 {
@@ -104,11 +146,21 @@ void build_sell(SellGraph &g, const int *dEu, const int *dEv, int V, int E, int 
     PFDR_CUDA(cub::DeviceReduce::Max(tmpm.p, tmp4, g.deg.p, dmax.p, V, st));
     ctx().stats.launches += 1;
     PFDR_CUDA(cudaMemcpyAsync(&g.max_width, dmax.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    // band detection (see build_slice_order)
+    DevBuf<int> dband(2);
+    dband.zero();
+    if (E > 0) {
+        PFDR_LAUNCH(max_offset_kernel, cdiv(E, 256), 256, 0, dEu, dEv, E, dband.p);
+        PFDR_LAUNCH(count_offset_kernel, cdiv(E, 256), 256, 0, dEu, dEv, E, dband.p, dband.p + 1);
+    }
+    int hband[2] = {0, 0};
+    PFDR_CUDA(cudaMemcpyAsync(hband, dband.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
     long long nslots = 0; int hbad = 0;
     PFDR_CUDA(cudaMemcpyAsync(&nslots, g.slice_off.p + g.nslices, sizeof(long long), cudaMemcpyDeviceToHost, st));
     PFDR_CUDA(cudaMemcpyAsync(&hbad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     PFDR_CUDA(cudaStreamSynchronize(st));
     PFDR_REQUIRE(!hbad, "edge list refers to a vertex outside [0, V)");
+    g.band = (hband[0] > 0 && (long long) hband[1] * 5 >= (long long) E) ? hband[0] : 0;
     PFDR_REQUIRE(nslots < 2147483647LL, "half-edge table exceeds 2^31 slots (very irregular degrees?)");
     g.nslots = nslots;
     ctx().stats.slots = nslots;

@@ -33,6 +33,7 @@ struct SP {
     double *sums;                 // [1] reduction scratch of the sharded path
     real aK, a1, aK1, rho, condMin;
     const long long *slice_off; const int *nbr, *twin, *hkey;
+    const int *order;             // [owned slices] processing order for banded graphs (graph.cuh), NULL = natural
     real *w;                      // [slots]   raw weight before any reconditioning (= La_d1[e] for every label)
     real *wk, *thk;               // [slots*K] raw weight / La_d1 over it, per label, after a reconditioning
     real *Z0, *Z1;                // [slots*K] edge copies, ping/pong
@@ -437,11 +438,12 @@ __global__ void __launch_bounds__(256, MINB) simplex_iter_kernel(SP<real> p)
     const int *__restrict__ nbr = p.nbr;
     const int *__restrict__ twin = p.twin;
     const int K = p.K, TPV = p.TPV, C = p.C, lane = threadIdx.x & 31;
-    const long long slice = ((long long) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long wslot = ((long long) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nslices = ((long long) p.Vown + C - 1) >> p.logC;
     const real rho = p.rho;
     double red[1] = {0.0};
-    if (slice < nslices) {                                                    // warp-uniform
+    if (wslot < nslices) {                                                    // warp-uniform
+        const long long slice = p.order ? (long long) p.order[wslot] : wslot;
         const int vl = lane >> p.logTPV, k0 = (lane & (TPV - 1)) * LPT;
         const int v = (int) (slice << p.logC) + vl;
         const bool on = (v < p.Vown) && (k0 < K);    // LPT == 4 requires K % 4 == 0: all LPT labels valid
@@ -544,7 +546,7 @@ struct SimplexSolver : SolverBase {
     DevIn<real> Q, La_f, La_d1, P0;
     DevIn<int> Eu, Ev;
     DevBuf<real> w, wk, thk, Z0, Z1, Pa, Pb, Fa, Fb, T, GaQ, Sinv, Sinvk, Gn, GaU, dObj, dDif, Pout, Qal;
-    DevBuf<int> lab;
+    DevBuf<int> lab, order;
     DevBuf<double> partial, sums;
     Halo<real> halo;
     bool sharded = false;
@@ -608,6 +610,19 @@ struct SimplexSolver : SolverBase {
         partial.alloc((size_t) std::max(grid, num_sms() * 8) * 2);
 
         p.Vown = Vown; p.sharded = sharded ? 1 : 0; p.sums = sums.p; p.Vglobal = sharded ? q.shard->Vglobal : V;
+        {   // banded graph whose +-band reuse window would not fit the L2: sweep (x,y)-tiles along z instead
+            const double bytes_per_vertex = (double) sizeof(real) * K * (2.0 * std::max(g.max_width, 1) + 6.0);
+            const char *e = getenv("PFDR_B200_TILE");
+            const long long tile_env = e ? atoll(e) : -1;
+            p.order = nullptr;
+            if (tile_env != 0 && g.band > 0 && ((double) g.band * bytes_per_vertex > 24e6 || tile_env > 0)) {
+                long long T = tile_env > 0 ? tile_env : (long long) (5e6 / bytes_per_vertex);
+                T = std::max<long long>(C, std::min<long long>(T, g.band));
+                T = (T / C) * C;
+                build_slice_order(g, (int) (((long long) Vown + C - 1) / C), (int) T, order);
+                p.order = order.p;
+            }
+        }
         p.ctl = ctl.p; p.K = K; p.V = V; p.E = E; p.TPV = TPV; p.C = C; p.logC = logC; p.logTPV = logTPV; p.LPT = LPT;
         p.loss = (q.al == (real) 0) ? LOSS_LIN : (q.al == (real) 1 ? LOSS_QUAD : LOSS_KLA);
         p.by_label = by_label;
