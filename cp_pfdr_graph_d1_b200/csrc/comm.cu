@@ -136,6 +136,8 @@ template <typename real> void comm_recv(real *buf, size_t count, int peer)
 {
     PFDR_NCCL(api().Recv(buf, count, NcclType<real>::v, peer, need_comm(), ctx().stream));
 }
+void comm_send_f64(const double *buf, size_t count, int peer) { comm_send<double>(buf, count, peer); }
+void comm_recv_f64(double *buf, size_t count, int peer) { comm_recv<double>(buf, count, peer); }
 template void comm_send<float>(const float *, size_t, int);
 template void comm_send<double>(const double *, size_t, int);
 template void comm_recv<float>(float *, size_t, int);
@@ -203,9 +205,21 @@ void Halo<real>::build(int mask)
 }
 
 template <typename real>
-void Halo<real>::exchange(int mask, PingPong<real> va0, PingPong<real> va1, PingPong<real> Z, const Ctl *ctl, int parity)
+void Halo<real>::exchange(int mask, PingPong<real> va0, PingPong<real> va1, PingPong<real> Z, const Ctl *ctl, int parity,
+                          double *allsums, int nvals)
 {
-    if (!nnb) return;
+    const int world = comm().world, me = comm().rank;
+    if (!nnb) {
+        if (allsums && world > 1) {
+            comm_group_start();
+            for (int r = 0; r < world; r++) if (r != me) {
+                comm_send_f64(allsums + (size_t) me * nvals, nvals, r);
+                comm_recv_f64(allsums + (size_t) r * nvals, nvals, r);
+            }
+            comm_group_end();
+        }
+        return;
+    }
     Layout &L = layouts[mask];
     if (!L.built) throw Error(PFDR_B200_ERR_ARG, "halo layout used before build()");
     if (L.pack_items)
@@ -215,6 +229,12 @@ void Halo<real>::exchange(int mask, PingPong<real> va0, PingPong<real> va1, Ping
     for (int i = 0; i < nnb; i++) {
         if (L.scnt[i]) comm_send<real>(sendbuf.p + L.soff[i], L.scnt[i], rank[i]);
         if (L.rcnt[i]) comm_recv<real>(recvbuf.p + L.roff[i], L.rcnt[i], rank[i]);
+    }
+    if (allsums) {
+        for (int r = 0; r < world; r++) if (r != me) {
+            comm_send_f64(allsums + (size_t) me * nvals, nvals, r);
+            comm_recv_f64(allsums + (size_t) r * nvals, nvals, r);
+        }
     }
     comm_group_end();
     if (L.unpack_items)

@@ -24,6 +24,8 @@ void comm_destroy();
 void comm_allreduce_sum(double *buf, int count);
 void comm_group_start();
 void comm_group_end();
+void comm_send_f64(const double *buf, size_t count, int peer);
+void comm_recv_f64(double *buf, size_t count, int peer);
 template <typename real> void comm_send(const real *buf, size_t count, int peer);
 template <typename real> void comm_recv(real *buf, size_t count, int peer);
 
@@ -64,7 +66,11 @@ struct Halo {
     void build(int mask);
     // mask = HALO_VA0 | HALO_VA1 | HALO_Z: which of the arrays travel.  parity selects which of the ping/pong
     // buffers is used, decided on the device from the control block (no host synchronisation)
-    void exchange(int mask, PingPong<real> va0, PingPong<real> va1, PingPong<real> Z, const Ctl *ctl, int parity);
+    // allsums != NULL: the same NCCL group also carries this rank's `nvals` reduction scalars (allsums[rank*nvals..])
+    // to every other rank and receives theirs into allsums[r*nvals..] - an all-gather by point-to-point messages, so
+    // that an iteration costs one NCCL launch instead of two; every rank then adds the partials in rank order.
+    void exchange(int mask, PingPong<real> va0, PingPong<real> va1, PingPong<real> Z, const Ctl *ctl, int parity,
+                  double *allsums = nullptr, int nvals = 0);
 };
 
 }  // namespace pfdr

@@ -29,7 +29,9 @@ struct QP {                       // kernel parameter block
     Ctl *ctl;
     int V, N, E;
     int Vown, sharded;            // vertices this rank owns (== V unless sharded: ghosts follow)
-    double *sums;                 // [2] reduction scratch of the sharded path (all-reduced between kernels)
+    int world, rank;              // sharded: sums holds one pair per rank, sums[2*rank..] is ours
+    double *sums;                 // [2*world] evolution sums of every rank (sharded path), gathered with the halo exchange
+    double *amp_sums;             // [2] amplitude sums (all-reduced)
     double *rsum;                 // [N] sum of A x over this rank's columns (sharded dense A)
     const long long *slice_off; const int *nbr, *twin, *hkey;
     real *w;                      // [slots] raw d1 weight of the half-edge's edge
@@ -120,7 +122,7 @@ __global__ void __launch_bounds__(256) amp_kernel(QP<real> p, int recond)
         else if (a < (real) 0) { r[0] = -(double) a; r[1] = 1.0; }
     }
     if (grid_sum<2>(p.ctl, p.partial, r, smem) && threadIdx.x == 0) {
-        if (p.sharded) { p.sums[0] = r[0]; p.sums[1] = r[1]; }       // finished by amp_finish_kernel after the all-reduce
+        if (p.sharded) { p.amp_sums[0] = r[0]; p.amp_sums[1] = r[1]; } // finished by amp_finish_kernel after the all-reduce
         else p.ctl->amp = recond ? (double) ((real) r[0] / (real) r[1]) : (double) ((real) r[1] / (real) r[0]);
     }
 }
@@ -128,7 +130,7 @@ __global__ void __launch_bounds__(256) amp_kernel(QP<real> p, int recond)
 template <typename real>
 __global__ void amp_finish_kernel(QP<real> p, int recond)
 {
-    const double a = p.sums[0], n = p.sums[1];
+    const double a = p.amp_sums[0], n = p.amp_sums[1];
     p.ctl->amp = recond ? (double) ((real) a / (real) n) : (double) ((real) n / (real) a);
 }
 
@@ -257,7 +259,9 @@ template <typename real>
 __global__ void quad_finalize_kernel(QP<real> p)
 {
     if (p.ctl->hold != 0 || p.ctl->state != ST_RUN) return;
-    quad_finalize(p, p.ctl->it, p.sums[0], p.sums[1]);
+    double d = 0.0, c = 0.0;
+    for (int r = 0; r < p.world; r++) { d += p.sums[2 * r]; c += p.sums[2 * r + 1]; }     // rank order: same bits everywhere
+    quad_finalize(p, p.ctl->it, d, c);
 }
 
 // U half-edge rows of the vertex are in flight at once: first every index / weight / own-copy load of the
@@ -352,7 +356,7 @@ __global__ void __launch_bounds__(256) quad_iter_kernel(QP<real> p)
         red[0] = (double) (dx * dx); red[1] = (double) (x * x);
     }
     if (grid_sum<2>(ctl, p.partial, red, smem) && threadIdx.x == 0) {
-        if (p.sharded) { p.sums[0] = red[0]; p.sums[1] = red[1]; }
+        if (p.sharded) { p.sums[2 * p.rank] = red[0]; p.sums[2 * p.rank + 1] = red[1]; }
         else quad_finalize(p, it, red[0], red[1]);
     }
 }
@@ -431,7 +435,7 @@ __global__ void __launch_bounds__(256, MINB) quad_iter_pipe_kernel(QP<real> p)
         red[0] = (double) (dx * dx); red[1] = (double) (x * x);
     }
     if (grid_sum<2>(ctl, p.partial, red, smem) && threadIdx.x == 0) {
-        if (p.sharded) { p.sums[0] = red[0]; p.sums[1] = red[1]; }
+        if (p.sharded) { p.sums[2 * p.rank] = red[0]; p.sums[2 * p.rank + 1] = red[1]; }
         else quad_finalize(p, it, red[0], red[1]);
     }
 }
@@ -556,7 +560,7 @@ __global__ void __launch_bounds__(32 * W * G) quad_rows_kernel(QP<real> p, int n
     block_sum<2>(acc, smem);
     if (threadIdx.x == 0) {
         ctl->ticket = 0;
-        if (p.sharded) { p.sums[0] = acc[0]; p.sums[1] = acc[1]; }
+        if (p.sharded) { p.sums[2 * p.rank] = acc[0]; p.sums[2 * p.rank + 1] = acc[1]; }
         else quad_finalize(p, it, acc[0], acc[1]);
     }
 }
@@ -790,7 +794,7 @@ struct QuadSolver : SolverBase {
     DevIn<real> Y, A, La_d1, La_l1, L, X0;
     DevIn<int> Eu, Ev;
     DevBuf<real> w, thc, Z0, Z1, X0b, X1b, P0b, P1b, T, Sinv, Ga, Ga0, G, Thl1, R, AtY, dObj, dDif, Xout;
-    DevBuf<double> partial, parts, sums, rsum;
+    DevBuf<double> partial, parts, sums, rsum, amp_sums;
     Halo<real> halo;
     bool sharded = false;
     int ogrid = 0;                  // CTAs covering the owned vertices
@@ -848,13 +852,14 @@ struct QuadSolver : SolverBase {
         if (q.Dif) dDif.alloc((size_t) std::max(q.itMax, 1));
         vgrid = (int) cdiv(V, 256);
         ogrid = sharded ? (int) cdiv(q.shard->Vown, 256) : vgrid;
-        ctl.alloc(1); sums.alloc(2);
+        ctl.alloc(1); sums.alloc(2 * (size_t) std::max(1, comm().world)); sums.zero(); amp_sums.alloc(2);
 
         // padded slots of Z must never hold garbage that could turn into NaN traps: zero them
         Z0.zero(); Z1.zero(); w.zero();
 
         p.ctl = ctl.p; p.V = V; p.N = N; p.E = E;
-        p.Vown = sharded ? q.shard->Vown : V; p.sharded = sharded ? 1 : 0; p.sums = sums.p;
+        p.Vown = sharded ? q.shard->Vown : V; p.sharded = sharded ? 1 : 0; p.sums = sums.p; p.amp_sums = amp_sums.p;
+        p.world = sharded ? comm().world : 1; p.rank = sharded ? comm().rank : 0;
         p.slice_off = g.slice_off.p; p.nbr = g.nbr.p; p.twin = g.twin.p; p.hkey = g.hkey.p;
         p.w = w.p; p.thc = nullptr; p.thc0 = 0; p.Z0 = Z0.p; p.Z1 = Z1.p;
         p.X0 = X0b.p; p.X1 = X1b.p; p.P0 = P0b.p; p.P1 = P1b.p; p.T = T.p; p.Sinv = Sinv.p; p.Ga = Ga.p; p.Ga0 = Ga0.p; p.G = G.p; p.Thl1 = Thl1.p;
@@ -912,7 +917,7 @@ struct QuadSolver : SolverBase {
         // first preconditioning
         if (q.N > 0) launch_atr(1);
         PFDR_LAUNCH(amp_kernel<real>, ogrid, 256, 0, p, 0);
-        if (sharded) { comm_allreduce_sum(sums.p, 2); PFDR_LAUNCH(amp_finish_kernel<real>, 1, 1, 0, p, 0); }
+        if (sharded) { comm_allreduce_sum(amp_sums.p, 2); PFDR_LAUNCH(amp_finish_kernel<real>, 1, 1, 0, p, 0); }
         PFDR_LAUNCH(init_vertex_kernel<real>, vgrid, 256, 0, p, X0.p);
         // ghosts: the metric constants and forward point come from their owners
         if (sharded) halo.exchange(HALO_VA0 | HALO_VA1, PingPong<real>(T.p), PingPong<real>(P0b.p), PingPong<real>(), nullptr, PARITY_ZERO);
@@ -957,8 +962,7 @@ struct QuadSolver : SolverBase {
         if (sharded) {     // new boundary forward points and cut-edge copies to the neighbours (taken from the buffers the
                            // iteration kernel just wrote), evolution sums over all ranks, then the iteration is closed
             halo.exchange(q.N == 0 ? (HALO_VA0 | HALO_Z) : HALO_Z, PingPong<real>(P0b.p, P1b.p), PingPong<real>(),
-                          PingPong<real>(Z0.p, Z1.p), ctl.p, PARITY_NEXT_IF_RAN);
-            comm_allreduce_sum(sums.p, 2);
+                          PingPong<real>(Z0.p, Z1.p), ctl.p, PARITY_NEXT_IF_RAN, sums.p, 2);
             PFDR_LAUNCH(quad_finalize_kernel<real>, 1, 1, 0, p);
         }
     }
@@ -1007,7 +1011,7 @@ struct QuadSolver : SolverBase {
 #undef PFDR_ROWS
     }
 
-    int launches_per_trip() const { return (q.N > 0 ? 3 : (q.N < 0 ? 1 : 0)) + (q.Obj ? 1 : 0) + 1 + (sharded ? (q.N > 0 ? 10 : 5) : 0); }
+    int launches_per_trip() const { return (q.N > 0 ? 3 : (q.N < 0 ? 1 : 0)) + (q.Obj ? 1 : 0) + 1 + (sharded ? (q.N > 0 ? 9 : 4) : 0); }
 
     // enqueue `trips` iterations; replays a captured CUDA graph when a whole batch is requested
     void enqueue_batch(int trips, int batch)

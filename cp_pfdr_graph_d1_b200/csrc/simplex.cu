@@ -30,6 +30,7 @@ struct SP {
     Ctl *ctl;
     int K, V, E, TPV, C, logC, logTPV, loss, by_label, LPT, stream_z;
     int Vown, sharded, Vglobal;   // vertices this rank owns (== V unless sharded: ghosts follow), global count
+    int world, rank;              // sharded: sums holds one value per rank, sums[rank] is ours
     double *sums;                 // [1] reduction scratch of the sharded path
     real aK, a1, aK1, rho, condMin;
     const long long *slice_off; const int *nbr, *twin, *hkey;
@@ -413,7 +414,9 @@ template <typename real>
 __global__ void simplex_finalize_kernel(SP<real> p)
 {
     if (p.ctl->hold != 0 || p.ctl->state != ST_RUN) return;
-    simplex_finalize(p, p.ctl->it, p.sums[0]);
+    double s = 0.0;
+    for (int r = 0; r < p.world; r++) s += p.sums[r];            // rank order: same bits everywhere
+    simplex_finalize(p, p.ctl->it, s);
 }
 
 template <typename real, int LPT, bool PERK, int LOSS, int MINB>
@@ -493,7 +496,7 @@ __global__ void __launch_bounds__(256, MINB) simplex_iter_kernel(SP<real> p)
         red[0] = simplex_epilogue<real, LPT, PERK, LOSS>(p, ctl, on, v, k0, vk, acc, Tv, pold, Pn, Fn);
     }
     if (grid_sum_s<1>(ctl, p.partial, red, smem) && threadIdx.x == 0) {
-        if (p.sharded) p.sums[0] = red[0];
+        if (p.sharded) p.sums[p.rank] = red[0];
         else simplex_finalize(p, it, red[0]);
     }
 }
@@ -602,7 +605,7 @@ struct SimplexSolver : SolverBase {
         if (by_label) lab.alloc(V);
         if (q.Obj) dObj.alloc((size_t) q.itMax + 1);
         if (q.Dif) dDif.alloc((size_t) std::max(q.itMax, 1));
-        ctl.alloc(1); sums.alloc(1);
+        ctl.alloc(1); sums.alloc((size_t) std::max(1, comm().world)); sums.zero();
         const long long nslices = ((long long) V + C - 1) / C;
         grid = (int) cdiv((size_t) nslices * 32, 256);
         const int Vown = sharded ? q.shard->Vown : V;
@@ -610,6 +613,7 @@ struct SimplexSolver : SolverBase {
         partial.alloc((size_t) std::max(grid, num_sms() * 8) * 2);
 
         p.Vown = Vown; p.sharded = sharded ? 1 : 0; p.sums = sums.p; p.Vglobal = sharded ? q.shard->Vglobal : V;
+        p.world = sharded ? comm().world : 1; p.rank = sharded ? comm().rank : 0;
         {   // banded graph whose +-band reuse window would not fit the L2: sweep (x,y)-tiles along z instead
             const double bytes_per_vertex = (double) sizeof(real) * K * (2.0 * std::max(g.max_width, 1) + 6.0);
             const char *e = getenv("PFDR_B200_TILE");
@@ -698,12 +702,12 @@ struct SimplexSolver : SolverBase {
         if (LPT == 4) { if (p.wk) launch_iter_loss<4, true>(); else launch_iter_loss<4, false>(); }
         else { if (p.wk) launch_iter_loss<1, true>(); else launch_iter_loss<1, false>(); }
         if (sharded) {     // evolution sum over all ranks, then the new boundary forward points and cut-edge copies
-            halo.exchange(HALO_VA0 | HALO_Z, PingPong<real>(Fa.p, Fb.p), PingPong<real>(), PingPong<real>(Z0.p, Z1.p), ctl.p, PARITY_NEXT_IF_RAN);
-            comm_allreduce_sum(sums.p, 1);
+            halo.exchange(HALO_VA0 | HALO_Z, PingPong<real>(Fa.p, Fb.p), PingPong<real>(), PingPong<real>(Z0.p, Z1.p), ctl.p,
+                          PARITY_NEXT_IF_RAN, sums.p, 1);
             PFDR_LAUNCH(simplex_finalize_kernel<real>, 1, 1, 0, p);
         }
     }
-    int launches_per_trip() const { return (q.Obj ? 1 : 0) + 1 + (sharded ? 5 : 0); }
+    int launches_per_trip() const { return (q.Obj ? 1 : 0) + 1 + (sharded ? 4 : 0); }
 
     void enqueue_batch(int batch)
     {
