@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libpfdr_b200.so")
+LIB_PATH = os.environ.get("PFDR_B200_LIBPATH") or os.path.join(_HERE, "lib", "libpfdr_b200.so")   # env: A/B of builds
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "pfdr_b200.h")
 
 

@@ -18,6 +18,7 @@
 // Th_d1 = (La_d1/w)(T[u]+T[v]); before any reconditioning w = La_d1[e] for all labels (:207-208), so
 // La_d1/w = 1, S is per vertex, and T doubles as the projection metric (the projection is invariant to a
 // positive rescaling of the metric, and the reference's normalisation Ga/max Ga (:362-369) is one).
+#include <type_traits>
 #include "graph.cuh"
 #include "solvers.cuh"
 
@@ -419,7 +420,7 @@ __global__ void simplex_finalize_kernel(SP<real> p)
     simplex_finalize(p, p.ctl->it, s);
 }
 
-template <typename real, int LPT, bool PERK, int LOSS, int MINB>
+template <typename real, int LPT, bool PERK, int LOSS, int MINB, bool IDX32>
 __global__ void __launch_bounds__(256, MINB) simplex_iter_kernel(SP<real> p)
 {
     typedef VecN<real, LPT> vec;
@@ -460,38 +461,43 @@ __global__ void __launch_bounds__(256, MINB) simplex_iter_kernel(SP<real> p)
         vec acc = splat<real, LPT>((real) 0);
         // Software pipeline over the vertex's rows: the indices (and the lane's own copy) of row j+1 are
         // requested while row j's gathers are in flight, so a row costs one memory round trip, not two.
+        // Element offsets are 32-bit when every array has < 2^32 elements (IDX32): one IMAD per gather address.
+        typedef typename std::conditional<IDX32, unsigned, size_t>::type idx_t;
+        const idx_t rowK = (idx_t) C * (idx_t) K;
+        int s = (int) s0;                                                // slot of this lane's vertex in row j
+        idx_t zoff = (idx_t) s0 * (idx_t) K + (idx_t) k0;               // its K-vector of edge copies
         int n_c = -1, tw_c = 0;
         real w_c = 0;
         vec zo_c = splat<real, LPT>((real) 0);
         if (on && width > 0) {
-            n_c = nbr[s0]; tw_c = twin[s0];
-            if (!PERK) w_c = p.w[s0];
-            zo_c = ldv<real, LPT>(Zin + (size_t) s0 * K + k0);
+            n_c = nbr[s]; tw_c = twin[s];
+            if (!PERK) w_c = p.w[s];
+            zo_c = ldv<real, LPT>(Zin + zoff);
         }
         for (int j = 0; j < width; j++) {
-            const long long s = s0 + ((long long) j << p.logC);
             const bool live = n_c >= 0;
             vec zt, fn, tn, wvk, th;
             if (live) {
-                zt = ldv<real, LPT>(Zin + (size_t) tw_c * K + k0);
-                fn = ldv<real, LPT>(Fc + (size_t) n_c * K + k0);
-                if (LOSS != LOSS_LIN) tn = ldv<real, LPT>(Tg + (size_t) n_c * K + k0);
-                if (PERK) { wvk = ldv<real, LPT>(p.wk + (size_t) s * K + k0); th = ldv<real, LPT>(p.thk + (size_t) s * K + k0); }
+                const idx_t no = (idx_t) n_c * (idx_t) K + (idx_t) k0;
+                zt = ldv<real, LPT>(Zin + ((idx_t) tw_c * (idx_t) K + (idx_t) k0));
+                fn = ldv<real, LPT>(Fc + no);
+                if (LOSS != LOSS_LIN) tn = ldv<real, LPT>(Tg + no);
+                if (PERK) { wvk = ldv<real, LPT>(p.wk + zoff); th = ldv<real, LPT>(p.thk + zoff); }
             }
             int n_n = -1, tw_n = 0;
             real w_n = 0;
             vec zo_n = zo_c;
             if (on && j + 1 < width) {
-                const long long s2 = s + C;
-                n_n = nbr[s2]; tw_n = twin[s2];
-                if (!PERK) w_n = p.w[s2];
-                zo_n = ldv<real, LPT>(Zin + (size_t) s2 * K + k0);
+                n_n = nbr[s + C]; tw_n = twin[s + C];
+                if (!PERK) w_n = p.w[s + C];
+                zo_n = ldv<real, LPT>(Zin + (zoff + rowK));
             }
             if (live) {
                 const vec zn = prox_row<real, LPT, PERK, LOSS>(rho, fown, pold, Tv, Sv, zo_c, zt, fn, tn, wvk, th, w_c, acc);
-                if (p.stream_z) stv_cs<real, LPT>(Zout + (size_t) s * K + k0, zn); else stv<real, LPT>(Zout + (size_t) s * K + k0, zn);
+                if (p.stream_z) stv_cs<real, LPT>(Zout + zoff, zn); else stv<real, LPT>(Zout + zoff, zn);
             }
             n_c = n_n; tw_c = tw_n; w_c = w_n; zo_c = zo_n;
+            s += C; zoff += rowK;
         }
         red[0] = simplex_epilogue<real, LPT, PERK, LOSS>(p, ctl, on, v, k0, vk, acc, Tv, pold, Pn, Fn);
     }
@@ -679,11 +685,13 @@ struct SimplexSolver : SolverBase {
         static int MB = -1;
         if (MB < 0) { const char *e = getenv("PFDR_B200_MINB"); MB = e ? atoi(e) : 0; }
         (void) U;
-        if (L == 4 && !PERK && LOSS == LOSS_KLA && MB == 5) PFDR_LAUNCH((simplex_iter_kernel<real, 4, false, LOSS_KLA, 5>), ogrid, 256, 0, p);
-        else if (L == 4 && !PERK && LOSS == LOSS_KLA && MB == 6) PFDR_LAUNCH((simplex_iter_kernel<real, 4, false, LOSS_KLA, 6>), ogrid, 256, 0, p);
-        else if (L == 4 && !PERK && LOSS == LOSS_KLA && MB == 8) PFDR_LAUNCH((simplex_iter_kernel<real, 4, false, LOSS_KLA, 8>), ogrid, 256, 0, p);
-        else if (L == 4 && !PERK && LOSS == LOSS_KLA && MB == 1) PFDR_LAUNCH((simplex_iter_kernel<real, 4, false, LOSS_KLA, 1>), ogrid, 256, 0, p);
-        else PFDR_LAUNCH((simplex_iter_kernel<real, L, PERK, LOSS, (sizeof(real) == 4 ? 4 : 2)>), ogrid, 256, 0, p);
+        constexpr int MBD = (sizeof(real) == 4 ? 4 : 2);
+        const bool small = (size_t) std::max<long long>(g.nslots, q.V) * (size_t) q.K < 0xFFFFFFFFull;
+        static int i32 = -1;
+        if (i32 < 0) { const char *e = getenv("PFDR_B200_IDX32"); i32 = (e && e[0] == '0') ? 0 : 1; }
+        (void) U; (void) MB;
+        if (L == 4 && !PERK && small && i32) PFDR_LAUNCH((simplex_iter_kernel<real, 4, false, LOSS, MBD, true>), ogrid, 256, 0, p);
+        else PFDR_LAUNCH((simplex_iter_kernel<real, L, PERK, LOSS, MBD, false>), ogrid, 256, 0, p);
     }
     template <int L, bool PERK>
     void launch_iter_loss()
