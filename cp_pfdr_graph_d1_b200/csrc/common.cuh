@@ -244,6 +244,52 @@ __device__ __forceinline__ double fast_rcp(double x)
     return r;
 }
 
+// Cheaper grid-wide deterministic sum for the iteration kernels: 32 values are added in `real` with one shuffle tree,
+// the per-warp results go to shared memory as doubles and thread 0 alone adds them in warp order (no second
+// shuffle tree in every warp).  The last CTA to arrive (ticket) adds the per-CTA partials in CTA order.
+// smem: >= NV*32 doubles.  Returns true in every thread of the last CTA; the totals are valid in thread 0.
+template <int NV, typename real>
+__device__ __forceinline__ bool grid_sum_fast(Ctl *ctl, double *partial, real (&v)[NV], double (&tot)[NV], double *smem)
+{
+    __shared__ int s_last_fast;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; i++)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; i++) smem[i * 32 + wid] = (double) v[i];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; i++) {
+            double a = 0.0;
+            for (int w = 0; w < nw; w++) a += smem[i * 32 + w];
+            partial[(size_t) blockIdx.x * NV + i] = a;
+        }
+        __threadfence();
+        s_last_fast = (atomicAdd(&ctl->ticket, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last_fast) return false;
+    __threadfence();
+    double acc[NV];
+#pragma unroll
+    for (int i = 0; i < NV; i++) acc[i] = 0.0;
+    const volatile double *vp = partial;
+    for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
+#pragma unroll
+        for (int i = 0; i < NV; i++) acc[i] += vp[(size_t) b * NV + i];
+    }
+    block_sum<NV>(acc, smem);
+#pragma unroll
+    for (int i = 0; i < NV; i++) tot[i] = acc[i];
+    if (threadIdx.x == 0) ctl->ticket = 0;
+    return true;
+}
+
 template <typename real> struct Pair;
 template <> struct Pair<float> { typedef float2 type; };
 template <> struct Pair<double> { typedef double2 type; };

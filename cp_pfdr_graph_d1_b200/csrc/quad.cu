@@ -383,7 +383,7 @@ __global__ void __launch_bounds__(256, MINB) quad_iter_pipe_kernel(QP<real> p)
     const real *__restrict__ wg = p.w;
     const real rho = p.rho;
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
-    double red[2] = {0.0, 0.0};
+    real red[2] = {(real) 0, (real) 0};
     if (v < p.Vown) {
         const long long base = p.slice_off[v >> 5];
         const int width = (int) ((p.slice_off[(v >> 5) + 1] - base) >> 5);
@@ -432,11 +432,12 @@ __global__ void __launch_bounds__(256, MINB) quad_iter_pipe_kernel(QP<real> p)
         (cur ? p.X0 : p.X1)[v] = x;
         if (p.N == 0) (cur ? p.P0 : p.P1)[v] = (real) 2 * x - p.Ga[v] * grad_at(p, v, x);
         const real dx = xo - x;
-        red[0] = (double) (dx * dx); red[1] = (double) (x * x);
+        red[0] = dx * dx; red[1] = x * x;
     }
-    if (grid_sum<2>(ctl, p.partial, red, smem) && threadIdx.x == 0) {
-        if (p.sharded) { p.sums[2 * p.rank] = red[0]; p.sums[2 * p.rank + 1] = red[1]; }
-        else quad_finalize(p, it, red[0], red[1]);
+    double tot[2];
+    if (grid_sum_fast<2, real>(ctl, p.partial, red, tot, smem) && threadIdx.x == 0) {
+        if (p.sharded) { p.sums[2 * p.rank] = tot[0]; p.sums[2 * p.rank + 1] = tot[1]; }
+        else quad_finalize(p, it, tot[0], tot[1]);
     }
 }
 

@@ -445,7 +445,7 @@ __global__ void __launch_bounds__(256, MINB) simplex_iter_kernel(SP<real> p)
     const long long wslot = ((long long) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nslices = ((long long) p.Vown + C - 1) >> p.logC;
     const real rho = p.rho;
-    double red[1] = {0.0};
+    real red[1] = {(real) 0};
     if (wslot < nslices) {                                                    // warp-uniform
         const long long slice = p.order ? (long long) p.order[wslot] : wslot;
         const int vl = lane >> p.logTPV, k0 = (lane & (TPV - 1)) * LPT;
@@ -499,11 +499,12 @@ __global__ void __launch_bounds__(256, MINB) simplex_iter_kernel(SP<real> p)
             n_c = n_n; tw_c = tw_n; w_c = w_n; zo_c = zo_n;
             s += C; zoff += rowK;
         }
-        red[0] = simplex_epilogue<real, LPT, PERK, LOSS>(p, ctl, on, v, k0, vk, acc, Tv, pold, Pn, Fn);
+        red[0] = (real) simplex_epilogue<real, LPT, PERK, LOSS>(p, ctl, on, v, k0, vk, acc, Tv, pold, Pn, Fn);
     }
-    if (grid_sum_s<1>(ctl, p.partial, red, smem) && threadIdx.x == 0) {
-        if (p.sharded) p.sums[p.rank] = red[0];
-        else simplex_finalize(p, it, red[0]);
+    double tot[1];
+    if (grid_sum_fast<1, real>(ctl, p.partial, red, tot, smem) && threadIdx.x == 0) {
+        if (p.sharded) p.sums[p.rank] = tot[0];
+        else simplex_finalize(p, it, tot[0]);
     }
 }
 
