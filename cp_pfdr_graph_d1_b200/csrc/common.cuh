@@ -234,7 +234,13 @@ __device__ __forceinline__ void block_sum(double (&v)[NV], double *smem /* >= NV
 
 // reciprocal for the recomputed edge constants: ~1 ulp (f32 MUFU.RCP; f64 MUFU.RCP64H + 2 Newton steps),
 // instead of the ~10 / ~25 instruction IEEE division sequences
-__device__ __forceinline__ float fast_rcp(float x) { return __fdividef(1.0f, x); }
+__device__ __forceinline__ float fast_rcp(float x)
+{   // one MUFU.RCP (__fdividef(1, x) wraps it in five more instructions of range handling that the sums of
+    // metric entries it is applied to never need)
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 __device__ __forceinline__ double fast_rcp(double x)
 {
     double r;
