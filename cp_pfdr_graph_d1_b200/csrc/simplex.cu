@@ -350,7 +350,7 @@ __device__ __forceinline__ double simplex_epilogue(const SP<real> &p, Ctl *ctl, 
 #pragma unroll
     for (int i = 0; i < LPT; i++) {
         if (!on) { m.v[i] = (real) 1; acc.v[i] = 0; }
-        xs.v[i] = acc.v[i] / m.v[i];
+        xs.v[i] = acc.v[i] * fast_rcp(m.v[i]);
         if (on && k0 + i < K) act |= 1u << i;
     }
     real la = 0;
@@ -359,7 +359,7 @@ __device__ __forceinline__ double simplex_epilogue(const SP<real> &p, Ctl *ctl, 
 #pragma unroll
         for (int i = 0; i < LPT; i++) if ((act >> i) & 1u) { sx += acc.v[i]; sm += m.v[i]; }
         sx = group_sum(sx, TPV); sm = group_sum(sm, TPV);
-        la = (sx - (real) 1) / sm;
+        la = (sx - (real) 1) * fast_rcp(sm);
         unsigned keep = act;
 #pragma unroll
         for (int i = 0; i < LPT; i++) if (((act >> i) & 1u) && xs.v[i] < la) keep &= ~(1u << i);

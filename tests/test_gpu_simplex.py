@@ -30,7 +30,7 @@ def test_simplex_parity(gpu_api, oracle, name, dtype):
     assert np.allclose(got.Obj[:n + 1], ref.Obj[:n + 1], rtol=tol, atol=tol * max(float(np.abs(ref.Obj).max()), 1.0) * 1e-1)
     if ref.Dif is not None and n and "labels" not in name:
         m = max(1, n // 2) if dtype is np.float32 else n
-        assert np.allclose(got.Dif[:m], ref.Dif[:m], rtol=5e-2 if dtype is np.float32 else 1e-4, atol=1e-12)
+        assert np.allclose(got.Dif[:m], ref.Dif[:m], rtol=5e-2 if dtype is np.float32 else 1e-4, atol=1e-6 if dtype is np.float32 else 1e-12)   # f32: rounding floor of a mean absolute change
     if "labels" in name and dtype is np.float64:
         assert np.array_equal(got.Dif[:n], ref.Dif[:n])
 
