@@ -19,7 +19,11 @@
 // so only the raw weight w is streamed per half-edge.
 #include "graph.cuh"
 #include "solvers.cuh"
+#include <cooperative_groups.h>
+#include <chrono>
+#include <vector>
 
+namespace cg = cooperative_groups;
 namespace pfdr {
 
 template <typename real> using pair_t = typename Pair<real>::type;
@@ -180,14 +184,8 @@ __global__ void __launch_bounds__(256) init_vertex_kernel(QP<real> p, const real
 // reconditioning, everything that is local to a vertex row in one kernel (ref :89-99, :167-250):
 // subgradients from the old metric, new raw weights, new metric, new edge copies, new forward point.
 template <typename real>
-__global__ void __launch_bounds__(256) recond_vertex_kernel(QP<real> p)
+__device__ __forceinline__ void recond_vertex(const QP<real> &p, int v, const real *X, real *Z, real *Pout, real c)
 {
-    const int v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= p.V) return;
-    const int cur = p.ctl->it & 1;
-    const real *X = cur ? p.X1 : p.X0;
-    real *Z = cur ? p.Z1 : p.Z0;
-    real c = (real) p.ctl->amp;
     const real x = X[v], g = grad_at(p, v, x);
     const real ga_old = p.Ga[v], sinv_old = p.Sinv[v];
     const int lane = v & 31;
@@ -225,7 +223,15 @@ __global__ void __launch_bounds__(256) recond_vertex_kernel(QP<real> p)
         const long long s = base + (long long) j * 32 + lane;
         if (p.nbr[s] >= 0) Z[s] = x - ga * (g + Z[s] / (p.w[s] * sinv));        // ref :247-248
     }
-    (cur ? p.P1 : p.P0)[v] = (real) 2 * x - ga * g;
+    Pout[v] = (real) 2 * x - ga * g;
+}
+
+template <typename real>
+__global__ void __launch_bounds__(256) recond_vertex_kernel(QP<real> p)
+{
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    const int cur = p.ctl->it & 1;
+    if (v < p.V) recond_vertex<real>(p, v, cur ? p.X1 : p.X0, cur ? p.Z1 : p.Z0, cur ? p.P1 : p.P0, (real) p.ctl->amp);
 }
 
 template <typename real>
@@ -439,6 +445,730 @@ __global__ void __launch_bounds__(256, MINB) quad_iter_pipe_kernel(QP<real> p)
         if (p.sharded) { p.sums[2 * p.rank] = tot[0]; p.sums[2 * p.rank + 1] = tot[1]; }
         else quad_finalize(p, it, tot[0], tot[1]);
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Small-problem mode: the whole solve in ONE launch of ONE thread-block cluster (up to 16 CTAs x 1024 threads).
+// The reduced problems that the cut-pursuit outer loop hands over (a few hundred to a few thousand vertices, up to
+// 1e4 iterations, reference src/CP_PFDR_graph_quadratic_d1_l1.cpp:848-859) are latency bound on the large path: one
+// launch (or four) per iteration and, inside it, a chain of dependent L2 round trips per half-edge row - with a
+// hub vertex (the background component of a reduced graph touches most others) the chain is its whole degree.
+//   * an iteration is two to four hardware cluster barriers (~0.2 us each) instead of kernel boundaries;
+//   * each CTA owns a range of SELL slices (vertices) and a range of edges;
+//   * the vertex arrays every edge gathers (X, forward point P, T) are replicated in each CTA's SHARED memory and
+//     refreshed from global memory (L2) with coalesced loads after the barrier that publishes them;
+//   * the edge prox is edge-parallel: one thread computes BOTH copies of an edge (same arithmetic as the two
+//     half-edge threads of the large path, bit for bit), reads the old copies from an edge-ordered array (coalesced)
+//     and scatters the new ones to their SELL slots, where the owner of the vertex reads its rows coalesced;
+//   * dense operators are applied by column slabs, the partial A x of the CTAs is exchanged through L2;
+//   * stopping rule, reconditioning and objective are evaluated on the device, identically in every CTA
+//     (partial sums exchanged through L2 and added in rank order).
+// Everything crossing CTAs goes through L2 (ld.global.cg) between cluster barriers (release / acquire).
+// ---------------------------------------------------------------------------------------------
+#ifdef PFDR_SMALL_PROF
+#define SPROF_DECL long long spt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, spc = clock64();
+#define SPROF(k) { const long long t_ = clock64(); spt[k] += t_ - spc; spc = t_; }
+#define SPROF_OUT if (rank == 0 && tid == 0) { for (int k = 0; k < 8; k++) printf("phase %d: %.3f us/it\n", k, (double) spt[k] / 1.9e3 / (it > 0 ? it : 1)); }
+#else
+#define SPROF_DECL
+#define SPROF(k)
+#define SPROF_OUT
+#endif
+
+constexpr int SMALL_MAX_SLICES = 1024;   // slices a CTA may own (32768 vertices)
+constexpr int SMALL_MAX_WIDE = 128;      // wide slices a CTA handles cooperatively; further ones take the per-thread path
+constexpr int SMALL_WIDE = 24;           // rows from which a slice counts as wide
+
+template <typename real> __device__ __forceinline__ void ld2(const real *q, real &a, real &b);
+template <> __device__ __forceinline__ void ld2<float>(const float *q, float &a, float &b) { const float2 t = *reinterpret_cast<const float2 *>(q); a = t.x; b = t.y; }
+template <> __device__ __forceinline__ void ld2<double>(const double *q, double &a, double &b) { const double2 t = *reinterpret_cast<const double2 *>(q); a = t.x; b = t.y; }
+template <typename real> __device__ __forceinline__ void st2(real *q, real a, real b);
+template <> __device__ __forceinline__ void st2<float>(float *q, float a, float b) { *reinterpret_cast<float2 *>(q) = make_float2(a, b); }
+template <> __device__ __forceinline__ void st2<double>(double *q, double a, double b) { *reinterpret_cast<double2 *>(q) = make_double2(a, b); }
+
+// Cluster barrier of the iteration loop: release on arrive (the CTA's global writes are performed before any CTA
+// passes), NO acquire on wait - an acquiring wait invalidates the whole L1 (CCTL.IVALL), and then every constant of
+// the iteration (indices, weights, metric) is fetched from L2 again, iteration after iteration.  Data written by
+// another CTA is only ever read with ld.global.cg (L2, never L1), so nothing stale can be observed.
+__device__ __forceinline__ void cluster_bar()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.aligned;\n" ::: "memory");
+}
+
+template <typename real>
+struct SmallArgs {
+    int nslots, nslices;
+    int *pos;          // [2E] SELL slot of every half-edge key
+    real *Ze;          // [2E] edge copies in edge order
+    double *xs;        // [2][16][2] partial sums of the CTAs, double-buffered
+    real *parts;       // [16][N] partial A x of the CTAs
+};
+
+template <typename real>
+__device__ __forceinline__ void small_block_sum2(double &a, double &b, double *sm /* 64 doubles */)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    a = warp_sum(a); b = warp_sum(b);
+    __syncthreads();
+    if (lane == 0) { sm[wid] = a; sm[32 + wid] = b; }
+    __syncthreads();
+    if (wid == 0) {
+        double x = lane < nw ? sm[lane] : 0.0, y = lane < nw ? sm[32 + lane] : 0.0;
+        x = warp_sum(x); y = warp_sum(y);
+        if (lane == 0) { sm[0] = x; sm[32] = y; }
+    }
+    __syncthreads();
+    a = sm[0]; b = sm[32];
+    __syncthreads();
+}
+
+// sum of (a, b) over the CTAs of the cluster, the same bits in every CTA; contains one cluster barrier, which also
+// publishes every global write made before the call
+template <typename real>
+__device__ __forceinline__ void cluster_sum2(cg::cluster_group &cl, double *xs, int &ph, int rank, int C, double &a, double &b,
+                                             double *sm)
+{
+    small_block_sum2<real>(a, b, sm);
+    if (threadIdx.x == 0) { xs[(ph * 16 + rank) * 2] = a; xs[(ph * 16 + rank) * 2 + 1] = b; }
+    cl.sync();
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        double x = lane < C ? __ldcg(xs + (ph * 16 + lane) * 2) : 0.0, y = lane < C ? __ldcg(xs + (ph * 16 + lane) * 2 + 1) : 0.0;
+        x = warp_sum(x); y = warp_sum(y);
+        if (lane == 0) { sm[0] = x; sm[32] = y; }
+    }
+    __syncthreads();
+    a = sm[0]; b = sm[32];
+    __syncthreads();
+    ph ^= 1;
+}
+
+template <typename real>
+__global__ void __launch_bounds__(512, 1) quad_small_kernel(QP<real> p, SmallArgs<real> a)
+{
+    extern __shared__ double dsm_small[];
+    cg::cluster_group cl = cg::this_cluster();
+    Ctl *ctl = p.ctl;
+    const int C = (int) gridDim.x, rank = (int) blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5, nt = blockDim.x;
+    const int V = p.V, N = p.N, E = p.E, itMax = ctl->itMax, track = ctl->track;
+    const int Np = N > 0 ? N : 0, Vp = (V + 3) & ~3;
+    double *red = dsm_small;                                     // [64] reductions
+    real *Xs = reinterpret_cast<real *>(dsm_small + 64);         // [V] iterate         } replicas of the arrays the edges gather
+    real *Ps = Xs + Vp;                                          // [V] forward point   }
+    real *Ts = Ps + Vp;                                          // [V] Ga.S            }
+    real *Rs = Ts + Vp;                                          // [N] residual
+    real *part = Rs + ((Np + 3) & ~3);                           // [nw * N] per-warp partial A x
+    __shared__ int sbase[SMALL_MAX_SLICES + 1];                  // slot offset of the own slices
+    __shared__ unsigned char isw[SMALL_MAX_SLICES];              // own slice is wide (handled by the whole CTA)
+    __shared__ int widelist[SMALL_MAX_WIDE], nwide;
+    __shared__ real wpart[32 * 32];
+    constexpr int EU = 2, VU = 8;
+    // ownership: SELL slices (vertices, slots) and edges in contiguous ranges
+    const int sl0 = (int) ((long long) a.nslices * rank / C), sl1 = (int) ((long long) a.nslices * (rank + 1) / C);
+    const int v0 = sl0 * 32, v1 = min(V, sl1 * 32);
+    const int s0 = (int) p.slice_off[sl0], s1 = (int) p.slice_off[sl1];
+    const int e0 = (int) ((long long) E * rank / C), e1 = (int) ((long long) E * (rank + 1) / C);
+    real *Xg = p.X0, *Pg = p.P0, *Zg = p.Z0;                     // one buffer each in this mode
+    int it = ctl->it;
+    if (it & 1) {                                                // resumed at an odd iteration: state sits in the other buffers
+        for (int v = v0 + tid; v < v1; v += nt) { Xg[v] = p.X1[v]; Pg[v] = p.P1[v]; }
+        for (int s = s0 + tid; s < s1; s += nt) Zg[s] = p.Z1[s];
+    }
+    for (int s = s0 + tid; s < s1; s += nt) { const int h = p.hkey[s]; if (h >= 0) a.pos[h] = s; }
+    for (int q = tid; q <= sl1 - sl0; q += nt) sbase[q] = (int) p.slice_off[sl0 + q];
+    __syncthreads();
+    if (tid == 0) {                                               // in slice order: deterministic
+        int n = 0;
+        for (int q = 0; q < sl1 - sl0; q++) {
+            const bool wide = ((sbase[q + 1] - sbase[q]) >> 5) > SMALL_WIDE && n < SMALL_MAX_WIDE;
+            isw[q] = wide;
+            if (wide) widelist[n++] = sl0 + q;
+        }
+        nwide = n;
+    }
+    cl.sync();
+    for (int h = 2 * e0 + tid; h < 2 * e1; h += nt) a.Ze[h] = __ldcg(Zg + __ldcg(a.pos + h));
+    for (int v = tid; v < V; v += nt) { Xs[v] = __ldcg(Xg + v); Ps[v] = __ldcg(Pg + v); Ts[v] = __ldcg(p.T + v); }
+    const real tol = (real) ctl->tol, rho = p.rho;
+    const double eps = ctl->eps;
+    double dif = ctl->dif, rcd = ctl->rcd;
+    bool per_slot = false;                           // thresholds per half-edge once reconditioned
+    int ph = 0;
+    const int *__restrict__ nbr = p.nbr;
+    __syncthreads();
+    SPROF_DECL
+    for (;;) {
+        const bool stop = (it == itMax || (real) dif < tol);                  // ref :429 (uniform over the cluster)
+        if (stop && !p.dObj) break;
+        SPROF(0)
+        // ---- forward point for dense operators (ref S1, S4, S6), own columns ----
+        if (N > 0) {
+            // partial A X: warp w walks the columns v0 + w, v0 + w + nw, ...; lanes along n
+            for (int n0 = 0; n0 < N; n0 += 32) {
+                const int n = n0 + lane;
+                if (n < N) {
+                    real acc = 0;
+#pragma unroll 4
+                    for (int v = v0 + wid; v < v1; v += nw) acc += __ldg(p.A + (size_t) N * v + n) * Xs[v];
+                    part[(size_t) wid * N + n] = acc;
+                }
+            }
+            __syncthreads();
+            for (int n = tid; n < N; n += nt) {
+                real acc = 0;
+                for (int w = 0; w < nw; w++) acc += part[(size_t) w * N + n];
+                a.parts[(size_t) rank * N + n] = acc;
+            }
+            cluster_bar();
+            for (int n = tid; n < N; n += nt) {
+                real acc = 0;
+                for (int q = 0; q < C; q++) acc += __ldcg(a.parts + (size_t) q * N + n);      // rank order: same bits everywhere
+                Rs[n] = p.Y[n] - acc;
+            }
+            __syncthreads();
+            // G = -A^t R: one warp per column, lanes along n
+            for (int v = v0 + wid; v < v1; v += nw) {
+                const real *col = p.A + (size_t) N * v;
+                real acc = 0;
+                for (int n = lane; n < N; n += 32) acc += __ldg(col + n) * Rs[n];
+                for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                if (lane == 0) { p.G[v] = -acc; Pg[v] = (real) 2 * Xs[v] - p.Ga[v] * (-acc); }
+            }
+        } else if (N < 0) {
+            // G = (A^tA) X: one warp per column;  P = 2X - Ga.(G - A^tY)
+            for (int v = v0 + wid; v < v1; v += nw) {
+                const real *col = p.A + (size_t) V * v;
+                real acc = 0;
+#pragma unroll 4
+                for (int u = lane; u < V; u += 32) acc += __ldg(col + u) * Xs[u];
+                for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                if (lane == 0) { p.G[v] = acc; Pg[v] = (real) 2 * Xs[v] - p.Ga[v] * (acc - p.Y[v]); }
+            }
+        }
+        SPROF(1)
+        if (N != 0) {
+            cluster_bar();
+            for (int v = tid; v < V; v += nt) Ps[v] = __ldcg(Pg + v);
+            __syncthreads();
+        }
+        SPROF(2)
+        // ---- objective of the current iterate (ref :388-422) ----
+        if (p.dObj) {
+            double o = 0.0, zero = 0.0;
+            for (int e = e0 + tid; e < e1; e += nt) o += (double) p.La_d1[e] * (double) rabs(Xs[p.Eu[e]] - Xs[p.Ev[e]]);
+            for (int v = v0 + tid; v < v1; v += nt) {
+                const real x = Xs[v];
+                if (N == 0) o += (double) x * ((double) 0.5 * (double) (p.A ? p.A[v] * x : x) - (double) p.Y[v]);
+                else if (N < 0) o += (double) x * ((double) 0.5 * (double) p.G[v] - (double) p.Y[v]);
+                if (p.La_l1) o += (double) p.La_l1[v] * (double) rabs(x);
+            }
+            if (N > 0 && rank == 0) for (int n = tid; n < N; n += nt) o += 0.5 * (double) Rs[n] * (double) Rs[n];
+            cluster_sum2<real>(cl, a.xs, ph, rank, C, o, zero, red);
+            if (rank == 0 && tid == 0) p.dObj[it] = (real) o;
+            if (stop) break;
+        }
+        // ---- reconditioning (ref :448-459): new amplitude constant, new metric, edge copies rebuilt ----
+        if ((real) dif < (real) rcd) {
+            double sa = 0.0, sn = 0.0;
+            for (int v = v0 + tid; v < v1; v += nt) {
+                const real x = Xs[v];
+                if (x != (real) 0) { sa += (double) rabs(x); sn += 1.0; }
+            }
+            cluster_sum2<real>(cl, a.xs, ph, rank, C, sa, sn, red);
+            const real c = (real) sa / (real) sn;
+            for (int v = v0 + tid; v < v1; v += nt) recond_vertex<real>(p, v, Xs, Zg, Pg, c);
+            per_slot = true;
+            rcd *= 0.01;
+            cl.sync();
+            for (int h = 2 * e0 + tid; h < 2 * e1; h += nt) a.Ze[h] = __ldcg(Zg + a.pos[h]);
+            for (int v = tid; v < V; v += nt) { Ps[v] = __ldcg(Pg + v); Ts[v] = __ldcg(p.T + v); }
+            __syncthreads();
+        }
+        // ---- edge prox + relaxation (ref S7, S8): both copies of an edge by one thread, EU edges in flight ----
+        for (int eb = e0 + tid; eb < e1; eb += EU * nt) {
+            int su[EU], sv[EU], u[EU], v[EU];
+            real zu[EU], zv[EU], thc[EU];
+#pragma unroll
+            for (int k = 0; k < EU; k++) {
+                const int e = eb + k * nt;
+                const bool in = e < e1;
+                const int2 ss = in ? *reinterpret_cast<const int2 *>(a.pos + 2 * e) : make_int2(0, 0);
+                su[k] = ss.x; sv[k] = ss.y;
+                u[k] = in ? __ldg(p.Eu + e) : 0; v[k] = in ? __ldg(p.Ev + e) : 0;
+                if (in) ld2(a.Ze + 2 * e, zu[k], zv[k]); else { zu[k] = 0; zv[k] = 0; }
+                thc[k] = (per_slot && in) ? p.thc[su[k]] : p.thc0;
+            }
+#pragma unroll
+            for (int k = 0; k < EU; k++) {
+                const int e = eb + k * nt;
+                if (e < e1) {
+                    const real Tu = Ts[u[k]], Tv = Ts[v[k]];
+                    const real tsum = Tu + Tv, inv = fast_rcp(tsum), th = thc[k] * tsum;
+                    const real wu = Tv * inv, wv = Tu * inv;     // W_d1 on the u side / on the v side
+                    const real pu = Ps[u[k]] - zu[k], pv = Ps[v[k]] - zv[k], d0 = pu - pv;
+                    const real b = d0 - min(max(d0, -th), th);   // soft threshold, exact 0 inside
+                    const real nu = zu[k] + rho * (fma(wu, d0, pv) + wv * b - Xs[u[k]]);
+                    const real nv = zv[k] + rho * (fma(wv, -d0, pu) + wu * (-b) - Xs[v[k]]);
+                    st2(a.Ze + 2 * e, nu, nv);
+                    Zg[su[k]] = nu; Zg[sv[k]] = nv;
+                }
+            }
+        }
+        SPROF(3)
+        cluster_bar();
+        SPROF(4)
+        // ---- average + vertex prox + evolution (ref S9, S10), own vertices ----
+        double sd = 0.0, sc = 0.0;
+        auto finish_vertex = [&](int v, real x, real xo) {
+            if (p.prox_kind == 0) {
+                if (p.La_l1) {
+                    const real th = p.Thl1[v];
+                    if (x > th) x -= th;
+                    else if (!p.positivity && x < -th) x += th;
+                    else x = 0;
+                } else if (p.positivity) { if (x < (real) 0) x = 0; }
+            } else {
+                if (p.has_lo && x < p.lo) x = p.lo;
+                else if (p.has_hi && x > p.hi) x = p.hi;
+            }
+            Xg[v] = x;
+            if (N == 0) Pg[v] = (real) 2 * x - p.Ga[v] * grad_at(p, v, x);
+            const real dx = xo - x;
+            sd += (double) (dx * dx); sc += (double) (x * x);
+        };
+        // (a) one thread per vertex, VU rows of its SELL column in flight, summed in the reference's order
+        for (int v = v0 + tid; v < v1; v += nt) {
+            const int sl = v >> 5;
+            if (isw[sl - sl0]) continue;                 // wide slice (a hub): all warps of the CTA, below
+            const int base = sbase[sl - sl0], width = (sbase[sl - sl0 + 1] - base) >> 5;
+            const int s = base + (v & 31);
+            const real Sv = p.Sinv[v];
+            real acc = 0;
+            for (int j0 = 0; j0 < width; j0 += VU) {
+                int nb[VU];
+                real ww[VU], zz[VU];
+#pragma unroll
+                for (int k = 0; k < VU; k++) {
+                    const bool in = j0 + k < width;
+                    const int sk = s + (j0 + k) * 32;
+                    nb[k] = in ? nbr[sk] : -1; ww[k] = in ? p.w[sk] : (real) 0; zz[k] = in ? __ldcg(Zg + sk) : (real) 0;
+                }
+#pragma unroll
+                for (int k = 0; k < VU; k++) if (nb[k] >= 0) acc += (ww[k] * Sv) * zz[k];
+            }
+            finish_vertex(v, acc, Xs[v]);
+        }
+        // (b) wide slices: warp w takes rows w, w + nw, ... of the slice (lanes = its 32 vertices), partial sums
+        //     folded through shared memory in warp order
+        for (int q = 0; q < nwide; q++) {
+            const int sl = widelist[q];
+            const int base = sbase[sl - sl0], width = (sbase[sl - sl0 + 1] - base) >> 5;
+            const int v = sl * 32 + lane;
+            const real Sv = v < V ? p.Sinv[v] : (real) 0;
+            real acc = 0;
+            for (int j0 = wid; j0 < width; j0 += VU * nw) {
+                int nb[VU];
+                real ww[VU], zz[VU];
+#pragma unroll
+                for (int k = 0; k < VU; k++) {
+                    const int j = j0 + k * nw;
+                    const bool in = j < width;
+                    const int sk = base + j * 32 + lane;
+                    nb[k] = in ? nbr[sk] : -1; ww[k] = in ? p.w[sk] : (real) 0; zz[k] = in ? __ldcg(Zg + sk) : (real) 0;
+                }
+#pragma unroll
+                for (int k = 0; k < VU; k++) if (nb[k] >= 0) acc += (ww[k] * Sv) * zz[k];
+            }
+            wpart[wid * 32 + lane] = acc;
+            __syncthreads();
+            if (wid == 0 && v < V) {
+                real t = 0;
+                for (int w = 0; w < nw; w++) t += wpart[w * 32 + lane];
+                finish_vertex(v, t, Xs[v]);
+            }
+            __syncthreads();
+        }
+        SPROF(5)
+        // ---- evolution sums over the cluster; the barrier publishes Xg / Pg; one L2 round trip refreshes the replicas ----
+        small_block_sum2<real>(sd, sc, red);
+        if (tid == 0) { a.xs[(ph * 16 + rank) * 2] = sd; a.xs[(ph * 16 + rank) * 2 + 1] = sc; }
+        cluster_bar();
+        SPROF(6)
+        {
+            double x = 0.0, y = 0.0;
+            if (tid < 32 && lane < C) { x = __ldcg(a.xs + (ph * 16 + lane) * 2); y = __ldcg(a.xs + (ph * 16 + lane) * 2 + 1); }
+            for (int v = tid; v < V; v += nt) { Xs[v] = __ldcg(Xg + v); if (N == 0) Ps[v] = __ldcg(Pg + v); }
+            if (tid < 32) {
+                x = warp_sum(x); y = warp_sum(y);
+                if (lane == 0) { red[0] = x; red[32] = y; }
+            }
+            __syncthreads();
+            sd = red[0]; sc = red[32];
+            ph ^= 1;
+        }
+        if (track) {
+            dif = (sc > eps) ? sd / sc : sd / eps;
+            if (rank == 0 && tid == 0 && p.dDif) p.dDif[it] = (real) dif;
+        }
+        it++;
+        SPROF(7)
+    }
+    SPROF_OUT
+    // the large path's readers (extract_x_kernel, a later run) look at the buffers of parity it & 1
+    for (int v = v0 + tid; v < v1; v += nt) { p.X1[v] = Xs[v]; p.P1[v] = Ps[v]; }
+    for (int s = s0 + tid; s < s1; s += nt) p.Z1[s] = __ldcg(Zg + s);
+    if (rank == 0 && tid == 0) { ctl->it = it; ctl->dif = dif; ctl->rcd = rcd; ctl->state = ST_FINAL; ctl->hold = 1; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Small-problem mode, push variant (the default when neither the objective record nor reconditioning is asked
+// for - the way cut-pursuit calls PFDR): same ownership and arithmetic as quad_small_kernel, but NOTHING crosses
+// CTAs through global memory inside the loop.  A cluster barrier with release/acquire costs a gpu-scope MEMBAR
+// plus an invalidation of the whole L1 (CCTL.IVALL), i.e. every constant of the iteration comes from L2 again.
+// Here every exchange is a push into the consumer's SHARED memory that completes a transaction count on the
+// consumer's mbarrier:
+//   * new edge copies:  st.async (4/8 bytes) to the SELL slot in the shared memory of the CTA that owns the vertex;
+//   * new iterate / forward point of the own vertices, partial A x: one bulk copy (cp.async.bulk shared::cta ->
+//     shared::cluster) per destination CTA;
+//   * evolution sums: one 16-byte st.async per destination CTA.
+// Consumers wait on their own mbarrier (try_wait.parity) - no fence, no L1 invalidation, constants stay in L1.
+// Replicas of X and P and the SELL-ordered edge copies are double-buffered by iteration parity (a CTA may be one
+// phase ahead of another); the old copy of an edge lives in an edge-ordered array private to the edge's owner.
+// ---------------------------------------------------------------------------------------------
+template <typename real>
+struct PushArgs {
+    int nslices, nso;  // nso: shared-memory slots per CTA for the own SELL rows (max over CTAs, multiple of 4)
+    int slb[17];       // slice range of CTA c: [slb[c], slb[c+1])
+    int *dst;          // [2E] (owner CTA << 24 | slot index inside the owner's range) of every half-edge key
+    real *Ze;          // [2E] edge copies in edge order
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *q) { return (uint32_t) __cvta_generic_to_shared(q); }
+__device__ __forceinline__ uint32_t map_rank(uint32_t addr, int rank)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_expect(uint32_t mbar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, int &phase)
+{
+    uint32_t ok = 0;
+    for (long long spin = 0; !ok; spin++) {
+        asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.b32 %0, 1, 0, P1;\n\t}"
+                     : "=r"(ok) : "r"(mbar), "r"(phase) : "memory");
+        if (spin > (1ll << 24)) __trap();            // seconds: a lost message must not hang the device
+    }
+    phase ^= 1;
+}
+__device__ __forceinline__ void push_val(uint32_t raddr, float v, uint32_t rmbar)
+{
+    asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(raddr), "r"(__float_as_uint(v)), "r"(rmbar) : "memory");
+}
+__device__ __forceinline__ void push_val(uint32_t raddr, double v, uint32_t rmbar)
+{
+    asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(raddr), "l"(__double_as_longlong(v)), "r"(rmbar) : "memory");
+}
+__device__ __forceinline__ void push_pair(uint32_t raddr, double a, double b, uint32_t rmbar)
+{
+    asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.v2.b64 [%0], {%1, %2}, [%3];" ::"r"(raddr), "l"(__double_as_longlong(a)),
+                 "l"(__double_as_longlong(b)), "r"(rmbar) : "memory");
+}
+__device__ __forceinline__ void push_bulk(uint32_t raddr, uint32_t laddr, uint32_t bytes, uint32_t rmbar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(raddr), "r"(laddr), "r"(bytes),
+                 "r"(rmbar) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <typename real>
+__global__ void __launch_bounds__(512, 1) quad_push_kernel(QP<real> p, PushArgs<real> a)
+{
+    extern __shared__ __align__(16) unsigned char push_smem[];
+    cg::cluster_group cl = cg::this_cluster();
+    Ctl *ctl = p.ctl;
+    const int C = (int) gridDim.x, rank = (int) blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5, nt = blockDim.x;
+    const int V = p.V, N = p.N, E = p.E, itMax = ctl->itMax, track = ctl->track;
+    const int Vq = a.nslices * 32, Nq = N > 0 ? ((N + 3) & ~3) : 0, nso = a.nso;
+    unsigned long long *mbars = reinterpret_cast<unsigned long long *>(push_smem);   // 0: Z, 1: X (+P, sums), 2: partial A x, 3: P (dense)
+    double *sums = reinterpret_cast<double *>(push_smem + 64);   // [16][2] evolution sums of the CTAs
+    double *red = sums + 32;                                     // [64]
+    real *Xs = reinterpret_cast<real *>(red + 64);               // [2][Vq] iterate         } replicas, by iteration parity
+    real *Ps = Xs + 2 * Vq;                                      // [2][Vq] forward point   }
+    real *Ts = Ps + 2 * Vq;                                      // [Vq]    Ga.S
+    real *Zs = Ts + Vq;                                          // [2][nso] new edge copies of the own SELL rows
+    real *partsS = Zs + 2 * nso;                                 // [16][Nq] partial A x of the CTAs
+    real *Rs = partsS + 16 * Nq;                                 // [Nq] residual
+    real *part = Rs + Nq;                                        // [nw][Nq] per-warp partial A x
+    __shared__ int sbase[SMALL_MAX_SLICES + 1];
+    __shared__ unsigned char isw[SMALL_MAX_SLICES];
+    __shared__ int widelist[SMALL_MAX_WIDE], nwide, s0r[17];
+    __shared__ real wpart[32 * 32];
+    constexpr int EU = 2, VU = 8;
+    const int sl0 = a.slb[rank], sl1 = a.slb[rank + 1];
+    const int v0 = sl0 * 32, v1 = min(V, sl1 * 32), v1q = sl1 * 32;
+    const int e0 = (int) ((long long) E * rank / C), e1 = (int) ((long long) E * (rank + 1) / C);
+    const uint32_t mb0 = smem_u32(mbars), mb1 = mb0 + 8, mb2 = mb0 + 16, mb3 = mb0 + 24;
+    int it = ctl->it;
+    if (tid <= C) s0r[tid] = (int) p.slice_off[a.slb[tid]];
+    for (int q = tid; q <= sl1 - sl0; q += nt) sbase[q] = (int) p.slice_off[sl0 + q];
+    if (tid == 0) {
+        for (int k = 0; k < 4; k++) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mb0 + 8 * k), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int s0 = s0r[rank], s1 = s0r[rank + 1];
+    if (tid == 0) {                                               // in slice order: deterministic
+        int n = 0;
+        for (int q = 0; q < sl1 - sl0; q++) {
+            const bool wide = ((sbase[q + 1] - sbase[q]) >> 5) > SMALL_WIDE && n < SMALL_MAX_WIDE;
+            isw[q] = wide;
+            if (wide) widelist[n++] = sl0 + q;
+        }
+        nwide = n;
+    }
+    {
+        const int cur = it & 1;                                  // this mode keeps its global state in the buffers of parity 0
+        if (cur) {
+            for (int v = v0 + tid; v < v1; v += nt) { p.X0[v] = p.X1[v]; p.P0[v] = p.P1[v]; }
+            for (int s = s0 + tid; s < s1; s += nt) p.Z0[s] = p.Z1[s];
+        }
+    }
+    double cnt = 0.0, zero = 0.0;
+    for (int s = s0 + tid; s < s1; s += nt) {
+        const int h = p.hkey[s];
+        if (h >= 0) { a.dst[h] = (rank << 24) | (s - s0); cnt += 1.0; }
+    }
+    small_block_sum2<real>(cnt, zero, red);
+    const uint32_t nz_own = (uint32_t) cnt;                      // half-edges whose copy lands in this CTA
+    cl.sync();                                                   // dst complete, mbarriers initialised everywhere
+    for (int h = 2 * e0 + tid; h < 2 * e1; h += nt) {
+        const int d = __ldcg(a.dst + h);
+        a.Ze[h] = __ldcg(p.Z0 + s0r[d >> 24] + (d & 0xffffff));
+    }
+    for (int v = tid; v < Vq; v += nt) {
+        const bool in = v < V;
+        Xs[v] = in ? __ldcg(p.X0 + v) : (real) 0; Ps[v] = in ? __ldcg(p.P0 + v) : (real) 0; Ts[v] = in ? p.T[v] : (real) 1;
+        Xs[Vq + v] = 0; Ps[Vq + v] = 0;
+    }
+    const real tol = (real) ctl->tol, rho = p.rho, thc0 = p.thc0;
+    const double eps = ctl->eps;
+    double dif = ctl->dif;
+    int phZ = 0, phX = 0, phA = 0, phP = 0, cb = 0;
+    const int it_start = it;
+    const int *__restrict__ nbr = p.nbr;
+    const uint32_t own_bytes = (uint32_t) ((v1q - v0) * sizeof(real)), all_bytes = (uint32_t) (Vq * sizeof(real));
+    __syncthreads();
+    SPROF_DECL
+    for (;;) {
+        if (it == itMax || (real) dif < tol) break;                           // ref :429 (uniform over the cluster)
+        const int nb = cb ^ 1, zb = it & 1;
+        real *Xc = Xs + cb * Vq, *Pc = Ps + cb * Vq, *Xn = Xs + nb * Vq, *Pn = Ps + nb * Vq, *Zc = Zs + zb * nso;
+        SPROF(0)
+        // ---- forward point for dense operators (ref S1, S4, S6), own columns ----
+        if (N != 0) {
+            if (N > 0) {
+                if (tid == 0) mbar_expect(mb2, (uint32_t) ((C - 1) * Nq * sizeof(real)));
+                for (int n0 = 0; n0 < N; n0 += 32) {
+                    const int n = n0 + lane;
+                    if (n < N) {
+                        real acc = 0;
+#pragma unroll 4
+                        for (int v = v0 + wid; v < v1; v += nw) acc += __ldg(p.A + (size_t) N * v + n) * Xc[v];
+                        part[wid * Nq + n] = acc;
+                    }
+                }
+                __syncthreads();
+                for (int n = tid; n < Nq; n += nt) {
+                    real acc = 0;
+                    if (n < N) for (int w = 0; w < nw; w++) acc += part[w * Nq + n];
+                    partsS[rank * Nq + n] = acc;
+                }
+                fence_async_smem();
+                __syncthreads();
+                if (tid < C && tid != rank)
+                    push_bulk(map_rank(smem_u32(partsS + rank * Nq), tid), smem_u32(partsS + rank * Nq), (uint32_t) (Nq * sizeof(real)), map_rank(mb2, tid));
+                mbar_wait(mb2, phA);
+                for (int n = tid; n < N; n += nt) {
+                    real acc = 0;
+                    for (int q = 0; q < C; q++) acc += partsS[q * Nq + n];                    // rank order: same bits everywhere
+                    Rs[n] = p.Y[n] - acc;
+                }
+                __syncthreads();
+            }
+            if (tid == 0) mbar_expect(mb3, all_bytes - own_bytes);
+            if (N > 0) {
+                for (int v = v0 + wid; v < v1; v += nw) {                                     // G = -A^t R, one warp per column
+                    const real *col = p.A + (size_t) N * v;
+                    real acc = 0;
+                    for (int n = lane; n < N; n += 32) acc += __ldg(col + n) * Rs[n];
+                    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                    if (lane == 0) Pc[v] = (real) 2 * Xc[v] - p.Ga[v] * (-acc);
+                }
+            } else {
+                for (int v = v0 + wid; v < v1; v += nw) {                                     // G = (A^tA) X
+                    const real *col = p.A + (size_t) V * v;
+                    real acc = 0;
+#pragma unroll 4
+                    for (int u = lane; u < V; u += 32) acc += __ldg(col + u) * Xc[u];
+                    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                    if (lane == 0) Pc[v] = (real) 2 * Xc[v] - p.Ga[v] * (acc - p.Y[v]);
+                }
+            }
+            fence_async_smem();
+            __syncthreads();
+            if (tid < C && tid != rank && own_bytes) push_bulk(map_rank(smem_u32(Pc + v0), tid), smem_u32(Pc + v0), own_bytes, map_rank(mb3, tid));
+            mbar_wait(mb3, phP);
+        }
+        SPROF(1)
+        // ---- edge prox + relaxation (ref S7, S8): both copies of an edge by one thread, pushed to the vertex owners ----
+        if (tid == 0) mbar_expect(mb0, nz_own * (uint32_t) sizeof(real));
+        const uint32_t zc0 = smem_u32(Zc);
+        for (int eb = e0 + tid; eb < e1; eb += EU * nt) {
+            int du[EU], dv[EU], u[EU], v[EU];
+            real zu[EU], zv[EU];
+#pragma unroll
+            for (int k = 0; k < EU; k++) {
+                const int e = eb + k * nt;
+                const bool in = e < e1;
+                const int2 dd = in ? *reinterpret_cast<const int2 *>(a.dst + 2 * e) : make_int2(0, 0);
+                du[k] = dd.x; dv[k] = dd.y;
+                u[k] = in ? __ldg(p.Eu + e) : 0; v[k] = in ? __ldg(p.Ev + e) : 0;
+                if (in) ld2(a.Ze + 2 * e, zu[k], zv[k]); else { zu[k] = 0; zv[k] = 0; }
+            }
+#pragma unroll
+            for (int k = 0; k < EU; k++) {
+                const int e = eb + k * nt;
+                if (e < e1) {
+                    const real Tu = Ts[u[k]], Tv = Ts[v[k]];
+                    const real tsum = Tu + Tv, inv = fast_rcp(tsum), th = thc0 * tsum;
+                    const real wu = Tv * inv, wv = Tu * inv;     // W_d1 on the u side / on the v side
+                    const real pu = Pc[u[k]] - zu[k], pv = Pc[v[k]] - zv[k], d0 = pu - pv;
+                    const real b = d0 - min(max(d0, -th), th);   // soft threshold, exact 0 inside
+                    const real nu = zu[k] + rho * (fma(wu, d0, pv) + wv * b - Xc[u[k]]);
+                    const real nv = zv[k] + rho * (fma(wv, -d0, pu) + wu * (-b) - Xc[v[k]]);
+                    st2(a.Ze + 2 * e, nu, nv);
+                    push_val(map_rank(zc0 + (uint32_t) ((du[k] & 0xffffff) * sizeof(real)), du[k] >> 24), nu, map_rank(mb0, du[k] >> 24));
+                    push_val(map_rank(zc0 + (uint32_t) ((dv[k] & 0xffffff) * sizeof(real)), dv[k] >> 24), nv, map_rank(mb0, dv[k] >> 24));
+                }
+            }
+        }
+        SPROF(2)
+        mbar_wait(mb0, phZ);
+        SPROF(3)
+        // ---- average + vertex prox + evolution (ref S9, S10), own vertices ----
+        if (tid == 0) mbar_expect(mb1, (all_bytes - own_bytes) * (N == 0 ? 2u : 1u) + (uint32_t) C * 16u);
+        double sd = 0.0, sc = 0.0;
+        auto finish_vertex = [&](int v, real x, real xo) {
+            if (p.prox_kind == 0) {
+                if (p.La_l1) {
+                    const real th = p.Thl1[v];
+                    if (x > th) x -= th;
+                    else if (!p.positivity && x < -th) x += th;
+                    else x = 0;
+                } else if (p.positivity) { if (x < (real) 0) x = 0; }
+            } else {
+                if (p.has_lo && x < p.lo) x = p.lo;
+                else if (p.has_hi && x > p.hi) x = p.hi;
+            }
+            Xn[v] = x;
+            if (N == 0) Pn[v] = (real) 2 * x - p.Ga[v] * grad_at(p, v, x);
+            const real dx = xo - x;
+            sd += (double) (dx * dx); sc += (double) (x * x);
+        };
+        for (int v = v0 + tid; v < v1; v += nt) {
+            const int sl = v >> 5;
+            if (isw[sl - sl0]) continue;                 // wide slice (a hub): all warps of the CTA, below
+            const int base = sbase[sl - sl0], width = (sbase[sl - sl0 + 1] - base) >> 5;
+            const int s = base + (v & 31);
+            const real Sv = p.Sinv[v];
+            real acc = 0;
+            for (int j0 = 0; j0 < width; j0 += VU) {
+                int nbk[VU];
+                real ww[VU], zz[VU];
+#pragma unroll
+                for (int k = 0; k < VU; k++) {
+                    const bool in = j0 + k < width;
+                    const int sk = s + (j0 + k) * 32;
+                    nbk[k] = in ? nbr[sk] : -1; ww[k] = in ? p.w[sk] : (real) 0; zz[k] = in ? Zc[sk - s0] : (real) 0;
+                }
+#pragma unroll
+                for (int k = 0; k < VU; k++) if (nbk[k] >= 0) acc += (ww[k] * Sv) * zz[k];
+            }
+            finish_vertex(v, acc, Xc[v]);
+        }
+        for (int q = 0; q < nwide; q++) {
+            const int sl = widelist[q];
+            const int base = sbase[sl - sl0], width = (sbase[sl - sl0 + 1] - base) >> 5;
+            const int v = sl * 32 + lane;
+            const real Sv = v < V ? p.Sinv[v] : (real) 0;
+            real acc = 0;
+            for (int j0 = wid; j0 < width; j0 += VU * nw) {
+                int nbk[VU];
+                real ww[VU], zz[VU];
+#pragma unroll
+                for (int k = 0; k < VU; k++) {
+                    const int j = j0 + k * nw;
+                    const bool in = j < width;
+                    const int sk = base + j * 32 + lane;
+                    nbk[k] = in ? nbr[sk] : -1; ww[k] = in ? p.w[sk] : (real) 0; zz[k] = in ? Zc[sk - s0] : (real) 0;
+                }
+#pragma unroll
+                for (int k = 0; k < VU; k++) if (nbk[k] >= 0) acc += (ww[k] * Sv) * zz[k];
+            }
+            wpart[wid * 32 + lane] = acc;
+            __syncthreads();
+            if (wid == 0 && v < V) {
+                real t = 0;
+                for (int w = 0; w < nw; w++) t += wpart[w * 32 + lane];
+                finish_vertex(v, t, Xc[v]);
+            }
+            __syncthreads();
+        }
+        SPROF(4)
+        // ---- publish: own chunk of the new iterate (and forward point) + evolution sums into every CTA ----
+        fence_async_smem();
+        small_block_sum2<real>(sd, sc, red);                                  // its barriers order the chunk writes
+        if (tid < C) {
+            if (tid != rank && own_bytes) {
+                push_bulk(map_rank(smem_u32(Xn + v0), tid), smem_u32(Xn + v0), own_bytes, map_rank(mb1, tid));
+                if (N == 0) push_bulk(map_rank(smem_u32(Pn + v0), tid), smem_u32(Pn + v0), own_bytes, map_rank(mb1, tid));
+            }
+            push_pair(map_rank(smem_u32(sums + 2 * rank), tid), sd, sc, map_rank(mb1, tid));
+        }
+        SPROF(5)
+        mbar_wait(mb1, phX);
+        SPROF(6)
+        if (track) {
+            double d = 0.0, c = 0.0;
+            for (int q = 0; q < C; q++) { d += sums[2 * q]; c += sums[2 * q + 1]; }           // rank order: same bits everywhere
+            dif = (c > eps) ? d / c : d / eps;
+            if (rank == 0 && tid == 0 && p.dDif) p.dDif[it] = (real) dif;
+        }
+        cb = nb;
+        it++;
+        SPROF(7)
+    }
+    SPROF_OUT
+    cl.sync();          // every CTA has received everything it was sent: outgoing copies are complete, peers may exit
+    // the large path's readers (extract_x_kernel, a later run) look at the buffers of parity it & 1
+    {
+        const real *Xc = Xs + cb * Vq, *Pc = Ps + cb * Vq;
+        for (int v = v0 + tid; v < v1; v += nt) {
+            p.X0[v] = Xc[v]; p.X1[v] = Xc[v];
+            if (N == 0) { p.P0[v] = Pc[v]; p.P1[v] = Pc[v]; }
+        }
+        if (it > it_start) {
+            const real *Zl = Zs + ((it - 1) & 1) * nso;
+            for (int s = s0 + tid; s < s1; s += nt) if (p.hkey[s] >= 0) { p.Z0[s] = Zl[s - s0]; p.Z1[s] = Zl[s - s0]; }
+        }
+    }
+    if (rank == 0 && tid == 0) { ctl->it = it; ctl->dif = dif; ctl->state = ST_FINAL; ctl->hold = 1; }
 }
 
 // Row-parallel variant: one thread per half-edge slot.  A CTA owns G slices (32 vertices each); warp (g, r)
@@ -796,6 +1526,9 @@ struct QuadSolver : SolverBase {
     DevIn<int> Eu, Ev;
     DevBuf<real> w, thc, Z0, Z1, X0b, X1b, P0b, P1b, T, Sinv, Ga, Ga0, G, Thl1, R, AtY, dObj, dDif, Xout;
     DevBuf<double> partial, parts, sums, rsum, amp_sums;
+    DevBuf<int> pos, dstb;          // small mode: slot / (owner CTA, slot) of every half-edge key
+    DevBuf<real> ze, sparts;        //             edge-ordered copies, partial A x of the CTAs
+    DevBuf<double> xsum;            //             partial sums of the CTAs
     Halo<real> halo;
     bool sharded = false;
     int ogrid = 0;                  // CTAs covering the owned vertices
@@ -1055,9 +1788,148 @@ struct QuadSolver : SolverBase {
         PFDR_LAUNCH(resume_kernel<real>, 1, 1, 0, p, 0.01);                   // ref :458
     }
 
+    // small-problem mode (quad_small_kernel): the whole solve in one launch of one thread-block cluster
+    size_t small_smem() const
+    {
+        const size_t Np = std::max(q.N, 0), Vp = ((size_t) q.V + 3) & ~(size_t) 3;
+        return 64 * sizeof(double) + (3 * Vp + ((Np + 3) & ~(size_t) 3) + 32 * Np) * sizeof(real);
+    }
+    bool small_mode() const
+    {
+        const char *e = getenv("PFDR_B200_SMALL");        // read per call: the tests switch it
+        if ((e && e[0] == '0') || sharded) return false;
+        const long long dense = q.N > 0 ? (long long) q.N * q.V : (q.N < 0 ? (long long) q.V * q.V : 0);
+        return small_smem() <= 200 * 1024 && g.nslices <= SMALL_MAX_SLICES && g.nslots <= (1 << 20) && q.E <= (1 << 19) && dense <= (1 << 22);
+    }
+
+    void run_small()
+    {
+        cudaStream_t st = ctx().stream;
+        static bool attr = false;
+        static int cmax = 8;
+        if (!attr) {
+            PFDR_CUDA(cudaFuncSetAttribute(quad_small_kernel<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            if (cudaFuncSetAttribute(quad_small_kernel<real>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) cmax = 16;
+            cudaGetLastError();
+            attr = true;
+        }
+        // CTAs of the cluster: enough that a CTA has about a thousand edges / vertices / matrix columns' worth of work
+        const long long dense = q.N > 0 ? (long long) q.N * q.V : (q.N < 0 ? (long long) q.V * q.V : 0);
+        const long long work = std::max<long long>(std::max<long long>(g.nslots, 2LL * q.E), dense / 16);
+        int C = 1;
+        while (C < cmax && work > 1024LL * C) C *= 2;
+        if (const char *e = getenv("PFDR_B200_SMALL_C")) C = std::max(1, std::min(cmax, atoi(e)));
+        SmallArgs<real> a{};
+        a.nslots = (int) g.nslots; a.nslices = (int) g.nslices;
+        pos.alloc(std::max<size_t>(2 * (size_t) q.E, 1));
+        ze.alloc(std::max<size_t>(2 * (size_t) q.E, 1));
+        xsum.alloc(64);
+        sparts.alloc(std::max<size_t>(16 * (size_t) std::max(q.N, 0), 1));
+        a.pos = pos.p; a.Ze = ze.p; a.xs = xsum.p; a.parts = sparts.p;
+        if (q.difRcd > (real) 0 && !thc.p) { thc.alloc(std::max<size_t>(g.nslots, 1)); thc.zero(); p.thc = thc.p; }
+        const size_t sm = small_smem();
+        ctx().in_loop = true;
+        PFDR_CUDA(cudaEventRecord(ev_b, st));
+        for (;; C /= 2) {
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3(C); cfg.blockDim = dim3(512); cfg.dynamicSmemBytes = sm; cfg.stream = st;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            const cudaError_t rc = cudaLaunchKernelEx(&cfg, quad_small_kernel<real>, p, a);
+            if (rc == cudaSuccess) break;
+            cudaGetLastError();
+            if (C == 1) PFDR_CUDA(rc);                       // a cluster this large may not be schedulable: halve it
+        }
+        ctx().count_launch();
+        PFDR_CUDA(cudaEventRecord(ev_c, st));
+        PFDR_CUDA(cudaMemcpyAsync(&hctl[0], ctl.p, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
+        PFDR_CUDA(cudaStreamSynchronize(st));
+        ctx().in_loop = false;
+        float ms = 0;
+        PFDR_CUDA(cudaEventElapsedTime(&ms, ev_b, ev_c));
+        ctx().stats.loop_ms = ms;
+        ctx().stats.iterations = hctl[0].it;
+    }
+
+    // push variant (quad_push_kernel): needs the slice offsets on the host to balance the CTAs and size their shared memory
+    bool run_push()
+    {
+        const char *e = getenv("PFDR_B200_PUSH");
+        if ((e && e[0] == '0') || q.Obj != nullptr || q.difRcd > (real) 0) return false;
+        cudaStream_t st = ctx().stream;
+        static bool attr = false;
+        static int cmax = 8;
+        if (!attr) {
+            PFDR_CUDA(cudaFuncSetAttribute(quad_push_kernel<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            if (cudaFuncSetAttribute(quad_push_kernel<real>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) cmax = 16;
+            cudaGetLastError();
+            attr = true;
+        }
+        const int S = g.nslices;
+        std::vector<long long> off((size_t) S + 1);
+        PFDR_CUDA(cudaMemcpyAsync(off.data(), g.slice_off.p, ((size_t) S + 1) * sizeof(long long), cudaMemcpyDeviceToHost, st));
+        PFDR_CUDA(cudaStreamSynchronize(st));
+        const long long dense = q.N > 0 ? (long long) q.N * q.V : (q.N < 0 ? (long long) q.V * q.V : 0);
+        const long long work = std::max<long long>(std::max<long long>(g.nslots, 2LL * q.E), dense / 16);
+        int C = 1;
+        while (C < cmax && work > 1024LL * C) C *= 2;
+        if (const char *ec = getenv("PFDR_B200_SMALL_C")) C = std::max(1, std::min(cmax, atoi(ec)));
+        const size_t Vq = (size_t) S * 32, Nq = q.N > 0 ? (((size_t) q.N + 3) & ~(size_t) 3) : 0;
+        for (;; C /= 2) {
+            // slices to CTAs, balanced by slots (a hub slice is as heavy as many ordinary ones)
+            PushArgs<real> a{};
+            a.nslices = S;
+            long long nso = 0;
+            a.slb[0] = 0;
+            for (int c = 1, sl = 0; c <= C; c++) {
+                const long long target = off[S] * c / C;
+                while (sl < S && off[sl + 1] <= target) sl++;
+                if (c == C) sl = S;
+                a.slb[c] = std::max(sl, a.slb[c - 1]);
+                nso = std::max(nso, off[a.slb[c]] - off[a.slb[c - 1]]);
+            }
+            for (int c = C + 1; c <= 16; c++) a.slb[c] = S;
+            a.nso = (int) ((nso + 3) & ~3LL);
+            const size_t sm = 64 + 256 + 512 + (5 * Vq + 2 * (size_t) a.nso + 17 * Nq + 16 * Nq) * sizeof(real);
+            bool fits = sm <= 200 * 1024;
+            for (int c = 0; c < C; c++) fits = fits && a.slb[c + 1] - a.slb[c] <= SMALL_MAX_SLICES;
+            if (fits) {
+                dstb.alloc(std::max<size_t>(2 * (size_t) q.E, 2));
+                ze.alloc(std::max<size_t>(2 * (size_t) q.E, 2));
+                a.dst = dstb.p; a.Ze = ze.p;
+                cudaLaunchConfig_t cfg{};
+                cfg.gridDim = dim3(C); cfg.blockDim = dim3(512); cfg.dynamicSmemBytes = sm; cfg.stream = st;
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeClusterDimension;
+                at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+                cfg.attrs = at; cfg.numAttrs = 1;
+                ctx().in_loop = true;
+                PFDR_CUDA(cudaEventRecord(ev_b, st));
+                const cudaError_t rc = cudaLaunchKernelEx(&cfg, quad_push_kernel<real>, p, a);
+                if (rc == cudaSuccess) break;
+                cudaGetLastError();
+                ctx().in_loop = false;
+                if (C == 1) return false;                    // a cluster this large may not be schedulable: halve it
+            } else if (C == 1) return false;                 // does not fit the shared memory of one CTA either
+        }
+        ctx().count_launch();
+        PFDR_CUDA(cudaEventRecord(ev_c, st));
+        PFDR_CUDA(cudaMemcpyAsync(&hctl[0], ctl.p, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
+        PFDR_CUDA(cudaStreamSynchronize(st));
+        ctx().in_loop = false;
+        float ms = 0;
+        PFDR_CUDA(cudaEventElapsedTime(&ms, ev_b, ev_c));
+        ctx().stats.loop_ms = ms;
+        ctx().stats.iterations = hctl[0].it;
+        return true;
+    }
+
     void run() override
     {
         cudaStream_t st = ctx().stream;
+        if (small_mode()) { if (!run_push()) run_small(); return; }
         // batch: enough trips per host round trip to hide it, small enough to bound the no-op tail
         const size_t work = (size_t) g.nslots + (size_t) q.V + (size_t) std::abs((double) q.N) * q.V;
         int batch = work > (1u << 24) ? 4 : (work > (1u << 20) ? 16 : 64);
@@ -1148,10 +2020,23 @@ template SolverBase *make_quadratic<double>(const QuadProblem<double> &);
 template <typename real>
 void solve_quadratic(const QuadProblem<real> &q)
 {
+    const bool trace = getenv("PFDR_B200_TRACE") != nullptr;      // one line per call on stderr (who spends what inside cut-pursuit)
+    const auto t0 = std::chrono::steady_clock::now();
     QuadSolver<real> s(q, false);
     s.setup();
+    const auto t1 = std::chrono::steady_clock::now();
     s.run();
+    const auto t2 = std::chrono::steady_clock::now();
     s.fetch(q.X, q.it, q.Obj, q.Dif);
+    if (trace) {
+        const auto t3 = std::chrono::steady_clock::now();
+        auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+            return std::chrono::duration<double, std::milli>(b - a).count();
+        };
+        fprintf(stderr, "[pfdr_b200] quadratic V=%d E=%d N=%d f%d: %d it, setup %.2f ms, run %.2f ms (device loop %.2f ms, %s), fetch %.2f ms\n",
+                q.V, q.E, q.N, (int) sizeof(real) * 8, (int) ctx().stats.iterations, ms(t0, t1), ms(t1, t2), ctx().stats.loop_ms,
+                s.small_mode() ? "cluster kernel" : "large path", ms(t2, t3));
+    }
 }
 
 template void solve_quadratic<float>(const QuadProblem<float> &);

@@ -103,8 +103,9 @@ QUAD_CASES = ["grid_identity", "grid_diag", "grid_diag_l1_pos", "grid_diag_l1", 
               "dense_direct_recond", "dense_ata", "dense_ata_odd", "dense_ata_box", "dense_ata_recond"]
 
 
-def run_quad(binder, name, dtype):
+def run_quad(binder, name, dtype, **override):
     fam, args, kw = quad_case(name, dtype)
+    kw.update(override)
     args = tuple(a.copy() if isinstance(a, np.ndarray) else a for a in args)
     f = binder.PFDR_graph_quadratic_d1_l1 if fam == "l1" else binder.PFDR_graph_quadratic_d1_bounds
     return f(*args, **kw)

@@ -13,10 +13,16 @@ def rel(a, b):
     return float(np.linalg.norm(a.astype(np.float64) - b) / max(float(np.linalg.norm(b)), 1e-300))
 
 
+@pytest.mark.parametrize("mode", ["large", "small", "small_c1", "small_c16"])
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 @pytest.mark.parametrize("name", problems.QUAD_CASES)
-def test_quadratic_parity(gpu_api, oracle, name, dtype):
+def test_quadratic_parity(gpu_api, oracle, monkeypatch, name, dtype, mode):
+    """mode "small": problems that fit run as ONE launch of the single-CTA persistent kernel (the path the
+    cut-pursuit reduced problems take); mode "large": always the one-kernel-per-iteration path"""
     from cp_pfdr_graph_d1_b200.api import _b
+    monkeypatch.setenv("PFDR_B200_SMALL", "0" if mode == "large" else "1")
+    if "_c" in mode:
+        monkeypatch.setenv("PFDR_B200_SMALL_C", mode.split("_c")[1])      # CTAs of the cluster (default: by size)
     got = problems.run_quad(_b(), name, dtype)
     ref = problems.run_quad(oracle, name, dtype)
     tol = TOL[dtype]
@@ -46,6 +52,47 @@ def test_exact_zeros_and_bounds(gpu_api, dtype):
     assert (r.X >= 0).all() and (r.X == 0).sum() > 100
     r = problems.run_quad(_b(), "grid_diag_box2", dtype)
     assert r.X.min() == dtype(0.5) and r.X.max() == dtype(2.5)
+
+
+@pytest.mark.parametrize("csize", ["auto", "1", "2", "16"])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("name", [n for n in problems.QUAD_CASES if "recond" not in n])
+def test_quadratic_parity_push(gpu_api, oracle, monkeypatch, name, dtype, csize):
+    """the way cut-pursuit calls PFDR (no objective record, no reconditioning) small problems run in the push
+    kernel: one launch of a thread-block cluster, CTAs exchanging through distributed shared memory"""
+    from cp_pfdr_graph_d1_b200.api import _b
+    monkeypatch.setenv("PFDR_B200_SMALL", "1")
+    if csize != "auto":
+        monkeypatch.setenv("PFDR_B200_SMALL_C", csize)
+    got = problems.run_quad(_b(), name, dtype, want_obj=False)
+    st = gpu_api.last_stats()
+    ref = problems.run_quad(oracle, name, dtype, want_obj=False)
+    tol = TOL[dtype]
+    slack = 0 if dtype is np.float64 else max(2, ref.it // 50)
+    assert st["loop_launches"] == 1 or ref.it == 0, st
+    assert abs(got.it - ref.it) <= slack, (got.it, ref.it)
+    assert rel(got.X, ref.X) < tol, rel(got.X, ref.X)
+    n = min(got.it, ref.it)
+    if ref.Dif is not None and n:
+        assert got.Dif.shape[0] == got.it
+        sel = ref.Dif[:n] > (1e-9 if dtype is np.float32 else 1e-24)
+        assert np.allclose(got.Dif[:n][sel], ref.Dif[:n][sel], rtol=5e-2 if dtype is np.float32 else 1e-4)
+
+
+@pytest.mark.parametrize("name", ["grid_diag", "dense_direct", "dense_ata_box"])
+def test_small_mode_is_one_launch(gpu_api, monkeypatch, name):
+    """small reduced problems (cut-pursuit) must not pay one launch per iteration"""
+    from cp_pfdr_graph_d1_b200.api import _b
+    if name not in problems.QUAD_CASES:
+        pytest.skip("no such case")
+    monkeypatch.setenv("PFDR_B200_SMALL", "1")
+    r = problems.run_quad(_b(), name, np.float64)
+    st = gpu_api.last_stats()
+    assert r.it > 1 and st["loop_launches"] == 1, st
+    monkeypatch.setenv("PFDR_B200_SMALL", "0")
+    r2 = problems.run_quad(_b(), name, np.float64)
+    assert gpu_api.last_stats()["loop_launches"] >= r2.it
+    assert abs(r.it - r2.it) <= 1 and rel(r.X, r2.X) < 1e-9
 
 
 def test_deterministic(gpu_api):
