@@ -47,6 +47,45 @@ struct Context {
 };
 Context &ctx();
 
+// Pinned control-block mirrors and events are recycled per host thread (and device): creating them costs a
+// large part of a millisecond per solve, and cut-pursuit calls the one-shot entry points once per outer iteration.
+struct HostCache {
+    int device = -1;
+    std::vector<void *> pinned;        // blocks of PINNED_BLOCK bytes
+    std::vector<cudaEvent_t> events;
+};
+constexpr size_t PINNED_BLOCK = 512;
+inline HostCache &host_cache()
+{
+    static thread_local HostCache c;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (c.device != dev) {             // different device: drop what belonged to the other one
+        for (void *q : c.pinned) cudaFreeHost(q);
+        for (cudaEvent_t e : c.events) cudaEventDestroy(e);
+        c.pinned.clear(); c.events.clear(); c.device = dev;
+    }
+    return c;
+}
+inline void *pinned_get()
+{
+    HostCache &c = host_cache();
+    void *q = nullptr;
+    if (!c.pinned.empty()) { q = c.pinned.back(); c.pinned.pop_back(); return q; }
+    PFDR_CUDA(cudaMallocHost(&q, PINNED_BLOCK));
+    return q;
+}
+inline void pinned_put(void *q) { if (q) host_cache().pinned.push_back(q); }
+inline cudaEvent_t event_get()
+{
+    HostCache &c = host_cache();
+    cudaEvent_t e = nullptr;
+    if (!c.events.empty()) { e = c.events.back(); c.events.pop_back(); return e; }
+    PFDR_CUDA(cudaEventCreate(&e));
+    return e;
+}
+inline void event_put(cudaEvent_t e) { if (e) host_cache().events.push_back(e); }
+
 #define PFDR_LAUNCH(kernel, grid, block, smem, ...)                                            \
     do {                                                                                       \
         kernel<<<(grid), (block), (smem), ::pfdr::ctx().stream>>>(__VA_ARGS__);                \

@@ -469,10 +469,17 @@ __global__ void __launch_bounds__(256, MINB) quad_iter_pipe_kernel(QP<real> p)
 #define SPROF_DECL long long spt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, spc = clock64();
 #define SPROF(k) { const long long t_ = clock64(); spt[k] += t_ - spc; spc = t_; }
 #define SPROF_OUT if (rank == 0 && tid == 0) { for (int k = 0; k < 8; k++) printf("phase %d: %.3f us/it\n", k, (double) spt[k] / 1.9e3 / (it > 0 ? it : 1)); }
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define GSTAMP(k) if (tid == 0 && it == itMax - 2) gst[k] = gtime();
+#define GSTAMP_DECL unsigned long long gst[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define GSTAMP_OUT if (tid == 0) printf("rank %d: edge0 %llu zpush %llu zwait %llu vertex %llu pub %llu xwait %llu\n", rank, gst[0] % 1000000, gst[1] % 1000000, gst[2] % 1000000, gst[3] % 1000000, gst[4] % 1000000, gst[5] % 1000000);
 #else
 #define SPROF_DECL
 #define SPROF(k)
 #define SPROF_OUT
+#define GSTAMP(k)
+#define GSTAMP_DECL
+#define GSTAMP_OUT
 #endif
 
 constexpr int SMALL_MAX_SLICES = 1024;   // slices a CTA may own (32768 vertices)
@@ -842,6 +849,7 @@ struct PushArgs {
     int slb[17];       // slice range of CTA c: [slb[c], slb[c+1])
     int *dst;          // [2E] (owner CTA << 24 | slot index inside the owner's range) of every half-edge key
     real *Ze;          // [2E] edge copies in edge order
+    real *wS;          // [nslots] w / S of the slot's vertex, 0 on padding
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *q) { return (uint32_t) __cvta_generic_to_shared(q); }
@@ -883,6 +891,18 @@ __device__ __forceinline__ void push_bulk(uint32_t raddr, uint32_t laddr, uint32
     asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(raddr), "r"(laddr), "r"(bytes),
                  "r"(rmbar) : "memory");
 }
+// 16 bytes of the own shared memory (src, 16-byte aligned) to the same offset in every other CTA of the cluster
+__device__ __forceinline__ void push_chunks(const void *src, uint32_t bytes, int rank, int C, uint32_t mbar)
+{
+    const uint32_t base = smem_u32(src), nch = bytes >> 4, total = nch * (uint32_t) (C - 1);
+    for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
+        const uint32_t d = i / nch, ch = i - d * nch;
+        const int dest = (int) d < rank ? (int) d : (int) d + 1;
+        const uint4 v = *reinterpret_cast<const uint4 *>(reinterpret_cast<const unsigned char *>(src) + 16 * ch);
+        asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(map_rank(base + 16 * ch, dest)),
+                     "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(map_rank(mbar, dest)) : "memory");
+    }
+}
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 template <typename real>
@@ -909,7 +929,7 @@ __global__ void __launch_bounds__(512, 1) quad_push_kernel(QP<real> p, PushArgs<
     __shared__ unsigned char isw[SMALL_MAX_SLICES];
     __shared__ int widelist[SMALL_MAX_WIDE], nwide, s0r[17];
     __shared__ real wpart[32 * 32];
-    constexpr int EU = 2, VU = 8;
+    constexpr int EU = 2;
     const int sl0 = a.slb[rank], sl1 = a.slb[rank + 1];
     const int v0 = sl0 * 32, v1 = min(V, sl1 * 32), v1q = sl1 * 32;
     const int e0 = (int) ((long long) E * rank / C), e1 = (int) ((long long) E * (rank + 1) / C);
@@ -944,6 +964,18 @@ __global__ void __launch_bounds__(512, 1) quad_push_kernel(QP<real> p, PushArgs<
         const int h = p.hkey[s];
         if (h >= 0) { a.dst[h] = (rank << 24) | (s - s0); cnt += 1.0; }
     }
+    for (int v = v0 + tid; v < v1; v += nt) {                    // w/S per own slot: constant without reconditioning
+        const int base = sbase[(v >> 5) - sl0], width = (sbase[(v >> 5) - sl0 + 1] - base) >> 5;
+        const real Sv = p.Sinv[v];
+        for (int j = 0; j < width; j++) {
+            const int sk = base + j * 32 + (v & 31);
+            a.wS[sk] = p.nbr[sk] >= 0 ? p.w[sk] * Sv : (real) 0;
+        }
+    }
+    for (int v = v1 + tid; v < v1q; v += nt) {                   // lanes past V in the last slice
+        const int base = sbase[(v >> 5) - sl0], width = (sbase[(v >> 5) - sl0 + 1] - base) >> 5;
+        for (int j = 0; j < width; j++) a.wS[base + j * 32 + (v & 31)] = 0;
+    }
     small_block_sum2<real>(cnt, zero, red);
     const uint32_t nz_own = (uint32_t) cnt;                      // half-edges whose copy lands in this CTA
     cl.sync();                                                   // dst complete, mbarriers initialised everywhere
@@ -965,6 +997,7 @@ __global__ void __launch_bounds__(512, 1) quad_push_kernel(QP<real> p, PushArgs<
     const uint32_t own_bytes = (uint32_t) ((v1q - v0) * sizeof(real)), all_bytes = (uint32_t) (Vq * sizeof(real));
     __syncthreads();
     SPROF_DECL
+    GSTAMP_DECL
     for (;;) {
         if (it == itMax || (real) dif < tol) break;                           // ref :429 (uniform over the cluster)
         const int nb = cb ^ 1, zb = it & 1;
@@ -972,27 +1005,25 @@ __global__ void __launch_bounds__(512, 1) quad_push_kernel(QP<real> p, PushArgs<
         SPROF(0)
         // ---- forward point for dense operators (ref S1, S4, S6), own columns ----
         if (N != 0) {
+            constexpr int GL = 8;                                             // lanes per column in the transposed products
             if (N > 0) {
+                // partial A X over the own columns: G threads per observation n, folded by shuffles
                 if (tid == 0) mbar_expect(mb2, (uint32_t) ((C - 1) * Nq * sizeof(real)));
-                for (int n0 = 0; n0 < N; n0 += 32) {
-                    const int n = n0 + lane;
-                    if (n < N) {
-                        real acc = 0;
-#pragma unroll 4
-                        for (int v = v0 + wid; v < v1; v += nw) acc += __ldg(p.A + (size_t) N * v + n) * Xc[v];
-                        part[wid * Nq + n] = acc;
-                    }
-                }
-                __syncthreads();
-                for (int n = tid; n < Nq; n += nt) {
+                int G = 1;
+                while (G < 32 && 2 * G * N <= nt) G *= 2;
+                const int g = tid & (G - 1);
+                for (int n0 = 0; n0 < N; n0 += nt / G) {                      // uniform trip count: shuffles below
+                    const int n = n0 + tid / G;
                     real acc = 0;
-                    if (n < N) for (int w = 0; w < nw; w++) acc += part[w * Nq + n];
-                    partsS[rank * Nq + n] = acc;
+                    if (n < N) {
+#pragma unroll 4
+                        for (int v = v0 + g; v < v1; v += G) acc += __ldg(p.A + (size_t) N * v + n) * Xc[v];
+                    }
+                    for (int o = G >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                    if (n < N && g == 0) partsS[rank * Nq + n] = acc;
                 }
-                fence_async_smem();
                 __syncthreads();
-                if (tid < C && tid != rank)
-                    push_bulk(map_rank(smem_u32(partsS + rank * Nq), tid), smem_u32(partsS + rank * Nq), (uint32_t) (Nq * sizeof(real)), map_rank(mb2, tid));
+                push_chunks(partsS + rank * Nq, (uint32_t) (Nq * sizeof(real)), rank, C, mb2);
                 mbar_wait(mb2, phA);
                 for (int n = tid; n < N; n += nt) {
                     real acc = 0;
@@ -1002,30 +1033,26 @@ __global__ void __launch_bounds__(512, 1) quad_push_kernel(QP<real> p, PushArgs<
                 __syncthreads();
             }
             if (tid == 0) mbar_expect(mb3, all_bytes - own_bytes);
-            if (N > 0) {
-                for (int v = v0 + wid; v < v1; v += nw) {                                     // G = -A^t R, one warp per column
-                    const real *col = p.A + (size_t) N * v;
-                    real acc = 0;
-                    for (int n = lane; n < N; n += 32) acc += __ldg(col + n) * Rs[n];
-                    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-                    if (lane == 0) Pc[v] = (real) 2 * Xc[v] - p.Ga[v] * (-acc);
-                }
-            } else {
-                for (int v = v0 + wid; v < v1; v += nw) {                                     // G = (A^tA) X
-                    const real *col = p.A + (size_t) V * v;
-                    real acc = 0;
+            // G = -A^t R  |  G = (A^tA) X - A^tY : GL lanes per own column
+            const int M = N > 0 ? N : V;
+            const real *rhs = N > 0 ? Rs : Xc;
+            for (int c0 = v0; c0 < v1; c0 += nt / GL) {                       // uniform trip count
+                const int v = c0 + tid / GL, gl = tid & (GL - 1);
+                real acc = 0;
+                if (v < v1) {
+                    const real *col = p.A + (size_t) M * v;
 #pragma unroll 4
-                    for (int u = lane; u < V; u += 32) acc += __ldg(col + u) * Xc[u];
-                    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-                    if (lane == 0) Pc[v] = (real) 2 * Xc[v] - p.Ga[v] * (acc - p.Y[v]);
+                    for (int m = gl; m < M; m += GL) acc += __ldg(col + m) * rhs[m];
                 }
+                for (int o = GL >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                if (v < v1 && gl == 0) Pc[v] = (real) 2 * Xc[v] - p.Ga[v] * (N > 0 ? -acc : acc - p.Y[v]);
             }
-            fence_async_smem();
             __syncthreads();
-            if (tid < C && tid != rank && own_bytes) push_bulk(map_rank(smem_u32(Pc + v0), tid), smem_u32(Pc + v0), own_bytes, map_rank(mb3, tid));
+            push_chunks(Pc + v0, own_bytes, rank, C, mb3);
             mbar_wait(mb3, phP);
         }
         SPROF(1)
+        GSTAMP(0)
         // ---- edge prox + relaxation (ref S7, S8): both copies of an edge by one thread, pushed to the vertex owners ----
         if (tid == 0) mbar_expect(mb0, nz_own * (uint32_t) sizeof(real));
         const uint32_t zc0 = smem_u32(Zc);
@@ -1059,8 +1086,10 @@ __global__ void __launch_bounds__(512, 1) quad_push_kernel(QP<real> p, PushArgs<
             }
         }
         SPROF(2)
+        GSTAMP(1)
         mbar_wait(mb0, phZ);
         SPROF(3)
+        GSTAMP(2)
         // ---- average + vertex prox + evolution (ref S9, S10), own vertices ----
         if (tid == 0) mbar_expect(mb1, (all_bytes - own_bytes) * (N == 0 ? 2u : 1u) + (uint32_t) C * 16u);
         double sd = 0.0, sc = 0.0;
@@ -1081,46 +1110,31 @@ __global__ void __launch_bounds__(512, 1) quad_push_kernel(QP<real> p, PushArgs<
             const real dx = xo - x;
             sd += (double) (dx * dx); sc += (double) (x * x);
         };
+        // stage 1: every own slot times its constant weight w/S (0 on padding), all threads, coalesced
+        for (int i = tid; i < s1 - s0; i += nt) {
+            const real c = a.wS[s0 + i];
+            Zc[i] = c != (real) 0 ? c * Zc[i] : (real) 0;
+        }
+        __syncthreads();
+        // stage 2: column sums in the reference's order (adding the zeros of the padding changes nothing)
         for (int v = v0 + tid; v < v1; v += nt) {
             const int sl = v >> 5;
             if (isw[sl - sl0]) continue;                 // wide slice (a hub): all warps of the CTA, below
             const int base = sbase[sl - sl0], width = (sbase[sl - sl0 + 1] - base) >> 5;
-            const int s = base + (v & 31);
-            const real Sv = p.Sinv[v];
+            const real *col = Zc + (base - s0) + (v & 31);
             real acc = 0;
-            for (int j0 = 0; j0 < width; j0 += VU) {
-                int nbk[VU];
-                real ww[VU], zz[VU];
-#pragma unroll
-                for (int k = 0; k < VU; k++) {
-                    const bool in = j0 + k < width;
-                    const int sk = s + (j0 + k) * 32;
-                    nbk[k] = in ? nbr[sk] : -1; ww[k] = in ? p.w[sk] : (real) 0; zz[k] = in ? Zc[sk - s0] : (real) 0;
-                }
-#pragma unroll
-                for (int k = 0; k < VU; k++) if (nbk[k] >= 0) acc += (ww[k] * Sv) * zz[k];
-            }
+#pragma unroll 8
+            for (int j = 0; j < width; j++) acc += col[j * 32];
             finish_vertex(v, acc, Xc[v]);
         }
         for (int q = 0; q < nwide; q++) {
             const int sl = widelist[q];
             const int base = sbase[sl - sl0], width = (sbase[sl - sl0 + 1] - base) >> 5;
             const int v = sl * 32 + lane;
-            const real Sv = v < V ? p.Sinv[v] : (real) 0;
+            const real *col = Zc + (base - s0) + lane;
             real acc = 0;
-            for (int j0 = wid; j0 < width; j0 += VU * nw) {
-                int nbk[VU];
-                real ww[VU], zz[VU];
-#pragma unroll
-                for (int k = 0; k < VU; k++) {
-                    const int j = j0 + k * nw;
-                    const bool in = j < width;
-                    const int sk = base + j * 32 + lane;
-                    nbk[k] = in ? nbr[sk] : -1; ww[k] = in ? p.w[sk] : (real) 0; zz[k] = in ? Zc[sk - s0] : (real) 0;
-                }
-#pragma unroll
-                for (int k = 0; k < VU; k++) if (nbk[k] >= 0) acc += (ww[k] * Sv) * zz[k];
-            }
+#pragma unroll 4
+            for (int j = wid; j < width; j += nw) acc += col[j * 32];
             wpart[wid * 32 + lane] = acc;
             __syncthreads();
             if (wid == 0 && v < V) {
@@ -1131,19 +1145,26 @@ __global__ void __launch_bounds__(512, 1) quad_push_kernel(QP<real> p, PushArgs<
             __syncthreads();
         }
         SPROF(4)
+        GSTAMP(3)
         // ---- publish: own chunk of the new iterate (and forward point) + evolution sums into every CTA ----
-        fence_async_smem();
-        small_block_sum2<real>(sd, sc, red);                                  // its barriers order the chunk writes
-        if (tid < C) {
-            if (tid != rank && own_bytes) {
-                push_bulk(map_rank(smem_u32(Xn + v0), tid), smem_u32(Xn + v0), own_bytes, map_rank(mb1, tid));
-                if (N == 0) push_bulk(map_rank(smem_u32(Pn + v0), tid), smem_u32(Pn + v0), own_bytes, map_rank(mb1, tid));
+        {
+            double *rb = red + (it & 1) * 32;                                 // by iteration parity: one barrier is enough
+            sd = warp_sum(sd); sc = warp_sum(sc);
+            if (lane == 0) { rb[2 * wid] = sd; rb[2 * wid + 1] = sc; }
+            __syncthreads();                                                  // also orders the chunk writes above
+            if (tid < C) {
+                double d = 0.0, c = 0.0;
+                for (int w = 0; w < nw; w++) { d += rb[2 * w]; c += rb[2 * w + 1]; }
+                push_pair(map_rank(smem_u32(sums + 2 * rank), tid), d, c, map_rank(mb1, tid));
             }
-            push_pair(map_rank(smem_u32(sums + 2 * rank), tid), sd, sc, map_rank(mb1, tid));
+            push_chunks(Xn + v0, own_bytes, rank, C, mb1);
+            if (N == 0) push_chunks(Pn + v0, own_bytes, rank, C, mb1);
         }
         SPROF(5)
+        GSTAMP(4)
         mbar_wait(mb1, phX);
         SPROF(6)
+        GSTAMP(5)
         if (track) {
             double d = 0.0, c = 0.0;
             for (int q = 0; q < C; q++) { d += sums[2 * q]; c += sums[2 * q + 1]; }           // rank order: same bits everywhere
@@ -1155,6 +1176,7 @@ __global__ void __launch_bounds__(512, 1) quad_push_kernel(QP<real> p, PushArgs<
         SPROF(7)
     }
     SPROF_OUT
+    GSTAMP_OUT
     cl.sync();          // every CTA has received everything it was sent: outgoing copies are complete, peers may exit
     // the large path's readers (extract_x_kernel, a later run) look at the buffers of parity it & 1
     {
@@ -1163,10 +1185,12 @@ __global__ void __launch_bounds__(512, 1) quad_push_kernel(QP<real> p, PushArgs<
             p.X0[v] = Xc[v]; p.X1[v] = Xc[v];
             if (N == 0) { p.P0[v] = Pc[v]; p.P1[v] = Pc[v]; }
         }
-        if (it > it_start) {
-            const real *Zl = Zs + ((it - 1) & 1) * nso;
-            for (int s = s0 + tid; s < s1; s += nt) if (p.hkey[s] >= 0) { p.Z0[s] = Zl[s - s0]; p.Z1[s] = Zl[s - s0]; }
-        }
+        if (it > it_start)
+            for (int h = 2 * e0 + tid; h < 2 * e1; h += nt) {
+                const int d = a.dst[h];
+                const real z = a.Ze[h];
+                p.Z0[s0r[d >> 24] + (d & 0xffffff)] = z; p.Z1[s0r[d >> 24] + (d & 0xffffff)] = z;
+            }
     }
     if (rank == 0 && tid == 0) { ctl->it = it; ctl->dif = dif; ctl->state = ST_FINAL; ctl->hold = 1; }
 }
@@ -1527,7 +1551,7 @@ struct QuadSolver : SolverBase {
     DevBuf<real> w, thc, Z0, Z1, X0b, X1b, P0b, P1b, T, Sinv, Ga, Ga0, G, Thl1, R, AtY, dObj, dDif, Xout;
     DevBuf<double> partial, parts, sums, rsum, amp_sums;
     DevBuf<int> pos, dstb;          // small mode: slot / (owner CTA, slot) of every half-edge key
-    DevBuf<real> ze, sparts;        //             edge-ordered copies, partial A x of the CTAs
+    DevBuf<real> ze, sparts, ws;        //             edge-ordered copies, partial A x of the CTAs
     DevBuf<double> xsum;            //             partial sums of the CTAs
     Halo<real> halo;
     bool sharded = false;
@@ -1543,8 +1567,8 @@ struct QuadSolver : SolverBase {
     ~QuadSolver() override
     {
         if (gexec) cudaGraphExecDestroy(gexec);
-        if (hctl) cudaFreeHost(hctl);
-        for (auto e : {ev[0], ev[1], ev_a, ev_b, ev_c}) if (e) cudaEventDestroy(e);
+        pinned_put(hctl);
+        for (auto e : {ev[0], ev[1], ev_a, ev_b, ev_c}) event_put(e);
     }
 
     void setup()
@@ -1560,9 +1584,10 @@ struct QuadSolver : SolverBase {
             PFDR_REQUIRE(q.shard->Vown > 0 && q.shard->Vown <= V, "bad shard: Vown");
         }
         cudaStream_t st = ctx().stream;
-        for (auto *e : {&ev[0], &ev[1], &ev_a, &ev_b, &ev_c}) PFDR_CUDA(cudaEventCreate(e));
+        for (auto *e : {&ev[0], &ev[1], &ev_a, &ev_b, &ev_c}) *e = event_get();
         PFDR_CUDA(cudaEventRecord(ev_a, st));
-        PFDR_CUDA(cudaMallocHost((void **) &hctl, 2 * sizeof(Ctl)));
+        static_assert(2 * sizeof(Ctl) <= PINNED_BLOCK, "control block mirror");
+        hctl = (Ctl *) pinned_get();
 
         const size_t ylen = (N > 0) ? (size_t) N : (size_t) V;
         // sharded dense A holds the OWNED columns only (ghost columns are never applied on this rank)
@@ -1813,11 +1838,7 @@ struct QuadSolver : SolverBase {
             cudaGetLastError();
             attr = true;
         }
-        // CTAs of the cluster: enough that a CTA has about a thousand edges / vertices / matrix columns' worth of work
-        const long long dense = q.N > 0 ? (long long) q.N * q.V : (q.N < 0 ? (long long) q.V * q.V : 0);
-        const long long work = std::max<long long>(std::max<long long>(g.nslots, 2LL * q.E), dense / 16);
-        int C = 1;
-        while (C < cmax && work > 1024LL * C) C *= 2;
+        int C = cmax;
         if (const char *e = getenv("PFDR_B200_SMALL_C")) C = std::max(1, std::min(cmax, atoi(e)));
         SmallArgs<real> a{};
         a.nslots = (int) g.nslots; a.nslices = (int) g.nslices;
@@ -1871,10 +1892,8 @@ struct QuadSolver : SolverBase {
         std::vector<long long> off((size_t) S + 1);
         PFDR_CUDA(cudaMemcpyAsync(off.data(), g.slice_off.p, ((size_t) S + 1) * sizeof(long long), cudaMemcpyDeviceToHost, st));
         PFDR_CUDA(cudaStreamSynchronize(st));
-        const long long dense = q.N > 0 ? (long long) q.N * q.V : (q.N < 0 ? (long long) q.V * q.V : 0);
-        const long long work = std::max<long long>(std::max<long long>(g.nslots, 2LL * q.E), dense / 16);
-        int C = 1;
-        while (C < cmax && work > 1024LL * C) C *= 2;
+        // the largest cluster is the fastest at every size measured (profiles/r01_notes.md): phases are latency chains
+        int C = cmax;
         if (const char *ec = getenv("PFDR_B200_SMALL_C")) C = std::max(1, std::min(cmax, atoi(ec)));
         const size_t Vq = (size_t) S * 32, Nq = q.N > 0 ? (((size_t) q.N + 3) & ~(size_t) 3) : 0;
         for (;; C /= 2) {
@@ -1898,7 +1917,8 @@ struct QuadSolver : SolverBase {
             if (fits) {
                 dstb.alloc(std::max<size_t>(2 * (size_t) q.E, 2));
                 ze.alloc(std::max<size_t>(2 * (size_t) q.E, 2));
-                a.dst = dstb.p; a.Ze = ze.p;
+                ws.alloc(std::max<size_t>(g.nslots, 1));
+                a.dst = dstb.p; a.Ze = ze.p; a.wS = ws.p;
                 cudaLaunchConfig_t cfg{};
                 cfg.gridDim = dim3(C); cfg.blockDim = dim3(512); cfg.dynamicSmemBytes = sm; cfg.stream = st;
                 cudaLaunchAttribute at[1];

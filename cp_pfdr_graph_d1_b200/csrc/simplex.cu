@@ -569,8 +569,8 @@ struct SimplexSolver : SolverBase {
     ~SimplexSolver() override
     {
         if (gexec) cudaGraphExecDestroy(gexec);
-        if (hctl) cudaFreeHost(hctl);
-        for (auto e : {ev[0], ev[1], ev_a, ev_b, ev_c}) if (e) cudaEventDestroy(e);
+        pinned_put(hctl);
+        for (auto e : {ev[0], ev[1], ev_a, ev_b, ev_c}) event_put(e);
     }
 
     void setup()
@@ -587,9 +587,10 @@ struct SimplexSolver : SolverBase {
         LPT = (K % 4 == 0 && !(fl && fl[0] == '1')) ? 4 : 1;
         PFDR_REQUIRE((K + LPT - 1) / LPT <= 32, "this build supports K <= 32 labels, or K <= 128 when K is a multiple of 4");
         cudaStream_t st = ctx().stream;
-        for (auto *e : {&ev[0], &ev[1], &ev_a, &ev_b, &ev_c}) PFDR_CUDA(cudaEventCreate(e));
+        for (auto *e : {&ev[0], &ev[1], &ev_a, &ev_b, &ev_c}) *e = event_get();
         PFDR_CUDA(cudaEventRecord(ev_a, st));
-        PFDR_CUDA(cudaMallocHost((void **) &hctl, 2 * sizeof(Ctl)));
+        static_assert(2 * sizeof(Ctl) <= PINNED_BLOCK, "control block mirror");
+        hctl = (Ctl *) pinned_get();
         int TPV = 1, logTPV = 0;
         while (TPV * LPT < K) { TPV <<= 1; logTPV++; }
         const int C = 32 / TPV;
