@@ -21,6 +21,7 @@
 #include <type_traits>
 #include "graph.cuh"
 #include "solvers.cuh"
+#include <chrono>
 
 namespace pfdr {
 
@@ -845,10 +846,22 @@ template SolverBase *make_simplex<double>(const SimplexProblem<double> &);
 template <typename real>
 void solve_simplex(const SimplexProblem<real> &q)
 {
+    const bool trace = getenv("PFDR_B200_TRACE") != nullptr;      // one line per call on stderr
+    const auto t0 = std::chrono::steady_clock::now();
     SimplexSolver<real> s(q, false);
     s.setup();
+    const auto t1 = std::chrono::steady_clock::now();
     s.run();
+    const auto t2 = std::chrono::steady_clock::now();
     s.fetch(q.P, q.it, q.Obj, q.Dif);
+    if (trace) {
+        const auto t3 = std::chrono::steady_clock::now();
+        auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+            return std::chrono::duration<double, std::milli>(b - a).count();
+        };
+        fprintf(stderr, "[pfdr_b200] simplex V=%d E=%d K=%d f%d: %d it, setup %.2f ms, run %.2f ms (device loop %.2f ms), fetch %.2f ms\n",
+                q.V, q.E, q.K, (int) sizeof(real) * 8, (int) ctx().stats.iterations, ms(t0, t1), ms(t1, t2), ctx().stats.loop_ms, ms(t2, t3));
+    }
 }
 template void solve_simplex<float>(const SimplexProblem<float> &);
 template void solve_simplex<double>(const SimplexProblem<double> &);

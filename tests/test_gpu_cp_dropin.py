@@ -69,3 +69,35 @@ def test_cp_simplex(cps):
     r1 = b200n.loss_d1_simplex(*args, **kw)
     assert r1["rV"] == r0["rV"] and np.array_equal(r1["Cv"], r0["Cv"])
     assert rel(r1["rX"], r0["rX"]) < 1e-5
+
+
+def test_cp_solve_time_vs_reference(cps):
+    """BASELINE.json's second figure, "CP solve time vs CPU": wall time of the reference's cut-pursuit on the
+    EEG-like problem at the reference's own settings (octave/example_EEG_CP.m:20-27: PFDR_itMax 1e4) with its PFDR
+    calls served by libpfdr_b200, beside the all-reference build on the same host.  The reduced problems
+    (hundreds of vertices, 1e4 iterations) are where a one-launch-per-iteration GPU path loses to the CPU;
+    they run in the single-launch cluster kernels.  Times are recorded, only a gross regression fails."""
+    import json
+    import os
+    import time
+    ref, b200n, _ = cps
+    out = {}
+    for level in (5, 6):
+        w = synth.eeg_like(level, 91, np.float64)
+        kw = dict(CP_difTol=1e-4, CP_itMax=10, rho=1.5, condMin=1e-3, difRcd=0.0, difTol=1e-6, itMax=10000)
+        args = (w["Y"], w["A"], w["Eu"], w["Ev"], w["La_d1"], w["La_l1"], 1, w["N"])
+        b200n.quadratic_d1_l1(*args, **kw)                      # warm-up: context, memory pool, kernel load
+        t0 = time.perf_counter(); r1 = b200n.quadratic_d1_l1(*args, **kw); t1 = time.perf_counter() - t0
+        t0 = time.perf_counter(); r0 = ref.quadratic_d1_l1(*args, **kw); t_ref = time.perf_counter() - t0
+        assert r1["rV"] == r0["rV"] and np.array_equal(r1["Cv"], r0["Cv"]) and rel(r1["rX"], r0["rX"]) < 1e-5
+        out[f"eeg_like_level{level}_V{w['V']}_N91_f64"] = dict(
+            cp_b200_s=round(t1, 3), cp_reference_s=round(t_ref, 3), speedup=round(t_ref / t1, 2), rV=int(r0["rV"]),
+            CP_it=int(r0["CP_it"]), host_cores=os.cpu_count())
+        assert t1 < 3 * t_ref, out
+    print("\nCP solve time vs CPU:", json.dumps(out))
+    try:
+        os.makedirs("gpurun_out", exist_ok=True)
+        with open("gpurun_out/cp_solve_time.json", "w") as f:
+            json.dump(out, f, indent=1)
+    except OSError:
+        pass
