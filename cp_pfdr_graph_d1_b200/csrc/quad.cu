@@ -1824,19 +1824,24 @@ struct QuadSolver : SolverBase {
         const char *e = getenv("PFDR_B200_SMALL");        // read per call: the tests switch it
         if ((e && e[0] == '0') || sharded) return false;
         const long long dense = q.N > 0 ? (long long) q.N * q.V : (q.N < 0 ? (long long) q.V * q.V : 0);
+        // Regular graphs without dense operator: the large path costs ~7.5 us per iteration whatever the size, the
+        // cluster kernels pass that near 50k slots (8000 vertices of a 3-D grid; profiles/r01_notes.md).  With a hub
+        // (a slice wider than SMALL_WIDE rows) the large path walks the hub's row serially: cluster kernels whenever they fit.
+        if (q.N == 0 && g.max_width <= SMALL_WIDE && g.nslots > 49152) return false;
         return small_smem() <= 200 * 1024 && g.nslices <= SMALL_MAX_SLICES && g.nslots <= (1 << 20) && q.E <= (1 << 19) && dense <= (1 << 22);
     }
 
     void run_small()
     {
         cudaStream_t st = ctx().stream;
-        static bool attr = false;
-        static int cmax = 8;
-        if (!attr) {
+        static int attr_dev = -1, cmax = 8;                      // function attributes are per device
+        int dev = 0;
+        PFDR_CUDA(cudaGetDevice(&dev));
+        if (attr_dev != dev) {
             PFDR_CUDA(cudaFuncSetAttribute(quad_small_kernel<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            if (cudaFuncSetAttribute(quad_small_kernel<real>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) cmax = 16;
+            cmax = cudaFuncSetAttribute(quad_small_kernel<real>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess ? 16 : 8;
             cudaGetLastError();
-            attr = true;
+            attr_dev = dev;
         }
         int C = cmax;
         if (const char *e = getenv("PFDR_B200_SMALL_C")) C = std::max(1, std::min(cmax, atoi(e)));
@@ -1880,13 +1885,14 @@ struct QuadSolver : SolverBase {
         const char *e = getenv("PFDR_B200_PUSH");
         if ((e && e[0] == '0') || q.Obj != nullptr || q.difRcd > (real) 0) return false;
         cudaStream_t st = ctx().stream;
-        static bool attr = false;
-        static int cmax = 8;
-        if (!attr) {
+        static int attr_dev = -1, cmax = 8;                      // function attributes are per device
+        int dev = 0;
+        PFDR_CUDA(cudaGetDevice(&dev));
+        if (attr_dev != dev) {
             PFDR_CUDA(cudaFuncSetAttribute(quad_push_kernel<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            if (cudaFuncSetAttribute(quad_push_kernel<real>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) cmax = 16;
+            cmax = cudaFuncSetAttribute(quad_push_kernel<real>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess ? 16 : 8;
             cudaGetLastError();
-            attr = true;
+            attr_dev = dev;
         }
         const int S = g.nslices;
         std::vector<long long> off((size_t) S + 1);
