@@ -996,6 +996,22 @@ __global__ void __launch_bounds__(512, 1) quad_push_kernel(QP<real> p, PushArgs<
     const int *__restrict__ nbr = p.nbr;
     const uint32_t own_bytes = (uint32_t) ((v1q - v0) * sizeof(real)), all_bytes = (uint32_t) (Vq * sizeof(real));
     __syncthreads();
+    // partial A x over the own columns (N > 0): G threads per observation n, folded by shuffles
+    auto own_partial = [&](const real *Xv) {
+        int G = 1;
+        while (G < 32 && 2 * G * N <= nt) G *= 2;
+        const int g = tid & (G - 1);
+        for (int n0 = 0; n0 < N; n0 += nt / G) {                              // uniform trip count: shuffles below
+            const int n = n0 + tid / G;
+            real acc = 0;
+            if (n < N) {
+#pragma unroll 4
+                for (int v = v0 + g; v < v1; v += G) acc += __ldg(p.A + (size_t) N * v + n) * Xv[v];
+            }
+            for (int o = G >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (n < N && g == 0) partsS[rank * Nq + n] = acc;
+        }
+    };
     SPROF_DECL
     GSTAMP_DECL
     for (;;) {
@@ -1007,24 +1023,14 @@ __global__ void __launch_bounds__(512, 1) quad_push_kernel(QP<real> p, PushArgs<
         if (N != 0) {
             constexpr int GL = 8;                                             // lanes per column in the transposed products
             if (N > 0) {
-                // partial A X over the own columns: G threads per observation n, folded by shuffles
-                if (tid == 0) mbar_expect(mb2, (uint32_t) ((C - 1) * Nq * sizeof(real)));
-                int G = 1;
-                while (G < 32 && 2 * G * N <= nt) G *= 2;
-                const int g = tid & (G - 1);
-                for (int n0 = 0; n0 < N; n0 += nt / G) {                      // uniform trip count: shuffles below
-                    const int n = n0 + tid / G;
-                    real acc = 0;
-                    if (n < N) {
-#pragma unroll 4
-                        for (int v = v0 + g; v < v1; v += G) acc += __ldg(p.A + (size_t) N * v + n) * Xc[v];
-                    }
-                    for (int o = G >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-                    if (n < N && g == 0) partsS[rank * Nq + n] = acc;
+                // partial A X over the own columns: after the first iteration it arrived with the iterate (see publish)
+                if (it == it_start) {
+                    if (tid == 0) mbar_expect(mb2, (uint32_t) ((C - 1) * Nq * sizeof(real)));
+                    own_partial(Xc);
+                    __syncthreads();
+                    push_chunks(partsS + rank * Nq, (uint32_t) (Nq * sizeof(real)), rank, C, mb2);
+                    mbar_wait(mb2, phA);
                 }
-                __syncthreads();
-                push_chunks(partsS + rank * Nq, (uint32_t) (Nq * sizeof(real)), rank, C, mb2);
-                mbar_wait(mb2, phA);
                 for (int n = tid; n < N; n += nt) {
                     real acc = 0;
                     for (int q = 0; q < C; q++) acc += partsS[q * Nq + n];                    // rank order: same bits everywhere
@@ -1091,7 +1097,7 @@ __global__ void __launch_bounds__(512, 1) quad_push_kernel(QP<real> p, PushArgs<
         SPROF(3)
         GSTAMP(2)
         // ---- average + vertex prox + evolution (ref S9, S10), own vertices ----
-        if (tid == 0) mbar_expect(mb1, (all_bytes - own_bytes) * (N == 0 ? 2u : 1u) + (uint32_t) C * 16u);
+        if (tid == 0) mbar_expect(mb1, (all_bytes - own_bytes) * (N == 0 ? 2u : 1u) + (uint32_t) C * 16u + (N > 0 ? (uint32_t) ((C - 1) * Nq * sizeof(real)) : 0u));
         double sd = 0.0, sc = 0.0;
         auto finish_vertex = [&](int v, real x, real xo) {
             if (p.prox_kind == 0) {
@@ -1159,6 +1165,11 @@ __global__ void __launch_bounds__(512, 1) quad_push_kernel(QP<real> p, PushArgs<
             }
             push_chunks(Xn + v0, own_bytes, rank, C, mb1);
             if (N == 0) push_chunks(Pn + v0, own_bytes, rank, C, mb1);
+            if (N > 0) {                                                      // the next iteration's partial A x rides along
+                own_partial(Xn);
+                __syncthreads();
+                push_chunks(partsS + rank * Nq, (uint32_t) (Nq * sizeof(real)), rank, C, mb1);
+            }
         }
         SPROF(5)
         GSTAMP(4)
