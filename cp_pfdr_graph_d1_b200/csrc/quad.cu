@@ -55,6 +55,8 @@ struct QP {                       // kernel parameter block
     int nparts;                   // CTAs of ax_partial
 };
 
+constexpr int HUB_ROWS = 32;      // rows of a SELL slice walked by one thread per vertex; past that the warp shares a hub's row
+
 template <typename real> __device__ __forceinline__ real rabs(real a) { return a < (real) 0 ? -a : a; }
 
 // gradient of the smooth part at vertex v (x = X[v]); dense cases read what the A-kernels left in G
@@ -369,7 +371,7 @@ __global__ void __launch_bounds__(256) quad_iter_kernel(QP<real> p)
 
 // Pipelined variant: one row at a time, the next row's indices / weight / own copy are requested while the
 // current row's gathers are in flight (as simplex_iter_kernel).  Few registers -> up to 64 warps per SM.
-template <typename real, bool PER_SLOT_TH, int MINB>
+template <typename real, bool PER_SLOT_TH, int MINB, bool HUB>
 __global__ void __launch_bounds__(256, MINB) quad_iter_pipe_kernel(QP<real> p)
 {
     __shared__ double smem[64];
@@ -390,23 +392,29 @@ __global__ void __launch_bounds__(256, MINB) quad_iter_pipe_kernel(QP<real> p)
     const real rho = p.rho;
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     real red[2] = {(real) 0, (real) 0};
-    if (v < p.Vown) {
-        const long long base = p.slice_off[v >> 5];
-        const int width = (int) ((p.slice_off[(v >> 5) + 1] - base) >> 5);
+    const bool own = v < p.Vown;
+    long long base = 0;
+    int width = 0;                                       // of the warp's slice (warp-uniform)
+    if ((v & ~31) < p.Vown) {
+        base = p.slice_off[v >> 5];
+        width = (int) ((p.slice_off[(v >> 5) + 1] - base) >> 5);
+    }
+    real xo = 0, po_v = 0, Tv = 1, Sv = 0, acc = 0;
+    if (own) {
+        const int wl = HUB ? min(width, HUB_ROWS) : width;   // HUB: rows past HUB_ROWS are shared by the warp, below
         int s = (int) base + (v & 31);
-        const real xo = (cur ? p.X1 : p.X0)[v], po_v = Pc[v];
-        const real Tv = Tg[v], Sv = p.Sinv[v];
-        real acc = 0;
+        xo = (cur ? p.X1 : p.X0)[v]; po_v = Pc[v];
+        Tv = Tg[v]; Sv = p.Sinv[v];
         int n_c = -1, tw_c = 0;
         real w_c = 0, zo_c = 0, th_c = p.thc0;
-        if (width > 0) { n_c = nbr[s]; tw_c = twin[s]; w_c = wg[s]; zo_c = Zin[s]; if (PER_SLOT_TH) th_c = p.thc[s]; }
-        for (int j = 0; j < width; j++, s += 32) {
+        if (wl > 0) { n_c = nbr[s]; tw_c = twin[s]; w_c = wg[s]; zo_c = Zin[s]; if (PER_SLOT_TH) th_c = p.thc[s]; }
+        for (int j = 0; j < wl; j++, s += 32) {
             const bool live = n_c >= 0;
             real pn = 0, Tn = 1, zt = 0;
             if (live) { pn = Pc[n_c]; Tn = Tg[n_c]; zt = Zin[tw_c]; }
             int n_n = -1, tw_n = 0;
             real w_n = 0, zo_n = 0, th_n = p.thc0;
-            if (j + 1 < width) {
+            if (j + 1 < wl) {
                 n_n = nbr[s + 32]; tw_n = twin[s + 32]; w_n = wg[s + 32]; zo_n = Zin[s + 32];
                 if (PER_SLOT_TH) th_n = p.thc[s + 32];
             }
@@ -423,6 +431,58 @@ __global__ void __launch_bounds__(256, MINB) quad_iter_pipe_kernel(QP<real> p)
             }
             n_c = n_n; tw_c = tw_n; w_c = w_n; zo_c = zo_n; th_c = th_n;
         }
+    }
+    if (HUB && width > HUB_ROWS) {
+        // A hub (the background component of a cut-pursuit reduced graph touches thousands of others): one thread
+        // walking its row serially would hold the whole launch.  The warp takes the rows past HUB_ROWS of every hub
+        // of its slice 32 at a time, every lane doing the full prox of one row; partial sums folded by shuffles.
+        // (HUB variant: launched only when the graph has such a slice, with a larger register budget.)
+        const int lane = threadIdx.x & 31;
+        unsigned m = __ballot_sync(0xffffffffu, own && nbr[(int) base + HUB_ROWS * 32 + lane] >= 0);
+        while (m) {
+            const int c = __ffs(m) - 1;
+            m &= m - 1;
+            const real xo_c = __shfl_sync(0xffffffffu, xo, c), po_c = __shfl_sync(0xffffffffu, po_v, c);
+            const real Tv_c = __shfl_sync(0xffffffffu, Tv, c), Sv_c = __shfl_sync(0xffffffffu, Sv, c);
+            real part = 0;
+            constexpr int HU = 4;                                             // rows in flight per lane
+            for (int j0 = HUB_ROWS + lane; j0 < width; j0 += 32 * HU) {
+                int sk[HU], n[HU], tw[HU];
+                real zo[HU], ww[HU], thc[HU], zt[HU], Tn[HU], pn[HU];
+#pragma unroll
+                for (int u = 0; u < HU; u++) {
+                    const int j = j0 + 32 * u;
+                    sk[u] = (int) base + j * 32 + c;
+                    n[u] = j < width ? nbr[sk[u]] : -1;
+                }
+#pragma unroll
+                for (int u = 0; u < HU; u++) {
+                    const bool live = n[u] >= 0;
+                    tw[u] = live ? twin[sk[u]] : 0; zo[u] = live ? Zin[sk[u]] : (real) 0; ww[u] = live ? wg[sk[u]] : (real) 0;
+                    thc[u] = (PER_SLOT_TH && live) ? p.thc[sk[u]] : p.thc0;
+                    Tn[u] = live ? Tg[n[u]] : (real) 1; pn[u] = live ? Pc[n[u]] : (real) 0;
+                }
+#pragma unroll
+                for (int u = 0; u < HU; u++) zt[u] = n[u] >= 0 ? Zin[tw[u]] : (real) 0;
+#pragma unroll
+                for (int u = 0; u < HU; u++) {
+                    if (n[u] >= 0) {
+                        const real tsum = Tv_c + Tn[u], inv = fast_rcp(tsum);
+                        const real th = thc[u] * tsum;
+                        const real wo = Tn[u] * inv, wt = Tv_c * inv;
+                        const real po = po_c - zo[u], pt = pn[u] - zt[u], d0 = po - pt;
+                        const real b = d0 - min(max(d0, -th), th);
+                        const real zn = zo[u] + rho * (fma(wo, d0, pt) + wt * b - xo_c);
+                        Zout[sk[u]] = zn;
+                        part += (ww[u] * Sv_c) * zn;
+                    }
+                }
+            }
+            for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+            if (lane == c) acc += part;
+        }
+    }
+    if (own) {
         real x = acc;
         if (p.prox_kind == 0) {                                                // ref l1.cpp :500-512
             if (p.La_l1) {
@@ -1750,12 +1810,16 @@ struct QuadSolver : SolverBase {
         static int pipe = -1;
         if (pipe < 0) { const char *e = getenv("PFDR_B200_PIPE"); pipe = e ? atoi(e) : (sizeof(real) == 4 ? 8 : 6); }
         if (mode == 1 && pipe > 0) {
-#define PFDR_PIPE(MB)                                                                              \
-            do {                                                                                   \
-                if (p.thc) PFDR_LAUNCH((quad_iter_pipe_kernel<real, true, MB>), ogrid, 256, 0, p); \
-                else PFDR_LAUNCH((quad_iter_pipe_kernel<real, false, MB>), ogrid, 256, 0, p);      \
+#define PFDR_PIPE(MB, HB)                                                                              \
+            do {                                                                                       \
+                if (p.thc) PFDR_LAUNCH((quad_iter_pipe_kernel<real, true, MB, HB>), ogrid, 256, 0, p); \
+                else PFDR_LAUNCH((quad_iter_pipe_kernel<real, false, MB, HB>), ogrid, 256, 0, p);      \
             } while (0)
-            if (pipe >= 8) PFDR_PIPE(8); else if (pipe >= 6) PFDR_PIPE(6); else PFDR_PIPE(4);
+            // a slice wider than HUB_ROWS (a hub vertex): variant whose warps share the hub's rows (PFDR_B200_HUB=0: off)
+            const char *he = getenv("PFDR_B200_HUB");
+            const bool hub_env = !(he && he[0] == '0');
+            if (hub_env && g.max_width > HUB_ROWS) PFDR_PIPE(2, true);
+            else if (pipe >= 8) PFDR_PIPE(8, false); else if (pipe >= 6) PFDR_PIPE(6, false); else PFDR_PIPE(4, false);
 #undef PFDR_PIPE
             return;
         }

@@ -421,7 +421,9 @@ __global__ void simplex_finalize_kernel(SP<real> p)
     simplex_finalize(p, p.ctl->it, s);
 }
 
-template <typename real, int LPT, bool PERK, int LOSS, int MINB, bool IDX32>
+constexpr int SIMPLEX_HUB_ROWS = 32;   // rows of a slice walked by one lane group per vertex; past that the warp shares a hub's rows
+
+template <typename real, int LPT, bool PERK, int LOSS, int MINB, bool IDX32, bool HUB>
 __global__ void __launch_bounds__(256, MINB) simplex_iter_kernel(SP<real> p)
 {
     typedef VecN<real, LPT> vec;
@@ -470,12 +472,13 @@ __global__ void __launch_bounds__(256, MINB) simplex_iter_kernel(SP<real> p)
         int n_c = -1, tw_c = 0;
         real w_c = 0;
         vec zo_c = splat<real, LPT>((real) 0);
-        if (on && width > 0) {
+        const int wl = HUB ? min(width, SIMPLEX_HUB_ROWS) : width;       // HUB: later rows are shared by the warp, below
+        if (on && wl > 0) {
             n_c = nbr[s]; tw_c = twin[s];
             if (!PERK) w_c = p.w[s];
             zo_c = ldv<real, LPT>(Zin + zoff);
         }
-        for (int j = 0; j < width; j++) {
+        for (int j = 0; j < wl; j++) {
             const bool live = n_c >= 0;
             vec zt, fn, tn, wvk, th;
             if (live) {
@@ -488,7 +491,7 @@ __global__ void __launch_bounds__(256, MINB) simplex_iter_kernel(SP<real> p)
             int n_n = -1, tw_n = 0;
             real w_n = 0;
             vec zo_n = zo_c;
-            if (on && j + 1 < width) {
+            if (on && j + 1 < wl) {
                 n_n = nbr[s + C]; tw_n = twin[s + C];
                 if (!PERK) w_n = p.w[s + C];
                 zo_n = ldv<real, LPT>(Zin + (zoff + rowK));
@@ -499,6 +502,64 @@ __global__ void __launch_bounds__(256, MINB) simplex_iter_kernel(SP<real> p)
             }
             n_c = n_n; tw_c = tw_n; w_c = w_n; zo_c = zo_n;
             s += C; zoff += rowK;
+        }
+        if (HUB && width > SIMPLEX_HUB_ROWS) {
+            // A hub vertex (a cut-pursuit reduced graph's background component): the C vertex groups of the warp
+            // share the rows past SIMPLEX_HUB_ROWS of every hub of the slice, each group doing the full prox of one
+            // row for its labels; the hub's state is broadcast by shuffles, the partial sums folded across groups.
+            const unsigned full = 0xffffffffu;
+            const int kl = lane & (TPV - 1);
+            const bool kok = k0 < K;
+            const unsigned m = __ballot_sync(full, v < p.Vown && nbr[(int) base + SIMPLEX_HUB_ROWS * C + vl] >= 0);
+            for (int c = 0; c < C; c++) {
+                if (!((m >> (c * TPV)) & 1u)) continue;                          // warp-uniform
+                const int src = c * TPV + kl;
+                vec pold_c, fown_c, Tv_c, Sv_c, part = splat<real, LPT>((real) 0);
+#pragma unroll
+                for (int i = 0; i < LPT; i++) {
+                    pold_c.v[i] = __shfl_sync(full, pold.v[i], src); fown_c.v[i] = __shfl_sync(full, fown.v[i], src);
+                    Tv_c.v[i] = __shfl_sync(full, Tv.v[i], src); Sv_c.v[i] = __shfl_sync(full, Sv.v[i], src);
+                }
+                constexpr int HU = 2;                                             // rows in flight per lane group
+                for (int j0 = SIMPLEX_HUB_ROWS + vl; j0 < width && kok; j0 += HU * C) {
+                    int sh[HU], n[HU], tw[HU];
+                    real wh[HU];
+                    vec zo[HU], zt[HU], fn[HU], tn[HU], wvk[HU], th[HU];
+#pragma unroll
+                    for (int u = 0; u < HU; u++) {
+                        const int j = j0 + u * C;
+                        sh[u] = (int) base + j * C + c;
+                        n[u] = j < width ? nbr[sh[u]] : -1;
+                    }
+#pragma unroll
+                    for (int u = 0; u < HU; u++) {
+                        if (n[u] >= 0) {
+                            const idx_t zo_off = (idx_t) sh[u] * (idx_t) K + (idx_t) k0, no = (idx_t) n[u] * (idx_t) K + (idx_t) k0;
+                            tw[u] = twin[sh[u]];
+                            wh[u] = PERK ? (real) 0 : p.w[sh[u]];
+                            zo[u] = ldv<real, LPT>(Zin + zo_off);
+                            fn[u] = ldv<real, LPT>(Fc + no);
+                            if (LOSS != LOSS_LIN) tn[u] = ldv<real, LPT>(Tg + no);
+                            if (PERK) { wvk[u] = ldv<real, LPT>(p.wk + zo_off); th[u] = ldv<real, LPT>(p.thk + zo_off); }
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < HU; u++)
+                        if (n[u] >= 0) zt[u] = ldv<real, LPT>(Zin + ((idx_t) tw[u] * (idx_t) K + (idx_t) k0));
+#pragma unroll
+                    for (int u = 0; u < HU; u++) {
+                        if (n[u] >= 0) {
+                            const vec zn = prox_row<real, LPT, PERK, LOSS>(rho, fown_c, pold_c, Tv_c, Sv_c, zo[u], zt[u], fn[u], tn[u], wvk[u], th[u], wh[u], part);
+                            stv<real, LPT>(Zout + ((idx_t) sh[u] * (idx_t) K + (idx_t) k0), zn);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < LPT; i++) {
+                    for (int o = TPV; o < 32; o <<= 1) part.v[i] += __shfl_xor_sync(full, part.v[i], o);
+                    if (vl == c) acc.v[i] += part.v[i];
+                }
+            }
         }
         red[0] = (real) simplex_epilogue<real, LPT, PERK, LOSS>(p, ctl, on, v, k0, vk, acc, Tv, pold, Pn, Fn);
     }
@@ -693,8 +754,12 @@ struct SimplexSolver : SolverBase {
         static int i32 = -1;
         if (i32 < 0) { const char *e = getenv("PFDR_B200_IDX32"); i32 = (e && e[0] == '0') ? 0 : 1; }
         (void) U; (void) MB;
-        if (L == 4 && !PERK && small && i32) PFDR_LAUNCH((simplex_iter_kernel<real, 4, false, LOSS, MBD, true>), ogrid, 256, 0, p);
-        else PFDR_LAUNCH((simplex_iter_kernel<real, L, PERK, LOSS, MBD, false>), ogrid, 256, 0, p);
+        // a slice wider than SIMPLEX_HUB_ROWS (a hub vertex): variant whose warps share the hub's rows (PFDR_B200_HUB=0: off)
+        const char *he = getenv("PFDR_B200_HUB");
+        const bool hub_env = !(he && he[0] == '0');
+        if (hub_env && g.max_width > SIMPLEX_HUB_ROWS) PFDR_LAUNCH((simplex_iter_kernel<real, L, PERK, LOSS, 1, false, true>), ogrid, 256, 0, p);
+        else if (L == 4 && !PERK && small && i32) PFDR_LAUNCH((simplex_iter_kernel<real, 4, false, LOSS, MBD, true, false>), ogrid, 256, 0, p);
+        else PFDR_LAUNCH((simplex_iter_kernel<real, L, PERK, LOSS, MBD, false, false>), ogrid, 256, 0, p);
     }
     template <int L, bool PERK>
     void launch_iter_loss()
