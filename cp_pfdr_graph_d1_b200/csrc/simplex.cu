@@ -61,7 +61,10 @@ __device__ __forceinline__ VecN<real, L> ldv(const real *q)
 {
     VecN<real, L> r;
     if constexpr (L == 1) r.v[0] = *q;
-    else if constexpr (sizeof(real) == 4) {
+    else if constexpr (L == 2) {
+        if constexpr (sizeof(real) == 4) { const float2 t = *reinterpret_cast<const float2 *>(q); r.v[0] = t.x; r.v[1] = t.y; }
+        else { const double2 t = *reinterpret_cast<const double2 *>(q); r.v[0] = t.x; r.v[1] = t.y; }
+    } else if constexpr (sizeof(real) == 4) {
         const float4 t = *reinterpret_cast<const float4 *>(q);
         r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
     } else {
@@ -74,7 +77,10 @@ template <typename real, int L>
 __device__ __forceinline__ void stv(real *q, const VecN<real, L> &r)
 {
     if constexpr (L == 1) *q = r.v[0];
-    else if constexpr (sizeof(real) == 4) *reinterpret_cast<float4 *>(q) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
+    else if constexpr (L == 2) {
+        if constexpr (sizeof(real) == 4) *reinterpret_cast<float2 *>(q) = make_float2(r.v[0], r.v[1]);
+        else *reinterpret_cast<double2 *>(q) = make_double2(r.v[0], r.v[1]);
+    } else if constexpr (sizeof(real) == 4) *reinterpret_cast<float4 *>(q) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
     else {
         *reinterpret_cast<double2 *>(q) = make_double2(r.v[0], r.v[1]);
         *reinterpret_cast<double2 *>(q + 2) = make_double2(r.v[2], r.v[3]);
@@ -85,7 +91,10 @@ template <typename real, int L>
 __device__ __forceinline__ void stv_cs(real *q, const VecN<real, L> &r)
 {
     if constexpr (L == 1) __stcs(q, r.v[0]);
-    else if constexpr (sizeof(real) == 4) __stcs(reinterpret_cast<float4 *>(q), make_float4(r.v[0], r.v[1], r.v[2], r.v[3]));
+    else if constexpr (L == 2) {
+        if constexpr (sizeof(real) == 4) __stcs(reinterpret_cast<float2 *>(q), make_float2(r.v[0], r.v[1]));
+        else __stcs(reinterpret_cast<double2 *>(q), make_double2(r.v[0], r.v[1]));
+    } else if constexpr (sizeof(real) == 4) __stcs(reinterpret_cast<float4 *>(q), make_float4(r.v[0], r.v[1], r.v[2], r.v[3]));
     else {
         __stcs(reinterpret_cast<double2 *>(q), make_double2(r.v[0], r.v[1]));
         __stcs(reinterpret_cast<double2 *>(q + 2), make_double2(r.v[2], r.v[3]));
@@ -646,7 +655,10 @@ struct SimplexSolver : SolverBase {
             PFDR_REQUIRE(q.shard->Vown > 0 && q.shard->Vown <= V, "bad shard: Vown");
         }
         const char *fl = getenv("PFDR_B200_LPT");
-        LPT = (K % 4 == 0 && !(fl && fl[0] == '1')) ? 4 : 1;
+        LPT = (K % 4 == 0) ? 4 : 1;
+        // float64: two labels per lane (one 16-byte access) halve the registers of a lane -> twice the resident warps
+        if (sizeof(real) == 8 && K % 2 == 0 && K <= 64 && !(fl && fl[0] == '4')) LPT = 2;
+        if (fl && fl[0] == '1') LPT = 1;
         PFDR_REQUIRE((K + LPT - 1) / LPT <= 32, "this build supports K <= 32 labels, or K <= 128 when K is a multiple of 4");
         cudaStream_t st = ctx().stream;
         for (auto *e : {&ev[0], &ev[1], &ev_a, &ev_b, &ev_c}) *e = event_get();
@@ -719,6 +731,7 @@ struct SimplexSolver : SolverBase {
     void launch_precond(const real *Pinit, int recond)
     {
         if (LPT == 4) PFDR_LAUNCH((simplex_precond_kernel<real, 4>), grid, 256, 0, p, Pinit, recond);
+        else if (LPT == 2) { if constexpr (sizeof(real) == 8) PFDR_LAUNCH((simplex_precond_kernel<real, 2>), grid, 256, 0, p, Pinit, recond); }
         else PFDR_LAUNCH((simplex_precond_kernel<real, 1>), grid, 256, 0, p, Pinit, recond);
     }
 
@@ -749,7 +762,7 @@ struct SimplexSolver : SolverBase {
         static int MB = -1;
         if (MB < 0) { const char *e = getenv("PFDR_B200_MINB"); MB = e ? atoi(e) : 0; }
         (void) U;
-        constexpr int MBD = (sizeof(real) == 4 ? 4 : 2);
+        constexpr int MBD = (sizeof(real) == 4 || L == 2) ? 4 : 2;
         const bool small = (size_t) std::max<long long>(g.nslots, q.V) * (size_t) q.K < 0xFFFFFFFFull;
         static int i32 = -1;
         if (i32 < 0) { const char *e = getenv("PFDR_B200_IDX32"); i32 = (e && e[0] == '0') ? 0 : 1; }
@@ -758,7 +771,9 @@ struct SimplexSolver : SolverBase {
         const char *he = getenv("PFDR_B200_HUB");
         const bool hub_env = !(he && he[0] == '0');
         if (hub_env && g.max_width > SIMPLEX_HUB_ROWS) PFDR_LAUNCH((simplex_iter_kernel<real, L, PERK, LOSS, 1, false, true>), ogrid, 256, 0, p);
-        else if (L == 4 && !PERK && small && i32) PFDR_LAUNCH((simplex_iter_kernel<real, 4, false, LOSS, MBD, true, false>), ogrid, 256, 0, p);
+        else if (L > 1 && !PERK && small && i32) {
+            if constexpr (L > 1) PFDR_LAUNCH((simplex_iter_kernel<real, L, false, LOSS, MBD, true, false>), ogrid, 256, 0, p);
+        }
         else PFDR_LAUNCH((simplex_iter_kernel<real, L, PERK, LOSS, MBD, false, false>), ogrid, 256, 0, p);
     }
     template <int L, bool PERK>
@@ -776,6 +791,7 @@ struct SimplexSolver : SolverBase {
             PFDR_LAUNCH(simplex_objective_kernel<real>, std::min<unsigned>(cdiv(work, 256), num_sms() * 8), 256, 0, p);
         }
         if (LPT == 4) { if (p.wk) launch_iter_loss<4, true>(); else launch_iter_loss<4, false>(); }
+        else if (LPT == 2) { if constexpr (sizeof(real) == 8) { if (p.wk) launch_iter_loss<2, true>(); else launch_iter_loss<2, false>(); } }
         else { if (p.wk) launch_iter_loss<1, true>(); else launch_iter_loss<1, false>(); }
         if (sharded) {     // evolution sum over all ranks, then the new boundary forward points and cut-edge copies
             halo.exchange(HALO_VA0 | HALO_Z, PingPong<real>(Fa.p, Fb.p), PingPong<real>(), PingPong<real>(Z0.p, Z1.p), ctl.p,
