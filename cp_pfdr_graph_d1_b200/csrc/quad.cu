@@ -508,7 +508,7 @@ __global__ void __launch_bounds__(256, MINB) quad_iter_pipe_kernel(QP<real> p)
 }
 
 // ---------------------------------------------------------------------------------------------
-// Small-problem mode: the whole solve in ONE launch of ONE thread-block cluster (up to 16 CTAs x 1024 threads).
+// Small-problem mode: the whole solve in ONE launch of ONE thread-block cluster (up to 16 CTAs x 512 threads).
 // The reduced problems that the cut-pursuit outer loop hands over (a few hundred to a few thousand vertices, up to
 // 1e4 iterations, reference src/CP_PFDR_graph_quadratic_d1_l1.cpp:848-859) are latency bound on the large path: one
 // launch (or four) per iteration and, inside it, a chain of dependent L2 round trips per half-edge row - with a
@@ -984,7 +984,6 @@ __global__ void __launch_bounds__(512, 1) quad_push_kernel(QP<real> p, PushArgs<
     real *Zs = Ts + Vq;                                          // [2][nso] new edge copies of the own SELL rows
     real *partsS = Zs + 2 * nso;                                 // [16][Nq] partial A x of the CTAs
     real *Rs = partsS + 16 * Nq;                                 // [Nq] residual
-    real *part = Rs + Nq;                                        // [nw][Nq] per-warp partial A x
     __shared__ int sbase[SMALL_MAX_SLICES + 1];
     __shared__ unsigned char isw[SMALL_MAX_SLICES];
     __shared__ int widelist[SMALL_MAX_WIDE], nwide, s0r[17];
@@ -1992,7 +1991,7 @@ struct QuadSolver : SolverBase {
             }
             for (int c = C + 1; c <= 16; c++) a.slb[c] = S;
             a.nso = (int) ((nso + 3) & ~3LL);
-            const size_t sm = 64 + 256 + 512 + (5 * Vq + 2 * (size_t) a.nso + 17 * Nq + 16 * Nq) * sizeof(real);
+            const size_t sm = 64 + 256 + 512 + (5 * Vq + 2 * (size_t) a.nso + 17 * Nq) * sizeof(real);
             bool fits = sm <= 200 * 1024;
             for (int c = 0; c < C; c++) fits = fits && a.slb[c + 1] - a.slb[c] <= SMALL_MAX_SLICES;
             if (fits) {
