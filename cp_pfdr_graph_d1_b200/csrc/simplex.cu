@@ -31,6 +31,7 @@ template <typename real>
 struct SP {
     Ctl *ctl;
     int K, V, E, TPV, C, logC, logTPV, loss, by_label, LPT, stream_z;
+    int Kv;                           // labels that exist (K is the row stride: Kv rounded up to a multiple of 4 when padded, else Kv)
     int Vown, sharded, Vglobal;   // vertices this rank owns (== V unless sharded: ghosts follow), global count
     int world, rank;              // sharded: sums holds one value per rank, sums[rank] is ours
     double *sums;                 // [1] reduction scratch of the sharded path
@@ -222,10 +223,10 @@ __global__ void __launch_bounds__(256) simplex_precond_kernel(SP<real> p, const 
     const int lane = threadIdx.x & 31;
     const long long slice = ((long long) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (slice >= ((long long) p.V + p.C - 1) >> p.logC) return;     // whole warp leaves together
-    const int K = p.K, TPV = p.TPV;
+    const int K = p.K, Kv = p.Kv, TPV = p.TPV;
     const int vl = lane >> p.logTPV, k0 = (lane & (TPV - 1)) * LPT;
     const int v = (int) (slice << p.logC) + vl;
-    const bool on = (v < p.V) && (k0 < K);
+    const bool on = (v < p.V) && (k0 < Kv);
     const size_t vk = (size_t) (on ? v : 0) * K + (on ? k0 : 0);
     const int cur = recond ? (p.ctl->it & 1) : 0;
     real *Pb = cur ? p.P1 : p.P0, *Fb = cur ? p.F1 : p.F0;
@@ -236,7 +237,7 @@ __global__ void __launch_bounds__(256) simplex_precond_kernel(SP<real> p, const 
     real P[LPT], q[LPT], S[LPT], ga_old[LPT], gaq_old[LPT], sinv_old[LPT];
 #pragma unroll
     for (int i = 0; i < LPT; i++) {
-        const bool li = on && k0 + i < K;
+        const bool li = on && k0 + i < Kv;
         P[i] = li ? (recond ? Pb[vk + i] : Pinit[vk + i]) : (real) 0;
         q[i] = li ? p.Q[vk + i] : (real) 0;
         S[i] = 0;
@@ -251,7 +252,7 @@ __global__ void __launch_bounds__(256) simplex_precond_kernel(SP<real> p, const 
             const real la = p.La_d1[p.hkey[s] >> 1];
             if (!recond && k0 == 0) p.w[s] = la;                               // ref :207-208
 #pragma unroll
-            for (int i = 0; i < LPT; i++) if (k0 + i < K) {
+            for (int i = 0; i < LPT; i++) if (k0 + i < Kv) {
                 const size_t sk = (size_t) s * K + k0 + i;
                 if (!recond) { S[i] += la; Z[sk] = P[i]; }                       // ref :419-430
                 else {
@@ -268,7 +269,7 @@ __global__ void __launch_bounds__(256) simplex_precond_kernel(SP<real> p, const 
     real ga[LPT], gloc = 0;
 #pragma unroll
     for (int i = 0; i < LPT; i++) {
-        const bool li = on && k0 + i < K;
+        const bool li = on && k0 + i < Kv;
         ga[i] = li ? metric(p, v, P[i], q[i], S[i]) : (real) 0;
         gloc = max(gloc, ga[i]);
     }
@@ -276,7 +277,7 @@ __global__ void __launch_bounds__(256) simplex_precond_kernel(SP<real> p, const 
     if (on) {
         if (!recond && k0 == 0) p.Sinv[v] = (real) 1 / S[0];
 #pragma unroll
-        for (int i = 0; i < LPT; i++) if (k0 + i < K) {
+        for (int i = 0; i < LPT; i++) if (k0 + i < Kv) {
             const real sinv = (real) 1 / S[i], gaq = metric_times_info(p, v, ga[i], q[i]);
             if (p.GaU) p.GaU[vk + i] = ga[i];
             p.T[vk + i] = ga[i] * S[i]; p.GaQ[vk + i] = gaq;
@@ -300,7 +301,7 @@ __global__ void __launch_bounds__(256) simplex_precond_kernel(SP<real> p, const 
         VecN<real, LPT> pv;
 #pragma unroll
         for (int i = 0; i < LPT; i++) pv.v[i] = P[i];
-        const int i = group_argmax<real, LPT>(pv, on ? k0 : K, K, TPV);
+        const int i = group_argmax<real, LPT>(pv, on ? k0 : Kv, Kv, TPV);
         if (on && k0 == 0) p.lab[v] = i;
     }
 }
@@ -361,7 +362,7 @@ __device__ __forceinline__ double simplex_epilogue(const SP<real> &p, Ctl *ctl, 
     for (int i = 0; i < LPT; i++) {
         if (!on) { m.v[i] = (real) 1; acc.v[i] = 0; }
         xs.v[i] = acc.v[i] * fast_rcp(m.v[i]);
-        if (on && k0 + i < K) act |= 1u << i;
+        if (on && k0 + i < p.Kv) act |= 1u << i;
     }
     real la = 0;
     for (;;) {
@@ -394,7 +395,7 @@ __device__ __forceinline__ double simplex_epilogue(const SP<real> &p, Ctl *ctl, 
     }
     double red = 0.0;
     if (p.by_label) {                                                         // ref :657-676
-        const int i = group_argmax<real, LPT>(pnew, on ? k0 : K, K, TPV);
+        const int i = group_argmax<real, LPT>(pnew, on ? k0 : p.Kv, p.Kv, TPV);
         if (on && k0 == 0 && ctl->track) { if (i != p.lab[v]) { red = 1.0; p.lab[v] = i; } }
     } else if (on) {                                                          // ref :681-687
         real d = 0;
@@ -610,8 +611,25 @@ template <typename real>
 __global__ void simplex_extract_kernel(SP<real> p, real *__restrict__ out)
 {
     const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (size_t) p.Vown * p.K) return;
-    out[i] = ((p.ctl->it & 1) ? p.P1 : p.P0)[i];
+    if (i >= (size_t) p.Vown * p.Kv) return;
+    const size_t v = i / p.Kv, k = i - v * p.Kv;                               // out has the caller's row stride Kv
+    out[i] = ((p.ctl->it & 1) ? p.P1 : p.P0)[v * p.K + k];
+}
+
+// K-vectors of the caller (row stride Kv) into rows of stride K >= Kv, the extra labels zero
+template <typename real>
+__global__ void simplex_pack_kernel(const real *__restrict__ in, real *__restrict__ out, size_t V, int Kv, int K)
+{
+    const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= V * (size_t) K) return;
+    const size_t v = i / K, k = i - v * K;
+    out[i] = k < (size_t) Kv ? in[v * Kv + k] : (real) 0;
+}
+template <typename real>
+__global__ void simplex_fill_kernel(real *__restrict__ out, size_t n, real x)
+{
+    const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = x;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -646,7 +664,8 @@ struct SimplexSolver : SolverBase {
 
     void setup()
     {
-        const int K = q.K, V = q.V, E = q.E;
+        const int Kv = q.K, V = q.V, E = q.E;
+        int K = Kv;                                           // row stride of every K-vector on the device
         PFDR_REQUIRE(K >= 1 && V > 0 && E >= 0 && q.itMax >= 0, "K, V must be positive, E and itMax non-negative");
         PFDR_REQUIRE(q.al >= (real) 0 && q.al <= (real) 1, "al must lie in [0, 1] (the reference is undefined beyond, SURVEY 5.1-10)");
         sharded = q.shard != nullptr;
@@ -659,7 +678,12 @@ struct SimplexSolver : SolverBase {
         // float64: two labels per lane (one 16-byte access) halve the registers of a lane -> twice the resident warps
         if (sizeof(real) == 8 && K % 2 == 0 && K <= 64 && !(fl && fl[0] == '4')) LPT = 2;
         if (fl && fl[0] == '1') LPT = 1;
-        PFDR_REQUIRE((K + LPT - 1) / LPT <= 32, "this build supports K <= 32 labels, or K <= 128 when K is a multiple of 4");
+        // More labels than 32 lanes can hold at this many labels per lane (K > 32 and not a multiple of 4, or the
+        // forced scalar path): rows are padded to a multiple of 4 labels on the device, the extra labels stay
+        // exactly 0 and never enter a projection, an arg-max or a sum (masks on Kv), four labels per lane.
+        const bool padded = (K + LPT - 1) / LPT > 32 || (fl && fl[0] == 'p' && K % 4 != 0);
+        if (padded) { K = (Kv + 3) & ~3; LPT = 4; }
+        PFDR_REQUIRE((K + LPT - 1) / LPT <= 32, "this build supports K <= 128 labels");
         cudaStream_t st = ctx().stream;
         for (auto *e : {&ev[0], &ev[1], &ev_a, &ev_b, &ev_c}) *e = event_get();
         PFDR_CUDA(cudaEventRecord(ev_a, st));
@@ -670,8 +694,15 @@ struct SimplexSolver : SolverBase {
         const int C = 32 / TPV;
         int logC = 0; while ((1 << logC) < C) logC++;
         const size_t VK = (size_t) V * K;
-        Eu.bind(q.Eu, E); Ev.bind(q.Ev, E); Q.bind(q.Q, VK); La_d1.bind(q.La_d1, E);
-        La_f.bind(q.al > (real) 0 ? q.La_f : nullptr, V); P0.bind(q.P, VK);
+        Eu.bind(q.Eu, E); Ev.bind(q.Ev, E); Q.bind(q.Q, (size_t) V * Kv); La_d1.bind(q.La_d1, E);
+        La_f.bind(q.al > (real) 0 ? q.La_f : nullptr, V); P0.bind(q.P, (size_t) V * Kv);
+        if (padded) {
+            DevBuf<real> Qp(VK), Pp(VK);
+            PFDR_LAUNCH(simplex_pack_kernel<real>, cdiv(VK, 256), 256, 0, Q.p, Qp.p, (size_t) V, Kv, K);
+            PFDR_LAUNCH(simplex_pack_kernel<real>, cdiv(VK, 256), 256, 0, P0.p, Pp.p, (size_t) V, Kv, K);
+            Q.own = std::move(Qp); Q.p = Q.own.p;
+            P0.own = std::move(Pp); P0.p = P0.own.p;
+        }
         if (LPT > 1 && ((uintptr_t) Q.p) % 32 != 0) {           // vector loads of Q (quadratic loss) need alignment
             Qal.alloc(VK);
             PFDR_CUDA(cudaMemcpyAsync(Qal.p, Q.p, VK * sizeof(real), cudaMemcpyDeviceToDevice, st));
@@ -683,6 +714,10 @@ struct SimplexSolver : SolverBase {
         Pa.alloc(VK); Pb.alloc(VK); Fa.alloc(VK); Fb.alloc(VK); T.alloc(VK); GaQ.alloc(VK); Sinv.alloc(V);
         if (q.difRcd > (real) 0) GaU.alloc(VK);
         Z0.zero(); Z1.zero(); w.zero();
+        if (padded) {           // what the extra labels read: T = 1 (a denominator), everything else 0
+            Pa.zero(); Pb.zero(); Fa.zero(); Fb.zero(); GaQ.zero();
+            PFDR_LAUNCH(simplex_fill_kernel<real>, cdiv(VK, 256), 256, 0, T.p, VK, (real) 1);
+        }
         const bool by_label = q.difTol >= (real) 1;
         if (by_label) lab.alloc(V);
         if (q.Obj) dObj.alloc((size_t) q.itMax + 1);
@@ -709,10 +744,10 @@ struct SimplexSolver : SolverBase {
                 p.order = order.p;
             }
         }
-        p.ctl = ctl.p; p.K = K; p.V = V; p.E = E; p.TPV = TPV; p.C = C; p.logC = logC; p.logTPV = logTPV; p.LPT = LPT;
+        p.ctl = ctl.p; p.K = K; p.Kv = Kv; p.V = V; p.E = E; p.TPV = TPV; p.C = C; p.logC = logC; p.logTPV = logTPV; p.LPT = LPT;
         p.loss = (q.al == (real) 0) ? LOSS_LIN : (q.al == (real) 1 ? LOSS_QUAD : LOSS_KLA);
         p.by_label = by_label;
-        p.aK = q.al / (real) K; p.a1 = (real) 1 - q.al; p.aK1 = p.aK / p.a1;                     // ref :386-391
+        p.aK = q.al / (real) Kv; p.a1 = (real) 1 - q.al; p.aK1 = p.aK / p.a1;                     // ref :386-391
         p.rho = q.rho; p.condMin = q.condMin;
         p.slice_off = g.slice_off.p; p.nbr = g.nbr.p; p.twin = g.twin.p; p.hkey = g.hkey.p;
         p.w = w.p; p.wk = nullptr; p.thk = nullptr; p.Z0 = Z0.p; p.Z1 = Z1.p;
@@ -763,7 +798,7 @@ struct SimplexSolver : SolverBase {
         if (MB < 0) { const char *e = getenv("PFDR_B200_MINB"); MB = e ? atoi(e) : 0; }
         (void) U;
         constexpr int MBD = (sizeof(real) == 4 || L == 2) ? 4 : 2;
-        const bool small = (size_t) std::max<long long>(g.nslots, q.V) * (size_t) q.K < 0xFFFFFFFFull;
+        const bool small = (size_t) std::max<long long>(g.nslots, q.V) * (size_t) p.K < 0xFFFFFFFFull;
         static int i32 = -1;
         if (i32 < 0) { const char *e = getenv("PFDR_B200_IDX32"); i32 = (e && e[0] == '0') ? 0 : 1; }
         (void) U; (void) MB;
@@ -787,7 +822,7 @@ struct SimplexSolver : SolverBase {
     void enqueue_trip()
     {
         if (q.Obj) {
-            const size_t work = (size_t) std::max(q.E, q.V) * q.K;
+            const size_t work = (size_t) std::max(q.E, q.V) * p.K;
             PFDR_LAUNCH(simplex_objective_kernel<real>, std::min<unsigned>(cdiv(work, 256), num_sms() * 8), 256, 0, p);
         }
         if (LPT == 4) { if (p.wk) launch_iter_loss<4, true>(); else launch_iter_loss<4, false>(); }
@@ -827,9 +862,10 @@ struct SimplexSolver : SolverBase {
     void recondition()
     {
         if (!wk.p) {
-            const size_t n = (size_t) std::max<long long>(g.nslots, 1) * q.K, VK = (size_t) q.V * q.K;
+            const size_t n = (size_t) std::max<long long>(g.nslots, 1) * p.K, VK = (size_t) q.V * p.K;
             wk.alloc(n); thk.alloc(n); wk.zero(); thk.zero();
             Sinvk.alloc(VK); Gn.alloc(VK);
+            if (p.K != p.Kv) { Sinvk.zero(); Gn.zero(); }                       // padded labels: defined values
         }
         p.wk = wk.p; p.thk = thk.p; p.Sinvk = Sinvk.p; p.Gn = Gn.p;
         if (gexec) { cudaGraphExecDestroy(gexec); gexec = nullptr; }
@@ -848,7 +884,7 @@ struct SimplexSolver : SolverBase {
     void run() override
     {
         cudaStream_t st = ctx().stream;
-        const size_t work = (size_t) g.nslots * q.K;
+        const size_t work = (size_t) g.nslots * p.K;
         int batch = work > (1u << 24) ? 4 : (work > (1u << 20) ? 16 : 64);
         batch = std::max(1, std::min(batch, q.itMax + 1));
         ctx().in_loop = true;
@@ -888,7 +924,7 @@ struct SimplexSolver : SolverBase {
         PFDR_CUDA(cudaMemcpyAsync(&hctl[0], ctl.p, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
         PFDR_CUDA(cudaStreamSynchronize(st));
         const Ctl h = hctl[0];
-        const size_t VK = (size_t) p.Vown * q.K;
+        const size_t VK = (size_t) p.Vown * p.Kv;
         if (Po) {
             if (is_device_ptr(Po)) PFDR_LAUNCH(simplex_extract_kernel<real>, cdiv(VK, 256), 256, 0, p, (real *) Po);
             else {

@@ -36,6 +36,24 @@ def test_simplex_parity(gpu_api, oracle, name, dtype):
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("name", ["kla", "kla_k3", "kla_k1", "kla_recond", "kla_labels", "lin", "quad_weighted", "kla_rand"])
+def test_simplex_parity_padded_rows(gpu_api, oracle, monkeypatch, name, dtype):
+    """the layout used for K > 32 not a multiple of 4 (rows padded to a multiple of 4 labels on the device, the extra
+    labels masked out of projection / arg-max / sums), forced here on small K (5, 3, 1) where every mask is exercised"""
+    from cp_pfdr_graph_d1_b200.api import _b
+    monkeypatch.setenv("PFDR_B200_LPT", "p")
+    got = problems.run_simplex(_b(), name, dtype)
+    ref = problems.run_simplex(oracle, name, dtype)
+    tol = TOL[dtype]
+    assert abs(got.it - ref.it) <= (0 if dtype is np.float64 else max(2, ref.it // 20)), (got.it, ref.it)
+    assert rel(got.X, ref.X) < tol, rel(got.X, ref.X)
+    assert got.X.shape == ref.X.shape and np.isfinite(got.X).all()
+    assert np.allclose(got.X.sum(axis=1), 1.0, atol=1e-5 if dtype is np.float32 else 1e-12) and (got.X >= 0).all()
+    n = min(got.it, ref.it)
+    assert np.allclose(got.Obj[:n + 1], ref.Obj[:n + 1], rtol=tol, atol=tol * max(float(np.abs(ref.Obj).max()), 1.0) * 1e-1)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
 @pytest.mark.parametrize("D", [1, 2, 5, 16, 32, 33, 100])
 def test_proj_simplex_metric(gpu_api, oracle, dtype, D):
     rng = np.random.default_rng(D)
