@@ -673,16 +673,17 @@ struct SimplexSolver : SolverBase {
             PFDR_REQUIRE(q.Obj == nullptr && q.difRcd == (real) 0, "sharded solves do not record Obj nor recondition in this build");
             PFDR_REQUIRE(q.shard->Vown > 0 && q.shard->Vown <= V, "bad shard: Vown");
         }
+        // Labels per lane: 4 in float32 (one 16-byte access per piece of a K-vector), 2 in float64 when that fits 32 lanes
+        // (half the registers of a lane, twice the resident warps), else 4.  When K is not a multiple of it, rows are
+        // padded on the device: the extra labels stay exactly 0 and never enter a projection, an arg-max or a sum
+        // (masks on Kv).  Measured on a 64^3 grid in float32: K = 5 / 13 / 21 run 2.0 / 2.5 / 2.7 x faster than with one
+        // label per lane (profiles/r01_notes.md).  PFDR_B200_LPT=1 forces one label per lane, =4 four (float64).
         const char *fl = getenv("PFDR_B200_LPT");
-        LPT = (K % 4 == 0) ? 4 : 1;
-        // float64: two labels per lane (one 16-byte access) halve the registers of a lane -> twice the resident warps
-        if (sizeof(real) == 8 && K % 2 == 0 && K <= 64 && !(fl && fl[0] == '4')) LPT = 2;
-        if (fl && fl[0] == '1') LPT = 1;
-        // More labels than 32 lanes can hold at this many labels per lane (K > 32 and not a multiple of 4, or the
-        // forced scalar path): rows are padded to a multiple of 4 labels on the device, the extra labels stay
-        // exactly 0 and never enter a projection, an arg-max or a sum (masks on Kv), four labels per lane.
-        const bool padded = (K + LPT - 1) / LPT > 32 || (fl && fl[0] == 'p' && K % 4 != 0);
-        if (padded) { K = (Kv + 3) & ~3; LPT = 4; }
+        LPT = 4;
+        if (sizeof(real) == 8 && ((Kv + 1) & ~1) <= 64 && !(fl && fl[0] == '4')) LPT = 2;
+        if (Kv <= 2 || (fl && fl[0] == '1' && Kv <= 32)) LPT = 1;
+        K = ((Kv + LPT - 1) / LPT) * LPT;
+        const bool padded = K != Kv;
         PFDR_REQUIRE((K + LPT - 1) / LPT <= 32, "this build supports K <= 128 labels");
         cudaStream_t st = ctx().stream;
         for (auto *e : {&ev[0], &ev[1], &ev_a, &ev_b, &ev_c}) *e = event_get();

@@ -37,11 +37,11 @@ def test_simplex_parity(gpu_api, oracle, name, dtype):
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 @pytest.mark.parametrize("name", ["kla", "kla_k3", "kla_k1", "kla_recond", "kla_labels", "lin", "quad_weighted", "kla_rand"])
-def test_simplex_parity_padded_rows(gpu_api, oracle, monkeypatch, name, dtype):
-    """the layout used for K > 32 not a multiple of 4 (rows padded to a multiple of 4 labels on the device, the extra
-    labels masked out of projection / arg-max / sums), forced here on small K (5, 3, 1) where every mask is exercised"""
+def test_simplex_parity_scalar_lanes(gpu_api, oracle, monkeypatch, name, dtype):
+    """K not a multiple of the labels per lane runs on padded rows by default (test_simplex_parity: K = 5, 3, 33, 50,
+    127 ...); this forces the one-label-per-lane kernels (the default only for K <= 2) on the same cases"""
     from cp_pfdr_graph_d1_b200.api import _b
-    monkeypatch.setenv("PFDR_B200_LPT", "p")
+    monkeypatch.setenv("PFDR_B200_LPT", "1")
     got = problems.run_simplex(_b(), name, dtype)
     ref = problems.run_simplex(oracle, name, dtype)
     tol = TOL[dtype]
