@@ -680,7 +680,10 @@ struct SimplexSolver : SolverBase {
         // label per lane (profiles/r01_notes.md).  PFDR_B200_LPT=1 forces one label per lane, =4 four (float64).
         const char *fl = getenv("PFDR_B200_LPT");
         LPT = 4;
-        if (sizeof(real) == 8 && ((Kv + 1) & ~1) <= 64 && !(fl && fl[0] == '4')) LPT = 2;
+        // (two labels per lane win on mid-size problems - 64^3 x 16 labels: 16.4 vs 16.9 ms per 100 iterations - and lose on
+        //  the full-size tiled sweep - 252^3: 10.4 vs 10.0 ms per iteration: chosen by size, PFDR_B200_LPT=2 / 4 force)
+        if (sizeof(real) == 8 && ((Kv + 1) & ~1) <= 64 && !(fl && fl[0] == '4') &&
+            ((size_t) V * (size_t) Kv <= ((size_t) 1 << 23) || (fl && fl[0] == '2'))) LPT = 2;
         if (Kv <= 2 || (fl && fl[0] == '1' && Kv <= 32)) LPT = 1;
         K = ((Kv + LPT - 1) / LPT) * LPT;
         const bool padded = K != Kv;
