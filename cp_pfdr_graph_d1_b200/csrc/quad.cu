@@ -975,9 +975,13 @@ __global__ void __launch_bounds__(512, 1) quad_push_kernel(QP<real> p, PushArgs<
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5, nt = blockDim.x;
     const int V = p.V, N = p.N, E = p.E, itMax = ctl->itMax, track = ctl->track;
     const int Vq = a.nslices * 32, Nq = N > 0 ? ((N + 3) & ~3) : 0, nso = a.nso;
-    unsigned long long *mbars = reinterpret_cast<unsigned long long *>(push_smem);   // 0: Z, 1: X (+P, sums), 2: partial A x, 3: P (dense)
-    double *sums = reinterpret_cast<double *>(push_smem + 64);   // [16][2] evolution sums of the CTAs
-    double *red = sums + 32;                                     // [64]
+    // mbarriers: 0 Z, 1 / 4 X (+P, sums, partial A x) of even / odd iterations, 2 partial A x (first iteration), 3 P (dense).
+    // A CTA with no edge into a slow CTA's vertices can run one iteration ahead of it: what it pushes for iteration
+    // it + 1 must neither be counted in the slow CTA's still open phase of iteration it (two X barriers, by parity)
+    // nor overwrite sums it has not read yet (two sets of sums).
+    unsigned long long *mbars = reinterpret_cast<unsigned long long *>(push_smem);
+    double *sums = reinterpret_cast<double *>(push_smem + 64);   // [2][16][2] evolution sums of the CTAs, by iteration parity
+    double *red = sums + 64;                                     // [64]
     real *Xs = reinterpret_cast<real *>(red + 64);               // [2][Vq] iterate         } replicas, by iteration parity
     real *Ps = Xs + 2 * Vq;                                      // [2][Vq] forward point   }
     real *Ts = Ps + 2 * Vq;                                      // [Vq]    Ga.S
@@ -992,12 +996,12 @@ __global__ void __launch_bounds__(512, 1) quad_push_kernel(QP<real> p, PushArgs<
     const int sl0 = a.slb[rank], sl1 = a.slb[rank + 1];
     const int v0 = sl0 * 32, v1 = min(V, sl1 * 32), v1q = sl1 * 32;
     const int e0 = (int) ((long long) E * rank / C), e1 = (int) ((long long) E * (rank + 1) / C);
-    const uint32_t mb0 = smem_u32(mbars), mb1 = mb0 + 8, mb2 = mb0 + 16, mb3 = mb0 + 24;
+    const uint32_t mb0 = smem_u32(mbars), mb2 = mb0 + 16, mb3 = mb0 + 24;
     int it = ctl->it;
     if (tid <= C) s0r[tid] = (int) p.slice_off[a.slb[tid]];
     for (int q = tid; q <= sl1 - sl0; q += nt) sbase[q] = (int) p.slice_off[sl0 + q];
     if (tid == 0) {
-        for (int k = 0; k < 4; k++) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mb0 + 8 * k), "r"(1));
+        for (int k = 0; k < 5; k++) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mb0 + 8 * k), "r"(1));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -1050,7 +1054,7 @@ __global__ void __launch_bounds__(512, 1) quad_push_kernel(QP<real> p, PushArgs<
     const real tol = (real) ctl->tol, rho = p.rho, thc0 = p.thc0;
     const double eps = ctl->eps;
     double dif = ctl->dif;
-    int phZ = 0, phX = 0, phA = 0, phP = 0, cb = 0;
+    int phZ = 0, phA = 0, phP = 0, cb = 0;
     const int it_start = it;
     const int *__restrict__ nbr = p.nbr;
     const uint32_t own_bytes = (uint32_t) ((v1q - v0) * sizeof(real)), all_bytes = (uint32_t) (Vq * sizeof(real));
@@ -1076,6 +1080,9 @@ __global__ void __launch_bounds__(512, 1) quad_push_kernel(QP<real> p, PushArgs<
     for (;;) {
         if (it == itMax || (real) dif < tol) break;                           // ref :429 (uniform over the cluster)
         const int nb = cb ^ 1, zb = it & 1;
+        const int rel_it = it - it_start;                                     // X barrier and sums of this iteration's parity
+        const uint32_t mb1 = mb0 + ((rel_it & 1) ? 32 : 8);
+        double *sums_it = sums + (rel_it & 1) * 32;
         real *Xc = Xs + cb * Vq, *Pc = Ps + cb * Vq, *Xn = Xs + nb * Vq, *Pn = Ps + nb * Vq, *Zc = Zs + zb * nso;
         SPROF(0)
         // ---- forward point for dense operators (ref S1, S4, S6), own columns ----
@@ -1220,7 +1227,7 @@ __global__ void __launch_bounds__(512, 1) quad_push_kernel(QP<real> p, PushArgs<
             if (tid < C) {
                 double d = 0.0, c = 0.0;
                 for (int w = 0; w < nw; w++) { d += rb[2 * w]; c += rb[2 * w + 1]; }
-                push_pair(map_rank(smem_u32(sums + 2 * rank), tid), d, c, map_rank(mb1, tid));
+                push_pair(map_rank(smem_u32(sums_it + 2 * rank), tid), d, c, map_rank(mb1, tid));
             }
             push_chunks(Xn + v0, own_bytes, rank, C, mb1);
             if (N == 0) push_chunks(Pn + v0, own_bytes, rank, C, mb1);
@@ -1232,12 +1239,12 @@ __global__ void __launch_bounds__(512, 1) quad_push_kernel(QP<real> p, PushArgs<
         }
         SPROF(5)
         GSTAMP(4)
-        mbar_wait(mb1, phX);
+        { int phX = (rel_it >> 1) & 1; mbar_wait(mb1, phX); }
         SPROF(6)
         GSTAMP(5)
         if (track) {
             double d = 0.0, c = 0.0;
-            for (int q = 0; q < C; q++) { d += sums[2 * q]; c += sums[2 * q + 1]; }           // rank order: same bits everywhere
+            for (int q = 0; q < C; q++) { d += sums_it[2 * q]; c += sums_it[2 * q + 1]; }     // rank order: same bits everywhere
             dif = (c > eps) ? d / c : d / eps;
             if (rank == 0 && tid == 0 && p.dDif) p.dDif[it] = (real) dif;
         }
@@ -1991,7 +1998,7 @@ struct QuadSolver : SolverBase {
             }
             for (int c = C + 1; c <= 16; c++) a.slb[c] = S;
             a.nso = (int) ((nso + 3) & ~3LL);
-            const size_t sm = 64 + 256 + 512 + (5 * Vq + 2 * (size_t) a.nso + 17 * Nq) * sizeof(real);
+            const size_t sm = 64 + 512 + 512 + (5 * Vq + 2 * (size_t) a.nso + 17 * Nq) * sizeof(real);
             bool fits = sm <= 200 * 1024;
             for (int c = 0; c < C; c++) fits = fits && a.slb[c + 1] - a.slb[c] <= SMALL_MAX_SLICES;
             if (fits) {
