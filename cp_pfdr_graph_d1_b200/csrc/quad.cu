@@ -38,6 +38,8 @@ struct QP {                       // kernel parameter block
     double *amp_sums;             // [2] amplitude sums (all-reduced)
     double *rsum;                 // [N] sum of A x over this rank's columns (sharded dense A)
     const long long *slice_off; const int *nbr, *twin, *hkey;
+    const int4 *pk;               // per slot {nbr, twin, w, [threshold]} in 16 bytes: one vector load per row in the iteration kernel
+    const int2 *pk2;              // per slot {nbr, twin}: float32 before a reconditioning (16 bytes would carry an unused word)
     real *w;                      // [slots] raw d1 weight of the half-edge's edge
     real *thc;                    // [slots] La_d1/w after a reconditioning (NULL: thc0 for all)
     real thc0;
@@ -369,9 +371,34 @@ __global__ void __launch_bounds__(256) quad_iter_kernel(QP<real> p)
     }
 }
 
+// The iteration-invariant per-slot data side by side, 16 bytes per slot: float32 {nbr, twin, w, La_d1/w}, float64
+// {nbr, twin, w}.  One 128-bit load per row replaces three or four 32/64-bit ones (fewer instructions in a kernel bound
+// by its dependent instruction stream, fewer concurrent DRAM streams): C2 f32 51.2 -> 46.4 us per iteration with the
+// index pair alone (profiles/r01_notes.md).  Rebuilt after every (re)conditioning; the other kernels keep the plain arrays.
+template <typename real>
+__global__ void pack_slots_kernel(QP<real> p, int4 *__restrict__ pk, long long nslots)
+{
+    const long long s = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nslots) return;
+    const real w = p.w[s];
+    int4 r;
+    r.x = p.nbr[s]; r.y = p.twin[s];
+    if (pk == nullptr) { const_cast<int2 *>(p.pk2)[s] = make_int2(r.x, r.y); return; }
+    if (sizeof(real) == 4) { r.z = __float_as_int((float) w); r.w = __float_as_int((float) (p.thc ? p.thc[s] : p.thc0)); }
+    else { r.z = __double2loint((double) w); r.w = __double2hiint((double) w); }
+    pk[s] = r;
+}
+template <typename real>
+__device__ __forceinline__ void unpack_slot(const int4 r, int &n, int &tw, real &w, real &th)
+{
+    n = r.x; tw = r.y;
+    if (sizeof(real) == 4) { w = (real) __int_as_float(r.z); th = (real) __int_as_float(r.w); }
+    else w = (real) __hiloint2double(r.w, r.z);
+}
+
 // Pipelined variant: one row at a time, the next row's indices / weight / own copy are requested while the
 // current row's gathers are in flight (as simplex_iter_kernel).  Few registers -> up to 64 warps per SM.
-template <typename real, bool PER_SLOT_TH, int MINB, bool HUB>
+template <typename real, bool PER_SLOT_TH, int MINB, bool HUB, int NT = 0>
 __global__ void __launch_bounds__(256, MINB) quad_iter_pipe_kernel(QP<real> p)
 {
     __shared__ double smem[64];
@@ -407,7 +434,15 @@ __global__ void __launch_bounds__(256, MINB) quad_iter_pipe_kernel(QP<real> p)
         Tv = Tg[v]; Sv = p.Sinv[v];
         int n_c = -1, tw_c = 0;
         real w_c = 0, zo_c = 0, th_c = p.thc0;
-        if (wl > 0) { n_c = nbr[s]; tw_c = twin[s]; w_c = wg[s]; zo_c = Zin[s]; if (PER_SLOT_TH) th_c = p.thc[s]; }
+        if (wl > 0) {
+            if (NT == 2) {
+                real th_pk = th_c;
+                unpack_slot<real>(__ldg(p.pk + s), n_c, tw_c, w_c, th_pk);
+                if (PER_SLOT_TH) th_c = sizeof(real) == 4 ? th_pk : p.thc[s];
+            } else if (NT == 1) { const int2 t = __ldg(p.pk2 + s); n_c = t.x; tw_c = t.y; w_c = wg[s]; if (PER_SLOT_TH) th_c = p.thc[s]; }
+            else { n_c = nbr[s]; tw_c = twin[s]; w_c = wg[s]; if (PER_SLOT_TH) th_c = p.thc[s]; }
+            zo_c = Zin[s];
+        }
         for (int j = 0; j < wl; j++, s += 32) {
             const bool live = n_c >= 0;
             real pn = 0, Tn = 1, zt = 0;
@@ -415,8 +450,15 @@ __global__ void __launch_bounds__(256, MINB) quad_iter_pipe_kernel(QP<real> p)
             int n_n = -1, tw_n = 0;
             real w_n = 0, zo_n = 0, th_n = p.thc0;
             if (j + 1 < wl) {
-                n_n = nbr[s + 32]; tw_n = twin[s + 32]; w_n = wg[s + 32]; zo_n = Zin[s + 32];
-                if (PER_SLOT_TH) th_n = p.thc[s + 32];
+                if (NT == 2) {
+                    real th_pk = th_n;
+                    unpack_slot<real>(__ldg(p.pk + s + 32), n_n, tw_n, w_n, th_pk);
+                    if (PER_SLOT_TH) th_n = sizeof(real) == 4 ? th_pk : p.thc[s + 32];
+                } else if (NT == 1) {
+                    const int2 t = __ldg(p.pk2 + s + 32); n_n = t.x; tw_n = t.y; w_n = wg[s + 32];
+                    if (PER_SLOT_TH) th_n = p.thc[s + 32];
+                } else { n_n = nbr[s + 32]; tw_n = twin[s + 32]; w_n = wg[s + 32]; if (PER_SLOT_TH) th_n = p.thc[s + 32]; }
+                zo_n = Zin[s + 32];
             }
             if (live) {
                 const real tsum = Tv + Tn, inv = fast_rcp(tsum);
@@ -1627,6 +1669,8 @@ struct QuadSolver : SolverBase {
     DevIn<int> Eu, Ev;
     DevBuf<real> w, thc, Z0, Z1, X0b, X1b, P0b, P1b, T, Sinv, Ga, Ga0, G, Thl1, R, AtY, dObj, dDif, Xout;
     DevBuf<double> partial, parts, sums, rsum, amp_sums;
+    DevBuf<int4> pkb;               // per-slot packs for the iteration kernel
+    DevBuf<int2> pk2b;
     DevBuf<int> pos, dstb;          // small mode: slot / (owner CTA, slot) of every half-edge key
     DevBuf<real> ze, sparts, ws;        //             edge-ordered copies, partial A x of the CTAs
     DevBuf<double> xsum;            //             partial sums of the CTAs
@@ -1698,6 +1742,7 @@ struct QuadSolver : SolverBase {
         p.world = sharded ? comm().world : 1; p.rank = sharded ? comm().rank : 0;
         p.slice_off = g.slice_off.p; p.nbr = g.nbr.p; p.twin = g.twin.p; p.hkey = g.hkey.p;
         p.w = w.p; p.thc = nullptr; p.thc0 = 0; p.Z0 = Z0.p; p.Z1 = Z1.p;
+        p.pk = nullptr; p.pk2 = nullptr;           // set by pack_slots() after each (re)conditioning (PFDR_B200_PACK=0: off)
         p.X0 = X0b.p; p.X1 = X1b.p; p.P0 = P0b.p; p.P1 = P1b.p; p.T = T.p; p.Sinv = Sinv.p; p.Ga = Ga.p; p.Ga0 = Ga0.p; p.G = G.p; p.Thl1 = Thl1.p;
         p.R = R.p; p.AtY = AtY.p; p.Y = Y.p; p.A = A.p; p.La_d1 = La_d1.p; p.La_l1 = La_l1.p; p.L = L.p;
         p.Eu = Eu.p; p.Ev = Ev.p; p.Ltype = q.Ltype; p.positivity = q.positivity; p.prox_kind = q.prox_kind;
@@ -1762,6 +1807,21 @@ struct QuadSolver : SolverBase {
         const real thc0 = (real) 1 / (real) hctl[1].amp;       // La_d1 / (c La_d1)
         if (gexec && thc0 != p.thc0) { cudaGraphExecDestroy(gexec); gexec = nullptr; }
         p.thc0 = thc0;
+        pack_slots();
+    }
+
+    // float32 before a reconditioning: {nbr, twin} in 8 bytes (the weight stays a separate stream: 16 bytes would carry
+    // an unused word: -4 % instead of -9.5 % on C2).  float64, and float32 with per-slot thresholds: 16 bytes.
+    void pack_slots()
+    {
+        const char *e = getenv("PFDR_B200_PACK");
+        p.pk = nullptr; p.pk2 = nullptr;
+        if (e && e[0] == '0') return;
+        const size_t ns = (size_t) std::max<long long>(g.nslots, 1);
+        // (buffers are kept across reset(): a captured graph holds their addresses)
+        if (sizeof(real) == 4 && !p.thc && !(e && e[0] == '4')) { if (pk2b.n != ns) pk2b.alloc(ns); p.pk2 = pk2b.p; }
+        else { if (pkb.n != ns) pkb.alloc(ns); p.pk = pkb.p; }
+        PFDR_LAUNCH(pack_slots_kernel<real>, cdiv(ns, 256), 256, 0, p, (int4 *) p.pk, g.nslots);
     }
 
     void launch_atr(int mode)
@@ -1816,10 +1876,15 @@ struct QuadSolver : SolverBase {
         static int pipe = -1;
         if (pipe < 0) { const char *e = getenv("PFDR_B200_PIPE"); pipe = e ? atoi(e) : (sizeof(real) == 4 ? 8 : 6); }
         if (mode == 1 && pipe > 0) {
-#define PFDR_PIPE(MB, HB)                                                                              \
-            do {                                                                                       \
-                if (p.thc) PFDR_LAUNCH((quad_iter_pipe_kernel<real, true, MB, HB>), ogrid, 256, 0, p); \
-                else PFDR_LAUNCH((quad_iter_pipe_kernel<real, false, MB, HB>), ogrid, 256, 0, p);      \
+#define PFDR_PIPE(MB, HB)                                                                                       \
+            do {                                                                                                \
+                if (p.pk && !(HB)) {                                                                            \
+                    if (p.thc) PFDR_LAUNCH((quad_iter_pipe_kernel<real, true, MB, false, 2>), ogrid, 256, 0, p);     \
+                    else PFDR_LAUNCH((quad_iter_pipe_kernel<real, false, MB, false, 2>), ogrid, 256, 0, p);          \
+                } else if (p.pk2 && !p.thc && !(HB)) {                                                          \
+                    PFDR_LAUNCH((quad_iter_pipe_kernel<real, false, MB, false, 1>), ogrid, 256, 0, p);               \
+                } else if (p.thc) PFDR_LAUNCH((quad_iter_pipe_kernel<real, true, MB, HB>), ogrid, 256, 0, p);   \
+                else PFDR_LAUNCH((quad_iter_pipe_kernel<real, false, MB, HB>), ogrid, 256, 0, p);               \
             } while (0)
             // a slice wider than HUB_ROWS (a hub vertex): variant whose warps share the hub's rows (PFDR_B200_HUB=0: off)
             const char *he = getenv("PFDR_B200_HUB");
@@ -1891,6 +1956,7 @@ struct QuadSolver : SolverBase {
         if (gexec) { cudaGraphExecDestroy(gexec); gexec = nullptr; }   // kernel parameters changed
         PFDR_LAUNCH(amp_kernel<real>, vgrid, 256, 0, p, 1);
         PFDR_LAUNCH(recond_vertex_kernel<real>, vgrid, 256, 0, p);
+        pack_slots();
         PFDR_LAUNCH(resume_kernel<real>, 1, 1, 0, p, 0.01);                   // ref :458
     }
 
