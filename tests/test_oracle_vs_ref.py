@@ -93,6 +93,18 @@ def test_simplex(oracle, reference, dtype, al, variant):
     assert np.allclose(a.X.sum(axis=1), 1, atol=1e-4 if dtype is np.float32 else 1e-10)
 
 
+@pytest.mark.parametrize("K", [1, 3, 16, 33, 50])
+def test_simplex_label_counts(oracle, reference, K):
+    """pins the oracle for the label counts the GPU parity cases use (tests/problems.py: K = 1 ... 127), among
+    them more than 32 labels and counts that are not a multiple of 4"""
+    w = synth.c4_simplex(5, K, np.float64)
+    kw = dict(rho=1.5, condMin=1e-2, difRcd=1e-2, difTol=1e-5, itMax=120, want_obj=True, want_dif=True)
+    a, b = (be.PFDR_graph_loss_d1_simplex(w["Q"].copy(), w["Q"], 0.05, w["Eu"], w["Ev"], w["La_d1"], **kw)
+            for be in (oracle, reference))
+    assert a.it == b.it and rel(a.X, b.X) < 1e-9
+    assert np.allclose(a.Obj[:a.it], b.Obj[:a.it], rtol=1e-8)
+
+
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 def test_proj_simplex_metric(oracle, reference, dtype):
     rng = np.random.default_rng(11)
