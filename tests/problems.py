@@ -103,6 +103,29 @@ QUAD_CASES = ["grid_identity", "grid_diag", "grid_diag_l1_pos", "grid_diag_l1", 
               "dense_direct_recond", "dense_ata", "dense_ata_odd", "dense_ata_box", "dense_ata_recond"]
 
 
+def irregular_case(V, kind, dt=np.float64):
+    """multigraph with self-loops, duplicate edges and (V > 8) a hub; diagonal, dense N x V or Gram operator; l1 + positivity"""
+    rng = np.random.default_rng(V * 7 + len(kind))
+    Eu, Ev = random_graph(V, 2 * V, V, self_loops=min(3, V), dups=min(5, V), hub=V > 8)
+    E = Eu.shape[0]
+    if kind == "diag":
+        A = rng.uniform(0.5, 1.5, V); Y = A * np.round(rng.uniform(0, 3, V)); N, Lt, L = 0, 1, A
+    else:
+        M = max(3, V // 3)
+        B = rng.normal(0, 1, (M, V))
+        lam = float(np.linalg.eigvalsh(B.T @ B).max())
+        x0 = np.round(rng.uniform(0, 2, V))
+        if kind == "dense":
+            A, Y, N = np.asfortranarray(B), B @ x0, M
+        else:
+            A, Y, N = np.asfortranarray(B.T @ B), B.T @ (B @ x0), -V
+        Lt, L = 0, np.array([lam])
+    La_d1 = rng.uniform(0.05, 0.5, E)
+    args = (np.zeros(V, dt), Y.astype(dt), A.astype(dt), Eu, Ev, La_d1.astype(dt), np.full(V, 0.01, dt), 1, Lt, L.astype(dt))
+    kw = dict(N=N, rho=1.5, condMin=1e-3, difRcd=0.0, difTol=1e-7, itMax=400, want_obj=False, want_dif=True)
+    return "l1", args, kw
+
+
 def run_quad(binder, name, dtype, **override):
     fam, args, kw = quad_case(name, dtype)
     kw.update(override)

@@ -147,41 +147,29 @@ def test_resident_handle_matches_one_shot(gpu_api, dtype):
 
 @pytest.mark.parametrize("V", [2, 5, 31, 32, 33, 64, 100, 257, 1000, 3000])
 @pytest.mark.parametrize("kind", ["diag", "dense", "ata"])
-def test_paths_agree_on_irregular_graphs(gpu_api, monkeypatch, V, kind):
+def test_paths_agree_on_irregular_graphs(gpu_api, oracle, monkeypatch, V, kind):
     """the three schedules of the quadratic solver (one kernel per iteration; cluster kernel exchanging through L2;
     cluster kernel exchanging through shared-memory pushes) on multigraphs with self-loops, duplicate edges and a hub,
-    from two vertices up: same iteration count, same minimiser to rounding (float64)"""
+    from two vertices up: same iteration count, same minimiser to rounding (float64), and the oracle's minimiser
+    (pinned against the reference on the same inputs by tests/test_oracle_vs_ref.py)"""
     from cp_pfdr_graph_d1_b200.api import _b
     if kind != "diag" and V > 1000:
         pytest.skip("dense operator: small sizes only")
-    rng = np.random.default_rng(V * 7 + len(kind))
-    Eu, Ev = problems.random_graph(V, 2 * V, V, self_loops=min(3, V), dups=min(5, V), hub=V > 8)
-    E = Eu.shape[0]
-    dt = np.float64
-    if kind == "diag":
-        A = rng.uniform(0.5, 1.5, V); Y = A * np.round(rng.uniform(0, 3, V)); N, Lt, L = 0, 1, A
-    else:
-        M = max(3, V // 3)
-        B = rng.normal(0, 1, (M, V))
-        lam = float(np.linalg.eigvalsh(B.T @ B).max())
-        x0 = np.round(rng.uniform(0, 2, V))
-        if kind == "dense":
-            A, Y, N = np.asfortranarray(B), B @ x0, M
-        else:
-            A, Y, N = np.asfortranarray(B.T @ B), B.T @ (B @ x0), -V
-        Lt, L = 0, np.array([lam])
-    La_d1 = rng.uniform(0.05, 0.5, E)
+    fam, args, kw = problems.irregular_case(V, kind)
+
+    def fresh():
+        return tuple(x.copy() if isinstance(x, np.ndarray) else x for x in args)
     res = {}
     for mode, env in (("large", {"PFDR_B200_SMALL": "0"}), ("l2", {"PFDR_B200_SMALL": "1", "PFDR_B200_PUSH": "0"}),
                       ("push", {"PFDR_B200_SMALL": "1", "PFDR_B200_PUSH": "1"})):
         for k, v in env.items():
             monkeypatch.setenv(k, v)
-        res[mode] = _b().PFDR_graph_quadratic_d1_l1(np.zeros(V, dt), Y.astype(dt), A.astype(dt), Eu, Ev, La_d1.astype(dt),
-                                                    np.full(V, 0.01, dt), 1, Lt, L.astype(dt), N=N, rho=1.5, condMin=1e-3,
-                                                    difRcd=0.0, difTol=1e-7, itMax=400, want_obj=False, want_dif=True)
+        res[mode] = _b().PFDR_graph_quadratic_d1_l1(*fresh(), **kw)
     ref = res["large"]
     assert np.isfinite(ref.X).all()
     for mode in ("l2", "push"):
         r = res[mode]
         assert abs(r.it - ref.it) <= 1, (mode, r.it, ref.it)
         assert rel(r.X, ref.X) < 1e-8, (mode, rel(r.X, ref.X))
+    orc = oracle.PFDR_graph_quadratic_d1_l1(*fresh(), **kw)
+    assert abs(orc.it - ref.it) <= 1 and rel(ref.X, orc.X) < 1e-5, (orc.it, ref.it, rel(ref.X, orc.X))

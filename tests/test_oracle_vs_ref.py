@@ -5,6 +5,8 @@ GPU schedule (tests/sell_model.py) against the oracle.  CPU only."""
 import numpy as np
 import pytest
 
+import problems
+
 from cp_pfdr_graph_d1_b200 import synth
 from cp_pfdr_graph_d1_b200.api import PFDR_graph_l22_d1_l1
 
@@ -91,6 +93,17 @@ def test_simplex(oracle, reference, dtype, al, variant):
     n = min(a.it, b.it)
     assert np.allclose(a.Obj[:n], b.Obj[:n], rtol=1e-3 if dtype is np.float32 else 1e-8)
     assert np.allclose(a.X.sum(axis=1), 1, atol=1e-4 if dtype is np.float32 else 1e-10)
+
+
+@pytest.mark.parametrize("V", [2, 5, 33, 100, 257])
+@pytest.mark.parametrize("kind", ["diag", "dense", "ata"])
+def test_quadratic_irregular_multigraphs(oracle, reference, V, kind):
+    """pins the oracle on what cut-pursuit's reduced graphs contain (self-loops, duplicate edges, a hub) from two
+    vertices up - the inputs of tests/test_gpu_quadratic.py::test_paths_agree_on_irregular_graphs"""
+    fam, args, kw = problems.irregular_case(V, kind)
+    a, b = (be.PFDR_graph_quadratic_d1_l1(*(x.copy() if isinstance(x, np.ndarray) else x for x in args), **kw)
+            for be in (oracle, reference))
+    assert np.isfinite(a.X).all() and a.it == b.it and rel(a.X, b.X) < 1e-9
 
 
 @pytest.mark.parametrize("K", [1, 3, 16, 33, 50])
