@@ -1,13 +1,18 @@
 #!/usr/bin/env python
 """bench.py - PFDR edge-updates/s on the BASELINE.json workloads (see DESIGN.md "Measurement").
 
+Default workload = the configuration the north-star target is quoted on: C4, PFDR_graph_loss_d1_simplex with the
+smoothed-KL loss, K = 16 labels, 252^3 grid (16.0M vertices / 47.8M edges), float32.
+
 A *step* is one complete PFDR solve of `iters` iterations (difTol = 0, so exactly itMax iterations run)
 on the resident synthetic problem: solver.reset() (initial iterate + first preconditioning, device only)
 followed by solver.run().  `value` = E * iters * steps / time with every input already in HBM;
-`e2e` = the same metric through the one-shot C-ABI call with pinned HOST buffers (upload, half-edge layout,
-preconditioning, iterations, download of the iterate all inside the timed region).
+`e2e` = the same metric through the one-shot C-ABI call with HOST buffers (upload, layout, preconditioning,
+iterations, download of the iterate all inside the timed region): pinned buffers (the headline) and pageable ones
+(what the MEX / cut-pursuit callers hand over).  `extra` = short resident runs of the other BASELINE configs,
+`cp_solve` = BASELINE's second figure (cut-pursuit wall time, reference CP code on libpfdr_b200 vs all-reference).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2_f32|c2_f64|c4_f32|c4_f64] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c4_f32|c4_f64|c2_f32|c2_f64|...] [--impl reference]
 """
 import argparse
 import json
@@ -66,6 +71,20 @@ def describe(name):
                 f"rho=1, difTol=0, itMax={iters}")
     return (f"C4 PFDR_graph_loss_d1_simplex smoothed-KL (al=0.05), K={K}, 3D grid {n}^3, {np.dtype(dt).name}, "
             f"rho=1.5, condMin=1e-2, difTol=0, itMax={iters}")
+
+
+def static_config(name, iters):
+    """the `config` object: a function of the workload alone, so that both arms print the same one"""
+    kind, n, dt, K, _ = WORKLOADS[name]
+    if kind == "ata":
+        V, E = n, None
+    else:
+        V, E = n ** 3, 3 * n * n * (n - 1)
+    B = algorithmic_bytes(kind, V, E or 0, np.dtype(dt).itemsize, K, N=256 if kind == "dense" else 0)
+    return {"workload": describe(name).replace(f"itMax={WORKLOADS[name][4]}", f"itMax={iters}"), "name": name, "V": V, "E": E, "K": K,
+            "iterations_per_step": iters,
+            "l2": f"no flush: one iteration streams {B / 1e6:.0f} MB algorithmic ({'>' if B > 126e6 else '<'} 126 MB L2); "
+                  "steps re-run the same resident problem"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -137,29 +156,16 @@ def host_inputs(name):
         w = synth.c2_denoise(n, dt, diag=True)
         w["Ys"] = (w["La_l2"] * w["Y"]).astype(dt)          # the l22 gateway's pre-scaling (mex :54-60)
         return w
-    return synth.c4_simplex(n, K, dt) if n <= 128 else None  # the full C4 is generated on the device
+    return synth.c4_simplex(n, K, dt)
 
 
-def device_inputs_c4(n, K, dt, dev):
-    """full-size C4 generated on the device with torch (same recipe as synth.c4_simplex, torch RNG)"""
-    import torch
-    tdt = torch.float32 if dt is np.float32 else torch.float64
-    V = n ** 3
-    g = torch.Generator(device=dev).manual_seed(6)
-    v = torch.arange(V, device=dev)
-    z, y, x = v // (n * n), (v // n) % n, v % n
-    lab = (4 * torch.clamp(4 * z // n, max=3) + torch.clamp(4 * y // n, max=3)) % K
-    Q = torch.rand((V, K), generator=g, device=dev, dtype=tdt)
-    Q[v, lab] += 2.0
-    Q /= Q.sum(dim=1, keepdim=True)
-    eu, ev = [], []
-    for ok, d in ((x < n - 1, 1), (y < n - 1, n), (z < n - 1, n * n)):
-        eu.append(torch.where(ok, v, -1)); ev.append(torch.where(ok, v + d, -1))
-    Eu = torch.stack(eu, 1).reshape(-1); Ev = torch.stack(ev, 1).reshape(-1)
-    keep = Eu >= 0
-    Eu, Ev = Eu[keep].to(torch.int32).contiguous(), Ev[keep].to(torch.int32).contiguous()
-    La_d1 = torch.full((Eu.shape[0],), 0.2, device=dev, dtype=tdt)
-    return dict(V=V, E=int(Eu.shape[0]), K=K, Q=Q, Eu=Eu, Ev=Ev, La_d1=La_d1, al=0.05)
+def cpu_sample_inputs(name):
+    """bounded sample of the workload for the CPU legs: C2 whole; full-size C4: the first 16 z-planes of the same grid"""
+    from cp_pfdr_graph_d1_b200 import synth
+    kind, n, dt, K, iters = WORKLOADS[name]
+    if kind == "simplex" and n > 128:
+        return synth.c4_simplex(n, K, dt, nz=16), f"first 16 of {n} z-planes of the same problem ({n}x{n}x16 grid, {n * n * 16} vertices)"
+    return host_inputs(name), "the whole problem"
 
 
 def grid_slab_simplex(n, K, dt, world, rank):
@@ -318,18 +324,26 @@ def make_solver(name, w, dev, itMax):
                              difRcd=0.0, difTol=0.0, itMax=itMax), d
 
 
-def one_shot_host(name, w, pinned, itMax, backend=None):
+def prep_host(name, bufs):
+    """initial iterate of the in/out argument (X = 0; P = Q as octave/mex/PFDR_graph_loss_d1_simplex_mex.cpp:33)"""
+    if WORKLOADS[name][0] == "quad":
+        bufs["X"][:] = 0
+    else:
+        bufs["P"][:] = bufs["Q"]
+
+
+def one_shot_host(name, w, pinned, itMax, backend=None, prepare=True):
     """the reference-facing call with HOST buffers (e2e leg and CPU legs); returns iterations done"""
     from cp_pfdr_graph_d1_b200 import api, DIAG
     b = backend or api._b()
     kind = WORKLOADS[name][0]
+    if prepare:
+        prep_host(name, pinned)
     if kind == "quad":
-        pinned["X"][:] = 0
         r = b.PFDR_graph_quadratic_d1_l1(pinned["X"], pinned["Ys"], pinned["La_l2"], pinned["Eu"], pinned["Ev"],
                                          pinned["La_d1"], None, 0, DIAG, pinned["La_l2"], 1.5, 1e-3, 0.0, 0.0,
                                          itMax, 0)
     else:
-        pinned["P"][:] = pinned["Q"]
         r = b.PFDR_graph_loss_d1_simplex(pinned["P"], pinned["Q"], 0.05, pinned["Eu"], pinned["Ev"], pinned["La_d1"],
                                          None, 1.5, 1e-2, 0.0, 0.0, itMax)
     return r.it
@@ -349,7 +363,7 @@ def pin(w, name, use_cuda=True):
     return out
 
 
-def cpu_reference_rate(name, w, seconds_target=12.0):
+def cpu_reference_rate(name, w, note, seconds_target=12.0):
     """edge-updates/s of the reference's own CPU implementation (oracle/_ref, all host cores) on a bounded
     sample of the workload: two-point timing (itMax = a, b) removes the setup.  Falls back to the serial port."""
     from oracle import oracle as O
@@ -371,7 +385,7 @@ def cpu_reference_rate(name, w, seconds_target=12.0):
     ta = min(ta, run(a))
     rate = E * (b - a) / max(tb - ta, 1e-9)
     return {"value": rate, "unit": "edge_updates/s", "cores": int(cores), "kind": kind_label,
-            "sample": f"{describe(name).split(',')[0]}: iterations {a}..{b} of the same problem (two-point timing, "
+            "sample": f"{describe(name).split(',')[0]}: {note}, iterations {a}..{b} (two-point timing, "
                       f"setup removed), {1e3 * (tb - ta) / (b - a):.2f} ms/iteration"}
 
 
@@ -382,25 +396,100 @@ def run_reference_arm(args):
         return
     name = args.workload
     kind, n, dt, K, iters = WORKLOADS[name]
-    if n > 128:                                      # the CPU arm runs the parity-sized instance of C4
-        name = "c4s_f32" if dt is np.float32 else "c4s_f64"
-    w = host_inputs(name)
+    iters = args.iters or iters
+    if kind in ("ata", "dense"):
+        print(json.dumps({"impl": "reference", "unavailable": "device-generated multi-GB workload: CPU arm runs c2/c4 only"}), flush=True)
+        return
+    w, note = cpu_sample_inputs(name)
     per_step = []
     cb = None
     for i in range(args.warmup + args.steps):
-        cb = cpu_reference_rate(name, w, seconds_target=6.0)
+        cb = cpu_reference_rate(name, w, note, seconds_target=6.0)
         if i >= args.warmup:
             per_step.append(cb["value"])
     val = float(np.mean(per_step))
-    E = int(w["E"])
+    cfg = static_config(name, iters)
     cb["value"] = val
     line = {"impl": "reference", "metric": "pfdr_edge_updates_per_s", "value": val, "unit": "edge_updates/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * E * WORKLOADS[name][4] / val, "higher_is_better": True, "scaling": "strong",
+            "ms_per_step": 1e3 * cfg["E"] * iters / val, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32" if dt is np.float32 else "f64", "data": "synthetic",
-            "config": {"workload": describe(name), "V": int(w["V"]), "E": E}, "cpu_baseline": cb,
+            "config": cfg, "cpu_baseline": cb,
             "e2e": {"value": val, "unit": "edge_updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+def resident_run(name, dev, stream, steps, warmup, iters=0, clock_index=None):
+    """builds the workload in HBM and times `steps` solves; returns (line fragment, host inputs or None)"""
+    import torch
+    from cp_pfdr_graph_d1_b200 import api
+    kind, n, dt, K, it0 = WORKLOADS[name]
+    iters = iters or it0
+    r = np.dtype(dt).itemsize
+    w = device_inputs_dense(name, dev) if kind in ("ata", "dense") else host_inputs(name)
+    V, E = int(w["V"]), int(w["E"])
+    B_iter = algorithmic_bytes(kind, V, E, r, K, N=abs(int(w.get("N", 0))) if kind == "dense" else 0)
+    solver, keep = make_solver(name, w, dev, iters)
+    setup = dict(solver.setup_stats)
+
+    def step():
+        solver.reset()
+        return solver.run()
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    loop_ms = launches = its = 0
+    clk = ClockSampler(clock_index) if clock_index is not None else None
+    if clk:
+        clk.__enter__()
+    with torch.cuda.stream(stream):
+        ev0.record(stream)
+        for _ in range(steps):
+            st = step()
+            loop_ms += st["loop_ms"]; launches += st["launches"]; its += st["iterations"]
+        ev1.record(stream)
+    torch.cuda.synchronize()
+    if clk:
+        clk.__exit__()
+    ms = ev0.elapsed_time(ev1)
+    assert its == iters * steps, (its, iters, steps)
+    solver.close()
+    del keep
+    torch.cuda.empty_cache()
+    peak, peak_src = peaks()
+    achieved = B_iter * its / (loop_ms * 1e-3) / 1e9
+    return dict(V=V, E=E, K=K, iters=iters, ms=ms, loop_ms=loop_ms, launches=launches, its=its, value=E * its / (ms * 1e-3),
+                B_iter=B_iter, achieved=achieved, peak=peak, peak_src=peak_src, setup=setup,
+                clocks=clk.summary() if clk else None, kind=kind, dt=dt), w
+
+
+KERNEL_NAMES = {"quad": "quad_dia_iter_kernel (grid graphs) / quad_iter_pipe_kernel", "simplex": "simplex_dia_iter_kernel (grid graphs) / simplex_iter_kernel",
+                "ata": "ata_gemv_kernel", "dense": "ax_partial_kernel + atr_kernel"}
+
+
+def cp_solve_time():
+    """BASELINE.json's second figure: wall time of the reference's UNMODIFIED cut-pursuit (oracle/_ref, built from the
+    reference's sources) with its PFDR / operator-norm calls served by libpfdr_b200 through the C++ shim, beside the
+    all-reference build on the host cores; EEG-like stand-in of config 1 (data/EEG.mat is absent), float64"""
+    from oracle import oracle as O
+    from cp_pfdr_graph_d1_b200 import synth
+    ref, b200 = O.cp_reference(), O.cp_b200()
+    if ref is None or b200 is None:
+        return None
+    w = synth.eeg_like(5, 91, np.float64)
+    kw = dict(CP_difTol=1e-4, CP_itMax=15, rho=1.5, condMin=1e-3, difRcd=0.0, difTol=1e-7, itMax=10000)
+    a = (w["Y"], w["A"], w["Eu"], w["Ev"], w["La_d1"], w["La_l1"], 1, w["N"])
+    b200.quadratic_d1_l1(*a, **kw)                                 # warm-up: context, memory pool, module load
+    t0 = time.perf_counter(); r1 = b200.quadratic_d1_l1(*a, **kw); t1 = time.perf_counter() - t0
+    t0 = time.perf_counter(); r0 = ref.quadratic_d1_l1(*a, **kw); t_ref = time.perf_counter() - t0
+    same = bool(r1["rV"] == r0["rV"] and np.array_equal(r1["Cv"], r0["Cv"]))
+    err = float(np.linalg.norm(r1["rX"] - r0["rX"]) / max(np.linalg.norm(r0["rX"]), 1e-300)) if same else None
+    return {"problem": f"CP_PFDR_graph_quadratic_d1_l1, EEG-like icosphere level 5 (V={w['V']}, N=91), float64, settings of "
+                       "octave/example_EEG_CP.m", "cp_b200_s": round(t1, 4), "cp_reference_s": round(t_ref, 4),
+            "rV": int(r0["rV"]), "rV_b200": int(r1["rV"]), "Cv_identical": same, "rX_rel_err": err,
+            "host_cores": os.cpu_count()}
 
 
 def main():
@@ -408,19 +497,18 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default="c2_f32", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c4_f32", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads and the cut-pursuit timing")
     ap.add_argument("--iters", type=int, default=0, help="override iterations per step")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
 
     import torch
-    import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         from cp_pfdr_graph_d1_b200 import dist_bench
@@ -435,84 +523,72 @@ def main():
     name = args.workload
     kind, n, dt, K, iters = WORKLOADS[name]
     iters = args.iters or iters
-    r = np.dtype(dt).itemsize
     if kind in ("ata", "dense"):
-        w = device_inputs_dense(name, dev)
-        args.no_cpu = args.no_e2e = True                 # several-GB matrices: device-resident legs only
-    else:
-        w = host_inputs(name) or device_inputs_c4(n, K, dt, dev)
-    V, E = int(w["V"]), int(w["E"])
-    B_iter = algorithmic_bytes(kind, V, E, r, K, N=abs(int(w.get("N", 0))) if kind == "dense" else 0)
-    solver, keep = make_solver(name, w, dev, iters)
-    setup = dict(solver.setup_stats)
-
-    def step():
-        solver.reset()
-        return solver.run()
-
-    for _ in range(args.warmup):
-        step()
-    torch.cuda.synchronize()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    loop_ms = launches = its = 0
-    with ClockSampler(local) as clk:
-        with torch.cuda.stream(stream):
-            ev0.record(stream)
-            for _ in range(args.steps):
-                st = step()
-                loop_ms += st["loop_ms"]; launches += st["launches"]; its += st["iterations"]
-            ev1.record(stream)
-        torch.cuda.synchronize()
-    ms = ev0.elapsed_time(ev1)
-    assert its == iters * args.steps, (its, iters, args.steps)
-    value = E * its / (ms * 1e-3)
-    peak, peak_src = peaks()
-    achieved = B_iter * its / (loop_ms * 1e-3) / 1e9
+        args.no_cpu = args.no_e2e = True                 # several-GB device-generated matrices: resident leg only
+    R, w = resident_run(name, dev, stream, args.steps, args.warmup, iters, clock_index=local)
+    E = R["E"]
     line = {
-        "metric": "pfdr_edge_updates_per_s", "value": value, "unit": "edge_updates/s", "n_gpus": 1,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "metric": "pfdr_edge_updates_per_s", "value": R["value"], "unit": "edge_updates/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": R["ms"] / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32" if dt is np.float32 else "f64", "data": "synthetic",
-        "config": {"workload": describe(name), "V": V, "E": E, "K": K, "iterations_per_step": iters,
-                   "slots": setup["slots"], "us_per_iteration": 1e3 * loop_ms / its,
-                   "edge_label_updates_per_s": value * K,
-                   "l2": f"no flush: one iteration streams {B_iter / 1e6:.0f} MB algorithmic "
-                         f"({'>' if B_iter > 126e6 else '<'} 126 MB L2); steps re-run the same resident problem"},
-        "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": measured_traffic(name), "peak_source": peak_src,
-                     "kernel": {"quad": "quad_iter_pipe_kernel", "simplex": "simplex_iter_kernel", "ata": "ata_gemv_kernel",
-                                "dense": "ax_partial_kernel + atr_kernel"}[kind],
-                     "algorithmic_bytes_per_launch": B_iter,
-                     "avg_launch_us": 1e3 * loop_ms / its},
-        "setup_ms_device_resident": setup["setup_ms"],
+        "config": static_config(name, iters),
+        "detail": {"slots": R["setup"]["slots"], "us_per_iteration": 1e3 * R["loop_ms"] / R["its"],
+                   "edge_label_updates_per_s": R["value"] * K, "setup_ms_device_resident": R["setup"]["setup_ms"]},
+        "gpu_launches": int(R["launches"]),
+        "roofline": {"bound": "hbm", "achieved": R["achieved"], "peak": R["peak"], "unit": "GB/s", "frac": R["achieved"] / R["peak"],
+                     "traffic": measured_traffic(name), "peak_source": R["peak_src"], "kernel": KERNEL_NAMES[kind],
+                     "algorithmic_bytes_per_launch": R["B_iter"], "avg_launch_us": 1e3 * R["loop_ms"] / R["its"]},
+        "clocks": R["clocks"],
     }
-    solver.close()
-    del keep
-    torch.cuda.empty_cache()
 
-    if not args.no_e2e and isinstance(w.get("Q", w.get("Y")), np.ndarray):
-        pinned = pin(w, name)
-        for _ in range(3):                                       # warm-up: memory pool growth, module load
-            one_shot_host(name, w, pinned, iters)
-        torch.cuda.synchronize()
-        t_e2e, h2d, d2h, n_e2e = 0.0, 0, 0, max(2, min(args.steps, 5))
-        for _ in range(n_e2e):
-            t0 = time.perf_counter()
-            done = one_shot_host(name, w, pinned, iters)
+    if not args.no_e2e:
+        def e2e_leg(bufs, reps):
+            for _ in range(2):                                   # warm-up: memory pool growth, module load
+                one_shot_host(name, w, bufs, iters)
             torch.cuda.synchronize()
-            t_e2e += time.perf_counter() - t0
-            s = api.last_stats()
-            h2d, d2h = s["h2d_bytes"], s["d2h_bytes"]
-            assert done == iters
-        line["e2e"] = {"value": E * iters * n_e2e / t_e2e, "unit": "edge_updates/s", "h2d_bytes_per_step": int(h2d),
-                       "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * t_e2e / n_e2e,
-                       "what": "one-shot C-ABI call, pinned host buffers in, host iterate out"}
+            t, h2d, d2h = 0.0, 0, 0
+            for _ in range(reps):
+                prep_host(name, bufs)                            # the caller's initial iterate: not part of the call
+                t0 = time.perf_counter()
+                done = one_shot_host(name, w, bufs, iters, prepare=False)
+                torch.cuda.synchronize()
+                t += time.perf_counter() - t0
+                s = api.last_stats()
+                h2d, d2h = s["h2d_bytes"], s["d2h_bytes"]
+                assert done == iters
+            return {"value": E * iters * reps / t, "unit": "edge_updates/s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * t / reps}
+        reps = max(2, min(args.steps, 3 if n > 128 else 5))
+        e = e2e_leg(pin(w, name), reps)
+        e["what"] = "one-shot C-ABI call (upload, layout, preconditioning, iterations, download): pinned host buffers in, host iterate out"
+        p = e2e_leg(pin(w, name, use_cuda=False), reps)
+        e["pageable"] = {"value": p["value"], "ms_per_step": p["ms_per_step"],
+                         "what": "same call with ordinary (pageable) host arrays, as the MEX / cut-pursuit callers pass"}
+        line["e2e"] = e
     else:
         line["e2e"] = None
-    line["clocks"] = clk.summary()
+    del w
     if not args.no_cpu:
-        wn = name if n <= 128 else ("c4s_f32" if dt is np.float32 else "c4s_f64")
-        line["cpu_baseline"] = cpu_reference_rate(wn, host_inputs(wn) if wn != name else w)
+        ws, note = cpu_sample_inputs(name)
+        line["cpu_baseline"] = cpu_reference_rate(name, ws, note)
+        del ws
+    if not args.no_extra:
+        extra = {}
+        for xn in ("c2_f32", "c2_f64", "c3_f32", "c5s_f32"):
+            if xn == name:
+                continue
+            try:
+                X, _ = resident_run(xn, dev, stream, 2, 2)
+                extra[xn] = {"workload": describe(xn), "value": X["value"], "unit": "edge_updates/s",
+                             "us_per_iteration": 1e3 * X["loop_ms"] / X["its"], "roofline_frac": X["achieved"] / X["peak"],
+                             "achieved_gbs": X["achieved"], "algorithmic_bytes_per_launch": X["B_iter"]}
+            except Exception as ex:                               # a secondary line must not lose the headline
+                extra[xn] = {"error": f"{type(ex).__name__}: {ex}"[:300]}
+        line["extra"] = extra
+        try:
+            line["cp_solve"] = cp_solve_time()
+        except Exception as ex:
+            line["cp_solve"] = {"error": f"{type(ex).__name__}: {ex}"[:300]}
     print(json.dumps(line), flush=True)
 
 

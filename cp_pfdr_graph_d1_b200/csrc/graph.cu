@@ -75,33 +75,7 @@ __global__ void count_offset_kernel(const int *__restrict__ Eu, const int *__res
     const unsigned m = __ballot_sync(0xffffffffu, hit);
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(count, __popc(m));
 }
-__global__ void slice_key_kernel(int nslices, int C, int band, int T, unsigned long long *__restrict__ key, int *__restrict__ val)
-{
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= nslices) return;
-    const long long v = (long long) s * C;
-    const long long z = v / band, r = v % band;
-    const long long ntile_z = ((long long) nslices * C + band - 1) / band + 1;
-    key[s] = (unsigned long long) (((r / T) * ntile_z + z) * T + (r % T));
-    val[s] = s;
-}
-
 }  // namespace
-
-void build_slice_order(const SellGraph &g, int nslices, int T, DevBuf<int> &order)
-{
-    cudaStream_t st = ctx().stream;
-    DevBuf<unsigned long long> key(nslices), skey(nslices);
-    DevBuf<int> val(nslices);
-    order.alloc(nslices);
-    PFDR_LAUNCH(slice_key_kernel, cdiv(nslices, 256), 256, 0, nslices, g.C, g.band, T, key.p, val.p);
-    size_t tb = 0;
-    PFDR_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, key.p, skey.p, val.p, order.p, nslices, 0, 64, st));
-    DevBuf<unsigned char> tmp(tb + 16);
-    PFDR_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, key.p, skey.p, val.p, order.p, nslices, 0, 64, st));
-    ctx().stats.launches += 1;
-    PFDR_CUDA(cudaStreamSynchronize(st));
-}
 
 void build_sell(SellGraph &g, const int *dEu, const int *dEv, int V, int E, int C)
 {

@@ -23,19 +23,13 @@ struct SellGraph {
     long long nslots = 0;
     int max_width = 0;             // widest slice (rows)
     int band = 0;                  // |u - v| shared by >= 20 % of the edges and maximal among all edges (n^2 on an
-                                   // n^3 grid), 0 if the graph has no such band
+                                   // n^3 grid), 0 if the graph has no such band (-> dia.cuh build_chunk_order)
     DevBuf<long long> slice_off;   // [nslices+1] slot offset of each slice
     DevBuf<int> nbr;               // [nslots] vertex at the other end (-1: padding)
     DevBuf<int> twin;              // [nslots] slot of the opposite half-edge
     DevBuf<int> hkey;              // [nslots] 2*e+side (-1: padding)
     DevBuf<int> deg;               // [V]
 };
-
-// Processing order of the slices for banded graphs (3-D grids): vertex v = z*band + r is visited in the order
-// (r / T, z, r % T), i.e. (x,y)-tiles of T vertices swept along z, so that a vertex's row and the gather of it by
-// its +-band neighbour are ~T vertices apart instead of a whole plane: the reuse then happens inside the L2.
-// Data layout and per-vertex arithmetic are untouched; only which CTA handles which slice changes.
-void build_slice_order(const SellGraph &g, int nslices, int T, DevBuf<int> &order);
 
 // Eu, Ev: device arrays of length E.  C must be a power of two <= 32.
 void build_sell(SellGraph &g, const int *dEu, const int *dEv, int V, int E, int C);

@@ -1952,7 +1952,8 @@ struct QuadSolver : SolverBase {
 
     void recondition()
     {
-        if (!thc.p) { thc.alloc(std::max<size_t>(g.nslots, 1)); thc.zero(); p.thc = thc.p; }
+        if (!thc.p) thc.alloc(std::max<size_t>(g.nslots, 1));
+        if (!p.thc) { thc.zero(); p.thc = thc.p; }                       // first reconditioning since setup() / reset()
         if (gexec) { cudaGraphExecDestroy(gexec); gexec = nullptr; }   // kernel parameters changed
         PFDR_LAUNCH(amp_kernel<real>, vgrid, 256, 0, p, 1);
         PFDR_LAUNCH(recond_vertex_kernel<real>, vgrid, 256, 0, p);
@@ -1999,7 +2000,10 @@ struct QuadSolver : SolverBase {
         xsum.alloc(64);
         sparts.alloc(std::max<size_t>(16 * (size_t) std::max(q.N, 0), 1));
         a.pos = pos.p; a.Ze = ze.p; a.xs = xsum.p; a.parts = sparts.p;
-        if (q.difRcd > (real) 0 && !thc.p) { thc.alloc(std::max<size_t>(g.nslots, 1)); thc.zero(); p.thc = thc.p; }
+        if (q.difRcd > (real) 0) {                               // (reset() clears p.thc, the buffer is kept)
+            if (!thc.p) thc.alloc(std::max<size_t>(g.nslots, 1));
+            thc.zero(); p.thc = thc.p;
+        }
         const size_t sm = small_smem();
         ctx().in_loop = true;
         PFDR_CUDA(cudaEventRecord(ev_b, st));

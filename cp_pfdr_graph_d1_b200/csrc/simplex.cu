@@ -23,195 +23,11 @@
 #include "solvers.cuh"
 #include <chrono>
 
+#include "simplex.cuh"
+#include "dia.cuh"
+#include "simplex_dia.cuh"
+
 namespace pfdr {
-
-enum : int { LOSS_LIN = 0, LOSS_QUAD = 1, LOSS_KLA = 2 };
-
-template <typename real>
-struct SP {
-    Ctl *ctl;
-    int K, V, E, TPV, C, logC, logTPV, loss, by_label, LPT, stream_z;
-    int Kv;                           // labels that exist (K is the row stride: Kv rounded up to a multiple of 4 when padded, else Kv)
-    int Vown, sharded, Vglobal;   // vertices this rank owns (== V unless sharded: ghosts follow), global count
-    int world, rank;              // sharded: sums holds one value per rank, sums[rank] is ours
-    double *sums;                 // [1] reduction scratch of the sharded path
-    real aK, a1, aK1, rho, condMin;
-    const long long *slice_off; const int *nbr, *twin, *hkey;
-    const int *order;             // [owned slices] processing order for banded graphs (graph.cuh), NULL = natural
-    real *w;                      // [slots]   raw weight before any reconditioning (= La_d1[e] for every label)
-    real *wk, *thk;               // [slots*K] raw weight / La_d1 over it, per label, after a reconditioning
-    real *Z0, *Z1;                // [slots*K] edge copies, ping/pong
-    real *P0, *P1, *F0, *F1;      // [V*K] iterate and forward point, ping/pong
-    real *T, *GaQ;                // [V*K] Ga.S  and  metric x first-order information (:308-335)
-    real *Sinv;                   // [V]   1/S before any reconditioning
-    real *Sinvk, *Gn, *GaU;       // [V*K] 1/S per label, normalised metric (after a reconditioning), raw metric
-    int *lab;                     // [V] previous arg-max label (difTol >= 1)
-    const real *Q, *La_f, *La_d1;
-    const int *Eu, *Ev;
-    double *partial;
-    real *dObj, *dDif;
-};
-
-template <typename real> __device__ __forceinline__ real sabs(real a) { return a < (real) 0 ? -a : a; }
-
-// ---- LPT-wide vectors of labels ----------------------------------------------------------------
-template <typename real, int L> struct VecN { real v[L]; };
-
-template <typename real, int L>
-__device__ __forceinline__ VecN<real, L> ldv(const real *q)
-{
-    VecN<real, L> r;
-    if constexpr (L == 1) r.v[0] = *q;
-    else if constexpr (L == 2) {
-        if constexpr (sizeof(real) == 4) { const float2 t = *reinterpret_cast<const float2 *>(q); r.v[0] = t.x; r.v[1] = t.y; }
-        else { const double2 t = *reinterpret_cast<const double2 *>(q); r.v[0] = t.x; r.v[1] = t.y; }
-    } else if constexpr (sizeof(real) == 4) {
-        const float4 t = *reinterpret_cast<const float4 *>(q);
-        r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
-    } else {
-        const double2 a = *reinterpret_cast<const double2 *>(q), b = *reinterpret_cast<const double2 *>(q + 2);
-        r.v[0] = a.x; r.v[1] = a.y; r.v[2] = b.x; r.v[3] = b.y;
-    }
-    return r;
-}
-template <typename real, int L>
-__device__ __forceinline__ void stv(real *q, const VecN<real, L> &r)
-{
-    if constexpr (L == 1) *q = r.v[0];
-    else if constexpr (L == 2) {
-        if constexpr (sizeof(real) == 4) *reinterpret_cast<float2 *>(q) = make_float2(r.v[0], r.v[1]);
-        else *reinterpret_cast<double2 *>(q) = make_double2(r.v[0], r.v[1]);
-    } else if constexpr (sizeof(real) == 4) *reinterpret_cast<float4 *>(q) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
-    else {
-        *reinterpret_cast<double2 *>(q) = make_double2(r.v[0], r.v[1]);
-        *reinterpret_cast<double2 *>(q + 2) = make_double2(r.v[2], r.v[3]);
-    }
-}
-// streaming (evict-first) store: the new edge copies are not touched again during this launch
-template <typename real, int L>
-__device__ __forceinline__ void stv_cs(real *q, const VecN<real, L> &r)
-{
-    if constexpr (L == 1) __stcs(q, r.v[0]);
-    else if constexpr (L == 2) {
-        if constexpr (sizeof(real) == 4) __stcs(reinterpret_cast<float2 *>(q), make_float2(r.v[0], r.v[1]));
-        else __stcs(reinterpret_cast<double2 *>(q), make_double2(r.v[0], r.v[1]));
-    } else if constexpr (sizeof(real) == 4) __stcs(reinterpret_cast<float4 *>(q), make_float4(r.v[0], r.v[1], r.v[2], r.v[3]));
-    else {
-        __stcs(reinterpret_cast<double2 *>(q), make_double2(r.v[0], r.v[1]));
-        __stcs(reinterpret_cast<double2 *>(q + 2), make_double2(r.v[2], r.v[3]));
-    }
-}
-template <typename real, int L>
-__device__ __forceinline__ VecN<real, L> splat(real x)
-{
-    VecN<real, L> r;
-#pragma unroll
-    for (int i = 0; i < L; i++) r.v[i] = x;
-    return r;
-}
-
-template <typename real>
-__device__ __forceinline__ real group_sum(real x, int TPV)
-{
-    for (int o = TPV >> 1; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-    return x;
-}
-template <typename real>
-__device__ __forceinline__ real group_max(real x, int TPV)
-{
-    for (int o = TPV >> 1; o > 0; o >>= 1) x = max(x, __shfl_xor_sync(0xffffffffu, x, o));
-    return x;
-}
-
-template <int NV>
-__device__ bool grid_sum_s(Ctl *ctl, double *partial, double (&v)[NV], double *smem)
-{
-    __shared__ int s_last;
-    block_sum<NV>(v, smem);
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int i = 0; i < NV; i++) partial[(size_t) blockIdx.x * NV + i] = v[i];
-        __threadfence();
-        const unsigned t = atomicAdd(&ctl->ticket, 1u);
-        s_last = (t == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!s_last) return false;
-    __threadfence();
-    double acc[NV];
-#pragma unroll
-    for (int i = 0; i < NV; i++) acc[i] = 0.0;
-    const volatile double *vp = partial;
-    for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
-#pragma unroll
-        for (int i = 0; i < NV; i++) acc[i] += vp[(size_t) b * NV + i];
-    }
-    block_sum<NV>(acc, smem);
-#pragma unroll
-    for (int i = 0; i < NV; i++) v[i] = acc[i];
-    if (threadIdx.x == 0) ctl->ticket = 0;
-    return true;
-}
-
-// forward point 2P - Ga.grad(P)  (ref :569-587)
-template <typename real>
-__device__ __forceinline__ real forward_point(int loss, real aK1, real P, real gaq, real q)
-{
-    if (loss == LOSS_LIN) return (real) 2 * P + gaq;
-    if (loss == LOSS_QUAD) return (real) 2 * P - gaq * (P - q);
-    return (real) 2 * P + gaq / (aK1 + P);
-}
-// P - Ga.grad(P), as the reference's subgradient expressions need it (:137-156, :337-358)
-template <typename real>
-__device__ __forceinline__ real explicit_point(int loss, real aK1, real P, real gaq, real q)
-{
-    if (loss == LOSS_LIN) return P + gaq;
-    if (loss == LOSS_QUAD) return P - gaq * (P - q);
-    return P + gaq / (aK1 + P);
-}
-
-// metric of one (vertex,label) from the loss Hessian and the weight sum S  (ref :160-190, :222-285)
-template <typename real>
-__device__ __forceinline__ real metric(const SP<real> &p, int v, real P, real q, real S)
-{
-    const real bound = (real) 1.9 * ((real) 2 - p.rho);
-    if (p.loss == LOSS_LIN) return (real) 1 / S;
-    if (p.loss == LOSS_QUAD) {
-        real ga = (real) 1 / ((p.La_f ? p.La_f[v] : (real) 1) + S);
-        if (p.La_f) { const real c = bound / p.La_f[v]; if (ga > c) ga = c; }
-        else if (bound < (real) 1) { if (ga > bound) ga = bound; }
-        return ga;
-    }
-    const real a = p.aK1 + P, cq = p.aK + p.a1 * q;
-    const real h = p.La_f ? p.La_f[v] * cq / (a * a) : cq / (a * a);
-    real ga = (real) 1 / (h + S);
-    const real b = p.La_f ? p.La_f[v] * (real) 1 / (p.aK1 * p.aK1) : (real) 1 / (p.aK1 * p.aK1);
-    const real c = bound / (cq * b);
-    if (ga > c) ga = c;
-    return ga;
-}
-template <typename real>
-__device__ __forceinline__ real metric_times_info(const SP<real> &p, int v, real ga, real q)
-{   // GaQ, ref :308-335
-    if (p.loss == LOSS_LIN) return ga * q;
-    if (p.loss == LOSS_QUAD) return p.La_f ? p.La_f[v] * ga : ga;
-    return p.La_f ? p.La_f[v] * ga * (p.aK + p.a1 * q) : ga * (p.aK + p.a1 * q);
-}
-
-// first arg-max label over the lanes of a vertex (ref :662-669): ties go to the lowest label
-template <typename real, int LPT>
-__device__ __forceinline__ int group_argmax(const VecN<real, LPT> &x, int k0, int K, int TPV)
-{
-    real a = -HUGE_VAL; int i = 0x7fffffff;
-#pragma unroll
-    for (int t = 0; t < LPT; t++) if (k0 + t < K && x.v[t] > a) { a = x.v[t]; i = k0 + t; }
-    for (int o = TPV >> 1; o > 0; o >>= 1) {
-        const real b = __shfl_xor_sync(0xffffffffu, a, o);
-        const int j = __shfl_xor_sync(0xffffffffu, i, o);
-        if (b > a || (b == a && j < i)) { a = b; i = j; }
-    }
-    return i;
-}
 
 // ---------------------------------------------------------------------------------------------
 // first preconditioning (recond = 0, ref :160-370 with Zu == NULL) and reconditioning (recond = 1):
@@ -312,116 +128,6 @@ __global__ void simplex_resume_kernel(SP<real> p)
     p.ctl->rcd *= 0.1; p.ctl->state = ST_RUN; p.ctl->hold = 0; p.ctl->scratch[0] = 1.0;     // ref :563
 }
 
-// ---------------------------------------------------------------------------------------------
-// fused iteration
-// ---------------------------------------------------------------------------------------------
-// d1 prox + relaxation of one half-edge row for the lane's LPT labels (ref :590-634); accumulates W.z into acc
-template <typename real, int LPT, bool PERK, int LOSS>
-__device__ __forceinline__ VecN<real, LPT> prox_row(real rho, const VecN<real, LPT> &fown, const VecN<real, LPT> &pold,
-    const VecN<real, LPT> &Tv, const VecN<real, LPT> &Sv, const VecN<real, LPT> &zo, const VecN<real, LPT> &zt,
-    const VecN<real, LPT> &fn, const VecN<real, LPT> &tn, const VecN<real, LPT> &wvk, const VecN<real, LPT> &th, real w,
-    VecN<real, LPT> &acc)
-{
-    VecN<real, LPT> zn;
-    const real ws = w * Sv.v[0];                                              // row weight W = w/S (per vertex before recond.)
-#pragma unroll
-    for (int i = 0; i < LPT; i++) {
-        const real po = fown.v[i] - zo.v[i], pt = fn.v[i] - zt.v[i];
-        const real d0 = po - pt;
-        if (LOSS == LOSS_LIN) {                                               // ref :599-614 (weights 1/2, threshold 2)
-            const real ds = d0 - min(max(d0, (real) -2), (real) 2);
-            zn.v[i] = zo.v[i] + rho * ((real) 0.5 * (po + pt) + (real) 0.5 * ds - pold.v[i]);
-        } else {                                                              // ref :615-631
-            const real tsum = Tv.v[i] + tn.v[i], inv = fast_rcp(tsum);
-            const real t = PERK ? th.v[i] * tsum : tsum;                      // La_d1/w = 1 before a reconditioning
-            const real wo = tn.v[i] * inv, wt = Tv.v[i] * inv;                // W_d1 own / twin side
-            const real ds = d0 - min(max(d0, -t), t);                         // soft threshold, exact 0 inside
-            // W_d1u.pu + W_d1v.pv = pt + wo.(po - pt) since the two weights sum to one
-            zn.v[i] = zo.v[i] + rho * (fma(wo, d0, pt) + wt * ds - pold.v[i]);
-        }
-        acc.v[i] += (PERK ? wvk.v[i] * Sv.v[i] : ws) * zn.v[i];
-    }
-    return zn;
-}
-
-// projection on the simplex in the metric m (Michelot's active-set iteration, all lanes of the vertex in parallel,
-// ref :651 / proj_simplex_metric.cpp:40-81), next (P, FP) (:569-587) and this lane's share of the evolution (:654-691)
-template <typename real, int LPT, bool PERK, int LOSS>
-__device__ __forceinline__ double simplex_epilogue(const SP<real> &p, Ctl *ctl, bool on, int v, int k0, size_t vk,
-    VecN<real, LPT> acc, const VecN<real, LPT> &Tv, const VecN<real, LPT> &pold, real *__restrict__ Pn, real *__restrict__ Fn)
-{
-    typedef VecN<real, LPT> vec;
-    const int K = p.K, TPV = p.TPV;
-    vec m;
-    if (PERK) { if (on) m = ldv<real, LPT>(p.Gn + vk); else m = splat<real, LPT>((real) 1); }
-    else if (LOSS == LOSS_LIN) m = splat<real, LPT>((real) 1);     // Ga = 1/S is the same for all labels
-    else m = Tv;
-    vec xs;
-    unsigned act = 0;
-#pragma unroll
-    for (int i = 0; i < LPT; i++) {
-        if (!on) { m.v[i] = (real) 1; acc.v[i] = 0; }
-        xs.v[i] = acc.v[i] * fast_rcp(m.v[i]);
-        if (on && k0 + i < p.Kv) act |= 1u << i;
-    }
-    real la = 0;
-    for (;;) {
-        real sx = 0, sm = 0;
-#pragma unroll
-        for (int i = 0; i < LPT; i++) if ((act >> i) & 1u) { sx += acc.v[i]; sm += m.v[i]; }
-        sx = group_sum(sx, TPV); sm = group_sum(sm, TPV);
-        la = (sx - (real) 1) * fast_rcp(sm);
-        unsigned keep = act;
-#pragma unroll
-        for (int i = 0; i < LPT; i++) if (((act >> i) & 1u) && xs.v[i] < la) keep &= ~(1u << i);
-        const bool changed = keep != act;
-        act = keep;
-        if (!__any_sync(0xffffffffu, changed)) break;
-    }
-    vec pnew;
-#pragma unroll
-    for (int i = 0; i < LPT; i++) pnew.v[i] = ((act >> i) & 1u) ? (xs.v[i] - la) * m.v[i] : (real) 0;
-    if (on) {
-        const vec gaq = ldv<real, LPT>(p.GaQ + vk);
-        vec qv = splat<real, LPT>((real) 0), f;
-        if (LOSS == LOSS_QUAD) qv = ldv<real, LPT>(p.Q + vk);
-#pragma unroll
-        for (int i = 0; i < LPT; i++) {
-            if (LOSS == LOSS_KLA) f.v[i] = (real) 2 * pnew.v[i] + gaq.v[i] * fast_rcp(p.aK1 + pnew.v[i]);
-            else f.v[i] = forward_point(LOSS, p.aK1, pnew.v[i], gaq.v[i], qv.v[i]);
-        }
-        stv<real, LPT>(Pn + vk, pnew);
-        stv<real, LPT>(Fn + vk, f);
-    }
-    double red = 0.0;
-    if (p.by_label) {                                                         // ref :657-676
-        const int i = group_argmax<real, LPT>(pnew, on ? k0 : p.Kv, p.Kv, TPV);
-        if (on && k0 == 0 && ctl->track) { if (i != p.lab[v]) { red = 1.0; p.lab[v] = i; } }
-    } else if (on) {                                                          // ref :681-687
-        real d = 0;
-#pragma unroll
-        for (int i = 0; i < LPT; i++) d += sabs(pold.v[i] - pnew.v[i]);
-        red = (double) d;
-    }
-    return red;
-}
-
-// end of an iteration: evolution measure (ref :654-691), iteration counter, stop / recondition decision (:551, :554)
-template <typename real>
-__device__ void simplex_finalize(const SP<real> &p, int it, double s)
-{
-    Ctl *ctl = p.ctl;
-    double dif = ctl->dif;
-    if (ctl->track) {
-        dif = p.by_label ? s : s / (double) p.Vglobal;              // ref :688 divides by the (global) vertex count
-        ctl->dif = dif;
-        if (p.dDif) p.dDif[it] = (real) dif;
-    }
-    const int itn = it + 1;
-    ctl->it = itn;
-    if (itn == ctl->itMax || (real) dif < (real) ctl->tol) ctl->state = ST_FINAL;
-    else if ((real) dif < (real) ctl->rcd) ctl->state = ST_RECOND;
-}
 template <typename real>
 __global__ void simplex_finalize_kernel(SP<real> p)
 {
@@ -640,8 +346,12 @@ struct SimplexSolver : SolverBase {
     const SimplexProblem<real> q;
     bool keep_p0 = false;
     SellGraph g;
+    DiaGraph dg;
+    bool dia = false;               // constant-offset layout (dia.cuh) instead of the half-edge table
+    long long nhalf = 0;            // half-edge copies held per label (slots of the table / 2.ND.V)
     SP<real> p{};
     DevBuf<Ctl> ctl;
+    DevBuf<real> Wrow;
     DevIn<real> Q, La_f, La_d1, P0;
     DevIn<int> Eu, Ev;
     DevBuf<real> w, wk, thk, Z0, Z1, Pa, Pb, Fa, Fb, T, GaQ, Sinv, Sinvk, Gn, GaU, dObj, dDif, Pout, Qal;
@@ -685,12 +395,21 @@ struct SimplexSolver : SolverBase {
         if (sizeof(real) == 8 && ((Kv + 1) & ~1) <= 64 && !(fl && fl[0] == '4') &&
             ((size_t) V * (size_t) Kv <= ((size_t) 1 << 23) || (fl && fl[0] == '2'))) LPT = 2;
         if (Kv <= 2 || (fl && fl[0] == '1' && Kv <= 32)) LPT = 1;
-        K = ((Kv + LPT - 1) / LPT) * LPT;
-        const bool padded = K != Kv;
-        PFDR_REQUIRE((K + LPT - 1) / LPT <= 32, "this build supports K <= 128 labels");
         cudaStream_t st = ctx().stream;
         for (auto *e : {&ev[0], &ev[1], &ev_a, &ev_b, &ev_c}) *e = event_get();
         PFDR_CUDA(cudaEventRecord(ev_a, st));
+        Eu.bind(q.Eu, E); Ev.bind(q.Ev, E);
+        {   // constant-offset graph (grids): index-free layout, PFDR_B200_DIA=0 keeps the half-edge table (tests compare the two)
+            const char *de = getenv("PFDR_B200_DIA");
+            constexpr int DL = SimplexDiaLanes<real>::LPT;
+            const bool lanes_ok = Kv >= 3 && (Kv + DL - 1) / DL <= 32 && !(fl && fl[0] != '0' + DL);
+            if (!sharded && lanes_ok && !(de && de[0] == '0') && (size_t) V * (size_t) (((Kv + DL - 1) / DL) * DL) * 6 < ((size_t) 1 << 40))
+                dia = build_dia(dg, Eu, Ev, V, E);
+            if (dia) LPT = DL;
+        }
+        K = ((Kv + LPT - 1) / LPT) * LPT;
+        const bool padded = K != Kv;
+        PFDR_REQUIRE((K + LPT - 1) / LPT <= 32, "this build supports K <= 128 labels");
         static_assert(2 * sizeof(Ctl) <= PINNED_BLOCK, "control block mirror");
         hctl = (Ctl *) pinned_get();
         int TPV = 1, logTPV = 0;
@@ -698,7 +417,7 @@ struct SimplexSolver : SolverBase {
         const int C = 32 / TPV;
         int logC = 0; while ((1 << logC) < C) logC++;
         const size_t VK = (size_t) V * K;
-        Eu.bind(q.Eu, E); Ev.bind(q.Ev, E); Q.bind(q.Q, (size_t) V * Kv); La_d1.bind(q.La_d1, E);
+        Q.bind(q.Q, (size_t) V * Kv); La_d1.bind(q.La_d1, E);
         La_f.bind(q.al > (real) 0 ? q.La_f : nullptr, V); P0.bind(q.P, (size_t) V * Kv);
         if (padded) {
             DevBuf<real> Qp(VK), Pp(VK);
@@ -712,9 +431,17 @@ struct SimplexSolver : SolverBase {
             PFDR_CUDA(cudaMemcpyAsync(Qal.p, Q.p, VK * sizeof(real), cudaMemcpyDeviceToDevice, st));
             Q.own = std::move(Qal); Q.p = Q.own.p;
         }
-        build_sell(g, Eu, Ev, V, E, C);
-        const size_t ns = (size_t) std::max<long long>(g.nslots, 1);
-        w.alloc(ns); Z0.alloc(ns * K); Z1.alloc(ns * K);
+        if (dia) {
+            nhalf = 2LL * dg.ND * V;
+            Wrow.alloc((size_t) nhalf); Wrow.zero();
+            ctx().stats.slots = 2LL * E;
+        } else {
+            build_sell(g, Eu, Ev, V, E, C);
+            nhalf = g.nslots;
+            w.alloc((size_t) std::max<long long>(nhalf, 1));
+        }
+        const size_t ns = (size_t) std::max<long long>(nhalf, 1);
+        Z0.alloc(ns * K); Z1.alloc(ns * K);
         Pa.alloc(VK); Pb.alloc(VK); Fa.alloc(VK); Fb.alloc(VK); T.alloc(VK); GaQ.alloc(VK); Sinv.alloc(V);
         if (q.difRcd > (real) 0) GaU.alloc(VK);
         Z0.zero(); Z1.zero(); w.zero();
@@ -736,15 +463,16 @@ struct SimplexSolver : SolverBase {
         p.Vown = Vown; p.sharded = sharded ? 1 : 0; p.sums = sums.p; p.Vglobal = sharded ? q.shard->Vglobal : V;
         p.world = sharded ? comm().world : 1; p.rank = sharded ? comm().rank : 0;
         {   // banded graph whose +-band reuse window would not fit the L2: sweep (x,y)-tiles along z instead
-            const double bytes_per_vertex = (double) sizeof(real) * K * (2.0 * std::max(g.max_width, 1) + 6.0);
+            const int width = dia ? 2 * dg.ND : std::max(g.max_width, 1), band = dia ? (dg.ND > 1 ? dg.band() : 0) : g.band;
+            const double bytes_per_vertex = (double) sizeof(real) * K * (2.0 * width + 6.0);
             const char *e = getenv("PFDR_B200_TILE");
             const long long tile_env = e ? atoll(e) : -1;
             p.order = nullptr;
-            if (tile_env != 0 && g.band > 0 && ((double) g.band * bytes_per_vertex > 24e6 || tile_env > 0)) {
+            if (tile_env != 0 && band > 0 && ((double) band * bytes_per_vertex > 24e6 || tile_env > 0)) {
                 long long T = tile_env > 0 ? tile_env : (long long) (5e6 / bytes_per_vertex);
-                T = std::max<long long>(C, std::min<long long>(T, g.band));
+                T = std::max<long long>(C, std::min<long long>(T, band));
                 T = (T / C) * C;
-                build_slice_order(g, (int) (((long long) Vown + C - 1) / C), (int) T, order);
+                build_chunk_order((int) (((long long) Vown + C - 1) / C), C, band, (int) T, order);
                 p.order = order.p;
             }
         }
@@ -754,6 +482,9 @@ struct SimplexSolver : SolverBase {
         p.aK = q.al / (real) Kv; p.a1 = (real) 1 - q.al; p.aK1 = p.aK / p.a1;                     // ref :386-391
         p.rho = q.rho; p.condMin = q.condMin;
         p.slice_off = g.slice_off.p; p.nbr = g.nbr.p; p.twin = g.twin.p; p.hkey = g.hkey.p;
+        p.dia_nd = dia ? dg.ND : 0;
+        for (int i = 0; i < 3; i++) p.dia_off[i] = dia ? dg.off[i] : 0;
+        p.vbeg = 0; p.vend = Vown; p.dmask = dg.mask.p; p.eoff = dg.eoff.p; p.Wrow = Wrow.p;
         p.w = w.p; p.wk = nullptr; p.thk = nullptr; p.Z0 = Z0.p; p.Z1 = Z1.p;
         p.P0 = Pa.p; p.P1 = Pb.p; p.F0 = Fa.p; p.F1 = Fb.p; p.T = T.p; p.GaQ = GaQ.p; p.Sinv = Sinv.p;
         p.Sinvk = nullptr; p.Gn = nullptr; p.GaU = GaU.p; p.lab = lab.p;
@@ -769,6 +500,7 @@ struct SimplexSolver : SolverBase {
 
     void launch_precond(const real *Pinit, int recond)
     {
+        if (dia) { simplex_dia_launch_precond<real>(p, Pinit, recond, grid); return; }
         if (LPT == 4) PFDR_LAUNCH((simplex_precond_kernel<real, 4>), grid, 256, 0, p, Pinit, recond);
         else if (LPT == 2) { if constexpr (sizeof(real) == 8) PFDR_LAUNCH((simplex_precond_kernel<real, 2>), grid, 256, 0, p, Pinit, recond); }
         else PFDR_LAUNCH((simplex_precond_kernel<real, 1>), grid, 256, 0, p, Pinit, recond);
@@ -829,7 +561,8 @@ struct SimplexSolver : SolverBase {
             const size_t work = (size_t) std::max(q.E, q.V) * p.K;
             PFDR_LAUNCH(simplex_objective_kernel<real>, std::min<unsigned>(cdiv(work, 256), num_sms() * 8), 256, 0, p);
         }
-        if (LPT == 4) { if (p.wk) launch_iter_loss<4, true>(); else launch_iter_loss<4, false>(); }
+        if (dia) simplex_dia_launch_iter<real>(p, ogrid);
+        else if (LPT == 4) { if (p.wk) launch_iter_loss<4, true>(); else launch_iter_loss<4, false>(); }
         else if (LPT == 2) { if constexpr (sizeof(real) == 8) { if (p.wk) launch_iter_loss<2, true>(); else launch_iter_loss<2, false>(); } }
         else { if (p.wk) launch_iter_loss<1, true>(); else launch_iter_loss<1, false>(); }
         if (sharded) {     // evolution sum over all ranks, then the new boundary forward points and cut-edge copies
@@ -866,7 +599,7 @@ struct SimplexSolver : SolverBase {
     void recondition()
     {
         if (!wk.p) {
-            const size_t n = (size_t) std::max<long long>(g.nslots, 1) * p.K, VK = (size_t) q.V * p.K;
+            const size_t n = (size_t) std::max<long long>(nhalf, 1) * p.K, VK = (size_t) q.V * p.K;
             wk.alloc(n); thk.alloc(n); wk.zero(); thk.zero();
             Sinvk.alloc(VK); Gn.alloc(VK);
             if (p.K != p.Kv) { Sinvk.zero(); Gn.zero(); }                       // padded labels: defined values
@@ -888,7 +621,7 @@ struct SimplexSolver : SolverBase {
     void run() override
     {
         cudaStream_t st = ctx().stream;
-        const size_t work = (size_t) g.nslots * p.K;
+        const size_t work = (size_t) nhalf * p.K;
         int batch = work > (1u << 24) ? 4 : (work > (1u << 20) ? 16 : 64);
         batch = std::max(1, std::min(batch, q.itMax + 1));
         ctx().in_loop = true;

@@ -29,9 +29,10 @@ def c2_denoise(n=100, dtype=np.float32, diag=True, seed=2, const_weights=False):
                 Eu=Eu, Ev=Ev, La_d1=La_d1.astype(dtype))
 
 
-def c4_simplex(n=64, K=16, dtype=np.float32, seed=6):
-    """C4: K-label smoothed-KL problem on the n^3 grid; truth label = 4*floor(4z/n) + floor(4y/n)."""
-    V, Eu, Ev = grid_graph(n)
+def c4_simplex(n=64, K=16, dtype=np.float32, seed=6, nz=None):
+    """C4: K-label smoothed-KL problem on the n^3 grid; truth label = 4*floor(4z/n) + floor(4y/n).
+    nz < n: only the first nz z-planes of that problem (a bounded sample for the CPU legs of bench.py)."""
+    V, Eu, Ev = grid_graph(n, nz)
     v = np.arange(V)
     z, y = v // (n * n), (v // n) % n
     lab = (4 * np.minimum(4 * z // n, 3) + np.minimum(4 * y // n, 3)) % K

@@ -1,0 +1,141 @@
+"""BASELINE.json's configurations at their PARITY sizes, CUDA path through the C ABI against
+the UNMODIFIED reference itself (oracle/_ref/libref.so, which travels to the GPU box) on the same seeded inputs:
+
+  C2  PFDR_graph_l22_d1_l1, grid 100^3 (1M vertices), float32 + float64, difTol=1e-5, itMax=1000, Obj + Dif
+  C4  PFDR_graph_loss_d1_simplex smoothed-KL, K=16, grid 64^3, difTol=1e-4
+  C3  CP_PFDR_graph_quadratic_d1_bounds with precomputed AtA, V=4096, 10-NN graph: identical rV / Cv
+  C5  a slice of PFDR_graph_quadratic_d1_l1 with dense A: n=100 (1M vertices), N=256
+  C1  EEG-like cut-pursuit (icosphere level 5) with libpfdr_b200's OWN operator_norm_matrix: identical rV / Cv
+
+Tolerances are BASELINE.json's: 1e-5 relative in float64, 1e-3 in float32 (iterate and objective).
+These are the sizes at which the full-size code paths switch on (many CTAs per reduction, graph batches of 4/16,
+stencil layout with thousands of tiles); the small cases of test_gpu_quadratic/simplex.py cover the option space."""
+import numpy as np
+import pytest
+
+from cp_pfdr_graph_d1_b200 import synth
+
+pytestmark = pytest.mark.gpu
+TOL = {np.float32: 1e-3, np.float64: 1e-5}
+
+
+def rel(a, b):
+    return float(np.linalg.norm(a.astype(np.float64) - b.astype(np.float64)) / max(float(np.linalg.norm(b.astype(np.float64))), 1e-300))
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_c2_grid100_vs_reference(gpu_api, reference, dtype):
+    w = synth.c2_denoise(100, dtype, diag=True)
+    kw = dict(rho=1.5, condMin=1e-3, difRcd=0.0, difTol=1e-5, itMax=1000, want_obj=True, want_dif=True)
+    got = gpu_api.PFDR_graph_l22_d1_l1(w["Y"], w["La_l2"], w["Eu"], w["Ev"], w["La_d1"], **kw)
+    ref = gpu_api.PFDR_graph_l22_d1_l1(w["Y"], w["La_l2"], w["Eu"], w["Ev"], w["La_d1"], backend=reference, **kw)
+    tol = TOL[dtype]
+    slack = 0 if dtype is np.float64 else max(2, ref.it // 50)
+    assert abs(got.it - ref.it) <= slack, (got.it, ref.it)
+    assert ref.it > 20
+    assert rel(got.X, ref.X) < tol, rel(got.X, ref.X)
+    n = min(got.it, ref.it)
+    assert np.allclose(got.Obj[:n + 1], ref.Obj[:n + 1], rtol=tol), np.abs(got.Obj[:n + 1] / ref.Obj[:n + 1] - 1).max()
+    sel = ref.Dif[:n] > (1e-9 if dtype is np.float32 else 1e-24)
+    assert np.allclose(got.Dif[:n][sel], ref.Dif[:n][sel], rtol=5e-2 if dtype is np.float32 else 1e-4)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_c2_grid100_l1_positivity_vs_reference(gpu_api, reference, dtype):
+    """the C2 variant of SURVEY 8d with La_l1 = 0.05 and positivity (exercises the l1 vertex prox at size)"""
+    w = synth.c2_denoise(100, dtype, diag=True)
+    La_l1 = np.full(w["V"], 0.05, dtype)
+    kw = dict(La_l1=La_l1, positivity=1, rho=1.5, condMin=1e-3, difRcd=0.0, difTol=1e-4, itMax=300, want_obj=True, want_dif=True)
+    got = gpu_api.PFDR_graph_l22_d1_l1(w["Y"], w["La_l2"], w["Eu"], w["Ev"], w["La_d1"], **kw)
+    ref = gpu_api.PFDR_graph_l22_d1_l1(w["Y"], w["La_l2"], w["Eu"], w["Ev"], w["La_d1"], backend=reference, **kw)
+    tol = TOL[dtype]
+    assert abs(got.it - ref.it) <= (0 if dtype is np.float64 else max(2, ref.it // 50)), (got.it, ref.it)
+    assert rel(got.X, ref.X) < tol, rel(got.X, ref.X)
+    n = min(got.it, ref.it)
+    assert np.allclose(got.Obj[:n + 1], ref.Obj[:n + 1], rtol=tol)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_c4_grid64_k16_vs_reference(gpu_api, reference, dtype):
+    w = synth.c4_simplex(64, 16, dtype)
+    kw = dict(rho=1.5, condMin=1e-2, difRcd=0.0, difTol=1e-4, itMax=120, want_obj=True, want_dif=True)
+    got = gpu_api.PFDR_graph_loss_d1_simplex(w["Q"].copy(), w["Q"], 0.05, w["Eu"], w["Ev"], w["La_d1"], **kw)
+    ref = reference.PFDR_graph_loss_d1_simplex(w["Q"].copy(), w["Q"], 0.05, w["Eu"], w["Ev"], w["La_d1"], **kw)
+    tol = TOL[dtype]
+    assert abs(got.it - ref.it) <= (0 if dtype is np.float64 else max(2, ref.it // 20)), (got.it, ref.it)
+    assert ref.it >= 20
+    assert rel(got.X, ref.X) < tol, rel(got.X, ref.X)
+    assert np.allclose(got.X.sum(axis=1), 1.0, atol=1e-5 if dtype is np.float32 else 1e-12) and (got.X >= 0).all()
+    n = min(got.it, ref.it)
+    assert np.allclose(got.Obj[:n + 1], ref.Obj[:n + 1], rtol=tol), np.abs(got.Obj[:n + 1] / ref.Obj[:n + 1] - 1).max()
+    m = max(1, n // 2) if dtype is np.float32 else n
+    assert np.allclose(got.Dif[:m], ref.Dif[:m], rtol=5e-2 if dtype is np.float32 else 1e-4, atol=1e-6 if dtype is np.float32 else 1e-12)
+
+
+def test_c4_grid64_k16_recond_labels_vs_reference(gpu_api, reference):
+    """C4 with a reconditioning (difRcd > 0) and the label-change stopping rule (difTol >= 1), float64"""
+    w = synth.c4_simplex(48, 16, np.float64)
+    for kw in (dict(difRcd=1e-2, difTol=1e-5, itMax=80), dict(difRcd=0.0, difTol=1.0, itMax=60)):
+        kw = dict(rho=1.5, condMin=1e-2, want_obj=True, want_dif=True, **kw)
+        got = gpu_api.PFDR_graph_loss_d1_simplex(w["Q"].copy(), w["Q"], 0.05, w["Eu"], w["Ev"], w["La_d1"], **kw)
+        ref = reference.PFDR_graph_loss_d1_simplex(w["Q"].copy(), w["Q"], 0.05, w["Eu"], w["Ev"], w["La_d1"], **kw)
+        assert got.it == ref.it, (got.it, ref.it)
+        assert rel(got.X, ref.X) < 1e-5, rel(got.X, ref.X)
+        assert np.allclose(got.Obj, ref.Obj, rtol=1e-5)
+        if kw["difTol"] >= 1:
+            assert np.array_equal(got.Dif, ref.Dif)
+
+
+def test_c5_slice_dense_n100_N256_vs_reference(gpu_api, reference):
+    """C5 at the largest size the reference's 32-bit N*V products allow comfortably: 1M vertices x 256 rows, float32"""
+    dt = np.float32
+    w = synth.dense_problem(100, 256, dt)
+    V, N = w["V"], w["N"]
+    lam = np.array([1.05 * (V ** 0.5 + N ** 0.5) ** 2 / 768.0], dt)     # Marchenko-Pastur edge of iid U(-1/16, 1/16) entries
+    kw = dict(N=N, Ltype=0, L=lam, rho=1.0, condMin=1e-3, difRcd=0.0, difTol=0.0, itMax=25, want_obj=True, want_dif=True)
+    args = (w["Y"], w["A"], w["Eu"], w["Ev"], w["La_d1"], None, 0)
+    got = gpu_api.PFDR_graph_quadratic_d1_l1(np.zeros(V, dt), *args, **kw)
+    ref = reference.PFDR_graph_quadratic_d1_l1(np.zeros(V, dt), *args, **kw)
+    assert got.it == ref.it == 25
+    assert rel(got.X, ref.X) < 1e-3, rel(got.X, ref.X)
+    assert np.allclose(got.Obj, ref.Obj, rtol=1e-3), np.abs(got.Obj / ref.Obj - 1).max()
+
+
+@pytest.fixture(scope="module")
+def cps(gpu_api):
+    from oracle import oracle as O
+    ref, b200 = O.cp_reference(), O.cp_b200()
+    if ref is None or b200 is None:
+        pytest.skip("oracle/_ref cut-pursuit libraries not built (need /root/reference at build time)")
+    return ref, b200
+
+
+def check_cp(r0, r1, tol=1e-5):
+    assert r1["rV"] == r0["rV"] and r1["CP_it"] == r0["CP_it"], (r1["rV"], r0["rV"], r1["CP_it"], r0["CP_it"])
+    assert np.array_equal(r1["Cv"], r0["Cv"])
+    assert rel(r1["rX"], r0["rX"]) < tol, rel(r1["rX"], r0["rX"])
+    assert np.allclose(r1["Obj"], r0["Obj"], rtol=tol)
+
+
+def test_c3_cp_bounds_ata_v4096(cps):
+    """config 3 at V = 4096: the reference's cut-pursuit with every hot-path routine (PFDR and operator_norm_matrix)
+    served by libpfdr_b200 -> identical component count and vertex -> component assignment"""
+    ref, b200 = cps
+    w = synth.c3_bounds_ata(4096, 10, 1024, np.float64)
+    kw = dict(CP_difTol=1e-4, CP_itMax=10, rho=1.5, condMin=1e-3, difRcd=0.0, difTol=1e-7, itMax=10000)
+    args = (w["AtY"], w["AtA"], w["Eu"], w["Ev"], w["La_d1"], 0.0, 1.0, -w["V"])
+    r0 = ref.quadratic_d1_bounds(*args, **kw)
+    assert r0["rV"] > 10
+    check_cp(r0, b200.quadratic_d1_bounds(*args, **kw))
+
+
+def test_c1_cp_eeg_like_level5_own_norm(cps):
+    """config 1 stand-in at the reference's settings (octave/example_EEG_CP.m:20-27) with libpfdr_b200's own
+    operator_norm_matrix behind the reference's unmodified cut-pursuit"""
+    ref, b200 = cps
+    w = synth.eeg_like(5, 91, np.float64)
+    kw = dict(CP_difTol=1e-4, CP_itMax=15, rho=1.5, condMin=1e-3, difRcd=0.0, difTol=1e-7, itMax=10000)
+    args = (w["Y"], w["A"], w["Eu"], w["Ev"], w["La_d1"], w["La_l1"], 1, w["N"])
+    r0 = ref.quadratic_d1_l1(*args, **kw)
+    assert r0["rV"] > 10
+    check_cp(r0, b200.quadratic_d1_l1(*args, **kw))

@@ -145,6 +145,28 @@ def test_resident_handle_matches_one_shot(gpu_api, dtype):
     s.close()
 
 
+@pytest.mark.parametrize("small", ["0", "1"])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("name", ["grid_diag_recond", "rand_big_recond", "dense_ata_recond"])
+def test_resident_handle_with_reconditioning(gpu_api, monkeypatch, name, dtype, small):
+    """(reset, run) x 3 on a handle whose solve reconditions (difRcd > 0): reset() drops the per-slot thresholds and
+    the next reconditioning must bring them back (both the one-kernel-per-iteration and the cluster path)"""
+    monkeypatch.setenv("PFDR_B200_SMALL", small)
+    fam, args, kw = problems.quad_case(name, dtype)
+    ref = problems.run_quad(gpu_api._b(), name, dtype)
+    X0, Y, A, Eu, Ev, La_d1, La_l1, pos, Ltype, L = args
+    s = gpu_api.QuadraticSolver(X0, Y, A, Eu, Ev, La_d1, La_l1, pos, Ltype=Ltype, L=L, rho=kw["rho"],
+                                condMin=kw["condMin"], difRcd=kw["difRcd"], difTol=kw["difTol"], itMax=kw["itMax"],
+                                N=kw["N"], want_obj=True, want_dif=True)
+    for _ in range(3):
+        s.reset()
+        s.run()
+        r = s.fetch(want_obj=True, want_dif=True)
+        assert r.it == ref.it
+        assert np.array_equal(r.X, ref.X) and np.array_equal(r.Dif, ref.Dif)
+    s.close()
+
+
 @pytest.mark.parametrize("V", [2, 5, 31, 32, 33, 64, 100, 257, 1000, 3000])
 @pytest.mark.parametrize("kind", ["diag", "dense", "ata"])
 def test_paths_agree_on_irregular_graphs(gpu_api, oracle, monkeypatch, V, kind):

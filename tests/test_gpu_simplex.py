@@ -53,6 +53,30 @@ def test_simplex_parity_scalar_lanes(gpu_api, oracle, monkeypatch, name, dtype):
     assert np.allclose(got.Obj[:n + 1], ref.Obj[:n + 1], rtol=tol, atol=tol * max(float(np.abs(ref.Obj).max()), 1.0) * 1e-1)
 
 
+@pytest.mark.parametrize("knobs", [{"PFDR_B200_TILE": "32"}, {"PFDR_B200_TILE": "8", "PFDR_B200_IDX32": "0"},
+                                   {"PFDR_B200_LPT": "4"}, {"PFDR_B200_LPT": "4", "PFDR_B200_TILE": "16"},
+                                   {"PFDR_B200_IDX32": "0"}, {"PFDR_B200_LPT": "2", "PFDR_B200_TILE": "24"}],
+                         ids=lambda k: "+".join(f"{a[10:]}={b}" for a, b in k.items()))
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("name", ["kla_k16", "kla_recond_k16", "kla_labels_k16", "quad_weighted_k16", "lin_k16", "kla_k33", "kla"])
+def test_simplex_parity_size_gated_paths(gpu_api, oracle, monkeypatch, name, dtype, knobs):
+    """the code paths that full-size problems switch on by size - the tiled slice order (252^3), four labels per lane
+    in float64 (V.K > 2^23), 64-bit element offsets (> 2^32 elements) - forced on the small cases the oracle can run"""
+    from cp_pfdr_graph_d1_b200.api import _b
+    for k, v in knobs.items():
+        monkeypatch.setenv(k, v)
+    got = problems.run_simplex(_b(), name, dtype)
+    ref = problems.run_simplex(oracle, name, dtype)
+    tol = TOL[dtype]
+    assert abs(got.it - ref.it) <= (0 if dtype is np.float64 else max(2, ref.it // 20)), (got.it, ref.it)
+    assert rel(got.X, ref.X) < tol, rel(got.X, ref.X)
+    assert np.allclose(got.X.sum(axis=1), 1.0, atol=1e-5 if dtype is np.float32 else 1e-12) and (got.X >= 0).all()
+    n = min(got.it, ref.it)
+    assert np.allclose(got.Obj[:n + 1], ref.Obj[:n + 1], rtol=tol, atol=tol * max(float(np.abs(ref.Obj).max()), 1.0) * 1e-1)
+    if "labels" in name and dtype is np.float64:
+        assert np.array_equal(got.Dif[:n], ref.Dif[:n])
+
+
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 @pytest.mark.parametrize("D", [1, 2, 5, 16, 32, 33, 100])
 def test_proj_simplex_metric(gpu_api, oracle, dtype, D):
