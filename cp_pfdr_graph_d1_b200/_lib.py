@@ -11,7 +11,8 @@ HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "pfdr_b200.h")
 class Stats(C.Structure):
     _fields_ = [("setup_ms", C.c_double), ("loop_ms", C.c_double), ("total_ms", C.c_double),
                 ("launches", C.c_longlong), ("loop_launches", C.c_longlong), ("iterations", C.c_int),
-                ("h2d_bytes", C.c_longlong), ("d2h_bytes", C.c_longlong), ("slots", C.c_longlong)]
+                ("h2d_bytes", C.c_longlong), ("d2h_bytes", C.c_longlong), ("slots", C.c_longlong),
+                ("layout", C.c_int), ("gpus", C.c_int)]
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -19,6 +19,9 @@
 // so only the raw weight w is streamed per half-edge.
 #include "graph.cuh"
 #include "solvers.cuh"
+#include "quad.cuh"
+#include "dia.cuh"
+#include "quad_dia.cuh"
 #include <cooperative_groups.h>
 #include <chrono>
 #include <vector>
@@ -26,81 +29,6 @@
 namespace cg = cooperative_groups;
 namespace pfdr {
 
-template <typename real> using pair_t = typename Pair<real>::type;
-
-template <typename real>
-struct QP {                       // kernel parameter block
-    Ctl *ctl;
-    int V, N, E;
-    int Vown, sharded;            // vertices this rank owns (== V unless sharded: ghosts follow)
-    int world, rank;              // sharded: sums holds one pair per rank, sums[2*rank..] is ours
-    double *sums;                 // [2*world] evolution sums of every rank (sharded path), gathered with the halo exchange
-    double *amp_sums;             // [2] amplitude sums (all-reduced)
-    double *rsum;                 // [N] sum of A x over this rank's columns (sharded dense A)
-    const long long *slice_off; const int *nbr, *twin, *hkey;
-    const int4 *pk;               // per slot {nbr, twin, w, [threshold]} in 16 bytes: one vector load per row in the iteration kernel
-    const int2 *pk2;              // per slot {nbr, twin}: float32 before a reconditioning (16 bytes would carry an unused word)
-    real *w;                      // [slots] raw d1 weight of the half-edge's edge
-    real *thc;                    // [slots] La_d1/w after a reconditioning (NULL: thc0 for all)
-    real thc0;
-    real *Z0, *Z1;                // [slots] edge copies, ping/pong by iteration parity
-    real *X0, *X1;                // [V] iterate, ping/pong by iteration parity
-    real *P0, *P1;                // [V] forward point 2x - Ga.grad(x), ping/pong (the only vertex value a
-                                  //     neighbour gathers, hence stored apart from x)
-    real *T, *Sinv, *Ga, *Ga0, *G, *Thl1, *R, *AtY;
-    const real *Y, *A, *La_d1, *La_l1, *L;
-    const int *Eu, *Ev;
-    int Ltype, positivity, prox_kind, has_lo, has_hi;
-    real lo, hi, rho, condMin;
-    double *partial;
-    real *dObj, *dDif;
-    int nparts;                   // CTAs of ax_partial
-};
-
-constexpr int HUB_ROWS = 32;      // rows of a SELL slice walked by one thread per vertex; past that the warp shares a hub's row
-
-template <typename real> __device__ __forceinline__ real rabs(real a) { return a < (real) 0 ? -a : a; }
-
-// gradient of the smooth part at vertex v (x = X[v]); dense cases read what the A-kernels left in G
-template <typename real>
-__device__ __forceinline__ real grad_at(const QP<real> &p, int v, real x)
-{
-    if (p.N == 0) return (p.A ? p.A[v] * x : x) - p.Y[v];
-    if (p.N < 0) return p.G[v] - p.Y[v];
-    return p.G[v];
-}
-
-// Sum NV doubles over the whole grid, deterministically: per-CTA partials, the last CTA to finish
-// adds them in a fixed order.  Returns true (in every thread) only in that last CTA, v valid in thread 0.
-template <int NV>
-__device__ bool grid_sum(Ctl *ctl, double *partial, double (&v)[NV], double *smem)
-{
-    __shared__ int s_last;
-    block_sum<NV>(v, smem);
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int i = 0; i < NV; i++) partial[(size_t) blockIdx.x * NV + i] = v[i];
-        __threadfence();
-        const unsigned t = atomicAdd(&ctl->ticket, 1u);
-        s_last = (t == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!s_last) return false;
-    __threadfence();
-    double acc[NV];
-#pragma unroll
-    for (int i = 0; i < NV; i++) acc[i] = 0.0;
-    const volatile double *vp = partial;
-    for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
-#pragma unroll
-        for (int i = 0; i < NV; i++) acc[i] += vp[(size_t) b * NV + i];
-    }
-    block_sum<NV>(acc, smem);
-#pragma unroll
-    for (int i = 0; i < NV; i++) v[i] = acc[i];
-    if (threadIdx.x == 0) ctl->ticket = 0;
-    return true;
-}
 
 // ---------------------------------------------------------------------------------------------
 // preconditioning (ref src/PFDR_graph_quadratic_d1_l1.cpp:57-268)
@@ -142,19 +70,6 @@ __global__ void amp_finish_kernel(QP<real> p, int recond)
     p.ctl->amp = recond ? (double) ((real) a / (real) n) : (double) ((real) n / (real) a);
 }
 
-template <typename real>
-__device__ __forceinline__ real clamp_metric(const QP<real> &p, int v, real ga)
-{   // ref :222-239
-    const real bound = (real) 1.9 * ((real) 2 - p.rho);
-    if (p.Ltype == PFDR_B200_SCAL || p.L == nullptr) {
-        const real b = p.L ? bound / p.L[0] : bound;
-        if (ga > b) ga = b;
-    } else if (p.L[v] > (real) 0) {
-        const real b = bound / p.L[v];
-        if (ga > b) ga = b;
-    }
-    return ga;
-}
 
 // first preconditioning + initial state: w = c La_d1 (:160-166), S, Ga, T, Th_l1, z_e = x (:321-324)
 template <typename real>
@@ -247,22 +162,6 @@ __global__ void resume_kernel(QP<real> p, double rcd_factor)
 // ---------------------------------------------------------------------------------------------
 // the fused iteration kernel
 // ---------------------------------------------------------------------------------------------
-// end of an iteration: evolution measure, iteration counter, stop / recondition decision (ref :429, :448, :515-529)
-template <typename real>
-__device__ void quad_finalize(const QP<real> &p, int it, double d, double c)
-{
-    Ctl *ctl = p.ctl;
-    double dif = ctl->dif;
-    if (ctl->track) {
-        dif = (c > ctl->eps) ? d / c : d / ctl->eps;
-        ctl->dif = dif;
-        if (p.dDif) p.dDif[it] = (real) dif;
-    }
-    const int itn = it + 1;
-    ctl->it = itn;
-    if (itn == ctl->itMax || (real) dif < (real) ctl->tol) ctl->state = ST_FINAL;
-    else if ((real) dif < (real) ctl->rcd) ctl->state = ST_RECOND;
-}
 
 // sharded path: the sums were all-reduced over the ranks between the iteration kernel and this one
 template <typename real>
@@ -1663,8 +1562,12 @@ struct QuadSolver : SolverBase {
     const QuadProblem<real> q;
     bool keep_x0 = false;
     SellGraph g;
+    DiaGraph dg;
+    bool dia = false;               // constant-offset layout (dia.cuh) instead of the half-edge table
+    long long nhalf = 0;            // half-edge copies held (slots of the table / 2.ND.V)
     QP<real> p{};
     DevBuf<Ctl> ctl;
+    DevBuf<real> Wrow;
     DevIn<real> Y, A, La_d1, La_l1, L, X0;
     DevIn<int> Eu, Ev;
     DevBuf<real> w, thc, Z0, Z1, X0b, X1b, P0b, P1b, T, Sinv, Ga, Ga0, G, Thl1, R, AtY, dObj, dDif, Xout;
@@ -1719,11 +1622,27 @@ struct QuadSolver : SolverBase {
         La_d1.bind(q.La_d1, E); La_l1.bind(q.prox_kind == 0 ? q.La_l1 : nullptr, V);
         L.bind(q.L, q.L ? (q.Ltype == PFDR_B200_SCAL ? 1 : (size_t) V) : 0);
         X0.bind(q.X, V);
-        build_sell(g, Eu, Ev, V, E, 32);
-        rowsW = g.max_width;
+        {   // Constant-offset graph (grids) that will not run in the single-launch cluster kernels: index-free layout.
+            // PFDR_B200_DIA=0 keeps the half-edge table, =1 tries the stencil layout at any size (tests compare the two).
+            const char *de = getenv("PFDR_B200_DIA"), *se = getenv("PFDR_B200_SMALL");
+            const bool small_off = se && se[0] == '0';
+            const bool forced = de && de[0] == '1';
+            if (!sharded && !(de && de[0] == '0') && (forced || small_off || !small_candidate()))
+                dia = build_dia(dg, Eu, Ev, V, E);
+        }
+        if (dia) {
+            nhalf = 2LL * dg.ND * V;
+            Wrow.alloc((size_t) nhalf);
+            ctx().stats.slots = 2LL * E; ctx().stats.layout = 1;
+        } else {
+            build_sell(g, Eu, Ev, V, E, 32);
+            rowsW = g.max_width;
+            nhalf = g.nslots;
+            w.alloc((size_t) std::max<long long>(nhalf, 1));
+        }
 
-        const size_t ns = (size_t) std::max<long long>(g.nslots, 1);
-        w.alloc(ns); Z0.alloc(ns); Z1.alloc(ns);
+        const size_t ns = (size_t) std::max<long long>(nhalf, 1);
+        Z0.alloc(ns); Z1.alloc(ns);
         X0b.alloc(V); X1b.alloc(V); P0b.alloc(V); P1b.alloc(V); T.alloc(V); Sinv.alloc(V); Ga.alloc(V); Ga0.alloc(V);
         if (La_l1.p) Thl1.alloc(V);
         if (N != 0) G.alloc(V);
@@ -1741,6 +1660,9 @@ struct QuadSolver : SolverBase {
         p.Vown = sharded ? q.shard->Vown : V; p.sharded = sharded ? 1 : 0; p.sums = sums.p; p.amp_sums = amp_sums.p;
         p.world = sharded ? comm().world : 1; p.rank = sharded ? comm().rank : 0;
         p.slice_off = g.slice_off.p; p.nbr = g.nbr.p; p.twin = g.twin.p; p.hkey = g.hkey.p;
+        p.dia_nd = dia ? dg.ND : 0;
+        for (int i = 0; i < 3; i++) p.dia_off[i] = dia ? dg.off[i] : 0;
+        p.vbeg = 0; p.vend = sharded ? q.shard->Vown : V; p.dmask = dg.mask.p; p.eoff = dg.eoff.p; p.Wrow = Wrow.p;
         p.w = w.p; p.thc = nullptr; p.thc0 = 0; p.Z0 = Z0.p; p.Z1 = Z1.p;
         p.pk = nullptr; p.pk2 = nullptr;           // set by pack_slots() after each (re)conditioning (PFDR_B200_PACK=0: off)
         p.X0 = X0b.p; p.X1 = X1b.p; p.P0 = P0b.p; p.P1 = P1b.p; p.T = T.p; p.Sinv = Sinv.p; p.Ga = Ga.p; p.Ga0 = Ga0.p; p.G = G.p; p.Thl1 = Thl1.p;
@@ -1765,7 +1687,7 @@ struct QuadSolver : SolverBase {
         } else if (N < 0) {
             vec = ((V % vmax == 0) && (((uintptr_t) A.p) % 16 == 0)) ? vmax : 1;
         }
-        const int maxgrid = std::max(std::max(std::max(vgrid, g.nslices), p.nparts), num_sms() * 8);
+        const int maxgrid = std::max(std::max(std::max(vgrid, dia ? 0 : g.nslices), p.nparts), num_sms() * 8);
         partial.alloc((size_t) maxgrid * 4);
         p.partial = partial.p;
 
@@ -1799,7 +1721,8 @@ struct QuadSolver : SolverBase {
         if (q.N > 0) launch_atr(1);
         PFDR_LAUNCH(amp_kernel<real>, ogrid, 256, 0, p, 0);
         if (sharded) { comm_allreduce_sum(amp_sums.p, 2); PFDR_LAUNCH(amp_finish_kernel<real>, 1, 1, 0, p, 0); }
-        PFDR_LAUNCH(init_vertex_kernel<real>, vgrid, 256, 0, p, X0.p);
+        if (dia) quad_dia_launch_init<real>(p, X0.p, vgrid);
+        else PFDR_LAUNCH(init_vertex_kernel<real>, vgrid, 256, 0, p, X0.p);
         // ghosts: the metric constants and forward point come from their owners
         if (sharded) halo.exchange(HALO_VA0 | HALO_VA1, PingPong<real>(T.p), PingPong<real>(P0b.p), PingPong<real>(), nullptr, PARITY_ZERO);
         PFDR_CUDA(cudaMemcpyAsync(&hctl[1], ctl.p, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
@@ -1816,7 +1739,7 @@ struct QuadSolver : SolverBase {
     {
         const char *e = getenv("PFDR_B200_PACK");
         p.pk = nullptr; p.pk2 = nullptr;
-        if (e && e[0] == '0') return;
+        if (dia || (e && e[0] == '0')) return;
         const size_t ns = (size_t) std::max<long long>(g.nslots, 1);
         // (buffers are kept across reset(): a captured graph holds their addresses)
         if (sizeof(real) == 4 && !p.thc && !(e && e[0] == '4')) { if (pk2b.n != ns) pk2b.alloc(ns); p.pk2 = pk2b.p; }
@@ -1869,6 +1792,7 @@ struct QuadSolver : SolverBase {
     int rowsW = 0;
     void launch_iter()
     {
+        if (dia) { quad_dia_launch_iter<real>(p, ogrid); return; }
         static int U = -1, mode = -1;
         if (U < 0) { const char *e = getenv("PFDR_B200_U"); U = e ? atoi(e) : 0; }
         if (mode < 0) { const char *e = getenv("PFDR_B200_KERNEL"); mode = (e && !strcmp(e, "rows")) ? 0 : 1; }
@@ -1952,11 +1876,12 @@ struct QuadSolver : SolverBase {
 
     void recondition()
     {
-        if (!thc.p) thc.alloc(std::max<size_t>(g.nslots, 1));
+        if (!thc.p) thc.alloc(std::max<size_t>(nhalf, 1));
         if (!p.thc) { thc.zero(); p.thc = thc.p; }                       // first reconditioning since setup() / reset()
         if (gexec) { cudaGraphExecDestroy(gexec); gexec = nullptr; }   // kernel parameters changed
         PFDR_LAUNCH(amp_kernel<real>, vgrid, 256, 0, p, 1);
-        PFDR_LAUNCH(recond_vertex_kernel<real>, vgrid, 256, 0, p);
+        if (dia) quad_dia_launch_recond<real>(p, vgrid);
+        else PFDR_LAUNCH(recond_vertex_kernel<real>, vgrid, 256, 0, p);
         pack_slots();
         PFDR_LAUNCH(resume_kernel<real>, 1, 1, 0, p, 0.01);                   // ref :458
     }
@@ -1967,10 +1892,17 @@ struct QuadSolver : SolverBase {
         const size_t Np = std::max(q.N, 0), Vp = ((size_t) q.V + 3) & ~(size_t) 3;
         return 64 * sizeof(double) + (3 * Vp + ((Np + 3) & ~(size_t) 3) + 32 * Np) * sizeof(real);
     }
+    // could the single-launch cluster kernels take this problem?  (decided before any layout exists: sizes only)
+    bool small_candidate() const
+    {
+        const long long dense = q.N > 0 ? (long long) q.N * q.V : (q.N < 0 ? (long long) q.V * q.V : 0);
+        if (q.N == 0 && 2LL * q.E > 49152) return false;
+        return small_smem() <= 200 * 1024 && q.V <= SMALL_MAX_SLICES * 32 && q.E <= (1 << 19) && dense <= (1 << 22);
+    }
     bool small_mode() const
     {
         const char *e = getenv("PFDR_B200_SMALL");        // read per call: the tests switch it
-        if ((e && e[0] == '0') || sharded) return false;
+        if ((e && e[0] == '0') || sharded || dia) return false;
         const long long dense = q.N > 0 ? (long long) q.N * q.V : (q.N < 0 ? (long long) q.V * q.V : 0);
         // Regular graphs without dense operator: the large path costs ~7.5 us per iteration whatever the size, the
         // cluster kernels pass that near 50k slots (8000 vertices of a 3-D grid; profiles/r01_notes.md).  With a hub
@@ -2108,7 +2040,8 @@ struct QuadSolver : SolverBase {
         cudaStream_t st = ctx().stream;
         if (small_mode()) { if (!run_push()) run_small(); return; }
         // batch: enough trips per host round trip to hide it, small enough to bound the no-op tail
-        const size_t work = (size_t) g.nslots + (size_t) q.V + (size_t) std::abs((double) q.N) * q.V;
+        ctx().stats.layout = dia ? 1 : 0; ctx().stats.gpus = 1;
+        const size_t work = (size_t) nhalf + (size_t) q.V + (size_t) std::abs((double) q.N) * q.V;
         int batch = work > (1u << 24) ? 4 : (work > (1u << 20) ? 16 : 64);
         batch = std::max(1, std::min(batch, q.itMax + 1));
         ctx().in_loop = true;

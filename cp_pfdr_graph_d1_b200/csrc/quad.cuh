@@ -1,0 +1,123 @@
+// quad.cuh - kernel parameter block and device helpers shared by the layouts of the quadratic family
+// (quad.cu: half-edge table and the single-launch cluster kernels; quad_dia.cu: constant-offset graphs).
+#pragma once
+#include "common.cuh"
+
+namespace pfdr {
+
+template <typename real> using pair_t = typename Pair<real>::type;
+
+template <typename real>
+struct QP {                       // kernel parameter block
+    Ctl *ctl;
+    int V, N, E;
+    int Vown, sharded;            // vertices this rank owns (== V unless sharded: ghosts follow)
+    int world, rank;              // sharded: sums holds one pair per rank, sums[2*rank..] is ours
+    double *sums;                 // [2*world] evolution sums of every rank (sharded path), gathered with the halo exchange
+    double *amp_sums;             // [2] amplitude sums (all-reduced)
+    double *rsum;                 // [N] sum of A x over this rank's columns (sharded dense A)
+    const long long *slice_off; const int *nbr, *twin, *hkey;
+    const int4 *pk;               // per slot {nbr, twin, w, [threshold]} in 16 bytes: one vector load per row in the iteration kernel
+    const int2 *pk2;              // per slot {nbr, twin}: float32 before a reconditioning (16 bytes would carry an unused word)
+    real *w;                      // [slots] raw d1 weight of the half-edge's edge
+    real *thc;                    // [slots] La_d1/w after a reconditioning (NULL: thc0 for all)
+    real thc0;
+    real *Z0, *Z1;                // [slots] edge copies, ping/pong by iteration parity
+    real *X0, *X1;                // [V] iterate, ping/pong by iteration parity
+    real *P0, *P1;                // [V] forward point 2x - Ga.grad(x), ping/pong (the only vertex value a
+                                  //     neighbour gathers, hence stored apart from x)
+    real *T, *Sinv, *Ga, *Ga0, *G, *Thl1, *R, *AtY;
+    const real *Y, *A, *La_d1, *La_l1, *L;
+    const int *Eu, *Ev;
+    int Ltype, positivity, prox_kind, has_lo, has_hi;
+    real lo, hi, rho, condMin;
+    double *partial;
+    real *dObj, *dDif;
+    int nparts;                   // CTAs of ax_partial
+    // constant-offset layout (dia.cuh; dia_nd > 0): Z0/Z1 are 2.ND planes of V edge copies; Wrow (row weight w/S) and,
+    // after a reconditioning, thc (La_d1/w) hold 2.ND planes of V in the order the half-edges are summed
+    int dia_nd, dia_off[3];
+    int vbeg, vend;               // vertices processed by the iteration kernel: [vbeg, vend)
+    const unsigned char *dmask;   // [V]
+    const int *eoff;              // [V]
+    real *Wrow;                   // [2.ND * V]
+};
+
+constexpr int HUB_ROWS = 32;      // rows of a SELL slice walked by one thread per vertex; past that the warp shares a hub's row
+
+template <typename real> __device__ __forceinline__ real rabs(real a) { return a < (real) 0 ? -a : a; }
+
+// gradient of the smooth part at vertex v (x = X[v]); dense cases read what the A-kernels left in G
+template <typename real>
+__device__ __forceinline__ real grad_at(const QP<real> &p, int v, real x)
+{
+    if (p.N == 0) return (p.A ? p.A[v] * x : x) - p.Y[v];
+    if (p.N < 0) return p.G[v] - p.Y[v];
+    return p.G[v];
+}
+
+// Sum NV doubles over the whole grid, deterministically: per-CTA partials, the last CTA to finish
+// adds them in a fixed order.  Returns true (in every thread) only in that last CTA, v valid in thread 0.
+template <int NV>
+__device__ bool grid_sum(Ctl *ctl, double *partial, double (&v)[NV], double *smem)
+{
+    __shared__ int s_last;
+    block_sum<NV>(v, smem);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; i++) partial[(size_t) blockIdx.x * NV + i] = v[i];
+        __threadfence();
+        const unsigned t = atomicAdd(&ctl->ticket, 1u);
+        s_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return false;
+    __threadfence();
+    double acc[NV];
+#pragma unroll
+    for (int i = 0; i < NV; i++) acc[i] = 0.0;
+    const volatile double *vp = partial;
+    for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
+#pragma unroll
+        for (int i = 0; i < NV; i++) acc[i] += vp[(size_t) b * NV + i];
+    }
+    block_sum<NV>(acc, smem);
+#pragma unroll
+    for (int i = 0; i < NV; i++) v[i] = acc[i];
+    if (threadIdx.x == 0) ctl->ticket = 0;
+    return true;
+}
+
+
+template <typename real>
+__device__ __forceinline__ real clamp_metric(const QP<real> &p, int v, real ga)
+{   // ref :222-239
+    const real bound = (real) 1.9 * ((real) 2 - p.rho);
+    if (p.Ltype == PFDR_B200_SCAL || p.L == nullptr) {
+        const real b = p.L ? bound / p.L[0] : bound;
+        if (ga > b) ga = b;
+    } else if (p.L[v] > (real) 0) {
+        const real b = bound / p.L[v];
+        if (ga > b) ga = b;
+    }
+    return ga;
+}
+
+// end of an iteration: evolution measure, iteration counter, stop / recondition decision (ref :429, :448, :515-529)
+template <typename real>
+__device__ void quad_finalize(const QP<real> &p, int it, double d, double c)
+{
+    Ctl *ctl = p.ctl;
+    double dif = ctl->dif;
+    if (ctl->track) {
+        dif = (c > ctl->eps) ? d / c : d / ctl->eps;
+        ctl->dif = dif;
+        if (p.dDif) p.dDif[it] = (real) dif;
+    }
+    const int itn = it + 1;
+    ctl->it = itn;
+    if (itn == ctl->itMax || (real) dif < (real) ctl->tol) ctl->state = ST_FINAL;
+    else if ((real) dif < (real) ctl->rcd) ctl->state = ST_RECOND;
+}
+
+}  // namespace pfdr

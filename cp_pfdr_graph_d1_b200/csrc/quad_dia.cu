@@ -1,0 +1,234 @@
+// quad_dia.cu - the quadratic-family kernels on constant-offset graphs (dia.cuh).  Same arithmetic in the same order as
+// the half-edge-table kernels of quad.cu (bit-identical results); one thread per vertex, every address computed from
+// the vertex number: the 2.ND half-edges of a vertex need 5 independent unit-stride loads each (own copy, twin copy,
+// neighbour's forward point and T, row weight), all issued before the first use - no index stream (24 B per edge
+// less HBM traffic than the table) and no dependent index -> gather chain.
+// ref src/PFDR_graph_quadratic_d1_l1.cpp:463-529 (iteration), :57-268 (preconditioning).
+#include "dia.cuh"
+#include "quad_dia.cuh"
+
+namespace pfdr {
+
+namespace {
+
+template <int ND>
+__device__ __forceinline__ int dia_edge_id(const int *__restrict__ eoff, const unsigned char *__restrict__ dmask,
+                                           int v, unsigned m, int h, const int (&off)[3])
+{
+    typedef DiaHalf<ND> H;
+    const int i = H::idx(h);
+    if (H::out(h)) return eoff[v] + __popc(m & ((1u << i) - 1u));
+    const int nb = v - off[i];
+    return eoff[nb] + __popc((unsigned) dmask[nb] & ((1u << i) - 1u));
+}
+
+// first preconditioning + initial state (as init_vertex_kernel of quad.cu): w = c La_d1 (:160-166), S, Ga, T, Th_l1, z_e = x
+template <typename real, int ND>
+__global__ void __launch_bounds__(256) quad_dia_init_kernel(QP<real> p, const real *__restrict__ X0)
+{
+    typedef DiaHalf<ND> H;
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= p.V) return;
+    const size_t Vp = (size_t) p.V;
+    const real c = (real) p.ctl->amp;
+    const real x = X0[v];
+    const unsigned m = p.dmask[v];
+    const int off[3] = {p.dia_off[0], p.dia_off[1], p.dia_off[2]};
+    real S = 0, wv[2 * ND];
+#pragma unroll
+    for (int h = 0; h < 2 * ND; h++) {
+        wv[h] = 0;
+        if ((m >> H::mask_bit(h)) & 1u) {
+            wv[h] = c * p.La_d1[dia_edge_id<ND>(p.eoff, p.dmask, v, m, h, off)];
+            S += wv[h];
+            p.Z0[(size_t) H::own_plane(h) * Vp + v] = x;
+        }
+    }
+    real ga = p.Ga0[v] + S;
+    if (p.La_l1) ga += c * p.La_l1[v];
+    ga = clamp_metric(p, v, (real) 1 / ga);
+    const real sinv = (real) 1 / S;
+    p.Ga[v] = ga; p.Sinv[v] = sinv; p.T[v] = ga * S;
+#pragma unroll
+    for (int h = 0; h < 2 * ND; h++) p.Wrow[(size_t) h * Vp + v] = wv[h] * sinv;
+    if (p.La_l1) p.Thl1[v] = ga * p.La_l1[v];
+    p.X0[v] = x;
+    p.P0[v] = (p.N == 0) ? (real) 2 * x - ga * grad_at(p, v, x) : (real) 0;
+}
+
+// reconditioning (as recond_vertex of quad.cu, ref :89-99, :167-250)
+template <typename real, int ND>
+__global__ void __launch_bounds__(256) quad_dia_recond_kernel(QP<real> p)
+{
+    typedef DiaHalf<ND> H;
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= p.V) return;
+    const size_t Vp = (size_t) p.V;
+    const int cur = p.ctl->it & 1;
+    const real *X = cur ? p.X1 : p.X0;
+    real *Z = cur ? p.Z1 : p.Z0, *Pout = cur ? p.P1 : p.P0;
+    real c = (real) p.ctl->amp;
+    const real x = X[v], g = grad_at(p, v, x);
+    const real ga_old = p.Ga[v];
+    const unsigned m = p.dmask[v];
+    const int off[3] = {p.dia_off[0], p.dia_off[1], p.dia_off[2]};
+    real S = 0, wv[2 * ND];
+#pragma unroll
+    for (int h = 0; h < 2 * ND; h++) {
+        wv[h] = 0;
+        if (!((m >> H::mask_bit(h)) & 1u)) continue;
+        const int n = H::out(h) ? v + off[H::idx(h)] : v - off[H::idx(h)];
+        const size_t zk = (size_t) H::own_plane(h) * Vp + v, hk = (size_t) h * Vp + v;
+        const real Wold = p.Wrow[hk];
+        Z[zk] = (Wold / ga_old) * (x - ga_old * g - Z[zk]);                   // ref :96-97
+        const real xn = X[n];
+        real a = rabs(x), b = rabs(xn), d = rabs(x - xn);                       // ref :172-186
+        if (a < b) a = b;
+        if (a < c) a = c;
+        a *= p.condMin;
+        if (d < a) d = a;
+        wv[h] = p.La_d1[dia_edge_id<ND>(p.eoff, p.dmask, v, m, h, off)] / d;
+        p.thc[hk] = d; S += wv[h];
+    }
+    real ga = p.Ga0[v] + S;
+    if (p.La_l1) {                                                             // ref :209-218
+        c *= p.condMin;
+        real d = rabs(x);
+        if (d < c) d = c;
+        ga += p.La_l1[v] / d;
+    }
+    ga = clamp_metric(p, v, (real) 1 / ga);
+    const real sinv = (real) 1 / S;
+    p.Ga[v] = ga; p.Sinv[v] = sinv; p.T[v] = ga * S;
+    if (p.La_l1) p.Thl1[v] = ga * p.La_l1[v];
+#pragma unroll
+    for (int h = 0; h < 2 * ND; h++) {
+        const real W = wv[h] * sinv;
+        p.Wrow[(size_t) h * Vp + v] = W;
+        if ((m >> H::mask_bit(h)) & 1u) {
+            const size_t zk = (size_t) H::own_plane(h) * Vp + v;
+            Z[zk] = x - ga * (g + Z[zk] / W);                                  // ref :247-248
+        }
+    }
+    Pout[v] = (real) 2 * x - ga * g;
+}
+
+// fused iteration: S6-S10 of SURVEY 3.3 + the next forward point when A is diagonal
+template <typename real, bool PER_SLOT_TH, int ND, int MINB>
+__global__ void __launch_bounds__(256, MINB) quad_dia_iter_kernel(QP<real> p)
+{
+    typedef DiaHalf<ND> H;
+    __shared__ double smem[64];
+    Ctl *ctl = p.ctl;
+    const CtlView cv = load_ctl(ctl);
+    if (cv.hold != 0 || cv.state != ST_RUN) {
+        if (cv.hold == 0 && blockIdx.x == 0 && threadIdx.x == 0) ctl->hold = 1;
+        return;
+    }
+    const int it = cv.it, cur = it & 1;
+    const real *__restrict__ Zin = cur ? p.Z1 : p.Z0;
+    real *__restrict__ Zout = cur ? p.Z0 : p.Z1;
+    const real *__restrict__ Pc = cur ? p.P1 : p.P0;
+    const real *__restrict__ Tg = p.T;
+    const real *__restrict__ Wrow = p.Wrow;
+    const real rho = p.rho;
+    const int v = p.vbeg + blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t Vp = (size_t) p.V;
+    real red[2] = {(real) 0, (real) 0};
+    if (v < p.vend) {
+        const unsigned m = __ldg(p.dmask + v);
+        const real xo = (cur ? p.X1 : p.X0)[v], po_v = Pc[v], Tv = Tg[v];
+        const int off[3] = {p.dia_off[0], p.dia_off[1], p.dia_off[2]};
+        real zo[2 * ND], zt[2 * ND], pn[2 * ND], Tn[2 * ND], wr[2 * ND], thc[2 * ND];
+#pragma unroll
+        for (int h = 0; h < 2 * ND; h++) {
+            zo[h] = 0; zt[h] = 0; pn[h] = 0; Tn[h] = 1; wr[h] = 0; thc[h] = p.thc0;
+            if ((m >> H::mask_bit(h)) & 1u) {
+                const int n = H::out(h) ? v + off[H::idx(h)] : v - off[H::idx(h)];
+                zo[h] = Zin[(size_t) H::own_plane(h) * Vp + v];
+                zt[h] = Zin[(size_t) H::twin_plane(h) * Vp + n];
+                pn[h] = Pc[n]; Tn[h] = Tg[n];
+                wr[h] = __ldg(Wrow + ((size_t) h * Vp + v));
+                if (PER_SLOT_TH) thc[h] = __ldg(p.thc + ((size_t) h * Vp + v));
+            }
+        }
+        real acc = 0;
+#pragma unroll
+        for (int h = 0; h < 2 * ND; h++) {
+            if ((m >> H::mask_bit(h)) & 1u) {
+                const real tsum = Tv + Tn[h], inv = fast_rcp(tsum);
+                const real th = thc[h] * tsum;                                // Th_d1
+                const real wo = Tn[h] * inv, wt = Tv * inv;                   // W_d1 own / twin side
+                const real po = po_v - zo[h], pt = pn[h] - zt[h], d0 = po - pt;
+                const real b = d0 - min(max(d0, -th), th);                    // soft threshold (ref :477-488), exact 0 inside
+                const real zn = zo[h] + rho * (fma(wo, d0, pt) + wt * b - xo);
+                Zout[(size_t) H::own_plane(h) * Vp + v] = zn;
+                acc += wr[h] * zn;
+            }
+        }
+        real x = acc;
+        if (p.prox_kind == 0) {                                                // ref l1.cpp :500-512
+            if (p.La_l1) {
+                const real th = p.Thl1[v];
+                if (x > th) x -= th;
+                else if (!p.positivity && x < -th) x += th;
+                else x = 0;
+            } else if (p.positivity) { if (x < (real) 0) x = 0; }
+        } else {                                                               // ref bounds.cpp :473-490
+            if (p.has_lo && x < p.lo) x = p.lo;
+            else if (p.has_hi && x > p.hi) x = p.hi;
+        }
+        (cur ? p.X0 : p.X1)[v] = x;
+        if (p.N == 0) (cur ? p.P0 : p.P1)[v] = (real) 2 * x - p.Ga[v] * grad_at(p, v, x);
+        const real dx = xo - x;
+        red[0] = dx * dx; red[1] = x * x;
+    }
+    double tot[2];
+    if (grid_sum_fast<2, real>(ctl, p.partial, red, tot, smem) && threadIdx.x == 0) {
+        if (p.sharded) { p.sums[2 * p.rank] = tot[0]; p.sums[2 * p.rank + 1] = tot[1]; }
+        else quad_finalize(p, it, tot[0], tot[1]);
+    }
+}
+
+}  // namespace
+
+#define PFDR_ND_SWITCH(CALL)                       \
+    do {                                           \
+        if (p.dia_nd == 1) { CALL(1); }            \
+        else if (p.dia_nd == 2) { CALL(2); }       \
+        else { CALL(3); }                          \
+    } while (0)
+
+template <typename real>
+void quad_dia_launch_init(const QP<real> &p, const real *X0, int grid)
+{
+#define CALL(N_) PFDR_LAUNCH((quad_dia_init_kernel<real, N_>), grid, 256, 0, p, X0)
+    PFDR_ND_SWITCH(CALL);
+#undef CALL
+}
+template <typename real>
+void quad_dia_launch_recond(const QP<real> &p, int grid)
+{
+#define CALL(N_) PFDR_LAUNCH((quad_dia_recond_kernel<real, N_>), grid, 256, 0, p)
+    PFDR_ND_SWITCH(CALL);
+#undef CALL
+}
+template <typename real>
+void quad_dia_launch_iter(const QP<real> &p, int grid)
+{
+    constexpr int MINB = sizeof(real) == 4 ? 4 : 2;      // float64, 3 offsets: 80+ registers (no spill at 2 CTAs per SM)
+#define CALL(N_)                                                                                         \
+    if (p.thc) PFDR_LAUNCH((quad_dia_iter_kernel<real, true, N_, MINB>), grid, 256, 0, p);               \
+    else PFDR_LAUNCH((quad_dia_iter_kernel<real, false, N_, MINB>), grid, 256, 0, p)
+    PFDR_ND_SWITCH(CALL);
+#undef CALL
+}
+
+template void quad_dia_launch_init<float>(const QP<float> &, const float *, int);
+template void quad_dia_launch_init<double>(const QP<double> &, const double *, int);
+template void quad_dia_launch_recond<float>(const QP<float> &, int);
+template void quad_dia_launch_recond<double>(const QP<double> &, int);
+template void quad_dia_launch_iter<float>(const QP<float> &, int);
+template void quad_dia_launch_iter<double>(const QP<double> &, int);
+
+}  // namespace pfdr

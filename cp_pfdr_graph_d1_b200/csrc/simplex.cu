@@ -434,7 +434,7 @@ struct SimplexSolver : SolverBase {
         if (dia) {
             nhalf = 2LL * dg.ND * V;
             Wrow.alloc((size_t) nhalf); Wrow.zero();
-            ctx().stats.slots = 2LL * E;
+            ctx().stats.slots = 2LL * E; ctx().stats.layout = 1;
         } else {
             build_sell(g, Eu, Ev, V, E, C);
             nhalf = g.nslots;
@@ -624,6 +624,7 @@ struct SimplexSolver : SolverBase {
         const size_t work = (size_t) nhalf * p.K;
         int batch = work > (1u << 24) ? 4 : (work > (1u << 20) ? 16 : 64);
         batch = std::max(1, std::min(batch, q.itMax + 1));
+        ctx().stats.layout = dia ? 1 : 0; ctx().stats.gpus = 1;
         ctx().in_loop = true;
         PFDR_CUDA(cudaEventRecord(ev_b, st));
         long long enqueued = 0, budget = (long long) q.itMax + 1 + 2LL * batch;

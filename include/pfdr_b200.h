@@ -163,7 +163,9 @@ typedef struct {
     long long loop_launches;    /* ... of which inside the iteration loop                         */
     int iterations;        /* == *it                                                              */
     long long h2d_bytes, d2h_bytes;  /* host<->device bytes moved by the call                     */
-    long long slots;       /* padded half-edge slots of the SELL layout (>= 2E)                   */
+    long long slots;       /* padded half-edge slots of the SELL layout (>= 2E); 2E on the stencil layout */
+    int layout;            /* 0: half-edge table (graph.cuh); 1: constant-offset / stencil layout (dia.cuh) */
+    int gpus;              /* devices the solve ran on                                            */
 } pfdr_b200_stats;
 int pfdr_b200_get_last_stats(pfdr_b200_stats *out);
 

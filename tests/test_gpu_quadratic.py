@@ -13,14 +13,17 @@ def rel(a, b):
     return float(np.linalg.norm(a.astype(np.float64) - b) / max(float(np.linalg.norm(b)), 1e-300))
 
 
-@pytest.mark.parametrize("mode", ["large", "small", "small_c1", "small_c16"])
+@pytest.mark.parametrize("mode", ["large", "table", "small", "small_c1", "small_c16"])
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 @pytest.mark.parametrize("name", problems.QUAD_CASES)
 def test_quadratic_parity(gpu_api, oracle, monkeypatch, name, dtype, mode):
     """mode "small": problems that fit run as ONE launch of the single-CTA persistent kernel (the path the
-    cut-pursuit reduced problems take); mode "large": always the one-kernel-per-iteration path"""
+    cut-pursuit reduced problems take); mode "large": always the one-kernel-per-iteration path (grid cases on the
+    stencil layout); mode "table": the same on the half-edge table whatever the graph"""
     from cp_pfdr_graph_d1_b200.api import _b
-    monkeypatch.setenv("PFDR_B200_SMALL", "0" if mode == "large" else "1")
+    monkeypatch.setenv("PFDR_B200_SMALL", "0" if mode in ("large", "table") else "1")
+    if mode == "table":
+        monkeypatch.setenv("PFDR_B200_DIA", "0")
     if "_c" in mode:
         monkeypatch.setenv("PFDR_B200_SMALL_C", mode.split("_c")[1])      # CTAs of the cluster (default: by size)
     got = problems.run_quad(_b(), name, dtype)
@@ -41,6 +44,66 @@ def test_quadratic_parity(gpu_api, oracle, monkeypatch, name, dtype, mode):
         # compare the evolution record above the rounding floor of the type (it is a squared relative change)
         sel = ref.Dif[:n] > (1e-9 if dtype is np.float32 else 1e-24)
         assert np.allclose(got.Dif[:n][sel], ref.Dif[:n][sel], rtol=5e-2 if dtype is np.float32 else 1e-4)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("name", [n for n in problems.QUAD_CASES if n.startswith(("grid", "dense"))])
+def test_stencil_layout_matches_table(gpu_api, monkeypatch, name, dtype):
+    """grid problems on the one-kernel-per-iteration path use the constant-offset layout; the half-edge table
+    (PFDR_B200_DIA=0) must give the same bits: same arithmetic, same summation order"""
+    from cp_pfdr_graph_d1_b200.api import _b
+    monkeypatch.setenv("PFDR_B200_SMALL", "0")
+    got = problems.run_quad(_b(), name, dtype)
+    assert gpu_api.last_stats()["layout"] == 1
+    monkeypatch.setenv("PFDR_B200_DIA", "0")
+    tab = problems.run_quad(_b(), name, dtype)
+    assert gpu_api.last_stats()["layout"] == 0
+    assert got.it == tab.it and np.array_equal(got.X, tab.X)
+    if got.Obj is not None:
+        assert np.array_equal(got.Obj, tab.Obj)
+    if got.Dif is not None:
+        assert np.array_equal(got.Dif, tab.Dif)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("kind", ["chain", "image", "image8"])
+@pytest.mark.parametrize("recond", [0.0, 1e-3])
+def test_stencil_layout_chain_and_image(gpu_api, oracle, monkeypatch, kind, dtype, recond):
+    """1-D chains (one offset), 2-D images (two offsets) and 8-connected images (four offsets: more than the stencil
+    layout holds, so the table is used) against the oracle, l1 + positivity"""
+    from cp_pfdr_graph_d1_b200.api import _b
+    monkeypatch.setenv("PFDR_B200_SMALL", "0")
+    rng = np.random.default_rng(len(kind))
+    if kind == "chain":
+        V = 3001
+        Eu = np.arange(V - 1, dtype=np.int32); Ev = Eu + 1
+    else:
+        nx, ny = 61, 47
+        V = nx * ny
+        v = np.arange(V).reshape(ny, nx)
+        offs = [(1, (slice(None), slice(None, -1))), (nx, (slice(None, -1), slice(None)))]
+        if kind == "image8":
+            offs = [(1, (slice(None), slice(None, -1))), (nx - 1, (slice(None, -1), slice(1, None))),
+                    (nx, (slice(None, -1), slice(None))), (nx + 1, (slice(None, -1), slice(None, -1)))]
+        eu = np.stack([v] * len(offs), -1); ev = np.stack([v + d for d, _ in offs], -1)
+        ok = np.zeros(eu.shape, bool)
+        for i, (_, sl) in enumerate(offs):
+            ok[sl + (i,)] = True
+        Eu, Ev = eu[ok].astype(np.int32), ev[ok].astype(np.int32)
+    A = rng.uniform(0.5, 1.5, V).astype(dtype)
+    Y = (A * (np.round(3 * np.arange(V) / V) + rng.normal(0, 0.3, V))).astype(dtype)
+    La_d1 = rng.uniform(0.05, 0.5, Eu.shape[0]).astype(dtype)
+    args = (Y, A, Eu, Ev, La_d1, np.full(V, 0.02, dtype), 1, 1, A)
+    kw = dict(N=0, rho=1.5, condMin=1e-3, difRcd=recond, difTol=1e-6, itMax=400, want_obj=True, want_dif=True)
+    got = _b().PFDR_graph_quadratic_d1_l1(np.zeros(V, dtype), *args, **kw)
+    assert gpu_api.last_stats()["layout"] == (0 if kind == "image8" else 1)
+    ref = oracle.PFDR_graph_quadratic_d1_l1(np.zeros(V, dtype), *args, **kw)
+    tol = TOL[dtype]
+    slack = 0 if dtype is np.float64 else max(2, ref.it // 10)
+    assert abs(got.it - ref.it) <= slack, (got.it, ref.it)
+    assert rel(got.X, ref.X) < tol, rel(got.X, ref.X)
+    n = min(got.it, ref.it)
+    assert np.allclose(got.Obj[:n + 1], ref.Obj[:n + 1], rtol=tol, atol=tol * abs(ref.Obj[0]) * 1e-2)
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])

@@ -53,9 +53,89 @@ def test_simplex_parity_scalar_lanes(gpu_api, oracle, monkeypatch, name, dtype):
     assert np.allclose(got.Obj[:n + 1], ref.Obj[:n + 1], rtol=tol, atol=tol * max(float(np.abs(ref.Obj).max()), 1.0) * 1e-1)
 
 
-@pytest.mark.parametrize("knobs", [{"PFDR_B200_TILE": "32"}, {"PFDR_B200_TILE": "8", "PFDR_B200_IDX32": "0"},
+def chain_or_image_case(kind, K, dtype):
+    """1-D chain (one offset) / 2-D image (two offsets) label problems: the other shapes of the stencil layout"""
+    rng = np.random.default_rng(K + len(kind))
+    if kind == "chain":
+        V = 501
+        Eu = np.arange(V - 1, dtype=np.int32); Ev = Eu + 1
+    else:
+        nx, ny = 23, 17
+        V = nx * ny
+        v = np.arange(V).reshape(ny, nx)
+        eu = np.stack([v, v], -1); ev = np.stack([v + 1, v + nx], -1)
+        ok = np.zeros(eu.shape, bool); ok[:, :-1, 0] = True; ok[:-1, :, 1] = True
+        Eu, Ev = eu[ok].astype(np.int32), ev[ok].astype(np.int32)
+    Q = rng.uniform(0, 1, (V, K))
+    Q[np.arange(V), (np.arange(V) * 3 // V) % K] += 1.5
+    Q = (Q / Q.sum(axis=1, keepdims=True)).astype(dtype)
+    La_d1 = rng.uniform(0.05, 0.3, Eu.shape[0]).astype(dtype)
+    return Q, Eu, Ev, La_d1
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("name", ["kla", "kla_weighted", "kla_recond", "kla_labels", "kla_k16", "kla_k3", "kla_k12", "kla_k64",
+                                  "kla_recond_k16", "lin_k16", "lin_recond_k16", "quad_k16", "quad_recond_k16",
+                                  "quad_weighted_k16", "kla_k33", "kla_recond_k33", "quad_weighted_k50", "kla_notrack"])
+def test_stencil_layout_matches_table(gpu_api, monkeypatch, name, dtype):
+    """grid problems run on the constant-offset layout (no index stream); the half-edge table (PFDR_B200_DIA=0) must
+    give the same bits: same arithmetic, same summation order"""
+    from cp_pfdr_graph_d1_b200.api import _b
+    got = problems.run_simplex(_b(), name, dtype)
+    K = got.X.shape[1]
+    expect_stencil = not (dtype is np.float64 and K > 64)
+    assert gpu_api.last_stats()["layout"] == (1 if expect_stencil else 0)
+    monkeypatch.setenv("PFDR_B200_DIA", "0")
+    if dtype is np.float64:
+        monkeypatch.setenv("PFDR_B200_LPT", "2")           # same lane layout as the stencil kernels -> same reduction trees
+    tab = problems.run_simplex(_b(), name, dtype)
+    assert gpu_api.last_stats()["layout"] == 0
+    assert got.it == tab.it
+    assert np.array_equal(got.X, tab.X)
+    assert np.array_equal(got.Obj, tab.Obj)
+    if got.Dif is not None:
+        assert np.array_equal(got.Dif, tab.Dif)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("K", [4, 7, 16])
+@pytest.mark.parametrize("kind", ["chain", "image"])
+@pytest.mark.parametrize("recond", [0.0, 1e-2])
+def test_stencil_layout_chain_and_image(gpu_api, oracle, kind, K, dtype, recond):
+    from cp_pfdr_graph_d1_b200.api import _b
+    Q, Eu, Ev, La_d1 = chain_or_image_case(kind, K, dtype)
+    kw = dict(rho=1.5, condMin=1e-2, difRcd=recond, difTol=1e-5, itMax=200, want_obj=True, want_dif=True)
+    got = _b().PFDR_graph_loss_d1_simplex(Q.copy(), Q, 0.05, Eu, Ev, La_d1, **kw)
+    assert gpu_api.last_stats()["layout"] == 1
+    ref = oracle.PFDR_graph_loss_d1_simplex(Q.copy(), Q, 0.05, Eu, Ev, La_d1, **kw)
+    tol = TOL[dtype]
+    assert abs(got.it - ref.it) <= (0 if dtype is np.float64 else max(2, ref.it // 20)), (got.it, ref.it)
+    assert rel(got.X, ref.X) < tol, rel(got.X, ref.X)
+    n = min(got.it, ref.it)
+    assert np.allclose(got.Obj[:n + 1], ref.Obj[:n + 1], rtol=tol, atol=tol * max(float(np.abs(ref.Obj).max()), 1.0) * 1e-1)
+
+
+def test_stencil_layout_not_used_for_other_numberings(gpu_api):
+    """a grid whose edge list is shuffled (or holds u > v) keeps the half-edge table: the per-vertex summation order
+    of the reference depends on the edge numbering"""
+    from cp_pfdr_graph_d1_b200.api import _b
+    args, kw = problems.simplex_case("kla_k16", np.float32)
+    P0, Q, al, Eu, Ev, La_d1 = args
+    ref = _b().PFDR_graph_loss_d1_simplex(P0.copy(), Q, al, Eu, Ev, La_d1, **kw)
+    assert gpu_api.last_stats()["layout"] == 1
+    perm = np.random.default_rng(0).permutation(Eu.shape[0])
+    got = _b().PFDR_graph_loss_d1_simplex(P0.copy(), Q, al, Eu[perm], Ev[perm], La_d1[perm], **kw)
+    assert gpu_api.last_stats()["layout"] == 0
+    assert abs(got.it - ref.it) <= 2 and rel(got.X, ref.X) < 1e-4
+    got = _b().PFDR_graph_loss_d1_simplex(P0.copy(), Q, al, Ev, Eu, La_d1, **kw)
+    assert gpu_api.last_stats()["layout"] == 0
+    assert abs(got.it - ref.it) <= 2 and rel(got.X, ref.X) < 1e-4
+
+
+@pytest.mark.parametrize("knobs", [{"PFDR_B200_TILE": "32"}, {"PFDR_B200_TILE": "32", "PFDR_B200_DIA": "0"},
+                                   {"PFDR_B200_TILE": "8", "PFDR_B200_IDX32": "0", "PFDR_B200_DIA": "0"}, {"PFDR_B200_TILE": "8"},
                                    {"PFDR_B200_LPT": "4"}, {"PFDR_B200_LPT": "4", "PFDR_B200_TILE": "16"},
-                                   {"PFDR_B200_IDX32": "0"}, {"PFDR_B200_LPT": "2", "PFDR_B200_TILE": "24"}],
+                                   {"PFDR_B200_IDX32": "0", "PFDR_B200_DIA": "0"}, {"PFDR_B200_LPT": "2", "PFDR_B200_TILE": "24"}],
                          ids=lambda k: "+".join(f"{a[10:]}={b}" for a, b in k.items()))
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 @pytest.mark.parametrize("name", ["kla_k16", "kla_recond_k16", "kla_labels_k16", "quad_weighted_k16", "lin_k16", "kla_k33", "kla"])
