@@ -87,17 +87,17 @@ __global__ void __launch_bounds__(256) init_vertex_kernel(QP<real> p, const real
         const long long s = base + (long long) j * 32 + lane;
         const int h = p.hkey[s];
         if (h >= 0) {
-            const real wv = c * p.La_d1[h >> 1];
-            p.w[s] = wv; S += wv; p.Z0[s] = x;
+            const real wv = mul_rn(c, p.La_d1[h >> 1]);
+            p.w[s] = wv; S = add_rn(S, wv); p.Z0[s] = x;
         }
     }
-    real ga = p.Ga0[v] + S;
-    if (p.La_l1) ga += c * p.La_l1[v];
+    real ga = add_rn(p.Ga0[v], S);
+    if (p.La_l1) ga = fma_rn(c, p.La_l1[v], ga);
     ga = clamp_metric(p, v, (real) 1 / ga);
-    p.Ga[v] = ga; p.Sinv[v] = (real) 1 / S; p.T[v] = ga * S;
-    if (p.La_l1) p.Thl1[v] = ga * p.La_l1[v];
+    p.Ga[v] = ga; p.Sinv[v] = (real) 1 / S; p.T[v] = mul_rn(ga, S);
+    if (p.La_l1) p.Thl1[v] = mul_rn(ga, p.La_l1[v]);
     p.X0[v] = x;
-    p.P0[v] = (p.N == 0) ? (real) 2 * x - ga * grad_at(p, v, x) : (real) 0;
+    p.P0[v] = (p.N == 0) ? forward_point_of(x, ga, grad_at(p, v, x)) : (real) 0;
 }
 
 // reconditioning, everything that is local to a vertex row in one kernel (ref :89-99, :167-250):
@@ -115,8 +115,8 @@ __device__ __forceinline__ void recond_vertex(const QP<real> &p, int v, const re
         const long long s = base + (long long) j * 32 + lane;
         const int n = p.nbr[s];
         if (n >= 0) {
-            const real Wold = p.w[s] * sinv_old;
-            Z[s] = (Wold / ga_old) * (x - ga_old * g - Z[s]);                 // ref :96-97
+            const real Wold = mul_rn(p.w[s], sinv_old);
+            Z[s] = mul_rn(Wold / ga_old, add_rn(fma_rn(-ga_old, g, x), -Z[s]));   // ref :96-97
             const real xn = X[n];
             real a = rabs(x), b = rabs(xn), d = rabs(x - xn);                   // ref :172-186
             if (a < b) a = b;
@@ -124,10 +124,10 @@ __device__ __forceinline__ void recond_vertex(const QP<real> &p, int v, const re
             a *= p.condMin;
             if (d < a) d = a;
             const real wv = p.La_d1[p.hkey[s] >> 1] / d;
-            p.w[s] = wv; p.thc[s] = d; S += wv;
+            p.w[s] = wv; p.thc[s] = d; S = add_rn(S, wv);
         }
     }
-    real ga = p.Ga0[v] + S;
+    real ga = add_rn(p.Ga0[v], S);
     if (p.La_l1) {                                                             // ref :209-218
         c *= p.condMin;
         real d = rabs(x);
@@ -136,13 +136,13 @@ __device__ __forceinline__ void recond_vertex(const QP<real> &p, int v, const re
     }
     ga = clamp_metric(p, v, (real) 1 / ga);
     const real sinv = (real) 1 / S;
-    p.Ga[v] = ga; p.Sinv[v] = sinv; p.T[v] = ga * S;
-    if (p.La_l1) p.Thl1[v] = ga * p.La_l1[v];
+    p.Ga[v] = ga; p.Sinv[v] = sinv; p.T[v] = mul_rn(ga, S);
+    if (p.La_l1) p.Thl1[v] = mul_rn(ga, p.La_l1[v]);
     for (int j = 0; j < width; j++) {
         const long long s = base + (long long) j * 32 + lane;
-        if (p.nbr[s] >= 0) Z[s] = x - ga * (g + Z[s] / (p.w[s] * sinv));        // ref :247-248
+        if (p.nbr[s] >= 0) Z[s] = fma_rn(-ga, add_rn(g, Z[s] / mul_rn(p.w[s], sinv)), x);   // ref :247-248
     }
-    Pout[v] = (real) 2 * x - ga * g;
+    Pout[v] = forward_point_of(x, ga, g);
 }
 
 template <typename real>
@@ -171,103 +171,6 @@ __global__ void quad_finalize_kernel(QP<real> p)
     double d = 0.0, c = 0.0;
     for (int r = 0; r < p.world; r++) { d += p.sums[2 * r]; c += p.sums[2 * r + 1]; }     // rank order: same bits everywhere
     quad_finalize(p, p.ctl->it, d, c);
-}
-
-// U half-edge rows of the vertex are in flight at once: first every index / weight / own-copy load of the
-// chunk is issued, then every gather (neighbour forward point, neighbour T, twin copy), then the arithmetic.
-// (v0 of this kernel kept 2 rows in flight and sat at 27 warps stalled on the scoreboard per issue.)
-template <typename real, bool PER_SLOT_TH, int U>
-__global__ void __launch_bounds__(256) quad_iter_kernel(QP<real> p)
-{
-    __shared__ double smem[64];
-    Ctl *ctl = p.ctl;
-    const CtlView cv = load_ctl(ctl);
-    if (cv.hold != 0 || cv.state != ST_RUN) {
-        if (cv.hold == 0 && blockIdx.x == 0 && threadIdx.x == 0) ctl->hold = 1;
-        return;
-    }
-    const int it = cv.it;
-    const int cur = it & 1;
-    const real *__restrict__ Zin = cur ? p.Z1 : p.Z0;
-    real *__restrict__ Zout = cur ? p.Z0 : p.Z1;
-    const real *__restrict__ Xc = cur ? p.X1 : p.X0;
-    const real *__restrict__ Pc = cur ? p.P1 : p.P0;
-    real *__restrict__ Xn = cur ? p.X0 : p.X1;
-    real *__restrict__ Pn = cur ? p.P0 : p.P1;
-    const real *__restrict__ Tg = p.T;
-    const int *__restrict__ nbr = p.nbr;
-    const int *__restrict__ twin = p.twin;
-    const real *__restrict__ wg = p.w;
-    const real rho = p.rho;
-
-    const int v = blockIdx.x * blockDim.x + threadIdx.x;
-    double red[2] = {0.0, 0.0};
-    if (v < p.Vown) {
-        const int lane = v & 31;
-        const long long base = p.slice_off[v >> 5];
-        const int width = (int) ((p.slice_off[(v >> 5) + 1] - base) >> 5);
-        const int s0 = (int) base + lane;
-        const real xo = Xc[v], po_v = Pc[v];
-        const real Tv = Tg[v], Sv = p.Sinv[v];
-        real acc = 0;
-        for (int j0 = 0; j0 < width; j0 += U) {
-            int n[U], tw[U];
-            real wv[U], zo[U], pn[U], Tn[U], zt[U], thc[U];
-#pragma unroll
-            for (int u = 0; u < U; u++) {
-                const bool in = j0 + u < width;
-                const int s = s0 + (j0 + u) * 32;
-                n[u] = in ? nbr[s] : -1;
-                tw[u] = in ? twin[s] : 0;
-                wv[u] = in ? wg[s] : (real) 0;
-                zo[u] = in ? Zin[s] : (real) 0;
-                thc[u] = PER_SLOT_TH ? (in ? p.thc[s] : (real) 0) : p.thc0;
-            }
-#pragma unroll
-            for (int u = 0; u < U; u++) {
-                const bool ok = n[u] >= 0;
-                pn[u] = ok ? Pc[n[u]] : (real) 0;
-                Tn[u] = ok ? Tg[n[u]] : (real) 1;
-                zt[u] = ok ? Zin[tw[u]] : (real) 0;
-            }
-#pragma unroll
-            for (int u = 0; u < U; u++) {
-                if (n[u] >= 0) {
-                    const real tsum = Tv + Tn[u];
-                    const real th = thc[u] * tsum;                                // Th_d1
-                    const real inv = fast_rcp(tsum);
-                    const real wo = Tn[u] * inv, wt = Tv * inv;                   // W_d1 own / twin side
-                    const real po = po_v - zo[u], pt = pn[u] - zt[u];
-                    const real a = wo * po + wt * pt;
-                    real b = po - pt;
-                    b = (b > th) ? b - th : ((b < -th) ? b + th : (real) 0);      // soft threshold (ref :477-488)
-                    const real zn = zo[u] + rho * (a + wt * b - xo);
-                    Zout[s0 + (j0 + u) * 32] = zn;
-                    acc += (wv[u] * Sv) * zn;
-                }
-            }
-        }
-        real x = acc;
-        if (p.prox_kind == 0) {                                                // ref l1.cpp :500-512
-            if (p.La_l1) {
-                const real th = p.Thl1[v];
-                if (x > th) x -= th;
-                else if (!p.positivity && x < -th) x += th;
-                else x = 0;
-            } else if (p.positivity) { if (x < (real) 0) x = 0; }
-        } else {                                                               // ref bounds.cpp :473-490
-            if (p.has_lo && x < p.lo) x = p.lo;
-            else if (p.has_hi && x > p.hi) x = p.hi;
-        }
-        Xn[v] = x;
-        if (p.N == 0) Pn[v] = (real) 2 * x - p.Ga[v] * grad_at(p, v, x);
-        const real dx = xo - x;
-        red[0] = (double) (dx * dx); red[1] = (double) (x * x);
-    }
-    if (grid_sum<2>(ctl, p.partial, red, smem) && threadIdx.x == 0) {
-        if (p.sharded) { p.sums[2 * p.rank] = red[0]; p.sums[2 * p.rank + 1] = red[1]; }
-        else quad_finalize(p, it, red[0], red[1]);
-    }
 }
 
 // The iteration-invariant per-slot data side by side, 16 bytes per slot: float32 {nbr, twin, w, La_d1/w}, float64
@@ -360,15 +263,9 @@ __global__ void __launch_bounds__(256, MINB) quad_iter_pipe_kernel(QP<real> p)
                 zo_n = Zin[s + 32];
             }
             if (live) {
-                const real tsum = Tv + Tn, inv = fast_rcp(tsum);
-                const real th = th_c * tsum;                                  // Th_d1
-                const real wo = Tn * inv, wt = Tv * inv;                      // W_d1 own / twin side
-                const real po = po_v - zo_c, pt = pn - zt, d0 = po - pt;
-                const real b = d0 - min(max(d0, -th), th);                    // soft threshold (ref :477-488), exact 0 inside
-                // W_d1u.pu + W_d1v.pv = pt + wo.(po - pt): the two weights sum to one
-                const real zn = zo_c + rho * (fma(wo, d0, pt) + wt * b - xo);
+                const real zn = d1_prox_half<real>(rho, xo, po_v, Tv, zo_c, zt, pn, Tn, th_c);
                 Zout[s] = zn;
-                acc += (w_c * Sv) * zn;
+                acc = fma_rn(mul_rn(w_c, Sv), zn, acc);
             }
             n_c = n_n; tw_c = tw_n; w_c = w_n; zo_c = zo_n; th_c = th_n;
         }
@@ -408,14 +305,9 @@ __global__ void __launch_bounds__(256, MINB) quad_iter_pipe_kernel(QP<real> p)
 #pragma unroll
                 for (int u = 0; u < HU; u++) {
                     if (n[u] >= 0) {
-                        const real tsum = Tv_c + Tn[u], inv = fast_rcp(tsum);
-                        const real th = thc[u] * tsum;
-                        const real wo = Tn[u] * inv, wt = Tv_c * inv;
-                        const real po = po_c - zo[u], pt = pn[u] - zt[u], d0 = po - pt;
-                        const real b = d0 - min(max(d0, -th), th);
-                        const real zn = zo[u] + rho * (fma(wo, d0, pt) + wt * b - xo_c);
+                        const real zn = d1_prox_half<real>(rho, xo_c, po_c, Tv_c, zo[u], zt[u], pn[u], Tn[u], thc[u]);
                         Zout[sk[u]] = zn;
-                        part += (ww[u] * Sv_c) * zn;
+                        part = fma_rn(mul_rn(ww[u], Sv_c), zn, part);
                     }
                 }
             }
@@ -437,7 +329,7 @@ __global__ void __launch_bounds__(256, MINB) quad_iter_pipe_kernel(QP<real> p)
             else if (p.has_hi && x > p.hi) x = p.hi;
         }
         (cur ? p.X0 : p.X1)[v] = x;
-        if (p.N == 0) (cur ? p.P0 : p.P1)[v] = (real) 2 * x - p.Ga[v] * grad_at(p, v, x);
+        if (p.N == 0) (cur ? p.P0 : p.P1)[v] = forward_point_diag(p, v, x);
         const real dx = xo - x;
         red[0] = dx * dx; red[1] = x * x;
     }
@@ -1213,131 +1105,6 @@ __global__ void __launch_bounds__(512, 1) quad_push_kernel(QP<real> p, PushArgs<
     if (rank == 0 && tid == 0) { ctl->it = it; ctl->dif = dif; ctl->state = ST_FINAL; ctl->hold = 1; }
 }
 
-// Row-parallel variant: one thread per half-edge slot.  A CTA owns G slices (32 vertices each); warp (g, r)
-// walks rows r, r+W, ... of slice g, so every load is a single coalesced row and a vertex's W rows are in
-// flight in W different warps (thread-level instead of instruction-level parallelism, ~32 registers).
-// The per-vertex sum is taken from shared memory in row order by the slice's first warp, i.e. still in
-// the reference's edge order and with no atomics.
-template <typename real, bool PER_SLOT_TH, int W, int G>
-__global__ void __launch_bounds__(32 * W * G) quad_rows_kernel(QP<real> p, int nslices)
-{
-    __shared__ real contrib[G][W][32];
-    __shared__ int s_width[G];
-    __shared__ double s_red[2][G];
-    Ctl *ctl = p.ctl;
-    const CtlView cv = load_ctl(ctl);
-    if (cv.hold != 0 || cv.state != ST_RUN) {
-        if (cv.hold == 0 && blockIdx.x == 0 && threadIdx.x == 0) ctl->hold = 1;
-        return;
-    }
-    const int it = cv.it, cur = it & 1;
-    const real *__restrict__ Zin = cur ? p.Z1 : p.Z0;
-    real *__restrict__ Zout = cur ? p.Z0 : p.Z1;
-    const real *__restrict__ Xc = cur ? p.X1 : p.X0;
-    const real *__restrict__ Pc = cur ? p.P1 : p.P0;
-    const real *__restrict__ Tg = p.T;
-    const real rho = p.rho;
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int g = warp / W, r = warp - g * W;
-    const int slice = blockIdx.x * G + g;
-    const bool live = slice < nslices;
-    const int v = slice * 32 + lane;
-    const bool vlive = live && v < p.Vown;
-    long long base = 0;
-    int width = 0;
-    if (live) { base = p.slice_off[slice]; width = (int) ((p.slice_off[slice + 1] - base) >> 5); }
-    if (r == 0 && lane == 0) s_width[g] = width;
-    real xo = 0, po_v = 0, Tv = 1, Sv = 0;
-    if (vlive) { xo = Xc[v]; po_v = Pc[v]; Tv = Tg[v]; Sv = p.Sinv[v]; }
-    __syncthreads();
-    int wmax = 0;
-#pragma unroll
-    for (int i = 0; i < G; i++) wmax = max(wmax, s_width[i]);
-    const int s0 = (int) base + lane;
-    real run = 0;
-    for (int j0 = 0; j0 < wmax; j0 += W) {
-        const int j = j0 + r;
-        real c = 0;
-        if (vlive && j < width) {
-            const int s = s0 + j * 32;
-            const int n = p.nbr[s];
-            if (n >= 0) {
-                const int tw = p.twin[s];
-                const real wv = p.w[s], zo = Zin[s];
-                const real thc = PER_SLOT_TH ? p.thc[s] : p.thc0;
-                const real pn = Pc[n], Tn = Tg[n], zt = Zin[tw];
-                const real tsum = Tv + Tn;
-                const real th = thc * tsum;
-                const real inv = fast_rcp(tsum);
-                const real wo = Tn * inv, wt = Tv * inv;
-                const real po = po_v - zo, pt = pn - zt;
-                const real a = wo * po + wt * pt;
-                real b = po - pt;
-                b = (b > th) ? b - th : ((b < -th) ? b + th : (real) 0);
-                const real zn = zo + rho * (a + wt * b - xo);
-                Zout[s] = zn;
-                c = (wv * Sv) * zn;
-            }
-        }
-        contrib[g][r][lane] = c;
-        __syncthreads();
-        if (r == 0) {
-#pragma unroll
-            for (int k = 0; k < W; k++) run += contrib[g][k][lane];
-        }
-        if (j0 + W < wmax) __syncthreads();
-    }
-    real d0 = 0, d1 = 0;
-    if (r == 0) {
-        if (vlive) {
-            real x = run;
-            if (p.prox_kind == 0) {                                            // ref l1.cpp :500-512
-                if (p.La_l1) {
-                    const real th = p.Thl1[v];
-                    if (x > th) x -= th;
-                    else if (!p.positivity && x < -th) x += th;
-                    else x = 0;
-                } else if (p.positivity) { if (x < (real) 0) x = 0; }
-            } else {                                                           // ref bounds.cpp :473-490
-                if (p.has_lo && x < p.lo) x = p.lo;
-                else if (p.has_hi && x > p.hi) x = p.hi;
-            }
-            (cur ? p.X0 : p.X1)[v] = x;
-            if (p.N == 0) (cur ? p.P0 : p.P1)[v] = (real) 2 * x - p.Ga[v] * grad_at(p, v, x);
-            const real dx = xo - x;
-            d0 = dx * dx; d1 = x * x;
-        }
-        // evolution sums (ref :515-529): 32 values in `real` inside the warp, double from there on
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { d0 += __shfl_xor_sync(0xffffffffu, d0, o); d1 += __shfl_xor_sync(0xffffffffu, d1, o); }
-        if (lane == 0) { s_red[0][g] = (double) d0; s_red[1][g] = (double) d1; }
-    }
-    __syncthreads();
-    __shared__ int s_last;
-    if (threadIdx.x == 0) {
-        double a = 0, b = 0;
-#pragma unroll
-        for (int i = 0; i < G; i++) { a += s_red[0][i]; b += s_red[1][i]; }
-        p.partial[2 * (size_t) blockIdx.x] = a; p.partial[2 * (size_t) blockIdx.x + 1] = b;
-        __threadfence();
-        s_last = (atomicAdd(&ctl->ticket, 1u) == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    double acc[2] = {0.0, 0.0};
-    const volatile double *vp = p.partial;
-    for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) { acc[0] += vp[2 * (size_t) b]; acc[1] += vp[2 * (size_t) b + 1]; }
-    __shared__ double smem[64];
-    block_sum<2>(acc, smem);
-    if (threadIdx.x == 0) {
-        ctl->ticket = 0;
-        if (p.sharded) { p.sums[2 * p.rank] = acc[0]; p.sums[2 * p.rank + 1] = acc[1]; }
-        else quad_finalize(p, it, acc[0], acc[1]);
-    }
-}
-
 template <typename real>
 __global__ void extract_x_kernel(QP<real> p, real *__restrict__ out)
 {
@@ -1786,58 +1553,22 @@ struct QuadSolver : SolverBase {
         }
     }
 
-    // default: one thread per vertex, rows software-pipelined (quad_iter_pipe_kernel).  For comparison
-    // (profiles/r01_notes.md): PFDR_B200_PIPE=0 -> chunked kernel (PFDR_B200_U rows in flight, default 8 / 4),
-    // PFDR_B200_KERNEL=rows -> row-parallel kernel.
+    // one thread per vertex, rows software-pipelined (quad_iter_pipe_kernel), 8 (float32) / 6 (float64) CTAs per SM
     int rowsW = 0;
     void launch_iter()
     {
         if (dia) { quad_dia_launch_iter<real>(p, ogrid); return; }
-        static int U = -1, mode = -1;
-        if (U < 0) { const char *e = getenv("PFDR_B200_U"); U = e ? atoi(e) : 0; }
-        if (mode < 0) { const char *e = getenv("PFDR_B200_KERNEL"); mode = (e && !strcmp(e, "rows")) ? 0 : 1; }
-        // default: pipelined kernel at 8 (f32) / 6 (f64) CTAs per SM; PFDR_B200_PIPE=0 selects the chunked kernel
-        static int pipe = -1;
-        if (pipe < 0) { const char *e = getenv("PFDR_B200_PIPE"); pipe = e ? atoi(e) : (sizeof(real) == 4 ? 8 : 6); }
-        if (mode == 1 && pipe > 0) {
-#define PFDR_PIPE(MB, HB)                                                                                       \
-            do {                                                                                                \
-                if (p.pk && !(HB)) {                                                                            \
-                    if (p.thc) PFDR_LAUNCH((quad_iter_pipe_kernel<real, true, MB, false, 2>), ogrid, 256, 0, p);     \
-                    else PFDR_LAUNCH((quad_iter_pipe_kernel<real, false, MB, false, 2>), ogrid, 256, 0, p);          \
-                } else if (p.pk2 && !p.thc && !(HB)) {                                                          \
-                    PFDR_LAUNCH((quad_iter_pipe_kernel<real, false, MB, false, 1>), ogrid, 256, 0, p);               \
-                } else if (p.thc) PFDR_LAUNCH((quad_iter_pipe_kernel<real, true, MB, HB>), ogrid, 256, 0, p);   \
-                else PFDR_LAUNCH((quad_iter_pipe_kernel<real, false, MB, HB>), ogrid, 256, 0, p);               \
-            } while (0)
-            // a slice wider than HUB_ROWS (a hub vertex): variant whose warps share the hub's rows (PFDR_B200_HUB=0: off)
-            const char *he = getenv("PFDR_B200_HUB");
-            const bool hub_env = !(he && he[0] == '0');
-            if (hub_env && g.max_width > HUB_ROWS) PFDR_PIPE(2, true);
-            else if (pipe >= 8) PFDR_PIPE(8, false); else if (pipe >= 6) PFDR_PIPE(6, false); else PFDR_PIPE(4, false);
-#undef PFDR_PIPE
-            return;
-        }
-        if (mode == 1) {
-            const int u = U > 0 ? U : (sizeof(real) == 4 ? 8 : 4);
-#define PFDR_ITER(UU)                                                                          \
-            do {                                                                               \
-                if (p.thc) PFDR_LAUNCH((quad_iter_kernel<real, true, UU>), ogrid, 256, 0, p);  \
-                else PFDR_LAUNCH((quad_iter_kernel<real, false, UU>), ogrid, 256, 0, p);       \
-            } while (0)
-            if (u <= 2) PFDR_ITER(2); else if (u <= 4) PFDR_ITER(4); else if (u <= 6) PFDR_ITER(6); else PFDR_ITER(8);
-#undef PFDR_ITER
-            return;
-        }
-        const int ns = g.nslices;
-#define PFDR_ROWS(WW, GG)                                                                                      \
-        do {                                                                                                   \
-            if (p.thc) PFDR_LAUNCH((quad_rows_kernel<real, true, WW, GG>), cdiv(ns, GG), 32 * WW * GG, 0, p, ns); \
-            else PFDR_LAUNCH((quad_rows_kernel<real, false, WW, GG>), cdiv(ns, GG), 32 * WW * GG, 0, p, ns);   \
-        } while (0)
-        if (rowsW <= 2) PFDR_ROWS(2, 4); else if (rowsW <= 4) PFDR_ROWS(4, 2); else if (rowsW <= 6) PFDR_ROWS(6, 2);
-        else PFDR_ROWS(8, 1);
-#undef PFDR_ROWS
+        constexpr int MB = sizeof(real) == 4 ? 8 : 6;
+        // a slice wider than HUB_ROWS (a hub vertex): variant whose warps share the hub's rows
+        if (g.max_width > HUB_ROWS) {
+            if (p.thc) PFDR_LAUNCH((quad_iter_pipe_kernel<real, true, 2, true>), ogrid, 256, 0, p);
+            else PFDR_LAUNCH((quad_iter_pipe_kernel<real, false, 2, true>), ogrid, 256, 0, p);
+        } else if (p.pk) {
+            if (p.thc) PFDR_LAUNCH((quad_iter_pipe_kernel<real, true, MB, false, 2>), ogrid, 256, 0, p);
+            else PFDR_LAUNCH((quad_iter_pipe_kernel<real, false, MB, false, 2>), ogrid, 256, 0, p);
+        } else if (p.pk2 && !p.thc) PFDR_LAUNCH((quad_iter_pipe_kernel<real, false, MB, false, 1>), ogrid, 256, 0, p);
+        else if (p.thc) PFDR_LAUNCH((quad_iter_pipe_kernel<real, true, MB, false>), ogrid, 256, 0, p);
+        else PFDR_LAUNCH((quad_iter_pipe_kernel<real, false, MB, false>), ogrid, 256, 0, p);
     }
 
     int launches_per_trip() const { return (q.N > 0 ? 3 : (q.N < 0 ? 1 : 0)) + (q.Obj ? 1 : 0) + 1 + (sharded ? (q.N > 0 ? 9 : 4) : 0); }

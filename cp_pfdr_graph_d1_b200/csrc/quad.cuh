@@ -43,6 +43,29 @@ struct QP {                       // kernel parameter block
     real *Wrow;                   // [2.ND * V]
 };
 
+// explicitly rounded operations: the d1 prox below is shared by the kernels of both layouts and must give the same bits
+// in each of them, whatever contraction (a*b+c -> fma) the compiler would choose in the surrounding code
+__device__ __forceinline__ float fma_rn(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+__device__ __forceinline__ double fma_rn(double a, double b, double c) { return __fma_rn(a, b, c); }
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+
+// d1 prox + relaxation of one half-edge (ref src/PFDR_graph_quadratic_d1_l1.cpp:467-489): new copy of the vertex that
+// owns it.  xo, po_v, Tv: iterate, forward point and T of that vertex; zo / zt: its copy / the twin copy; pn, Tn: forward
+// point and T of the neighbour; thc: La_d1 / w.  W_d1u.pu + W_d1v.pv = pt + wo.(po - pt) since the two weights sum to one.
+template <typename real>
+__device__ __forceinline__ real d1_prox_half(real rho, real xo, real po_v, real Tv, real zo, real zt, real pn, real Tn, real thc)
+{
+    const real tsum = add_rn(Tv, Tn), inv = fast_rcp(tsum);
+    const real th = mul_rn(thc, tsum);                                    // Th_d1
+    const real wo = mul_rn(Tn, inv), wt = mul_rn(Tv, inv);                // W_d1 own / twin side
+    const real po = add_rn(po_v, -zo), pt = add_rn(pn, -zt), d0 = add_rn(po, -pt);
+    const real b = add_rn(d0, -min(max(d0, -th), th));                    // soft threshold (ref :477-488), exact 0 inside
+    return fma_rn(rho, add_rn(fma_rn(wt, b, fma_rn(wo, d0, pt)), -xo), zo);
+}
+
 constexpr int HUB_ROWS = 32;      // rows of a SELL slice walked by one thread per vertex; past that the warp shares a hub's row
 
 template <typename real> __device__ __forceinline__ real rabs(real a) { return a < (real) 0 ? -a : a; }
@@ -51,9 +74,18 @@ template <typename real> __device__ __forceinline__ real rabs(real a) { return a
 template <typename real>
 __device__ __forceinline__ real grad_at(const QP<real> &p, int v, real x)
 {
-    if (p.N == 0) return (p.A ? p.A[v] * x : x) - p.Y[v];
+    if (p.N == 0) return p.A ? fma_rn(p.A[v], x, -p.Y[v]) : add_rn(x, -p.Y[v]);
     if (p.N < 0) return p.G[v] - p.Y[v];
     return p.G[v];
+}
+
+// forward point 2x - Ga.grad f(x) for diagonal / identity A (S1 + S4 + S6 of the next trip, ref :377-385, :441-445, :463-464)
+template <typename real>
+__device__ __forceinline__ real forward_point_of(real x, real ga, real g) { return fma_rn(-ga, g, mul_rn((real) 2, x)); }
+template <typename real>
+__device__ __forceinline__ real forward_point_diag(const QP<real> &p, int v, real x)
+{
+    return forward_point_of(x, p.Ga[v], grad_at(p, v, x));
 }
 
 // Sum NV doubles over the whole grid, deterministically: per-CTA partials, the last CTA to finish

@@ -39,21 +39,21 @@ __global__ void __launch_bounds__(256) quad_dia_init_kernel(QP<real> p, const re
     for (int h = 0; h < 2 * ND; h++) {
         wv[h] = 0;
         if ((m >> H::mask_bit(h)) & 1u) {
-            wv[h] = c * p.La_d1[dia_edge_id<ND>(p.eoff, p.dmask, v, m, h, off)];
-            S += wv[h];
+            wv[h] = mul_rn(c, p.La_d1[dia_edge_id<ND>(p.eoff, p.dmask, v, m, h, off)]);
+            S = add_rn(S, wv[h]);
             p.Z0[(size_t) H::own_plane(h) * Vp + v] = x;
         }
     }
-    real ga = p.Ga0[v] + S;
-    if (p.La_l1) ga += c * p.La_l1[v];
+    real ga = add_rn(p.Ga0[v], S);
+    if (p.La_l1) ga = fma_rn(c, p.La_l1[v], ga);
     ga = clamp_metric(p, v, (real) 1 / ga);
     const real sinv = (real) 1 / S;
-    p.Ga[v] = ga; p.Sinv[v] = sinv; p.T[v] = ga * S;
+    p.Ga[v] = ga; p.Sinv[v] = sinv; p.T[v] = mul_rn(ga, S);
 #pragma unroll
-    for (int h = 0; h < 2 * ND; h++) p.Wrow[(size_t) h * Vp + v] = wv[h] * sinv;
-    if (p.La_l1) p.Thl1[v] = ga * p.La_l1[v];
+    for (int h = 0; h < 2 * ND; h++) p.Wrow[(size_t) h * Vp + v] = mul_rn(wv[h], sinv);
+    if (p.La_l1) p.Thl1[v] = mul_rn(ga, p.La_l1[v]);
     p.X0[v] = x;
-    p.P0[v] = (p.N == 0) ? (real) 2 * x - ga * grad_at(p, v, x) : (real) 0;
+    p.P0[v] = (p.N == 0) ? forward_point_of(x, ga, grad_at(p, v, x)) : (real) 0;
 }
 
 // reconditioning (as recond_vertex of quad.cu, ref :89-99, :167-250)
@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(256) quad_dia_recond_kernel(QP<real> p)
         const int n = H::out(h) ? v + off[H::idx(h)] : v - off[H::idx(h)];
         const size_t zk = (size_t) H::own_plane(h) * Vp + v, hk = (size_t) h * Vp + v;
         const real Wold = p.Wrow[hk];
-        Z[zk] = (Wold / ga_old) * (x - ga_old * g - Z[zk]);                   // ref :96-97
+        Z[zk] = mul_rn(Wold / ga_old, add_rn(fma_rn(-ga_old, g, x), -Z[zk]));  // ref :96-97
         const real xn = X[n];
         real a = rabs(x), b = rabs(xn), d = rabs(x - xn);                       // ref :172-186
         if (a < b) a = b;
@@ -88,9 +88,9 @@ __global__ void __launch_bounds__(256) quad_dia_recond_kernel(QP<real> p)
         a *= p.condMin;
         if (d < a) d = a;
         wv[h] = p.La_d1[dia_edge_id<ND>(p.eoff, p.dmask, v, m, h, off)] / d;
-        p.thc[hk] = d; S += wv[h];
+        p.thc[hk] = d; S = add_rn(S, wv[h]);
     }
-    real ga = p.Ga0[v] + S;
+    real ga = add_rn(p.Ga0[v], S);
     if (p.La_l1) {                                                             // ref :209-218
         c *= p.condMin;
         real d = rabs(x);
@@ -99,22 +99,25 @@ __global__ void __launch_bounds__(256) quad_dia_recond_kernel(QP<real> p)
     }
     ga = clamp_metric(p, v, (real) 1 / ga);
     const real sinv = (real) 1 / S;
-    p.Ga[v] = ga; p.Sinv[v] = sinv; p.T[v] = ga * S;
-    if (p.La_l1) p.Thl1[v] = ga * p.La_l1[v];
+    p.Ga[v] = ga; p.Sinv[v] = sinv; p.T[v] = mul_rn(ga, S);
+    if (p.La_l1) p.Thl1[v] = mul_rn(ga, p.La_l1[v]);
 #pragma unroll
     for (int h = 0; h < 2 * ND; h++) {
-        const real W = wv[h] * sinv;
+        const real W = mul_rn(wv[h], sinv);
         p.Wrow[(size_t) h * Vp + v] = W;
         if ((m >> H::mask_bit(h)) & 1u) {
             const size_t zk = (size_t) H::own_plane(h) * Vp + v;
-            Z[zk] = x - ga * (g + Z[zk] / W);                                  // ref :247-248
+            Z[zk] = fma_rn(-ga, add_rn(g, Z[zk] / W), x);                      // ref :247-248
         }
     }
-    Pout[v] = (real) 2 * x - ga * g;
+    Pout[v] = forward_point_of(x, ga, g);
 }
 
-// fused iteration: S6-S10 of SURVEY 3.3 + the next forward point when A is diagonal
-template <typename real, bool PER_SLOT_TH, int ND, int MINB>
+// fused iteration: S6-S10 of SURVEY 3.3 + the next forward point when A is diagonal.
+// Persistent warps (one wave of resident CTAs): a warp walks chunks of 32 consecutive vertices, no block-level
+// synchronisation inside the loop; loads never depend on the edge mask (neighbour index clamped into [0, V), a
+// half-edge that does not exist is dropped at compute time); G half-edges (5 loads each) are requested at a time.
+template <typename real, bool PER_SLOT_TH, int ND, int G, int MINB>
 __global__ void __launch_bounds__(256, MINB) quad_dia_iter_kernel(QP<real> p)
 {
     typedef DiaHalf<ND> H;
@@ -128,42 +131,45 @@ __global__ void __launch_bounds__(256, MINB) quad_dia_iter_kernel(QP<real> p)
     const int it = cv.it, cur = it & 1;
     const real *__restrict__ Zin = cur ? p.Z1 : p.Z0;
     real *__restrict__ Zout = cur ? p.Z0 : p.Z1;
+    const real *__restrict__ Xc = cur ? p.X1 : p.X0;
+    real *__restrict__ Xn = cur ? p.X0 : p.X1;
     const real *__restrict__ Pc = cur ? p.P1 : p.P0;
+    real *__restrict__ Pn = cur ? p.P0 : p.P1;
     const real *__restrict__ Tg = p.T;
     const real *__restrict__ Wrow = p.Wrow;
-    const real rho = p.rho;
-    const int v = p.vbeg + blockIdx.x * blockDim.x + threadIdx.x;
+    const real rho = p.rho, thc0 = p.thc0;
     const size_t Vp = (size_t) p.V;
-    real red[2] = {(real) 0, (real) 0};
-    if (v < p.vend) {
+    const int Vm1 = p.V - 1;
+    const int off[3] = {p.dia_off[0], p.dia_off[1], p.dia_off[2]};
+    const int stride = (int) (gridDim.x * blockDim.x);              // a warp takes 32 consecutive vertices per trip
+    double red0 = 0.0, red1 = 0.0;
+    for (int v = p.vbeg + (int) (blockIdx.x * blockDim.x + threadIdx.x); v < p.vend; v += stride) {
         const unsigned m = __ldg(p.dmask + v);
-        const real xo = (cur ? p.X1 : p.X0)[v], po_v = Pc[v], Tv = Tg[v];
-        const int off[3] = {p.dia_off[0], p.dia_off[1], p.dia_off[2]};
-        real zo[2 * ND], zt[2 * ND], pn[2 * ND], Tn[2 * ND], wr[2 * ND], thc[2 * ND];
-#pragma unroll
-        for (int h = 0; h < 2 * ND; h++) {
-            zo[h] = 0; zt[h] = 0; pn[h] = 0; Tn[h] = 1; wr[h] = 0; thc[h] = p.thc0;
-            if ((m >> H::mask_bit(h)) & 1u) {
-                const int n = H::out(h) ? v + off[H::idx(h)] : v - off[H::idx(h)];
-                zo[h] = Zin[(size_t) H::own_plane(h) * Vp + v];
-                zt[h] = Zin[(size_t) H::twin_plane(h) * Vp + n];
-                pn[h] = Pc[n]; Tn[h] = Tg[n];
-                wr[h] = __ldg(Wrow + ((size_t) h * Vp + v));
-                if (PER_SLOT_TH) thc[h] = __ldg(p.thc + ((size_t) h * Vp + v));
-            }
-        }
+        const real xo = Xc[v], po_v = Pc[v], Tv = Tg[v];
         real acc = 0;
 #pragma unroll
-        for (int h = 0; h < 2 * ND; h++) {
-            if ((m >> H::mask_bit(h)) & 1u) {
-                const real tsum = Tv + Tn[h], inv = fast_rcp(tsum);
-                const real th = thc[h] * tsum;                                // Th_d1
-                const real wo = Tn[h] * inv, wt = Tv * inv;                   // W_d1 own / twin side
-                const real po = po_v - zo[h], pt = pn[h] - zt[h], d0 = po - pt;
-                const real b = d0 - min(max(d0, -th), th);                    // soft threshold (ref :477-488), exact 0 inside
-                const real zn = zo[h] + rho * (fma(wo, d0, pt) + wt * b - xo);
-                Zout[(size_t) H::own_plane(h) * Vp + v] = zn;
-                acc += wr[h] * zn;
+        for (int h0 = 0; h0 < 2 * ND; h0 += G) {
+            real zo[G], zt[G], pn[G], Tn[G], wr[G], thc[G];
+#pragma unroll
+            for (int u = 0; u < G; u++) {
+                const int h = h0 + u;
+                if (h < 2 * ND) {
+                    const int n = H::out(h) ? min(v + off[H::idx(h)], Vm1) : max(v - off[H::idx(h)], 0);
+                    zo[u] = Zin[(size_t) H::own_plane(h) * Vp + v];
+                    zt[u] = Zin[(size_t) H::twin_plane(h) * Vp + n];
+                    pn[u] = Pc[n]; Tn[u] = Tg[n];
+                    wr[u] = __ldg(Wrow + ((size_t) h * Vp + v));
+                    thc[u] = PER_SLOT_TH ? __ldg(p.thc + ((size_t) h * Vp + v)) : thc0;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < G; u++) {
+                const int h = h0 + u;
+                if (h < 2 * ND && ((m >> H::mask_bit(h)) & 1u)) {
+                    const real zn = d1_prox_half<real>(rho, xo, po_v, Tv, zo[u], zt[u], pn[u], Tn[u], thc[u]);
+                    Zout[(size_t) H::own_plane(h) * Vp + v] = zn;
+                    acc = fma_rn(wr[u], zn, acc);
+                }
             }
         }
         real x = acc;
@@ -178,13 +184,13 @@ __global__ void __launch_bounds__(256, MINB) quad_dia_iter_kernel(QP<real> p)
             if (p.has_lo && x < p.lo) x = p.lo;
             else if (p.has_hi && x > p.hi) x = p.hi;
         }
-        (cur ? p.X0 : p.X1)[v] = x;
-        if (p.N == 0) (cur ? p.P0 : p.P1)[v] = (real) 2 * x - p.Ga[v] * grad_at(p, v, x);
+        Xn[v] = x;
+        if (p.N == 0) Pn[v] = forward_point_diag(p, v, x);
         const real dx = xo - x;
-        red[0] = dx * dx; red[1] = x * x;
+        red0 += (double) (dx * dx); red1 += (double) (x * x);
     }
-    double tot[2];
-    if (grid_sum_fast<2, real>(ctl, p.partial, red, tot, smem) && threadIdx.x == 0) {
+    double tot[2] = {red0, red1};
+    if (grid_sum<2>(ctl, p.partial, tot, smem) && threadIdx.x == 0) {
         if (p.sharded) { p.sums[2 * p.rank] = tot[0]; p.sums[2 * p.rank + 1] = tot[1]; }
         else quad_finalize(p, it, tot[0], tot[1]);
     }
@@ -216,10 +222,12 @@ void quad_dia_launch_recond(const QP<real> &p, int grid)
 template <typename real>
 void quad_dia_launch_iter(const QP<real> &p, int grid)
 {
-    constexpr int MINB = sizeof(real) == 4 ? 4 : 2;      // float64, 3 offsets: 80+ registers (no spill at 2 CTAs per SM)
+    constexpr int MINB = sizeof(real) == 4 ? 4 : 3;
+    constexpr int G = sizeof(real) == 4 ? 6 : 3;         // half-edges requested at a time (5 loads each)
+    const int g = std::min(grid, num_sms() * MINB);      // one wave of resident CTAs
 #define CALL(N_)                                                                                         \
-    if (p.thc) PFDR_LAUNCH((quad_dia_iter_kernel<real, true, N_, MINB>), grid, 256, 0, p);               \
-    else PFDR_LAUNCH((quad_dia_iter_kernel<real, false, N_, MINB>), grid, 256, 0, p)
+    if (p.thc) PFDR_LAUNCH((quad_dia_iter_kernel<real, true, N_, G, MINB>), g, 256, 0, p);               \
+    else PFDR_LAUNCH((quad_dia_iter_kernel<real, false, N_, G, MINB>), g, 256, 0, p)
     PFDR_ND_SWITCH(CALL);
 #undef CALL
 }

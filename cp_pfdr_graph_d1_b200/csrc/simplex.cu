@@ -469,10 +469,12 @@ struct SimplexSolver : SolverBase {
             const long long tile_env = e ? atoll(e) : -1;
             p.order = nullptr;
             if (tile_env != 0 && band > 0 && ((double) band * bytes_per_vertex > 24e6 || tile_env > 0)) {
-                long long T = tile_env > 0 ? tile_env : (long long) (5e6 / bytes_per_vertex);
+                long long T = tile_env > 0 ? tile_env : (long long) (9.3e6 / bytes_per_vertex);   // C4 252^3 f32: 32 rows of a plane (profiles/r02_notes.md)
                 T = std::max<long long>(C, std::min<long long>(T, band));
                 T = (T / C) * C;
-                build_chunk_order((int) (((long long) Vown + C - 1) / C), C, band, (int) T, order);
+                const char *pe = getenv("PFDR_B200_PATCH");
+                const int nx = (dia && dg.ND == 3 && dg.off[0] == 1 && dg.off[2] % dg.off[1] == 0 && !(pe && pe[0] == '0')) ? dg.off[1] : 0;
+                build_chunk_order((int) (((long long) Vown + C - 1) / C), C, band, (int) T, order, nx);
                 p.order = order.p;
             }
         }

@@ -237,7 +237,8 @@ __device__ __forceinline__ VecN<real, LPT> prox_row(real rho, const VecN<real, L
 // ref :651 / proj_simplex_metric.cpp:40-81), next (P, FP) (:569-587) and this lane's share of the evolution (:654-691)
 template <typename real, int LPT, bool PERK, int LOSS>
 __device__ __forceinline__ double simplex_epilogue(const SP<real> &p, Ctl *ctl, bool on, int v, int k0, size_t vk,
-    VecN<real, LPT> acc, const VecN<real, LPT> &Tv, const VecN<real, LPT> &pold, real *__restrict__ Pn, real *__restrict__ Fn)
+    VecN<real, LPT> acc, const VecN<real, LPT> &Tv, const VecN<real, LPT> &pold, real *__restrict__ Pn, real *__restrict__ Fn,
+    const VecN<real, LPT> *gaq_pre = nullptr)       // GaQ of the lane's labels when the caller fetched it ahead of time
 {
     typedef VecN<real, LPT> vec;
     const int K = p.K, TPV = p.TPV;
@@ -271,7 +272,7 @@ __device__ __forceinline__ double simplex_epilogue(const SP<real> &p, Ctl *ctl, 
 #pragma unroll
     for (int i = 0; i < LPT; i++) pnew.v[i] = ((act >> i) & 1u) ? (xs.v[i] - la) * m.v[i] : (real) 0;
     if (on) {
-        const vec gaq = ldv<real, LPT>(p.GaQ + vk);
+        const vec gaq = gaq_pre ? *gaq_pre : ldv<real, LPT>(p.GaQ + vk);
         vec qv = splat<real, LPT>((real) 0), f;
         if (LOSS == LOSS_QUAD) qv = ldv<real, LPT>(p.Q + vk);
 #pragma unroll

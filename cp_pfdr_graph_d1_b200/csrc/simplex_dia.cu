@@ -131,6 +131,12 @@ __global__ void __launch_bounds__(256) simplex_dia_precond_kernel(SP<real> p, co
 // ---------------------------------------------------------------------------------------------
 // fused iteration (ref :569-691)
 // ---------------------------------------------------------------------------------------------
+// Persistent warps: the grid is one wave of resident CTAs and every warp walks its own sequence of chunks (C consecutive
+// vertices) with no block-level synchronisation inside the loop - the one-CTA-per-64-vertices form spent 18 % of its
+// issue slots' stall time at the CTA barriers of the control-block broadcast and of the final reduction (ncu, r01), and
+// a finished warp kept its registers idle until the slowest warp of its CTA was done.  Loads never depend on the edge
+// mask: the neighbour index is clamped into [0, V) and a half-edge that does not exist is dropped at compute time, so
+// the whole group of loads is issued as soon as the chunk number is known (which is fetched one chunk ahead).
 template <typename real, int LPT, bool PERK, int LOSS, int ND, int G, int MINB>
 __global__ void __launch_bounds__(256, MINB) simplex_dia_iter_kernel(SP<real> p)
 {
@@ -152,63 +158,78 @@ __global__ void __launch_bounds__(256, MINB) simplex_dia_iter_kernel(SP<real> p)
     real *__restrict__ Fn = cur ? p.F0 : p.F1;
     const real *__restrict__ Tg = p.T;
     const real *__restrict__ Wrow = p.Wrow;
+    const int *__restrict__ order = p.order;
     const int K = p.K, TPV = p.TPV, lane = threadIdx.x & 31;
-    const long long wslot = ((long long) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const long long nchunks = ((long long) (p.vend - p.vbeg) + p.C - 1) >> p.logC;
+    const int vl = lane >> p.logTPV, k0 = (lane & (TPV - 1)) * LPT;
+    const int nchunks = (int) (((long long) (p.vend - p.vbeg) + p.C - 1) >> p.logC);
+    const int nwarps = (int) gridDim.x * (int) (blockDim.x >> 5);        // both far below 2^31
+    const size_t VK = (size_t) p.V * K, Vp = (size_t) p.V;
+    const int Vm1 = p.V - 1;
     const real rho = p.rho;
-    real red[1] = {(real) 0};
-    if (wslot < nchunks) {                                                    // warp-uniform
-        const long long chunk = p.order ? (long long) p.order[wslot] : wslot;
-        const int vl = lane >> p.logTPV, k0 = (lane & (TPV - 1)) * LPT;
-        const int v = p.vbeg + (int) (chunk << p.logC) + vl;
+    const int off[3] = {p.dia_off[0], p.dia_off[1], p.dia_off[2]};
+    double red = 0.0;
+    int idx = (int) blockIdx.x * (int) (blockDim.x >> 5) + (int) (threadIdx.x >> 5);
+    int chunk_next = idx < nchunks ? (order ? __ldg(order + idx) : idx) : 0;
+    for (; idx < nchunks; idx += nwarps) {                                    // warp-uniform trip count
+        const int chunk = chunk_next;
+        if (idx + nwarps < nchunks) chunk_next = order ? __ldg(order + (idx + nwarps)) : idx + nwarps;
+        const int v = p.vbeg + (chunk << p.logC) + vl;
         const bool on = (v < p.vend) && (k0 < K);
         const int vs = on ? v : p.vbeg;
-        const size_t VK = (size_t) p.V * K, Vp = (size_t) p.V;
         const size_t vk = (size_t) vs * K + (on ? k0 : 0);
         const unsigned m = on ? (unsigned) __ldg(p.dmask + vs) : 0u;
         const vec pold = ldv<real, LPT>(Pc + vk), fown = ldv<real, LPT>(Fc + vk), Tv = ldv<real, LPT>(Tg + vk);
         vec Sv;
         if (PERK) Sv = ldv<real, LPT>(p.Sinvk + vk); else Sv = splat<real, LPT>((real) 1);   // row weights hold w/S already
-        const int off[3] = {p.dia_off[0], p.dia_off[1], p.dia_off[2]};
-        vec acc = splat<real, LPT>((real) 0);
+        vec acc = splat<real, LPT>((real) 0), gaq;
 #pragma unroll
         for (int h0 = 0; h0 < 2 * ND; h0 += G) {
             vec zo[G], zt[G], fn[G], tn[G], wvk[G], th[G];
             real wr[G];
-            bool ex[G];
 #pragma unroll
             for (int u = 0; u < G; u++) {
                 const int h = h0 + u;
-                ex[u] = h < 2 * ND && ((m >> H::mask_bit(h)) & 1u);
-                wr[u] = 0;
-                if (ex[u]) {
+                if (h < 2 * ND) {
                     const int i_off = H::idx(h);
-                    const int nb = H::out(h) ? v + off[i_off] : v - off[i_off];
-                    const size_t nk = (size_t) nb * K + k0, zk = (size_t) H::own_plane(h) * VK + vk;
+                    const int nb = H::out(h) ? min(vs + off[i_off], Vm1) : max(vs - off[i_off], 0);
+                    const size_t nk = (size_t) nb * K + (on ? k0 : 0), zk = (size_t) H::own_plane(h) * VK + vk;
                     zo[u] = ldv<real, LPT>(Zin + zk);
                     zt[u] = ldv<real, LPT>(Zin + ((size_t) H::twin_plane(h) * VK + nk));
                     fn[u] = ldv<real, LPT>(Fc + nk);
                     if (LOSS != LOSS_LIN) tn[u] = ldv<real, LPT>(Tg + nk);
                     if (PERK) { wvk[u] = ldv<real, LPT>(p.wk + zk); th[u] = ldv<real, LPT>(p.thk + zk); }
-                    else wr[u] = __ldg(Wrow + ((size_t) h * Vp + v));
+                    else wr[u] = __ldg(Wrow + ((size_t) h * Vp + vs));
                 }
             }
+            if (h0 + G >= 2 * ND) gaq = ldv<real, LPT>(p.GaQ + vk);           // for the epilogue, behind the last group's loads
 #pragma unroll
             for (int u = 0; u < G; u++) {
                 const int h = h0 + u;
-                if (ex[u]) {
+                if (h < 2 * ND && ((m >> H::mask_bit(h)) & 1u)) {
                     const vec zn = prox_row<real, LPT, PERK, LOSS>(rho, fown, pold, Tv, Sv, zo[u], zt[u], fn[u], tn[u], wvk[u], th[u], wr[u], acc);
                     stv<real, LPT>(Zout + ((size_t) H::own_plane(h) * VK + vk), zn);
                 }
             }
         }
-        red[0] = (real) simplex_epilogue<real, LPT, PERK, LOSS>(p, ctl, on, v, k0, vk, acc, Tv, pold, Pn, Fn);
+        red += simplex_epilogue<real, LPT, PERK, LOSS>(p, ctl, on, v, k0, vk, acc, Tv, pold, Pn, Fn, &gaq);
     }
-    double tot[1];
-    if (grid_sum_fast<1, real>(ctl, p.partial, red, tot, smem) && threadIdx.x == 0) {
+    double tot[1] = {red};
+    if (grid_sum_s<1>(ctl, p.partial, tot, smem) && threadIdx.x == 0) {
         if (p.sharded) p.sums[p.rank] = tot[0];
         else simplex_finalize(p, it, tot[0]);
     }
+}
+
+// CTAs of `kernel` that are resident at once on the current device (persistent grids are exactly one wave)
+template <typename Kernel>
+int resident_ctas(Kernel kernel, int threads, int expect_per_sm)
+{
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) != cudaSuccess || per_sm < 1) {
+        cudaGetLastError();
+        per_sm = expect_per_sm;
+    }
+    return num_sms() * per_sm;
 }
 
 template <typename real, int LPT, bool PERK, int LOSS, int ND>
@@ -216,9 +237,27 @@ void launch_iter_nd(const SP<real> &p, int grid)
 {
     // half-edges per group / resident CTAs per SM: 2 x 4 vector loads of 16 bytes in flight per lane at 3 CTAs per SM
     // (85 registers); 1-D chains take their two half-edges at once
-    constexpr int G = ND == 1 ? 2 : (ND == 2 ? 2 : 2);
-    constexpr int MINB = PERK ? 2 : 3;
-    PFDR_LAUNCH((simplex_dia_iter_kernel<real, LPT, PERK, LOSS, ND, G, MINB>), grid, 256, 0, p);
+    // float32: 2 half-edges (8 vector loads of 16 bytes per lane) in flight at 3 CTAs per SM; float64 (4 labels = 32 bytes
+    // per lane and vector): one half-edge at a time at 2 CTAs per SM
+    constexpr int G = sizeof(real) == 4 ? 2 : 1;
+    constexpr int MINB = (PERK || sizeof(real) == 8) ? 2 : 3;
+    // one wave of resident CTAs (persistent warps); small problems: one warp per chunk
+    const int wave = resident_ctas(simplex_dia_iter_kernel<real, LPT, PERK, LOSS, ND, G, MINB>, 256, MINB);
+#ifdef PFDR_TUNE
+    // tuning build only (-DPFDR_TUNE): other group sizes / occupancies of the C4 kernel, chosen by PFDR_B200_DIAV
+    if constexpr (sizeof(real) == 4 && !PERK && LOSS == LOSS_KLA && ND == 3) {
+        const char *e = getenv("PFDR_B200_DIAV");
+        const int var = e ? atoi(e) : 0;
+        const int ws = getenv("PFDR_B200_WAVES") ? atoi(getenv("PFDR_B200_WAVES")) : 1;
+        if (var == 1) { PFDR_LAUNCH((simplex_dia_iter_kernel<real, LPT, PERK, LOSS, ND, 3, 2>), std::min(grid, num_sms() * 2 * ws), 256, 0, p); return; }
+        if (var == 2) { PFDR_LAUNCH((simplex_dia_iter_kernel<real, LPT, PERK, LOSS, ND, 2, 2>), std::min(grid, num_sms() * 2 * ws), 256, 0, p); return; }
+        if (var == 3) { PFDR_LAUNCH((simplex_dia_iter_kernel<real, LPT, PERK, LOSS, ND, 1, 4>), std::min(grid, num_sms() * 4 * ws), 256, 0, p); return; }
+        if (var == 4) { PFDR_LAUNCH((simplex_dia_iter_kernel<real, LPT, PERK, LOSS, ND, 6, 2>), std::min(grid, num_sms() * 2 * ws), 256, 0, p); return; }
+        if (var == 5) { PFDR_LAUNCH((simplex_dia_iter_kernel<real, LPT, PERK, LOSS, ND, 2, 4>), std::min(grid, num_sms() * 4 * ws), 256, 0, p); return; }
+        if (ws > 1) { PFDR_LAUNCH((simplex_dia_iter_kernel<real, LPT, PERK, LOSS, ND, G, MINB>), std::min(grid, wave * ws), 256, 0, p); return; }
+    }
+#endif
+    PFDR_LAUNCH((simplex_dia_iter_kernel<real, LPT, PERK, LOSS, ND, G, MINB>), std::min(grid, wave), 256, 0, p);
 }
 template <typename real, int LPT, bool PERK, int LOSS>
 void launch_iter_loss(const SP<real> &p, int grid)

@@ -117,9 +117,11 @@ def check_cp(r0, r1, tol=1e-5):
     assert np.allclose(r1["Obj"], r0["Obj"], rtol=tol)
 
 
-def test_c3_cp_bounds_ata_v4096(cps):
+def test_c3_cp_bounds_ata_v4096(cps, monkeypatch):
     """config 3 at V = 4096: the reference's cut-pursuit with every hot-path routine (PFDR and operator_norm_matrix)
-    served by libpfdr_b200 -> identical component count and vertex -> component assignment"""
+    served by libpfdr_b200 -> identical component count and vertex -> component assignment.  The power method's
+    starts are seeded by the clock in the reference (time + thread id): both builds run with the clock pinned."""
+    monkeypatch.setenv("PFDR_B200_OPNORM_TIME", "42")
     ref, b200 = cps
     w = synth.c3_bounds_ata(4096, 10, 1024, np.float64)
     kw = dict(CP_difTol=1e-4, CP_itMax=10, rho=1.5, condMin=1e-3, difRcd=0.0, difTol=1e-7, itMax=10000)
@@ -129,9 +131,10 @@ def test_c3_cp_bounds_ata_v4096(cps):
     check_cp(r0, b200.quadratic_d1_bounds(*args, **kw))
 
 
-def test_c1_cp_eeg_like_level5_own_norm(cps):
+def test_c1_cp_eeg_like_level5_own_norm(cps, monkeypatch):
     """config 1 stand-in at the reference's settings (octave/example_EEG_CP.m:20-27) with libpfdr_b200's own
-    operator_norm_matrix behind the reference's unmodified cut-pursuit"""
+    operator_norm_matrix behind the reference's unmodified cut-pursuit (clock pinned in both builds)"""
+    monkeypatch.setenv("PFDR_B200_OPNORM_TIME", "42")
     ref, b200 = cps
     w = synth.eeg_like(5, 91, np.float64)
     kw = dict(CP_difTol=1e-4, CP_itMax=15, rho=1.5, condMin=1e-3, difRcd=0.0, difTol=1e-7, itMax=10000)

@@ -10,6 +10,13 @@ from cp_pfdr_graph_d1_b200 import synth
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True)
+def pinned_clock(monkeypatch):
+    """the reference seeds the power method's starts with time(NULL) + thread id; oracle/_ref pins its clock to 42 and
+    libpfdr_b200's operator_norm_matrix (which draws the same starts) is given the same clock"""
+    monkeypatch.setenv("PFDR_B200_OPNORM_TIME", "42")
+
+
 @pytest.fixture(scope="module")
 def cps(gpu_api):
     from oracle import oracle as O
@@ -45,7 +52,7 @@ def test_cp_quadratic_l1_eeg_like(cps, duplex):
     r0 = ref.quadratic_d1_l1(*args, **kw)
     assert r0["rV"] > 10
     check(r0, b200n.quadratic_d1_l1(*args, **kw))
-    check(r0, b200.quadratic_d1_l1(*args, **kw), strict=False)
+    check(r0, b200.quadratic_d1_l1(*args, **kw))
 
 
 def test_cp_quadratic_bounds_ata(cps):
@@ -56,7 +63,7 @@ def test_cp_quadratic_bounds_ata(cps):
     args = (w["AtY"], w["AtA"], w["Eu"], w["Ev"], w["La_d1"], 0.0, 1.0, -w["V"])
     r0 = ref.quadratic_d1_bounds(*args, **kw)
     check(r0, b200n.quadratic_d1_bounds(*args, **kw))
-    check(r0, b200.quadratic_d1_bounds(*args, **kw), strict=False)
+    check(r0, b200.quadratic_d1_bounds(*args, **kw))
 
 
 def test_cp_simplex(cps):

@@ -61,8 +61,8 @@ def test_stencil_layout_matches_table(gpu_api, monkeypatch, name, dtype):
     assert got.it == tab.it and np.array_equal(got.X, tab.X)
     if got.Obj is not None:
         assert np.array_equal(got.Obj, tab.Obj)
-    if got.Dif is not None:
-        assert np.array_equal(got.Dif, tab.Dif)
+    if got.Dif is not None:      # the evolution sums are associated differently (per-lane double accumulators)
+        assert np.allclose(got.Dif, tab.Dif, rtol=1e-5 if dtype is np.float32 else 1e-12, atol=0)
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])

@@ -82,19 +82,19 @@ def test_stencil_layout_matches_table(gpu_api, monkeypatch, name, dtype):
     give the same bits: same arithmetic, same summation order"""
     from cp_pfdr_graph_d1_b200.api import _b
     got = problems.run_simplex(_b(), name, dtype)
-    K = got.X.shape[1]
-    expect_stencil = not (dtype is np.float64 and K > 64)
-    assert gpu_api.last_stats()["layout"] == (1 if expect_stencil else 0)
+    assert gpu_api.last_stats()["layout"] == 1
     monkeypatch.setenv("PFDR_B200_DIA", "0")
     if dtype is np.float64:
-        monkeypatch.setenv("PFDR_B200_LPT", "2")           # same lane layout as the stencil kernels -> same reduction trees
+        monkeypatch.setenv("PFDR_B200_LPT", "4")           # same lane layout as the stencil kernels -> same reduction trees
     tab = problems.run_simplex(_b(), name, dtype)
     assert gpu_api.last_stats()["layout"] == 0
     assert got.it == tab.it
     assert np.array_equal(got.X, tab.X)
     assert np.array_equal(got.Obj, tab.Obj)
-    if got.Dif is not None:
+    if got.Dif is not None and "labels" in name:
         assert np.array_equal(got.Dif, tab.Dif)
+    elif got.Dif is not None:        # the evolution sums are associated differently (per-lane double accumulators)
+        assert np.allclose(got.Dif, tab.Dif, rtol=1e-5 if dtype is np.float32 else 1e-12, atol=0)
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
@@ -179,8 +179,13 @@ def test_proj_simplex_empty(gpu_api):
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
-@pytest.mark.parametrize("shape", [(20, 50), (50, 20), (0, 30), (37, 0), (91, 700), (300, 300)])
-def test_operator_norm(gpu_api, dtype, shape):
+@pytest.mark.parametrize("shape", [(20, 50), (50, 20), (0, 30), (37, 0), (91, 700), (300, 300), (0, 1500), (1200, 1300), (64, 5000)])
+def test_operator_norm(gpu_api, monkeypatch, dtype, shape):
+    """same estimator as the reference, start for start (glibc rand_r streams seeded time + thread, nbInit rounded up to
+    the core count, the reference's stopping rule): with the clock pinned like oracle/_ref's, the two values agree to
+    rounding; and with a tight tolerance the value is lambda_max.  n > 1024 takes the batched all-SM path."""
+    from oracle import oracle as O
+    monkeypatch.setenv("PFDR_B200_OPNORM_TIME", "42")
     rng = np.random.default_rng(12)
     M, N = shape
     if M == 0 or N == 0:
@@ -191,10 +196,15 @@ def test_operator_norm(gpu_api, dtype, shape):
     else:
         A = np.asfortranarray(rng.standard_normal((M, N)).astype(dtype))
         lam = np.linalg.norm(A.astype(np.float64), 2) ** 2
-    got = gpu_api.operator_norm_matrix(A, M, N, 1e-4, 300, 10)
-    assert lam * 0.98 < got <= lam * (1 + 1e-4), (got, lam)
-    again = gpu_api.operator_norm_matrix(A, M, N, 1e-4, 300, 10)
-    assert got == again                         # seeded starts: reproducible, unlike the reference
+    got = gpu_api.operator_norm_matrix(A, M, N, 1e-3, 100, 10)
+    again = gpu_api.operator_norm_matrix(A, M, N, 1e-3, 100, 10)
+    assert got == again
+    ref = O.reference()
+    if ref is not None:                        # the reference's own value at its cut-pursuit settings (nTol 1e-3, 100, 10)
+        want = ref.operator_norm_matrix(A, M, N, 1e-3, 100, 10)
+        assert abs(got - want) <= (2e-3 if dtype is np.float32 else 1e-9) * want, (got, want, lam)
+    tight = gpu_api.operator_norm_matrix(A, M, N, 1e-7 if dtype is np.float64 else 1e-6, 3000, 10)
+    assert lam * (1 - (2e-3 if dtype is np.float32 else 2e-4)) < tight <= lam * (1 + (1e-4 if dtype is np.float32 else 1e-9)), (tight, lam)
 
 
 def test_simplex_rejects_bad_args(gpu_api):
