@@ -169,25 +169,12 @@ def cpu_sample_inputs(name):
 
 
 def grid_slab_simplex(n, K, dt, world, rank):
-    """rank's z-slab of the full-size C4 grid, generated directly in local numbering (no global arrays):
-    same recipe as synth.c4_simplex with a per-vertex counter-based RNG so that every rank draws the same Q
-    for the vertices it shares with its neighbours."""
+    """rank's slab of the C4 grid (shard.SlabPlan: vertices [lo, hi) = owned planes + one ghost plane each side),
+    generated directly, no global arrays: same recipe as synth.c4_simplex with a counter-based RNG per (vertex, label),
+    so that the ranks agree on the rows they share"""
     from cp_pfdr_graph_d1_b200 import shard
-    V = n ** 3
-    b = shard.slab_bounds(V, world)
-    v0, v1 = int(b[rank]), int(b[rank + 1])
-    lo, hi = max(v0 - n * n, 0), min(v1 + n * n, V)          # owned range plus one plane of possible ghosts each side
-    g = np.arange(lo, hi, dtype=np.int64)
-    z, y, x = g // (n * n), (g // n) % n, g % n
-    eu, ev = [], []
-    for ok, d in ((x < n - 1, 1), (y < n - 1, n), (z < n - 1, n * n)):
-        eu.append(np.where(ok, g, -1)); ev.append(np.where(ok, g + d, -1))
-    Eu, Ev = np.stack(eu, 1).reshape(-1), np.stack(ev, 1).reshape(-1)
-    keep = (Eu >= 0) & (Ev < hi) & (((Eu >= v0) & (Eu < v1)) | ((Ev >= v0) & (Ev < v1)))
-    Eu, Ev = Eu[keep], Ev[keep]
-    # global edge ids are only needed for ordering: vertex-major emission order == ascending (u, direction)
-    plan = shard.make_plan_local(V, Eu, Ev, world, rank, b)
-    gl = np.concatenate([np.arange(v0, v1), plan.ghosts])
+    plan = shard.grid_slab_plan(n, world, rank)
+    gl = np.arange(plan.lo, plan.hi, dtype=np.int64)
     zz, yy = gl // (n * n), (gl // n) % n
     lab = (4 * np.minimum(4 * zz // n, 3) + np.minimum(4 * yy // n, 3)) % K
     # counter-based uniform(0,1): splitmix64 of (vertex, label)
@@ -199,7 +186,21 @@ def grid_slab_simplex(n, K, dt, world, rank):
     Q[np.arange(gl.shape[0]), lab] += 2.0
     Q /= Q.sum(axis=1, keepdims=True)
     E_global = 3 * n * n * (n - 1)
-    return dict(plan=plan, V=V, E=E_global, Q=Q.astype(dt), La_d1=np.full(plan.Eu.shape[0], 0.2, dt))
+    return dict(plan=plan, V=n ** 3, E=E_global, Q=Q.astype(dt), La_d1=np.full(plan.Eu.shape[0], 0.2, dt))
+
+
+def device_grid_edges(n, dev):
+    """edge list of synth.grid_graph(n) built on the device (the full C4 graph has 48M edges)"""
+    import torch
+    V = n ** 3
+    v = torch.arange(V, device=dev)
+    z, y, x = v // (n * n), (v // n) % n, v % n
+    eu, ev = [], []
+    for ok, d in ((x < n - 1, 1), (y < n - 1, n), (z < n - 1, n * n)):
+        eu.append(torch.where(ok, v, -1)); ev.append(torch.where(ok, v + d, -1))
+    Eu = torch.stack(eu, 1).reshape(-1); Ev = torch.stack(ev, 1).reshape(-1)
+    keep = Eu >= 0
+    return Eu[keep].to(torch.int32).contiguous(), Ev[keep].to(torch.int32).contiguous()
 
 
 def torch_lambda_max(matvec, V, dev, tdt, iters=30):

@@ -13,7 +13,7 @@ Context &ctx()
 static thread_local std::string g_err;
 
 // library-owned launch stream: graph capture is not allowed on the legacy default stream
-static cudaStream_t own_stream()
+cudaStream_t own_stream()
 {
     static thread_local cudaStream_t s = nullptr;
     if (!s) PFDR_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
@@ -78,7 +78,7 @@ int pfdr_b200_quadratic_d1_l1_##SUF(int V, int E, int N, real *X, const real *Y,
     return guarded([&] {                                                                                \
         QuadProblem<real> q{V, E, N, X, Y, A, Eu, Ev, La_d1, La_l1, positivity, 0, 0, 0, Ltype, L, rho, \
                             condMin, difRcd, difTol, itMax, it, Obj, Dif, verbose};                     \
-        solve_quadratic<real>(q);                                                                       \
+        if (!solve_quadratic_multi<real>(q)) solve_quadratic<real>(q);                                  \
     });                                                                                                 \
 }                                                                                                       \
 int pfdr_b200_quadratic_d1_bounds_##SUF(int V, int E, int N, real *X, const real *Y, const real *A,     \
@@ -89,7 +89,7 @@ int pfdr_b200_quadratic_d1_bounds_##SUF(int V, int E, int N, real *X, const real
     return guarded([&] {                                                                                \
         QuadProblem<real> q{V, E, N, X, Y, A, Eu, Ev, La_d1, nullptr, 0, 1, lo, hi, Ltype, L, rho,      \
                             condMin, difRcd, difTol, itMax, it, Obj, Dif, verbose};                     \
-        solve_quadratic<real>(q);                                                                       \
+        if (!solve_quadratic_multi<real>(q)) solve_quadratic<real>(q);                                  \
     });                                                                                                 \
 }
 
@@ -104,7 +104,7 @@ int pfdr_b200_loss_d1_simplex_##SUF(int K, int V, int E, real al, const real *La
     return guarded([&] {                                                                                \
         SimplexProblem<real> q{K, V, E, al, La_f, P, Q, Eu, Ev, La_d1, rho, condMin, difRcd, difTol,    \
                                itMax, it, Obj, Dif, verbose};                                           \
-        solve_simplex<real>(q);                                                                         \
+        if (!solve_simplex_multi<real>(q)) solve_simplex<real>(q);                                      \
     });                                                                                                 \
 }                                                                                                       \
 int pfdr_b200_proj_simplex_metric_##SUF(real *X, const real *M, int D, int N, int nm, const real *A,    \
@@ -193,6 +193,49 @@ int pfdr_b200_solver_create_simplex_sharded_##SUF(pfdr_b200_solver **out, const 
 
 HANDLE_SHARDED(f32, float)
 HANDLE_SHARDED(f64, double)
+
+#define HANDLE_SLAB(SUF, real)                                                                          \
+int pfdr_b200_solver_create_simplex_slab_##SUF(pfdr_b200_solver **out, const pfdr_b200_slab *sl, int K, \
+    int Vloc, int Eloc, real al, const real *La_f, const real *P0, const real *Q, const int *Eu,        \
+    const int *Ev, const real *La_d1, real rho, real condMin, real difRcd, real difTol, int itMax,      \
+    int want_obj, int want_dif)                                                                         \
+{                                                                                                       \
+    return guarded([&] {                                                                                \
+        PFDR_REQUIRE(out != nullptr && sl != nullptr, "solver_create_slab: NULL argument");             \
+        real *flag = reinterpret_cast<real *>(sizeof(real));                                            \
+        SimplexProblem<real> q{K, Vloc, Eloc, al, La_f, const_cast<real *>(P0), Q, Eu, Ev, La_d1, rho,  \
+                               condMin, difRcd, difTol, itMax, nullptr, want_obj ? flag : nullptr,      \
+                               want_dif ? flag : nullptr, 0, nullptr, sl};                              \
+        *out = reinterpret_cast<pfdr_b200_solver *>(make_simplex<real>(q));                             \
+    });                                                                                                 \
+}                                                                                                       \
+int pfdr_b200_solver_create_quadratic_slab_##SUF(pfdr_b200_solver **out, const pfdr_b200_slab *sl,      \
+    int prox_kind, int Vloc, int Eloc, int N, const real *X0, const real *Y, const real *A,             \
+    const int *Eu, const int *Ev, const real *La_d1, const real *La_l1, int positivity, real lo,        \
+    real hi, int Ltype, const real *L, real rho, real condMin, real difRcd, real difTol, int itMax,     \
+    int want_obj, int want_dif)                                                                         \
+{                                                                                                       \
+    return guarded([&] {                                                                                \
+        PFDR_REQUIRE(out != nullptr && sl != nullptr, "solver_create_slab: NULL argument");             \
+        real *flag = reinterpret_cast<real *>(sizeof(real));                                            \
+        QuadProblem<real> q{Vloc, Eloc, N, const_cast<real *>(X0), Y, A, Eu, Ev, La_d1, La_l1,          \
+                            positivity, prox_kind, lo, hi, Ltype, L, rho, condMin, difRcd, difTol,      \
+                            itMax, nullptr, want_obj ? flag : nullptr, want_dif ? flag : nullptr, 0,    \
+                            nullptr, sl};                                                               \
+        *out = reinterpret_cast<pfdr_b200_solver *>(make_quadratic<real>(q));                           \
+    });                                                                                                 \
+}
+HANDLE_SLAB(f32, float)
+HANDLE_SLAB(f64, double)
+
+int pfdr_b200_slab_export(pfdr_b200_solver *s, void *blob)
+{
+    return guarded([&] { PFDR_REQUIRE(s && blob, "NULL argument"); reinterpret_cast<SolverBase *>(s)->slab_export(blob); });
+}
+int pfdr_b200_slab_connect(pfdr_b200_solver *s, const void *blobs, int same_process)
+{
+    return guarded([&] { PFDR_REQUIRE(s && blobs, "NULL argument"); reinterpret_cast<SolverBase *>(s)->slab_connect(blobs, same_process != 0); });
+}
 
 int pfdr_b200_comm_unique_id(void *out128)
 {

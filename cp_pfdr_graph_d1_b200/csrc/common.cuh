@@ -102,40 +102,42 @@ inline void event_put(cudaEvent_t e) { if (e) host_cache().events.push_back(e); 
 // and they are called once per cut-pursuit iteration by the reference's outer loop).  PFDR_B200_POOL=0 reverts.
 inline bool use_pool()
 {
-    static int v = -1;
-    if (v < 0) {
-        const char *e = getenv("PFDR_B200_POOL");
-        v = (e && e[0] == '0') ? 0 : 1;
-        if (v) {
-            int dev = 0, ok = 0;
-            cudaGetDevice(&dev);
-            cudaDeviceGetAttribute(&ok, cudaDevAttrMemoryPoolsSupported, dev);
-            cudaMemPool_t pool;
-            if (ok && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-                unsigned long long thr = ~0ull;
-                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-            } else v = 0;
-            cudaGetLastError();
-        }
+    static int env = -1;
+    static bool lifted[64] = {};                     // per device (several host threads may drive one GPU each)
+    if (env < 0) { const char *e = getenv("PFDR_B200_POOL"); env = (e && e[0] == '0') ? 0 : 1; }
+    if (!env) return false;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !lifted[dev]) {
+        int ok = 0;
+        cudaDeviceGetAttribute(&ok, cudaDevAttrMemoryPoolsSupported, dev);
+        cudaMemPool_t pool;
+        if (ok && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            unsigned long long thr = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+            lifted[dev] = true;
+        } else { cudaGetLastError(); return false; }
+        cudaGetLastError();
     }
-    return v != 0;
+    return true;
 }
 
 template <typename T>
 struct DevBuf {
     T *p = nullptr;
     size_t n = 0;
-    bool pooled = false;
+    bool pooled = false, borrowed = false;
     DevBuf() {}
     explicit DevBuf(size_t count) { alloc(count); }
     DevBuf(const DevBuf &) = delete;
     DevBuf &operator=(const DevBuf &) = delete;
-    DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n), pooled(o.pooled) { o.p = nullptr; o.n = 0; }
+    DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n), pooled(o.pooled), borrowed(o.borrowed) { o.p = nullptr; o.n = 0; }
     DevBuf &operator=(DevBuf &&o) noexcept
     {
-        if (this != &o) { release(); p = o.p; n = o.n; pooled = o.pooled; o.p = nullptr; o.n = 0; }
+        if (this != &o) { release(); p = o.p; n = o.n; pooled = o.pooled; borrowed = o.borrowed; o.p = nullptr; o.n = 0; }
         return *this;
     }
+    void borrow(T *q, size_t count) { release(); p = q; n = count; borrowed = true; }     // memory owned by someone else (a slab arena)
     ~DevBuf() { release(); }
     void alloc(size_t count) {
         release();
@@ -146,8 +148,8 @@ struct DevBuf {
         else PFDR_CUDA(cudaMalloc((void **) &p, count * sizeof(T)));
     }
     void release() {
-        if (p) { if (pooled) cudaFreeAsync(p, ctx().stream); else cudaFree(p); }
-        p = nullptr; n = 0;
+        if (p && !borrowed) { if (pooled) cudaFreeAsync(p, ctx().stream); else cudaFree(p); }
+        p = nullptr; n = 0; borrowed = false;
     }
     void zero() { if (p) PFDR_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), ctx().stream)); }
     operator T *() const { return p; }

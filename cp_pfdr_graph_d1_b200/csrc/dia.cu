@@ -69,13 +69,13 @@ __global__ void __launch_bounds__(256) dia_in_kernel(int V, Offs o, const unsign
     mask[v] = (unsigned char) m;
 }
 
-__global__ void chunk_key_kernel(int nchunks, int C, int band, int T, int nx, unsigned long long *__restrict__ key, int *__restrict__ val)
+__global__ void chunk_key_kernel(int nchunks, int C, int band, int T, int nx, long long v0, unsigned long long *__restrict__ key, int *__restrict__ val)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= nchunks) return;
-    const long long v = (long long) s * C;
+    const long long v = v0 + (long long) s * C;                     // global number of the chunk's first vertex
     const long long z = v / band, r = v % band;
-    const long long nz = ((long long) nchunks * C + band - 1) / band + 1;
+    const long long nz = (v0 + (long long) nchunks * C + band - 1) / band + 1;
     if (nx > 0) {
         // 3-D grid (rows of nx vertices): tiles of TY rows swept along z, and inside a tile patches of 8 rows x one chunk,
         // the 8 chunks of a patch consecutive (= the 8 warps of a CTA round): +-nx neighbours are loaded by the same SM
@@ -88,13 +88,13 @@ __global__ void chunk_key_kernel(int nchunks, int C, int band, int T, int nx, un
 
 }  // namespace
 
-void build_chunk_order(int nchunks, int C, int band, int T, DevBuf<int> &order, int nx)
+void build_chunk_order(int nchunks, int C, int band, int T, DevBuf<int> &order, int nx, long long v0)
 {
     cudaStream_t st = ctx().stream;
     DevBuf<unsigned long long> key(nchunks), skey(nchunks);
     DevBuf<int> val(nchunks);
     order.alloc(nchunks);
-    PFDR_LAUNCH(chunk_key_kernel, cdiv(nchunks, 256), 256, 0, nchunks, C, band, T, nx, key.p, val.p);
+    PFDR_LAUNCH(chunk_key_kernel, cdiv(nchunks, 256), 256, 0, nchunks, C, band, T, nx, v0, key.p, val.p);
     size_t tb = 0;
     PFDR_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, key.p, skey.p, val.p, order.p, nchunks, 0, 64, st));
     DevBuf<unsigned char> tmp(tb + 16);

@@ -39,9 +39,9 @@ template <typename real>
 __global__ void __launch_bounds__(256) amp_kernel(QP<real> p, int recond)
 {
     __shared__ double smem[64];
-    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    const int v = p.vbeg + blockIdx.x * blockDim.x + threadIdx.x;       // owned vertices
     double r[2] = {0.0, 0.0};
-    if (v < p.Vown) {
+    if (v < p.vend) {
         real a;
         if (recond) {
             a = ((p.ctl->it & 1) ? p.X1 : p.X0)[v];
@@ -1110,7 +1110,7 @@ __global__ void extract_x_kernel(QP<real> p, real *__restrict__ out)
 {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= p.Vown) return;
-    out[v] = ((p.ctl->it & 1) ? p.X1 : p.X0)[v];
+    out[v] = ((p.ctl->it & 1) ? p.X1 : p.X0)[p.vbeg + v];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1345,6 +1345,8 @@ struct QuadSolver : SolverBase {
     DevBuf<real> ze, sparts, ws;        //             edge-ordered copies, partial A x of the CTAs
     DevBuf<double> xsum;            //             partial sums of the CTAs
     Halo<real> halo;
+    SlabLink link;                  // slab-sharded solve (slab.cuh)
+    bool slab = false;
     bool sharded = false;
     int ogrid = 0;                  // CTAs covering the owned vertices
     Ctl *hctl = nullptr;            // pinned mirror of the control block, one per batch in flight
@@ -1369,6 +1371,14 @@ struct QuadSolver : SolverBase {
         PFDR_REQUIRE(q.itMax >= 0, "itMax must be non-negative");
         PFDR_REQUIRE(N == 0 || q.A != nullptr, "A must not be NULL when N != 0");
         sharded = q.shard != nullptr;
+        slab = q.slab != nullptr;
+        if (slab) {
+            PFDR_REQUIRE(!sharded, "a solve is sharded either by slabs or by a shard plan");
+            PFDR_REQUIRE(N == 0, "slab-sharded solves support diagonal / identity A (N = 0) in this build");
+            PFDR_REQUIRE(q.Obj == nullptr && q.difRcd == (real) 0, "slab-sharded solves do not record Obj nor recondition in this build");
+            PFDR_REQUIRE(q.slab->world >= 1 && q.slab->lo <= q.slab->v0 && q.slab->v0 < q.slab->v1 && q.slab->v1 <= q.slab->hi &&
+                         q.slab->hi - q.slab->lo == V, "bad slab: need lo <= v0 < v1 <= hi and Vloc = hi - lo");
+        }
         if (sharded) {
             PFDR_REQUIRE(N >= 0, "sharded solves support N >= 0 (A diagonal, identity or dense N-by-Vown) in this build");
             PFDR_REQUIRE(q.Obj == nullptr && q.difRcd == (real) 0, "sharded solves do not record Obj nor recondition in this build");
@@ -1394,8 +1404,9 @@ struct QuadSolver : SolverBase {
             const char *de = getenv("PFDR_B200_DIA"), *se = getenv("PFDR_B200_SMALL");
             const bool small_off = se && se[0] == '0';
             const bool forced = de && de[0] == '1';
-            if (!sharded && !(de && de[0] == '0') && (forced || small_off || !small_candidate()))
+            if (!sharded && !(de && de[0] == '0') && (forced || small_off || slab || !small_candidate()))
                 dia = build_dia(dg, Eu, Ev, V, E);
+            PFDR_REQUIRE(dia || !slab, "slab sharding needs a constant-offset (grid) graph with its edges in vertex-major order");
         }
         if (dia) {
             nhalf = 2LL * dg.ND * V;
@@ -1409,27 +1420,37 @@ struct QuadSolver : SolverBase {
         }
 
         const size_t ns = (size_t) std::max<long long>(nhalf, 1);
-        Z0.alloc(ns); Z1.alloc(ns);
-        X0b.alloc(V); X1b.alloc(V); P0b.alloc(V); P1b.alloc(V); T.alloc(V); Sinv.alloc(V); Ga.alloc(V); Ga0.alloc(V);
+        if (slab) {          // what the neighbouring ranks write / copy into lives in the peer-visible arena
+            link.reserve(SLAB_Z0, ns * sizeof(real)); link.reserve(SLAB_Z1, ns * sizeof(real));
+            link.reserve(SLAB_F0, (size_t) V * sizeof(real)); link.reserve(SLAB_F1, (size_t) V * sizeof(real)); link.reserve(SLAB_T, (size_t) V * sizeof(real));
+            link.commit(q.slab->world, q.slab->rank, q.slab->lo, q.slab->hi, q.slab->v0, q.slab->v1, 1);
+            Z0.borrow(link.ptr<real>(SLAB_Z0), ns); Z1.borrow(link.ptr<real>(SLAB_Z1), ns);
+            P0b.borrow(link.ptr<real>(SLAB_F0), V); P1b.borrow(link.ptr<real>(SLAB_F1), V); T.borrow(link.ptr<real>(SLAB_T), V);
+        } else {
+            Z0.alloc(ns); Z1.alloc(ns); P0b.alloc(V); P1b.alloc(V); T.alloc(V);
+        }
+        X0b.alloc(V); X1b.alloc(V); Sinv.alloc(V); Ga.alloc(V); Ga0.alloc(V);
         if (La_l1.p) Thl1.alloc(V);
         if (N != 0) G.alloc(V);
         if (N > 0) { R.alloc(N); AtY.alloc(V); rsum.alloc(N); p.rsum = rsum.p; }
         if (q.Obj) dObj.alloc((size_t) q.itMax + 1);
         if (q.Dif) dDif.alloc((size_t) std::max(q.itMax, 1));
         vgrid = (int) cdiv(V, 256);
-        ogrid = sharded ? (int) cdiv(q.shard->Vown, 256) : vgrid;
+        ogrid = sharded ? (int) cdiv(q.shard->Vown, 256) : (slab ? (int) cdiv(q.slab->v1 - q.slab->v0, 256) : vgrid);
         ctl.alloc(1); sums.alloc(2 * (size_t) std::max(1, comm().world)); sums.zero(); amp_sums.alloc(2);
 
         // padded slots of Z must never hold garbage that could turn into NaN traps: zero them
         Z0.zero(); Z1.zero(); w.zero();
 
         p.ctl = ctl.p; p.V = V; p.N = N; p.E = E;
-        p.Vown = sharded ? q.shard->Vown : V; p.sharded = sharded ? 1 : 0; p.sums = sums.p; p.amp_sums = amp_sums.p;
+        p.Vown = sharded ? q.shard->Vown : (slab ? q.slab->v1 - q.slab->v0 : V); p.sharded = sharded ? 1 : 0; p.sums = sums.p; p.amp_sums = amp_sums.p;
         p.world = sharded ? comm().world : 1; p.rank = sharded ? comm().rank : 0;
         p.slice_off = g.slice_off.p; p.nbr = g.nbr.p; p.twin = g.twin.p; p.hkey = g.hkey.p;
         p.dia_nd = dia ? dg.ND : 0;
         for (int i = 0; i < 3; i++) p.dia_off[i] = dia ? dg.off[i] : 0;
-        p.vbeg = 0; p.vend = sharded ? q.shard->Vown : V; p.dmask = dg.mask.p; p.eoff = dg.eoff.p; p.Wrow = Wrow.p;
+        p.vbeg = slab ? q.slab->v0 - q.slab->lo : 0; p.vend = p.vbeg + p.Vown; p.dmask = dg.mask.p; p.eoff = dg.eoff.p; p.Wrow = Wrow.p;
+        p.slab = SlabDev{}; p.plo = SlabPeer<real>{}; p.phi = SlabPeer<real>{};
+        if (slab) { p.slab = link.dev(); p.slab.band = dg.band(); }
         p.w = w.p; p.thc = nullptr; p.thc0 = 0; p.Z0 = Z0.p; p.Z1 = Z1.p;
         p.pk = nullptr; p.pk2 = nullptr;           // set by pack_slots() after each (re)conditioning (PFDR_B200_PACK=0: off)
         p.X0 = X0b.p; p.X1 = X1b.p; p.P0 = P0b.p; p.P1 = P1b.p; p.T = T.p; p.Sinv = Sinv.p; p.Ga = Ga.p; p.Ga0 = Ga0.p; p.G = G.p; p.Thl1 = Thl1.p;
@@ -1462,9 +1483,64 @@ struct QuadSolver : SolverBase {
             halo.setup(*q.shard, g.hkey.p, g.nslots, 2 * (size_t) E, 1);
             halo.build(HALO_VA0 | HALO_VA1); halo.build(HALO_VA0 | HALO_Z); halo.build(HALO_VA0); halo.build(HALO_Z);
         }
-        reset();
+        if (!(slab && link.world > 1)) reset();            // a slab-sharded solve is initialised by slab_connect (collective)
         if (!keep_x0) X0.own.release();
         PFDR_CUDA(cudaEventRecord(ev_b, st));
+    }
+
+    // ghost zones of the neighbours <- this rank's boundary: metric T, forward point and cut-edge copies of the parity-0 buffers
+    void slab_refresh()
+    {
+        const size_t Vp = (size_t) q.V;
+        const int ND = dg.ND;
+        for (int side = 0; side < 2; side++) {
+            const int nb = side ? link.nb_hi : link.nb_lo;
+            if (nb < 0) continue;
+            const SlabBlob &b = link.blobs[nb];
+            const long long depth = side ? b.v0 - b.lo : b.hi - b.v1;          // its ghost zone on our side
+            const long long first = side ? p.vend - depth : p.vbeg;
+            const long long dshift = link.lo - b.lo;
+            const size_t Vn = (size_t) (b.hi - b.lo);
+            link.push<real>(SLAB_T, nb, (size_t) first, (size_t) depth, dshift);
+            link.push<real>(SLAB_F0, nb, (size_t) first, (size_t) depth, dshift);
+            for (int i = 0; i < ND; i++) {                                       // copies on the cut edges of offset d_i
+                const long long d = std::min<long long>(dg.off[i], depth), f = side ? p.vend - d : p.vbeg;
+                const int plane = side ? i : ND + i;                             // our out_i copies go up, our in_i copies down
+                link.push<real>(SLAB_Z0, nb, (size_t) plane * Vp + (size_t) f, (size_t) d,
+                                (long long) plane * ((long long) Vn - (long long) Vp) + dshift);
+            }
+        }
+        link.barrier();
+    }
+    void slab_check()
+    {
+        int err = 0;
+        PFDR_CUDA(cudaMemcpy(&err, &link.ptr<SlabMail>(SLAB_MAILBOX)->error, sizeof(int), cudaMemcpyDeviceToHost));
+        if (err) throw Error(PFDR_B200_ERR_CUDA, "slab-sharded solve: a rank stopped answering (timed out waiting for its flag)");
+    }
+    void slab_export(void *blob) override
+    {
+        PFDR_REQUIRE(slab, "not a slab-sharded solver");
+        memset(blob, 0, PFDR_B200_SLAB_BLOB);
+        memcpy(blob, &link.mine, sizeof(SlabBlob));
+    }
+    void slab_connect(const void *blobs, bool same_process) override
+    {
+        PFDR_REQUIRE(slab, "not a slab-sharded solver");
+        std::vector<SlabBlob> all(link.world);
+        for (int r = 0; r < link.world; r++) memcpy(&all[r], (const char *) blobs + (size_t) r * PFDR_B200_SLAB_BLOB, sizeof(SlabBlob));
+        link.connect(all.data(), same_process);
+        p.slab = link.dev(); p.slab.band = dg.band();
+        for (int side = 0; side < 2; side++) {
+            const int nb = side ? link.nb_hi : link.nb_lo;
+            if (nb < 0) continue;
+            SlabPeer<real> &pe = side ? p.phi : p.plo;
+            pe.Z[0] = link.ptr<real>(SLAB_Z0, nb); pe.Z[1] = link.ptr<real>(SLAB_Z1, nb);
+            pe.F[0] = link.ptr<real>(SLAB_F0, nb); pe.F[1] = link.ptr<real>(SLAB_F1, nb);
+            pe.plane = (size_t) (link.blobs[nb].hi - link.blobs[nb].lo);
+            pe.shift = link.lo - link.blobs[nb].lo;
+        }
+        if (link.world > 1) reset();                          // collective: first preconditioning, ghost zones, barrier
     }
 
     // initial iterate, edge copies, first preconditioning and control block: device work only
@@ -1484,16 +1560,28 @@ struct QuadSolver : SolverBase {
         h.eps = (double) (((real) 0 < q.difTol && q.difTol < real_eps<real>()) ? q.difTol : real_eps<real>());
         hctl[0] = h;
         PFDR_CUDA(cudaMemcpyAsync(ctl.p, &hctl[0], sizeof(Ctl), cudaMemcpyHostToDevice, st));
+        const bool linked = slab && link.world > 1;
+        if (linked) {                                        // nobody still iterates on the buffers about to be rewritten
+            PFDR_REQUIRE(link.connected, "slab-sharded solver: reset before slab_connect");
+            link.barrier();
+            link.run_id++;
+            p.slab.run_id = link.run_id;
+            if (gexec) { cudaGraphExecDestroy(gexec); gexec = nullptr; }
+        }
+        p.sharded = (sharded || linked) ? 1 : 0;             // amp_kernel leaves its sums for the all-reduce
         // first preconditioning
         if (q.N > 0) launch_atr(1);
         PFDR_LAUNCH(amp_kernel<real>, ogrid, 256, 0, p, 0);
         if (sharded) { comm_allreduce_sum(amp_sums.p, 2); PFDR_LAUNCH(amp_finish_kernel<real>, 1, 1, 0, p, 0); }
+        if (linked) { link.allreduce_sum(amp_sums.p, 2); PFDR_LAUNCH(amp_finish_kernel<real>, 1, 1, 0, p, 0); p.sharded = 0; }
         if (dia) quad_dia_launch_init<real>(p, X0.p, vgrid);
         else PFDR_LAUNCH(init_vertex_kernel<real>, vgrid, 256, 0, p, X0.p);
         // ghosts: the metric constants and forward point come from their owners
         if (sharded) halo.exchange(HALO_VA0 | HALO_VA1, PingPong<real>(T.p), PingPong<real>(P0b.p), PingPong<real>(), nullptr, PARITY_ZERO);
+        if (linked) slab_refresh();
         PFDR_CUDA(cudaMemcpyAsync(&hctl[1], ctl.p, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
         PFDR_CUDA(cudaStreamSynchronize(st));
+        if (linked) slab_check();
         const real thc0 = (real) 1 / (real) hctl[1].amp;       // La_d1 / (c La_d1)
         if (gexec && thc0 != p.thc0) { cudaGraphExecDestroy(gexec); gexec = nullptr; }
         p.thc0 = thc0;
@@ -1771,7 +1859,7 @@ struct QuadSolver : SolverBase {
         cudaStream_t st = ctx().stream;
         if (small_mode()) { if (!run_push()) run_small(); return; }
         // batch: enough trips per host round trip to hide it, small enough to bound the no-op tail
-        ctx().stats.layout = dia ? 1 : 0; ctx().stats.gpus = 1;
+        ctx().stats.layout = dia ? 1 : 0; ctx().stats.gpus = slab ? link.world : 1;
         const size_t work = (size_t) nhalf + (size_t) q.V + (size_t) std::abs((double) q.N) * q.V;
         int batch = work > (1u << 24) ? 4 : (work > (1u << 20) ? 16 : 64);
         batch = std::max(1, std::min(batch, q.itMax + 1));
@@ -1806,6 +1894,7 @@ struct QuadSolver : SolverBase {
         PFDR_CUDA(cudaEventElapsedTime(&ms, ev_b, ev_c));
         ctx().stats.loop_ms = ms;
         ctx().stats.iterations = hctl[0].it;
+        if (slab && link.world > 1) slab_check();
     }
 
     // waits for batch slot b: 0 = still running, 1 = finished, 2 = frozen for a reconditioning

@@ -2,6 +2,7 @@
 // (quad.cu: half-edge table and the single-launch cluster kernels; quad_dia.cu: constant-offset graphs).
 #pragma once
 #include "common.cuh"
+#include "slab.cuh"
 
 namespace pfdr {
 
@@ -41,6 +42,9 @@ struct QP {                       // kernel parameter block
     const unsigned char *dmask;   // [V]
     const int *eoff;              // [V]
     real *Wrow;                   // [2.ND * V]
+    // slab-sharded solve (slab.cuh): V counts the vertices held (owned + ghost zones), [vbeg, vend) are the owned ones
+    SlabDev slab;
+    SlabPeer<real> plo, phi;      // the ghost zones this rank writes: in the rank below / above (F = forward point P)
 };
 
 // explicitly rounded operations: the d1 prox below is shared by the kernels of both layouts and must give the same bits
@@ -150,6 +154,38 @@ __device__ void quad_finalize(const QP<real> &p, int it, double d, double c)
     ctl->it = itn;
     if (itn == ctl->itMax || (real) dif < (real) ctl->tol) ctl->state = ST_FINAL;
     else if ((real) dif < (real) ctl->rcd) ctl->state = ST_RECOND;
+}
+
+// slab-sharded solve: what the kernel of trip `it` does before touching any data (slab.cuh).  Called by one thread of every
+// CTA; all of them (on every rank) return the same state.
+template <typename real>
+__device__ int quad_slab_decide(const QP<real> &p, int it)
+{
+    Ctl *ctl = p.ctl;
+    if (it == 0) return ST_RUN;
+    SlabMail *me = p.slab.mail[p.slab.rank];
+    const unsigned long long target = (p.slab.run_id << 32) | (unsigned long long) it;
+    bool ok = true;
+    if (p.slab.nb_lo >= 0) ok = slab_wait(&me->sum_flag[p.slab.nb_lo], target, me) && ok;
+    if (p.slab.nb_hi >= 0) ok = slab_wait(&me->sum_flag[p.slab.nb_hi], target, me) && ok;
+    const int track = ctl->track;
+    double dif = ctl->dif;
+    if (ok && track) {
+        double d = 0.0, c = 0.0;
+        for (int q = 0; q < p.slab.world; q++) {                                   // rank order: same bits everywhere
+            ok = slab_wait(&me->sum_flag[q], target, me) && ok;
+            d += me->sums[q][0]; c += me->sums[q][1];
+        }
+        dif = (c > ctl->eps) ? d / c : d / ctl->eps;                               // ref :515-529
+    }
+    int state = ST_RUN;
+    if (!ok || it == ctl->itMax || (real) dif < (real) ctl->tol) state = ST_FINAL;
+    else if ((real) dif < (real) ctl->rcd) state = ST_RECOND;
+    if (blockIdx.x == 0) {
+        if (track && ok) { ctl->dif = dif; if (p.dDif) p.dDif[it - 1] = (real) dif; }
+        if (state != ST_RUN) { ctl->state = state; ctl->hold = 1; }
+    }
+    return state;
 }
 
 }  // namespace pfdr

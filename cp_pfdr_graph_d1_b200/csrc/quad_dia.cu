@@ -27,8 +27,8 @@ template <typename real, int ND>
 __global__ void __launch_bounds__(256) quad_dia_init_kernel(QP<real> p, const real *__restrict__ X0)
 {
     typedef DiaHalf<ND> H;
-    const int v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= p.V) return;
+    const int v = p.vbeg + blockIdx.x * blockDim.x + threadIdx.x;   // owned vertices (slab-sharded: ghosts come from their owners)
+    if (v >= p.vend) return;
     const size_t Vp = (size_t) p.V;
     const real c = (real) p.ctl->amp;
     const real x = X0[v];
@@ -61,8 +61,8 @@ template <typename real, int ND>
 __global__ void __launch_bounds__(256) quad_dia_recond_kernel(QP<real> p)
 {
     typedef DiaHalf<ND> H;
-    const int v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= p.V) return;
+    const int v = p.vbeg + blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= p.vend) return;
     const size_t Vp = (size_t) p.V;
     const int cur = p.ctl->it & 1;
     const real *X = cur ? p.X1 : p.X0;
@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(256) quad_dia_recond_kernel(QP<real> p)
 // Persistent warps (one wave of resident CTAs): a warp walks chunks of 32 consecutive vertices, no block-level
 // synchronisation inside the loop; loads never depend on the edge mask (neighbour index clamped into [0, V), a
 // half-edge that does not exist is dropped at compute time); G half-edges (5 loads each) are requested at a time.
-template <typename real, bool PER_SLOT_TH, int ND, int G, int MINB>
+template <typename real, bool PER_SLOT_TH, int ND, int G, int MINB, bool SLAB = false>
 __global__ void __launch_bounds__(256, MINB) quad_dia_iter_kernel(QP<real> p)
 {
     typedef DiaHalf<ND> H;
@@ -129,6 +129,12 @@ __global__ void __launch_bounds__(256, MINB) quad_dia_iter_kernel(QP<real> p)
         return;
     }
     const int it = cv.it, cur = it & 1;
+    if (SLAB) {             // neighbours' pushes of the previous trip have landed; stop / recondition decision over all ranks
+        __shared__ int s_state;
+        if (threadIdx.x == 0) s_state = quad_slab_decide(p, it);
+        __syncthreads();
+        if (s_state != ST_RUN) return;
+    }
     const real *__restrict__ Zin = cur ? p.Z1 : p.Z0;
     real *__restrict__ Zout = cur ? p.Z0 : p.Z1;
     const real *__restrict__ Xc = cur ? p.X1 : p.X0;
@@ -143,6 +149,7 @@ __global__ void __launch_bounds__(256, MINB) quad_dia_iter_kernel(QP<real> p)
     const int off[3] = {p.dia_off[0], p.dia_off[1], p.dia_off[2]};
     const int stride = (int) (gridDim.x * blockDim.x);              // a warp takes 32 consecutive vertices per trip
     double red0 = 0.0, red1 = 0.0;
+    bool pushed = false;              // (a vertex with a cut edge lies within `band` of the slab's end, so its forward point travels too)
     for (int v = p.vbeg + (int) (blockIdx.x * blockDim.x + threadIdx.x); v < p.vend; v += stride) {
         const unsigned m = __ldg(p.dmask + v);
         const real xo = Xc[v], po_v = Pc[v], Tv = Tg[v];
@@ -169,6 +176,10 @@ __global__ void __launch_bounds__(256, MINB) quad_dia_iter_kernel(QP<real> p)
                     const real zn = d1_prox_half<real>(rho, xo, po_v, Tv, zo[u], zt[u], pn[u], Tn[u], thc[u]);
                     Zout[(size_t) H::own_plane(h) * Vp + v] = zn;
                     acc = fma_rn(wr[u], zn, acc);
+                    if (SLAB) {     // the other end belongs to the rank above / below: its twin copy lives there too
+                        if (H::out(h)) { if (v + off[H::idx(h)] >= p.vend) p.phi.Z[cur ^ 1][(size_t) H::own_plane(h) * p.phi.plane + (size_t) ((long long) v + p.phi.shift)] = zn; }
+                        else if (v - off[H::idx(h)] < p.vbeg) p.plo.Z[cur ^ 1][(size_t) H::own_plane(h) * p.plo.plane + (size_t) ((long long) v + p.plo.shift)] = zn;
+                    }
                 }
             }
         }
@@ -185,13 +196,25 @@ __global__ void __launch_bounds__(256, MINB) quad_dia_iter_kernel(QP<real> p)
             else if (p.has_hi && x > p.hi) x = p.hi;
         }
         Xn[v] = x;
-        if (p.N == 0) Pn[v] = forward_point_diag(p, v, x);
+        if (p.N == 0) {
+            const real fp = forward_point_diag(p, v, x);
+            Pn[v] = fp;
+            if (SLAB) {     // boundary vertices: the neighbouring rank gathers this forward point from its ghost zone
+                if (p.plo.F[0] && v < p.vbeg + p.slab.band) { p.plo.F[cur ^ 1][(long long) v + p.plo.shift] = fp; pushed = true; }
+                if (p.phi.F[0] && v >= p.vend - p.slab.band) { p.phi.F[cur ^ 1][(long long) v + p.phi.shift] = fp; pushed = true; }
+            }
+        }
         const real dx = xo - x;
         red0 += (double) (dx * dx); red1 += (double) (x * x);
     }
+    if (SLAB && pushed) __threadfence_system();             // this thread's stores into the neighbours' ghost zones
     double tot[2] = {red0, red1};
     if (grid_sum<2>(ctl, p.partial, tot, smem) && threadIdx.x == 0) {
-        if (p.sharded) { p.sums[2 * p.rank] = tot[0]; p.sums[2 * p.rank + 1] = tot[1]; }
+        if (SLAB) {
+            ctl->it = it + 1;
+            const double v4[SLAB_NSUM] = {tot[0], tot[1], 0.0, 0.0};
+            slab_post(p.slab, v4, (unsigned long long) (it + 1));
+        } else if (p.sharded) { p.sums[2 * p.rank] = tot[0]; p.sums[2 * p.rank + 1] = tot[1]; }
         else quad_finalize(p, it, tot[0], tot[1]);
     }
 }
@@ -226,7 +249,8 @@ void quad_dia_launch_iter(const QP<real> &p, int grid)
     constexpr int G = sizeof(real) == 4 ? 6 : 3;         // half-edges requested at a time (5 loads each)
     const int g = std::min(grid, num_sms() * MINB);      // one wave of resident CTAs
 #define CALL(N_)                                                                                         \
-    if (p.thc) PFDR_LAUNCH((quad_dia_iter_kernel<real, true, N_, G, MINB>), g, 256, 0, p);               \
+    if (p.slab.on) PFDR_LAUNCH((quad_dia_iter_kernel<real, false, N_, G, MINB, true>), g, 256, 0, p);    \
+    else if (p.thc) PFDR_LAUNCH((quad_dia_iter_kernel<real, true, N_, G, MINB>), g, 256, 0, p);          \
     else PFDR_LAUNCH((quad_dia_iter_kernel<real, false, N_, G, MINB>), g, 256, 0, p)
     PFDR_ND_SWITCH(CALL);
 #undef CALL

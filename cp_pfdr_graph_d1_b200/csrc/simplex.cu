@@ -319,7 +319,7 @@ __global__ void simplex_extract_kernel(SP<real> p, real *__restrict__ out)
     const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t) p.Vown * p.Kv) return;
     const size_t v = i / p.Kv, k = i - v * p.Kv;                               // out has the caller's row stride Kv
-    out[i] = ((p.ctl->it & 1) ? p.P1 : p.P0)[v * p.K + k];
+    out[i] = ((p.ctl->it & 1) ? p.P1 : p.P0)[(v + (size_t) (p.dia_nd ? p.vbeg : 0)) * p.K + k];
 }
 
 // K-vectors of the caller (row stride Kv) into rows of stride K >= Kv, the extra labels zero
@@ -358,6 +358,8 @@ struct SimplexSolver : SolverBase {
     DevBuf<int> lab, order;
     DevBuf<double> partial, sums;
     Halo<real> halo;
+    SlabLink link;                  // slab-sharded solve (slab.cuh)
+    bool slab = false;
     bool sharded = false;
     Ctl *hctl = nullptr;
     cudaEvent_t ev[2]{}, ev_a{}, ev_b{}, ev_c{};
@@ -379,6 +381,13 @@ struct SimplexSolver : SolverBase {
         PFDR_REQUIRE(K >= 1 && V > 0 && E >= 0 && q.itMax >= 0, "K, V must be positive, E and itMax non-negative");
         PFDR_REQUIRE(q.al >= (real) 0 && q.al <= (real) 1, "al must lie in [0, 1] (the reference is undefined beyond, SURVEY 5.1-10)");
         sharded = q.shard != nullptr;
+        slab = q.slab != nullptr;
+        if (slab) {
+            PFDR_REQUIRE(!sharded, "a solve is sharded either by slabs or by a shard plan");
+            PFDR_REQUIRE(q.Obj == nullptr && q.difRcd == (real) 0, "slab-sharded solves do not record Obj nor recondition in this build");
+            PFDR_REQUIRE(q.slab->world >= 1 && q.slab->lo <= q.slab->v0 && q.slab->v0 < q.slab->v1 && q.slab->v1 <= q.slab->hi &&
+                         q.slab->hi - q.slab->lo == V, "bad slab: need lo <= v0 < v1 <= hi and Vloc = hi - lo");
+        }
         if (sharded) {
             PFDR_REQUIRE(q.Obj == nullptr && q.difRcd == (real) 0, "sharded solves do not record Obj nor recondition in this build");
             PFDR_REQUIRE(q.shard->Vown > 0 && q.shard->Vown <= V, "bad shard: Vown");
@@ -406,6 +415,8 @@ struct SimplexSolver : SolverBase {
             if (!sharded && lanes_ok && !(de && de[0] == '0') && (size_t) V * (size_t) (((Kv + DL - 1) / DL) * DL) * 6 < ((size_t) 1 << 40))
                 dia = build_dia(dg, Eu, Ev, V, E);
             if (dia) LPT = DL;
+            PFDR_REQUIRE(dia || !slab, "slab sharding needs a constant-offset (grid) graph with its edges in vertex-major order, "
+                                       "K >= 3 labels and a plain PFDR_B200_DIA / PFDR_B200_LPT environment");
         }
         K = ((Kv + LPT - 1) / LPT) * LPT;
         const bool padded = K != Kv;
@@ -441,8 +452,16 @@ struct SimplexSolver : SolverBase {
             w.alloc((size_t) std::max<long long>(nhalf, 1));
         }
         const size_t ns = (size_t) std::max<long long>(nhalf, 1);
-        Z0.alloc(ns * K); Z1.alloc(ns * K);
-        Pa.alloc(VK); Pb.alloc(VK); Fa.alloc(VK); Fb.alloc(VK); T.alloc(VK); GaQ.alloc(VK); Sinv.alloc(V);
+        if (slab) {          // what the neighbouring ranks write / copy into lives in the peer-visible arena
+            link.reserve(SLAB_Z0, ns * K * sizeof(real)); link.reserve(SLAB_Z1, ns * K * sizeof(real));
+            link.reserve(SLAB_F0, VK * sizeof(real)); link.reserve(SLAB_F1, VK * sizeof(real)); link.reserve(SLAB_T, VK * sizeof(real));
+            link.commit(q.slab->world, q.slab->rank, q.slab->lo, q.slab->hi, q.slab->v0, q.slab->v1, K);
+            Z0.borrow(link.ptr<real>(SLAB_Z0), ns * K); Z1.borrow(link.ptr<real>(SLAB_Z1), ns * K);
+            Fa.borrow(link.ptr<real>(SLAB_F0), VK); Fb.borrow(link.ptr<real>(SLAB_F1), VK); T.borrow(link.ptr<real>(SLAB_T), VK);
+        } else {
+            Z0.alloc(ns * K); Z1.alloc(ns * K); Fa.alloc(VK); Fb.alloc(VK); T.alloc(VK);
+        }
+        Pa.alloc(VK); Pb.alloc(VK); GaQ.alloc(VK); Sinv.alloc(V);
         if (q.difRcd > (real) 0) GaU.alloc(VK);
         Z0.zero(); Z1.zero(); w.zero();
         if (padded) {           // what the extra labels read: T = 1 (a denominator), everything else 0
@@ -456,11 +475,11 @@ struct SimplexSolver : SolverBase {
         ctl.alloc(1); sums.alloc((size_t) std::max(1, comm().world)); sums.zero();
         const long long nslices = ((long long) V + C - 1) / C;
         grid = (int) cdiv((size_t) nslices * 32, 256);
-        const int Vown = sharded ? q.shard->Vown : V;
+        const int Vown = sharded ? q.shard->Vown : (slab ? q.slab->v1 - q.slab->v0 : V);
         ogrid = (int) cdiv((size_t) (((long long) Vown + C - 1) / C) * 32, 256);
         partial.alloc((size_t) std::max(grid, num_sms() * 8) * 2);
 
-        p.Vown = Vown; p.sharded = sharded ? 1 : 0; p.sums = sums.p; p.Vglobal = sharded ? q.shard->Vglobal : V;
+        p.Vown = Vown; p.sharded = sharded ? 1 : 0; p.sums = sums.p; p.Vglobal = sharded ? q.shard->Vglobal : (slab ? q.slab->Vglobal : V);
         p.world = sharded ? comm().world : 1; p.rank = sharded ? comm().rank : 0;
         {   // banded graph whose +-band reuse window would not fit the L2: sweep (x,y)-tiles along z instead
             const int width = dia ? 2 * dg.ND : std::max(g.max_width, 1), band = dia ? (dg.ND > 1 ? dg.band() : 0) : g.band;
@@ -474,7 +493,7 @@ struct SimplexSolver : SolverBase {
                 T = (T / C) * C;
                 const char *pe = getenv("PFDR_B200_PATCH");
                 const int nx = (dia && dg.ND == 3 && dg.off[0] == 1 && dg.off[2] % dg.off[1] == 0 && !(pe && pe[0] == '0')) ? dg.off[1] : 0;
-                build_chunk_order((int) (((long long) Vown + C - 1) / C), C, band, (int) T, order, nx);
+                build_chunk_order((int) (((long long) Vown + C - 1) / C), C, band, (int) T, order, nx, slab ? q.slab->v0 : 0);
                 p.order = order.p;
             }
         }
@@ -486,7 +505,9 @@ struct SimplexSolver : SolverBase {
         p.slice_off = g.slice_off.p; p.nbr = g.nbr.p; p.twin = g.twin.p; p.hkey = g.hkey.p;
         p.dia_nd = dia ? dg.ND : 0;
         for (int i = 0; i < 3; i++) p.dia_off[i] = dia ? dg.off[i] : 0;
-        p.vbeg = 0; p.vend = Vown; p.dmask = dg.mask.p; p.eoff = dg.eoff.p; p.Wrow = Wrow.p;
+        p.vbeg = slab ? q.slab->v0 - q.slab->lo : 0; p.vend = p.vbeg + Vown; p.dmask = dg.mask.p;
+        p.slab = SlabDev{}; p.plo = SlabPeer<real>{}; p.phi = SlabPeer<real>{};
+        if (slab) { p.slab = link.dev(); p.slab.band = dg.band(); } p.eoff = dg.eoff.p; p.Wrow = Wrow.p;
         p.w = w.p; p.wk = nullptr; p.thk = nullptr; p.Z0 = Z0.p; p.Z1 = Z1.p;
         p.P0 = Pa.p; p.P1 = Pb.p; p.F0 = Fa.p; p.F1 = Fb.p; p.T = T.p; p.GaQ = GaQ.p; p.Sinv = Sinv.p;
         p.Sinvk = nullptr; p.Gn = nullptr; p.GaU = GaU.p; p.lab = lab.p;
@@ -495,7 +516,7 @@ struct SimplexSolver : SolverBase {
         { const char *e = getenv("PFDR_B200_STREAMZ"); p.stream_z = (e && e[0] == '1') ? 1 : 0; }
 
         if (sharded) { halo.setup(*q.shard, g.hkey.p, g.nslots, 2 * (size_t) E, K); halo.build(HALO_VA0 | HALO_VA1); halo.build(HALO_VA0 | HALO_Z); }
-        reset();
+        if (!(slab && link.world > 1)) reset();            // a slab-sharded solve is initialised by slab_connect (collective)
         if (!keep_p0) P0.own.release();
         PFDR_CUDA(cudaEventRecord(ev_b, st));
     }
@@ -521,9 +542,74 @@ struct SimplexSolver : SolverBase {
         h.dif = (double) (q.difTol > q.difRcd ? q.difTol : q.difRcd);
         hctl[0] = h;
         PFDR_CUDA(cudaMemcpyAsync(ctl.p, &hctl[0], sizeof(Ctl), cudaMemcpyHostToDevice, st));
+        if (slab && link.world > 1) {                          // nobody still iterates on the buffers about to be rewritten
+            PFDR_REQUIRE(link.connected, "slab-sharded solver: reset before slab_connect");
+            link.barrier();
+            link.run_id++;
+            p.slab.run_id = link.run_id;
+            if (gexec) { cudaGraphExecDestroy(gexec); gexec = nullptr; }
+        }
         launch_precond(P0.p, 0);
         if (sharded) halo.exchange(HALO_VA0 | HALO_VA1, PingPong<real>(T.p), PingPong<real>(Fa.p), PingPong<real>(), nullptr, PARITY_ZERO);
+        if (slab && link.connected && link.world > 1) slab_refresh();
         PFDR_CUDA(cudaStreamSynchronize(st));
+        if (slab && link.world > 1) slab_check();
+    }
+
+    // ghost zones of the neighbours <- this rank's boundary: metric T, forward point and cut-edge copies of the CURRENT
+    // (parity 0) buffers; afterwards every rank has everything the first trip reads
+    void slab_refresh()
+    {
+        const size_t VK = (size_t) q.V * p.K;
+        const int K = p.K, ND = dg.ND;
+        for (int side = 0; side < 2; side++) {
+            const int nb = side ? link.nb_hi : link.nb_lo;
+            if (nb < 0) continue;
+            const SlabBlob &b = link.blobs[nb];
+            const long long depth = side ? b.v0 - b.lo : b.hi - b.v1;          // its ghost zone on our side
+            const long long first = side ? p.vend - depth : p.vbeg;
+            const long long dshift = (link.lo - b.lo) * K;
+            const size_t VKn = (size_t) (b.hi - b.lo) * K;
+            link.push<real>(SLAB_T, nb, (size_t) first * K, (size_t) depth * K, dshift);
+            link.push<real>(SLAB_F0, nb, (size_t) first * K, (size_t) depth * K, dshift);
+            for (int i = 0; i < ND; i++) {                                       // copies on the cut edges of offset d_i
+                const long long d = std::min<long long>(dg.off[i], depth), f = side ? p.vend - d : p.vbeg;
+                const int plane = side ? i : ND + i;                             // our out_i copies go up, our in_i copies down
+                link.push<real>(SLAB_Z0, nb, (size_t) plane * VK + (size_t) f * K, (size_t) d * K,
+                                (long long) plane * ((long long) VKn - (long long) VK) + dshift);
+            }
+        }
+        link.barrier();
+    }
+    void slab_check()
+    {
+        int err = 0;
+        PFDR_CUDA(cudaMemcpy(&err, &link.ptr<SlabMail>(SLAB_MAILBOX)->error, sizeof(int), cudaMemcpyDeviceToHost));
+        if (err) throw Error(PFDR_B200_ERR_CUDA, "slab-sharded solve: a rank stopped answering (timed out waiting for its flag)");
+    }
+    void slab_export(void *blob) override
+    {
+        PFDR_REQUIRE(slab, "not a slab-sharded solver");
+        memset(blob, 0, PFDR_B200_SLAB_BLOB);
+        memcpy(blob, &link.mine, sizeof(SlabBlob));
+    }
+    void slab_connect(const void *blobs, bool same_process) override
+    {
+        PFDR_REQUIRE(slab, "not a slab-sharded solver");
+        std::vector<SlabBlob> all(link.world);
+        for (int r = 0; r < link.world; r++) memcpy(&all[r], (const char *) blobs + (size_t) r * PFDR_B200_SLAB_BLOB, sizeof(SlabBlob));
+        link.connect(all.data(), same_process);
+        p.slab = link.dev(); p.slab.band = dg.band();
+        for (int side = 0; side < 2; side++) {
+            const int nb = side ? link.nb_hi : link.nb_lo;
+            if (nb < 0) continue;
+            SlabPeer<real> &pe = side ? p.phi : p.plo;
+            pe.Z[0] = link.ptr<real>(SLAB_Z0, nb); pe.Z[1] = link.ptr<real>(SLAB_Z1, nb);
+            pe.F[0] = link.ptr<real>(SLAB_F0, nb); pe.F[1] = link.ptr<real>(SLAB_F1, nb);
+            pe.plane = (size_t) (link.blobs[nb].hi - link.blobs[nb].lo) * p.K;
+            pe.shift = (link.lo - link.blobs[nb].lo) * p.K;
+        }
+        if (link.world > 1) reset();                          // collective: first preconditioning, ghost zones, barrier
     }
 
     template <int L, bool PERK, int LOSS>
@@ -626,7 +712,7 @@ struct SimplexSolver : SolverBase {
         const size_t work = (size_t) nhalf * p.K;
         int batch = work > (1u << 24) ? 4 : (work > (1u << 20) ? 16 : 64);
         batch = std::max(1, std::min(batch, q.itMax + 1));
-        ctx().stats.layout = dia ? 1 : 0; ctx().stats.gpus = 1;
+        ctx().stats.layout = dia ? 1 : 0; ctx().stats.gpus = slab ? link.world : 1;
         ctx().in_loop = true;
         PFDR_CUDA(cudaEventRecord(ev_b, st));
         long long enqueued = 0, budget = (long long) q.itMax + 1 + 2LL * batch;
@@ -656,6 +742,7 @@ struct SimplexSolver : SolverBase {
         PFDR_CUDA(cudaEventElapsedTime(&ms, ev_b, ev_c));
         ctx().stats.loop_ms = ms;
         ctx().stats.iterations = hctl[0].it;
+        if (slab && link.world > 1) slab_check();
     }
 
     void fetch(void *Po, int *ito, void *Objo, void *Difo) override

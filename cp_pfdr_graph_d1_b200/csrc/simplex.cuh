@@ -3,6 +3,7 @@
 #pragma once
 #include <type_traits>
 #include "common.cuh"
+#include "slab.cuh"
 
 namespace pfdr {
 
@@ -38,6 +39,9 @@ struct SP {
     const unsigned char *dmask;   // [V]
     const int *eoff;              // [V]
     real *Wrow;                   // [2.ND * V]
+    // slab-sharded solve (slab.cuh): V counts the vertices held (owned + ghost zones), [vbeg, vend) are the owned ones
+    SlabDev slab;
+    SlabPeer<real> plo, phi;      // the ghost zones this rank writes: in the rank below / above
 };
 
 template <typename real> __device__ __forceinline__ real sabs(real a) { return a < (real) 0 ? -a : a; }
@@ -238,7 +242,8 @@ __device__ __forceinline__ VecN<real, LPT> prox_row(real rho, const VecN<real, L
 template <typename real, int LPT, bool PERK, int LOSS>
 __device__ __forceinline__ double simplex_epilogue(const SP<real> &p, Ctl *ctl, bool on, int v, int k0, size_t vk,
     VecN<real, LPT> acc, const VecN<real, LPT> &Tv, const VecN<real, LPT> &pold, real *__restrict__ Pn, real *__restrict__ Fn,
-    const VecN<real, LPT> *gaq_pre = nullptr)       // GaQ of the lane's labels when the caller fetched it ahead of time
+    const VecN<real, LPT> *gaq_pre = nullptr,       // GaQ of the lane's labels when the caller fetched it ahead of time
+    real *Fpush_lo = nullptr, real *Fpush_hi = nullptr)   // slab-sharded: where a neighbouring rank keeps this vertex's forward point
 {
     typedef VecN<real, LPT> vec;
     const int K = p.K, TPV = p.TPV;
@@ -282,6 +287,8 @@ __device__ __forceinline__ double simplex_epilogue(const SP<real> &p, Ctl *ctl, 
         }
         stv<real, LPT>(Pn + vk, pnew);
         stv<real, LPT>(Fn + vk, f);
+        if (Fpush_lo) stv<real, LPT>(Fpush_lo, f);
+        if (Fpush_hi) stv<real, LPT>(Fpush_hi, f);
     }
     double red = 0.0;
     if (p.by_label) {                                                         // ref :657-676
@@ -311,6 +318,35 @@ __device__ void simplex_finalize(const SP<real> &p, int it, double s)
     ctl->it = itn;
     if (itn == ctl->itMax || (real) dif < (real) ctl->tol) ctl->state = ST_FINAL;
     else if ((real) dif < (real) ctl->rcd) ctl->state = ST_RECOND;
+}
+
+// slab-sharded solve: what the kernel of trip `it` does before touching any data (slab.cuh).  Called by one thread of every
+// CTA; all of them (on every rank) return the same state.
+template <typename real>
+__device__ int simplex_slab_decide(const SP<real> &p, int it)
+{
+    Ctl *ctl = p.ctl;
+    if (it == 0) return ST_RUN;
+    SlabMail *me = p.slab.mail[p.slab.rank];
+    const unsigned long long target = (p.slab.run_id << 32) | (unsigned long long) it;
+    bool ok = true;
+    if (p.slab.nb_lo >= 0) ok = slab_wait(&me->sum_flag[p.slab.nb_lo], target, me) && ok;
+    if (p.slab.nb_hi >= 0) ok = slab_wait(&me->sum_flag[p.slab.nb_hi], target, me) && ok;
+    const int track = ctl->track;
+    double dif = ctl->dif;
+    if (ok && track) {
+        double s = 0.0;
+        for (int q = 0; q < p.slab.world; q++) { ok = slab_wait(&me->sum_flag[q], target, me) && ok; s += me->sums[q][0]; }   // rank order
+        dif = p.by_label ? s : s / (double) p.Vglobal;              // ref :688
+    }
+    int state = ST_RUN;
+    if (!ok || it == ctl->itMax || (real) dif < (real) ctl->tol) state = ST_FINAL;
+    else if ((real) dif < (real) ctl->rcd) state = ST_RECOND;
+    if (blockIdx.x == 0) {
+        if (track && ok) { ctl->dif = dif; if (p.dDif) p.dDif[it - 1] = (real) dif; }
+        if (state != ST_RUN) { ctl->state = state; ctl->hold = 1; }
+    }
+    return state;
 }
 
 }  // namespace pfdr

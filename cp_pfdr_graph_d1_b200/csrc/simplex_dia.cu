@@ -35,12 +35,12 @@ __global__ void __launch_bounds__(256) simplex_dia_precond_kernel(SP<real> p, co
     typedef DiaHalf<ND> H;
     const int lane = threadIdx.x & 31;
     const long long chunk = ((long long) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (chunk >= ((long long) p.V + p.C - 1) >> p.logC) return;     // whole warp leaves together
+    if (chunk >= ((long long) (p.vend - p.vbeg) + p.C - 1) >> p.logC) return;     // whole warp leaves together
     const int K = p.K, Kv = p.Kv, TPV = p.TPV;
     const int vl = lane >> p.logTPV, k0 = (lane & (TPV - 1)) * LPT;
-    const int v = (int) (chunk << p.logC) + vl;
-    const bool on = (v < p.V) && (k0 < Kv);
-    const int vs = on ? v : 0;
+    const int v = p.vbeg + (int) (chunk << p.logC) + vl;          // owned vertices only (slab-sharded: ghosts come from their owners)
+    const bool on = (v < p.vend) && (k0 < Kv);
+    const int vs = on ? v : p.vbeg;
     const size_t VK = (size_t) p.V * K, Vp = (size_t) p.V;
     const size_t vk = (size_t) vs * K + (on ? k0 : 0);
     const int cur = recond ? (p.ctl->it & 1) : 0;
@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(256) simplex_dia_precond_kernel(SP<real> p, co
 // a finished warp kept its registers idle until the slowest warp of its CTA was done.  Loads never depend on the edge
 // mask: the neighbour index is clamped into [0, V) and a half-edge that does not exist is dropped at compute time, so
 // the whole group of loads is issued as soon as the chunk number is known (which is fetched one chunk ahead).
-template <typename real, int LPT, bool PERK, int LOSS, int ND, int G, int MINB>
+template <typename real, int LPT, bool PERK, int LOSS, int ND, int G, int MINB, bool SLAB = false>
 __global__ void __launch_bounds__(256, MINB) simplex_dia_iter_kernel(SP<real> p)
 {
     typedef VecN<real, LPT> vec;
@@ -150,6 +150,12 @@ __global__ void __launch_bounds__(256, MINB) simplex_dia_iter_kernel(SP<real> p)
         return;
     }
     const int it = cv.it, cur = it & 1;
+    if (SLAB) {             // neighbours' pushes of the previous trip have landed; stop / recondition decision over all ranks
+        __shared__ int s_state;
+        if (threadIdx.x == 0) s_state = simplex_slab_decide(p, it);
+        __syncthreads();
+        if (s_state != ST_RUN) return;
+    }
     const real *__restrict__ Zin = cur ? p.Z1 : p.Z0;
     real *__restrict__ Zout = cur ? p.Z0 : p.Z1;
     const real *__restrict__ Pc = cur ? p.P1 : p.P0;
@@ -168,6 +174,7 @@ __global__ void __launch_bounds__(256, MINB) simplex_dia_iter_kernel(SP<real> p)
     const real rho = p.rho;
     const int off[3] = {p.dia_off[0], p.dia_off[1], p.dia_off[2]};
     double red = 0.0;
+    bool pushed = false;
     int idx = (int) blockIdx.x * (int) (blockDim.x >> 5) + (int) (threadIdx.x >> 5);
     int chunk_next = idx < nchunks ? (order ? __ldg(order + idx) : idx) : 0;
     for (; idx < nchunks; idx += nwarps) {                                    // warp-uniform trip count
@@ -208,14 +215,29 @@ __global__ void __launch_bounds__(256, MINB) simplex_dia_iter_kernel(SP<real> p)
                 if (h < 2 * ND && ((m >> H::mask_bit(h)) & 1u)) {
                     const vec zn = prox_row<real, LPT, PERK, LOSS>(rho, fown, pold, Tv, Sv, zo[u], zt[u], fn[u], tn[u], wvk[u], th[u], wr[u], acc);
                     stv<real, LPT>(Zout + ((size_t) H::own_plane(h) * VK + vk), zn);
+                    if (SLAB) {     // the other end belongs to the rank above / below: its twin copy lives there too
+                        if (H::out(h)) { if (v + off[H::idx(h)] >= p.vend) stv<real, LPT>(p.phi.Z[cur ^ 1] + ((size_t) H::own_plane(h) * p.phi.plane + (size_t) ((long long) vk + p.phi.shift)), zn); }
+                        else if (v - off[H::idx(h)] < p.vbeg) stv<real, LPT>(p.plo.Z[cur ^ 1] + ((size_t) H::own_plane(h) * p.plo.plane + (size_t) ((long long) vk + p.plo.shift)), zn);
+                    }
                 }
             }
         }
-        red += simplex_epilogue<real, LPT, PERK, LOSS>(p, ctl, on, v, k0, vk, acc, Tv, pold, Pn, Fn, &gaq);
+        real *flo = nullptr, *fhi = nullptr;
+        if (SLAB && on) {
+            if (p.plo.F[0] && v < p.vbeg + p.slab.band) flo = p.plo.F[cur ^ 1] + ((long long) vk + p.plo.shift);
+            if (p.phi.F[0] && v >= p.vend - p.slab.band) fhi = p.phi.F[cur ^ 1] + ((long long) vk + p.phi.shift);
+            pushed = pushed || flo || fhi;          // (a vertex with a cut edge lies within `band` of the slab's end)
+        }
+        red += simplex_epilogue<real, LPT, PERK, LOSS>(p, ctl, on, v, k0, vk, acc, Tv, pold, Pn, Fn, &gaq, flo, fhi);
     }
+    if (SLAB && pushed) __threadfence_system();             // this thread's stores into the neighbours' ghost zones
     double tot[1] = {red};
     if (grid_sum_s<1>(ctl, p.partial, tot, smem) && threadIdx.x == 0) {
-        if (p.sharded) p.sums[p.rank] = tot[0];
+        if (SLAB) {
+            ctl->it = it + 1;
+            const double v4[SLAB_NSUM] = {tot[0], 0.0, 0.0, 0.0};
+            slab_post(p.slab, v4, (unsigned long long) (it + 1));
+        } else if (p.sharded) p.sums[p.rank] = tot[0];
         else simplex_finalize(p, it, tot[0]);
     }
 }
@@ -257,6 +279,13 @@ void launch_iter_nd(const SP<real> &p, int grid)
         if (ws > 1) { PFDR_LAUNCH((simplex_dia_iter_kernel<real, LPT, PERK, LOSS, ND, G, MINB>), std::min(grid, wave * ws), 256, 0, p); return; }
     }
 #endif
+    if constexpr (!PERK) {
+        if (p.slab.on) {
+            const int w2 = resident_ctas(simplex_dia_iter_kernel<real, LPT, PERK, LOSS, ND, G, MINB, true>, 256, MINB);
+            PFDR_LAUNCH((simplex_dia_iter_kernel<real, LPT, PERK, LOSS, ND, G, MINB, true>), std::min(grid, w2), 256, 0, p);
+            return;
+        }
+    }
     PFDR_LAUNCH((simplex_dia_iter_kernel<real, LPT, PERK, LOSS, ND, G, MINB>), std::min(grid, wave), 256, 0, p);
 }
 template <typename real, int LPT, bool PERK, int LOSS>

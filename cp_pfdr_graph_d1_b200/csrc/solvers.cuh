@@ -15,6 +15,7 @@ struct QuadProblem {
     int Ltype; const real *L; real rho, condMin, difRcd, difTol;
     int itMax; int *it; real *Obj, *Dif; int verbose;
     const ShardInfo *shard = nullptr;   // non-NULL: this rank's part of a vertex-sharded problem (comm.cuh)
+    const pfdr_b200_slab *slab = nullptr;   // non-NULL: this rank's slab of a stencil graph (slab.cuh)
 };
 
 // A solver resident on the device: layout + preconditioner built once, then reset()/run() any number
@@ -24,6 +25,9 @@ struct SolverBase {
     virtual void reset() = 0;                                   // back to the initial iterate (device only)
     virtual void run() = 0;                                     // iterate until the stopping rule fires
     virtual void fetch(void *X, int *it, void *Obj, void *Dif) = 0;
+    // slab-sharded solves (slab.cuh): publish this rank's arena / attach the other ranks' (collective)
+    virtual void slab_export(void *blob) { throw Error(PFDR_B200_ERR_ARG, "not a slab-sharded solver"); }
+    virtual void slab_connect(const void *blobs, bool same_process) { throw Error(PFDR_B200_ERR_ARG, "not a slab-sharded solver"); }
 };
 template <typename real> SolverBase *make_quadratic(const QuadProblem<real> &q);
 template <typename real> void solve_quadratic(const QuadProblem<real> &q);
@@ -34,9 +38,14 @@ struct SimplexProblem {
     int K, V, E; real al; const real *La_f; real *P; const real *Q; const int *Eu, *Ev; const real *La_d1;
     real rho, condMin, difRcd, difTol; int itMax; int *it; real *Obj, *Dif; int verbose;
     const ShardInfo *shard = nullptr;
+    const pfdr_b200_slab *slab = nullptr;
 };
 template <typename real> SolverBase *make_simplex(const SimplexProblem<real> &q);
 template <typename real> void solve_simplex(const SimplexProblem<real> &q);
+
+// PFDR_B200_GPUS=N: the one-shot solves of large grid problems over N GPUs (multi.cu); false = not taken, solve on one GPU
+template <typename real> bool solve_simplex_multi(const SimplexProblem<real> &q);
+template <typename real> bool solve_quadratic_multi(const QuadProblem<real> &q);
 
 template <typename real> void proj_simplex_metric(real *X, const real *M, int D, int N, int nm, const real *A, int na);
 template <typename real> real operator_norm_matrix(int M, int N, const real *A, real nTol, int itMax, int nbInit, int verbose);

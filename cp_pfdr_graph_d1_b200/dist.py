@@ -132,6 +132,117 @@ class ShardedSimplexSolver(_Solver):
         self.setup_stats = last_stats()
 
 
+class _Slab(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("world", "rank", "Vglobal", "v0", "v1", "lo", "hi")]
+
+
+SLAB_BLOB = 256
+
+
+def exchange_blobs(mine, world, rank):
+    """all ranks' blobs, in rank order, over the default torch.distributed group (any backend)"""
+    import torch
+    import torch.distributed as dist
+    box = [None] * world
+    dist.all_gather_object(box, bytes(mine))
+    return b"".join(box)
+
+
+class _SlabSolver(_Solver):
+    def _connect(self, plan, same_process=False, blobs=None):
+        mine = (C.c_ubyte * SLAB_BLOB)()
+        self._lib.pfdr_b200_slab_export.argtypes = [C.c_void_p, C.c_void_p]
+        self._chk(self._lib.pfdr_b200_slab_export(self._h, mine))
+        self.blob = bytes(mine)
+        if blobs is None and plan.world > 1:
+            blobs = exchange_blobs(mine, plan.world, plan.rank)
+        if blobs is not None or plan.world == 1:
+            self.connect(blobs if blobs is not None else self.blob, same_process)
+
+    def connect(self, blobs, same_process=False):
+        buf = (C.c_ubyte * len(blobs)).from_buffer_copy(blobs)
+        self._lib.pfdr_b200_slab_connect.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        self._chk(self._lib.pfdr_b200_slab_connect(self._h, buf, int(same_process)))
+
+
+class SlabSimplexSolver(_SlabSolver):
+    """PFDR_graph_loss_d1_simplex on this rank's slab of a grid graph (shard.SlabPlan): halo exchange by direct stores
+    into the neighbours' memory, no collective library.  P0, Q are GLOBAL (V, K) host arrays unless local=True (then
+    rows [lo, hi), and La_d1 per local edge).  `connect=False` defers the (collective) attach: export `.blob`,
+    gather all ranks' blobs yourself and call .connect(blobs)."""
+
+    def __init__(self, plan, P0, Q, al, La_d1, La_f=None, rho=1.5, condMin=1e-2, difTol=1e-4, itMax=500,
+                 want_dif=False, local=False, connect=True, same_process=False):
+        super().__init__()
+        dt = np.dtype(P0.dtype)
+        R, suf = _CT[dt]
+        P, PI = C.POINTER(R), C.POINTER(C.c_int)
+        va = (lambda a: a) if local else plan.vertex_array
+        ea = (lambda a: a) if local else plan.edge_array
+        P0l, Ql, La_fl = (None if a is None else np.ascontiguousarray(va(a), dtype=dt) for a in (P0, Q, La_f))
+        La_d1l = np.ascontiguousarray(ea(La_d1), dtype=dt)
+        Eu, Ev = np.ascontiguousarray(plan.Eu, np.int32), np.ascontiguousarray(plan.Ev, np.int32)
+        K = int(P0l.shape[1])
+        assert P0l.shape[0] == plan.Vloc and La_d1l.shape[0] == Eu.shape[0]
+        self._keep = [P0l, Ql, La_fl, La_d1l, Eu, Ev]
+        self._dt, self._shape, self._itMax, self.plan = dt, (plan.Vown, K), itMax, plan
+        sl = _Slab(plan.world, plan.rank, plan.V_global, plan.v0, plan.v1, plan.lo, plan.hi)
+        ptr = lambda a, t=R: None if a is None else a.ctypes.data_as(C.POINTER(t))
+        f = getattr(self._lib, f"pfdr_b200_solver_create_simplex_slab_{suf}")
+        f.argtypes = [C.POINTER(C.c_void_p), C.POINTER(_Slab), C.c_int, C.c_int, C.c_int, R, P, P, P, PI, PI, P, R, R, R,
+                      R, C.c_int, C.c_int, C.c_int]
+        self._chk(f(C.byref(self._h), C.byref(sl), K, plan.Vloc, int(Eu.shape[0]), al, ptr(La_fl), ptr(P0l), ptr(Ql),
+                    ptr(Eu, C.c_int), ptr(Ev, C.c_int), ptr(La_d1l), rho, condMin, 0.0, difTol, itMax, 0, int(want_dif)))
+        self.setup_stats = last_stats()
+        if connect:
+            self._connect(plan, same_process)
+
+
+class SlabQuadraticSolver(_SlabSolver):
+    """PFDR_graph_quadratic_d1_{l1,bounds} on this rank's slab of a grid graph: A None / 1-D (N = 0) or dense N-by-V
+    (N > 0: this rank keeps the columns of its owned vertices, Y has length N).  Arrays are GLOBAL host arrays unless
+    local=True (vertex arrays then cover [lo, hi), a dense A the owned columns)."""
+
+    def __init__(self, plan, X0, Y, A, La_d1, La_l1=None, positivity=0, min=-np.inf, max=np.inf, prox="l1", Ltype=0,
+                 L=None, rho=1.5, condMin=1e-3, difTol=1e-5, itMax=1000, want_dif=False, local=False, N=None,
+                 connect=True, same_process=False):
+        super().__init__()
+        from ._abi import _real_dtype, _ptr
+        dt = _real_dtype(X0)
+        R, suf = _CT[dt]
+        P, PI = C.POINTER(R), C.POINTER(C.c_int)
+        dense = A is not None and len(A.shape) == 2
+        if N is None:
+            N = int(A.shape[0]) if dense else 0
+        if local:
+            X0l, Yl, Al, La_l1l, Ll, La_d1l = X0, Y, A, La_l1, L, La_d1
+        else:
+            va, ea = plan.vertex_array, plan.edge_array
+            X0l, La_l1l = (None if a is None else np.ascontiguousarray(va(a), dtype=dt) for a in (X0, La_l1))
+            if dense:
+                Yl = np.ascontiguousarray(Y, dtype=dt)
+                Al = np.asfortranarray(np.asarray(A)[:, plan.v0:plan.v1], dtype=dt)
+            else:
+                Yl = np.ascontiguousarray(va(Y), dtype=dt)
+                Al = None if A is None else np.ascontiguousarray(va(A), dtype=dt)
+            Ll = None if L is None else (np.ascontiguousarray(L, dtype=dt) if Ltype == 0 else np.ascontiguousarray(va(L), dtype=dt))
+            La_d1l = np.ascontiguousarray(ea(La_d1), dtype=dt)
+        Eu, Ev = np.ascontiguousarray(plan.Eu, np.int32), np.ascontiguousarray(plan.Ev, np.int32)
+        self._keep = [X0l, Yl, Al, La_l1l, Ll, La_d1l, Eu, Ev]
+        self._dt, self._shape, self._itMax, self.plan = dt, (plan.Vown,), itMax, plan
+        sl = _Slab(plan.world, plan.rank, plan.V_global, plan.v0, plan.v1, plan.lo, plan.hi)
+        f = getattr(self._lib, f"pfdr_b200_solver_create_quadratic_slab_{suf}")
+        f.argtypes = [C.POINTER(C.c_void_p), C.POINTER(_Slab), C.c_int, C.c_int, C.c_int, C.c_int, P, P, P, PI, PI, P, P,
+                      C.c_int, R, R, C.c_int, P, R, R, R, R, C.c_int, C.c_int, C.c_int]
+        self._chk(f(C.byref(self._h), C.byref(sl), 0 if prox == "l1" else 1, plan.Vloc, int(Eu.shape[0]), int(N),
+                    _ptr(X0l, R), _ptr(Yl, R), _ptr(Al, R), _ptr(Eu, C.c_int), _ptr(Ev, C.c_int), _ptr(La_d1l, R),
+                    _ptr(La_l1l, R), int(positivity), float(min), float(max), int(Ltype), _ptr(Ll, R), rho, condMin, 0.0,
+                    difTol, itMax, 0, int(want_dif)))
+        self.setup_stats = last_stats()
+        if connect:
+            self._connect(plan, same_process)
+
+
 def gather_owned(local, plan):
     """all ranks' owned parts -> the global array (on every rank)"""
     import torch.distributed as dist

@@ -1,9 +1,16 @@
 """bench.py under torchrun (WORLD_SIZE > 1): the same workload, vertex-sharded over the ranks (strong scaling).
-Each rank builds the seeded global problem on the host, keeps its slab (shard.make_plan), creates a sharded
-solver and runs the same steps; time is the max over ranks of the CUDA-event time of the timed region."""
+
+Grid workloads (C2, C4 - every BASELINE config that shards but the dense one) run slab-sharded (csrc/slab.cuh): the
+iteration kernel of a rank stores its boundary forward points and cut-edge copies straight into the neighbours' memory
+over NVLink, one flag per rank pair and iteration; torch.distributed only carries the 256-byte arena descriptors at
+set-up.  The dense-operator workloads (C5) use the NCCL halo engine (csrc/comm.cu).  Time = max over ranks of the
+CUDA-event time of the timed region.  During warm-up rank 0 also solves the SAME problem unsharded on its own GPU and
+the line carries `parity_vs_1gpu`: relative error of the gathered sharded iterate against it (0 expected: the sharded
+arithmetic is the single-GPU arithmetic; only the stopping sums - unused here, difTol = 0 - are associated differently)."""
 import json
 import os
 import sys
+import time
 
 import numpy as np
 
@@ -18,39 +25,41 @@ def main(args):
 
     world, rank, local = int(os.environ["WORLD_SIZE"]), int(os.environ["RANK"]), int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
     stream = torch.cuda.Stream()
     api.set_stream(stream.cuda_stream)
-    pd.init_comm(local)
+    api._lib.load().pfdr_b200_set_device(local)
 
     name = args.workload
     kind, n, dt, K, iters = B.WORKLOADS[name]
     iters = args.iters or iters
     r = np.dtype(dt).itemsize
-    Ndense = 0
+    tdt = torch.float32 if dt is np.float32 else torch.float64
+    Ndense, slab = 0, kind in ("quad", "simplex")
+    if kind == "ata":
+        raise SystemExit("AtA problems do not shard (DESIGN.md section 6): run this workload with --gpus 1")
     if kind == "dense":
-        w = B.device_slab_dense(n, 256, dt, world, rank, torch.device("cuda", local))
+        pd.init_comm(local)
+        w = B.device_slab_dense(n, 256, dt, world, rank, dev)
         plan, V, E, Ndense = w["plan"], w["V"], w["E"], w["N"]
         torch.cuda.synchronize()
-        solver = pd.ShardedQuadraticSolver(plan, w["X0"], w["Y"], w["A"], w["La_d1"], None, 0, Ltype=0, L=w["L"], rho=1.0,
-                                           condMin=1e-3, difTol=0.0, itMax=iters, local=True, N=Ndense)
-    elif kind == "ata":
-        raise SystemExit("AtA problems do not shard (DESIGN.md section 6): run this workload with --gpus 1")
-    elif n > 128 and kind == "simplex":
-        w = B.grid_slab_simplex(n, K, dt, world, rank)            # slab generated directly (no global arrays)
+        mk = lambda: pd.ShardedQuadraticSolver(plan, w["X0"], w["Y"], w["A"], w["La_d1"], None, 0, Ltype=0, L=w["L"], rho=1.0,
+                                               condMin=1e-3, difTol=0.0, itMax=iters, local=True, N=Ndense)
+    elif kind == "simplex":
+        w = B.grid_slab_simplex(n, K, dt, world, rank)            # this rank's planes only (no global arrays)
         plan, V, E = w["plan"], w["V"], w["E"]
-        solver = pd.ShardedSimplexSolver(plan, w["Q"], w["Q"], 0.05, w["La_d1"], rho=1.5, condMin=1e-2, difTol=0.0,
-                                         itMax=iters, local=True)
+        mk = lambda: pd.SlabSimplexSolver(plan, w["Q"], w["Q"], 0.05, w["La_d1"], rho=1.5, condMin=1e-2, difTol=0.0,
+                                          itMax=iters, local=True)
     else:
-        w = B.host_inputs(name)
-        V, E = int(w["V"]), int(w["E"])
-        plan = shard.make_plan(V, w["Eu"], w["Ev"], world, rank)
-        if kind == "quad":
-            solver = pd.ShardedQuadraticSolver(plan, np.zeros(V, dt), w["Ys"], w["La_l2"], w["La_d1"], None, 0, Ltype=1,
-                                               L=w["La_l2"], rho=1.5, condMin=1e-3, difTol=0.0, itMax=iters)
-        else:
-            solver = pd.ShardedSimplexSolver(plan, w["Q"], w["Q"], 0.05, w["La_d1"], rho=1.5, condMin=1e-2, difTol=0.0,
-                                             itMax=iters)
+        g = B.host_inputs(name)
+        V, E = int(g["V"]), int(g["E"])
+        plan = shard.make_slab_plan(V, g["Eu"], g["Ev"], world, rank)
+        w = dict(X0=np.zeros(plan.Vloc, dt), Ys=plan.vertex_array(g["Ys"]), La_l2=plan.vertex_array(g["La_l2"]),
+                 La_d1=plan.edge_array(g["La_d1"]))
+        mk = lambda: pd.SlabQuadraticSolver(plan, w["X0"], w["Ys"], w["La_l2"], w["La_d1"], None, 0, Ltype=1, L=w["La_l2"],
+                                            rho=1.5, condMin=1e-3, difTol=0.0, itMax=iters, local=True, N=0)
+    solver = mk()
     B_iter = B.algorithmic_bytes(kind, V, E, r, K, N=Ndense)
 
     def step():
@@ -60,8 +69,48 @@ def main(args):
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize()
+
+    # ---- correctness of the sharded solve: against the unsharded solve of the same problem on rank 0's GPU ----
+    parity = None
+    if slab:
+        bounds = shard.slab_bounds_aligned(V, plan.band, world)
+
+        def gather_to0(t):                                   # rows of every rank's owned range -> rank 0 (sizes differ)
+            if rank != 0:
+                dist.send(t.contiguous(), 0)
+                return None
+            out = [t]
+            for q in range(1, world):
+                buf = torch.empty((int(bounds[q + 1] - bounds[q]),) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
+                dist.recv(buf, q)
+                out.append(buf)
+            return out
+
+        parts = gather_to0(torch.from_numpy(np.ascontiguousarray(solver.fetch().X)).to(dev))
+        if kind == "simplex":
+            qparts = gather_to0(torch.from_numpy(np.ascontiguousarray(plan.owned(w["Q"]))).to(dev))
+        if rank == 0:
+            got = torch.cat(parts)
+            if kind == "simplex":
+                Qg = torch.cat(qparts)
+                del qparts
+                Eu, Ev = B.device_grid_edges(n, dev)
+                La = torch.full((Eu.shape[0],), 0.2, device=dev, dtype=tdt)
+                torch.cuda.synchronize()
+                one = api.SimplexSolver(Qg, Qg, 0.05, Eu, Ev, La, None, rho=1.5, condMin=1e-2, difRcd=0.0, difTol=0.0, itMax=iters)
+            else:
+                one = api.QuadraticSolver(np.zeros(V, dt), g["Ys"], g["La_l2"], g["Eu"], g["Ev"], g["La_d1"], None, 0, Ltype=1,
+                                          L=g["La_l2"], rho=1.5, condMin=1e-3, difRcd=0.0, difTol=0.0, itMax=iters, N=0)
+            one.run()
+            ref = torch.from_numpy(one.fetch().X).to(dev)
+            one.close()
+            parity = float((got - ref).double().norm() / ref.double().norm())
+            del got, ref, parts
+            torch.cuda.empty_cache()
+    torch.cuda.synchronize()
     dist.barrier()
     torch.cuda.synchronize()
+
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     loop_ms = launches = its = 0
     with B.ClockSampler(local) as clk:
@@ -77,21 +126,15 @@ def main(args):
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, loop_ms_max = float(t[0]), float(t[1])
 
-    # end to end at N GPUs: every rank builds its sharded solver from HOST (pinned) local arrays - upload, half-edge
-    # layout, preconditioning - iterates and reads its part of the iterate back; max over ranks of the wall time
+    # end to end at N GPUs: every rank builds its sharded solver from HOST (pinned) arrays of its slab - upload, layout,
+    # preconditioning, attach - iterates and reads its part of the iterate back; max over ranks of the wall time
     e2e = None
-    if kind in ("quad", "simplex") and not (n > 128 and kind == "simplex" and world < 2):
-        import time
+    if slab and not args.no_e2e:
         solver.close()
         pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
-        if kind == "quad":
-            loc = [pin(plan.vertex_array(a)) for a in (np.zeros(V, dt), w["Ys"], w["La_l2"])] + [pin(plan.edge_array(w["La_d1"]))]
-            mk = lambda: pd.ShardedQuadraticSolver(plan, loc[0], loc[1], loc[2], loc[3], None, 0, Ltype=1, L=loc[2], rho=1.5,
-                                                   condMin=1e-3, difTol=0.0, itMax=iters, local=True, N=0)
-        else:
-            Ql = pin(w["Q"] if n > 128 else plan.vertex_array(w["Q"]))
-            Ld = pin(w["La_d1"] if n > 128 else plan.edge_array(w["La_d1"]))
-            mk = lambda: pd.ShardedSimplexSolver(plan, Ql, Ql, 0.05, Ld, rho=1.5, condMin=1e-2, difTol=0.0, itMax=iters, local=True)
+        for k in list(w):
+            if isinstance(w[k], np.ndarray):
+                w[k] = pin(w[k])
         times, h2d, d2h = [], 0, 0
         for i in range(4):                                   # first two: warm-up (memory pool growth)
             dist.barrier()
@@ -110,7 +153,7 @@ def main(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e = {"value": E * iters / float(te[0]), "unit": "edge_updates/s", "h2d_bytes_per_step": int(te[1]),
                "d2h_bytes_per_step": int(te[2]), "ms_per_step": 1e3 * float(te[0]),
-               "what": "per rank: sharded solver built from pinned host arrays of its shard, run, owned iterate read back; "
+               "what": "per rank: slab solver built from pinned host arrays of its slab, attached, run, owned iterate read back; "
                        "max over ranks (h2d/d2h: largest rank)"}
         solver = None
     if rank == 0:
@@ -118,26 +161,27 @@ def main(args):
         value = E * its / (ms * 1e-3)
         peak, peak_src = B.peaks()
         achieved = B_iter * its / (loop_ms_max * 1e-3) / 1e9
-        halo_bytes = sum((nb.send_vertices.shape[0] + nb.send_halfedges.shape[0]) for nb in plan.neighbors) * K * r
+        par = (f"vertex slabs x{world}: halo (boundary forward points + cut-edge copies) stored by the iteration kernel into the "
+               "neighbours' memory over NVLink (CUDA IPC), one flag per rank pair and iteration, no collective on the data path"
+               if slab else f"vertex shards x{world}, dense A by columns: NCCL halo exchange + all-reduce of A x and of the stopping scalars")
         line = {
             "metric": "pfdr_edge_updates_per_s", "value": value, "unit": "edge_updates/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32" if dt is np.float32 else "f64", "data": "synthetic",
-            "config": {"workload": B.describe(name), "V": V, "E": E, "K": K, "iterations_per_step": iters,
-                       "us_per_iteration": 1e3 * loop_ms_max / its, "parallelism": f"vertex slabs x{world}, NCCL halo "
-                       "exchange (boundary forward points + cut-edge copies) + all-reduce of the stopping scalars",
-                       "halo_bytes_per_iteration_rank0": int(halo_bytes),
-                       "l2": "no flush: steps re-run the same resident problem"},
+            "config": B.static_config(name, iters),
+            "detail": {"us_per_iteration": 1e3 * loop_ms_max / its, "parallelism": par, "parity_vs_1gpu": parity,
+                       "edge_label_updates_per_s": value * K},
+            "parity_vs_1gpu": parity,
             "gpu_launches": int(t[2]),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak * world, "unit": "GB/s",
                          "frac": achieved / (peak * world), "traffic": None, "peak_source": peak_src + f" x {world} GPUs",
-                         "kernel": {"quad": "quad_iter_pipe_kernel", "simplex": "simplex_iter_kernel",
-                                    "dense": "ax_partial_kernel + atr_kernel"}[kind],
+                         "kernel": B.KERNEL_NAMES[kind],
                          "algorithmic_bytes_per_launch": B_iter / world, "avg_launch_us": 1e3 * loop_ms_max / its},
             "e2e": e2e, "clocks": clk.summary(),
         }
         print(json.dumps(line), flush=True)
     if solver is not None:
         solver.close()
-    pd.destroy_comm()
+    if kind == "dense":
+        pd.destroy_comm()
     dist.destroy_process_group()

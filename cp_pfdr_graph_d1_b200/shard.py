@@ -106,3 +106,84 @@ def make_plan_local(V, Eu, Ev, world, rank, bounds=None):
     """as make_plan, but Eu/Ev hold only the edges touching this rank (global vertex ids, in global edge order):
     for problems too large to enumerate every edge on every rank.  edge_ids are then positions in that list."""
     return make_plan(V, Eu, Ev, world, rank, bounds)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# slab sharding of constant-offset (grid) graphs: csrc/slab.cuh.  Rank r owns the contiguous range [v0, v1) and
+# holds every vertex array over [lo, hi) = [v0 - band, v1 + band) clipped to the graph, numbered from lo - the local
+# graph is again a constant-offset graph with the same offsets, so the index-free kernels run on it unchanged and a
+# neighbour's ghost zone is a contiguous range of each array.
+# ---------------------------------------------------------------------------------------------------------------
+@dataclass
+class SlabPlan:
+    rank: int
+    world: int
+    V_global: int
+    band: int
+    v0: int
+    v1: int
+    lo: int
+    hi: int
+    Eu: np.ndarray                # local edge list (vertex numbers relative to lo, int32), global order
+    Ev: np.ndarray
+    edge_ids: np.ndarray          # positions of the local edges in the edge list the plan was made from
+
+    @property
+    def Vown(self):
+        return self.v1 - self.v0
+
+    @property
+    def Vloc(self):
+        return self.hi - self.lo
+
+    def vertex_array(self, a):
+        """rows [lo, hi) of a global per-vertex array (the ghost rows are carried but never read)"""
+        return None if a is None else np.ascontiguousarray(np.asarray(a)[self.lo:self.hi])
+
+    def edge_array(self, a):
+        return None if a is None else np.ascontiguousarray(np.asarray(a)[self.edge_ids])
+
+    def owned(self, a_local):
+        return a_local[self.v0 - self.lo:self.v1 - self.lo]
+
+
+def slab_bounds_aligned(V, band, world):
+    """contiguous ranges whose boundaries are multiples of `band` (whole z-planes of a grid) when there are enough planes"""
+    planes = V // band if band > 0 and V % band == 0 else 0
+    if planes >= 2 * world:
+        return np.array([band * ((planes * r) // world) for r in range(world + 1)], dtype=np.int64)
+    return slab_bounds(V, world)
+
+
+def make_slab_plan(V, Eu, Ev, world, rank, bounds=None):
+    """Eu < Ev in vertex-major order (the numbering the stencil layout needs); Eu/Ev may hold only the edges that
+    touch this rank's range (global vertex numbers, global order)"""
+    Eu = np.asarray(Eu, dtype=np.int64)
+    Ev = np.asarray(Ev, dtype=np.int64)
+    band = int((Ev - Eu).max()) if Eu.shape[0] else 1
+    bounds = slab_bounds_aligned(V, band, world) if bounds is None else np.asarray(bounds, dtype=np.int64)
+    v0, v1 = int(bounds[rank]), int(bounds[rank + 1])
+    lo, hi = max(v0 - band, 0), min(v1 + band, int(V))
+    if world > 1 and (bounds[1:] - bounds[:-1]).min() < band:
+        raise ValueError("slab sharding: a rank's range is thinner than the band of the graph (too many ranks)")
+    mine = ((Eu >= v0) & (Eu < v1)) | ((Ev >= v0) & (Ev < v1))
+    eids = np.nonzero(mine)[0]
+    return SlabPlan(rank, world, int(V), band, v0, v1, lo, hi, (Eu[eids] - lo).astype(np.int32), (Ev[eids] - lo).astype(np.int32), eids)
+
+
+def grid_slab_plan(n, world, rank, nz=None):
+    """slab plan of the n x n x nz grid of synth.grid_graph built from this rank's planes only (no global edge list)"""
+    nz = n if nz is None else nz
+    V, band = n * n * nz, n * n
+    b = slab_bounds_aligned(V, band, world)
+    v0, v1 = int(b[rank]), int(b[rank + 1])
+    lo, hi = max(v0 - band, 0), min(v1 + band, V)
+    g = np.arange(lo, hi, dtype=np.int64)
+    z, y, x = g // band, (g // n) % n, g % n
+    eu, ev = [], []
+    for ok, d in ((x < n - 1, 1), (y < n - 1, n), (z < nz - 1, band)):
+        eu.append(np.where(ok, g, -1)); ev.append(np.where(ok, g + d, -1))
+    Eu, Ev = np.stack(eu, 1).reshape(-1), np.stack(ev, 1).reshape(-1)
+    keep = (Eu >= 0) & (Ev < hi) & (((Eu >= v0) & (Eu < v1)) | ((Ev >= v0) & (Ev < v1)))
+    Eu, Ev = Eu[keep], Ev[keep]
+    return SlabPlan(rank, world, V, band, v0, v1, lo, hi, (Eu - lo).astype(np.int32), (Ev - lo).astype(np.int32), None)

@@ -149,6 +149,34 @@ int pfdr_b200_solver_create_simplex_sharded_f64(pfdr_b200_solver **out, const pf
     int E, double al, const double *La_f, const double *P0, const double *Q, const int *Eu, const int *Ev,
     const double *La_d1, double rho, double condMin, double difRcd, double difTol, int itMax, int want_obj, int want_dif);
 
+/* ---- slab-sharded solves of grid (constant-offset) graphs: peer-memory halo exchange, no collective library ----
+ * Rank r of `world` owns the contiguous global vertex range [v0, v1) and is given every vertex array over
+ * [lo, hi) = [v0 - band, v1 + band) clipped to [0, Vglobal) (band = largest edge offset, n^2 on an n^3 grid; the values
+ * of the ghost rows are not read), the edges with at least one owned end in GLOBAL order with vertex numbers relative
+ * to lo, and their weights.  Create the solver on every rank, exchange the PFDR_B200_SLAB_BLOB-byte blobs of
+ * pfdr_b200_slab_export (any transport: torch.distributed, MPI, a file ...), hand the table of all ranks' blobs to
+ * pfdr_b200_slab_connect, then reset / run / fetch collectively.  Ranks live in separate processes (CUDA IPC) or in
+ * one process (same_process = 1, peer access); each on its OWN GPU - their kernels wait on one another.
+ * fetch returns the owned rows.  Replaces nothing in the reference (which has no distributed mode). */
+#define PFDR_B200_SLAB_BLOB 256
+typedef struct { int world, rank, Vglobal, v0, v1, lo, hi; } pfdr_b200_slab;
+int pfdr_b200_solver_create_simplex_slab_f32(pfdr_b200_solver **out, const pfdr_b200_slab *slab, int K, int Vloc, int Eloc,
+    float al, const float *La_f, const float *P0, const float *Q, const int *Eu, const int *Ev, const float *La_d1,
+    float rho, float condMin, float difRcd, float difTol, int itMax, int want_obj, int want_dif);
+int pfdr_b200_solver_create_simplex_slab_f64(pfdr_b200_solver **out, const pfdr_b200_slab *slab, int K, int Vloc, int Eloc,
+    double al, const double *La_f, const double *P0, const double *Q, const int *Eu, const int *Ev, const double *La_d1,
+    double rho, double condMin, double difRcd, double difTol, int itMax, int want_obj, int want_dif);
+int pfdr_b200_solver_create_quadratic_slab_f32(pfdr_b200_solver **out, const pfdr_b200_slab *slab, int prox_kind, int Vloc,
+    int Eloc, int N, const float *X0, const float *Y, const float *A, const int *Eu, const int *Ev, const float *La_d1,
+    const float *La_l1, int positivity, float lo, float hi, int Ltype, const float *L, float rho, float condMin,
+    float difRcd, float difTol, int itMax, int want_obj, int want_dif);
+int pfdr_b200_solver_create_quadratic_slab_f64(pfdr_b200_solver **out, const pfdr_b200_slab *slab, int prox_kind, int Vloc,
+    int Eloc, int N, const double *X0, const double *Y, const double *A, const int *Eu, const int *Ev, const double *La_d1,
+    const double *La_l1, int positivity, double lo, double hi, int Ltype, const double *L, double rho, double condMin,
+    double difRcd, double difTol, int itMax, int want_obj, int want_dif);
+int pfdr_b200_slab_export(pfdr_b200_solver *s, void *blob);                              /* PFDR_B200_SLAB_BLOB bytes out */
+int pfdr_b200_slab_connect(pfdr_b200_solver *s, const void *blobs, int same_process);    /* world x PFDR_B200_SLAB_BLOB in */
+
 /* ---- run-time controls and introspection (no counterpart in the reference) ----------------- */
 const char *pfdr_b200_last_error(void);      /* message of the last non-zero status (thread local) */
 int pfdr_b200_version(void);
