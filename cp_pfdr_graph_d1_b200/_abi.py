@@ -23,22 +23,45 @@ class PfdrError(RuntimeError):
     pass
 
 
+_NP_OF = {C.c_float: np.float32, C.c_double: np.float64, C.c_int: np.int32}
+
+
 def _ptr(a, ctype):
-    """host numpy array / torch cuda tensor / None -> pointer argument"""
+    """host numpy array / torch cuda tensor / None -> pointer argument.  The array must already have the element type the
+    C signature expects and be contiguous: a pointer to anything else would be reinterpreted silently."""
     if a is None:
         return None
+    want = np.dtype(_NP_OF[ctype])
     if isinstance(a, np.ndarray):
+        if a.dtype != want:
+            raise TypeError(f"array of {a.dtype} where the C signature takes {want}")
+        if not (a.flags.c_contiguous or a.flags.f_contiguous):
+            raise TypeError("array must be contiguous (C- or Fortran-ordered)")
         return a.ctypes.data_as(C.POINTER(ctype))
     if hasattr(a, "data_ptr"):          # torch tensor (device pointers are accepted by libpfdr_b200 only)
+        import torch
+        tdt = {np.dtype(np.float32): torch.float32, np.dtype(np.float64): torch.float64, np.dtype(np.int32): torch.int32}[want]
+        if a.dtype != tdt:
+            raise TypeError(f"tensor of {a.dtype} where the C signature takes {want}")
+        if not a.is_cuda:
+            raise TypeError("torch tensors must live on a CUDA device (pass numpy arrays for host data)")
+        if not (a.is_contiguous() or a.t().is_contiguous()):
+            raise TypeError("tensor must be contiguous")
         return C.cast(C.c_void_p(a.data_ptr()), C.POINTER(ctype))
     raise TypeError(f"unsupported array type {type(a)}")
 
 
 def _real_dtype(a):
     if isinstance(a, np.ndarray):
+        if a.dtype not in _CT:
+            raise TypeError(f"the in/out array must be float32 or float64, not {a.dtype}")
         return a.dtype
     import torch
-    return np.dtype(np.float32) if a.dtype == torch.float32 else np.dtype(np.float64)
+    if a.dtype == torch.float32:
+        return np.dtype(np.float32)
+    if a.dtype == torch.float64:
+        return np.dtype(np.float64)
+    raise TypeError(f"the in/out tensor must be float32 or float64, not {a.dtype}")
 
 
 def _as_real(a, dt):
@@ -87,6 +110,8 @@ class Binder:
         dt = _real_dtype(X)
         R, suf = _CT[dt]
         P, PI = C.POINTER(R), C.POINTER(C.c_int)
+        if isinstance(X, np.ndarray) and not X.flags.c_contiguous:
+            raise TypeError("X is updated in place: it must be a C-contiguous array")
         V = int(X.shape[0])
         E = int(Eu.shape[0])
         Y, A, La_d1, L = (_as_real(a, dt) for a in (Y, A, La_d1, L))
@@ -131,6 +156,8 @@ class Binder:
         dt = _real_dtype(P)
         R, suf = _CT[dt]
         PR, PI = C.POINTER(R), C.POINTER(C.c_int)
+        if isinstance(P, np.ndarray) and not P.flags.c_contiguous:
+            raise TypeError("P is updated in place: it must be a C-contiguous (V, K) array")
         V, K = int(P.shape[0]), int(P.shape[1])
         E = int(Eu.shape[0])
         Q, La_d1, La_f = (_as_rows(a, dt) for a in (Q, La_d1, La_f))

@@ -20,7 +20,6 @@ cudaStream_t own_stream()
     return s;
 }
 
-static thread_local bool g_user_stream = false;
 static thread_local pfdr_b200_stats g_last_stats{};
 
 template <typename F>
@@ -34,9 +33,10 @@ static int guarded(F &&f)
             throw Error(PFDR_B200_ERR_CUDA, std::string("no usable CUDA device (libpfdr_b200 has no CPU fallback): ") +
                                                 cudaGetErrorString(e));
         if (c.device >= 0) PFDR_CUDA(cudaSetDevice(c.device));
-        if (!g_user_stream) c.stream = own_stream();
+        if (!c.user_stream) c.stream = own_stream();
         c.stats = pfdr_b200_stats{};
         c.in_loop = false;
+        c.ordered = false;
         const auto t0 = std::chrono::steady_clock::now();
         f();
         c.stats.total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
@@ -64,7 +64,7 @@ int pfdr_b200_set_device(int device) { ctx().device = device; return PFDR_B200_O
 int pfdr_b200_set_stream(void *s)
 {
     ctx().stream = (cudaStream_t) s;
-    g_user_stream = (s != nullptr);
+    ctx().user_stream = (s != nullptr);
     return PFDR_B200_OK;
 }
 int pfdr_b200_get_last_stats(pfdr_b200_stats *out) { if (!out) return PFDR_B200_ERR_ARG; *out = g_last_stats; return PFDR_B200_OK; }

@@ -43,6 +43,8 @@ struct Context {
     cudaStream_t stream = 0;
     pfdr_b200_stats stats{};
     bool in_loop = false;
+    bool user_stream = false;      // the stream was given by pfdr_b200_set_stream (else: library-owned, non-blocking)
+    bool ordered = false;          // this call has already been ordered after the caller's default-stream work
     void count_launch() { stats.launches++; if (in_loop) stats.loop_launches++; }
 };
 Context &ctx();
@@ -155,6 +157,26 @@ struct DevBuf {
     operator T *() const { return p; }
 };
 
+inline bool is_device_ptr(const void *q);
+
+// A device pointer handed in by the caller may still be written by work the caller enqueued.  The library runs on its
+// own non-blocking stream unless pfdr_b200_set_stream gave it the caller's: order that stream after everything
+// enqueued so far on the legacy default stream (which itself waits for all blocking streams) - the stream a
+// torch / CUDA runtime user produces data on unless they say otherwise.  (pfdr_b200.h: producers on other
+// non-blocking streams must pass that stream with pfdr_b200_set_stream or synchronise it.)
+inline void order_after_caller()
+{
+    Context &c = ctx();
+    if (c.user_stream || c.ordered) return;
+    c.ordered = true;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(c.stream, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) { cudaGetLastError(); return; }
+    cudaEvent_t e = event_get();
+    PFDR_CUDA(cudaEventRecord(e, cudaStreamLegacy));
+    PFDR_CUDA(cudaStreamWaitEvent(c.stream, e, 0));
+    event_put(e);
+}
+
 inline bool is_device_ptr(const void *q)
 {
     if (!q) return false;
@@ -172,7 +194,7 @@ struct DevIn {
     DevBuf<T> own;
     void bind(const T *src, size_t count) {
         if (!src || !count) { p = nullptr; return; }
-        if (is_device_ptr(src)) { p = src; return; }
+        if (is_device_ptr(src)) { order_after_caller(); p = src; return; }
         own.alloc(count);
         PFDR_CUDA(cudaMemcpyAsync(own.p, src, count * sizeof(T), cudaMemcpyHostToDevice, ctx().stream));
         ctx().stats.h2d_bytes += (long long) (count * sizeof(T));
@@ -336,6 +358,37 @@ __device__ __forceinline__ bool grid_sum_fast(Ctl *ctl, double *partial, real (&
     if (threadIdx.x == 0) ctl->ticket = 0;
     return true;
 }
+
+// `verbose` of the reference (src/PFDR_graph_quadratic_d1_l1.cpp:43-55, :425-428): a progress message every `verbose`
+// iterations - iteration count, and the evolution measure with its thresholds when it is monitored.  The host sees the
+// device's control block one batch of iterations behind, so the lines of a batch appear together; the evolution value
+// of each reported iteration comes from the per-iteration record on the device (kept whenever verbose > 0).
+struct ProgressPrinter {
+    int every = 0, next = 0;
+    cudaStream_t side = nullptr;
+    ~ProgressPrinter() { if (side) cudaStreamDestroy(side); }
+    void start(int verbose) { every = verbose > 0 ? verbose : 0; next = every; }
+    template <typename real>
+    void upto(int it_done, int itMax, const real *dDif, bool track, double tol, double rcd)
+    {
+        if (!every || it_done < next) return;
+        const int first = next, count = (it_done - first) / every + 1;
+        std::vector<real> vals;
+        if (track && dDif) {          // completed iterations only: their record is final, whatever is still queued
+            if (!side) PFDR_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+            vals.resize((size_t) it_done - first + 1);
+            PFDR_CUDA(cudaMemcpyAsync(vals.data(), dDif + (first - 1), vals.size() * sizeof(real), cudaMemcpyDeviceToHost, side));
+            PFDR_CUDA(cudaStreamSynchronize(side));
+        }
+        for (int k = 0; k < count; k++) {
+            const int it = first + k * every;
+            printf("iteration %d (max. %d)\n", it, itMax);
+            if (!vals.empty()) printf("iterate evolution %g (recond. %g; tol. %g)\n", (double) vals[(size_t) k * every], rcd, tol);
+        }
+        fflush(stdout);
+        next = first + count * every;
+    }
+};
 
 template <typename real> struct Pair;
 template <> struct Pair<float> { typedef float2 type; };

@@ -1352,6 +1352,7 @@ struct QuadSolver : SolverBase {
     Ctl *hctl = nullptr;            // pinned mirror of the control block, one per batch in flight
     cudaEvent_t ev[2]{}, ev_a{}, ev_b{}, ev_c{};
     cudaGraphExec_t gexec = nullptr;
+    ProgressPrinter progress;
     int graph_trips = 0;
     int vec = 1, TX = 1, GL = 1, vgrid = 0;
     size_t ax_smem = 0;
@@ -1434,7 +1435,7 @@ struct QuadSolver : SolverBase {
         if (N != 0) G.alloc(V);
         if (N > 0) { R.alloc(N); AtY.alloc(V); rsum.alloc(N); p.rsum = rsum.p; }
         if (q.Obj) dObj.alloc((size_t) q.itMax + 1);
-        if (q.Dif) dDif.alloc((size_t) std::max(q.itMax, 1));
+        if (q.Dif || q.verbose > 0) dDif.alloc((size_t) std::max(q.itMax, 1));
         vgrid = (int) cdiv(V, 256);
         ogrid = sharded ? (int) cdiv(q.shard->Vown, 256) : (slab ? (int) cdiv(q.slab->v1 - q.slab->v0, 256) : vgrid);
         ctl.alloc(1); sums.alloc(2 * (size_t) std::max(1, comm().world)); sums.zero(); amp_sums.alloc(2);
@@ -1867,6 +1868,7 @@ struct QuadSolver : SolverBase {
         PFDR_CUDA(cudaEventRecord(ev_b, st));
         // Pipelined: batch k is enqueued before the verdict of batch k-1 is read, so the GPU never
         // idles on the host.  Launches enqueued after the device froze are no-ops.
+        progress.start(q.verbose);
         long long enqueued = 0, budget = (long long) q.itMax + 1 + 2LL * batch;
         int fresh_from = 0;             // batches older than this predate the last reconditioning
         for (int k = 0;; k++) {
@@ -1877,6 +1879,8 @@ struct QuadSolver : SolverBase {
             int verdict = 0;
             if (k >= 1 && k - 1 >= fresh_from) verdict = inspect((k - 1) & 1);
             if (verdict == 0 && enqueued >= budget) verdict = (k >= fresh_from) ? inspect(k & 1) : 0;
+            if (progress.every && k >= 1 && k - 1 >= fresh_from)
+                progress.upto(hctl[(k - 1) & 1].it, q.itMax, dDif.p, hctl[(k - 1) & 1].track != 0, hctl[(k - 1) & 1].tol, hctl[(k - 1) & 1].rcd);
             if (verdict == 1) break;
             if (verdict == 2) {         // frozen for a reconditioning; batches <= k were no-ops past the freeze
                 PFDR_CUDA(cudaStreamSynchronize(st));
@@ -1929,9 +1933,10 @@ struct QuadSolver : SolverBase {
         if (cudaEventElapsedTime(&ms, ev_b, ev_c) == cudaSuccess) ctx().stats.loop_ms = ms;
         cudaGetLastError();
         ctx().stats.iterations = h.it;
-        if (q.verbose) {
-            printf("PFDR (B200): %d iterations (max. %d), iterate evolution %g, loop %.3f ms\n", h.it, q.itMax,
-                   h.dif, ctx().stats.loop_ms);
+        if (q.verbose) {                                                       // final information (ref :535-539)
+            printf("iteration %d (max. %d)\n", h.it, q.itMax);
+            if (h.track) printf("iterate evolution %g (recond. %g; tol. %g)\n", h.dif, h.rcd, h.tol);
+            printf("PFDR on B200: loop %.3f ms, %lld kernel launches\n", ctx().stats.loop_ms, ctx().stats.loop_launches);
             fflush(stdout);
         }
     }

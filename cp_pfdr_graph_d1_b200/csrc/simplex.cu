@@ -364,6 +364,7 @@ struct SimplexSolver : SolverBase {
     Ctl *hctl = nullptr;
     cudaEvent_t ev[2]{}, ev_a{}, ev_b{}, ev_c{};
     cudaGraphExec_t gexec = nullptr;
+    ProgressPrinter progress;
     int graph_trips = 0, grid = 0, ogrid = 0, LPT = 1, Vglobal = 0;
 
     SimplexSolver(const SimplexProblem<real> &q_, bool keep) : q(q_), keep_p0(keep) {}
@@ -471,7 +472,7 @@ struct SimplexSolver : SolverBase {
         const bool by_label = q.difTol >= (real) 1;
         if (by_label) lab.alloc(V);
         if (q.Obj) dObj.alloc((size_t) q.itMax + 1);
-        if (q.Dif) dDif.alloc((size_t) std::max(q.itMax, 1));
+        if (q.Dif || q.verbose > 0) dDif.alloc((size_t) std::max(q.itMax, 1));
         ctl.alloc(1); sums.alloc((size_t) std::max(1, comm().world)); sums.zero();
         const long long nslices = ((long long) V + C - 1) / C;
         grid = (int) cdiv((size_t) nslices * 32, 256);
@@ -715,6 +716,7 @@ struct SimplexSolver : SolverBase {
         ctx().stats.layout = dia ? 1 : 0; ctx().stats.gpus = slab ? link.world : 1;
         ctx().in_loop = true;
         PFDR_CUDA(cudaEventRecord(ev_b, st));
+        progress.start(q.verbose);
         long long enqueued = 0, budget = (long long) q.itMax + 1 + 2LL * batch;
         int fresh_from = 0;
         for (int k = 0;; k++) {
@@ -725,6 +727,8 @@ struct SimplexSolver : SolverBase {
             int verdict = 0;
             if (k >= 1 && k - 1 >= fresh_from) verdict = inspect((k - 1) & 1);
             if (verdict == 0 && enqueued >= budget) verdict = (k >= fresh_from) ? inspect(k & 1) : 0;
+            if (progress.every && k >= 1 && k - 1 >= fresh_from)
+                progress.upto(hctl[(k - 1) & 1].it, q.itMax, dDif.p, hctl[(k - 1) & 1].track != 0, hctl[(k - 1) & 1].tol, hctl[(k - 1) & 1].rcd);
             if (verdict == 1) break;
             if (verdict == 2) {
                 PFDR_CUDA(cudaStreamSynchronize(st));
@@ -769,9 +773,10 @@ struct SimplexSolver : SolverBase {
         if (cudaEventElapsedTime(&ms, ev_b, ev_c) == cudaSuccess) ctx().stats.loop_ms = ms;
         cudaGetLastError();
         ctx().stats.iterations = h.it;
-        if (q.verbose) {
-            printf("PFDR simplex (B200): %d iterations (max. %d), evolution %g, loop %.3f ms\n", h.it, q.itMax, h.dif,
-                   ctx().stats.loop_ms);
+        if (q.verbose) {                                                       // final information, as the reference's
+            printf("iteration %d (max. %d)\n", h.it, q.itMax);
+            if (h.track) printf("iterate evolution %g (recond. %g; tol. %g)\n", h.dif, h.rcd, h.tol);
+            printf("PFDR on B200: loop %.3f ms, %lld kernel launches\n", ctx().stats.loop_ms, ctx().stats.loop_launches);
             fflush(stdout);
         }
     }
@@ -894,6 +899,7 @@ void proj_simplex_metric(real *X, const real *M, int D, int N, int nm, const rea
     if (N == 0) return;
     const size_t n = (size_t) D * N;
     const bool inplace = is_device_ptr(X);
+    if (inplace) order_after_caller();
     DevBuf<real> xbuf;
     real *dX = X;
     if (!inplace) {

@@ -52,3 +52,25 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 txt = open(os.path.join(root, f)).read()
                 assert "liboracle" not in txt and "libref" not in txt and "from oracle" not in txt, f
+
+
+def test_binder_rejects_wrong_element_types():
+    """pointers are passed raw: an array of another element type, or a non-contiguous one, must be refused, not reinterpreted"""
+    import ctypes as C
+    import numpy as np
+    import pytest
+    from cp_pfdr_graph_d1_b200 import _abi
+    with pytest.raises(TypeError):
+        _abi._ptr(np.zeros(4, np.float64), C.c_float)
+    with pytest.raises(TypeError):
+        _abi._ptr(np.zeros(4, np.int64), C.c_int)
+    with pytest.raises(TypeError):
+        _abi._ptr(np.zeros((4, 6), np.float32)[::2, ::2], C.c_float)
+    with pytest.raises(TypeError):
+        _abi._real_dtype(np.zeros(4, np.float16))
+    import torch
+    with pytest.raises(TypeError):
+        _abi._ptr(torch.zeros(4, dtype=torch.float32), C.c_float)          # a CPU tensor is not a device pointer
+    with pytest.raises(TypeError):
+        _abi._real_dtype(torch.zeros(4, dtype=torch.bfloat16))
+    assert _abi._ptr(np.zeros(4, np.float32), C.c_float) is not None and _abi._ptr(None, C.c_float) is None

@@ -258,3 +258,19 @@ def test_paths_agree_on_irregular_graphs(gpu_api, oracle, monkeypatch, V, kind):
         assert rel(r.X, ref.X) < 1e-8, (mode, rel(r.X, ref.X))
     orc = oracle.PFDR_graph_quadratic_d1_l1(*fresh(), **kw)
     assert abs(orc.it - ref.it) <= 1 and rel(ref.X, orc.X) < 1e-5, (orc.it, ref.it, rel(ref.X, orc.X))
+
+
+def test_verbose_progress_lines(gpu_api, monkeypatch, capfd):
+    """`verbose` of the reference (src/PFDR_graph_quadratic_d1_l1.cpp:43-55, :425-428): a message every `verbose`
+    iterations with the iteration count and the evolution measure against its thresholds, and the final information"""
+    import re
+    from cp_pfdr_graph_d1_b200.api import _b
+    monkeypatch.setenv("PFDR_B200_SMALL", "0")
+    r = problems.run_quad(_b(), "grid_diag", np.float64, verbose=25, want_obj=False)
+    out = capfd.readouterr().out
+    its = [int(m) for m in re.findall(r"^iteration (\d+) \(max\. 300\)$", out, flags=re.M)]
+    assert its[:-1] == list(range(25, r.it + 1, 25))[:len(its) - 1] and its[-1] == r.it, (its, r.it)
+    evo = re.findall(r"^iterate evolution (\S+) \(recond\. (\S+); tol\. (\S+)\)$", out, flags=re.M)
+    assert len(evo) == len(its)
+    assert abs(float(evo[0][0]) - float(r.Dif[24])) <= 1e-5 * float(r.Dif[24])          # the value of THAT iteration
+    assert abs(float(evo[0][2]) - 1e-10) < 1e-16                                        # difTol^2, as the reference prints it

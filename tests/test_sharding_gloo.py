@@ -12,6 +12,7 @@ import torch.multiprocessing as mp
 
 from cp_pfdr_graph_d1_b200 import shard, synth
 
+import dia_model
 import problems
 import sell_model
 
@@ -112,3 +113,81 @@ def test_plan_invariants(world):
             assert (nb.send_vertices < p.Vown).all() and (nb.recv_vertices >= p.Vown).all()
     assert (owners == 1).all()
     assert ((covered == 1) | (covered == 2)).all()              # cut edges live on exactly two ranks
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# slab sharding of grid graphs (shard.SlabPlan, csrc/slab.cuh): the ranks WRITE into each other's ghost zones
+# ---------------------------------------------------------------------------------------------------------------
+class GlooSlabComm(GlooComm):
+    """the peer stores of the CUDA path as messages: every rank sends its neighbours (array, plane, position, values)"""
+
+    def __init__(self, plan):
+        r = [None] * plan.world
+        dist.all_gather_object(r, (plan.lo, plan.hi, plan.v0, plan.v1))
+        self.ranges, self.plan = r, plan
+
+    def push(self, msgs):
+        got = []
+        box = [None] * self.plan.world
+        dist.all_gather_object(box, msgs)                      # tiny problems: an all-gather of the per-destination lists
+        for sender in box:
+            got += sender.get(self.plan.rank, [])
+        return got
+
+
+def _slab_worker(rank, world, port, n, dtype_name, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        dtype = np.dtype(dtype_name).type
+        w = synth.c2_denoise(n, dtype, diag=True)
+        A = w["La_l2"]
+        plan = shard.make_slab_plan(w["V"], w["Eu"], w["Ev"], world, rank)
+        x, it = dia_model.quad_n0_slab(plan, GlooSlabComm(plan), np.zeros(w["V"], dtype), (A * w["Y"]).astype(dtype), A, w["La_d1"],
+                                       1.5, 1e-5, 120, (dtype(0.2), dtype(2.5)))
+        parts = [None] * world
+        dist.all_gather_object(parts, (plan.v0, x, it))
+        if rank == 0:
+            np.save(out, np.concatenate([p[1] for p in sorted(parts, key=lambda t: t[0])]))
+            np.save(out + ".it.npy", np.array([p[2] for p in parts]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n", [(2, 8), (3, 9), (4, 8)])
+def test_slab_schedule_matches_oracle(oracle, tmp_path, world, n):
+    """world-size 2 / 3 / 4 gloo groups run the slab schedule (numpy compute, ghost-zone writes as messages) and must
+    reproduce the unsharded oracle: checks which vertices / planes travel, where they land, and the shared stop rule"""
+    dtype = np.float64
+    out = str(tmp_path / "x.npy")
+    mp.spawn(_slab_worker, args=(world, _free_port(), n, np.dtype(dtype).name, out), nprocs=world, join=True)
+    got, its = np.load(out), np.load(out + ".it.npy")
+    w = synth.c2_denoise(n, dtype, diag=True)
+    A = w["La_l2"]
+    ref = oracle.PFDR_graph_quadratic_d1_bounds(np.zeros(w["V"], dtype), (A * w["Y"]).astype(dtype), A, w["Eu"], w["Ev"], w["La_d1"],
+                                                0.2, 2.5, 1, A, rho=1.5, condMin=1e-3, difRcd=0.0, difTol=1e-5, itMax=120, N=0)
+    assert (its == ref.it).all(), (its, ref.it)
+    assert np.linalg.norm(got - ref.X) / np.linalg.norm(ref.X) < 1e-10
+
+
+@pytest.mark.parametrize("world", [2, 3, 5])
+def test_slab_plan_invariants(world):
+    n, nz = 6, 11
+    V, Eu, Ev = synth.grid_graph(n, nz)
+    plans = [shard.make_slab_plan(V, Eu, Ev, world, r) for r in range(world)]
+    owners = np.zeros(V, int)
+    covered = np.zeros(Eu.shape[0], int)
+    for p in plans:
+        g = shard.grid_slab_plan(n, world, p.rank, nz)             # built from the rank's planes alone: same plan
+        assert (g.v0, g.v1, g.lo, g.hi) == (p.v0, p.v1, p.lo, p.hi) and np.array_equal(g.Eu, p.Eu) and np.array_equal(g.Ev, p.Ev)
+        assert p.band == n * n and p.v0 % p.band == 0 and p.lo == max(p.v0 - p.band, 0) and p.hi == min(p.v1 + p.band, V)
+        owners[p.v0:p.v1] += 1
+        covered[p.edge_ids] += 1
+        assert np.array_equal(p.Eu + p.lo, Eu[p.edge_ids]) and np.array_equal(p.Ev + p.lo, Ev[p.edge_ids])
+        assert (np.diff(p.edge_ids) > 0).all() and p.Eu.min() >= 0 and p.Ev.max() < p.Vloc
+        # the local graph is again a vertex-major constant-offset graph: what the stencil layout needs
+        d = p.Ev - p.Eu
+        assert set(d.tolist()) <= {1, n, n * n} and ((np.diff(p.Eu) > 0) | ((np.diff(p.Eu) == 0) & (np.diff(d) > 0))).all()
+    assert (owners == 1).all() and ((covered == 1) | (covered == 2)).all()
+    with pytest.raises(ValueError):
+        shard.make_slab_plan(V, Eu, Ev, 12, 0)                      # slabs thinner than the band
