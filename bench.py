@@ -203,6 +203,9 @@ def device_grid_edges(n, dev):
     return Eu[keep].to(torch.int32).contiguous(), Ev[keep].to(torch.int32).contiguous()
 
 
+OPNORM_C3_S = None
+
+
 def torch_lambda_max(matvec, V, dev, tdt, iters=30):
     """largest eigenvalue of A^tA by power iteration in torch (bench input preparation only)"""
     import torch
@@ -231,7 +234,14 @@ def device_inputs_dense(name, dev):
         del G
         x0 = torch.from_numpy(np.round(4 * pts[:, 0]) / 4).to(dev, tdt)
         AtY = AtA @ x0 + 0.01 * torch.randn(V, generator=g, device=dev, dtype=tdt)
-        lam = torch_lambda_max(lambda x: AtA @ x, V, dev, tdt)
+        # SCAL Lipschitz constant from the library's own operator_norm_matrix (the routine cut-pursuit calls for it,
+        # reference src/CP_PFDR_graph_quadratic_d1_bounds.cpp:769): the symmetric V x V system takes its batched path
+        from cp_pfdr_graph_d1_b200 import api
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        lam = 1.01 * api.operator_norm_matrix(AtA, 0, V, 1e-3, 100, 10)
+        global OPNORM_C3_S
+        OPNORM_C3_S = time.perf_counter() - t0
         return dict(V=V, E=int(Eu.shape[0]), N=-V, A=AtA.contiguous(), Y=AtY, Eu=to_dev(Eu, dev), Ev=to_dev(Ev, dev),
                     La_d1=torch.full((Eu.shape[0],), 0.02, device=dev, dtype=tdt), L=torch.tensor([lam], device=dev, dtype=tdt))
     V, Eu, Ev = synth.grid_graph(n)
@@ -583,6 +593,8 @@ def main():
                 extra[xn] = {"workload": describe(xn), "value": X["value"], "unit": "edge_updates/s",
                              "us_per_iteration": 1e3 * X["loop_ms"] / X["its"], "roofline_frac": X["achieved"] / X["peak"],
                              "achieved_gbs": X["achieved"], "algorithmic_bytes_per_launch": X["B_iter"]}
+                if xn == "c3_f32" and OPNORM_C3_S is not None:
+                    extra[xn]["operator_norm_matrix_s"] = round(OPNORM_C3_S, 4)
             except Exception as ex:                               # a secondary line must not lose the headline
                 extra[xn] = {"error": f"{type(ex).__name__}: {ex}"[:300]}
         line["extra"] = extra

@@ -101,13 +101,10 @@ inline void event_put(cudaEvent_t e) { if (e) host_cache().events.push_back(e); 
 // Device memory comes from the stream-ordered allocator (cudaMallocAsync on the launch stream) with the pool's
 // release threshold lifted, so the ~25 arrays of a solve cost microseconds after the first call instead of a
 // cudaMalloc/cudaFree pair each (tens of milliseconds per solve: most of the one-shot entry points' overhead,
-// and they are called once per cut-pursuit iteration by the reference's outer loop).  PFDR_B200_POOL=0 reverts.
+// and they are called once per cut-pursuit iteration by the reference's outer loop).
 inline bool use_pool()
 {
-    static int env = -1;
     static bool lifted[64] = {};                     // per device (several host threads may drive one GPU each)
-    if (env < 0) { const char *e = getenv("PFDR_B200_POOL"); env = (e && e[0] == '0') ? 0 : 1; }
-    if (!env) return false;
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && !lifted[dev]) {
@@ -242,7 +239,8 @@ struct Ctl {
     int itMax;
     int track;         // evolution is monitored (difTol > 0 || difRcd > 0 || Dif != NULL)
     unsigned ticket;   // last-block-done counter
-    int pad0, pad1;
+    int bdone;         // slab-sharded solves: boundary chunks completed since reset() (slab.cuh)
+    int pad1;
     double dif;        // current evolution measure (as the reference's `dif`)
     double tol;        // stop threshold in the units of dif  (quadratic: difTol^2, simplex: difTol)
     double rcd;        // reconditioning threshold, same units

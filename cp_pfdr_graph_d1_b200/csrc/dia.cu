@@ -69,10 +69,14 @@ __global__ void __launch_bounds__(256) dia_in_kernel(int V, Offs o, const unsign
     mask[v] = (unsigned char) m;
 }
 
-__global__ void chunk_key_kernel(int nchunks, int C, int band, int T, int nx, long long v0, unsigned long long *__restrict__ key, int *__restrict__ val)
+__global__ void chunk_key_kernel(int nchunks, int C, int band, int T, int nx, long long v0, int lowB, int highB, int nown,
+                                 unsigned long long *__restrict__ key, int *__restrict__ val)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= nchunks) return;
+    // slab-sharded: chunks holding a vertex within the band of a neighbouring rank come first (slab.cuh)
+    const bool interior = !((long long) s * C < lowB || ((long long) s + 1) * C > (long long) nown - highB);
+    if (T <= 0) { key[s] = ((unsigned long long) interior << 62) | (unsigned long long) s; val[s] = s; return; }
     const long long v = v0 + (long long) s * C;                     // global number of the chunk's first vertex
     const long long z = v / band, r = v % band;
     const long long nz = (v0 + (long long) nchunks * C + band - 1) / band + 1;
@@ -83,18 +87,19 @@ __global__ void chunk_key_kernel(int nchunks, int C, int band, int T, int nx, lo
         key[s] = (unsigned long long) (((((y / TY) * nz + z) * (TY / 8) + (y % TY) / 8) * npx + x / C) * 8 + y % 8);
     } else
         key[s] = (unsigned long long) (((r / T) * nz + z) * T + (r % T));
+    key[s] |= (unsigned long long) interior << 62;
     val[s] = s;
 }
 
 }  // namespace
 
-void build_chunk_order(int nchunks, int C, int band, int T, DevBuf<int> &order, int nx, long long v0)
+void build_chunk_order(int nchunks, int C, int band, int T, DevBuf<int> &order, int nx, long long v0, int lowB, int highB, int nown)
 {
     cudaStream_t st = ctx().stream;
     DevBuf<unsigned long long> key(nchunks), skey(nchunks);
     DevBuf<int> val(nchunks);
     order.alloc(nchunks);
-    PFDR_LAUNCH(chunk_key_kernel, cdiv(nchunks, 256), 256, 0, nchunks, C, band, T, nx, v0, key.p, val.p);
+    PFDR_LAUNCH(chunk_key_kernel, cdiv(nchunks, 256), 256, 0, nchunks, C, std::max(band, 1), T, nx, v0, lowB, highB, nown > 0 ? nown : nchunks * C, key.p, val.p);
     size_t tb = 0;
     PFDR_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, key.p, skey.p, val.p, order.p, nchunks, 0, 64, st));
     DevBuf<unsigned char> tmp(tb + 16);

@@ -40,8 +40,10 @@ bool build_dia(DiaGraph &g, const int *dEu, const int *dEv, int V, int E);
 // Processing order of chunks of C consecutive vertices for banded graphs (see graph.cuh build_slice_order): vertex
 // v = z*band + r is visited in the order (r / T, z, r % T).  nx > 0 (3-D grid with rows of nx vertices): the tile is a
 // band of rows and is walked in patches of 8 rows x one chunk, so that the 8 warps of a CTA hold vertical neighbours.
-// v0: global number of the first vertex of chunk 0 (slab-sharded solves order their owned range).
-void build_chunk_order(int nchunks, int C, int band, int T, DevBuf<int> &order, int nx = 0, long long v0 = 0);
+// v0: global number of the first vertex of chunk 0 (slab-sharded solves order their owned range); lowB / highB > 0:
+// chunks holding one of the first lowB / last highB of the nown vertices come first (slab.cuh); T <= 0: no tiling.
+void build_chunk_order(int nchunks, int C, int band, int T, DevBuf<int> &order, int nx = 0, long long v0 = 0,
+                       int lowB = 0, int highB = 0, int nown = 0);
 
 // device helpers --------------------------------------------------------------------------------
 // half-edge h = 0 .. 2ND-1 of a vertex in the reference's summation order

@@ -1451,9 +1451,9 @@ struct QuadSolver : SolverBase {
         for (int i = 0; i < 3; i++) p.dia_off[i] = dia ? dg.off[i] : 0;
         p.vbeg = slab ? q.slab->v0 - q.slab->lo : 0; p.vend = p.vbeg + p.Vown; p.dmask = dg.mask.p; p.eoff = dg.eoff.p; p.Wrow = Wrow.p;
         p.slab = SlabDev{}; p.plo = SlabPeer<real>{}; p.phi = SlabPeer<real>{};
-        if (slab) { p.slab = link.dev(); p.slab.band = dg.band(); }
+        if (slab) { p.slab = link.dev(); slab_geometry(); }
         p.w = w.p; p.thc = nullptr; p.thc0 = 0; p.Z0 = Z0.p; p.Z1 = Z1.p;
-        p.pk = nullptr; p.pk2 = nullptr;           // set by pack_slots() after each (re)conditioning (PFDR_B200_PACK=0: off)
+        p.pk = nullptr; p.pk2 = nullptr;           // set by pack_slots() after each (re)conditioning 
         p.X0 = X0b.p; p.X1 = X1b.p; p.P0 = P0b.p; p.P1 = P1b.p; p.T = T.p; p.Sinv = Sinv.p; p.Ga = Ga.p; p.Ga0 = Ga0.p; p.G = G.p; p.Thl1 = Thl1.p;
         p.R = R.p; p.AtY = AtY.p; p.Y = Y.p; p.A = A.p; p.La_d1 = La_d1.p; p.La_l1 = La_l1.p; p.L = L.p;
         p.Eu = Eu.p; p.Ev = Ev.p; p.Ltype = q.Ltype; p.positivity = q.positivity; p.prox_kind = q.prox_kind;
@@ -1489,6 +1489,15 @@ struct QuadSolver : SolverBase {
         PFDR_CUDA(cudaEventRecord(ev_b, st));
     }
 
+    // boundary vertices (within the band of a neighbouring rank) are worked on first: slab.cuh
+    void slab_geometry()
+    {
+        const int nown = p.vend - p.vbeg;
+        p.slab.band = dg.band();
+        p.slab.lowB = link.nb_lo >= 0 ? std::min(dg.band(), nown) : 0;
+        p.slab.highB = link.nb_hi >= 0 ? std::min(dg.band(), nown - p.slab.lowB) : 0;
+        p.slab.nbchunks = (p.slab.lowB + p.slab.highB + 31) / 32;
+    }
     // ghost zones of the neighbours <- this rank's boundary: metric T, forward point and cut-edge copies of the parity-0 buffers
     void slab_refresh()
     {
@@ -1531,7 +1540,7 @@ struct QuadSolver : SolverBase {
         std::vector<SlabBlob> all(link.world);
         for (int r = 0; r < link.world; r++) memcpy(&all[r], (const char *) blobs + (size_t) r * PFDR_B200_SLAB_BLOB, sizeof(SlabBlob));
         link.connect(all.data(), same_process);
-        p.slab = link.dev(); p.slab.band = dg.band();
+        p.slab = link.dev(); slab_geometry();
         for (int side = 0; side < 2; side++) {
             const int nb = side ? link.nb_hi : link.nb_lo;
             if (nb < 0) continue;
@@ -1593,12 +1602,11 @@ struct QuadSolver : SolverBase {
     // an unused word: -4 % instead of -9.5 % on C2).  float64, and float32 with per-slot thresholds: 16 bytes.
     void pack_slots()
     {
-        const char *e = getenv("PFDR_B200_PACK");
         p.pk = nullptr; p.pk2 = nullptr;
-        if (dia || (e && e[0] == '0')) return;
+        if (dia) return;
         const size_t ns = (size_t) std::max<long long>(g.nslots, 1);
         // (buffers are kept across reset(): a captured graph holds their addresses)
-        if (sizeof(real) == 4 && !p.thc && !(e && e[0] == '4')) { if (pk2b.n != ns) pk2b.alloc(ns); p.pk2 = pk2b.p; }
+        if (sizeof(real) == 4 && !p.thc) { if (pk2b.n != ns) pk2b.alloc(ns); p.pk2 = pk2b.p; }
         else { if (pkb.n != ns) pkb.alloc(ns); p.pk = pkb.p; }
         PFDR_LAUNCH(pack_slots_kernel<real>, cdiv(ns, 256), 256, 0, p, (int4 *) p.pk, g.nslots);
     }
@@ -1687,12 +1695,7 @@ struct QuadSolver : SolverBase {
         }
     }
 
-    static bool use_graph()
-    {
-        static int v = -1;
-        if (v < 0) { const char *e = getenv("PFDR_B200_GRAPH"); v = (e && e[0] == '0') ? 0 : 1; }
-        return v != 0;
-    }
+    static bool use_graph() { return true; }            // batches of iterations replay as CUDA graphs
 
     void recondition()
     {

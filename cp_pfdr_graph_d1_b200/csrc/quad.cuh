@@ -166,15 +166,15 @@ __device__ int quad_slab_decide(const QP<real> &p, int it)
     SlabMail *me = p.slab.mail[p.slab.rank];
     const unsigned long long target = (p.slab.run_id << 32) | (unsigned long long) it;
     bool ok = true;
-    if (p.slab.nb_lo >= 0) ok = slab_wait(&me->sum_flag[p.slab.nb_lo], target, me) && ok;
-    if (p.slab.nb_hi >= 0) ok = slab_wait(&me->sum_flag[p.slab.nb_hi], target, me) && ok;
+    if (p.slab.nb_lo >= 0) ok = slab_wait(&me->halo_flag[p.slab.nb_lo], target, me) && ok;
+    if (p.slab.nb_hi >= 0) ok = slab_wait(&me->halo_flag[p.slab.nb_hi], target, me) && ok;
     const int track = ctl->track;
     double dif = ctl->dif;
     if (ok && track) {
         double d = 0.0, c = 0.0;
         for (int q = 0; q < p.slab.world; q++) {                                   // rank order: same bits everywhere
             ok = slab_wait(&me->sum_flag[q], target, me) && ok;
-            d += me->sums[q][0]; c += me->sums[q][1];
+            d += me->sums[(it - 1) & 1][q][0]; c += me->sums[(it - 1) & 1][q][1];
         }
         dif = (c > ctl->eps) ? d / c : d / ctl->eps;                               // ref :515-529
     }

@@ -148,9 +148,19 @@ __global__ void __launch_bounds__(256, MINB) quad_dia_iter_kernel(QP<real> p)
     const int Vm1 = p.V - 1;
     const int off[3] = {p.dia_off[0], p.dia_off[1], p.dia_off[2]};
     const int stride = (int) (gridDim.x * blockDim.x);              // a warp takes 32 consecutive vertices per trip
+    const int nown = p.vend - p.vbeg, lane = threadIdx.x & 31;
+    // slab-sharded: the vertices within `band` of a neighbouring rank come first (work index -> vertex below), so that the
+    // neighbours learn early that their ghost zones are written; the interior follows and touches no ghost data
+    const int lowB = SLAB ? p.slab.lowB : 0, nB = SLAB ? p.slab.lowB + p.slab.highB : 0;
+    int bcount = 0;
     double red0 = 0.0, red1 = 0.0;
-    bool pushed = false;              // (a vertex with a cut edge lies within `band` of the slab's end, so its forward point travels too)
-    for (int v = p.vbeg + (int) (blockIdx.x * blockDim.x + threadIdx.x); v < p.vend; v += stride) {
+    for (int i0 = (int) (blockIdx.x * blockDim.x + threadIdx.x) - lane; i0 < nown; i0 += stride) {      // warp-uniform
+        const bool bchunk = SLAB && i0 < nB;
+        if (SLAB && !bchunk && bcount) { slab_boundary_done(p.slab, &ctl->bdone, bcount, it); bcount = 0; }
+        if (bchunk) bcount++;
+        const int i = i0 + lane;
+        if (i >= nown) continue;
+        const int v = !SLAB ? p.vbeg + i : (i < lowB ? p.vbeg + i : (i < nB ? p.vend - nB + i : p.vbeg + lowB + (i - nB)));
         const unsigned m = __ldg(p.dmask + v);
         const real xo = Xc[v], po_v = Pc[v], Tv = Tg[v];
         real acc = 0;
@@ -200,20 +210,20 @@ __global__ void __launch_bounds__(256, MINB) quad_dia_iter_kernel(QP<real> p)
             const real fp = forward_point_diag(p, v, x);
             Pn[v] = fp;
             if (SLAB) {     // boundary vertices: the neighbouring rank gathers this forward point from its ghost zone
-                if (p.plo.F[0] && v < p.vbeg + p.slab.band) { p.plo.F[cur ^ 1][(long long) v + p.plo.shift] = fp; pushed = true; }
-                if (p.phi.F[0] && v >= p.vend - p.slab.band) { p.phi.F[cur ^ 1][(long long) v + p.phi.shift] = fp; pushed = true; }
+                if (p.plo.F[0] && v < p.vbeg + p.slab.band) p.plo.F[cur ^ 1][(long long) v + p.plo.shift] = fp;
+                if (p.phi.F[0] && v >= p.vend - p.slab.band) p.phi.F[cur ^ 1][(long long) v + p.phi.shift] = fp;
             }
         }
         const real dx = xo - x;
         red0 += (double) (dx * dx); red1 += (double) (x * x);
     }
-    if (SLAB && pushed) __threadfence_system();             // this thread's stores into the neighbours' ghost zones
+    if (SLAB && bcount) slab_boundary_done(p.slab, &ctl->bdone, bcount, it);
     double tot[2] = {red0, red1};
     if (grid_sum<2>(ctl, p.partial, tot, smem) && threadIdx.x == 0) {
         if (SLAB) {
             ctl->it = it + 1;
             const double v4[SLAB_NSUM] = {tot[0], tot[1], 0.0, 0.0};
-            slab_post(p.slab, v4, (unsigned long long) (it + 1));
+            if (ctl->track) slab_post(p.slab, v4, (unsigned long long) (it + 1));     // stopping sums: only when someone waits for them
         } else if (p.sharded) { p.sums[2 * p.rank] = tot[0]; p.sums[2 * p.rank + 1] = tot[1]; }
         else quad_finalize(p, it, tot[0], tot[1]);
     }

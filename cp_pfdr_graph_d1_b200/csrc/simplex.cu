@@ -360,6 +360,7 @@ struct SimplexSolver : SolverBase {
     Halo<real> halo;
     SlabLink link;                  // slab-sharded solve (slab.cuh)
     bool slab = false;
+    int slab_lowB = 0, slab_highB = 0, slab_nbchunks = 0;
     bool sharded = false;
     Ctl *hctl = nullptr;
     cudaEvent_t ev[2]{}, ev_a{}, ev_b{}, ev_c{};
@@ -488,13 +489,21 @@ struct SimplexSolver : SolverBase {
             const char *e = getenv("PFDR_B200_TILE");
             const long long tile_env = e ? atoll(e) : -1;
             p.order = nullptr;
-            if (tile_env != 0 && band > 0 && ((double) band * bytes_per_vertex > 24e6 || tile_env > 0)) {
+            const int nchunks = (int) (((long long) Vown + C - 1) / C);
+            // slab-sharded: the chunks within the band of a neighbouring rank are worked on first (slab.cuh)
+            slab_lowB = (slab && q.slab->rank > 0) ? std::min(dg.band(), Vown) : 0;
+            slab_highB = (slab && q.slab->rank + 1 < q.slab->world) ? std::min(dg.band(), Vown - slab_lowB) : 0;
+            {
+                const long long lowc = ((long long) slab_lowB + C - 1) / C, firsthigh = slab_highB ? ((long long) Vown - slab_highB) / C : nchunks;
+                slab_nbchunks = (int) std::min<long long>(nchunks, lowc + (nchunks - firsthigh) - std::max<long long>(0, lowc - firsthigh));
+            }
+            const bool tiled = tile_env != 0 && band > 0 && ((double) band * bytes_per_vertex > 24e6 || tile_env > 0);
+            if (tiled || slab_lowB + slab_highB > 0) {
                 long long T = tile_env > 0 ? tile_env : (long long) (9.3e6 / bytes_per_vertex);   // C4 252^3 f32: 32 rows of a plane (profiles/r02_notes.md)
-                T = std::max<long long>(C, std::min<long long>(T, band));
-                T = (T / C) * C;
-                const char *pe = getenv("PFDR_B200_PATCH");
-                const int nx = (dia && dg.ND == 3 && dg.off[0] == 1 && dg.off[2] % dg.off[1] == 0 && !(pe && pe[0] == '0')) ? dg.off[1] : 0;
-                build_chunk_order((int) (((long long) Vown + C - 1) / C), C, band, (int) T, order, nx, slab ? q.slab->v0 : 0);
+                T = std::max<long long>(C, std::min<long long>(T, std::max(band, C)));
+                T = tiled ? (T / C) * C : 0;
+                const int nx = (dia && dg.ND == 3 && dg.off[0] == 1 && dg.off[2] % dg.off[1] == 0) ? dg.off[1] : 0;
+                build_chunk_order(nchunks, C, band, (int) T, order, nx, slab ? q.slab->v0 : 0, slab_lowB, slab_highB, Vown);
                 p.order = order.p;
             }
         }
@@ -508,13 +517,13 @@ struct SimplexSolver : SolverBase {
         for (int i = 0; i < 3; i++) p.dia_off[i] = dia ? dg.off[i] : 0;
         p.vbeg = slab ? q.slab->v0 - q.slab->lo : 0; p.vend = p.vbeg + Vown; p.dmask = dg.mask.p;
         p.slab = SlabDev{}; p.plo = SlabPeer<real>{}; p.phi = SlabPeer<real>{};
-        if (slab) { p.slab = link.dev(); p.slab.band = dg.band(); } p.eoff = dg.eoff.p; p.Wrow = Wrow.p;
+        if (slab) { p.slab = link.dev(); p.slab.band = dg.band(); p.slab.lowB = slab_lowB; p.slab.highB = slab_highB; p.slab.nbchunks = slab_nbchunks; } p.eoff = dg.eoff.p; p.Wrow = Wrow.p;
         p.w = w.p; p.wk = nullptr; p.thk = nullptr; p.Z0 = Z0.p; p.Z1 = Z1.p;
         p.P0 = Pa.p; p.P1 = Pb.p; p.F0 = Fa.p; p.F1 = Fb.p; p.T = T.p; p.GaQ = GaQ.p; p.Sinv = Sinv.p;
         p.Sinvk = nullptr; p.Gn = nullptr; p.GaU = GaU.p; p.lab = lab.p;
         p.Q = Q.p; p.La_f = La_f.p; p.La_d1 = La_d1.p; p.Eu = Eu.p; p.Ev = Ev.p;
         p.partial = partial.p; p.dObj = dObj.p; p.dDif = dDif.p;
-        { const char *e = getenv("PFDR_B200_STREAMZ"); p.stream_z = (e && e[0] == '1') ? 1 : 0; }
+        p.stream_z = 0;
 
         if (sharded) { halo.setup(*q.shard, g.hkey.p, g.nslots, 2 * (size_t) E, K); halo.build(HALO_VA0 | HALO_VA1); halo.build(HALO_VA0 | HALO_Z); }
         if (!(slab && link.world > 1)) reset();            // a slab-sharded solve is initialised by slab_connect (collective)
@@ -600,7 +609,7 @@ struct SimplexSolver : SolverBase {
         std::vector<SlabBlob> all(link.world);
         for (int r = 0; r < link.world; r++) memcpy(&all[r], (const char *) blobs + (size_t) r * PFDR_B200_SLAB_BLOB, sizeof(SlabBlob));
         link.connect(all.data(), same_process);
-        p.slab = link.dev(); p.slab.band = dg.band();
+        p.slab = link.dev(); p.slab.band = dg.band(); p.slab.lowB = slab_lowB; p.slab.highB = slab_highB; p.slab.nbchunks = slab_nbchunks;
         for (int side = 0; side < 2; side++) {
             const int nb = side ? link.nb_hi : link.nb_lo;
             if (nb < 0) continue;
@@ -616,21 +625,12 @@ struct SimplexSolver : SolverBase {
     template <int L, bool PERK, int LOSS>
     void launch_iter_u()
     {
-        static int U = -1;
-        if (U < 0) { const char *e = getenv("PFDR_B200_U"); U = e ? atoi(e) : 0; }
-        // PFDR_B200_MINB (tuning): minimum resident CTAs per SM the compiler must fit registers for
-        static int MB = -1;
-        if (MB < 0) { const char *e = getenv("PFDR_B200_MINB"); MB = e ? atoi(e) : 0; }
-        (void) U;
         constexpr int MBD = (sizeof(real) == 4 || L == 2) ? 4 : 2;
         const bool small = (size_t) std::max<long long>(g.nslots, q.V) * (size_t) p.K < 0xFFFFFFFFull;
-        static int i32 = -1;
-        if (i32 < 0) { const char *e = getenv("PFDR_B200_IDX32"); i32 = (e && e[0] == '0') ? 0 : 1; }
-        (void) U; (void) MB;
-        // a slice wider than SIMPLEX_HUB_ROWS (a hub vertex): variant whose warps share the hub's rows (PFDR_B200_HUB=0: off)
-        const char *he = getenv("PFDR_B200_HUB");
-        const bool hub_env = !(he && he[0] == '0');
-        if (hub_env && g.max_width > SIMPLEX_HUB_ROWS) PFDR_LAUNCH((simplex_iter_kernel<real, L, PERK, LOSS, 1, false, true>), ogrid, 256, 0, p);
+        const char *ie = getenv("PFDR_B200_IDX32");              // read per call: the tests switch it (0: 64-bit element offsets)
+        const bool i32 = !(ie && ie[0] == '0');
+        // a slice wider than SIMPLEX_HUB_ROWS (a hub vertex): variant whose warps share the hub's rows
+        if (g.max_width > SIMPLEX_HUB_ROWS) PFDR_LAUNCH((simplex_iter_kernel<real, L, PERK, LOSS, 1, false, true>), ogrid, 256, 0, p);
         else if (L > 1 && !PERK && small && i32) {
             if constexpr (L > 1) PFDR_LAUNCH((simplex_iter_kernel<real, L, false, LOSS, MBD, true, false>), ogrid, 256, 0, p);
         }
@@ -665,9 +665,6 @@ struct SimplexSolver : SolverBase {
     void enqueue_batch(int batch)
     {
         cudaStream_t st = ctx().stream;
-        static int use_graph = -1;
-        if (use_graph < 0) { const char *e = getenv("PFDR_B200_GRAPH"); use_graph = (e && e[0] == '0') ? 0 : 1; }
-        if (!use_graph) { for (int i = 0; i < batch; i++) enqueue_trip(); return; }
         if (!gexec || graph_trips != batch) {
             if (gexec) { cudaGraphExecDestroy(gexec); gexec = nullptr; }
             cudaGraph_t graph;

@@ -330,13 +330,13 @@ __device__ int simplex_slab_decide(const SP<real> &p, int it)
     SlabMail *me = p.slab.mail[p.slab.rank];
     const unsigned long long target = (p.slab.run_id << 32) | (unsigned long long) it;
     bool ok = true;
-    if (p.slab.nb_lo >= 0) ok = slab_wait(&me->sum_flag[p.slab.nb_lo], target, me) && ok;
-    if (p.slab.nb_hi >= 0) ok = slab_wait(&me->sum_flag[p.slab.nb_hi], target, me) && ok;
+    if (p.slab.nb_lo >= 0) ok = slab_wait(&me->halo_flag[p.slab.nb_lo], target, me) && ok;
+    if (p.slab.nb_hi >= 0) ok = slab_wait(&me->halo_flag[p.slab.nb_hi], target, me) && ok;
     const int track = ctl->track;
     double dif = ctl->dif;
     if (ok && track) {
         double s = 0.0;
-        for (int q = 0; q < p.slab.world; q++) { ok = slab_wait(&me->sum_flag[q], target, me) && ok; s += me->sums[q][0]; }   // rank order
+        for (int q = 0; q < p.slab.world; q++) { ok = slab_wait(&me->sum_flag[q], target, me) && ok; s += me->sums[(it - 1) & 1][q][0]; }   // rank order
         dif = p.by_label ? s : s / (double) p.Vglobal;              // ref :688
     }
     int state = ST_RUN;

@@ -174,12 +174,17 @@ __global__ void __launch_bounds__(256, MINB) simplex_dia_iter_kernel(SP<real> p)
     const real rho = p.rho;
     const int off[3] = {p.dia_off[0], p.dia_off[1], p.dia_off[2]};
     double red = 0.0;
-    bool pushed = false;
+    int bcount = 0;                 // slab-sharded: boundary chunks come first in the work order (slab.cuh)
     int idx = (int) blockIdx.x * (int) (blockDim.x >> 5) + (int) (threadIdx.x >> 5);
     int chunk_next = idx < nchunks ? (order ? __ldg(order + idx) : idx) : 0;
     for (; idx < nchunks; idx += nwarps) {                                    // warp-uniform trip count
         const int chunk = chunk_next;
         if (idx + nwarps < nchunks) chunk_next = order ? __ldg(order + (idx + nwarps)) : idx + nwarps;
+        if (SLAB) {
+            const bool bchunk = idx < p.slab.nbchunks;
+            if (!bchunk && bcount) { slab_boundary_done(p.slab, &ctl->bdone, bcount, it); bcount = 0; }
+            if (bchunk) bcount++;
+        }
         const int v = p.vbeg + (chunk << p.logC) + vl;
         const bool on = (v < p.vend) && (k0 < K);
         const int vs = on ? v : p.vbeg;
@@ -226,17 +231,16 @@ __global__ void __launch_bounds__(256, MINB) simplex_dia_iter_kernel(SP<real> p)
         if (SLAB && on) {
             if (p.plo.F[0] && v < p.vbeg + p.slab.band) flo = p.plo.F[cur ^ 1] + ((long long) vk + p.plo.shift);
             if (p.phi.F[0] && v >= p.vend - p.slab.band) fhi = p.phi.F[cur ^ 1] + ((long long) vk + p.phi.shift);
-            pushed = pushed || flo || fhi;          // (a vertex with a cut edge lies within `band` of the slab's end)
         }
         red += simplex_epilogue<real, LPT, PERK, LOSS>(p, ctl, on, v, k0, vk, acc, Tv, pold, Pn, Fn, &gaq, flo, fhi);
     }
-    if (SLAB && pushed) __threadfence_system();             // this thread's stores into the neighbours' ghost zones
+    if (SLAB && bcount) slab_boundary_done(p.slab, &ctl->bdone, bcount, it);
     double tot[1] = {red};
     if (grid_sum_s<1>(ctl, p.partial, tot, smem) && threadIdx.x == 0) {
         if (SLAB) {
             ctl->it = it + 1;
             const double v4[SLAB_NSUM] = {tot[0], 0.0, 0.0, 0.0};
-            slab_post(p.slab, v4, (unsigned long long) (it + 1));
+            if (ctl->track) slab_post(p.slab, v4, (unsigned long long) (it + 1));     // stopping sums: only when someone waits for them
         } else if (p.sharded) p.sums[p.rank] = tot[0];
         else simplex_finalize(p, it, tot[0]);
     }

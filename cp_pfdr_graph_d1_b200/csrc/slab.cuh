@@ -7,12 +7,16 @@
 // new copies on the cut edges - is STORED BY THE ITERATION KERNEL ITSELF into the neighbour's ghost zone through
 // peer-mapped pointers (NVLink / NVSwitch; cudaIpc handles between processes, plain peer access inside one process):
 // no pack / unpack kernels, no send / receive.  Synchronisation is one 64-bit flag per rank pair and iteration:
-//   * the last CTA of rank r's iteration kernel, after a system-scope fence, writes r's stopping sums and the flag
-//     "r has completed iteration k" into the mailbox of EVERY rank (release stores);
-//   * the next kernel of a rank starts by waiting (acquire loads on its own mailbox) for the flags of its two
-//     neighbours - their pushes have landed and they no longer read what is about to be overwritten - and, when the
-//     evolution is monitored, of all ranks, adds the sums in rank order and takes the stop / recondition decision:
-//     every rank takes the same one at the same iteration, `*it` and Dif[] are exact.
+//   * a rank works on its boundary vertices (within `band` of a neighbour) FIRST; the warp that completes the last
+//     boundary chunk, after a system-scope fence, raises the flag "boundary part of iteration k done" in its two
+//     neighbours' mailboxes: its stores into their ghost zones have landed, and it no longer reads its own ghost
+//     zones - then the rank goes on with its interior, which touches no ghost data, while the flag travels;
+//   * the next kernel of a rank starts by waiting (acquire loads on its own mailbox) for the boundary flags of its
+//     neighbours - normally raised long before;
+//   * when the evolution is monitored, the last CTA also writes the rank's stopping sums and "iteration k completed"
+//     into the mailbox of EVERY rank, and the next kernel waits for all of them, adds the sums in rank order and
+//     takes the stop / recondition decision: every rank takes the same one at the same iteration, `*it` and Dif[]
+//     are exact.
 // Buffers are ping/pong by iteration parity, so a rank may run at most one iteration ahead of a neighbour.
 // Kernels of different ranks wait on one another: every rank must be on its own GPU (never two ranks on one device).
 #pragma once
@@ -25,7 +29,10 @@ constexpr int SLAB_NSUM = 4;
 
 struct SlabMail {                                   // one per rank, inside its peer-visible arena; slot [q] is written by rank q
     unsigned long long sum_flag[SLAB_MAXW];         // (run id << 32) | iterations completed by rank q
-    double sums[SLAB_MAXW][SLAB_NSUM];              // rank q's stopping sums of that iteration (+ objective part)
+    unsigned long long halo_flag[SLAB_MAXW];        // (run id << 32) | iterations whose BOUNDARY part rank q has completed:
+                                                    //   its stores into our ghost zones have landed, it no longer reads its own
+    double sums[2][SLAB_MAXW][SLAB_NSUM];           // rank q's stopping sums of iteration k in slot [k & 1] (+ objective part):
+                                                    //   q may finish k+1 before a slow reader has looked at k, never k+2
     unsigned long long bar[SLAB_MAXW];              // barrier epochs
     unsigned long long ax_flag[SLAB_MAXW];          // dense A: epoch of rank q's partial products
     unsigned long long red_flag[SLAB_MAXW];         // small all-reduce (preconditioner sums): epoch of rank q's contribution
@@ -43,6 +50,8 @@ struct SlabPeer {                                   // a neighbour's arrays as s
 
 struct SlabDev {                                    // kernel-side view of the link
     int on, world, rank, nb_lo, nb_hi, band;
+    int lowB, highB;                                // owned vertices within `band` of the rank below / above (0: no such rank)
+    int nbchunks;                                   // boundary chunks of this rank per iteration (they come first in its work order)
     unsigned long long run_id;
     SlabMail *mail[SLAB_MAXW];                      // every rank's mailbox (mail[rank] is local memory)
 };
@@ -75,16 +84,31 @@ __device__ __forceinline__ bool slab_wait(const unsigned long long *flag, unsign
         __nanosleep(64);
     }
 }
-// rank's sums and its "iteration `done` completed" flag into every mailbox (called by one thread, after the grid's
-// peer stores were fenced at system scope)
+// rank's sums and its "iteration `done` completed" flag into every mailbox (one thread).  One fence, then relaxed flag
+// stores: a release store per destination would wait for the NVLink round trip of each in turn.
 __device__ __forceinline__ void slab_post(const SlabDev &s, const double (&v)[SLAB_NSUM], unsigned long long done)
 {
-    __threadfence_system();
     for (int q = 0; q < s.world; q++) {
-        SlabMail *m = s.mail[q];
 #pragma unroll
-        for (int i = 0; i < SLAB_NSUM; i++) m->sums[s.rank][i] = v[i];
-        st_release_sys(&m->sum_flag[s.rank], (s.run_id << 32) | done);
+        for (int i = 0; i < SLAB_NSUM; i++) s.mail[q]->sums[(done - 1) & 1][s.rank][i] = v[i];
+    }
+    __threadfence_system();
+    for (int q = 0; q < s.world; q++) *((volatile unsigned long long *) &s.mail[q]->sum_flag[s.rank]) = (s.run_id << 32) | done;
+}
+// a warp has finished `count` boundary chunks of trip `it` (its lanes' stores into the neighbours' ghost zones are issued):
+// the warp completing the rank's last one raises the boundary flag at both neighbours.  bdone counts chunks since reset().
+__device__ __forceinline__ void slab_boundary_done(const SlabDev &s, int *bdone, int count, int it)
+{
+    __threadfence_system();                                      // every lane: its peer stores, before the count moves
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) {
+        const unsigned target = ((unsigned) it + 1u) * (unsigned) s.nbchunks;                  // modulo 2^32, as the counter
+        if (atomicAdd((unsigned *) bdone, (unsigned) count) + (unsigned) count == target) {
+            __threadfence_system();
+            const unsigned long long f = (s.run_id << 32) | (unsigned long long) (it + 1);
+            if (s.nb_lo >= 0) *((volatile unsigned long long *) &s.mail[s.nb_lo]->halo_flag[s.rank]) = f;
+            if (s.nb_hi >= 0) *((volatile unsigned long long *) &s.mail[s.nb_hi]->halo_flag[s.rank]) = f;
+        }
     }
 }
 

@@ -81,14 +81,16 @@ def single_gpu(gpu_api, oracle, case):
     return b.PFDR_graph_quadratic_d1_l1(np.zeros(V, dt), *args, **k2), oracle.PFDR_graph_quadratic_d1_l1(np.zeros(V, dt), *args, **k2)
 
 
-def check(got_X, got_it, got_Dif, one, ref, dt):
+def check(got_X, got_it, got_Dif, one, ref, dt, exact=True):
     rel = lambda a, c: float(np.linalg.norm(a.astype(np.float64) - c) / np.linalg.norm(c.astype(np.float64)))
     assert got_it == one.it, (got_it, one.it)
-    if one.Dif is None or one.Dif.shape[0] == 0:
-        assert np.array_equal(got_X, one.X)                    # no stopping sums involved: the very same arithmetic
+    tracked = one.Dif is not None and one.Dif.shape[0] > 0
+    if not tracked and exact:
+        assert np.array_equal(got_X, one.X)                    # no global sum involved: the very same arithmetic
     else:
         assert rel(got_X, one.X) < (1e-12 if dt is np.float64 else 1e-6)
-        assert np.allclose(got_Dif, one.Dif, rtol=1e-9 if dt is np.float64 else 1e-4)
+    if tracked:
+        assert np.allclose(got_Dif, one.Dif, rtol=1e-9 if dt is np.float64 else 1e-4), np.abs(got_Dif / one.Dif - 1).max()
     assert abs(one.it - ref.it) <= (0 if dt is np.float64 else max(2, ref.it // 20))
     assert rel(got_X, ref.X) < (1e-5 if dt is np.float64 else 1e-3)
 
@@ -111,7 +113,8 @@ def test_slab_ranks_match_single_gpu(gpu_api, oracle, tmp_path, case, world):
     got = np.load(out)
     assert int(got["gpus"]) == world and int(got["layout"]) == 1
     one, ref = single_gpu(gpu_api, oracle, case)
-    check(got["X"], int(got["it"]), got["Dif"], one, ref, case_inputs(case)[3])
+    # (quadratic family: the preconditioner's mean amplitude is a sum over all vertices, added rank by rank)
+    check(got["X"], int(got["it"]), got["Dif"], one, ref, case_inputs(case)[3], exact=case.startswith("simplex"))
 
 
 @pytest.mark.parametrize("case", ["simplex_k16", "simplex_k16notrack", "quad_f64", "quad_notrack"])
@@ -156,7 +159,7 @@ def test_slab_ranks_in_one_process(gpu_api, oracle, case):
     assert not errs, errs
     X = np.concatenate([o[1].X for o in sorted(out, key=lambda t: t[0])])
     one, ref = single_gpu(gpu_api, oracle, case)
-    check(X, out[0][1].it, out[0][1].Dif, one, ref, dt)
+    check(X, out[0][1].it, out[0][1].Dif, one, ref, dt, exact=case.startswith("simplex"))
 
 
 @pytest.mark.parametrize("family", ["simplex", "quad"])
@@ -183,7 +186,11 @@ def test_one_shot_entry_points_on_two_gpus(gpu_api, monkeypatch, family):
     two = call()
     st = gpu_api.last_stats()
     assert st["gpus"] == 2 and st["layout"] == 1, st
-    assert two.it == one.it == 30 and np.array_equal(two.X, one.X)
+    assert two.it == one.it == 30
+    if family == "simplex":
+        assert np.array_equal(two.X, one.X)
+    else:       # the preconditioner's mean amplitude is a sum over all vertices, added rank by rank
+        assert np.linalg.norm(two.X.astype(np.float64) - one.X) / np.linalg.norm(one.X.astype(np.float64)) < 1e-6
 
 
 def test_template_symbol_of_the_shim_on_two_gpus(gpu_api, monkeypatch):
