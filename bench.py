@@ -492,6 +492,10 @@ def cp_solve_time():
     w = synth.eeg_like(5, 91, np.float64)
     kw = dict(CP_difTol=1e-4, CP_itMax=15, rho=1.5, condMin=1e-3, difRcd=0.0, difTol=1e-7, itMax=10000)
     a = (w["Y"], w["A"], w["Eu"], w["Ev"], w["La_d1"], w["La_l1"], 1, w["N"])
+    # the reference seeds operator_norm_matrix's power method with time(NULL) + thread id; oracle/_ref runs with its clock
+    # pinned and libpfdr_b200 (which draws the same starts, csrc/opnorm.cu) is given the same clock, so that the two
+    # cut-pursuit runs take the same metric and their components can be compared one by one
+    os.environ["PFDR_B200_OPNORM_TIME"] = "42"
     b200.quadratic_d1_l1(*a, **kw)                                 # warm-up: context, memory pool, module load
     t0 = time.perf_counter(); r1 = b200.quadratic_d1_l1(*a, **kw); t1 = time.perf_counter() - t0
     t0 = time.perf_counter(); r0 = ref.quadratic_d1_l1(*a, **kw); t_ref = time.perf_counter() - t0

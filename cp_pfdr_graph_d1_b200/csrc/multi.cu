@@ -147,7 +147,7 @@ template <typename real>
 bool solve_simplex_multi(const SimplexProblem<real> &q)
 {
     const int world = gpus_wanted();
-    if (world < 2 || q.Obj || q.difRcd > (real) 0 || q.K < 3 || q.E < 1 || q.itMax < 1) return false;
+    if (world < 2 || q.K < 3 || q.E < 1 || q.itMax < 1) return false;
     if (is_device_ptr(q.P) || is_device_ptr(q.Q) || is_device_ptr(q.Eu) || is_device_ptr(q.Ev) || is_device_ptr(q.La_d1)) return false;
     if ((long long) q.V * q.K < (1LL << 22)) return false;                       // small problems: one GPU is faster
     const long long band = sample_band(q.Eu, q.Ev, q.E);
@@ -164,13 +164,14 @@ bool solve_simplex_multi(const SimplexProblem<real> &q)
             l.P = q.P + (size_t) sl.lo * K; l.Q = q.Q + (size_t) sl.lo * K;
             l.La_f = q.La_f ? q.La_f + sl.lo : nullptr;
             l.Eu = ed.Eu.data(); l.Ev = ed.Ev.data(); l.La_d1 = q.La_d1 + ed.e0;
-            l.it = nullptr; l.Obj = nullptr; l.Dif = q.Dif ? reinterpret_cast<real *>(sizeof(real)) : nullptr;
+            l.it = nullptr; l.Obj = q.Obj ? reinterpret_cast<real *>(sizeof(real)) : nullptr;
+            l.Dif = q.Dif ? reinterpret_cast<real *>(sizeof(real)) : nullptr;
             l.verbose = 0; l.shard = nullptr; l.slab = &sl;
             return make_simplex<real>(l);
         },
         [&](int r, const pfdr_b200_slab &sl, SolverBase *s) {
             int it_r = 0;
-            s->fetch(q.P + (size_t) sl.v0 * K, &it_r, nullptr, r == 0 ? q.Dif : nullptr);
+            s->fetch(q.P + (size_t) sl.v0 * K, &it_r, r == 0 ? q.Obj : nullptr, r == 0 ? q.Dif : nullptr);
             if (r == 0) it = it_r;
         });
     } catch (const Error &e) {       // not a grid graph after all, GPUs without peer access, ...: one GPU takes it
@@ -188,7 +189,7 @@ template <typename real>
 bool solve_quadratic_multi(const QuadProblem<real> &q)
 {
     const int world = gpus_wanted();
-    if (world < 2 || q.N != 0 || q.Obj || q.difRcd > (real) 0 || q.E < 1 || q.itMax < 1) return false;
+    if (world < 2 || q.N != 0 || q.E < 1 || q.itMax < 1) return false;
     if (is_device_ptr(q.X) || is_device_ptr(q.Y) || is_device_ptr(q.Eu) || is_device_ptr(q.Ev) || is_device_ptr(q.La_d1)) return false;
     if (q.V < (1 << 21)) return false;                                           // small problems: one GPU is faster
     const long long band = sample_band(q.Eu, q.Ev, q.E);
@@ -205,13 +206,14 @@ bool solve_quadratic_multi(const QuadProblem<real> &q)
             l.La_l1 = q.La_l1 ? q.La_l1 + sl.lo : nullptr;
             l.L = (q.L && q.Ltype == PFDR_B200_DIAG) ? q.L + sl.lo : q.L;
             l.Eu = ed.Eu.data(); l.Ev = ed.Ev.data(); l.La_d1 = q.La_d1 + ed.e0;
-            l.it = nullptr; l.Obj = nullptr; l.Dif = q.Dif ? reinterpret_cast<real *>(sizeof(real)) : nullptr;
+            l.it = nullptr; l.Obj = q.Obj ? reinterpret_cast<real *>(sizeof(real)) : nullptr;
+            l.Dif = q.Dif ? reinterpret_cast<real *>(sizeof(real)) : nullptr;
             l.verbose = 0; l.shard = nullptr; l.slab = &sl;
             return make_quadratic<real>(l);
         },
         [&](int r, const pfdr_b200_slab &sl, SolverBase *s) {
             int it_r = 0;
-            s->fetch(q.X + sl.v0, &it_r, nullptr, r == 0 ? q.Dif : nullptr);
+            s->fetch(q.X + sl.v0, &it_r, r == 0 ? q.Obj : nullptr, r == 0 ? q.Dif : nullptr);
             if (r == 0) it = it_r;
         });
     } catch (const Error &e) {

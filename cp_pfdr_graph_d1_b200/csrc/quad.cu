@@ -157,7 +157,11 @@ template <typename real>
 __global__ void resume_kernel(QP<real> p, double rcd_factor)
 {
     p.ctl->rcd *= rcd_factor; p.ctl->state = ST_RUN; p.ctl->hold = 0;
+    p.ctl->scratch[1] = (double) (p.ctl->it + 1);            // slab-sharded: this trip's reconditioning test has been made
 }
+
+template <typename real>
+__global__ void quad_obj_final_kernel(QP<real> p) { p.dObj[p.ctl->it] = (real) *p.obj_part; }
 
 // ---------------------------------------------------------------------------------------------
 // the fused iteration kernel
@@ -1127,9 +1131,13 @@ __global__ void __launch_bounds__(256) objective_kernel(QP<real> p)
     const real *__restrict__ X = (it & 1) ? p.X1 : p.X0;
     double r[1] = {0.0};
     const size_t stride = (size_t) gridDim.x * blockDim.x, t0 = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
-    for (size_t e = t0; e < (size_t) p.E; e += stride)
-        r[0] += (double) p.La_d1[e] * (double) rabs(X[p.Eu[e]] - X[p.Ev[e]]);
-    for (size_t v = t0; v < (size_t) p.V; v += stride) {
+    const bool slab = p.slab.on != 0;                        // slab-sharded: owned vertices, edges whose first end is owned
+    for (size_t e = t0; e < (size_t) p.E; e += stride) {
+        const int u = p.Eu[e];
+        if (slab && (u < p.vbeg || u >= p.vend)) continue;
+        r[0] += (double) p.La_d1[e] * (double) rabs(X[u] - X[p.Ev[e]]);
+    }
+    for (size_t v = (slab ? (size_t) p.vbeg : 0) + t0; v < (slab ? (size_t) p.vend : (size_t) p.V); v += stride) {
         const real x = X[v];
         if (p.N == 0) r[0] += (double) x * ((double) 0.5 * (double) (p.A ? p.A[v] * x : x) - (double) p.Y[v]);
         else if (p.N < 0) r[0] += (double) x * ((double) 0.5 * (double) p.G[v] - (double) p.Y[v]);
@@ -1137,7 +1145,10 @@ __global__ void __launch_bounds__(256) objective_kernel(QP<real> p)
     }
     if (p.N > 0)
         for (size_t n = t0; n < (size_t) p.N; n += stride) r[0] += 0.5 * (double) p.R[n] * (double) p.R[n];
-    if (grid_sum<1>(ctl, p.partial, r, smem) && threadIdx.x == 0) p.dObj[it] = (real) r[0];
+    if (grid_sum<1>(ctl, p.partial, r, smem) && threadIdx.x == 0) {
+        if (slab) *p.obj_part = r[0];                            // travels with the trip's stopping sums (quad_slab_decide)
+        else p.dObj[it] = (real) r[0];
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1338,7 +1349,7 @@ struct QuadSolver : SolverBase {
     DevIn<real> Y, A, La_d1, La_l1, L, X0;
     DevIn<int> Eu, Ev;
     DevBuf<real> w, thc, Z0, Z1, X0b, X1b, P0b, P1b, T, Sinv, Ga, Ga0, G, Thl1, R, AtY, dObj, dDif, Xout;
-    DevBuf<double> partial, parts, sums, rsum, amp_sums;
+    DevBuf<double> partial, parts, sums, rsum, amp_sums, obj_part;
     DevBuf<int4> pkb;               // per-slot packs for the iteration kernel
     DevBuf<int2> pk2b;
     DevBuf<int> pos, dstb;          // small mode: slot / (owner CTA, slot) of every half-edge key
@@ -1347,6 +1358,7 @@ struct QuadSolver : SolverBase {
     Halo<real> halo;
     SlabLink link;                  // slab-sharded solve (slab.cuh)
     bool slab = false;
+    int recond_parity = 0;          // parity of the trip a reconditioning interrupts
     bool sharded = false;
     int ogrid = 0;                  // CTAs covering the owned vertices
     Ctl *hctl = nullptr;            // pinned mirror of the control block, one per batch in flight
@@ -1376,7 +1388,6 @@ struct QuadSolver : SolverBase {
         if (slab) {
             PFDR_REQUIRE(!sharded, "a solve is sharded either by slabs or by a shard plan");
             PFDR_REQUIRE(N == 0, "slab-sharded solves support diagonal / identity A (N = 0) in this build");
-            PFDR_REQUIRE(q.Obj == nullptr && q.difRcd == (real) 0, "slab-sharded solves do not record Obj nor recondition in this build");
             PFDR_REQUIRE(q.slab->world >= 1 && q.slab->lo <= q.slab->v0 && q.slab->v0 < q.slab->v1 && q.slab->v1 <= q.slab->hi &&
                          q.slab->hi - q.slab->lo == V, "bad slab: need lo <= v0 < v1 <= hi and Vloc = hi - lo");
         }
@@ -1424,13 +1435,16 @@ struct QuadSolver : SolverBase {
         if (slab) {          // what the neighbouring ranks write / copy into lives in the peer-visible arena
             link.reserve(SLAB_Z0, ns * sizeof(real)); link.reserve(SLAB_Z1, ns * sizeof(real));
             link.reserve(SLAB_F0, (size_t) V * sizeof(real)); link.reserve(SLAB_F1, (size_t) V * sizeof(real)); link.reserve(SLAB_T, (size_t) V * sizeof(real));
+            link.reserve(SLAB_X0, (size_t) V * sizeof(real)); link.reserve(SLAB_X1, (size_t) V * sizeof(real));
             link.commit(q.slab->world, q.slab->rank, q.slab->lo, q.slab->hi, q.slab->v0, q.slab->v1, 1);
             Z0.borrow(link.ptr<real>(SLAB_Z0), ns); Z1.borrow(link.ptr<real>(SLAB_Z1), ns);
             P0b.borrow(link.ptr<real>(SLAB_F0), V); P1b.borrow(link.ptr<real>(SLAB_F1), V); T.borrow(link.ptr<real>(SLAB_T), V);
+            X0b.borrow(link.ptr<real>(SLAB_X0), V); X1b.borrow(link.ptr<real>(SLAB_X1), V);
+            obj_part.alloc(1); obj_part.zero();
         } else {
-            Z0.alloc(ns); Z1.alloc(ns); P0b.alloc(V); P1b.alloc(V); T.alloc(V);
+            Z0.alloc(ns); Z1.alloc(ns); P0b.alloc(V); P1b.alloc(V); T.alloc(V); X0b.alloc(V); X1b.alloc(V);
         }
-        X0b.alloc(V); X1b.alloc(V); Sinv.alloc(V); Ga.alloc(V); Ga0.alloc(V);
+        Sinv.alloc(V); Ga.alloc(V); Ga0.alloc(V);
         if (La_l1.p) Thl1.alloc(V);
         if (N != 0) G.alloc(V);
         if (N > 0) { R.alloc(N); AtY.alloc(V); rsum.alloc(N); p.rsum = rsum.p; }
@@ -1460,7 +1474,7 @@ struct QuadSolver : SolverBase {
         p.lo = q.lo; p.hi = q.hi;
         p.has_lo = (q.prox_kind == 1 && -HUGE_VAL < (double) q.lo);
         p.has_hi = (q.prox_kind == 1 && (double) q.hi < HUGE_VAL);
-        p.rho = q.rho; p.condMin = q.condMin; p.dObj = dObj.p; p.dDif = dDif.p;
+        p.rho = q.rho; p.condMin = q.condMin; p.dObj = dObj.p; p.dDif = dDif.p; p.obj_part = obj_part.p;
 
         // dense operator geometry
         const int vmax = (sizeof(real) == 4) ? 4 : 2;
@@ -1499,7 +1513,7 @@ struct QuadSolver : SolverBase {
         p.slab.nbchunks = (p.slab.lowB + p.slab.highB + 31) / 32;
     }
     // ghost zones of the neighbours <- this rank's boundary: metric T, forward point and cut-edge copies of the parity-0 buffers
-    void slab_refresh()
+    void slab_refresh(int par = 0)
     {
         const size_t Vp = (size_t) q.V;
         const int ND = dg.ND;
@@ -1512,11 +1526,12 @@ struct QuadSolver : SolverBase {
             const long long dshift = link.lo - b.lo;
             const size_t Vn = (size_t) (b.hi - b.lo);
             link.push<real>(SLAB_T, nb, (size_t) first, (size_t) depth, dshift);
-            link.push<real>(SLAB_F0, nb, (size_t) first, (size_t) depth, dshift);
+            link.push<real>(par ? SLAB_F1 : SLAB_F0, nb, (size_t) first, (size_t) depth, dshift);
+            link.push<real>(par ? SLAB_X1 : SLAB_X0, nb, (size_t) first, (size_t) depth, dshift);
             for (int i = 0; i < ND; i++) {                                       // copies on the cut edges of offset d_i
                 const long long d = std::min<long long>(dg.off[i], depth), f = side ? p.vend - d : p.vbeg;
                 const int plane = side ? i : ND + i;                             // our out_i copies go up, our in_i copies down
-                link.push<real>(SLAB_Z0, nb, (size_t) plane * Vp + (size_t) f, (size_t) d,
+                link.push<real>(par ? SLAB_Z1 : SLAB_Z0, nb, (size_t) plane * Vp + (size_t) f, (size_t) d,
                                 (long long) plane * ((long long) Vn - (long long) Vp) + dshift);
             }
         }
@@ -1547,6 +1562,7 @@ struct QuadSolver : SolverBase {
             SlabPeer<real> &pe = side ? p.phi : p.plo;
             pe.Z[0] = link.ptr<real>(SLAB_Z0, nb); pe.Z[1] = link.ptr<real>(SLAB_Z1, nb);
             pe.F[0] = link.ptr<real>(SLAB_F0, nb); pe.F[1] = link.ptr<real>(SLAB_F1, nb);
+            pe.X[0] = link.ptr<real>(SLAB_X0, nb); pe.X[1] = link.ptr<real>(SLAB_X1, nb);
             pe.plane = (size_t) (link.blobs[nb].hi - link.blobs[nb].lo);
             pe.shift = link.lo - link.blobs[nb].lo;
         }
@@ -1702,10 +1718,18 @@ struct QuadSolver : SolverBase {
         if (!thc.p) thc.alloc(std::max<size_t>(nhalf, 1));
         if (!p.thc) { thc.zero(); p.thc = thc.p; }                       // first reconditioning since setup() / reset()
         if (gexec) { cudaGraphExecDestroy(gexec); gexec = nullptr; }   // kernel parameters changed
-        PFDR_LAUNCH(amp_kernel<real>, vgrid, 256, 0, p, 1);
+        const bool linked = slab && link.world > 1;
+        if (linked) {               // mean amplitude over all ranks' vertices
+            p.sharded = 1;
+            PFDR_LAUNCH(amp_kernel<real>, ogrid, 256, 0, p, 1);
+            link.allreduce_sum(amp_sums.p, 2);
+            PFDR_LAUNCH(amp_finish_kernel<real>, 1, 1, 0, p, 1);
+            p.sharded = 0;
+        } else PFDR_LAUNCH(amp_kernel<real>, vgrid, 256, 0, p, 1);
         if (dia) quad_dia_launch_recond<real>(p, vgrid);
         else PFDR_LAUNCH(recond_vertex_kernel<real>, vgrid, 256, 0, p);
         pack_slots();
+        if (linked) slab_refresh(recond_parity);     // new metric, forward point and copies of the boundary -> neighbours' ghost zones
         PFDR_LAUNCH(resume_kernel<real>, 1, 1, 0, p, 0.01);                   // ref :458
     }
 
@@ -1887,6 +1911,7 @@ struct QuadSolver : SolverBase {
             if (verdict == 1) break;
             if (verdict == 2) {         // frozen for a reconditioning; batches <= k were no-ops past the freeze
                 PFDR_CUDA(cudaStreamSynchronize(st));
+                recond_parity = hctl[k & 1].it & 1;            // (the device froze at the trip that asked for it)
                 recondition();
                 fresh_from = k + 1;
                 budget = enqueued + (long long) q.itMax + 1 + 2LL * batch;
@@ -1901,7 +1926,14 @@ struct QuadSolver : SolverBase {
         PFDR_CUDA(cudaEventElapsedTime(&ms, ev_b, ev_c));
         ctx().stats.loop_ms = ms;
         ctx().stats.iterations = hctl[0].it;
-        if (slab && link.world > 1) slab_check();
+        if (slab && link.world > 1) {
+            if (q.Obj) {             // objective of the final iterate: the last trip's parts were not carried by an iteration
+                link.allreduce_sum(obj_part.p, 1);
+                PFDR_LAUNCH(quad_obj_final_kernel<real>, 1, 1, 0, p);
+                PFDR_CUDA(cudaStreamSynchronize(st));
+            }
+            slab_check();
+        }
     }
 
     // waits for batch slot b: 0 = still running, 1 = finished, 2 = frozen for a reconditioning

@@ -45,6 +45,7 @@ struct QP {                       // kernel parameter block
     // slab-sharded solve (slab.cuh): V counts the vertices held (owned + ghost zones), [vbeg, vend) are the owned ones
     SlabDev slab;
     SlabPeer<real> plo, phi;      // the ghost zones this rank writes: in the rank below / above (F = forward point P)
+    double *obj_part;             // [1] this rank's part of the objective of the current iterate (Obj requested)
 };
 
 // explicitly rounded operations: the d1 prox below is shared by the kernels of both layouts and must give the same bits
@@ -169,20 +170,22 @@ __device__ int quad_slab_decide(const QP<real> &p, int it)
     if (p.slab.nb_lo >= 0) ok = slab_wait(&me->halo_flag[p.slab.nb_lo], target, me) && ok;
     if (p.slab.nb_hi >= 0) ok = slab_wait(&me->halo_flag[p.slab.nb_hi], target, me) && ok;
     const int track = ctl->track;
-    double dif = ctl->dif;
-    if (ok && track) {
-        double d = 0.0, c = 0.0;
-        for (int q = 0; q < p.slab.world; q++) {                                   // rank order: same bits everywhere
+    const bool all = track || p.dObj;                               // someone needs every rank's sums of the previous trip
+    double dif = ctl->dif, d = 0.0, c = 0.0, obj = 0.0;
+    if (ok && all) {
+        for (int q = 0; q < p.slab.world; q++) {                    // rank order: same bits everywhere
             ok = slab_wait(&me->sum_flag[q], target, me) && ok;
-            d += me->sums[(it - 1) & 1][q][0]; c += me->sums[(it - 1) & 1][q][1];
+            d += me->sums[(it - 1) & 1][q][0]; c += me->sums[(it - 1) & 1][q][1]; obj += me->sums[(it - 1) & 1][q][2];
         }
-        dif = (c > ctl->eps) ? d / c : d / ctl->eps;                               // ref :515-529
+        if (track) dif = (c > ctl->eps) ? d / c : d / ctl->eps;     // ref :515-529
     }
+    const bool recond_done = ctl->scratch[1] == (double) (it + 1);  // this trip already reconditioned (the test is made once per trip)
     int state = ST_RUN;
     if (!ok || it == ctl->itMax || (real) dif < (real) ctl->tol) state = ST_FINAL;
-    else if ((real) dif < (real) ctl->rcd) state = ST_RECOND;
+    else if (!recond_done && (real) dif < (real) ctl->rcd) state = ST_RECOND;
     if (blockIdx.x == 0) {
         if (track && ok) { ctl->dif = dif; if (p.dDif) p.dDif[it - 1] = (real) dif; }
+        if (p.dObj && ok) p.dObj[it - 1] = (real) obj;              // objective of the iterate the previous trip started from
         if (state != ST_RUN) { ctl->state = state; ctl->hold = 1; }
     }
     return state;

@@ -210,8 +210,8 @@ __global__ void __launch_bounds__(256, MINB) quad_dia_iter_kernel(QP<real> p)
             const real fp = forward_point_diag(p, v, x);
             Pn[v] = fp;
             if (SLAB) {     // boundary vertices: the neighbouring rank gathers this forward point from its ghost zone
-                if (p.plo.F[0] && v < p.vbeg + p.slab.band) p.plo.F[cur ^ 1][(long long) v + p.plo.shift] = fp;
-                if (p.phi.F[0] && v >= p.vend - p.slab.band) p.phi.F[cur ^ 1][(long long) v + p.phi.shift] = fp;
+                if (p.plo.F[0] && v < p.vbeg + p.slab.band) { p.plo.F[cur ^ 1][(long long) v + p.plo.shift] = fp; p.plo.X[cur ^ 1][(long long) v + p.plo.shift] = x; }
+                if (p.phi.F[0] && v >= p.vend - p.slab.band) { p.phi.F[cur ^ 1][(long long) v + p.phi.shift] = fp; p.phi.X[cur ^ 1][(long long) v + p.phi.shift] = x; }
             }
         }
         const real dx = xo - x;
@@ -222,8 +222,8 @@ __global__ void __launch_bounds__(256, MINB) quad_dia_iter_kernel(QP<real> p)
     if (grid_sum<2>(ctl, p.partial, tot, smem) && threadIdx.x == 0) {
         if (SLAB) {
             ctl->it = it + 1;
-            const double v4[SLAB_NSUM] = {tot[0], tot[1], 0.0, 0.0};
-            if (ctl->track) slab_post(p.slab, v4, (unsigned long long) (it + 1));     // stopping sums: only when someone waits for them
+            const double v4[SLAB_NSUM] = {tot[0], tot[1], p.obj_part ? *p.obj_part : 0.0, 0.0};
+            if (ctl->track || p.dObj) slab_post(p.slab, v4, (unsigned long long) (it + 1));   // only when someone waits for them
         } else if (p.sharded) { p.sums[2 * p.rank] = tot[0]; p.sums[2 * p.rank + 1] = tot[1]; }
         else quad_finalize(p, it, tot[0], tot[1]);
     }
@@ -259,7 +259,8 @@ void quad_dia_launch_iter(const QP<real> &p, int grid)
     constexpr int G = sizeof(real) == 4 ? 6 : 3;         // half-edges requested at a time (5 loads each)
     const int g = std::min(grid, num_sms() * MINB);      // one wave of resident CTAs
 #define CALL(N_)                                                                                         \
-    if (p.slab.on) PFDR_LAUNCH((quad_dia_iter_kernel<real, false, N_, G, MINB, true>), g, 256, 0, p);    \
+    if (p.slab.on && p.thc) PFDR_LAUNCH((quad_dia_iter_kernel<real, true, N_, G, MINB, true>), g, 256, 0, p);   \
+    else if (p.slab.on) PFDR_LAUNCH((quad_dia_iter_kernel<real, false, N_, G, MINB, true>), g, 256, 0, p);    \
     else if (p.thc) PFDR_LAUNCH((quad_dia_iter_kernel<real, true, N_, G, MINB>), g, 256, 0, p);          \
     else PFDR_LAUNCH((quad_dia_iter_kernel<real, false, N_, G, MINB>), g, 256, 0, p)
     PFDR_ND_SWITCH(CALL);

@@ -126,6 +126,7 @@ template <typename real>
 __global__ void simplex_resume_kernel(SP<real> p)
 {
     p.ctl->rcd *= 0.1; p.ctl->state = ST_RUN; p.ctl->hold = 0; p.ctl->scratch[0] = 1.0;     // ref :563
+    p.ctl->scratch[1] = (double) (p.ctl->it + 1);            // slab-sharded: this trip's reconditioning test has been made
 }
 
 template <typename real>
@@ -299,7 +300,9 @@ __global__ void __launch_bounds__(256) simplex_objective_kernel(SP<real> p)
     const real *__restrict__ P = (it & 1) ? p.P1 : p.P0;
     double r[1] = {0.0};
     const size_t stride = (size_t) gridDim.x * blockDim.x, t0 = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
-    for (size_t i = t0; i < (size_t) p.V * K; i += stride) {
+    const bool slab = p.slab.on != 0;                        // slab-sharded: owned vertices, edges whose first end is owned
+    const size_t i0 = slab ? (size_t) p.vbeg * K : 0, i1 = slab ? (size_t) p.vend * K : (size_t) p.V * K;
+    for (size_t i = i0 + t0; i < i1; i += stride) {
         const real Pv = P[i], q = p.Q[i];
         const double lf = p.La_f ? (double) p.La_f[i / K] : 1.0;
         if (p.loss == LOSS_LIN) r[0] -= (double) Pv * (double) q;
@@ -308,10 +311,18 @@ __global__ void __launch_bounds__(256) simplex_objective_kernel(SP<real> p)
     }
     for (size_t i = t0; i < (size_t) p.E * K; i += stride) {
         const size_t e = i / K, k = i % K;
-        r[0] += (double) p.La_d1[e] * (double) sabs(P[(size_t) p.Eu[e] * K + k] - P[(size_t) p.Ev[e] * K + k]);
+        const int u = p.Eu[e];
+        if (slab && (u < p.vbeg || u >= p.vend)) continue;
+        r[0] += (double) p.La_d1[e] * (double) sabs(P[(size_t) u * K + k] - P[(size_t) p.Ev[e] * K + k]);
     }
-    if (grid_sum_s<1>(ctl, p.partial, r, smem) && threadIdx.x == 0) p.dObj[it] = (real) r[0];
+    if (grid_sum_s<1>(ctl, p.partial, r, smem) && threadIdx.x == 0) {
+        if (slab) *p.obj_part = r[0];                            // travels with the trip's stopping sums (simplex_slab_decide)
+        else p.dObj[it] = (real) r[0];
+    }
 }
+
+template <typename real>
+__global__ void simplex_obj_final_kernel(SP<real> p) { p.dObj[p.ctl->it] = (real) *p.obj_part; }
 
 template <typename real>
 __global__ void simplex_extract_kernel(SP<real> p, real *__restrict__ out)
@@ -356,11 +367,12 @@ struct SimplexSolver : SolverBase {
     DevIn<int> Eu, Ev;
     DevBuf<real> w, wk, thk, Z0, Z1, Pa, Pb, Fa, Fb, T, GaQ, Sinv, Sinvk, Gn, GaU, dObj, dDif, Pout, Qal;
     DevBuf<int> lab, order;
-    DevBuf<double> partial, sums;
+    DevBuf<double> partial, sums, obj_part;
     Halo<real> halo;
     SlabLink link;                  // slab-sharded solve (slab.cuh)
     bool slab = false;
     int slab_lowB = 0, slab_highB = 0, slab_nbchunks = 0;
+    int hctl_it_parity = 0;         // parity of the trip a reconditioning interrupts
     bool sharded = false;
     Ctl *hctl = nullptr;
     cudaEvent_t ev[2]{}, ev_a{}, ev_b{}, ev_c{};
@@ -386,7 +398,6 @@ struct SimplexSolver : SolverBase {
         slab = q.slab != nullptr;
         if (slab) {
             PFDR_REQUIRE(!sharded, "a solve is sharded either by slabs or by a shard plan");
-            PFDR_REQUIRE(q.Obj == nullptr && q.difRcd == (real) 0, "slab-sharded solves do not record Obj nor recondition in this build");
             PFDR_REQUIRE(q.slab->world >= 1 && q.slab->lo <= q.slab->v0 && q.slab->v0 < q.slab->v1 && q.slab->v1 <= q.slab->hi &&
                          q.slab->hi - q.slab->lo == V, "bad slab: need lo <= v0 < v1 <= hi and Vloc = hi - lo");
         }
@@ -457,13 +468,16 @@ struct SimplexSolver : SolverBase {
         if (slab) {          // what the neighbouring ranks write / copy into lives in the peer-visible arena
             link.reserve(SLAB_Z0, ns * K * sizeof(real)); link.reserve(SLAB_Z1, ns * K * sizeof(real));
             link.reserve(SLAB_F0, VK * sizeof(real)); link.reserve(SLAB_F1, VK * sizeof(real)); link.reserve(SLAB_T, VK * sizeof(real));
+            link.reserve(SLAB_X0, VK * sizeof(real)); link.reserve(SLAB_X1, VK * sizeof(real));
             link.commit(q.slab->world, q.slab->rank, q.slab->lo, q.slab->hi, q.slab->v0, q.slab->v1, K);
             Z0.borrow(link.ptr<real>(SLAB_Z0), ns * K); Z1.borrow(link.ptr<real>(SLAB_Z1), ns * K);
             Fa.borrow(link.ptr<real>(SLAB_F0), VK); Fb.borrow(link.ptr<real>(SLAB_F1), VK); T.borrow(link.ptr<real>(SLAB_T), VK);
+            Pa.borrow(link.ptr<real>(SLAB_X0), VK); Pb.borrow(link.ptr<real>(SLAB_X1), VK);
+            obj_part.alloc(1); obj_part.zero();
         } else {
-            Z0.alloc(ns * K); Z1.alloc(ns * K); Fa.alloc(VK); Fb.alloc(VK); T.alloc(VK);
+            Z0.alloc(ns * K); Z1.alloc(ns * K); Fa.alloc(VK); Fb.alloc(VK); T.alloc(VK); Pa.alloc(VK); Pb.alloc(VK);
         }
-        Pa.alloc(VK); Pb.alloc(VK); GaQ.alloc(VK); Sinv.alloc(V);
+        GaQ.alloc(VK); Sinv.alloc(V);
         if (q.difRcd > (real) 0) GaU.alloc(VK);
         Z0.zero(); Z1.zero(); w.zero();
         if (padded) {           // what the extra labels read: T = 1 (a denominator), everything else 0
@@ -522,7 +536,7 @@ struct SimplexSolver : SolverBase {
         p.P0 = Pa.p; p.P1 = Pb.p; p.F0 = Fa.p; p.F1 = Fb.p; p.T = T.p; p.GaQ = GaQ.p; p.Sinv = Sinv.p;
         p.Sinvk = nullptr; p.Gn = nullptr; p.GaU = GaU.p; p.lab = lab.p;
         p.Q = Q.p; p.La_f = La_f.p; p.La_d1 = La_d1.p; p.Eu = Eu.p; p.Ev = Ev.p;
-        p.partial = partial.p; p.dObj = dObj.p; p.dDif = dDif.p;
+        p.partial = partial.p; p.dObj = dObj.p; p.dDif = dDif.p; p.obj_part = obj_part.p;
         p.stream_z = 0;
 
         if (sharded) { halo.setup(*q.shard, g.hkey.p, g.nslots, 2 * (size_t) E, K); halo.build(HALO_VA0 | HALO_VA1); halo.build(HALO_VA0 | HALO_Z); }
@@ -568,7 +582,7 @@ struct SimplexSolver : SolverBase {
 
     // ghost zones of the neighbours <- this rank's boundary: metric T, forward point and cut-edge copies of the CURRENT
     // (parity 0) buffers; afterwards every rank has everything the first trip reads
-    void slab_refresh()
+    void slab_refresh(int par = 0)
     {
         const size_t VK = (size_t) q.V * p.K;
         const int K = p.K, ND = dg.ND;
@@ -581,11 +595,12 @@ struct SimplexSolver : SolverBase {
             const long long dshift = (link.lo - b.lo) * K;
             const size_t VKn = (size_t) (b.hi - b.lo) * K;
             link.push<real>(SLAB_T, nb, (size_t) first * K, (size_t) depth * K, dshift);
-            link.push<real>(SLAB_F0, nb, (size_t) first * K, (size_t) depth * K, dshift);
+            link.push<real>(par ? SLAB_F1 : SLAB_F0, nb, (size_t) first * K, (size_t) depth * K, dshift);
+            link.push<real>(par ? SLAB_X1 : SLAB_X0, nb, (size_t) first * K, (size_t) depth * K, dshift);
             for (int i = 0; i < ND; i++) {                                       // copies on the cut edges of offset d_i
                 const long long d = std::min<long long>(dg.off[i], depth), f = side ? p.vend - d : p.vbeg;
                 const int plane = side ? i : ND + i;                             // our out_i copies go up, our in_i copies down
-                link.push<real>(SLAB_Z0, nb, (size_t) plane * VK + (size_t) f * K, (size_t) d * K,
+                link.push<real>(par ? SLAB_Z1 : SLAB_Z0, nb, (size_t) plane * VK + (size_t) f * K, (size_t) d * K,
                                 (long long) plane * ((long long) VKn - (long long) VK) + dshift);
             }
         }
@@ -616,6 +631,7 @@ struct SimplexSolver : SolverBase {
             SlabPeer<real> &pe = side ? p.phi : p.plo;
             pe.Z[0] = link.ptr<real>(SLAB_Z0, nb); pe.Z[1] = link.ptr<real>(SLAB_Z1, nb);
             pe.F[0] = link.ptr<real>(SLAB_F0, nb); pe.F[1] = link.ptr<real>(SLAB_F1, nb);
+            pe.X[0] = link.ptr<real>(SLAB_X0, nb); pe.X[1] = link.ptr<real>(SLAB_X1, nb);
             pe.plane = (size_t) (link.blobs[nb].hi - link.blobs[nb].lo) * p.K;
             pe.shift = (link.lo - link.blobs[nb].lo) * p.K;
         }
@@ -693,6 +709,7 @@ struct SimplexSolver : SolverBase {
         p.wk = wk.p; p.thk = thk.p; p.Sinvk = Sinvk.p; p.Gn = Gn.p;
         if (gexec) { cudaGraphExecDestroy(gexec); gexec = nullptr; }
         launch_precond(nullptr, 1);
+        if (slab && link.world > 1) slab_refresh(hctl_it_parity);   // new metric, forward point and copies of the boundary -> neighbours' ghost zones
         PFDR_LAUNCH(simplex_resume_kernel<real>, 1, 1, 0, p);
     }
 
@@ -729,6 +746,7 @@ struct SimplexSolver : SolverBase {
             if (verdict == 1) break;
             if (verdict == 2) {
                 PFDR_CUDA(cudaStreamSynchronize(st));
+                hctl_it_parity = hctl[k & 1].it & 1;            // (the device froze at the trip that asked for it)
                 recondition();
                 fresh_from = k + 1;
                 budget = enqueued + (long long) q.itMax + 1 + 2LL * batch;
@@ -743,7 +761,14 @@ struct SimplexSolver : SolverBase {
         PFDR_CUDA(cudaEventElapsedTime(&ms, ev_b, ev_c));
         ctx().stats.loop_ms = ms;
         ctx().stats.iterations = hctl[0].it;
-        if (slab && link.world > 1) slab_check();
+        if (slab && link.world > 1) {
+            if (q.Obj) {             // objective of the final iterate: the last trip's parts were not carried by an iteration
+                link.allreduce_sum(obj_part.p, 1);
+                PFDR_LAUNCH(simplex_obj_final_kernel<real>, 1, 1, 0, p);
+                PFDR_CUDA(cudaStreamSynchronize(st));
+            }
+            slab_check();
+        }
     }
 
     void fetch(void *Po, int *ito, void *Objo, void *Difo) override

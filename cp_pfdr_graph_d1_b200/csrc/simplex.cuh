@@ -42,6 +42,7 @@ struct SP {
     // slab-sharded solve (slab.cuh): V counts the vertices held (owned + ghost zones), [vbeg, vend) are the owned ones
     SlabDev slab;
     SlabPeer<real> plo, phi;      // the ghost zones this rank writes: in the rank below / above
+    double *obj_part;             // [1] this rank's part of the objective of the current iterate (Obj requested)
 };
 
 template <typename real> __device__ __forceinline__ real sabs(real a) { return a < (real) 0 ? -a : a; }
@@ -243,7 +244,8 @@ template <typename real, int LPT, bool PERK, int LOSS>
 __device__ __forceinline__ double simplex_epilogue(const SP<real> &p, Ctl *ctl, bool on, int v, int k0, size_t vk,
     VecN<real, LPT> acc, const VecN<real, LPT> &Tv, const VecN<real, LPT> &pold, real *__restrict__ Pn, real *__restrict__ Fn,
     const VecN<real, LPT> *gaq_pre = nullptr,       // GaQ of the lane's labels when the caller fetched it ahead of time
-    real *Fpush_lo = nullptr, real *Fpush_hi = nullptr)   // slab-sharded: where a neighbouring rank keeps this vertex's forward point
+    real *Fpush_lo = nullptr, real *Fpush_hi = nullptr,   // slab-sharded: where a neighbouring rank keeps this vertex's forward point
+    real *Ppush_lo = nullptr, real *Ppush_hi = nullptr)   // ... and its iterate (read there by the objective and by a reconditioning)
 {
     typedef VecN<real, LPT> vec;
     const int K = p.K, TPV = p.TPV;
@@ -287,8 +289,8 @@ __device__ __forceinline__ double simplex_epilogue(const SP<real> &p, Ctl *ctl, 
         }
         stv<real, LPT>(Pn + vk, pnew);
         stv<real, LPT>(Fn + vk, f);
-        if (Fpush_lo) stv<real, LPT>(Fpush_lo, f);
-        if (Fpush_hi) stv<real, LPT>(Fpush_hi, f);
+        if (Fpush_lo) { stv<real, LPT>(Fpush_lo, f); stv<real, LPT>(Ppush_lo, pnew); }
+        if (Fpush_hi) { stv<real, LPT>(Fpush_hi, f); stv<real, LPT>(Ppush_hi, pnew); }
     }
     double red = 0.0;
     if (p.by_label) {                                                         // ref :657-676
@@ -333,17 +335,22 @@ __device__ int simplex_slab_decide(const SP<real> &p, int it)
     if (p.slab.nb_lo >= 0) ok = slab_wait(&me->halo_flag[p.slab.nb_lo], target, me) && ok;
     if (p.slab.nb_hi >= 0) ok = slab_wait(&me->halo_flag[p.slab.nb_hi], target, me) && ok;
     const int track = ctl->track;
-    double dif = ctl->dif;
-    if (ok && track) {
-        double s = 0.0;
-        for (int q = 0; q < p.slab.world; q++) { ok = slab_wait(&me->sum_flag[q], target, me) && ok; s += me->sums[(it - 1) & 1][q][0]; }   // rank order
-        dif = p.by_label ? s : s / (double) p.Vglobal;              // ref :688
+    const bool all = track || p.dObj;                               // someone needs every rank's sums of the previous trip
+    double dif = ctl->dif, s = 0.0, obj = 0.0;
+    if (ok && all) {
+        for (int q = 0; q < p.slab.world; q++) {                    // rank order: same bits everywhere
+            ok = slab_wait(&me->sum_flag[q], target, me) && ok;
+            s += me->sums[(it - 1) & 1][q][0]; obj += me->sums[(it - 1) & 1][q][2];
+        }
+        if (track) dif = p.by_label ? s : s / (double) p.Vglobal;   // ref :688
     }
+    const bool recond_done = ctl->scratch[1] == (double) (it + 1);  // this trip already reconditioned (the test is made once per trip)
     int state = ST_RUN;
     if (!ok || it == ctl->itMax || (real) dif < (real) ctl->tol) state = ST_FINAL;
-    else if ((real) dif < (real) ctl->rcd) state = ST_RECOND;
+    else if (!recond_done && (real) dif < (real) ctl->rcd) state = ST_RECOND;
     if (blockIdx.x == 0) {
         if (track && ok) { ctl->dif = dif; if (p.dDif) p.dDif[it - 1] = (real) dif; }
+        if (p.dObj && ok) p.dObj[it - 1] = (real) obj;              // objective of the iterate the previous trip started from
         if (state != ST_RUN) { ctl->state = state; ctl->hold = 1; }
     }
     return state;

@@ -227,20 +227,20 @@ __global__ void __launch_bounds__(256, MINB) simplex_dia_iter_kernel(SP<real> p)
                 }
             }
         }
-        real *flo = nullptr, *fhi = nullptr;
+        real *flo = nullptr, *fhi = nullptr, *xlo = nullptr, *xhi = nullptr;
         if (SLAB && on) {
-            if (p.plo.F[0] && v < p.vbeg + p.slab.band) flo = p.plo.F[cur ^ 1] + ((long long) vk + p.plo.shift);
-            if (p.phi.F[0] && v >= p.vend - p.slab.band) fhi = p.phi.F[cur ^ 1] + ((long long) vk + p.phi.shift);
+            if (p.plo.F[0] && v < p.vbeg + p.slab.band) { flo = p.plo.F[cur ^ 1] + ((long long) vk + p.plo.shift); xlo = p.plo.X[cur ^ 1] + ((long long) vk + p.plo.shift); }
+            if (p.phi.F[0] && v >= p.vend - p.slab.band) { fhi = p.phi.F[cur ^ 1] + ((long long) vk + p.phi.shift); xhi = p.phi.X[cur ^ 1] + ((long long) vk + p.phi.shift); }
         }
-        red += simplex_epilogue<real, LPT, PERK, LOSS>(p, ctl, on, v, k0, vk, acc, Tv, pold, Pn, Fn, &gaq, flo, fhi);
+        red += simplex_epilogue<real, LPT, PERK, LOSS>(p, ctl, on, v, k0, vk, acc, Tv, pold, Pn, Fn, &gaq, flo, fhi, xlo, xhi);
     }
     if (SLAB && bcount) slab_boundary_done(p.slab, &ctl->bdone, bcount, it);
     double tot[1] = {red};
     if (grid_sum_s<1>(ctl, p.partial, tot, smem) && threadIdx.x == 0) {
         if (SLAB) {
             ctl->it = it + 1;
-            const double v4[SLAB_NSUM] = {tot[0], 0.0, 0.0, 0.0};
-            if (ctl->track) slab_post(p.slab, v4, (unsigned long long) (it + 1));     // stopping sums: only when someone waits for them
+            const double v4[SLAB_NSUM] = {tot[0], 0.0, p.obj_part ? *p.obj_part : 0.0, 0.0};
+            if (ctl->track || p.dObj) slab_post(p.slab, v4, (unsigned long long) (it + 1));   // only when someone waits for them
         } else if (p.sharded) p.sums[p.rank] = tot[0];
         else simplex_finalize(p, it, tot[0]);
     }
@@ -283,12 +283,10 @@ void launch_iter_nd(const SP<real> &p, int grid)
         if (ws > 1) { PFDR_LAUNCH((simplex_dia_iter_kernel<real, LPT, PERK, LOSS, ND, G, MINB>), std::min(grid, wave * ws), 256, 0, p); return; }
     }
 #endif
-    if constexpr (!PERK) {
-        if (p.slab.on) {
-            const int w2 = resident_ctas(simplex_dia_iter_kernel<real, LPT, PERK, LOSS, ND, G, MINB, true>, 256, MINB);
-            PFDR_LAUNCH((simplex_dia_iter_kernel<real, LPT, PERK, LOSS, ND, G, MINB, true>), std::min(grid, w2), 256, 0, p);
-            return;
-        }
+    if (p.slab.on) {
+        const int w2 = resident_ctas(simplex_dia_iter_kernel<real, LPT, PERK, LOSS, ND, G, MINB, true>, 256, MINB);
+        PFDR_LAUNCH((simplex_dia_iter_kernel<real, LPT, PERK, LOSS, ND, G, MINB, true>), std::min(grid, w2), 256, 0, p);
+        return;
     }
     PFDR_LAUNCH((simplex_dia_iter_kernel<real, LPT, PERK, LOSS, ND, G, MINB>), std::min(grid, wave), 256, 0, p);
 }

@@ -172,7 +172,7 @@ class SlabSimplexSolver(_SlabSolver):
     gather all ranks' blobs yourself and call .connect(blobs)."""
 
     def __init__(self, plan, P0, Q, al, La_d1, La_f=None, rho=1.5, condMin=1e-2, difTol=1e-4, itMax=500,
-                 want_dif=False, local=False, connect=True, same_process=False):
+                 want_dif=False, local=False, connect=True, same_process=False, difRcd=0.0, want_obj=False):
         super().__init__()
         dt = np.dtype(P0.dtype)
         R, suf = _CT[dt]
@@ -192,7 +192,7 @@ class SlabSimplexSolver(_SlabSolver):
         f.argtypes = [C.POINTER(C.c_void_p), C.POINTER(_Slab), C.c_int, C.c_int, C.c_int, R, P, P, P, PI, PI, P, R, R, R,
                       R, C.c_int, C.c_int, C.c_int]
         self._chk(f(C.byref(self._h), C.byref(sl), K, plan.Vloc, int(Eu.shape[0]), al, ptr(La_fl), ptr(P0l), ptr(Ql),
-                    ptr(Eu, C.c_int), ptr(Ev, C.c_int), ptr(La_d1l), rho, condMin, 0.0, difTol, itMax, 0, int(want_dif)))
+                    ptr(Eu, C.c_int), ptr(Ev, C.c_int), ptr(La_d1l), rho, condMin, difRcd, difTol, itMax, int(want_obj), int(want_dif)))
         self.setup_stats = last_stats()
         if connect:
             self._connect(plan, same_process)
@@ -205,7 +205,7 @@ class SlabQuadraticSolver(_SlabSolver):
 
     def __init__(self, plan, X0, Y, A, La_d1, La_l1=None, positivity=0, min=-np.inf, max=np.inf, prox="l1", Ltype=0,
                  L=None, rho=1.5, condMin=1e-3, difTol=1e-5, itMax=1000, want_dif=False, local=False, N=None,
-                 connect=True, same_process=False):
+                 connect=True, same_process=False, difRcd=0.0, want_obj=False):
         super().__init__()
         from ._abi import _real_dtype, _ptr
         dt = _real_dtype(X0)
@@ -236,8 +236,8 @@ class SlabQuadraticSolver(_SlabSolver):
                       C.c_int, R, R, C.c_int, P, R, R, R, R, C.c_int, C.c_int, C.c_int]
         self._chk(f(C.byref(self._h), C.byref(sl), 0 if prox == "l1" else 1, plan.Vloc, int(Eu.shape[0]), int(N),
                     _ptr(X0l, R), _ptr(Yl, R), _ptr(Al, R), _ptr(Eu, C.c_int), _ptr(Ev, C.c_int), _ptr(La_d1l, R),
-                    _ptr(La_l1l, R), int(positivity), float(min), float(max), int(Ltype), _ptr(Ll, R), rho, condMin, 0.0,
-                    difTol, itMax, 0, int(want_dif)))
+                    _ptr(La_l1l, R), int(positivity), float(min), float(max), int(Ltype), _ptr(Ll, R), rho, condMin, difRcd,
+                    difTol, itMax, int(want_obj), int(want_dif)))
         self.setup_stats = last_stats()
         if connect:
             self._connect(plan, same_process)

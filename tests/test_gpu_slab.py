@@ -27,14 +27,19 @@ def case_inputs(case):
         n, nz = (12, 16) if "tall" in tag else (14, 14)
         w = synth.c4_simplex(n, K, dt, nz=nz)
         kw = dict(rho=1.5, condMin=1e-2, difTol=0.0 if "notrack" in tag else 1e-4, itMax=40 if "notrack" in tag else 200)
+        if "recond" in tag:            # reconditions on the way (difRcd > 0) and records the objective
+            kw.update(difRcd=1e-2, difTol=1e-5, itMax=300, want_obj=True)
         return fam, w, kw, dt
     w = synth.c2_denoise(20, dt, diag=True)
     w["Ys"] = (w["La_l2"] * w["Y"]).astype(dt)
     kw = dict(rho=1.5, condMin=1e-3, difTol=0.0 if "notrack" in tag else 1e-5, itMax=40 if "notrack" in tag else 300)
+    if "recond" in tag:
+        kw.update(difRcd=1e-3, difTol=1e-6, itMax=500, want_obj=True)
     return fam, w, kw, dt
 
 
 def make_solver(pd, plan, fam, w, kw, dt, **extra):
+    kw = dict(kw)
     if fam == "simplex":
         return pd.SlabSimplexSolver(plan, w["Q"], w["Q"], 0.05, w["La_d1"], want_dif=kw["difTol"] > 0, **kw, **extra)
     V = w["V"]
@@ -57,12 +62,13 @@ def _worker(rank, world, port, case, out):
         res = []
         for _ in range(2):                       # a second (reset, run) on the same handle: flags carry the run number
             st = s.run()
-            r = s.fetch(want_dif=kw["difTol"] > 0)
-            res.append((pd.gather_owned(r.X, plan), r.it, r.Dif))
+            r = s.fetch(want_dif=kw["difTol"] > 0, want_obj=kw.get("want_obj", False))
+            res.append((pd.gather_owned(r.X, plan), r.it, r.Dif, r.Obj))
             s.reset()
         if rank == 0:
             assert np.array_equal(res[0][0], res[1][0]) and res[0][1] == res[1][1]
-            np.savez(out, X=res[0][0], it=res[0][1], Dif=res[0][2] if res[0][2] is not None else np.zeros(0), gpus=st["gpus"], layout=st["layout"])
+            np.savez(out, X=res[0][0], it=res[0][1], Dif=res[0][2] if res[0][2] is not None else np.zeros(0),
+                     Obj=res[0][3] if res[0][3] is not None else np.zeros(0), gpus=st["gpus"], layout=st["layout"])
         s.close()
     finally:
         dist.destroy_process_group()
@@ -73,11 +79,11 @@ def single_gpu(gpu_api, oracle, case):
     b = gpu_api._b()
     if fam == "simplex":
         args = (w["Q"], 0.05, w["Eu"], w["Ev"], w["La_d1"])
-        k2 = dict(kw, difRcd=0.0, want_dif=kw["difTol"] > 0)
+        k2 = dict(dict(difRcd=0.0), **kw, want_dif=kw["difTol"] > 0)
         return b.PFDR_graph_loss_d1_simplex(w["Q"].copy(), *args, **k2), oracle.PFDR_graph_loss_d1_simplex(w["Q"].copy(), *args, **k2)
     V = w["V"]
     args = (w["Ys"], w["La_l2"], w["Eu"], w["Ev"], w["La_d1"], np.full(V, 0.05, dt), 1, 1, w["La_l2"])
-    k2 = dict(kw, difRcd=0.0, N=0, want_dif=kw["difTol"] > 0)
+    k2 = dict(dict(difRcd=0.0), **kw, N=0, want_dif=kw["difTol"] > 0)
     return b.PFDR_graph_quadratic_d1_l1(np.zeros(V, dt), *args, **k2), oracle.PFDR_graph_quadratic_d1_l1(np.zeros(V, dt), *args, **k2)
 
 
@@ -95,7 +101,8 @@ def check(got_X, got_it, got_Dif, one, ref, dt, exact=True):
     assert rel(got_X, ref.X) < (1e-5 if dt is np.float64 else 1e-3)
 
 
-CASES = ["simplex_k5", "simplex_k16", "simplex_k16notrack", "simplex_k16f32", "simplex_k5tall", "quad_f64", "quad_f32", "quad_notrack"]
+CASES = ["simplex_k5", "simplex_k16", "simplex_k16notrack", "simplex_k16f32", "simplex_k5tall", "simplex_k16recond", "simplex_k5tallrecond",
+         "quad_f64", "quad_f32", "quad_notrack", "quad_recond"]
 
 
 @pytest.mark.parametrize("world", [2, 4])
@@ -115,6 +122,8 @@ def test_slab_ranks_match_single_gpu(gpu_api, oracle, tmp_path, case, world):
     one, ref = single_gpu(gpu_api, oracle, case)
     # (quadratic family: the preconditioner's mean amplitude is a sum over all vertices, added rank by rank)
     check(got["X"], int(got["it"]), got["Dif"], one, ref, case_inputs(case)[3], exact=case.startswith("simplex"))
+    if one.Obj is not None:                                      # objective record: every entry, the final iterate's included
+        assert got["Obj"].shape == one.Obj.shape and np.allclose(got["Obj"], one.Obj, rtol=1e-10)
 
 
 @pytest.mark.parametrize("case", ["simplex_k16", "simplex_k16notrack", "quad_f64", "quad_notrack"])
