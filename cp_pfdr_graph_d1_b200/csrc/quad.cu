@@ -1132,6 +1132,10 @@ __global__ void __launch_bounds__(256) objective_kernel(QP<real> p)
     double r[1] = {0.0};
     const size_t stride = (size_t) gridDim.x * blockDim.x, t0 = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
     const bool slab = p.slab.on != 0;                        // slab-sharded: owned vertices, edges whose first end is owned
+    if (slab) {                                              // ... whose other end may be a ghost: the neighbours' stores have landed
+        if (threadIdx.x == 0) slab_wait_neighbours(p.slab, it);
+        __syncthreads();
+    }
     for (size_t e = t0; e < (size_t) p.E; e += stride) {
         const int u = p.Eu[e];
         if (slab && (u < p.vbeg || u >= p.vend)) continue;

@@ -301,6 +301,10 @@ __global__ void __launch_bounds__(256) simplex_objective_kernel(SP<real> p)
     double r[1] = {0.0};
     const size_t stride = (size_t) gridDim.x * blockDim.x, t0 = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
     const bool slab = p.slab.on != 0;                        // slab-sharded: owned vertices, edges whose first end is owned
+    if (slab) {                                              // ... whose other end may be a ghost: the neighbours' stores have landed
+        if (threadIdx.x == 0) slab_wait_neighbours(p.slab, it);
+        __syncthreads();
+    }
     const size_t i0 = slab ? (size_t) p.vbeg * K : 0, i1 = slab ? (size_t) p.vend * K : (size_t) p.V * K;
     for (size_t i = i0 + t0; i < i1; i += stride) {
         const real Pv = P[i], q = p.Q[i];
@@ -417,6 +421,9 @@ struct SimplexSolver : SolverBase {
         if (sizeof(real) == 8 && ((Kv + 1) & ~1) <= 64 && !(fl && fl[0] == '4') &&
             ((size_t) V * (size_t) Kv <= ((size_t) 1 << 23) || (fl && fl[0] == '2'))) LPT = 2;
         if (Kv <= 2 || (fl && fl[0] == '1' && Kv <= 32)) LPT = 1;
+        // more than 128 labels: 8 or 16 labels per lane (a vertex still fits one warp; registers spill - a correct, slow path
+        // for a size the reference accepts)
+        if (Kv > 128) LPT = Kv <= 256 ? 8 : 16;
         cudaStream_t st = ctx().stream;
         for (auto *e : {&ev[0], &ev[1], &ev_a, &ev_b, &ev_c}) *e = event_get();
         PFDR_CUDA(cudaEventRecord(ev_a, st));
@@ -424,7 +431,7 @@ struct SimplexSolver : SolverBase {
         {   // constant-offset graph (grids): index-free layout, PFDR_B200_DIA=0 keeps the half-edge table (tests compare the two)
             const char *de = getenv("PFDR_B200_DIA");
             constexpr int DL = SimplexDiaLanes<real>::LPT;
-            const bool lanes_ok = Kv >= 3 && (Kv + DL - 1) / DL <= 32 && !(fl && fl[0] != '0' + DL);
+            const bool lanes_ok = Kv >= 3 && Kv <= 128 && !(fl && fl[0] != '0' + DL);
             if (!sharded && lanes_ok && !(de && de[0] == '0') && (size_t) V * (size_t) (((Kv + DL - 1) / DL) * DL) * 6 < ((size_t) 1 << 40))
                 dia = build_dia(dg, Eu, Ev, V, E);
             if (dia) LPT = DL;
@@ -433,7 +440,7 @@ struct SimplexSolver : SolverBase {
         }
         K = ((Kv + LPT - 1) / LPT) * LPT;
         const bool padded = K != Kv;
-        PFDR_REQUIRE((K + LPT - 1) / LPT <= 32, "this build supports K <= 128 labels");
+        PFDR_REQUIRE((K + LPT - 1) / LPT <= 32, "this build supports K <= 512 labels");
         static_assert(2 * sizeof(Ctl) <= PINNED_BLOCK, "control block mirror");
         hctl = (Ctl *) pinned_get();
         int TPV = 1, logTPV = 0;
@@ -548,7 +555,9 @@ struct SimplexSolver : SolverBase {
     void launch_precond(const real *Pinit, int recond)
     {
         if (dia) { simplex_dia_launch_precond<real>(p, Pinit, recond, grid); return; }
-        if (LPT == 4) PFDR_LAUNCH((simplex_precond_kernel<real, 4>), grid, 256, 0, p, Pinit, recond);
+        if (LPT == 16) PFDR_LAUNCH((simplex_precond_kernel<real, 16>), grid, 256, 0, p, Pinit, recond);
+        else if (LPT == 8) PFDR_LAUNCH((simplex_precond_kernel<real, 8>), grid, 256, 0, p, Pinit, recond);
+        else if (LPT == 4) PFDR_LAUNCH((simplex_precond_kernel<real, 4>), grid, 256, 0, p, Pinit, recond);
         else if (LPT == 2) { if constexpr (sizeof(real) == 8) PFDR_LAUNCH((simplex_precond_kernel<real, 2>), grid, 256, 0, p, Pinit, recond); }
         else PFDR_LAUNCH((simplex_precond_kernel<real, 1>), grid, 256, 0, p, Pinit, recond);
     }
@@ -652,6 +661,14 @@ struct SimplexSolver : SolverBase {
         }
         else PFDR_LAUNCH((simplex_iter_kernel<real, L, PERK, LOSS, MBD, false, false>), ogrid, 256, 0, p);
     }
+    // K > 128: one generic variant per (labels per lane, loss): 64-bit offsets, one CTA per SM's worth of registers
+    template <int L, bool PERK>
+    void launch_iter_wide()
+    {
+        if (p.loss == LOSS_LIN) PFDR_LAUNCH((simplex_iter_kernel<real, L, PERK, LOSS_LIN, 1, false, false>), ogrid, 256, 0, p);
+        else if (p.loss == LOSS_QUAD) PFDR_LAUNCH((simplex_iter_kernel<real, L, PERK, LOSS_QUAD, 1, false, false>), ogrid, 256, 0, p);
+        else PFDR_LAUNCH((simplex_iter_kernel<real, L, PERK, LOSS_KLA, 1, false, false>), ogrid, 256, 0, p);
+    }
     template <int L, bool PERK>
     void launch_iter_loss()
     {
@@ -667,6 +684,8 @@ struct SimplexSolver : SolverBase {
             PFDR_LAUNCH(simplex_objective_kernel<real>, std::min<unsigned>(cdiv(work, 256), num_sms() * 8), 256, 0, p);
         }
         if (dia) simplex_dia_launch_iter<real>(p, ogrid);
+        else if (LPT == 16) { if (p.wk) launch_iter_wide<16, true>(); else launch_iter_wide<16, false>(); }
+        else if (LPT == 8) { if (p.wk) launch_iter_wide<8, true>(); else launch_iter_wide<8, false>(); }
         else if (LPT == 4) { if (p.wk) launch_iter_loss<4, true>(); else launch_iter_loss<4, false>(); }
         else if (LPT == 2) { if constexpr (sizeof(real) == 8) { if (p.wk) launch_iter_loss<2, true>(); else launch_iter_loss<2, false>(); } }
         else { if (p.wk) launch_iter_loss<1, true>(); else launch_iter_loss<1, false>(); }

@@ -58,12 +58,18 @@ __device__ __forceinline__ VecN<real, L> ldv(const real *q)
     else if constexpr (L == 2) {
         if constexpr (sizeof(real) == 4) { const float2 t = *reinterpret_cast<const float2 *>(q); r.v[0] = t.x; r.v[1] = t.y; }
         else { const double2 t = *reinterpret_cast<const double2 *>(q); r.v[0] = t.x; r.v[1] = t.y; }
-    } else if constexpr (sizeof(real) == 4) {
-        const float4 t = *reinterpret_cast<const float4 *>(q);
-        r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
-    } else {
-        const double2 a = *reinterpret_cast<const double2 *>(q), b = *reinterpret_cast<const double2 *>(q + 2);
-        r.v[0] = a.x; r.v[1] = a.y; r.v[2] = b.x; r.v[3] = b.y;
+    } else {                                         // L = 4, 8, 16: pieces of four labels (16 / 2 x 16 bytes)
+        static_assert(L % 4 == 0, "labels per lane: 1, 2 or a multiple of 4");
+#pragma unroll
+        for (int j = 0; j < L; j += 4) {
+            if constexpr (sizeof(real) == 4) {
+                const float4 t = *reinterpret_cast<const float4 *>(q + j);
+                r.v[j] = t.x; r.v[j + 1] = t.y; r.v[j + 2] = t.z; r.v[j + 3] = t.w;
+            } else {
+                const double2 a = *reinterpret_cast<const double2 *>(q + j), b = *reinterpret_cast<const double2 *>(q + j + 2);
+                r.v[j] = a.x; r.v[j + 1] = a.y; r.v[j + 2] = b.x; r.v[j + 3] = b.y;
+            }
+        }
     }
     return r;
 }
@@ -74,10 +80,15 @@ __device__ __forceinline__ void stv(real *q, const VecN<real, L> &r)
     else if constexpr (L == 2) {
         if constexpr (sizeof(real) == 4) *reinterpret_cast<float2 *>(q) = make_float2(r.v[0], r.v[1]);
         else *reinterpret_cast<double2 *>(q) = make_double2(r.v[0], r.v[1]);
-    } else if constexpr (sizeof(real) == 4) *reinterpret_cast<float4 *>(q) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
-    else {
-        *reinterpret_cast<double2 *>(q) = make_double2(r.v[0], r.v[1]);
-        *reinterpret_cast<double2 *>(q + 2) = make_double2(r.v[2], r.v[3]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < L; j += 4) {
+            if constexpr (sizeof(real) == 4) *reinterpret_cast<float4 *>(q + j) = make_float4(r.v[j], r.v[j + 1], r.v[j + 2], r.v[j + 3]);
+            else {
+                *reinterpret_cast<double2 *>(q + j) = make_double2(r.v[j], r.v[j + 1]);
+                *reinterpret_cast<double2 *>(q + j + 2) = make_double2(r.v[j + 2], r.v[j + 3]);
+            }
+        }
     }
 }
 // streaming (evict-first) store: the new edge copies are not touched again during this launch
@@ -88,10 +99,15 @@ __device__ __forceinline__ void stv_cs(real *q, const VecN<real, L> &r)
     else if constexpr (L == 2) {
         if constexpr (sizeof(real) == 4) __stcs(reinterpret_cast<float2 *>(q), make_float2(r.v[0], r.v[1]));
         else __stcs(reinterpret_cast<double2 *>(q), make_double2(r.v[0], r.v[1]));
-    } else if constexpr (sizeof(real) == 4) __stcs(reinterpret_cast<float4 *>(q), make_float4(r.v[0], r.v[1], r.v[2], r.v[3]));
-    else {
-        __stcs(reinterpret_cast<double2 *>(q), make_double2(r.v[0], r.v[1]));
-        __stcs(reinterpret_cast<double2 *>(q + 2), make_double2(r.v[2], r.v[3]));
+    } else {
+#pragma unroll
+        for (int j = 0; j < L; j += 4) {
+            if constexpr (sizeof(real) == 4) __stcs(reinterpret_cast<float4 *>(q + j), make_float4(r.v[j], r.v[j + 1], r.v[j + 2], r.v[j + 3]));
+            else {
+                __stcs(reinterpret_cast<double2 *>(q + j), make_double2(r.v[j], r.v[j + 1]));
+                __stcs(reinterpret_cast<double2 *>(q + j + 2), make_double2(r.v[j + 2], r.v[j + 3]));
+            }
+        }
     }
 }
 template <typename real, int L>

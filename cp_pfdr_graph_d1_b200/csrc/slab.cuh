@@ -84,6 +84,17 @@ __device__ __forceinline__ bool slab_wait(const unsigned long long *flag, unsign
         __nanosleep(64);
     }
 }
+// before a kernel of trip `it` reads ghost-zone data: the neighbours' stores of trip it - 1 have landed (one thread per CTA calls)
+__device__ __forceinline__ bool slab_wait_neighbours(const SlabDev &s, int it)
+{
+    if (it == 0) return true;
+    SlabMail *me = s.mail[s.rank];
+    const unsigned long long target = (s.run_id << 32) | (unsigned long long) it;
+    bool ok = true;
+    if (s.nb_lo >= 0) ok = slab_wait(&me->halo_flag[s.nb_lo], target, me) && ok;
+    if (s.nb_hi >= 0) ok = slab_wait(&me->halo_flag[s.nb_hi], target, me) && ok;
+    return ok;
+}
 // rank's sums and its "iteration `done` completed" flag into every mailbox (one thread).  One fence, then relaxed flag
 // stores: a release store per destination would wait for the NVLink round trip of each in turn.
 __device__ __forceinline__ void slab_post(const SlabDev &s, const double (&v)[SLAB_NSUM], unsigned long long done)

@@ -139,12 +139,15 @@ SIMPLEX_CASES = ["kla", "kla_weighted", "kla_recond", "kla_labels", "kla_k16", "
                  "quad_k16", "quad_recond_k16", "quad_weighted_k16", "kla_rand_k16",
                  "lin", "lin_recond", "quad", "quad_weighted", "quad_recond", "kla_rand", "kla_it0", "kla_notrack",
                  # more than 32 labels, not a multiple of 4: rows padded to 4 labels per lane on the device
-                 "kla_k33", "kla_recond_k33", "kla_labels_k33", "lin_k33", "quad_weighted_k50", "kla_rand_k50", "kla_k127"]
+                 "kla_k33", "kla_recond_k33", "kla_labels_k33", "lin_k33", "quad_weighted_k50", "kla_rand_k50", "kla_k127",
+                 # more than 128 labels: 8 / 16 labels per lane
+                 "kla_k200", "kla_recond_k200", "quad_weighted_k300", "lin_k511"]
 
 
 def simplex_case(name, dtype):
     K = 5
-    for tag, k in (("k16", 16), ("k3", 3), ("k1", 1), ("k32", 32), ("k12", 12), ("k64", 64), ("k33", 33), ("k50", 50), ("k127", 127)):
+    for tag, k in (("k16", 16), ("k3", 3), ("k1", 1), ("k32", 32), ("k12", 12), ("k64", 64), ("k33", 33), ("k50", 50), ("k127", 127),
+                   ("k200", 200), ("k300", 300), ("k511", 511)):
         if name.endswith("_" + tag) or ("_" + tag + "_") in name:
             K = k
     al = 0.0 if name.startswith("lin") else (1.0 if name.startswith("quad") else 0.05)
