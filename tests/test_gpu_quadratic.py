@@ -66,6 +66,48 @@ def test_stencil_layout_matches_table(gpu_api, monkeypatch, name, dtype):
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("variant", ["plain", "l1_pos", "box", "identity", "chain", "image"])
+def test_stencil_four_vertices_per_thread_matches_table(gpu_api, monkeypatch, variant, dtype):
+    """grids whose strides are multiples of 4 (16^3 here; 100^3, 252^3 ... in practice) run the kernel that takes four
+    consecutive vertices per thread with 16-byte accesses: same bits as the half-edge table"""
+    from cp_pfdr_graph_d1_b200 import synth
+    from cp_pfdr_graph_d1_b200.api import _b
+    monkeypatch.setenv("PFDR_B200_SMALL", "0")
+    if variant == "chain":
+        V = 8192
+        Eu = np.arange(V - 1, dtype=np.int32); Ev = Eu + 1
+    elif variant == "image":
+        nx, ny = 64, 96
+        V = nx * ny
+        v = np.arange(V).reshape(ny, nx)
+        eu = np.stack([v, v], -1); ev = np.stack([v + 1, v + nx], -1)
+        ok = np.zeros(eu.shape, bool); ok[:, :-1, 0] = True; ok[:-1, :, 1] = True
+        Eu, Ev = eu[ok].astype(np.int32), ev[ok].astype(np.int32)
+    else:
+        V, Eu, Ev = synth.grid_graph(16)
+    rng = np.random.default_rng(5)
+    A = None if variant == "identity" else rng.uniform(0.5, 1.5, V).astype(dtype)
+    Y = (np.round(4 * np.arange(V) / V) + rng.normal(0, 0.3, V)).astype(dtype)
+    if A is not None:
+        Y = (A * Y).astype(dtype)
+    La_d1 = rng.uniform(0.1, 0.5, Eu.shape[0]).astype(dtype)
+    kw = dict(N=0, rho=1.5, condMin=1e-3, difRcd=0.0, difTol=1e-6, itMax=150, want_obj=True, want_dif=True)
+    Lt, L = (1, A) if A is not None else (0, None)
+    if variant == "box":
+        call = lambda: _b().PFDR_graph_quadratic_d1_bounds(np.zeros(V, dtype), Y, A, Eu, Ev, La_d1, 0.5, 3.0, Lt, L, **kw)
+    else:
+        l1 = np.full(V, 0.05, dtype) if variant == "l1_pos" else None
+        call = lambda: _b().PFDR_graph_quadratic_d1_l1(np.zeros(V, dtype), Y, A, Eu, Ev, La_d1, l1, int(variant == "l1_pos"), Lt, L, **kw)
+    got = call()
+    assert gpu_api.last_stats()["layout"] == 1
+    monkeypatch.setenv("PFDR_B200_DIA", "0")
+    tab = call()
+    assert gpu_api.last_stats()["layout"] == 0
+    assert got.it == tab.it and np.array_equal(got.X, tab.X) and np.array_equal(got.Obj, tab.Obj)
+    assert np.allclose(got.Dif, tab.Dif, rtol=1e-5 if dtype is np.float32 else 1e-12, atol=0)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
 @pytest.mark.parametrize("kind", ["chain", "image", "image8"])
 @pytest.mark.parametrize("recond", [0.0, 1e-3])
 def test_stencil_layout_chain_and_image(gpu_api, oracle, monkeypatch, kind, dtype, recond):
