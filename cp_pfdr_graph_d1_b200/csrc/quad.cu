@@ -1765,7 +1765,7 @@ struct QuadSolver : SolverBase {
     void run_small()
     {
         cudaStream_t st = ctx().stream;
-        static int attr_dev = -1, cmax = 8;                      // function attributes are per device
+        static thread_local int attr_dev = -1, cmax = 8;                      // function attributes are per device
         int dev = 0;
         PFDR_CUDA(cudaGetDevice(&dev));
         if (attr_dev != dev) {
@@ -1819,7 +1819,7 @@ struct QuadSolver : SolverBase {
         const char *e = getenv("PFDR_B200_PUSH");
         if ((e && e[0] == '0') || q.Obj != nullptr || q.difRcd > (real) 0) return false;
         cudaStream_t st = ctx().stream;
-        static int attr_dev = -1, cmax = 8;                      // function attributes are per device
+        static thread_local int attr_dev = -1, cmax = 8;                      // function attributes are per device
         int dev = 0;
         PFDR_CUDA(cudaGetDevice(&dev));
         if (attr_dev != dev) {

@@ -229,135 +229,6 @@ __global__ void __launch_bounds__(256, MINB) quad_dia_iter_kernel(QP<real> p)
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// Four consecutive vertices per thread (grids whose row / plane strides are multiples of 4, before any reconditioning,
-// one GPU): every plane access of the four is ONE 16-byte (float32) or 2 x 16-byte (float64) access, the +-1 neighbours
-// come out of the vectors already held plus one scalar per side.  Same arithmetic per vertex, in the same order, as the
-// one-vertex kernel above (d1_prox_half) - the instruction stream per vertex, which bounds that kernel at C2's size
-// (issue active 49 %, profiles/r02_notes.md), is about a third.
-// ---------------------------------------------------------------------------------------------
-template <typename real> struct V4 { real v[4]; };
-template <typename real>
-__device__ __forceinline__ V4<real> ld4(const real *q)
-{
-    V4<real> r;
-    if constexpr (sizeof(real) == 4) { const float4 t = *reinterpret_cast<const float4 *>(q); r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w; }
-    else {
-        const double2 a = *reinterpret_cast<const double2 *>(q), b = *reinterpret_cast<const double2 *>(q + 2);
-        r.v[0] = a.x; r.v[1] = a.y; r.v[2] = b.x; r.v[3] = b.y;
-    }
-    return r;
-}
-template <typename real>
-__device__ __forceinline__ void st4(real *q, const V4<real> &r)
-{
-    if constexpr (sizeof(real) == 4) *reinterpret_cast<float4 *>(q) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
-    else {
-        *reinterpret_cast<double2 *>(q) = make_double2(r.v[0], r.v[1]);
-        *reinterpret_cast<double2 *>(q + 2) = make_double2(r.v[2], r.v[3]);
-    }
-}
-
-template <typename real, int ND, int MINB>
-__global__ void __launch_bounds__(256, MINB) quad_dia_iter4_kernel(QP<real> p)
-{
-    typedef DiaHalf<ND> H;
-    typedef V4<real> vec;
-    __shared__ double smem[64];
-    Ctl *ctl = p.ctl;
-    const CtlView cv = load_ctl(ctl);
-    if (cv.hold != 0 || cv.state != ST_RUN) {
-        if (cv.hold == 0 && blockIdx.x == 0 && threadIdx.x == 0) ctl->hold = 1;
-        return;
-    }
-    const int it = cv.it, cur = it & 1;
-    const real *__restrict__ Zin = cur ? p.Z1 : p.Z0;
-    real *__restrict__ Zout = cur ? p.Z0 : p.Z1;
-    const real *__restrict__ Xc = cur ? p.X1 : p.X0;
-    real *__restrict__ Xn = cur ? p.X0 : p.X1;
-    const real *__restrict__ Pc = cur ? p.P1 : p.P0;
-    real *__restrict__ Pn = cur ? p.P0 : p.P1;
-    const real *__restrict__ Tg = p.T;
-    const real *__restrict__ Wrow = p.Wrow;
-    const real rho = p.rho, thc0 = p.thc0;
-    const size_t Vp = (size_t) p.V;
-    const int V = p.V, ngroups = V >> 2;
-    const int off[3] = {p.dia_off[0], p.dia_off[1], p.dia_off[2]};
-    const int stride = (int) (gridDim.x * blockDim.x);
-    double red0 = 0.0, red1 = 0.0;
-    for (int g = (int) (blockIdx.x * blockDim.x + threadIdx.x); g < ngroups; g += stride) {
-        const int v = g << 2;
-        const unsigned m4 = __ldg(reinterpret_cast<const unsigned *>(p.dmask + v));      // the four vertices' edge masks
-        const vec xo = ld4(Xc + v), po = ld4(Pc + v), Tv = ld4(Tg + v);
-        vec zo[2 * ND];                                                                 // own copies, by plane
-#pragma unroll
-        for (int pl = 0; pl < 2 * ND; pl++) zo[pl] = ld4(Zin + (size_t) pl * Vp + v);
-        // the unit offset (off[0] == 1): neighbours v-1 .. v+2 and v+1 .. v+4 = the vectors above shifted by one + one scalar
-        const int vm = max(v - 1, 0), vp4 = min(v + 4, V - 1);
-        const real p_m = Pc[vm], p_p = Pc[vp4], T_m = Tg[vm], T_p = Tg[vp4];
-        const real zt_m = Zin[(size_t) 0 * Vp + vm];              // copy of v-1 on out_0(v-1): twin of in_0(v)
-        const real zt_p = Zin[(size_t) ND * Vp + vp4];            // copy of v+4 on in_0(v+4): twin of out_0(v+3)
-        vec acc; acc.v[0] = acc.v[1] = acc.v[2] = acc.v[3] = 0;
-#pragma unroll
-        for (int h = 0; h < 2 * ND; h++) {
-            const int i = H::idx(h), bit = H::mask_bit(h);
-            vec zt, pn, Tn;
-            if (i == 0) {                                          // offset 1
-                if (H::out(h)) {
-#pragma unroll
-                    for (int k = 0; k < 3; k++) { zt.v[k] = zo[ND].v[k + 1]; pn.v[k] = po.v[k + 1]; Tn.v[k] = Tv.v[k + 1]; }
-                    zt.v[3] = zt_p; pn.v[3] = p_p; Tn.v[3] = T_p;
-                } else {
-#pragma unroll
-                    for (int k = 1; k < 4; k++) { zt.v[k] = zo[0].v[k - 1]; pn.v[k] = po.v[k - 1]; Tn.v[k] = Tv.v[k - 1]; }
-                    zt.v[0] = zt_m; pn.v[0] = p_m; Tn.v[0] = T_m;
-                }
-            } else {                                               // offsets that are multiples of 4: aligned vectors
-                const int n = H::out(h) ? min(v + off[i], V - 4) : max(v - off[i], 0);
-                zt = ld4(Zin + (size_t) H::twin_plane(h) * Vp + n);
-                pn = ld4(Pc + n); Tn = ld4(Tg + n);
-            }
-            const vec wr = ld4(Wrow + (size_t) h * Vp + v);
-            vec zn = zo[H::own_plane(h)];
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                if ((m4 >> (8 * k + bit)) & 1u) {
-                    zn.v[k] = d1_prox_half<real>(rho, xo.v[k], po.v[k], Tv.v[k], zo[H::own_plane(h)].v[k], zt.v[k], pn.v[k], Tn.v[k], thc0);
-                    acc.v[k] = fma_rn(wr.v[k], zn.v[k], acc.v[k]);
-                }
-            }
-            st4(Zout + (size_t) H::own_plane(h) * Vp + v, zn);     // (a copy that does not exist keeps its value: never read)
-        }
-        vec th1, ga, av, yv;
-        if (p.prox_kind == 0 && p.La_l1) th1 = ld4(p.Thl1 + v);
-        if (p.N == 0) { ga = ld4(p.Ga + v); yv = ld4(p.Y + v); if (p.A) av = ld4(p.A + v); }
-        vec xn, fp;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            real x = acc.v[k];
-            if (p.prox_kind == 0) {                                            // ref l1.cpp :500-512
-                if (p.La_l1) {
-                    const real th = th1.v[k];
-                    if (x > th) x -= th;
-                    else if (!p.positivity && x < -th) x += th;
-                    else x = 0;
-                } else if (p.positivity) { if (x < (real) 0) x = 0; }
-            } else {                                                           // ref bounds.cpp :473-490
-                if (p.has_lo && x < p.lo) x = p.lo;
-                else if (p.has_hi && x > p.hi) x = p.hi;
-            }
-            xn.v[k] = x;
-            if (p.N == 0) fp.v[k] = forward_point_of(x, ga.v[k], p.A ? fma_rn(av.v[k], x, -yv.v[k]) : add_rn(x, -yv.v[k]));
-            const real dx = xo.v[k] - x;
-            red0 += (double) (dx * dx); red1 += (double) (x * x);
-        }
-        st4(Xn + v, xn);
-        if (p.N == 0) st4(Pn + v, fp);
-    }
-    double tot[2] = {red0, red1};
-    if (grid_sum<2>(ctl, p.partial, tot, smem) && threadIdx.x == 0) quad_finalize(p, it, tot[0], tot[1]);
-}
-
 }  // namespace
 
 #define PFDR_ND_SWITCH(CALL)                       \
@@ -387,21 +258,6 @@ void quad_dia_launch_iter(const QP<real> &p, int grid)
     constexpr int MINB = sizeof(real) == 4 ? 4 : 3;
     constexpr int G = sizeof(real) == 4 ? 6 : 3;         // half-edges requested at a time (5 loads each)
     const int g = std::min(grid, num_sms() * MINB);      // one wave of resident CTAs
-    // four vertices per thread when every plane access of a group of four is an aligned vector access
-    bool vec4 = !p.slab.on && !p.thc && p.vbeg == 0 && p.vend == p.V && p.V % 4 == 0 && p.V >= 4096 && p.dia_off[0] == 1;
-    for (int i = 1; i < p.dia_nd; i++) vec4 = vec4 && p.dia_off[i] % 4 == 0;
-    for (const void *q : {(const void *) p.Z0, (const void *) p.Z1, (const void *) p.X0, (const void *) p.X1, (const void *) p.P0, (const void *) p.P1,
-                          (const void *) p.T, (const void *) p.Wrow, (const void *) p.Ga, (const void *) p.Y, (const void *) p.A, (const void *) p.Thl1,
-                          (const void *) p.dmask})
-        vec4 = vec4 && ((uintptr_t) q % 16 == 0);
-    if (vec4) {
-        constexpr int MB4 = sizeof(real) == 4 ? 2 : 1;      // float64: 4 x 6 copies in registers need more than 128
-        const int g4 = std::min((int) cdiv((size_t) (p.V / 4), 256), num_sms() * MB4);
-        if (p.dia_nd == 1) PFDR_LAUNCH((quad_dia_iter4_kernel<real, 1, MB4>), g4, 256, 0, p);
-        else if (p.dia_nd == 2) PFDR_LAUNCH((quad_dia_iter4_kernel<real, 2, MB4>), g4, 256, 0, p);
-        else PFDR_LAUNCH((quad_dia_iter4_kernel<real, 3, MB4>), g4, 256, 0, p);
-        return;
-    }
 #define CALL(N_)                                                                                         \
     if (p.slab.on && p.thc) PFDR_LAUNCH((quad_dia_iter_kernel<real, true, N_, G, MINB, true>), g, 256, 0, p);   \
     else if (p.slab.on) PFDR_LAUNCH((quad_dia_iter_kernel<real, false, N_, G, MINB, true>), g, 256, 0, p);    \

@@ -67,9 +67,9 @@ def test_stencil_layout_matches_table(gpu_api, monkeypatch, name, dtype):
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 @pytest.mark.parametrize("variant", ["plain", "l1_pos", "box", "identity", "chain", "image"])
-def test_stencil_four_vertices_per_thread_matches_table(gpu_api, monkeypatch, variant, dtype):
-    """grids whose strides are multiples of 4 (16^3 here; 100^3, 252^3 ... in practice) run the kernel that takes four
-    consecutive vertices per thread with 16-byte accesses: same bits as the half-edge table"""
+def test_stencil_layout_matches_table_larger_grids(gpu_api, monkeypatch, variant, dtype):
+    """16^3 grids, 8192-vertex chains and 64 x 96 images (several trips per persistent warp) with every vertex prox:
+    the stencil kernels give the same bits as the half-edge table"""
     from cp_pfdr_graph_d1_b200 import synth
     from cp_pfdr_graph_d1_b200.api import _b
     monkeypatch.setenv("PFDR_B200_SMALL", "0")
