@@ -103,38 +103,64 @@ def measured_traffic(name):
 
 
 class ClockSampler:
-    """samples nvidia-smi clocks / throttle reasons while the timed region runs"""
+    """samples nvidia-smi clocks / throttle reasons every 50 ms; the summary is over the samples that arrived inside the
+    timed region (mark_start() .. mark_end()).  nvidia-smi needs a few hundred ms to start: start() is called ahead of the
+    warm-up and waits for the first sample, so that even a sub-second timed region is covered."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.rows, self.proc, self.index = [], None, index
+        self.rows, self.proc, self.index, self.t0, self.t1 = [], None, index, None, None
 
-    def __enter__(self):
+    def start(self, wait_s=3.0):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
+            t_end = time.perf_counter() + wait_s
+            while not self.rows and time.perf_counter() < t_end:
+                time.sleep(0.01)
         except OSError:
             self.proc = None
         return self
 
+    def __enter__(self):                      # with-block = the timed region
+        if self.proc is None:
+            self.start()
+        self.mark_start()
+        return self
+
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def mark_start(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def __exit__(self, *a):
+        if self.t1 is None:
+            self.mark_end()
+        self.stop()
+
+    def stop(self):
         if self.proc:
-            time.sleep(0.15)
+            time.sleep(0.12)
             self.proc.terminate()
             self.t.join(timeout=2)
+            self.proc = None
 
     def summary(self):
+        t0, t1 = self.t0 or 0.0, self.t1 or float("inf")
+        inside = [r for t, r in self.rows if t0 <= t <= t1 + 0.06]     # (+ one sampling period: the row reporting the last 50 ms)
+        rows, where = (inside, "timed region") if inside else ([r for t, r in self.rows if t0 - 0.5 <= t <= t1 + 0.5], "within 0.5 s of the timed region")
         sm, mx, reasons = [], 0.0, set()
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[0])); mx = max(mx, float(r[1]))
             except (ValueError, IndexError):
@@ -143,7 +169,7 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": where, "timed_region_s": round(t1 - t0, 4) if self.t1 else None}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -447,14 +473,14 @@ def resident_run(name, dev, stream, steps, warmup, iters=0, clock_index=None):
         solver.reset()
         return solver.run()
 
+    clk = ClockSampler(clock_index).start() if clock_index is not None else None
     for _ in range(warmup):
         step()
     torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     loop_ms = launches = its = 0
-    clk = ClockSampler(clock_index) if clock_index is not None else None
     if clk:
-        clk.__enter__()
+        clk.mark_start()
     with torch.cuda.stream(stream):
         ev0.record(stream)
         for _ in range(steps):
@@ -463,7 +489,8 @@ def resident_run(name, dev, stream, steps, warmup, iters=0, clock_index=None):
         ev1.record(stream)
     torch.cuda.synchronize()
     if clk:
-        clk.__exit__()
+        clk.mark_end()
+        clk.stop()
     ms = ev0.elapsed_time(ev1)
     assert its == iters * steps, (its, iters, steps)
     solver.close()

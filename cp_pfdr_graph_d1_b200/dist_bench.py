@@ -66,6 +66,7 @@ def main(args):
         solver.reset()
         return solver.run()
 
+    clk = B.ClockSampler(local).start() if rank == 0 else None        # nvidia-smi is up and sampling before the timed region
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize()
@@ -113,15 +114,19 @@ def main(args):
 
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     loop_ms = launches = its = 0
-    with B.ClockSampler(local) as clk:
-        ev0.record(stream)
-        for _ in range(args.steps):
-            st = step()
-            loop_ms += st["loop_ms"]; launches += st["launches"]; its += st["iterations"]
-        ev1.record(stream)
-        torch.cuda.synchronize()
-        dist.barrier()
-        torch.cuda.synchronize()
+    if clk:
+        clk.mark_start()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        st = step()
+        loop_ms += st["loop_ms"]; launches += st["launches"]; its += st["iterations"]
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    if clk:
+        clk.mark_end()
+        clk.stop()
+    dist.barrier()
+    torch.cuda.synchronize()
     t = torch.tensor([ev0.elapsed_time(ev1), loop_ms, float(launches)], device="cuda", dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, loop_ms_max = float(t[0]), float(t[1])

@@ -202,6 +202,56 @@ def test_one_shot_entry_points_on_two_gpus(gpu_api, monkeypatch, family):
         assert np.linalg.norm(two.X.astype(np.float64) - one.X) / np.linalg.norm(one.X.astype(np.float64)) < 1e-6
 
 
+@pytest.mark.parametrize("family", ["simplex", "quad"])
+def test_one_shot_entry_points_on_two_gpus_full_semantics(gpu_api, monkeypatch, family):
+    """the same with everything the reference's signature offers: stopping rule, Obj and Dif records, a reconditioning"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from cp_pfdr_graph_d1_b200 import synth
+    b = gpu_api._b()
+    if family == "simplex":
+        w = synth.c4_simplex(64, 16, np.float64)
+        call = lambda: b.PFDR_graph_loss_d1_simplex(w["Q"].copy(), w["Q"], 0.05, w["Eu"], w["Ev"], w["La_d1"], rho=1.5, condMin=1e-2,
+                                                    difRcd=3e-3, difTol=1e-4, itMax=60, want_obj=True, want_dif=True)
+    else:
+        w = synth.c2_denoise(130, np.float64, diag=True)
+        Ys = w["La_l2"] * w["Y"]
+        call = lambda: b.PFDR_graph_quadratic_d1_l1(np.zeros(w["V"]), Ys, w["La_l2"], w["Eu"], w["Ev"], w["La_d1"], np.full(w["V"], 0.05), 1, 1,
+                                                    w["La_l2"], rho=1.5, condMin=1e-3, difRcd=3e-2, difTol=1e-4, itMax=60, N=0,
+                                                    want_obj=True, want_dif=True)
+    one = call()
+    monkeypatch.setenv("PFDR_B200_GPUS", "2")
+    two = call()
+    assert gpu_api.last_stats()["gpus"] == 2
+    assert two.it == one.it and one.it > 5, (two.it, one.it)
+    assert np.linalg.norm(two.X - one.X) / np.linalg.norm(one.X) < 1e-12
+    assert two.Obj.shape == one.Obj.shape and np.allclose(two.Obj, one.Obj, rtol=1e-10)
+    assert np.allclose(two.Dif, one.Dif, rtol=1e-9)
+
+
+def test_one_shot_entry_points_fall_back_to_one_gpu(gpu_api, monkeypatch):
+    """PFDR_B200_GPUS set, but the problem is not one the slab path takes (an irregular graph; a small grid): solved on one
+    GPU, same result as without the variable"""
+    import problems
+    b = gpu_api._b()
+    monkeypatch.setenv("PFDR_B200_GPUS", "2")
+    r = problems.run_quad(b, "rand_big", np.float64)
+    assert gpu_api.last_stats()["gpus"] == 1
+    monkeypatch.delenv("PFDR_B200_GPUS")
+    r1 = problems.run_quad(b, "rand_big", np.float64)
+    assert r.it == r1.it and np.array_equal(r.X, r1.X)
+    V = 1 << 21                                                  # large enough, but the edge list is not vertex-major: table layout
+    rng = np.random.default_rng(0)
+    Eu = np.arange(V - 1, dtype=np.int32); Ev = Eu + 1
+    perm = rng.permutation(V - 1)
+    Y = rng.normal(0, 1, V).astype(np.float32)
+    monkeypatch.setenv("PFDR_B200_GPUS", "2")
+    r = b.PFDR_graph_quadratic_d1_l1(np.zeros(V, np.float32), Y, None, Eu[perm], Ev[perm], np.full(V - 1, 0.3, np.float32), None, 0, 0, None,
+                                     difTol=0.0, itMax=5, N=0)
+    assert gpu_api.last_stats()["gpus"] == 1 and r.it == 5 and np.isfinite(r.X).all()
+
+
 def test_template_symbol_of_the_shim_on_two_gpus(gpu_api, monkeypatch):
     """the drop-in boundary itself: the reference's C++ template instantiation PFDR_graph_loss_d1_simplex<float>
     (mangled symbol of lib/libpfdr_b200_shim.so, what the MEX gateways and CP_*.cpp link against) on two GPUs"""
