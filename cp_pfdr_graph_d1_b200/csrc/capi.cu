@@ -35,6 +35,7 @@ static int guarded(F &&f)
         if (c.device >= 0) PFDR_CUDA(cudaSetDevice(c.device));
         if (!c.user_stream) c.stream = own_stream();
         c.stats = pfdr_b200_stats{};
+        c.stats.gpus = 1;
         c.in_loop = false;
         c.ordered = false;
         const auto t0 = std::chrono::steady_clock::now();

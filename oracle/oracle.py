@@ -139,3 +139,101 @@ def cp_reference():
 def cp_b200(refnorm=False):
     path = CP_B200_REFNORM_SO if refnorm else CP_B200_SO
     return CutPursuit(path) if os.path.exists(path) else None
+
+
+# ---------------------------------------------------------------------------------------------------
+# reduced-problem construction of the cut-pursuit (oracle/cp_reduce_oracle_impl.h)
+# ---------------------------------------------------------------------------------------------------
+def component_lists(Cv, rV):
+    """(Vc, rVc): vertices grouped by component, ascending vertex number inside a component"""
+    Cv = np.asarray(Cv, np.int32)
+    Vc = np.argsort(Cv, kind="stable").astype(np.int32)
+    rVc = np.concatenate([[0], np.cumsum(np.bincount(Cv, minlength=rV))]).astype(np.int32)
+    return Vc, rVc
+
+
+class CpReduceOracle:
+    """ctypes access to oracle_cp_{gradient,reduce,residual,equilibrate}_{f32,f64}"""
+
+    def __init__(self):
+        if not os.path.exists(ORACLE_SO):
+            build(ref=False)
+        self.lib = C.CDLL(ORACLE_SO)
+
+    @staticmethod
+    def _t(dt):
+        return (C.c_float, "f32") if np.dtype(dt) == np.float32 else (C.c_double, "f64")
+
+    @staticmethod
+    def _p(a, t):
+        return None if a is None else np.ascontiguousarray(a).ctypes.data_as(C.POINTER(t)) if a.ndim == 1 else a.ctypes.data_as(C.POINTER(t))
+
+    def gradient(self, V, N, A, YorR, rX, Cv, Vc, rVc):
+        dt = rX.dtype
+        R, suf = self._t(dt)
+        f = getattr(self.lib, f"oracle_cp_gradient_{suf}")
+        f.restype = None
+        out = np.zeros(V, dt)
+        p, I = self._p, C.c_int
+        f.argtypes = [I, I, I] + [C.POINTER(R)] * 3 + [C.POINTER(I)] * 3 + [C.POINTER(R)]
+        f(V, N, int(rX.shape[0]), p(A, R), p(YorR, R), p(rX, R), p(Cv, I), p(Vc, I), p(rVc, I), p(out, R))
+        return out
+
+    def reduce(self, V, N, A, Y, Vc, rVc, preAt):
+        dt = Y.dtype
+        R, suf = self._t(dt)
+        rV = int(rVc.shape[0]) - 1
+        f = getattr(self.lib, f"oracle_cp_reduce_{suf}")
+        f.restype = None
+        rA = np.zeros((N, rV), dt, order="F") if N > 0 else None
+        rAA = (np.zeros(rV, dt) if N == 0 else np.zeros((rV, rV), dt, order="F")) if (preAt or N <= 0) else None
+        rY = np.zeros(rV, dt) if (preAt or N <= 0) else None
+        p, I = self._p, C.c_int
+        f.argtypes = [I, I, I, C.POINTER(R), C.POINTER(R), C.POINTER(I), C.POINTER(I), I] + [C.POINTER(R)] * 3
+        f(V, N, rV, p(A, R), p(Y, R), p(Vc, I), p(rVc, I), int(preAt), p(rA, R), p(rAA, R), p(rY, R))
+        return rA, rAA, rY
+
+    def residual(self, rA, rX, Y):
+        dt = Y.dtype
+        R, suf = self._t(dt)
+        f = getattr(self.lib, f"oracle_cp_residual_{suf}")
+        f.restype = None
+        N, rV = rA.shape
+        out = np.zeros(N, dt)
+        p = self._p
+        f.argtypes = [C.c_int, C.c_int] + [C.POINTER(R)] * 4
+        f(N, rV, p(rA, R), p(rX, R), p(Y, R), p(out, R))
+        return out
+
+    def equilibrate(self, N, M, preAt):
+        dt = M.dtype
+        R, suf = self._t(dt)
+        rV = M.shape[1]
+        f = getattr(self.lib, f"oracle_cp_equilibrate_{suf}")
+        f.restype = None
+        S, d = np.zeros_like(M, order="F"), np.zeros(rV, dt)
+        p = self._p
+        f.argtypes = [C.c_int, C.c_int, C.c_int] + [C.POINTER(R)] * 3
+        f(N, rV, int(preAt), p(M, R), p(S, R), p(d, R))
+        return S, d
+
+
+def reduced_graph(Cv, rV, Eu, Ev, La_d1, La_l1, eps):
+    """reduced connectivity of src/CP_PFDR_graph_quadratic_d1_l1.cpp:603-661 as far as the minimiser of the reduced problem
+    depends on it: one edge per pair of neighbouring components carrying the sum of the weights between them, a self-loop
+    of weight eps on isolated components, per-component sums of the l1 weights.  (Edge order and self-loops on cut edges
+    inside one component - which the reference also emits - only change the preconditioner, not the minimiser.)"""
+    cu, cv = Cv[Eu].astype(np.int64), Cv[Ev].astype(np.int64)
+    keep = (cu != cv) & (La_d1 != 0)
+    lo, hi = np.minimum(cu, cv)[keep], np.maximum(cu, cv)[keep]
+    key, inv = np.unique(lo * rV + hi, return_inverse=True)
+    w = np.bincount(inv, weights=La_d1[keep].astype(np.float64), minlength=key.shape[0])
+    rEu, rEv = (key // rV).astype(np.int32), (key % rV).astype(np.int32)
+    touched = np.zeros(rV, bool)
+    touched[rEu] = True
+    touched[rEv] = True
+    iso = np.nonzero(~touched)[0].astype(np.int32)
+    rEu, rEv = np.concatenate([rEu, iso]), np.concatenate([rEv, iso])
+    w = np.concatenate([w, np.full(iso.shape[0], eps)]).astype(La_d1.dtype)
+    rl1 = None if La_l1 is None else np.bincount(Cv, weights=La_l1.astype(np.float64), minlength=rV).astype(La_l1.dtype)
+    return rEu, rEv, w, rl1

@@ -10,6 +10,7 @@
 #define REAL_HUGE HUGE_VALF
 #define FN(name) name##_f32
 #include "pfdr_oracle_impl.h"
+#include "cp_reduce_oracle_impl.h"
 #undef REAL
 #undef REAL_EPS
 #undef REAL_HUGE
@@ -20,3 +21,4 @@
 #define REAL_HUGE HUGE_VAL
 #define FN(name) name##_f64
 #include "pfdr_oracle_impl.h"
+#include "cp_reduce_oracle_impl.h"

@@ -179,3 +179,105 @@ def test_gpu_schedule_model(oracle, dtype, variant):
                                1.5, 1e-3, 1e-5, 150)
     assert abs(it - r.it) <= (0 if dtype is np.float64 else 2)
     assert rel(x, r.X) < (1e-4 if dtype is np.float32 else 1e-11)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the reduced-problem construction has no entry point in the reference (inline blocks of the cut-pursuit).
+# Pin: the reference's own cut-pursuit, stopped after ONE outer iteration, returns the components Cv and the reduced
+# values rX = argmin of the reduced problem; the restated blocks (oracle/cp_reduce_oracle_impl.h) must rebuild a reduced
+# problem with the same minimiser from the same Cv.
+# ---------------------------------------------------------------------------------------------------------------------
+def _cp_chain(reference_cp, mode, preAt_wanted=None):
+    from oracle import oracle as O
+    from cp_pfdr_graph_d1_b200 import synth
+    dt = np.float64
+    if mode == "diag":
+        w = synth.c2_denoise(9, dt, diag=True)
+        V, N, A, Y = w["V"], 0, w["La_l2"], (w["La_l2"] * w["Y"]).astype(dt)
+        Eu, Ev, La_d1, La_l1, pos = w["Eu"], w["Ev"], w["La_d1"], None, 0
+    else:
+        w = synth.eeg_like(2, 24, dt)
+        V, Eu, Ev, La_d1, La_l1, pos = w["V"], w["Eu"], w["Ev"], w["La_d1"], w["La_l1"], 1
+        if mode == "direct":
+            N, A, Y = w["N"], w["A"], w["Y"]
+        else:
+            N, A, Y = -V, np.asfortranarray(w["A"].T @ w["A"]), w["A"].T @ w["Y"]
+    kw = dict(CP_difTol=0.0, CP_itMax=1, rho=1.5, condMin=1e-3, difRcd=0.0, difTol=1e-10, itMax=200000)
+    if mode == "ata":
+        # the l1 cut-pursuit of the reference cannot run with N < 0 (src/CP_PFDR_graph_quadratic_d1_l1.cpp:81 derives a thread
+        # count from N and hands libgomp a negative one); its bounds twin (same blocks, src/CP_PFDR_graph_quadratic_d1_bounds.cpp:
+        # 640-750) can: x >= 0 as the box [0, inf), no l1 term
+        La_l1 = None
+        r = reference_cp.quadratic_d1_bounds(Y, A, Eu, Ev, La_d1, 0.0, np.inf, N, **kw)
+    else:
+        r = reference_cp.quadratic_d1_l1(Y, A, Eu, Ev, La_d1, La_l1, pos, N, **kw)
+    rV, Cv = r["rV"], r["Cv"]
+    assert 1 < rV < V
+    red = O.CpReduceOracle()
+    Vc, rVc = O.component_lists(Cv, rV)
+    # the rule of :671 with PFDR_it = PFDR_itMax on the first outer iteration
+    preAt = (N <= 0) or (rV < (2 * N * kw["itMax"]) // (N + kw["itMax"]))
+    if preAt_wanted is not None:
+        preAt = preAt_wanted                     # either form of the reduced problem has the same minimiser
+    rA, rAA, rY = red.reduce(V, N, A, Y, Vc, rVc, preAt)
+    rEu, rEv, rLa, rl1 = O.reduced_graph(Cv, rV, Eu, Ev, La_d1, La_l1, np.finfo(dt).eps)
+    orc = O.oracle()
+    X = np.zeros(rV, dt)
+    common = dict(rho=1.5, condMin=1e-3, difRcd=0.0, difTol=1e-10, itMax=200000)
+    if N == 0:
+        out = orc.PFDR_graph_quadratic_d1_l1(X, rY, rAA, rEu, rEv, rLa, rl1, pos, 1, rAA, N=0, **common)
+    elif preAt:
+        S, d = red.equilibrate(N, rAA, True)
+        c = np.linalg.eigvalsh(S).max()
+        if mode == "ata":
+            out = orc.PFDR_graph_quadratic_d1_bounds(X, rY, rAA, rEu, rEv, rLa, 0.0, np.inf, 1, (d * d * c).astype(dt), N=-rV, **common)
+        else:
+            out = orc.PFDR_graph_quadratic_d1_l1(X, rY, rAA, rEu, rEv, rLa, rl1, pos, 1, (d * d * c).astype(dt), N=-rV, **common)
+    else:
+        S, d = red.equilibrate(N, rA, False)
+        c = np.linalg.norm(S, 2) ** 2
+        out = orc.PFDR_graph_quadratic_d1_l1(X, Y, rA, rEu, rEv, rLa, rl1, pos, 1, (d * d * c).astype(dt), N=N, **common)
+    return r, out, (rA, rAA, rY, Vc, rVc, A, Y, N, V)
+
+
+@pytest.mark.parametrize("mode,preAt", [("direct", True), ("direct", False), ("ata", None), ("diag", None)])
+def test_cp_reduce_chain(reference, mode, preAt):
+    from oracle import oracle as O
+    cp = O.cp_reference()
+    if cp is None:
+        pytest.skip("oracle/_ref/libref.so not built")
+    r, out, _ = _cp_chain(cp, mode, preAt)
+    assert rel(out.X, r["rX"]) < 1e-6, (mode, rel(out.X, r["rX"]))
+
+
+def test_cp_reduce_identities():
+    """algebra the blocks must satisfy whatever the reference does: with S the V x rV indicator matrix of the components,
+    rA = A S, rAA = S^t (A^t A) S, rY = S^t A^t Y; the gradient blocks agree with a dense evaluation; R = Y - A x"""
+    from oracle import oracle as O
+    red = O.CpReduceOracle()
+    rng = np.random.default_rng(3)
+    V, N, rV = 57, 13, 7
+    Cv = rng.integers(0, rV, V).astype(np.int32)
+    Cv[:rV] = np.arange(rV)
+    Vc, rVc = O.component_lists(Cv, rV)
+    S = np.zeros((V, rV)); S[np.arange(V), Cv] = 1
+    A = np.asfortranarray(rng.normal(0, 1, (N, V))); Y = rng.normal(0, 1, N)
+    rA, rAA, rY = red.reduce(V, N, A, Y, Vc, rVc, True)
+    assert np.allclose(rA, A @ S, rtol=1e-12) and np.allclose(rAA, S.T @ A.T @ A @ S, rtol=1e-11) and np.allclose(rY, S.T @ A.T @ Y, rtol=1e-11)
+    assert np.array_equal(rAA, rAA.T)
+    M = np.asfortranarray(A.T @ A); AtY = A.T @ Y
+    _, rAA2, rY2 = red.reduce(V, -V, M, AtY, Vc, rVc, True)
+    assert np.allclose(rAA2, S.T @ M @ S, rtol=1e-11) and np.allclose(rY2, S.T @ AtY, rtol=1e-11) and np.array_equal(rAA2, rAA2.T)
+    a = rng.uniform(0.5, 2, V)
+    _, rAA3, rY3 = red.reduce(V, 0, a, AtY, Vc, rVc, True)
+    assert np.allclose(rAA3, S.T @ a) and np.allclose(rY3, S.T @ AtY)
+    _, rAA4, _ = red.reduce(V, 0, None, AtY, Vc, rVc, True)
+    assert np.array_equal(rAA4, np.bincount(Cv, minlength=rV).astype(float))
+    rX = rng.normal(0, 1, rV); rX[2] = 0.0
+    x = rX[Cv]
+    R = red.residual(rA, rX, Y)
+    assert np.allclose(R, Y - A @ x, rtol=1e-11, atol=1e-12)
+    assert np.allclose(red.gradient(V, N, A, R, rX, Cv, Vc, rVc), -A.T @ R, rtol=1e-11, atol=1e-12)
+    assert np.allclose(red.gradient(V, -V, M, AtY, rX, Cv, Vc, rVc), M @ x - AtY, rtol=1e-10, atol=1e-11)
+    assert np.allclose(red.gradient(V, 0, a, AtY, rX, Cv, Vc, rVc), a * x - AtY, rtol=1e-12)
+    assert np.allclose(red.gradient(V, 0, None, AtY, rX, Cv, Vc, rVc), x - AtY, rtol=1e-12)
