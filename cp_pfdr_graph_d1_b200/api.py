@@ -179,3 +179,138 @@ class SimplexSolver(_Solver):
                     _ptr(Eu, _C.c_int), _ptr(Ev, _C.c_int), _ptr(La_d1, R), rho, condMin, difRcd, difTol, itMax,
                     int(want_obj), int(want_dif)))
         self.setup_stats = last_stats()
+
+
+class CpOperator:
+    """The dense passes of the cut-pursuit's outer iteration with the operator resident in HBM (include/pfdr_b200.h,
+    reference src/CP_PFDR_graph_quadratic_d1_l1.cpp:340-374 gradient, :664-772 reduced operator, :889-903 residual).
+    A: (N, V) Fortran-ordered with N > 0; (V, V) A^tA with N = -V; 1-D diagonal of A^tA or None (identity) with N = 0.
+    A torch CUDA tensor is used in place (and must outlive the handle).  dtype: only read when A is None."""
+
+    def __init__(self, A, V, N, dtype=np.float64):
+        self._lib = _lib.load()
+        self._h = _C.c_void_p()
+        self.V, self.N = int(V), int(N)
+        if A is None:                                   # identity: `dtype` says which arithmetic the calls use
+            if N != 0:
+                raise PfdrError("A is required unless N == 0")
+            dt = np.dtype(dtype)
+        else:
+            dt = _real_dtype(A)
+            A = _as_real(A, dt)
+        self._dt, self._keep, self.rV = dt, A, 0
+        R, suf = _CT[dt]
+        f = getattr(self._lib, f"pfdr_b200_cp_operator_create_{suf}")
+        f.argtypes = [_C.POINTER(_C.c_void_p), _C.c_int, _C.c_int, _C.POINTER(R)]
+        self._chk(f(_C.byref(self._h), self.V, self.N, _ptr(A, R)))
+        for name, n in (("set_components", 3), ("reduce", 6), ("gradient", 4), ("residual", 4)):
+            getattr(self._lib, f"pfdr_b200_cp_{name}").argtypes = [_C.c_void_p] * n
+        self._lib.pfdr_b200_cp_set_components.argtypes = [_C.c_void_p, _C.c_int, _C.POINTER(_C.c_int)]
+        self._lib.pfdr_b200_cp_reduce.argtypes = [_C.c_void_p, _C.c_void_p, _C.c_int, _C.c_void_p, _C.c_void_p, _C.c_void_p]
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise PfdrError(f"libpfdr_b200 status {rc}: {self._lib.pfdr_b200_last_error().decode()}")
+
+    def _vp(self, a):
+        return None if a is None else _C.cast(_ptr(_as_real(a, self._dt), _CT[self._dt][0]), _C.c_void_p)
+
+    def set_components(self, Cv, rV):
+        Cv = _as_int(Cv)
+        self._chk(self._lib.pfdr_b200_cp_set_components(self._h, int(rV), _ptr(Cv, _C.c_int)))
+        self.rV = int(rV)
+
+    def reduce(self, Y, preAt=True, want_rA=True):
+        """-> (rA or None, rAA or None, rY or None) as numpy arrays (rA, rAA Fortran-ordered)"""
+        N, rV, dt = self.N, self.rV, self._dt
+        pre = bool(preAt) or N <= 0
+        rA = np.zeros((N, rV), dt, order="F") if (N > 0 and want_rA) else None
+        rAA = (np.zeros(rV, dt) if N == 0 else np.zeros((rV, rV), dt, order="F")) if pre else None
+        rY = np.zeros(rV, dt) if pre else None
+        Y = None if Y is None else _as_real(Y, dt)
+        self._chk(self._lib.pfdr_b200_cp_reduce(self._h, self._vp(Y), int(pre), self._vp(rA), self._vp(rAA), self._vp(rY)))
+        return rA, rAA, rY
+
+    def gradient(self, rX, YorR=None):
+        out = np.zeros(self.V, self._dt)
+        self._chk(self._lib.pfdr_b200_cp_gradient(self._h, self._vp(np.ascontiguousarray(rX, self._dt)),
+                                                  self._vp(YorR), self._vp(out)))
+        return out
+
+    def residual(self, rX, Y):
+        out = np.zeros(self.N, self._dt)
+        self._chk(self._lib.pfdr_b200_cp_residual(self._h, self._vp(np.ascontiguousarray(rX, self._dt)), self._vp(Y), self._vp(out)))
+        return out
+
+    def close(self):
+        if self._h:
+            self._lib.pfdr_b200_cp_operator_destroy.argtypes = [_C.c_void_p]
+            self._lib.pfdr_b200_cp_operator_destroy(self._h)
+            self._h = _C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ---- graph passes of the cut-pursuit's outer iteration (csrc/cpgraph.cu; reference src/CP_PFDR_graph_quadratic_d1_l1.cpp) ----
+def _u8(a):
+    return np.ascontiguousarray(a, dtype=np.uint8)
+
+
+def cp_components(V, Eu, Ev, active):
+    """connected components of the non-active edges, numbered by smallest vertex (:570-600) -> (Cv, rV)"""
+    lib = _lib.load()
+    Eu, Ev, active = _as_int(Eu), _as_int(Ev), _u8(active)
+    Cv, rV = np.zeros(V, np.int32), _C.c_int(0)
+    PI, PB = _C.POINTER(_C.c_int), _C.POINTER(_C.c_ubyte)
+    f = lib.pfdr_b200_cp_components
+    f.argtypes = [_C.c_int, _C.c_int, PI, PI, PB, PI, PI]
+    rc = f(int(V), int(Eu.shape[0]), _ptr(Eu, _C.c_int), _ptr(Ev, _C.c_int), active.ctypes.data_as(PB), _ptr(Cv, _C.c_int), _C.byref(rV))
+    if rc != 0:
+        raise PfdrError(f"libpfdr_b200 status {rc}: {lib.pfdr_b200_last_error().decode()}")
+    return Cv, rV.value
+
+
+def cp_reduced_edges(V, Eu, Ev, active, La_d1, Cv, rV, eps=None, capacity=None):
+    """reduced connectivity (:603-661) -> (rEu, rEv, rLa_d1), sorted by (rEu, rEv)"""
+    lib = _lib.load()
+    dt = _real_dtype(La_d1)
+    R, suf = _CT[dt]
+    Eu, Ev, active, Cv, La_d1 = _as_int(Eu), _as_int(Ev), _u8(active), _as_int(Cv), _as_real(La_d1, dt)
+    E = int(Eu.shape[0])
+    cap = int(capacity) if capacity is not None else E + int(rV)
+    eps = float(np.finfo(dt).eps) if eps is None else float(eps)
+    rEu, rEv, rLa, rE = np.zeros(cap, np.int32), np.zeros(cap, np.int32), np.zeros(cap, dt), _C.c_int(0)
+    PI, PB, PR = _C.POINTER(_C.c_int), _C.POINTER(_C.c_ubyte), _C.POINTER(R)
+    f = getattr(lib, f"pfdr_b200_cp_reduced_edges_{suf}")
+    f.argtypes = [_C.c_int, _C.c_int, PI, PI, PB, PR, PI, _C.c_int, R, _C.c_int, PI, PI, PI, PR]
+    rc = f(int(V), E, _ptr(Eu, _C.c_int), _ptr(Ev, _C.c_int), active.ctypes.data_as(PB), _ptr(La_d1, R), _ptr(Cv, _C.c_int), int(rV), eps,
+           cap, _C.byref(rE), _ptr(rEu, _C.c_int), _ptr(rEv, _C.c_int), _ptr(rLa, R))
+    if rc != 0:
+        raise PfdrError(f"libpfdr_b200 status {rc}: {lib.pfdr_b200_last_error().decode()}")
+    n = rE.value
+    return rEu[:n].copy(), rEv[:n].copy(), rLa[:n].copy()
+
+
+def cp_merge(Eu, Ev, Cv, rX, CP_difTol, active, eps=None):
+    """merge step (:863-886): clears `active` (uint8 array, in place) between components of relatively equal value;
+    returns the number of edges deactivated"""
+    lib = _lib.load()
+    dt = _real_dtype(rX)
+    R, suf = _CT[dt]
+    if not (isinstance(active, np.ndarray) and active.dtype == np.uint8 and active.flags.c_contiguous):
+        raise TypeError("active is updated in place: it must be a contiguous uint8 array")
+    Eu, Ev, Cv, rX = _as_int(Eu), _as_int(Ev), _as_int(Cv), _as_real(rX, dt)
+    eps = float(np.finfo(dt).eps) if eps is None else float(eps)
+    n = _C.c_int(0)
+    PI, PB, PR = _C.POINTER(_C.c_int), _C.POINTER(_C.c_ubyte), _C.POINTER(R)
+    f = getattr(lib, f"pfdr_b200_cp_merge_{suf}")
+    f.argtypes = [_C.c_int, _C.c_int, PI, PI, PI, _C.c_int, PR, R, R, PB, PI]
+    rc = f(int(Cv.shape[0]), int(Eu.shape[0]), _ptr(Eu, _C.c_int), _ptr(Ev, _C.c_int), _ptr(Cv, _C.c_int), int(rX.shape[0]), _ptr(rX, R),
+           float(CP_difTol), eps, active.ctypes.data_as(PB), _C.byref(n))
+    if rc != 0:
+        raise PfdrError(f"libpfdr_b200 status {rc}: {lib.pfdr_b200_last_error().decode()}")
+    return n.value

@@ -238,6 +238,57 @@ int pfdr_b200_slab_connect(pfdr_b200_solver *s, const void *blobs, int same_proc
     return guarded([&] { PFDR_REQUIRE(s && blobs, "NULL argument"); reinterpret_cast<SolverBase *>(s)->slab_connect(blobs, same_process != 0); });
 }
 
+/* ---- cut-pursuit outer iteration: resident operator, reduced-problem construction ---- */
+int pfdr_b200_cp_operator_create_f32(pfdr_b200_cp_operator **out, int V, int N, const float *A)
+{
+    return guarded([&] { PFDR_REQUIRE(out != nullptr, "cp_operator_create: out must not be NULL");
+                         *out = reinterpret_cast<pfdr_b200_cp_operator *>(make_cp_operator<float>(V, N, A)); });
+}
+int pfdr_b200_cp_operator_create_f64(pfdr_b200_cp_operator **out, int V, int N, const double *A)
+{
+    return guarded([&] { PFDR_REQUIRE(out != nullptr, "cp_operator_create: out must not be NULL");
+                         *out = reinterpret_cast<pfdr_b200_cp_operator *>(make_cp_operator<double>(V, N, A)); });
+}
+int pfdr_b200_cp_set_components(pfdr_b200_cp_operator *op, int rV, const int *Cv)
+{
+    return guarded([&] { PFDR_REQUIRE(op, "NULL operator"); reinterpret_cast<CpOperatorBase *>(op)->set_components(rV, Cv); });
+}
+int pfdr_b200_cp_reduce(pfdr_b200_cp_operator *op, const void *Y, int preAt, void *rA, void *rAA, void *rY)
+{
+    return guarded([&] { PFDR_REQUIRE(op, "NULL operator"); reinterpret_cast<CpOperatorBase *>(op)->reduce(Y, preAt, rA, rAA, rY); });
+}
+int pfdr_b200_cp_gradient(pfdr_b200_cp_operator *op, const void *rX, const void *YorR, void *DfS)
+{
+    return guarded([&] { PFDR_REQUIRE(op, "NULL operator"); reinterpret_cast<CpOperatorBase *>(op)->gradient(rX, YorR, DfS); });
+}
+int pfdr_b200_cp_residual(pfdr_b200_cp_operator *op, const void *rX, const void *Y, void *R)
+{
+    return guarded([&] { PFDR_REQUIRE(op, "NULL operator"); reinterpret_cast<CpOperatorBase *>(op)->residual(rX, Y, R); });
+}
+int pfdr_b200_cp_operator_destroy(pfdr_b200_cp_operator *op)
+{
+    return guarded([&] { delete reinterpret_cast<CpOperatorBase *>(op); });
+}
+
+int pfdr_b200_cp_components(int V, int E, const int *Eu, const int *Ev, const unsigned char *active, int *Cv, int *rV)
+{
+    return guarded([&] { cp_components(V, E, Eu, Ev, active, Cv, rV); });
+}
+#define CP_GRAPH(SUF, real)                                                                                       \
+int pfdr_b200_cp_reduced_edges_##SUF(int V, int E, const int *Eu, const int *Ev, const unsigned char *active,     \
+    const real *La_d1, const int *Cv, int rV, real eps, int capacity, int *rE, int *rEu, int *rEv, real *rLa_d1)  \
+{                                                                                                                 \
+    return guarded([&] { cp_reduced_edges<real>(V, E, Eu, Ev, active, La_d1, Cv, rV, eps, capacity, rE, rEu, rEv, \
+                                                rLa_d1); });                                                      \
+}                                                                                                                 \
+int pfdr_b200_cp_merge_##SUF(int V, int E, const int *Eu, const int *Ev, const int *Cv, int rV, const real *rX,   \
+    real CP_difTol, real eps, unsigned char *active, int *deactivated)                                            \
+{                                                                                                                 \
+    return guarded([&] { cp_merge<real>(V, E, Eu, Ev, Cv, rV, rX, CP_difTol, eps, active, deactivated); });       \
+}
+CP_GRAPH(f32, float)
+CP_GRAPH(f64, double)
+
 int pfdr_b200_comm_unique_id(void *out128)
 {
     return guarded([&] { PFDR_REQUIRE(out128, "NULL id buffer"); comm_unique_id(out128); });

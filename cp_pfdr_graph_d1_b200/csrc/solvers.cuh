@@ -47,6 +47,25 @@ template <typename real> void solve_simplex(const SimplexProblem<real> &q);
 template <typename real> bool solve_simplex_multi(const SimplexProblem<real> &q);
 template <typename real> bool solve_quadratic_multi(const QuadProblem<real> &q);
 
+// dense passes of the cut-pursuit's outer iteration with the operator resident on the device (cpreduce.cu)
+struct CpOperatorBase {
+    virtual ~CpOperatorBase() {}
+    virtual void set_components(int rV, const int *Cv) = 0;
+    virtual void reduce(const void *Y, int preAt, void *rA, void *rAA, void *rY) = 0;
+    virtual void gradient(const void *rX, const void *YorR, void *DfS) = 0;
+    virtual void residual(const void *rX, const void *Y, void *R) = 0;
+};
+template <typename real> CpOperatorBase *make_cp_operator(int V, int N, const real *A);
+
+// graph passes of the cut-pursuit's outer iteration (cpgraph.cu)
+void cp_components(int V, int E, const int *Eu, const int *Ev, const unsigned char *active, int *Cv, int *rV);
+template <typename real>
+void cp_reduced_edges(int V, int E, const int *Eu, const int *Ev, const unsigned char *active, const real *La_d1, const int *Cv, int rV,
+                      real eps, int cap, int *rE, int *rEu, int *rEv, real *rLa_d1);
+template <typename real>
+void cp_merge(int V, int E, const int *Eu, const int *Ev, const int *Cv, int rV, const real *rX, real CP_difTol, real eps,
+              unsigned char *active, int *count);
+
 template <typename real> void proj_simplex_metric(real *X, const real *M, int D, int N, int nm, const real *A, int na);
 template <typename real> real operator_norm_matrix(int M, int N, const real *A, real nTol, int itMax, int nbInit, int verbose);
 

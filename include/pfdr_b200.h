@@ -113,6 +113,53 @@ int pfdr_b200_solver_run(pfdr_b200_solver *s);     /* iterate until the stopping
 int pfdr_b200_solver_fetch(pfdr_b200_solver *s, void *X, int *it, void *Obj, void *Dif);
 int pfdr_b200_solver_destroy(pfdr_b200_solver *s);
 
+/* ---- cut-pursuit outer iteration: the dense passes around the PFDR call --------
+ * The reference's cut-pursuit (src/CP_PFDR_graph_quadratic_d1_l1.cpp, ..._bounds.cpp) runs, once per outer
+ * iteration and on the host, three passes over the full operator: the gradient of the quadratic term that feeds
+ * the steepest cut (:340-374), the reduced operator of the new components (:664-772) and, for N > 0, the residual
+ * of the reduced solution (:889-903).  A pfdr_b200_cp_operator keeps A (N > 0: N x V column major; N = -V: the
+ * V x V matrix A^tA; N = 0: the diagonal of A^tA, NULL = identity) in HBM across outer iterations; the calls below
+ * replace those blocks one for one.  `real` is the type of the create call; host or device pointers.
+ *   set_components  rV, Cv[V] as the reference holds them after its connected-components pass (:574-600)
+ *   reduce          N > 0: rA (N x rV), and when preAt: rAA = rA^t rA (rV x rV, exactly symmetric), rY = rA^t Y (Y: N values)
+ *                   N < 0: rAA (rV x rV), rY (Y: the V values of A^tY);  N = 0: rAA (rV: summed diagonal or component
+ *                   sizes), rY.   rA may be NULL (kept on the device for residual()); rAA / rY may be NULL when N > 0 && !preAt
+ *   gradient        DfS[V] before the d1 contribution; YorR: N > 0: the residual R (NULL = the one kept by the last
+ *                   residual()), else the observation A^tY (V values)
+ *   residual        N > 0 only: R = Y - rA rX for the components and rA of the last reduce()
+ * Component sums are taken in ascending vertex order, in double: results agree with the reference's to rounding
+ * (tests: 1e-10 relative in float64, 1e-3 in float32). */
+typedef struct pfdr_b200_cp_operator pfdr_b200_cp_operator;
+int pfdr_b200_cp_operator_create_f32(pfdr_b200_cp_operator **out, int V, int N, const float *A);
+int pfdr_b200_cp_operator_create_f64(pfdr_b200_cp_operator **out, int V, int N, const double *A);
+int pfdr_b200_cp_set_components(pfdr_b200_cp_operator *op, int rV, const int *Cv);
+int pfdr_b200_cp_reduce(pfdr_b200_cp_operator *op, const void *Y, int preAt, void *rA, void *rAA, void *rY);
+int pfdr_b200_cp_gradient(pfdr_b200_cp_operator *op, const void *rX, const void *YorR, void *DfS);
+int pfdr_b200_cp_residual(pfdr_b200_cp_operator *op, const void *rX, const void *Y, void *R);
+int pfdr_b200_cp_operator_destroy(pfdr_b200_cp_operator *op);
+
+/* ---- cut-pursuit outer iteration: the graph passes ---------------------------------
+ * `active[e]` = 1 when edge e is cut (the reference keeps the flag in its graph structure, arcs[2e].is_active).
+ *   components     Cv[V], *rV: connected components of the NON-active edges, numbered by smallest vertex - the numbering
+ *                  of the reference's sweep (src/CP_PFDR_graph_quadratic_d1_l1.cpp:570-600), bit-identical
+ *   reduced_edges  reduced connectivity of :603-661: one edge (rEu <= rEv) per pair of components joined by active edges
+ *                  of nonzero weight, weights added (an active edge inside one component gives the loop (c, c) and counts
+ *                  twice, as in the reference), the loop (c, c) of weight eps on components no such edge touches.  Sorted by
+ *                  (rEu, rEv) - the reference emits first-encounter order.  `capacity` = room in the three output arrays
+ *                  (E + rV always suffices); *rE is set even when the call fails for lack of room
+ *   merge          :863-886: clears active[e] where |a - b| / max(|a|, |b|, eps) <= CP_difTol, a, b the values rX of the two
+ *                  components; *deactivated (may be NULL) = how many
+ * Host or device pointers. */
+int pfdr_b200_cp_components(int V, int E, const int *Eu, const int *Ev, const unsigned char *active, int *Cv, int *rV);
+int pfdr_b200_cp_reduced_edges_f32(int V, int E, const int *Eu, const int *Ev, const unsigned char *active,
+    const float *La_d1, const int *Cv, int rV, float eps, int capacity, int *rE, int *rEu, int *rEv, float *rLa_d1);
+int pfdr_b200_cp_reduced_edges_f64(int V, int E, const int *Eu, const int *Ev, const unsigned char *active,
+    const double *La_d1, const int *Cv, int rV, double eps, int capacity, int *rE, int *rEu, int *rEv, double *rLa_d1);
+int pfdr_b200_cp_merge_f32(int V, int E, const int *Eu, const int *Ev, const int *Cv, int rV, const float *rX,
+    float CP_difTol, float eps, unsigned char *active, int *deactivated);
+int pfdr_b200_cp_merge_f64(int V, int E, const int *Eu, const int *Ev, const int *Cv, int rV, const double *rX,
+    double CP_difTol, double eps, unsigned char *active, int *deactivated);
+
 /* ---- vertex-sharded solves over NCCL (no counterpart in the reference) ---------------------
  * One process per GPU.  Rank r owns a contiguous vertex range plus every edge touching it; vertices at the
  * far end of a cut edge are ghosts numbered after the owned ones (cp_pfdr_graph_d1_b200/shard.py builds the

@@ -44,6 +44,9 @@ if [ -f "$SHIMDIR/libpfdr_b200_shim.so" ]; then
              CP_PFDR_graph_loss_d1_simplex graph maxflow ref_wrap_l1 ref_wrap_bounds ref_wrap_misc; do
         cp_objs+=("$OUT/obj/$f.o")
     done
+    # the product's own gateway for the Python module (cp_pfdr_graph_d1_b200/libCP.py) rides in the same library
+    g++ $CXXFLAGS -I"$REF/include" -c "$HERE/../cp_pfdr_graph_d1_b200/csrc/cp_gateway.cpp" -o "$OUT/obj/cp_gateway.o"
+    cp_objs+=("$OUT/obj/cp_gateway.o")
     LINK=(-shared -fopenmp -Wl,-Bsymbolic-functions -L"$SHIMDIR" -lpfdr_b200_shim -lpfdr_b200
           -Wl,-rpath,'$ORIGIN/../../cp_pfdr_graph_d1_b200/lib')
     g++ -o "$OUT/libcp_b200.so" "${cp_objs[@]}" "${LINK[@]}"

@@ -140,3 +140,99 @@ void FN(oracle_cp_equilibrate)(int N, int rV, int preAt, const REAL *M, REAL *S,
         }
     }
 }
+
+#ifndef ORACLE_CP_GRAPH_ONCE
+#define ORACLE_CP_GRAPH_ONCE
+/* connected components of the graph restricted to its NON-active edges (reference :570-600): vertices are visited in
+ * ascending order, an unassigned vertex opens component number rV and a breadth-first sweep over non-active edges assigns
+ * everything reachable - so components are numbered by their smallest vertex.  Vc / rVc receive the visiting order.
+ * The reference walks its own adjacency lists (src/graph.cpp); the sweep below walks a CSR built from the edge list, which
+ * changes the order inside Vc but neither Cv nor rVc.  Returns rV. */
+int oracle_cp_components(int V, int E, const int *Eu, const int *Ev, const unsigned char *active, int *Cv, int *Vc, int *rVc)
+{
+    int *deg = (int *) calloc((size_t) V + 1, sizeof(int));
+    for (int e = 0; e < E; e++) if (!active[e]) { deg[Eu[e] + 1]++; deg[Ev[e] + 1]++; }
+    for (int v = 0; v < V; v++) deg[v + 1] += deg[v];
+    int *adj = (int *) malloc(sizeof(int) * (size_t) (deg[V] > 0 ? deg[V] : 1));
+    int *fill = (int *) malloc(sizeof(int) * (size_t) V);
+    for (int v = 0; v < V; v++) fill[v] = deg[v];
+    for (int e = 0; e < E; e++) if (!active[e]) { adj[fill[Eu[e]]++] = Ev[e]; adj[fill[Ev[e]]++] = Eu[e]; }
+    for (int v = 0; v < V; v++) Cv[v] = -1;
+    int rV = 0, assigned = 0, head = 0;
+    rVc[0] = 0;
+    for (int u = 0; u < V; u++) {
+        if (Cv[u] != -1) continue;
+        Cv[u] = rV;
+        Vc[assigned++] = u;
+        while (head < assigned) {
+            const int v = Vc[head++];
+            for (int k = deg[v]; k < deg[v + 1]; k++) {
+                const int w = adj[k];
+                if (Cv[w] != -1) continue;
+                Cv[w] = rV;
+                Vc[assigned++] = w;
+            }
+        }
+        rVc[++rV] = assigned;
+    }
+    free(deg); free(adj); free(fill);
+    return rV;
+}
+#endif
+
+/* reduced connectivity (reference :603-661), in canonical form: one reduced edge per unordered pair of components joined
+ * by at least one ACTIVE edge of nonzero weight, weights added up; an active edge whose two ends lie in the same component
+ * yields the loop (c, c) and is met from both of its ends, so it counts twice (:622-640 walks every member's arcs);
+ * components touched by no such edge get the loop (c, c) of weight eps (:645-648).
+ * Output sorted by (smaller component, larger component) - the reference emits first-encounter order, which only matters
+ * for the rounding of sums downstream.  acc: double so that the comparison is about the rule, not summation order.
+ * rEu / rEv / rLa need room for E + rV entries.  Returns rE. */
+int FN(oracle_cp_reduced_edges)(int V, int E, const int *Eu, const int *Ev, const unsigned char *active, const REAL *La_d1,
+                                const int *Cv, int rV, REAL eps, int *rEu, int *rEv, REAL *rLa)
+{
+    (void) V;
+    /* bucket the active nonzero edges by smaller component, then sort each bucket by larger component (insertion into a
+     * per-bucket list is enough at test sizes) */
+    int *cnt = (int *) calloc((size_t) rV + 1, sizeof(int));
+    for (int e = 0; e < E; e++) if (active[e] && La_d1[e] != 0) { const int a = Cv[Eu[e]], b = Cv[Ev[e]]; cnt[(a < b ? a : b) + 1]++; }
+    for (int c = 0; c < rV; c++) cnt[c + 1] += cnt[c];
+    const int m = cnt[rV];
+    int *hi = (int *) malloc(sizeof(int) * (size_t) (m > 0 ? m : 1));
+    double *w = (double *) malloc(sizeof(double) * (size_t) (m > 0 ? m : 1));
+    int *fill = (int *) malloc(sizeof(int) * (size_t) rV);
+    for (int c = 0; c < rV; c++) fill[c] = cnt[c];
+    unsigned char *touched = (unsigned char *) calloc((size_t) rV, 1);
+    for (int e = 0; e < E; e++) if (active[e] && La_d1[e] != 0) {
+        const int a = Cv[Eu[e]], b = Cv[Ev[e]], lo = a < b ? a : b, up = a < b ? b : a;
+        hi[fill[lo]] = up; w[fill[lo]] = (a == b ? 2.0 : 1.0) * (double) La_d1[e]; fill[lo]++;
+        touched[a] = touched[b] = 1;
+    }
+    int rE = 0;
+    double *sum = (double *) calloc((size_t) rV, sizeof(double));
+    unsigned char *seen = (unsigned char *) calloc((size_t) rV, 1);
+    for (int c = 0; c < rV; c++) {
+        for (int k = cnt[c]; k < cnt[c + 1]; k++) { sum[hi[k]] += w[k]; seen[hi[k]] = 1; }
+        if (!touched[c]) { rEu[rE] = c; rEv[rE] = c; rLa[rE++] = eps; continue; }
+        for (int d = c; d < rV; d++) if (seen[d]) { rEu[rE] = c; rEv[rE] = d; rLa[rE++] = (REAL) sum[d]; seen[d] = 0; sum[d] = 0.0; }
+    }
+    free(cnt); free(hi); free(w); free(fill); free(touched); free(sum); free(seen);
+    return rE;
+}
+
+/* merge step (reference :863-886): an active edge whose two components took (relatively) equal values is deactivated:
+ * d = |a - b| / max(|a|, |b|, eps) <= CP_difTol.  Returns the number of edges deactivated. */
+int FN(oracle_cp_merge)(int E, const int *Eu, const int *Ev, const int *Cv, const REAL *rX, REAL CP_difTol, REAL eps, unsigned char *active)
+{
+    int n = 0;
+    for (int e = 0; e < E; e++) {
+        if (!active[e]) continue;
+        REAL a = rX[Cv[Eu[e]]], b = rX[Cv[Ev[e]]], d = a - b;
+        if (a < 0) a = -a;
+        if (b < 0) b = -b;
+        if (d < 0) d = -d;
+        if (a < b) a = b;
+        d = (a > eps) ? d / a : d / eps;
+        if (d <= CP_difTol) { active[e] = 0; n++; }
+    }
+    return n;
+}

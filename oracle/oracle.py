@@ -237,3 +237,46 @@ def reduced_graph(Cv, rV, Eu, Ev, La_d1, La_l1, eps):
     w = np.concatenate([w, np.full(iso.shape[0], eps)]).astype(La_d1.dtype)
     rl1 = None if La_l1 is None else np.bincount(Cv, weights=La_l1.astype(np.float64), minlength=rV).astype(La_l1.dtype)
     return rEu, rEv, w, rl1
+
+
+class CpGraphOracle:
+    """ctypes access to oracle_cp_components / oracle_cp_reduced_edges_* / oracle_cp_merge_* """
+
+    def __init__(self):
+        if not os.path.exists(ORACLE_SO):
+            build(ref=False)
+        self.lib = C.CDLL(ORACLE_SO)
+
+    def components(self, V, Eu, Ev, active):
+        I, B = C.POINTER(C.c_int), C.POINTER(C.c_ubyte)
+        Eu, Ev, active = (np.ascontiguousarray(Eu, np.int32), np.ascontiguousarray(Ev, np.int32), np.ascontiguousarray(active, np.uint8))
+        Cv, Vc, rVc = np.zeros(V, np.int32), np.zeros(V, np.int32), np.zeros(V + 1, np.int32)
+        f = self.lib.oracle_cp_components
+        f.restype, f.argtypes = C.c_int, [C.c_int, C.c_int, I, I, B, I, I, I]
+        rV = f(V, Eu.shape[0], Eu.ctypes.data_as(I), Ev.ctypes.data_as(I), active.ctypes.data_as(B), Cv.ctypes.data_as(I), Vc.ctypes.data_as(I),
+               rVc.ctypes.data_as(I))
+        return Cv, rV, Vc, rVc[:rV + 1].copy()
+
+    def reduced_edges(self, V, Eu, Ev, active, La_d1, Cv, rV, eps):
+        dt = La_d1.dtype
+        R, suf = (C.c_float, "f32") if dt == np.float32 else (C.c_double, "f64")
+        I, B, P = C.POINTER(C.c_int), C.POINTER(C.c_ubyte), C.POINTER(R)
+        Eu, Ev, active, Cv = (np.ascontiguousarray(Eu, np.int32), np.ascontiguousarray(Ev, np.int32), np.ascontiguousarray(active, np.uint8),
+                              np.ascontiguousarray(Cv, np.int32))
+        E = Eu.shape[0]
+        rEu, rEv, rLa = np.zeros(E + rV, np.int32), np.zeros(E + rV, np.int32), np.zeros(E + rV, dt)
+        f = getattr(self.lib, f"oracle_cp_reduced_edges_{suf}")
+        f.restype, f.argtypes = C.c_int, [C.c_int, C.c_int, I, I, B, P, I, C.c_int, R, I, I, P]
+        n = f(V, E, Eu.ctypes.data_as(I), Ev.ctypes.data_as(I), active.ctypes.data_as(B), np.ascontiguousarray(La_d1).ctypes.data_as(P),
+              Cv.ctypes.data_as(I), rV, eps, rEu.ctypes.data_as(I), rEv.ctypes.data_as(I), rLa.ctypes.data_as(P))
+        return rEu[:n].copy(), rEv[:n].copy(), rLa[:n].copy()
+
+    def merge(self, Eu, Ev, Cv, rX, tol, eps, active):
+        dt = rX.dtype
+        R, suf = (C.c_float, "f32") if dt == np.float32 else (C.c_double, "f64")
+        I, B, P = C.POINTER(C.c_int), C.POINTER(C.c_ubyte), C.POINTER(R)
+        Eu, Ev, Cv = (np.ascontiguousarray(Eu, np.int32), np.ascontiguousarray(Ev, np.int32), np.ascontiguousarray(Cv, np.int32))
+        f = getattr(self.lib, f"oracle_cp_merge_{suf}")
+        f.restype, f.argtypes = C.c_int, [C.c_int, I, I, I, P, R, R, B]
+        return f(Eu.shape[0], Eu.ctypes.data_as(I), Ev.ctypes.data_as(I), Cv.ctypes.data_as(I), np.ascontiguousarray(rX).ctypes.data_as(P), tol, eps,
+                 active.ctypes.data_as(B))

@@ -74,3 +74,23 @@ def test_binder_rejects_wrong_element_types():
     with pytest.raises(TypeError):
         _abi._real_dtype(torch.zeros(4, dtype=torch.bfloat16))
     assert _abi._ptr(np.zeros(4, np.float32), C.c_float) is not None and _abi._ptr(None, C.c_float) is None
+
+
+def test_libcp_signature_matches_the_reference_binding():
+    """keyword names and defaults of python/CP_quadratic_l1_py.cpp:68-76 / :111-116"""
+    import inspect
+    from cp_pfdr_graph_d1_b200 import libCP
+    sig = inspect.signature(libCP.CP_quadratic_l1)
+    assert list(sig.parameters) == ["obs", "source", "target", "edge_weight", "A", "l1_weight", "positivity", "PFDR_rho",
+                                    "PFDR_condMin", "CP_difTol", "PFDR_difRcd", "PFDR_difTol", "CP_itMax", "PFDR_itMax", "verbose"]
+    d = {k: v.default for k, v in sig.parameters.items() if v.default is not inspect.Parameter.empty}
+    assert d == dict(positivity=0, PFDR_rho=1.0, PFDR_condMin=1e-3, CP_difTol=1e-3, PFDR_difRcd=0.0, PFDR_difTol=1e-4,
+                     CP_itMax=10, PFDR_itMax=10000, verbose=0)
+
+
+def test_libcp_fails_loudly_without_its_library(monkeypatch, tmp_path):
+    from cp_pfdr_graph_d1_b200 import libCP
+    monkeypatch.setenv("PFDR_B200_CP_LIB", str(tmp_path / "absent.so"))
+    monkeypatch.setattr(libCP, "_lib", None)
+    with pytest.raises(ImportError):
+        libCP.CP_quadratic_l1(np.zeros(3), np.array([0, 1]), np.array([1, 2]), 0.1, 1.0, 0.0)

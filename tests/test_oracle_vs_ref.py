@@ -281,3 +281,55 @@ def test_cp_reduce_identities():
     assert np.allclose(red.gradient(V, -V, M, AtY, rX, Cv, Vc, rVc), M @ x - AtY, rtol=1e-10, atol=1e-11)
     assert np.allclose(red.gradient(V, 0, a, AtY, rX, Cv, Vc, rVc), a * x - AtY, rtol=1e-12)
     assert np.allclose(red.gradient(V, 0, None, AtY, rX, Cv, Vc, rVc), x - AtY, rtol=1e-12)
+
+
+# the component numbering of the restated sweep against the reference's own (:570-600) - every cut-pursuit
+# run returns Cv; cutting exactly the edges whose ends lie in different components of that Cv and sweeping again must give
+# the same numbering back (components of the reference are connected through their non-cut edges by construction).
+@pytest.mark.parametrize("kind", ["eeg", "grid", "knn"])
+def test_cp_components_numbering(reference, kind):
+    from oracle import oracle as O
+    cp = O.cp_reference()
+    if cp is None:
+        pytest.skip("oracle/_ref/libref.so not built")
+    dt = np.float64
+    kw = dict(CP_difTol=1e-4, CP_itMax=4, rho=1.5, condMin=1e-3, difRcd=0.0, difTol=1e-6, itMax=2000)
+    if kind == "eeg":
+        w = synth.eeg_like(3, 30, dt)
+        r = cp.quadratic_d1_l1(w["Y"], w["A"], w["Eu"], w["Ev"], w["La_d1"], w["La_l1"], 1, w["N"], **kw)
+    elif kind == "grid":
+        w = synth.c2_denoise(12, dt, diag=True)
+        r = cp.quadratic_d1_l1((w["La_l2"] * w["Y"]).astype(dt), w["La_l2"], w["Eu"], w["Ev"], w["La_d1"], None, 0, 0, **kw)
+    else:
+        w = synth.c3_bounds_ata(400, 8, 128, dt)
+        r = cp.quadratic_d1_bounds(w["AtY"], w["AtA"], w["Eu"], w["Ev"], w["La_d1"], 0.0, 1.0, -w["V"], **kw)
+    Cv, rV = r["Cv"], r["rV"]
+    assert rV > 1
+    active = (Cv[w["Eu"]] != Cv[w["Ev"]]).astype(np.uint8)
+    oCv, orV, Vc, rVc = O.CpGraphOracle().components(w["V"], w["Eu"], w["Ev"], active)
+    assert orV == rV and np.array_equal(oCv, Cv)
+    assert np.array_equal(np.sort(Vc), np.arange(w["V"])) and np.array_equal(np.diff(rVc), np.bincount(Cv, minlength=rV))
+    assert all(np.all(Cv[Vc[rVc[c]:rVc[c + 1]]] == c) for c in range(rV))
+
+
+def test_cp_reduced_edges_and_merge_rules():
+    """hand-checked instance of :603-661 and :863-886: path 0-1-2-3-4 plus the chord 0-2 and an isolated vertex 5"""
+    from oracle import oracle as O
+    g = O.CpGraphOracle()
+    Eu = np.array([0, 1, 2, 3, 0], np.int32); Ev = np.array([1, 2, 3, 4, 2], np.int32)
+    La = np.array([1.0, 2.0, 4.0, 0.0, 8.0])
+    active = np.array([0, 1, 1, 1, 1], np.uint8)             # 0-1 joined; 1-2, 2-3 cut; 3-4 cut but weightless; 0-2 cut
+    Cv, rV, _, _ = g.components(6, Eu, Ev, active)
+    assert rV == 5 and np.array_equal(Cv, [0, 0, 1, 2, 3, 4])
+    rEu, rEv, rLa = g.reduced_edges(6, Eu, Ev, active, La, Cv, rV, 1e-16)
+    # {0,1}-{2}: 2 + 8; {2}-{3}: 4; {4} and {5} untouched by a nonzero cut edge -> loops of weight eps
+    assert list(zip(rEu, rEv)) == [(0, 1), (1, 2), (3, 3), (4, 4)] and np.allclose(rLa, [10.0, 4.0, 1e-16, 1e-16])
+    active2 = np.array([1, 0, 0, 0, 0], np.uint8)            # cut edge 0-1 inside a component (0 and 1 stay joined through 2): a loop, met twice
+    Cv2, rV2, _, _ = g.components(6, Eu, Ev, active2)
+    assert rV2 == 2 and np.array_equal(Cv2, [0, 0, 0, 0, 0, 1])
+    rEu, rEv, rLa = g.reduced_edges(6, Eu, Ev, active2, La, Cv2, rV2, 1e-16)
+    assert list(zip(rEu, rEv)) == [(0, 0), (1, 1)] and np.allclose(rLa, [2 * 1.0, 1e-16])
+    rX = np.array([1.0, 1.0005, 2.0, 0.0, 1e-20])
+    act = active.copy()
+    n = g.merge(Eu, Ev, Cv, rX, 1e-3, 1e-16, act)            # 1-2 and 0-2 join components 0 and 1 (values 1 / 1.0005: within 1e-3 relative)
+    assert n == 2 and np.array_equal(act, [0, 0, 1, 1, 0])
