@@ -534,6 +534,73 @@ def cp_solve_time():
             "host_cores": os.cpu_count()}
 
 
+def cp_outer_times(dev, with_cpu=True):
+    """the passes of one cut-pursuit outer iteration around the PFDR call, operator resident in HBM,
+    device in / device out.  Config 3 size for the dense passes (A^tA, V = 32768, float32: 4.3 GB read once per pass),
+    config 4's graph (252^3 grid, 48M edges) for the graph passes; the CPU figure is the oracle restatement of the
+    reference's serial sweep on the same graph (kind "port", 1 core)."""
+    import torch
+    from cp_pfdr_graph_d1_b200 import api
+    peak, _ = peaks()
+
+    def timed(f, reps=5):
+        f(); torch.cuda.synchronize()
+        t = []
+        for _ in range(reps):
+            torch.cuda.synchronize(); t0 = time.perf_counter(); f(); torch.cuda.synchronize(); t.append(time.perf_counter() - t0)
+        return float(np.median(t))
+
+    out = {}
+    V, rV = 32768, 300
+    g = torch.Generator(device=dev).manual_seed(5)
+    G = torch.randn(2048, V, device=dev, dtype=torch.float32, generator=g)
+    M = (G.t() @ G) / 2048 + 0.1 * torch.eye(V, device=dev)
+    del G
+    rng = np.random.default_rng(12)
+    Cv = rng.integers(0, rV, V).astype(np.int32); Cv[:rV] = np.arange(rV)
+    AtY = torch.randn(V, device=dev, dtype=torch.float32, generator=g)
+    rX = torch.rand(rV, device=dev, dtype=torch.float32, generator=g)
+    op = api.CpOperator(M, V, -V)
+    t_set = timed(lambda: op.set_components(Cv, rV))
+    t_red = timed(lambda: op.reduce(AtY, on_device=True))
+    t_grad = timed(lambda: op.gradient(rX, AtY, on_device=True))
+    B = V * V * 4
+    out["dense_ata_f32"] = {"V": V, "rV": rV, "operator_bytes": B, "set_components_ms": 1e3 * t_set,
+                            "reduce_ms": 1e3 * t_red, "reduce_gbs": B / t_red / 1e9, "reduce_frac": B / t_red / 1e9 / peak,
+                            "gradient_ms": 1e3 * t_grad, "gradient_gbs": B / t_grad / 1e9, "gradient_frac": B / t_grad / 1e9 / peak,
+                            "what": "wall clock around the C-ABI call (launches + one sync), outputs left on the device"}
+    op.close(); del M, op
+    torch.cuda.empty_cache()
+
+    n = 252
+    Vg = n ** 3
+    Eu, Ev = device_grid_edges(n, dev)
+    E = int(Eu.shape[0])
+    v = torch.arange(Vg, device=dev)
+    lab = 4 * (4 * (v // (n * n)) // n) + 4 * ((v // n) % n) // n            # config 4's ground-truth labels: 16 bars
+    del v
+    active = ((lab[Eu.long()] != lab[Ev.long()]) | (torch.rand(E, device=dev, generator=g) < 0.02)).to(torch.uint8)
+    del lab
+    res = {}
+    t_cc = timed(lambda: res.__setitem__("cc", api.cp_components(Vg, Eu, Ev, active, on_device=True)))
+    Cvd, rVg = res["cc"]
+    La = torch.full((E,), 0.2, device=dev, dtype=torch.float32)
+    t_re = timed(lambda: res.__setitem__("re", api.cp_reduced_edges(Vg, Eu, Ev, active, La, Cvd, rVg)))
+    rXg = torch.rand(rVg, device=dev, dtype=torch.float32, generator=g)
+    act2 = active.clone()
+    t_mg = timed(lambda: api.cp_merge(Eu, Ev, Cvd, rXg, 1e-3, act2))
+    out["graph_252"] = {"V": Vg, "E": E, "rV": int(rVg), "rE": int(res["re"][0].shape[0]), "components_ms": 1e3 * t_cc,
+                        "reduced_edges_ms": 1e3 * t_re, "merge_ms": 1e3 * t_mg}
+    if with_cpu:
+        from oracle import oracle as O
+        hEu, hEv, hact = Eu.cpu().numpy(), Ev.cpu().numpy(), active.cpu().numpy()
+        t0 = time.perf_counter()
+        oCv, orV, _, _ = O.CpGraphOracle().components(Vg, hEu, hEv, hact)
+        out["graph_252"]["components_cpu_port_ms"] = 1e3 * (time.perf_counter() - t0)
+        out["graph_252"]["Cv_identical"] = bool(orV == rVg and np.array_equal(oCv, Cvd.cpu().numpy()))
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -633,6 +700,10 @@ def main():
             line["cp_solve"] = cp_solve_time()
         except Exception as ex:
             line["cp_solve"] = {"error": f"{type(ex).__name__}: {ex}"[:300]}
+        try:
+            line["cp_outer"] = cp_outer_times(dev, with_cpu=not args.no_cpu)
+        except Exception as ex:
+            line["cp_outer"] = {"error": f"{type(ex).__name__}: {ex}"[:300]}
     print(json.dumps(line), flush=True)
 
 

@@ -220,26 +220,39 @@ class CpOperator:
         self._chk(self._lib.pfdr_b200_cp_set_components(self._h, int(rV), _ptr(Cv, _C.c_int)))
         self.rV = int(rV)
 
-    def reduce(self, Y, preAt=True, want_rA=True):
-        """-> (rA or None, rAA or None, rY or None) as numpy arrays (rA, rAA Fortran-ordered)"""
+    def reduce(self, Y, preAt=True, want_rA=True, on_device=False):
+        """-> (rA or None, rAA or None, rY or None): numpy arrays (rA, rAA Fortran-ordered), or with on_device torch CUDA
+        tensors holding the same column-major data (rA as (rV, N), rAA as (rV, rV): transposes of the matrices)"""
         N, rV, dt = self.N, self.rV, self._dt
         pre = bool(preAt) or N <= 0
-        rA = np.zeros((N, rV), dt, order="F") if (N > 0 and want_rA) else None
-        rAA = (np.zeros(rV, dt) if N == 0 else np.zeros((rV, rV), dt, order="F")) if pre else None
-        rY = np.zeros(rV, dt) if pre else None
+        if on_device:
+            import torch
+            tdt = torch.float32 if dt == np.float32 else torch.float64
+            new = lambda *shape: torch.empty(*shape, dtype=tdt, device="cuda")
+            rA = new(rV, N) if (N > 0 and want_rA) else None
+            rAA = (new(rV) if N == 0 else new(rV, rV)) if pre else None
+            rY = new(rV) if pre else None
+        else:
+            rA = np.zeros((N, rV), dt, order="F") if (N > 0 and want_rA) else None
+            rAA = (np.zeros(rV, dt) if N == 0 else np.zeros((rV, rV), dt, order="F")) if pre else None
+            rY = np.zeros(rV, dt) if pre else None
         Y = None if Y is None else _as_real(Y, dt)
         self._chk(self._lib.pfdr_b200_cp_reduce(self._h, self._vp(Y), int(pre), self._vp(rA), self._vp(rAA), self._vp(rY)))
         return rA, rAA, rY
 
-    def gradient(self, rX, YorR=None):
-        out = np.zeros(self.V, self._dt)
-        self._chk(self._lib.pfdr_b200_cp_gradient(self._h, self._vp(np.ascontiguousarray(rX, self._dt)),
+    def gradient(self, rX, YorR=None, on_device=False):
+        if on_device:
+            import torch
+            out = torch.empty(self.V, dtype=torch.float32 if self._dt == np.float32 else torch.float64, device="cuda")
+        else:
+            out = np.zeros(self.V, self._dt)
+        self._chk(self._lib.pfdr_b200_cp_gradient(self._h, self._vp(rX),
                                                   self._vp(YorR), self._vp(out)))
         return out
 
     def residual(self, rX, Y):
         out = np.zeros(self.N, self._dt)
-        self._chk(self._lib.pfdr_b200_cp_residual(self._h, self._vp(np.ascontiguousarray(rX, self._dt)), self._vp(Y), self._vp(out)))
+        self._chk(self._lib.pfdr_b200_cp_residual(self._h, self._vp(rX), self._vp(Y), self._vp(out)))
         return out
 
     def close(self):
@@ -257,18 +270,34 @@ class CpOperator:
 
 # ---- graph passes of the cut-pursuit's outer iteration (csrc/cpgraph.cu; reference src/CP_PFDR_graph_quadratic_d1_l1.cpp) ----
 def _u8(a):
-    return np.ascontiguousarray(a, dtype=np.uint8)
+    return a if hasattr(a, "data_ptr") else np.ascontiguousarray(a, dtype=np.uint8)
 
 
-def cp_components(V, Eu, Ev, active):
-    """connected components of the non-active edges, numbered by smallest vertex (:570-600) -> (Cv, rV)"""
+def _u8_ptr(a):
+    PB = _C.POINTER(_C.c_ubyte)
+    if hasattr(a, "data_ptr"):
+        import torch
+        if a.dtype != torch.uint8 or not a.is_cuda or not a.is_contiguous():
+            raise TypeError("edge flags on the device must be a contiguous torch.uint8 CUDA tensor")
+        return _C.cast(_C.c_void_p(a.data_ptr()), PB)
+    return a.ctypes.data_as(PB)
+
+
+def cp_components(V, Eu, Ev, active, on_device=False):
+    """connected components of the non-active edges, numbered by smallest vertex (:570-600) -> (Cv, rV); inputs numpy or
+    torch CUDA tensors; Cv a numpy array, or a torch CUDA tensor with on_device"""
     lib = _lib.load()
     Eu, Ev, active = _as_int(Eu), _as_int(Ev), _u8(active)
-    Cv, rV = np.zeros(V, np.int32), _C.c_int(0)
+    rV = _C.c_int(0)
+    if on_device:
+        import torch
+        Cv = torch.empty(V, dtype=torch.int32, device="cuda")
+    else:
+        Cv = np.zeros(V, np.int32)
     PI, PB = _C.POINTER(_C.c_int), _C.POINTER(_C.c_ubyte)
     f = lib.pfdr_b200_cp_components
     f.argtypes = [_C.c_int, _C.c_int, PI, PI, PB, PI, PI]
-    rc = f(int(V), int(Eu.shape[0]), _ptr(Eu, _C.c_int), _ptr(Ev, _C.c_int), active.ctypes.data_as(PB), _ptr(Cv, _C.c_int), _C.byref(rV))
+    rc = f(int(V), int(Eu.shape[0]), _ptr(Eu, _C.c_int), _ptr(Ev, _C.c_int), _u8_ptr(active), _ptr(Cv, _C.c_int), _C.byref(rV))
     if rc != 0:
         raise PfdrError(f"libpfdr_b200 status {rc}: {lib.pfdr_b200_last_error().decode()}")
     return Cv, rV.value
@@ -287,7 +316,7 @@ def cp_reduced_edges(V, Eu, Ev, active, La_d1, Cv, rV, eps=None, capacity=None):
     PI, PB, PR = _C.POINTER(_C.c_int), _C.POINTER(_C.c_ubyte), _C.POINTER(R)
     f = getattr(lib, f"pfdr_b200_cp_reduced_edges_{suf}")
     f.argtypes = [_C.c_int, _C.c_int, PI, PI, PB, PR, PI, _C.c_int, R, _C.c_int, PI, PI, PI, PR]
-    rc = f(int(V), E, _ptr(Eu, _C.c_int), _ptr(Ev, _C.c_int), active.ctypes.data_as(PB), _ptr(La_d1, R), _ptr(Cv, _C.c_int), int(rV), eps,
+    rc = f(int(V), E, _ptr(Eu, _C.c_int), _ptr(Ev, _C.c_int), _u8_ptr(active), _ptr(La_d1, R), _ptr(Cv, _C.c_int), int(rV), eps,
            cap, _C.byref(rE), _ptr(rEu, _C.c_int), _ptr(rEv, _C.c_int), _ptr(rLa, R))
     if rc != 0:
         raise PfdrError(f"libpfdr_b200 status {rc}: {lib.pfdr_b200_last_error().decode()}")
@@ -301,8 +330,8 @@ def cp_merge(Eu, Ev, Cv, rX, CP_difTol, active, eps=None):
     lib = _lib.load()
     dt = _real_dtype(rX)
     R, suf = _CT[dt]
-    if not (isinstance(active, np.ndarray) and active.dtype == np.uint8 and active.flags.c_contiguous):
-        raise TypeError("active is updated in place: it must be a contiguous uint8 array")
+    if not hasattr(active, "data_ptr") and not (isinstance(active, np.ndarray) and active.dtype == np.uint8 and active.flags.c_contiguous):
+        raise TypeError("active is updated in place: it must be a contiguous uint8 array (or torch.uint8 CUDA tensor)")
     Eu, Ev, Cv, rX = _as_int(Eu), _as_int(Ev), _as_int(Cv), _as_real(rX, dt)
     eps = float(np.finfo(dt).eps) if eps is None else float(eps)
     n = _C.c_int(0)
@@ -310,7 +339,7 @@ def cp_merge(Eu, Ev, Cv, rX, CP_difTol, active, eps=None):
     f = getattr(lib, f"pfdr_b200_cp_merge_{suf}")
     f.argtypes = [_C.c_int, _C.c_int, PI, PI, PI, _C.c_int, PR, R, R, PB, PI]
     rc = f(int(Cv.shape[0]), int(Eu.shape[0]), _ptr(Eu, _C.c_int), _ptr(Ev, _C.c_int), _ptr(Cv, _C.c_int), int(rX.shape[0]), _ptr(rX, R),
-           float(CP_difTol), eps, active.ctypes.data_as(PB), _C.byref(n))
+           float(CP_difTol), eps, _u8_ptr(active), _C.byref(n))
     if rc != 0:
         raise PfdrError(f"libpfdr_b200 status {rc}: {lib.pfdr_b200_last_error().decode()}")
     return n.value

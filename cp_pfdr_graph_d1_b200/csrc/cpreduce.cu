@@ -17,8 +17,7 @@ namespace pfdr {
 namespace {
 
 constexpr int PIECE = 64;                  // component members per piece
-constexpr int PHASES = 8;                  // warps of a CTA = interleaved sub-sequences of a piece
-constexpr int PER_PHASE = PIECE / PHASES;
+constexpr int LOADS = 8;                   // column loads a thread has in flight
 
 // ---------------------------------------------------------------------------------------------
 // component lists
@@ -55,8 +54,8 @@ __device__ __forceinline__ void piece_range(int p, const int *__restrict__ first
 
 // ---------------------------------------------------------------------------------------------
 // Pp[p][r] = sum over the members s of piece p of M[r + ld * Vc[s]]        (columns of a column-major matrix)
-// CTA = 8 warps: warp w takes members s0 + w, s0 + w + 8, ...; a lane owns VEC consecutive rows.  The (up to) 8 column
-// indices and then the 8 vector loads of a thread are issued before the first use.
+// A thread owns VEC consecutive rows and adds the (up to 64) columns of the piece in member order, eight vector loads in
+// flight at a time; a CTA of W warps covers W * 32 * VEC consecutive rows, i.e. reads W * 512 B (float) of every column.
 // ---------------------------------------------------------------------------------------------
 template <typename real, int VEC> struct RowVec;
 template <> struct RowVec<float, 4> {
@@ -74,52 +73,41 @@ template <typename real> struct RowVec<real, 1> {
 };
 
 template <typename real, int VEC>
-__global__ void __launch_bounds__(32 * PHASES) seg_colsum_kernel(const real *__restrict__ M, size_t ld, int rows, const int *__restrict__ Vc,
-                                                                const int *__restrict__ rVc, const int *__restrict__ first, int rV,
-                                                                double *__restrict__ Pp)
+__global__ void __launch_bounds__(256) seg_colsum_kernel(const real *__restrict__ M, size_t ld, int rows, const int *__restrict__ Vc,
+                                                        const int *__restrict__ rVc, const int *__restrict__ first, int rV,
+                                                        double *__restrict__ Pp)
 {
     const int p = blockIdx.x;
     if (p >= first[rV]) return;
     __shared__ int s_rng[2];
-    __shared__ double sm[PHASES][32 * VEC];
-    if (threadIdx.x == 0) { int c, s0, s1; piece_range(p, first, rVc, rV, c, s0, s1); s_rng[0] = s0; s_rng[1] = s1; }
+    __shared__ int s_idx[PIECE];
+    if (threadIdx.x == 0) { int c, s0, s1; piece_range(p, first, rVc, rV, c, s0, s1); s_rng[0] = s0; s_rng[1] = s1 - s0; }
     __syncthreads();
-    const int s0 = s_rng[0], s1 = s_rng[1];
-    const int lane = threadIdx.x & 31, ph = threadIdx.x >> 5;
-    const int r0 = (blockIdx.y * 32 + lane) * VEC;
-    int idx[PER_PHASE];
-#pragma unroll
-    for (int j = 0; j < PER_PHASE; j++) { const int s = s0 + ph + PHASES * j; idx[j] = s < s1 ? Vc[s] : -1; }
+    const int n = s_rng[1];
+    for (int j = threadIdx.x; j < n; j += blockDim.x) s_idx[j] = Vc[s_rng[0] + j];
+    __syncthreads();
+    const int r0 = (blockIdx.y * blockDim.x + threadIdx.x) * VEC;
+    if (r0 >= rows) return;
     double acc[VEC];
 #pragma unroll
     for (int i = 0; i < VEC; i++) acc[i] = 0.0;
-    if (r0 < rows) {
-        real v[PER_PHASE][VEC];
+    for (int j0 = 0; j0 < n; j0 += LOADS) {
+        real v[LOADS][VEC];
 #pragma unroll
-        for (int j = 0; j < PER_PHASE; j++) {
-            if (idx[j] >= 0) RowVec<real, VEC>::load(M + ld * (size_t) idx[j] + r0, v[j]);
+        for (int j = 0; j < LOADS; j++) {
+            if (j0 + j < n) RowVec<real, VEC>::load(M + ld * (size_t) s_idx[j0 + j] + r0, v[j]);
             else {
 #pragma unroll
                 for (int i = 0; i < VEC; i++) v[j][i] = (real) 0;
             }
         }
 #pragma unroll
-        for (int j = 0; j < PER_PHASE; j++)
+        for (int j = 0; j < LOADS; j++)
 #pragma unroll
             for (int i = 0; i < VEC; i++) acc[i] += (double) v[j][i];
     }
 #pragma unroll
-    for (int i = 0; i < VEC; i++) sm[ph][lane * VEC + i] = acc[i];
-    __syncthreads();
-    if (ph == 0 && r0 < rows) {
-#pragma unroll
-        for (int i = 0; i < VEC; i++) {
-            double t = 0.0;
-#pragma unroll
-            for (int w = 0; w < PHASES; w++) t += sm[w][lane * VEC + i];
-            Pp[(size_t) p * rows + r0 + i] = t;
-        }
-    }
+    for (int i = 0; i < VEC; i++) Pp[(size_t) p * rows + r0 + i] = acc[i];
 }
 
 // out[c][r] = sum of the pieces of component c, in piece order; stored in `real`
@@ -145,35 +133,47 @@ __global__ void comp_size_kernel(const int *__restrict__ rVc, int rV, real *__re
 // ---------------------------------------------------------------------------------------------
 // N > 0: rAA = rA^t rA (lower triangle computed, mirrored), rY = rA^t Y
 // ---------------------------------------------------------------------------------------------
+// 64 x 64 tile of rAA per CTA, 4 x 4 per thread, 16 rows of rA staged per step as [row][column] so that a thread's four
+// operands of either side are 32 contiguous bytes; products and sums in double, n ascending
 template <typename real>
 __global__ void __launch_bounds__(256) syrk_kernel(const real *__restrict__ rA, int N, int rV, real *__restrict__ rAA)
 {
     const int bu = blockIdx.y, bv = blockIdx.x;
     if (bv > bu) return;
-    __shared__ double a[32][33], b[32][33];
+    constexpr int T = 64, KC = 16, LD = T + 2;
+    __shared__ __align__(16) double a[KC][LD], b[KC][LD];
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-    double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
-    for (int n0 = 0; n0 < N; n0 += 32) {
+    double acc[4][4];
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const int col = (threadIdx.x >> 5) + 8 * k, n = n0 + (threadIdx.x & 31);
-            const int cu = bu * 32 + col, cv = bv * 32 + col;
-            a[col][threadIdx.x & 31] = (cu < rV && n < N) ? (double) rA[(size_t) N * cu + n] : 0.0;
-            b[col][threadIdx.x & 31] = (cv < rV && n < N) ? (double) rA[(size_t) N * cv + n] : 0.0;
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] = 0.0;
+    for (int n0 = 0; n0 < N; n0 += KC) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int e = threadIdx.x + 256 * q, k = e & (KC - 1), col = e >> 4, n = n0 + k;
+            const int cu = bu * T + col, cv = bv * T + col;
+            a[k][col] = (cu < rV && n < N) ? (double) rA[(size_t) N * cu + n] : 0.0;
+            b[k][col] = (cv < rV && n < N) ? (double) rA[(size_t) N * cv + n] : 0.0;
         }
         __syncthreads();
-#pragma unroll 8
-        for (int nn = 0; nn < 32; nn++) {
-            const double a0 = a[ty * 2][nn], a1 = a[ty * 2 + 1][nn], b0 = b[tx * 2][nn], b1 = b[tx * 2 + 1][nn];
-            acc[0][0] += a0 * b0; acc[0][1] += a0 * b1; acc[1][0] += a1 * b0; acc[1][1] += a1 * b1;
+#pragma unroll
+        for (int k = 0; k < KC; k++) {
+            const double2 a01 = *reinterpret_cast<const double2 *>(&a[k][ty * 4]), a23 = *reinterpret_cast<const double2 *>(&a[k][ty * 4 + 2]);
+            const double2 b01 = *reinterpret_cast<const double2 *>(&b[k][tx * 4]), b23 = *reinterpret_cast<const double2 *>(&b[k][tx * 4 + 2]);
+            const double av[4] = {a01.x, a01.y, a23.x, a23.y}, bw[4] = {b01.x, b01.y, b23.x, b23.y};
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) acc[i][j] += av[i] * bw[j];
         }
         __syncthreads();
     }
 #pragma unroll
-    for (int i = 0; i < 2; i++)
+    for (int i = 0; i < 4; i++)
 #pragma unroll
-        for (int j = 0; j < 2; j++) {
-            const int cu = bu * 32 + ty * 2 + i, cv = bv * 32 + tx * 2 + j;
+        for (int j = 0; j < 4; j++) {
+            const int cu = bu * T + ty * 4 + i, cv = bv * T + tx * 4 + j;
             if (cu < rV && cv <= cu) {
                 const real t = (real) acc[i][j];
                 rAA[(size_t) rV * cu + cv] = t;
@@ -330,13 +330,12 @@ struct CpOperator : CpOperatorBase {
     // Pp[p][r] over the pieces of the current components
     void colsum(const real *M, size_t ld, int rows, double *Pp)
     {
-        if (vec4_ok(M, ld, rows)) {
-            dim3 grid(pieces_max, cdiv(rows, 128));
-            { auto kern = seg_colsum_kernel<real, 4>; PFDR_LAUNCH(kern, grid, 32 * PHASES, 0, M, ld, rows, Vc.p, rVc.p, first.p, rV, Pp); }
-        } else {
-            dim3 grid(pieces_max, cdiv(rows, 32));
-            { auto kern = seg_colsum_kernel<real, 1>; PFDR_LAUNCH(kern, grid, 32 * PHASES, 0, M, ld, rows, Vc.p, rVc.p, first.p, rV, Pp); }
-        }
+        const bool v4 = vec4_ok(M, ld, rows);
+        const int per_warp = v4 ? 128 : 32;
+        const int warps = (int) std::min<size_t>(8, cdiv(rows, per_warp));
+        dim3 grid(pieces_max, cdiv(rows, (size_t) per_warp * warps));
+        if (v4) { auto kern = seg_colsum_kernel<real, 4>; PFDR_LAUNCH(kern, grid, 32 * warps, 0, M, ld, rows, Vc.p, rVc.p, first.p, rV, Pp); }
+        else { auto kern = seg_colsum_kernel<real, 1>; PFDR_LAUNCH(kern, grid, 32 * warps, 0, M, ld, rows, Vc.p, rVc.p, first.p, rV, Pp); }
     }
 
     // out[c] = sum of vec over component c (vec indexed by vertex)
@@ -366,7 +365,7 @@ struct CpOperator : CpOperatorBase {
             copy_out(static_cast<real *>(rA_out), rA.p, (size_t) N * rV);
             if (pre) {
                 DevBuf<real> rAA((size_t) rV * rV);
-                dim3 grid(cdiv(rV, 32), cdiv(rV, 32));
+                dim3 grid(cdiv(rV, 64), cdiv(rV, 64));
                 PFDR_LAUNCH(syrk_kernel<real>, grid, 256, 0, rA.p, N, rV, rAA.p);
                 if (vec4_ok(rA.p, (size_t) N, N) && vec4_ok(Y.p, 4, N))
                     { auto kern = col_dot_kernel<real, 4, 32>; PFDR_LAUNCH(kern, cdiv(rV, 8), 256, 0, rA.p, (size_t) N, N, rV, Y.p, (const real *) nullptr, 0, rY.p); }

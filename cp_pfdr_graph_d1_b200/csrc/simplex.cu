@@ -904,17 +904,22 @@ __global__ void __launch_bounds__(256) proj_small_kernel(real *__restrict__ X, c
 }
 
 // any D: one thread per column, the reference's loops verbatim on global memory, flags in a bit set
+// WORDS > 0: the flags of up to 32 * WORDS coordinates in local memory; WORDS == 0: in the scratch array `flags`
+// (words_per_col words per column) - no limit on D
 template <typename real, int WORDS>
 __global__ void __launch_bounds__(128) proj_serial_kernel(real *__restrict__ X, const real *__restrict__ M, int D, int N,
-                                                          int nm, const real *__restrict__ A, int na)
+                                                          int nm, const real *__restrict__ A, int na, unsigned *__restrict__ flags,
+                                                          int words_per_col)
 {
     const long long n = (long long) blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
     real *x = X + (size_t) n * D;
     const real *m = M + (size_t) (n < nm ? n : nm - 1) * D;
     const real a = A[n < na ? n : na - 1];
-    unsigned act[WORDS];
-    for (int i = 0; i < WORDS; i++) act[i] = 0;
+    unsigned local[WORDS > 0 ? WORDS : 1];
+    unsigned *act = WORDS > 0 ? local : flags + (size_t) n * words_per_col;
+    const int words = WORDS > 0 ? WORDS : words_per_col;
+    for (int i = 0; i < words; i++) act[i] = 0;
     real la = (x[0] - a) / m[0], s = m[0];
     x[0] = x[0] / m[0]; act[0] = 1u;
     for (int d = 1; d < D; d++) {
@@ -936,7 +941,6 @@ template <typename real>
 void proj_simplex_metric(real *X, const real *M, int D, int N, int nm, const real *A, int na)
 {
     PFDR_REQUIRE(D >= 1 && N >= 0 && nm >= 1 && na >= 1, "proj_simplex_metric: D, nm, na must be positive");
-    PFDR_REQUIRE(D <= 4096, "proj_simplex_metric: D > 4096 is not supported");
     if (N == 0) return;
     const size_t n = (size_t) D * N;
     const bool inplace = is_device_ptr(X);
@@ -956,8 +960,15 @@ void proj_simplex_metric(real *X, const real *M, int D, int N, int nm, const rea
         while (TPV < D) { TPV <<= 1; logTPV++; }
         const size_t warps = ((size_t) N + (32 / TPV) - 1) / (32 / TPV);
         PFDR_LAUNCH(proj_small_kernel<real>, cdiv(warps * 32, 256), 256, 0, dX, dM.p, D, N, nm, dA.p, na, TPV, logTPV);
+    } else if (D <= 4096) {
+        PFDR_LAUNCH((proj_serial_kernel<real, 128>), cdiv(N, 128), 128, 0, dX, dM.p, D, N, nm, dA.p, na, (unsigned *) nullptr, 0);
     } else {
-        PFDR_LAUNCH((proj_serial_kernel<real, 128>), cdiv(N, 128), 128, 0, dX, dM.p, D, N, nm, dA.p, na);
+        const int words = (D + 31) / 32;
+        DevBuf<unsigned> flags((size_t) N * words);
+        PFDR_LAUNCH((proj_serial_kernel<real, 0>), cdiv(N, 128), 128, 0, dX, dM.p, D, N, nm, dA.p, na, flags.p, words);
+        if (!inplace) copy_out(X, dX, n);
+        PFDR_CUDA(cudaStreamSynchronize(ctx().stream));
+        return;
     }
     if (!inplace) copy_out(X, dX, n);
     PFDR_CUDA(cudaStreamSynchronize(ctx().stream));

@@ -173,6 +173,18 @@ def test_proj_simplex_metric(gpu_api, oracle, dtype, D):
         assert np.array_equal(got == 0, ref == 0) or dtype is np.float32
 
 
+@pytest.mark.parametrize("D", [4096, 5000])
+def test_proj_simplex_metric_many_coordinates(gpu_api, oracle, D):
+    """no limit on D (the reference has none, src/proj_simplex_metric.cpp:18-83): flags in local memory up to 4096
+    coordinates, in a scratch array beyond"""
+    rng = np.random.default_rng(D)
+    X = rng.normal(0.0, 1.0, (40, D))
+    M = rng.uniform(0.2, 1.0, (40, D))
+    got = gpu_api.proj_simplex_metric(X.copy(), M, None)
+    ref = oracle.proj_simplex_metric(X.copy(), M, None)
+    assert np.allclose(got, ref, rtol=1e-10, atol=1e-13) and np.array_equal(got == 0, ref == 0)
+
+
 def test_proj_simplex_empty(gpu_api):
     X = np.zeros((0, 4), np.float32)
     gpu_api.proj_simplex_metric(X, np.ones((1, 4), np.float32))
