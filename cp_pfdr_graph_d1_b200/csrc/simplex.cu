@@ -24,7 +24,6 @@
 #include <chrono>
 
 #include "simplex.cuh"
-#include <cooperative_groups.h>
 #include "dia.cuh"
 #include "simplex_dia.cuh"
 
@@ -141,17 +140,16 @@ __global__ void simplex_finalize_kernel(SP<real> p)
 
 constexpr int SIMPLEX_HUB_ROWS = 32;   // rows of a slice walked by one lane group per vertex; past that the warp shares a hub's rows
 
-// One iteration over the half-edge table; false when the control block says the solve is on hold (nothing done).
-// COH: arrays written by other CTAs of the same launch (forward points, edge copies, iterate) are read through L2.
-template <typename real, int LPT, bool PERK, int LOSS, bool IDX32, bool HUB, bool COH>
-__device__ __forceinline__ bool simplex_iter_body(const SP<real> &p, double *smem)
+template <typename real, int LPT, bool PERK, int LOSS, int MINB, bool IDX32, bool HUB>
+__global__ void __launch_bounds__(256, MINB) simplex_iter_kernel(SP<real> p)
 {
     typedef VecN<real, LPT> vec;
+    __shared__ double smem[32];
     Ctl *ctl = p.ctl;
     const CtlView cv = load_ctl(ctl);
     if (cv.hold != 0 || cv.state != ST_RUN) {
         if (cv.hold == 0 && blockIdx.x == 0 && threadIdx.x == 0) ctl->hold = 1;
-        return false;
+        return;
     }
     const int it = cv.it, cur = it & 1;
     const real *__restrict__ Zin = cur ? p.Z1 : p.Z0;
@@ -174,7 +172,7 @@ __device__ __forceinline__ bool simplex_iter_body(const SP<real> &p, double *sme
         const int v = (int) (slice << p.logC) + vl;
         const bool on = (v < p.Vown) && (k0 < K);    // LPT == 4 requires K % 4 == 0: all LPT labels valid
         const size_t vk = (size_t) (on ? v : 0) * K + (on ? k0 : 0);
-        const vec pold = ldm<real, LPT, COH>(Pc + vk), fown = ldm<real, LPT, COH>(Fc + vk), Tv = ldv<real, LPT>(Tg + vk);
+        const vec pold = ldv<real, LPT>(Pc + vk), fown = ldv<real, LPT>(Fc + vk), Tv = ldv<real, LPT>(Tg + vk);
         vec Sv;
         if (PERK) Sv = ldv<real, LPT>(p.Sinvk + vk); else Sv = splat<real, LPT>(p.Sinv[on ? v : 0]);
         const long long base = p.slice_off[slice];
@@ -195,15 +193,15 @@ __device__ __forceinline__ bool simplex_iter_body(const SP<real> &p, double *sme
         if (on && wl > 0) {
             n_c = nbr[s]; tw_c = twin[s];
             if (!PERK) w_c = p.w[s];
-            zo_c = ldm<real, LPT, COH>(Zin + zoff);
+            zo_c = ldv<real, LPT>(Zin + zoff);
         }
         for (int j = 0; j < wl; j++) {
             const bool live = n_c >= 0;
             vec zt, fn, tn, wvk, th;
             if (live) {
                 const idx_t no = (idx_t) n_c * (idx_t) K + (idx_t) k0;
-                zt = ldm<real, LPT, COH>(Zin + ((idx_t) tw_c * (idx_t) K + (idx_t) k0));
-                fn = ldm<real, LPT, COH>(Fc + no);
+                zt = ldv<real, LPT>(Zin + ((idx_t) tw_c * (idx_t) K + (idx_t) k0));
+                fn = ldv<real, LPT>(Fc + no);
                 if (LOSS != LOSS_LIN) tn = ldv<real, LPT>(Tg + no);
                 if (PERK) { wvk = ldv<real, LPT>(p.wk + zoff); th = ldv<real, LPT>(p.thk + zoff); }
             }
@@ -213,7 +211,7 @@ __device__ __forceinline__ bool simplex_iter_body(const SP<real> &p, double *sme
             if (on && j + 1 < wl) {
                 n_n = nbr[s + C]; tw_n = twin[s + C];
                 if (!PERK) w_n = p.w[s + C];
-                zo_n = ldm<real, LPT, COH>(Zin + (zoff + rowK));
+                zo_n = ldv<real, LPT>(Zin + (zoff + rowK));
             }
             if (live) {
                 const vec zn = prox_row<real, LPT, PERK, LOSS>(rho, fown, pold, Tv, Sv, zo_c, zt, fn, tn, wvk, th, w_c, acc);
@@ -256,15 +254,15 @@ __device__ __forceinline__ bool simplex_iter_body(const SP<real> &p, double *sme
                             const idx_t zo_off = (idx_t) sh[u] * (idx_t) K + (idx_t) k0, no = (idx_t) n[u] * (idx_t) K + (idx_t) k0;
                             tw[u] = twin[sh[u]];
                             wh[u] = PERK ? (real) 0 : p.w[sh[u]];
-                            zo[u] = ldm<real, LPT, COH>(Zin + zo_off);
-                            fn[u] = ldm<real, LPT, COH>(Fc + no);
+                            zo[u] = ldv<real, LPT>(Zin + zo_off);
+                            fn[u] = ldv<real, LPT>(Fc + no);
                             if (LOSS != LOSS_LIN) tn[u] = ldv<real, LPT>(Tg + no);
                             if (PERK) { wvk[u] = ldv<real, LPT>(p.wk + zo_off); th[u] = ldv<real, LPT>(p.thk + zo_off); }
                         }
                     }
 #pragma unroll
                     for (int u = 0; u < HU; u++)
-                        if (n[u] >= 0) zt[u] = ldm<real, LPT, COH>(Zin + ((idx_t) tw[u] * (idx_t) K + (idx_t) k0));
+                        if (n[u] >= 0) zt[u] = ldv<real, LPT>(Zin + ((idx_t) tw[u] * (idx_t) K + (idx_t) k0));
 #pragma unroll
                     for (int u = 0; u < HU; u++) {
                         if (n[u] >= 0) {
@@ -286,30 +284,6 @@ __device__ __forceinline__ bool simplex_iter_body(const SP<real> &p, double *sme
     if (grid_sum_fast<1, real>(ctl, p.partial, red, tot, smem) && threadIdx.x == 0) {
         if (p.sharded) p.sums[p.rank] = tot[0];
         else simplex_finalize(p, it, tot[0]);
-    }
-    return true;
-}
-
-template <typename real, int LPT, bool PERK, int LOSS, int MINB, bool IDX32, bool HUB>
-__global__ void __launch_bounds__(256, MINB) simplex_iter_kernel(SP<real> p)
-{
-    __shared__ double smem[32];
-    simplex_iter_body<real, LPT, PERK, LOSS, IDX32, HUB, false>(p, smem);
-}
-
-// Small problems (the reduced problems of the cut-pursuit, ref src/CP_PFDR_graph_loss_d1_simplex.cpp:778): the whole grid
-// is ONE thread-block cluster and runs `trips` iterations per launch, a cluster barrier between them instead of a kernel
-// boundary.  Same body, same order of every sum: results are bit-identical to the one-launch-per-iteration path.  Every
-// CTA of the cluster takes the same decision at the top of a trip (the control block was settled before the barrier).
-template <typename real, int LPT, bool PERK, int LOSS, bool IDX32, bool HUB>
-__global__ void __launch_bounds__(256, 1) simplex_loop_kernel(SP<real> p, int trips)
-{
-    __shared__ double smem[32];
-    cooperative_groups::cluster_group cl = cooperative_groups::this_cluster();
-    for (int t = 0; t < trips; t++) {
-        if (!simplex_iter_body<real, LPT, PERK, LOSS, IDX32, HUB, true>(p, smem)) break;
-        __threadfence();
-        cl.sync();
     }
 }
 
@@ -409,9 +383,6 @@ struct SimplexSolver : SolverBase {
     cudaGraphExec_t gexec = nullptr;
     ProgressPrinter progress;
     int graph_trips = 0, grid = 0, ogrid = 0, LPT = 1, Vglobal = 0;
-    int loop_trips = 0;             // > 0 while enqueue_trip() is to launch the multi-iteration cluster kernel
-    bool loop_off = false, looped = false;
-    cudaError_t loop_rc = cudaSuccess;
 
     SimplexSolver(const SimplexProblem<real> &q_, bool keep) : q(q_), keep_p0(keep) {}
     ~SimplexSolver() override
@@ -676,23 +647,6 @@ struct SimplexSolver : SolverBase {
         if (link.world > 1) reset();                          // collective: first preconditioning, ghost zones, barrier
     }
 
-    // one iteration (loop_trips == 0) or, for a grid that fits one thread-block cluster, loop_trips iterations in one launch
-    template <int L, bool PERK, int LOSS, int MB, bool I32, bool HUB>
-    void launch_variant()
-    {
-        if (loop_trips == 0) { PFDR_LAUNCH((simplex_iter_kernel<real, L, PERK, LOSS, MB, I32, HUB>), ogrid, 256, 0, p); return; }
-        auto kern = simplex_loop_kernel<real, L, PERK, LOSS, I32, HUB>;
-        if (ogrid > 8) cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(ogrid); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = ctx().stream;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = ogrid; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
-        loop_rc = cudaLaunchKernelEx(&cfg, kern, p, loop_trips);
-        if (loop_rc != cudaSuccess) cudaGetLastError();          // a cluster this large may not be schedulable: the caller falls back
-        else ctx().count_launch();
-    }
     template <int L, bool PERK, int LOSS>
     void launch_iter_u()
     {
@@ -701,11 +655,11 @@ struct SimplexSolver : SolverBase {
         const char *ie = getenv("PFDR_B200_IDX32");              // read per call: the tests switch it (0: 64-bit element offsets)
         const bool i32 = !(ie && ie[0] == '0');
         // a slice wider than SIMPLEX_HUB_ROWS (a hub vertex): variant whose warps share the hub's rows
-        if (g.max_width > SIMPLEX_HUB_ROWS) launch_variant<L, PERK, LOSS, 1, false, true>();
+        if (g.max_width > SIMPLEX_HUB_ROWS) PFDR_LAUNCH((simplex_iter_kernel<real, L, PERK, LOSS, 1, false, true>), ogrid, 256, 0, p);
         else if (L > 1 && !PERK && small && i32) {
-            if constexpr (L > 1) launch_variant<L, false, LOSS, MBD, true, false>();
+            if constexpr (L > 1) PFDR_LAUNCH((simplex_iter_kernel<real, L, false, LOSS, MBD, true, false>), ogrid, 256, 0, p);
         }
-        else launch_variant<L, PERK, LOSS, MBD, false, false>();
+        else PFDR_LAUNCH((simplex_iter_kernel<real, L, PERK, LOSS, MBD, false, false>), ogrid, 256, 0, p);
     }
     // K > 128: one generic variant per (labels per lane, loss): 64-bit offsets, one CTA per SM's worth of registers
     template <int L, bool PERK>
@@ -743,24 +697,9 @@ struct SimplexSolver : SolverBase {
     }
     int launches_per_trip() const { return (q.Obj ? 1 : 0) + 1 + (sharded ? 4 : 0); }
 
-    // the iteration grid fits one thread-block cluster: a batch of iterations is one launch (simplex_loop_kernel)
-    bool loop_mode() const
-    {
-        if (loop_off || dia || sharded || slab || q.Obj || LPT > 4 || ogrid > 16) return false;
-        const char *se = getenv("PFDR_B200_SMALL");
-        return !(se && se[0] == '0');
-    }
-
     void enqueue_batch(int batch)
     {
         cudaStream_t st = ctx().stream;
-        if (loop_mode()) {
-            loop_trips = batch; loop_rc = cudaSuccess;
-            enqueue_trip();
-            loop_trips = 0;
-            if (loop_rc == cudaSuccess) { looped = true; return; }
-            loop_off = true;                                     // not schedulable on this device: the graph path from here on
-        }
         if (!gexec || graph_trips != batch) {
             if (gexec) { cudaGraphExecDestroy(gexec); gexec = nullptr; }
             cudaGraph_t graph;
@@ -910,9 +849,8 @@ void solve_simplex(const SimplexProblem<real> &q)
         auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
             return std::chrono::duration<double, std::milli>(b - a).count();
         };
-        fprintf(stderr, "[pfdr_b200] simplex V=%d E=%d K=%d f%d: %d it, setup %.2f ms, run %.2f ms (%s, device loop %.2f ms), fetch %.2f ms\n",
-                q.V, q.E, q.K, (int) sizeof(real) * 8, (int) ctx().stats.iterations, ms(t0, t1), ms(t1, t2),
-                s.looped ? "cluster kernel" : "one launch per iteration", ctx().stats.loop_ms, ms(t2, t3));
+        fprintf(stderr, "[pfdr_b200] simplex V=%d E=%d K=%d f%d: %d it, setup %.2f ms, run %.2f ms (device loop %.2f ms), fetch %.2f ms\n",
+                q.V, q.E, q.K, (int) sizeof(real) * 8, (int) ctx().stats.iterations, ms(t0, t1), ms(t1, t2), ctx().stats.loop_ms, ms(t2, t3));
     }
 }
 template void solve_simplex<float>(const SimplexProblem<float> &);

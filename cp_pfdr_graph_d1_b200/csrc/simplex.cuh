@@ -73,35 +73,6 @@ __device__ __forceinline__ VecN<real, L> ldv(const real *q)
     }
     return r;
 }
-// the same through L2 only (ld.global.cg): for arrays other CTAs write during the SAME launch (the multi-iteration
-// cluster kernel) - a line cached in this SM's L1 by an earlier iteration would be stale
-template <typename real, int L>
-__device__ __forceinline__ VecN<real, L> ldv_cg(const real *q)
-{
-    VecN<real, L> r;
-    if constexpr (L == 1) r.v[0] = __ldcg(q);
-    else if constexpr (L == 2) {
-        if constexpr (sizeof(real) == 4) { const float2 t = __ldcg(reinterpret_cast<const float2 *>(q)); r.v[0] = t.x; r.v[1] = t.y; }
-        else { const double2 t = __ldcg(reinterpret_cast<const double2 *>(q)); r.v[0] = t.x; r.v[1] = t.y; }
-    } else {
-#pragma unroll
-        for (int j = 0; j < L; j += 4) {
-            if constexpr (sizeof(real) == 4) {
-                const float4 t = __ldcg(reinterpret_cast<const float4 *>(q + j));
-                r.v[j] = t.x; r.v[j + 1] = t.y; r.v[j + 2] = t.z; r.v[j + 3] = t.w;
-            } else {
-                const double2 a = __ldcg(reinterpret_cast<const double2 *>(q + j)), b = __ldcg(reinterpret_cast<const double2 *>(q + j + 2));
-                r.v[j] = a.x; r.v[j + 1] = a.y; r.v[j + 2] = b.x; r.v[j + 3] = b.y;
-            }
-        }
-    }
-    return r;
-}
-template <typename real, int L, bool COH>
-__device__ __forceinline__ VecN<real, L> ldm(const real *q)
-{
-    if constexpr (COH) return ldv_cg<real, L>(q); else return ldv<real, L>(q);
-}
 template <typename real, int L>
 __device__ __forceinline__ void stv(real *q, const VecN<real, L> &r)
 {

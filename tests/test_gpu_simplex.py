@@ -53,33 +53,6 @@ def test_simplex_parity_scalar_lanes(gpu_api, oracle, monkeypatch, name, dtype):
     assert np.allclose(got.Obj[:n + 1], ref.Obj[:n + 1], rtol=tol, atol=tol * max(float(np.abs(ref.Obj).max()), 1.0) * 1e-1)
 
 
-@pytest.mark.parametrize("dtype", [np.float32, np.float64])
-@pytest.mark.parametrize("name", ["kla_rand", "kla_rand_k16", "kla_rand_k50", "kla", "kla_recond", "kla_labels", "kla_k16", "kla_recond_k16",
-                                  "lin_k16", "quad_weighted_k16", "kla_k33", "kla_k1", "kla_it0", "kla_notrack"])
-def test_cluster_loop_kernel_matches_one_launch_per_iteration(gpu_api, oracle, monkeypatch, name, dtype):
-    """small problems without an objective record (the way the cut-pursuit calls, ref src/CP_PFDR_graph_loss_d1_simplex.cpp:778)
-    run whole batches of iterations in one launch of a thread-block cluster; PFDR_B200_SMALL=0 forces one launch per
-    iteration: same body, same bits.  Both against the oracle."""
-    from cp_pfdr_graph_d1_b200.api import _b
-    args, kw = problems.simplex_case(name, dtype)
-    kw = dict(kw, want_obj=False)
-    monkeypatch.setenv("PFDR_B200_DIA", "0")                     # the half-edge table (what irregular reduced graphs take)
-    run = lambda b: b.PFDR_graph_loss_d1_simplex(*(a.copy() if isinstance(a, np.ndarray) else a for a in args), **kw)
-    got = run(_b())
-    st = gpu_api.last_stats()
-    monkeypatch.setenv("PFDR_B200_SMALL", "0")
-    one = run(_b())
-    st1 = gpu_api.last_stats()
-    assert got.it == one.it and np.array_equal(got.X, one.X)
-    if got.Dif is not None:
-        assert np.array_equal(got.Dif, one.Dif)
-    if got.it > 4:
-        assert st["loop_launches"] * 4 <= st1["loop_launches"], (st["loop_launches"], st1["loop_launches"])
-    ref = run(oracle)
-    assert abs(got.it - ref.it) <= (0 if dtype is np.float64 else max(2, ref.it // 20))
-    assert rel(got.X, ref.X) < TOL[dtype]
-
-
 def chain_or_image_case(kind, K, dtype):
     """1-D chain (one offset) / 2-D image (two offsets) label problems: the other shapes of the stencil layout"""
     rng = np.random.default_rng(K + len(kind))
