@@ -126,14 +126,15 @@ struct DevBuf {
     T *p = nullptr;
     size_t n = 0;
     bool pooled = false, borrowed = false;
+    cudaStream_t home = nullptr;       // stream the block was allocated on: freed on the same one, whoever destroys the buffer
     DevBuf() {}
     explicit DevBuf(size_t count) { alloc(count); }
     DevBuf(const DevBuf &) = delete;
     DevBuf &operator=(const DevBuf &) = delete;
-    DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n), pooled(o.pooled), borrowed(o.borrowed) { o.p = nullptr; o.n = 0; }
+    DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n), pooled(o.pooled), borrowed(o.borrowed), home(o.home) { o.p = nullptr; o.n = 0; }
     DevBuf &operator=(DevBuf &&o) noexcept
     {
-        if (this != &o) { release(); p = o.p; n = o.n; pooled = o.pooled; borrowed = o.borrowed; o.p = nullptr; o.n = 0; }
+        if (this != &o) { release(); p = o.p; n = o.n; pooled = o.pooled; borrowed = o.borrowed; home = o.home; o.p = nullptr; o.n = 0; }
         return *this;
     }
     void borrow(T *q, size_t count) { release(); p = q; n = count; borrowed = true; }     // memory owned by someone else (a slab arena)
@@ -143,11 +144,12 @@ struct DevBuf {
         n = count;
         if (!count) return;
         pooled = use_pool();
-        if (pooled) PFDR_CUDA(cudaMallocAsync((void **) &p, count * sizeof(T), ctx().stream));
+        home = ctx().stream;
+        if (pooled) PFDR_CUDA(cudaMallocAsync((void **) &p, count * sizeof(T), home));
         else PFDR_CUDA(cudaMalloc((void **) &p, count * sizeof(T)));
     }
     void release() {
-        if (p && !borrowed) { if (pooled) cudaFreeAsync(p, ctx().stream); else cudaFree(p); }
+        if (p && !borrowed) { if (pooled) cudaFreeAsync(p, home); else cudaFree(p); }
         p = nullptr; n = 0; borrowed = false;
     }
     void zero() { if (p) PFDR_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), ctx().stream)); }
@@ -214,10 +216,11 @@ inline void copy_out(T *dst, const T *dev_src, size_t count)
 
 inline int num_sms()
 {
-    static int sms = 0;
-    if (!sms) {
-        int dev; PFDR_CUDA(cudaGetDevice(&dev));
+    static thread_local int sms = 0, of_dev = -1;      // per host thread and device (a thread may drive one GPU of several)
+    int dev; PFDR_CUDA(cudaGetDevice(&dev));
+    if (dev != of_dev) {
         PFDR_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        of_dev = dev;
     }
     return sms;
 }
