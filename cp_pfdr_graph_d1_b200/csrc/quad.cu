@@ -1241,6 +1241,25 @@ __global__ void __launch_bounds__(256) ax_partial_kernel(QP<real> p, int TX, dou
         if (on) {
             const real *__restrict__ Ab = p.A + (size_t) nb * VEC;
             size_t v = v0 + ty;
+            // eight columns in flight per thread (the same two groups of four, added in the same order as the loop below)
+            for (; v + 7 * (size_t) TY < v1; v += 8 * (size_t) TY) {
+                real a0[VEC], a1[VEC], a2[VEC], a3[VEC], a4[VEC], a5[VEC], a6[VEC], a7[VEC];
+                vload<real, VEC>(Ab + (size_t) N * v, a0);
+                vload<real, VEC>(Ab + (size_t) N * (v + TY), a1);
+                vload<real, VEC>(Ab + (size_t) N * (v + 2 * (size_t) TY), a2);
+                vload<real, VEC>(Ab + (size_t) N * (v + 3 * (size_t) TY), a3);
+                vload<real, VEC>(Ab + (size_t) N * (v + 4 * (size_t) TY), a4);
+                vload<real, VEC>(Ab + (size_t) N * (v + 5 * (size_t) TY), a5);
+                vload<real, VEC>(Ab + (size_t) N * (v + 6 * (size_t) TY), a6);
+                vload<real, VEC>(Ab + (size_t) N * (v + 7 * (size_t) TY), a7);
+                const real x0 = X[v], x1 = X[v + TY], x2 = X[v + 2 * (size_t) TY], x3 = X[v + 3 * (size_t) TY];
+                const real x4 = X[v + 4 * (size_t) TY], x5 = X[v + 5 * (size_t) TY], x6 = X[v + 6 * (size_t) TY], x7 = X[v + 7 * (size_t) TY];
+#pragma unroll
+                for (int k = 0; k < VEC; k++) {
+                    part[k] += a0[k] * x0 + a1[k] * x1 + a2[k] * x2 + a3[k] * x3;
+                    part[k] += a4[k] * x4 + a5[k] * x5 + a6[k] * x6 + a7[k] * x7;
+                }
+            }
             for (; v + 3 * (size_t) TY < v1; v += 4 * (size_t) TY) {
                 real a0[VEC], a1[VEC], a2[VEC], a3[VEC];
                 vload<real, VEC>(Ab + (size_t) N * v, a0);
@@ -1301,37 +1320,52 @@ __global__ void ax_apply_kernel(QP<real> p)
 
 // N>0, pass 2 (mode 0):  G = -A^t R, P = 2X - Ga.G  (ref :432-440, :463-464); GL lanes per column.
 // mode 1 (setup): Ga0 = ||A_v||^2 and AtY = <A_v, Y>   (ref :102-110, :126-134).
+constexpr int ATR_COLS = 4;            // columns a lane group works on at a time: 4 x (N / GL) vector loads in flight per lane
 template <typename real, int VEC>
 __global__ void __launch_bounds__(256) atr_kernel(QP<real> p, int GL, int mode)
 {
     const CtlView cv = load_ctl(p.ctl);
     if (mode == 0 && cv.hold) return;
     const int N = p.N;
-    const size_t gid = ((size_t) blockIdx.x * blockDim.x + threadIdx.x) / GL;
+    const size_t grp = ((size_t) blockIdx.x * blockDim.x + threadIdx.x) / GL;
     const int gl = threadIdx.x % GL;
-    const bool live = gid < (size_t) p.Vown;
-    const size_t v = live ? gid : (size_t) p.Vown - 1;
-    const real *__restrict__ col = p.A + (size_t) N * v;
+    const size_t vb = grp * ATR_COLS, Vown = (size_t) p.Vown;
     const real *__restrict__ rhs = mode ? p.Y : p.R;
+    const real *col[ATR_COLS];
+#pragma unroll
+    for (int c = 0; c < ATR_COLS; c++) col[c] = p.A + (size_t) N * (vb + c < Vown ? vb + c : Vown - 1);
     const int nvec = (N + VEC - 1) / VEC;
-    real s0 = 0, s1 = 0;
+    real s0[ATR_COLS], s1[ATR_COLS];
+#pragma unroll
+    for (int c = 0; c < ATR_COLS; c++) { s0[c] = 0; s1[c] = 0; }
     for (int nb = gl; nb < nvec; nb += GL) {
-        real a[VEC], r[VEC];
-        vload<real, VEC>(col + (size_t) nb * VEC, a);
+        real a[ATR_COLS][VEC], r[VEC];
+#pragma unroll
+        for (int c = 0; c < ATR_COLS; c++) vload<real, VEC>(col[c] + (size_t) nb * VEC, a[c]);
         vload<real, VEC>(rhs + (size_t) nb * VEC, r);
 #pragma unroll
-        for (int k = 0; k < VEC; k++) { s0 += a[k] * r[k]; if (mode) s1 += a[k] * a[k]; }
+        for (int c = 0; c < ATR_COLS; c++)
+#pragma unroll
+            for (int k = 0; k < VEC; k++) { s0[c] += a[c][k] * r[k]; if (mode) s1[c] += a[c][k] * a[c][k]; }
     }
     for (int o = GL >> 1; o > 0; o >>= 1) {
-        s0 += __shfl_xor_sync(0xffffffffu, s0, o);
-        if (mode) s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+#pragma unroll
+        for (int c = 0; c < ATR_COLS; c++) {
+            s0[c] += __shfl_xor_sync(0xffffffffu, s0[c], o);
+            if (mode) s1[c] += __shfl_xor_sync(0xffffffffu, s1[c], o);
+        }
     }
-    if (live && gl == 0) {
-        if (mode) { p.Ga0[v] = s1; p.AtY[v] = s0; }
-        else {
-            const real g = -s0;
-            p.G[v] = g;
-            ((cv.it & 1) ? p.P1 : p.P0)[v] = (real) 2 * ((cv.it & 1) ? p.X1 : p.X0)[v] - p.Ga[v] * g;
+    if (gl == 0) {
+#pragma unroll
+        for (int c = 0; c < ATR_COLS; c++) {
+            const size_t v = vb + c;
+            if (v >= Vown) continue;
+            if (mode) { p.Ga0[v] = s1[c]; p.AtY[v] = s0[c]; }
+            else {
+                const real g = -s0[c];
+                p.G[v] = g;
+                ((cv.it & 1) ? p.P1 : p.P0)[v] = (real) 2 * ((cv.it & 1) ? p.X1 : p.X0)[v] - p.Ga[v] * g;
+            }
         }
     }
 }
@@ -1633,7 +1667,7 @@ struct QuadSolver : SolverBase {
 
     void launch_atr(int mode)
     {
-        const size_t threads = (size_t) p.Vown * GL;
+        const size_t threads = (((size_t) p.Vown + ATR_COLS - 1) / ATR_COLS) * GL;
         if (vec > 1) PFDR_LAUNCH((atr_kernel<real, (sizeof(real) == 4 ? 4 : 2)>), cdiv(threads, 256), 256, 0, p, GL, mode);
         else PFDR_LAUNCH((atr_kernel<real, 1>), cdiv(threads, 256), 256, 0, p, GL, mode);
     }
