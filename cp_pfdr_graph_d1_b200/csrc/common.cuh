@@ -11,6 +11,9 @@
 #include <vector>
 #include <cfloat>
 #include <cmath>
+#include <atomic>
+#include <mutex>
+#include <thread>
 #include "../../include/pfdr_b200.h"
 
 namespace pfdr {
@@ -185,6 +188,94 @@ inline bool is_device_ptr(const void *q)
     return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Large transfers from / to ORDINARY (pageable) host memory - what the MEX gateways and the cut-pursuit hand over.
+// cudaMemcpyAsync on pageable memory stages through one driver buffer at 10-12 GB/s; here a few host threads copy
+// chunks into / out of their own pinned blocks while the DMA engine moves the previous ones, which brings the C4 upload
+// (2.6 GB) and download (1 GB) close to the pinned rate.  Pinned and registered memory take the plain path.
+// ---------------------------------------------------------------------------------------------
+constexpr size_t STAGE_CHUNK = 4u << 20;
+constexpr int STAGE_THREADS = 4;
+
+struct StagePool {
+    std::mutex m;
+    std::vector<void *> blocks;
+    void *get()
+    {
+        { std::lock_guard<std::mutex> g(m); if (!blocks.empty()) { void *q = blocks.back(); blocks.pop_back(); return q; } }
+        void *q = nullptr;
+        return cudaMallocHost(&q, STAGE_CHUNK) == cudaSuccess ? q : nullptr;
+    }
+    void put(void *q)
+    {
+        if (!q) return;
+        std::lock_guard<std::mutex> g(m);
+        if (blocks.size() < 4 * STAGE_THREADS) blocks.push_back(q); else cudaFreeHost(q);
+    }
+};
+inline StagePool &stage_pool() { static StagePool sp; return sp; }
+
+inline size_t stage_min_bytes()
+{
+    const char *e = getenv("PFDR_B200_STAGE_MIN");           // debug switch (tests): stage transfers of at least this many bytes
+    return e ? (size_t) strtoull(e, nullptr, 10) : ((size_t) 64 << 20);
+}
+inline bool is_pageable_host(const void *q)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, q) != cudaSuccess) { cudaGetLastError(); return true; }
+    return at.type == cudaMemoryTypeUnregistered;
+}
+
+// dev <- host (to_device) or host <- dev, `bytes` bytes, enqueued on st; returns when every pinned block is free again
+// (to_device: the data is on the device or in flight behind st; from device: the data is in `host`)
+inline void staged_copy(void *dev, void *host, size_t bytes, bool to_device, cudaStream_t st)
+{
+    int device = 0;
+    PFDR_CUDA(cudaGetDevice(&device));
+    const size_t nch = (bytes + STAGE_CHUNK - 1) / STAGE_CHUNK;
+    const int T = (int) std::min<size_t>(STAGE_THREADS, nch);
+    std::atomic<int> failed{0};
+    auto work = [&](int t) {
+        if (cudaSetDevice(device) != cudaSuccess) { failed = 1; return; }
+        void *buf[2] = {stage_pool().get(), stage_pool().get()};
+        cudaEvent_t ev[2] = {nullptr, nullptr};
+        bool ok = buf[0] && buf[1] && cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming) == cudaSuccess &&
+                  cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming) == cudaSuccess;
+        size_t pend_off[2] = {0, 0}, pend_n[2] = {0, 0};
+        bool busy[2] = {false, false};
+        auto settle = [&](int k) {             // the transfer using block k is over; from device: hand its bytes to the caller
+            if (!busy[k]) return;
+            if (cudaEventSynchronize(ev[k]) != cudaSuccess) ok = false;
+            if (!to_device && ok) memcpy((char *) host + pend_off[k], buf[k], pend_n[k]);
+            busy[k] = false;
+        };
+        int k = 0;
+        for (size_t c = (size_t) t; c < nch && ok; c += (size_t) T, k ^= 1) {
+            const size_t off = c * STAGE_CHUNK, n = std::min(STAGE_CHUNK, bytes - off);
+            settle(k);
+            if (!ok) break;
+            cudaError_t rc;
+            if (to_device) {
+                memcpy(buf[k], (const char *) host + off, n);
+                rc = cudaMemcpyAsync((char *) dev + off, buf[k], n, cudaMemcpyHostToDevice, st);
+            } else {
+                rc = cudaMemcpyAsync(buf[k], (const char *) dev + off, n, cudaMemcpyDeviceToHost, st);
+            }
+            if (rc != cudaSuccess || cudaEventRecord(ev[k], st) != cudaSuccess) { ok = false; break; }
+            pend_off[k] = off; pend_n[k] = n; busy[k] = true;
+        }
+        settle(0); settle(1);
+        if (!ok) failed = 1;
+        for (int i = 0; i < 2; i++) { if (ev[i]) cudaEventDestroy(ev[i]); stage_pool().put(buf[i]); }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < T; t++) th.emplace_back(work, t);
+    work(0);
+    for (auto &x : th) x.join();
+    if (failed) { cudaGetLastError(); throw Error(PFDR_B200_ERR_CUDA, "staged host transfer failed"); }
+}
+
 // A read-only input array that lives on the device for the duration of a call: either the
 // caller's own device pointer (used in place) or an uploaded copy of the caller's host array.
 template <typename T>
@@ -195,7 +286,10 @@ struct DevIn {
         if (!src || !count) { p = nullptr; return; }
         if (is_device_ptr(src)) { order_after_caller(); p = src; return; }
         own.alloc(count);
-        PFDR_CUDA(cudaMemcpyAsync(own.p, src, count * sizeof(T), cudaMemcpyHostToDevice, ctx().stream));
+        if (count * sizeof(T) >= stage_min_bytes() && is_pageable_host(src))
+            staged_copy(own.p, const_cast<T *>(src), count * sizeof(T), true, ctx().stream);
+        else
+            PFDR_CUDA(cudaMemcpyAsync(own.p, src, count * sizeof(T), cudaMemcpyHostToDevice, ctx().stream));
         ctx().stats.h2d_bytes += (long long) (count * sizeof(T));
         p = own.p;
     }
@@ -209,7 +303,10 @@ inline void copy_out(T *dst, const T *dev_src, size_t count)
     if (is_device_ptr(dst)) {
         PFDR_CUDA(cudaMemcpyAsync(dst, dev_src, count * sizeof(T), cudaMemcpyDeviceToDevice, ctx().stream));
     } else {
-        PFDR_CUDA(cudaMemcpyAsync(dst, dev_src, count * sizeof(T), cudaMemcpyDeviceToHost, ctx().stream));
+        if (count * sizeof(T) >= stage_min_bytes() && is_pageable_host(dst))
+            staged_copy(const_cast<T *>(dev_src), dst, count * sizeof(T), false, ctx().stream);
+        else
+            PFDR_CUDA(cudaMemcpyAsync(dst, dev_src, count * sizeof(T), cudaMemcpyDeviceToHost, ctx().stream));
         ctx().stats.d2h_bytes += (long long) (count * sizeof(T));
     }
 }

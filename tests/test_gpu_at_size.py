@@ -142,3 +142,56 @@ def test_c1_cp_eeg_like_level5_own_norm(cps, monkeypatch):
     r0 = ref.quadratic_d1_l1(*args, **kw)
     assert r0["rV"] > 10
     check_cp(r0, b200.quadratic_d1_l1(*args, **kw))
+
+
+def test_c4_full_size_252_two_layouts_agree(gpu_api, monkeypatch):
+    """the configuration the headline is quoted on, at FULL size (252^3 = 16M vertices, 47.8M edges, K = 16, float32):
+    too large for the CPU checkers inside a test, so a size-independent property instead - the two independent device
+    implementations (stencil layout with its tiled sweep, 8-row patches and persistent warps; half-edge table with 32-bit
+    gathers), each checked against the oracle at small sizes, must give the same bits, and the iterate must stay on the simplex"""
+    import torch
+    if torch.cuda.get_device_properties(0).total_memory < 60e9:
+        pytest.skip("needs ~40 GB of device memory")
+    w = synth.c4_simplex(252, 16, np.float32)
+    kw = dict(rho=1.5, condMin=1e-2, difRcd=0.0, difTol=1e-9, itMax=6, want_dif=True)
+
+    def solve():
+        s = gpu_api.SimplexSolver(w["Q"], w["Q"], 0.05, w["Eu"], w["Ev"], w["La_d1"], **kw)
+        s.run()
+        layout = gpu_api.last_stats()["layout"]
+        r = s.fetch(want_dif=True)
+        s.close()
+        return r, layout
+
+    a, la = solve()
+    monkeypatch.setenv("PFDR_B200_DIA", "0")
+    b, lb = solve()
+    assert (la, lb) == (1, 0)
+    assert a.it == b.it == 6
+    assert np.array_equal(a.X, b.X)
+    assert np.allclose(a.Dif, b.Dif, rtol=1e-5)                  # evolution sums are associated differently in the two kernels
+    assert (a.X >= 0).all() and np.abs(a.X.sum(axis=1, dtype=np.float64) - 1.0).max() < 1e-5
+    assert (np.argmax(a.X, axis=1) == w["labels"]).mean() > 0.99      # and it is solving the problem: the planted labels
+
+
+@pytest.mark.parametrize("family", ["quad", "simplex"])
+def test_staged_transfers_of_pageable_arrays(gpu_api, monkeypatch, family):
+    """arrays of 64 MB and more in ordinary host memory go up and down through pinned blocks filled by a few host threads
+    (common.cuh staged_copy); PFDR_B200_STAGE_MIN lowers the threshold so that 100^3 / 64^3 problems take that path with
+    several chunks per array: same bits as the plain copies"""
+    if family == "quad":
+        w = synth.c2_denoise(100, np.float64, diag=True)
+        Ys = w["La_l2"] * w["Y"]
+        run = lambda: gpu_api.PFDR_graph_quadratic_d1_l1(np.zeros(w["V"]), Ys, w["La_l2"], w["Eu"], w["Ev"], w["La_d1"], None, 0, 1, w["La_l2"],
+                                                         rho=1.5, condMin=1e-3, difRcd=0.0, difTol=0.0, itMax=30, N=0)
+    else:
+        w = synth.c4_simplex(64, 16, np.float32)
+        run = lambda: gpu_api.PFDR_graph_loss_d1_simplex(w["Q"].copy(), w["Q"], 0.05, w["Eu"], w["Ev"], w["La_d1"], rho=1.5, condMin=1e-2,
+                                                         difRcd=0.0, difTol=0.0, itMax=20)
+    plain = run()
+    s0 = gpu_api.last_stats()
+    monkeypatch.setenv("PFDR_B200_STAGE_MIN", "65536")
+    staged = run()
+    s1 = gpu_api.last_stats()
+    assert staged.it == plain.it and np.array_equal(staged.X, plain.X)
+    assert (s1["h2d_bytes"], s1["d2h_bytes"]) == (s0["h2d_bytes"], s0["d2h_bytes"])
