@@ -118,6 +118,7 @@ void run_ranks(int world, int base_device, const std::vector<long long> &bounds,
                 gate.abort();
             }
             delete s;
+            slab_release_cache();                            // this thread ends here: its cached arena goes back now
         });
     }
     for (auto &t : threads) t.join();

@@ -1,6 +1,7 @@
 // slab.cu - host side of the peer-memory link between the ranks of a slab-sharded solve (slab.cuh)
 #include "slab.cuh"
 #include <unistd.h>
+#include <cstring>
 
 namespace pfdr {
 
@@ -49,11 +50,58 @@ void SlabLink::allreduce_sum(double *vals, int n)
     PFDR_CUDA(cudaGetLastError());
 }
 
+// Allocating, exporting, mapping and freeing a multi-GB arena costs ~150 ms per solver (cudaMalloc + cudaIpcOpenMemHandle
+// per peer + cudaFree, measured at 252^3 on 2 GPUs) - as much as the iterations of a short solve.  Callers that solve again
+// and again with the same shapes (a benchmark's end-to-end leg, a cut-pursuit re-solving on one graph) get the previous
+// arena back: one arena per host thread is kept after its solver is gone, and peers' arenas stay mapped, keyed by their
+// IPC handle.  Safe because an arena is only ever written by peers between connect() - which follows the exchange of the
+// descriptors, i.e. every rank's commit() and its clearing of the arena - and the end of run(), whose last trip waits for
+// the neighbours' last stores (simplex_slab_decide / quad_slab_decide).
+namespace {
+struct ArenaSlot {
+    void *ptr = nullptr; size_t bytes = 0; int device = -1;
+};
+struct PeerMaps {
+    struct Entry { char ipc[64]; void *ptr; long long pid; int device; };
+    std::vector<Entry> e;
+    void *find(const char *ipc) const { for (const Entry &x : e) if (!memcmp(x.ipc, ipc, 64)) return x.ptr; return nullptr; }
+    // a process keeps one arena per GPU: a new handle from the same (process, GPU) means the old arena is gone
+    void drop_stale(const char *ipc, long long pid, int device)
+    {
+        for (size_t i = 0; i < e.size();) {
+            if (e[i].pid == pid && e[i].device == device && memcmp(e[i].ipc, ipc, 64)) { cudaIpcCloseMemHandle(e[i].ptr); cudaGetLastError(); e.erase(e.begin() + i); }
+            else i++;
+        }
+    }
+    void add(const char *ipc, void *ptr, long long pid, int device)
+    {
+        if (e.size() >= 2 * SLAB_MAXW) { cudaIpcCloseMemHandle(e.front().ptr); cudaGetLastError(); e.erase(e.begin()); }   // oldest mapping goes
+        Entry x; memcpy(x.ipc, ipc, 64); x.ptr = ptr; x.pid = pid; x.device = device; e.push_back(x);
+    }
+};
+ArenaSlot &arena_slot() { static thread_local ArenaSlot s; return s; }
+PeerMaps &peer_maps() { static thread_local PeerMaps m; return m; }
+}  // namespace
+
+// gives the calling thread's cached arena and peer mappings back (a host thread that ends must call it: nothing is
+// released implicitly - no CUDA calls from thread-local destructors, which also run while a process is being torn down)
+void slab_release_cache()
+{
+    ArenaSlot &slot = arena_slot();
+    if (slot.ptr) { cudaFree(slot.ptr); slot.ptr = nullptr; slot.bytes = 0; }
+    PeerMaps &m = peer_maps();
+    for (const PeerMaps::Entry &x : m.e) cudaIpcCloseMemHandle(x.ptr);
+    m.e.clear();
+    cudaGetLastError();
+}
+
 SlabLink::~SlabLink()
 {
-    for (size_t q = 0; q < base.size(); q++)
-        if (base[q] && opened[q]) cudaIpcCloseMemHandle(base[q]);
-    if (arena) cudaFree(arena);
+    if (arena) {
+        ArenaSlot &slot = arena_slot();
+        if (slot.ptr) cudaFree(slot.ptr);
+        slot.ptr = arena; slot.bytes = arena_bytes; slot.device = mine.device;
+    }
     cudaGetLastError();
 }
 
@@ -72,14 +120,19 @@ void SlabLink::commit(int world_, int rank_, long long lo_, long long hi_, long 
     nb_lo = rank > 0 ? rank - 1 : -1;
     nb_hi = rank + 1 < world ? rank + 1 : -1;
     if (arena_bytes == 0) arena_bytes = (sizeof(SlabMail) + 255) & ~(size_t) 255;
+    PFDR_CUDA(cudaGetDevice(&mine.device));
     // peer-visible memory must come from cudaMalloc (the stream-ordered pool cannot be exported)
-    PFDR_CUDA(cudaMalloc(&arena, arena_bytes));
+    ArenaSlot &slot = arena_slot();
+    if (slot.ptr && slot.bytes == arena_bytes && slot.device == mine.device) { arena = slot.ptr; slot.ptr = nullptr; }
+    else {
+        if (slot.ptr) { cudaFree(slot.ptr); slot.ptr = nullptr; }
+        PFDR_CUDA(cudaMalloc(&arena, arena_bytes));
+    }
     PFDR_CUDA(cudaMemsetAsync(arena, 0, arena_bytes, ctx().stream));
     PFDR_CUDA(cudaStreamSynchronize(ctx().stream));
     mine.off[SLAB_MAILBOX] = 0;
     mine.base = (unsigned long long) (uintptr_t) arena;
     mine.pid = (long long) getpid();
-    PFDR_CUDA(cudaGetDevice(&mine.device));
     mine.rank = rank; mine.lo = lo; mine.hi = hi; mine.v0 = v0; mine.v1 = v1; mine.width = width; mine.bytes = arena_bytes;
     if (world > 1) {
         cudaIpcMemHandle_t h;
@@ -114,10 +167,15 @@ void SlabLink::connect(const SlabBlob *all, bool same_process)
             }
             base[q] = (void *) (uintptr_t) blobs[q].base;
         } else {
-            cudaIpcMemHandle_t h;
-            memcpy(&h, blobs[q].ipc, 64);
-            void *p = nullptr;
-            PFDR_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+            const char *ipc = (const char *) blobs[q].ipc;
+            peer_maps().drop_stale(ipc, blobs[q].pid, blobs[q].device);
+            void *p = peer_maps().find(ipc);                     // still mapped from an earlier solver of this thread
+            if (!p) {
+                cudaIpcMemHandle_t h;
+                memcpy(&h, ipc, 64);
+                PFDR_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+                peer_maps().add(ipc, p, blobs[q].pid, blobs[q].device);
+            }
             base[q] = p; opened[q] = true;
         }
     }

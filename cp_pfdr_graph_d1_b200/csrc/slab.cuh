@@ -149,7 +149,7 @@ struct SlabLink {
     SlabBlob mine{};
     std::vector<SlabBlob> blobs;                    // every rank's, after connect()
     std::vector<void *> base;                       // every rank's arena as mapped here (NULL: not mapped)
-    std::vector<bool> opened;                       // mapped through cudaIpcOpenMemHandle (to be closed)
+    std::vector<bool> opened;                       // mapped through cudaIpcOpenMemHandle (kept in the thread's mapping cache, slab.cu)
     unsigned long long bar_epoch = 0, red_epoch = 0, run_id = 0;
     bool connected = false;
 
@@ -171,5 +171,7 @@ struct SlabLink {
     // copies `count` elements starting at local element `from` of array `which` into the same global position of rank r's copy
     template <typename T> void push(int which, int r, size_t from_elem, size_t count, long long shift_elems);
 };
+
+void slab_release_cache();                          // the calling thread's cached arena / peer mappings (slab.cu)
 
 }  // namespace pfdr
