@@ -10,7 +10,8 @@ followed by solver.run().  `value` = E * iters * steps / time with every input a
 `e2e` = the same metric through the one-shot C-ABI call with HOST buffers (upload, layout, preconditioning,
 iterations, download of the iterate all inside the timed region): pinned buffers (the headline) and pageable ones
 (what the MEX / cut-pursuit callers hand over).  `extra` = short resident runs of the other BASELINE configs,
-`cp_solve` = BASELINE's second figure (cut-pursuit wall time, reference CP code on libpfdr_b200 vs all-reference).
+`cp_solve` = BASELINE's second figure (cut-pursuit wall time, reference CP code on libpfdr_b200 vs all-reference),
+`cp_outer` = the dense and graph passes of one cut-pursuit outer iteration on the device.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c4_f32|c4_f64|c2_f32|c2_f64|...] [--impl reference]
 """
