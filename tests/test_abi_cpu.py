@@ -94,3 +94,58 @@ def test_libcp_fails_loudly_without_its_library(monkeypatch, tmp_path):
     monkeypatch.setattr(libCP, "_lib", None)
     with pytest.raises(ImportError):
         libCP.CP_quadratic_l1(np.zeros(3), np.array([0, 1]), np.array([1, 2]), 0.1, 1.0, 0.0)
+
+
+_STUB_C = r"""
+#include <string.h>
+double seen[16];
+#define STUB(SUF, real)                                                                                         \
+int cp_b200_quadratic_d1_l1_##SUF(int V, int E, int N, const real *Y, const real *A, const int *Eu,             \
+    const int *Ev, const real *La_d1, const real *La_l1, int positivity, real CP_difTol, int CP_itMax,          \
+    real PFDR_rho, real PFDR_condMin, real PFDR_difRcd, real PFDR_difTol, int PFDR_itMax, int verbose,          \
+    int *Cv, real *rX, int *CP_it)                                                                              \
+{                                                                                                               \
+    double s[16] = {V, E, N, Y[V > 1 ? 1 : 0], A ? A[1] : -1.0, Eu[E - 1], Ev[E - 1], La_d1[E - 1], La_l1[V - 1], \
+                    positivity, CP_difTol, CP_itMax, PFDR_rho, PFDR_difTol, PFDR_itMax, sizeof(real)};          \
+    memcpy(seen, s, sizeof(s));                                                                                 \
+    for (int v = 0; v < V; v++) Cv[v] = v & 1;                                                                  \
+    rX[0] = (real) 1.5; rX[1] = (real) 2.5; *CP_it = 3;                                                         \
+    return 2;                                                                                                   \
+}
+STUB(f32, float)
+STUB(f64, double)
+"""
+
+
+def test_libcp_argument_handling_against_a_stub_gateway(monkeypatch, tmp_path):
+    """the host logic of libCP.CP_quadratic_l1 (A modes, scalar overloads, integer edge types, element type) checked on the
+    arguments a stub of csrc/cp_gateway.cpp receives - what the Boost module derives at python/CP_quadratic_l1_py.cpp:115-170"""
+    import subprocess
+    from cp_pfdr_graph_d1_b200 import libCP
+    src, so = tmp_path / "stub.c", tmp_path / "libstub.so"
+    src.write_text(_STUB_C)
+    subprocess.check_call(["gcc", "-shared", "-fPIC", "-O1", "-o", str(so), str(src)])
+    monkeypatch.setenv("PFDR_B200_CP_LIB", str(so))
+    monkeypatch.setattr(libCP, "_lib", None)
+    seen = lambda: np.array((C.c_double * 16).in_dll(libCP._load(), "seen"))
+    Eu, Ev = np.array([0, 1, 2], np.uint32), np.array([1, 2, 3], np.int64)
+    # matrix mode, float64, array weights
+    obs = np.arange(3.0); A = np.arange(12.0).reshape(3, 4)
+    Cv, rX = libCP.CP_quadratic_l1(obs, Eu, Ev, np.array([.1, .2, .3]), A, np.array([1., 2., 3., 4.]), positivity=1, PFDR_rho=1.5)
+    assert Cv.tolist() == [0, 1, 0, 1] and rX.tolist() == [1.5, 2.5] and rX.dtype == np.float64
+    s = seen()
+    assert s[:3].tolist() == [4, 3, 3]                 # V = columns of A, E, N = len(obs)
+    assert s[3] == 1.0 and s[4] == A[1, 0]              # A handed over column major: element 1 is A[1, 0]
+    assert s[5:10].tolist() == [2, 3, .3, 4., 1] and s[12] == 1.5 and s[15] == 8
+    assert s[10:12].tolist() == [1e-3, 10] and s[13:15].tolist() == [1e-4, 10000]        # the Boost module's defaults
+    # diagonal mode, float32, scalar weights: V = N, N -> 0, observation and operator pre-multiplied
+    obs = np.array([1., 2., 3., 4.], np.float32); a = np.array([2., 3., 4., 5.], np.float32)
+    Cv, rX = libCP.CP_quadratic_l1(obs, Eu, Ev, 0.25, a, 0.5)
+    s = seen()
+    assert rX.dtype == np.float32 and s[:3].tolist() == [4, 3, 0] and s[15] == 4
+    assert s[3] == 2. * 3. and s[4] == 3. * 3. and s[7] == 0.25 and s[8] == 0.5 and s[9] == 0
+    # identity mode: A a scalar
+    libCP.CP_quadratic_l1(obs, Eu, Ev, 0.25, 1.0, np.float32(0.5))
+    s = seen()
+    assert s[:3].tolist() == [4, 3, 0] and s[3] == 2. and s[4] == -1.0
+    monkeypatch.setattr(libCP, "_lib", None)
