@@ -66,6 +66,21 @@ def main():
     np.savez_compressed(os.path.join(HERE, "reference_outputs.npz"), **out)
     print("wrote", len(out), "arrays,", os.path.getsize(os.path.join(HERE, "reference_outputs.npz")), "bytes")
 
+    # cut-pursuit blocks: what the reference's cut-pursuit returns on the seeded problems of
+    # tests/test_oracle_vs_ref.py - components and reduced values after one outer iteration, components after four
+    import test_oracle_vs_ref as T
+    cp = O.cp_reference()
+    cpo = {}
+    for mode in ("direct", "ata", "diag"):
+        r = T.cp_chain_reference(cp, mode)
+        cpo[f"chain/{mode}/Cv"], cpo[f"chain/{mode}/rX"] = r["Cv"].astype(np.int32), r["rX"]
+        cpo[f"chain/{mode}/sha"] = np.array(digest([a for a in T.cp_chain_problem(mode) if isinstance(a, np.ndarray)]))
+    for kind in ("eeg", "grid", "knn"):
+        r = T.cp_numbering_reference(cp, kind)
+        cpo[f"numbering/{kind}/Cv"] = r["Cv"].astype(np.int32)
+    np.savez_compressed(os.path.join(HERE, "reference_cp_outputs.npz"), **cpo)
+    print("wrote", len(cpo), "arrays,", os.path.getsize(os.path.join(HERE, "reference_cp_outputs.npz")), "bytes")
+
 
 if __name__ == "__main__":
     main()

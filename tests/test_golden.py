@@ -84,3 +84,37 @@ def test_gpu_proj_golden(gpu_api, dtype):
     got = gpu_api.proj_simplex_metric(X.copy(), M, A)
     assert np.allclose(got, GOLD[f"proj/{np.dtype(dtype).name}/X"], rtol=1e-4 if dtype is np.float32 else 1e-11,
                        atol=1e-6 if dtype is np.float32 else 1e-14)
+
+
+# ---- cut-pursuit blocks: the pins of tests/test_oracle_vs_ref.py on stored outputs of the reference's
+# cut-pursuit, so that they also hold where oracle/_ref cannot be built ------------------------------------------------
+GOLD_CP = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_cp_outputs.npz"))
+
+
+@pytest.mark.parametrize("mode,preAt", [("direct", True), ("direct", False), ("ata", None), ("diag", None)])
+def test_oracle_cp_reduce_chain_golden(oracle, mode, preAt):
+    import test_oracle_vs_ref as T
+    assert G.digest([a for a in T.cp_chain_problem(mode) if isinstance(a, np.ndarray)]) == str(GOLD_CP[f"chain/{mode}/sha"]), \
+        "seeded inputs drifted: regenerate the fixtures"
+    Cv, rX = GOLD_CP[f"chain/{mode}/Cv"], GOLD_CP[f"chain/{mode}/rX"]
+    X = T.cp_chain_oracle(mode, Cv, rX.shape[0], preAt)
+    assert rel(X, rX) < 1e-6
+
+
+@pytest.mark.parametrize("kind", ["eeg", "grid", "knn"])
+def test_oracle_cp_components_numbering_golden(kind):
+    import test_oracle_vs_ref as T
+    Cv = GOLD_CP[f"numbering/{kind}/Cv"]
+    T.check_cp_numbering(kind, Cv, int(Cv.max()) + 1)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["eeg", "grid", "knn"])
+def test_gpu_cp_components_numbering_golden(gpu_api, kind):
+    """the device sweep reproduces the reference's own component numbering from its cut"""
+    import test_oracle_vs_ref as T
+    w = T.cp_numbering_graph(kind)
+    Cv = GOLD_CP[f"numbering/{kind}/Cv"]
+    active = (Cv[w["Eu"]] != Cv[w["Ev"]]).astype(np.uint8)
+    got, rV = gpu_api.cp_components(w["V"], w["Eu"], w["Ev"], active)
+    assert rV == int(Cv.max()) + 1 and np.array_equal(got, Cv)

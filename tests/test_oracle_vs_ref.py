@@ -187,36 +187,43 @@ def test_gpu_schedule_model(oracle, dtype, variant):
 # values rX = argmin of the reduced problem; the restated blocks (oracle/cp_reduce_oracle_impl.h) must rebuild a reduced
 # problem with the same minimiser from the same Cv.
 # ---------------------------------------------------------------------------------------------------------------------
-def _cp_chain(reference_cp, mode, preAt_wanted=None):
-    from oracle import oracle as O
-    from cp_pfdr_graph_d1_b200 import synth
+CP_CHAIN_KW = dict(CP_difTol=0.0, CP_itMax=1, rho=1.5, condMin=1e-3, difRcd=0.0, difTol=1e-10, itMax=200000)
+
+
+def cp_chain_problem(mode):
+    """seeded inputs of the three operator modes: (V, N, A, Y, Eu, Ev, La_d1, La_l1, positivity)"""
     dt = np.float64
     if mode == "diag":
         w = synth.c2_denoise(9, dt, diag=True)
-        V, N, A, Y = w["V"], 0, w["La_l2"], (w["La_l2"] * w["Y"]).astype(dt)
-        Eu, Ev, La_d1, La_l1, pos = w["Eu"], w["Ev"], w["La_d1"], None, 0
-    else:
-        w = synth.eeg_like(2, 24, dt)
-        V, Eu, Ev, La_d1, La_l1, pos = w["V"], w["Eu"], w["Ev"], w["La_d1"], w["La_l1"], 1
-        if mode == "direct":
-            N, A, Y = w["N"], w["A"], w["Y"]
-        else:
-            N, A, Y = -V, np.asfortranarray(w["A"].T @ w["A"]), w["A"].T @ w["Y"]
-    kw = dict(CP_difTol=0.0, CP_itMax=1, rho=1.5, condMin=1e-3, difRcd=0.0, difTol=1e-10, itMax=200000)
+        return w["V"], 0, w["La_l2"], (w["La_l2"] * w["Y"]).astype(dt), w["Eu"], w["Ev"], w["La_d1"], None, 0
+    w = synth.eeg_like(2, 24, dt)
+    V = w["V"]
+    if mode == "direct":
+        return V, w["N"], w["A"], w["Y"], w["Eu"], w["Ev"], w["La_d1"], w["La_l1"], 1
+    # the l1 cut-pursuit of the reference cannot run with N < 0 (src/CP_PFDR_graph_quadratic_d1_l1.cpp:81 derives a thread
+    # count from N and hands libgomp a negative one); its bounds twin (same blocks, src/CP_PFDR_graph_quadratic_d1_bounds.cpp:
+    # 640-750) can: x >= 0 as the box [0, inf), no l1 term
+    return V, -V, np.asfortranarray(w["A"].T @ w["A"]), w["A"].T @ w["Y"], w["Eu"], w["Ev"], w["La_d1"], None, 1
+
+
+def cp_chain_reference(reference_cp, mode):
+    """the reference's own cut-pursuit stopped after one outer iteration -> dict(rV, Cv, rX)"""
+    V, N, A, Y, Eu, Ev, La_d1, La_l1, pos = cp_chain_problem(mode)
     if mode == "ata":
-        # the l1 cut-pursuit of the reference cannot run with N < 0 (src/CP_PFDR_graph_quadratic_d1_l1.cpp:81 derives a thread
-        # count from N and hands libgomp a negative one); its bounds twin (same blocks, src/CP_PFDR_graph_quadratic_d1_bounds.cpp:
-        # 640-750) can: x >= 0 as the box [0, inf), no l1 term
-        La_l1 = None
-        r = reference_cp.quadratic_d1_bounds(Y, A, Eu, Ev, La_d1, 0.0, np.inf, N, **kw)
-    else:
-        r = reference_cp.quadratic_d1_l1(Y, A, Eu, Ev, La_d1, La_l1, pos, N, **kw)
-    rV, Cv = r["rV"], r["Cv"]
+        return reference_cp.quadratic_d1_bounds(Y, A, Eu, Ev, La_d1, 0.0, np.inf, N, **CP_CHAIN_KW)
+    return reference_cp.quadratic_d1_l1(Y, A, Eu, Ev, La_d1, La_l1, pos, N, **CP_CHAIN_KW)
+
+
+def cp_chain_oracle(mode, Cv, rV, preAt_wanted=None):
+    """reduced problem rebuilt from the components by the restated blocks, solved by the oracle PFDR -> reduced values"""
+    from oracle import oracle as O
+    dt = np.float64
+    V, N, A, Y, Eu, Ev, La_d1, La_l1, pos = cp_chain_problem(mode)
     assert 1 < rV < V
     red = O.CpReduceOracle()
     Vc, rVc = O.component_lists(Cv, rV)
     # the rule of :671 with PFDR_it = PFDR_itMax on the first outer iteration
-    preAt = (N <= 0) or (rV < (2 * N * kw["itMax"]) // (N + kw["itMax"]))
+    preAt = (N <= 0) or (rV < (2 * N * CP_CHAIN_KW["itMax"]) // (N + CP_CHAIN_KW["itMax"]))
     if preAt_wanted is not None:
         preAt = preAt_wanted                     # either form of the reduced problem has the same minimiser
     rA, rAA, rY = red.reduce(V, N, A, Y, Vc, rVc, preAt)
@@ -237,17 +244,21 @@ def _cp_chain(reference_cp, mode, preAt_wanted=None):
         S, d = red.equilibrate(N, rA, False)
         c = np.linalg.norm(S, 2) ** 2
         out = orc.PFDR_graph_quadratic_d1_l1(X, Y, rA, rEu, rEv, rLa, rl1, pos, 1, (d * d * c).astype(dt), N=N, **common)
-    return r, out, (rA, rAA, rY, Vc, rVc, A, Y, N, V)
+    return out.X
 
 
-@pytest.mark.parametrize("mode,preAt", [("direct", True), ("direct", False), ("ata", None), ("diag", None)])
+CP_CHAIN_CASES = [("direct", True), ("direct", False), ("ata", None), ("diag", None)]
+
+
+@pytest.mark.parametrize("mode,preAt", CP_CHAIN_CASES)
 def test_cp_reduce_chain(reference, mode, preAt):
     from oracle import oracle as O
     cp = O.cp_reference()
     if cp is None:
         pytest.skip("oracle/_ref/libref.so not built")
-    r, out, _ = _cp_chain(cp, mode, preAt)
-    assert rel(out.X, r["rX"]) < 1e-6, (mode, rel(out.X, r["rX"]))
+    r = cp_chain_reference(cp, mode)
+    X = cp_chain_oracle(mode, r["Cv"], r["rV"], preAt)
+    assert rel(X, r["rX"]) < 1e-6, (mode, rel(X, r["rX"]))
 
 
 def test_cp_reduce_identities():
@@ -286,30 +297,42 @@ def test_cp_reduce_identities():
 # the component numbering of the restated sweep against the reference's own (:570-600) - every cut-pursuit
 # run returns Cv; cutting exactly the edges whose ends lie in different components of that Cv and sweeping again must give
 # the same numbering back (components of the reference are connected through their non-cut edges by construction).
-@pytest.mark.parametrize("kind", ["eeg", "grid", "knn"])
-def test_cp_components_numbering(reference, kind):
-    from oracle import oracle as O
-    cp = O.cp_reference()
-    if cp is None:
-        pytest.skip("oracle/_ref/libref.so not built")
+CP_NUMBERING_KW = dict(CP_difTol=1e-4, CP_itMax=4, rho=1.5, condMin=1e-3, difRcd=0.0, difTol=1e-6, itMax=2000)
+
+
+def cp_numbering_graph(kind):
     dt = np.float64
-    kw = dict(CP_difTol=1e-4, CP_itMax=4, rho=1.5, condMin=1e-3, difRcd=0.0, difTol=1e-6, itMax=2000)
+    return synth.eeg_like(3, 30, dt) if kind == "eeg" else (synth.c2_denoise(12, dt, diag=True) if kind == "grid" else synth.c3_bounds_ata(400, 8, 128, dt))
+
+
+def cp_numbering_reference(cp, kind):
+    w, kw, dt = cp_numbering_graph(kind), CP_NUMBERING_KW, np.float64
     if kind == "eeg":
-        w = synth.eeg_like(3, 30, dt)
-        r = cp.quadratic_d1_l1(w["Y"], w["A"], w["Eu"], w["Ev"], w["La_d1"], w["La_l1"], 1, w["N"], **kw)
-    elif kind == "grid":
-        w = synth.c2_denoise(12, dt, diag=True)
-        r = cp.quadratic_d1_l1((w["La_l2"] * w["Y"]).astype(dt), w["La_l2"], w["Eu"], w["Ev"], w["La_d1"], None, 0, 0, **kw)
-    else:
-        w = synth.c3_bounds_ata(400, 8, 128, dt)
-        r = cp.quadratic_d1_bounds(w["AtY"], w["AtA"], w["Eu"], w["Ev"], w["La_d1"], 0.0, 1.0, -w["V"], **kw)
-    Cv, rV = r["Cv"], r["rV"]
+        return cp.quadratic_d1_l1(w["Y"], w["A"], w["Eu"], w["Ev"], w["La_d1"], w["La_l1"], 1, w["N"], **kw)
+    if kind == "grid":
+        return cp.quadratic_d1_l1((w["La_l2"] * w["Y"]).astype(dt), w["La_l2"], w["Eu"], w["Ev"], w["La_d1"], None, 0, 0, **kw)
+    return cp.quadratic_d1_bounds(w["AtY"], w["AtA"], w["Eu"], w["Ev"], w["La_d1"], 0.0, 1.0, -w["V"], **kw)
+
+
+def check_cp_numbering(kind, Cv, rV):
+    from oracle import oracle as O
+    w = cp_numbering_graph(kind)
     assert rV > 1
     active = (Cv[w["Eu"]] != Cv[w["Ev"]]).astype(np.uint8)
     oCv, orV, Vc, rVc = O.CpGraphOracle().components(w["V"], w["Eu"], w["Ev"], active)
     assert orV == rV and np.array_equal(oCv, Cv)
     assert np.array_equal(np.sort(Vc), np.arange(w["V"])) and np.array_equal(np.diff(rVc), np.bincount(Cv, minlength=rV))
     assert all(np.all(Cv[Vc[rVc[c]:rVc[c + 1]]] == c) for c in range(rV))
+
+
+@pytest.mark.parametrize("kind", ["eeg", "grid", "knn"])
+def test_cp_components_numbering(reference, kind):
+    from oracle import oracle as O
+    cp = O.cp_reference()
+    if cp is None:
+        pytest.skip("oracle/_ref/libref.so not built")
+    r = cp_numbering_reference(cp, kind)
+    check_cp_numbering(kind, r["Cv"], r["rV"])
 
 
 def test_cp_reduced_edges_and_merge_rules():
