@@ -4,9 +4,9 @@
  * The reference does not expose these steps as functions: they are inline blocks of
  * CP_PFDR_graph_quadratic_d1_l1() (src/CP_PFDR_graph_quadratic_d1_l1.cpp).  Each function below restates one block,
  * with the block's own accumulation type (REAL) and member order (the component list Vc / rVc).  The restatement is
- * pinned through the only observable the reference offers - the reduced values its cut-pursuit returns after ONE outer
- * iteration (tests/test_oracle_vs_ref.py::test_cp_reduce_chain_*): reference Cv -> these functions -> oracle PFDR ->
- * the reference's rX.
+ * pinned through the only observable the reference offers - the components and reduced values its cut-pursuit returns
+ * (stopped after a few outer iterations; tests/test_oracle_vs_ref.py::test_cp_reduce_chain, tests/test_golden.py):
+ * reference Cv -> these functions -> oracle PFDR -> the reference's rX.
  *
  * Components: rV of them; Vc[rVc[c] .. rVc[c+1]) lists the vertices of component c (reference :574-600). */
 

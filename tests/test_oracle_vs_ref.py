@@ -183,11 +183,11 @@ def test_gpu_schedule_model(oracle, dtype, variant):
 
 # ---------------------------------------------------------------------------------------------------------------------
 # the reduced-problem construction has no entry point in the reference (inline blocks of the cut-pursuit).
-# Pin: the reference's own cut-pursuit, stopped after ONE outer iteration, returns the components Cv and the reduced
-# values rX = argmin of the reduced problem; the restated blocks (oracle/cp_reduce_oracle_impl.h) must rebuild a reduced
+# Pin: the reference's own cut-pursuit, stopped after a few outer iterations, returns the components Cv and the reduced
+# values rX = argmin of the last reduced problem; the restated blocks (oracle/cp_reduce_oracle_impl.h) must rebuild a reduced
 # problem with the same minimiser from the same Cv.
 # ---------------------------------------------------------------------------------------------------------------------
-CP_CHAIN_KW = dict(CP_difTol=0.0, CP_itMax=1, rho=1.5, condMin=1e-3, difRcd=0.0, difTol=1e-10, itMax=200000)
+CP_CHAIN_KW = dict(CP_difTol=0.0, CP_itMax=6, rho=1.5, condMin=1e-3, difRcd=0.0, difTol=1e-10, itMax=200000)
 
 
 def cp_chain_problem(mode):
@@ -207,7 +207,7 @@ def cp_chain_problem(mode):
 
 
 def cp_chain_reference(reference_cp, mode):
-    """the reference's own cut-pursuit stopped after one outer iteration -> dict(rV, Cv, rX)"""
+    """the reference's own cut-pursuit stopped after CP_itMax outer iterations -> dict(rV, Cv, rX) of the last reduced problem"""
     V, N, A, Y, Eu, Ev, La_d1, La_l1, pos = cp_chain_problem(mode)
     if mode == "ata":
         return reference_cp.quadratic_d1_bounds(Y, A, Eu, Ev, La_d1, 0.0, np.inf, N, **CP_CHAIN_KW)
@@ -222,7 +222,7 @@ def cp_chain_oracle(mode, Cv, rV, preAt_wanted=None):
     assert 1 < rV < V
     red = O.CpReduceOracle()
     Vc, rVc = O.component_lists(Cv, rV)
-    # the rule of :671 with PFDR_it = PFDR_itMax on the first outer iteration
+    # the rule of :671 (PFDR_it = iterations of the previous reduced solve; PFDR_itMax on the first outer iteration)
     preAt = (N <= 0) or (rV < (2 * N * CP_CHAIN_KW["itMax"]) // (N + CP_CHAIN_KW["itMax"]))
     if preAt_wanted is not None:
         preAt = preAt_wanted                     # either form of the reduced problem has the same minimiser
