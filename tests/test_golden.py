@@ -118,3 +118,37 @@ def test_gpu_cp_components_numbering_golden(gpu_api, kind):
     active = (Cv[w["Eu"]] != Cv[w["Ev"]]).astype(np.uint8)
     got, rV = gpu_api.cp_components(w["V"], w["Eu"], w["Ev"], active)
     assert rV == int(Cv.max()) + 1 and np.array_equal(got, Cv)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["direct", "ata", "diag"])
+def test_gpu_cp_reduce_on_the_reference_components_golden(gpu_api, mode):
+    """the device passes on the components the reference's cut-pursuit actually produced (stored fixtures): reduced operator
+    against the restated blocks, and - closing the chain on the device - the library's own PFDR on the device-built reduced
+    problem reproduces the reference's reduced values"""
+    import test_oracle_vs_ref as T
+    from oracle import oracle as O
+    V, N, A, Y, Eu, Ev, La_d1, La_l1, pos = T.cp_chain_problem(mode)
+    Cv, rX = GOLD_CP[f"chain/{mode}/Cv"], GOLD_CP[f"chain/{mode}/rX"]
+    rV = rX.shape[0]
+    Vc, rVc = O.component_lists(Cv, rV)
+    op = gpu_api.CpOperator(A, V, N)
+    op.set_components(Cv, rV)
+    rA, rAA, rY = op.reduce(Y, True)
+    oA, oAA, oY = O.CpReduceOracle().reduce(V, N, A, Y, Vc, rVc, True)
+    assert rel(rAA, oAA) < 1e-10 and rel(rY, oY) < 1e-10 and (N <= 0 or rel(rA, oA) < 1e-10)
+    active = (Cv[Eu] != Cv[Ev]).astype(np.uint8)
+    rEu, rEv, rLa = gpu_api.cp_reduced_edges(V, Eu, Ev, active, La_d1, Cv, rV)
+    rl1 = None if La_l1 is None else np.bincount(Cv, weights=La_l1, minlength=rV)
+    kw = dict(rho=1.5, condMin=1e-3, difRcd=0.0, difTol=1e-10, itMax=200000)
+    if N == 0:
+        x = gpu_api.PFDR_graph_quadratic_d1_l1(np.zeros(rV), rY, rAA, rEu, rEv, rLa, rl1, pos, 1, rAA, N=0, **kw).X
+    else:
+        d = np.sqrt(np.diag(rAA))
+        L = d * d * np.linalg.eigvalsh(rAA / np.outer(d, d)).max()
+        if mode == "ata":
+            x = gpu_api.PFDR_graph_quadratic_d1_bounds(np.zeros(rV), rY, rAA, rEu, rEv, rLa, 0.0, np.inf, 1, L, N=-rV, **kw).X
+        else:
+            x = gpu_api.PFDR_graph_quadratic_d1_l1(np.zeros(rV), rY, rAA, rEu, rEv, rLa, rl1, pos, 1, L, N=-rV, **kw).X
+    assert rel(x, rX) < 1e-6
+    op.close()
